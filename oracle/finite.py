@@ -1,0 +1,383 @@
+"""Finite-MPS sweep algorithms of the reference restated on charged dense tensors.
+
+State layout: ``A[l, p, r]`` dense arrays plus one integer charge per basis index of every bond
+(``Space.index_charges``) and per physical state.  Symmetric tensors are exactly zero outside the
+charge-conserving entries, so dense einsum reproduces what TensorKit computes block-wise.
+
+Restates: FiniteMPS random construction + gauge (src/states/finitemps.jl:143-197,
+src/states/orthoview.jl:49-143), FinEnv (src/environments/FinEnv.jl:41-70,114-145), DMRG and
+DMRG2 sweeps (src/algorithms/groundstate/dmrg.jl:22-55,80-137), calc_galerkin
+(src/algorithms/toolbox.jl:17-22), expectation_value (src/algorithms/expval.jl:92-109),
+entanglement_spectrum (toolbox.jl:65-69), TDVP/TDVP2 (src/algorithms/timestep/tdvp.jl:61-151).
+"""
+from __future__ import annotations
+import numpy as np
+from .spaces import Space, fuse, infimum, dual
+from .blocks import mask3
+from .contract import (transfer_left_sparse, transfer_right_sparse, dAC_sparse, dAC2_sparse, dC_dense)
+from .krylov import eigsolve_lanczos, exponentiate_lanczos
+from .linalg import tsvd, qrpos, lqpos
+from .mpo import MPOHamiltonian
+
+
+def virtual_spaces(pspace: Space, L: int, maxV, left: Space = None, right: Space = None):
+    """finitemps.jl:183-192: full-rank-limited bond spaces. maxV: Space or list of L-1 Spaces."""
+    left = left or Space((0,), (1,), pspace.modulus)
+    right = right or Space((0,), (1,), pspace.modulus)
+    maxVs = list(maxV) if isinstance(maxV, (list, tuple)) else [maxV] * (L - 1)
+    V = [None] * (L + 1)
+    V[0] = left
+    for k in range(1, L):
+        V[k] = infimum(fuse(V[k - 1], pspace), maxVs[k - 1])
+    V[L] = right
+    for k in range(L - 1, 0, -1):
+        V[k] = infimum(V[k], fuse(V[k + 1], dual(pspace)))
+    return V
+
+
+def gaussian_bond_space(D, parity, sigma=1.5, qmax=5, modulus=0):
+    """SURVEY.md 8d config 3 recipe: n_q = round(D g(q)/sum g), g = exp(-q^2/2 sigma^2), |q| <= qmax,
+    fix-up on the q ~ 0 sector so that sum n_q = D.  Charges are 2q; ``parity`` selects integer (0)
+    or half-integer (1) q."""
+    cs = [c for c in range(-2 * qmax, 2 * qmax + 1) if (c % 2) == parity]
+    g = np.array([np.exp(-(c / 2) ** 2 / (2 * sigma ** 2)) for c in cs])
+    n = np.rint(D * g / g.sum()).astype(int)
+    i0 = int(np.argmin(np.abs(np.array(cs))))
+    n[i0] += D - n.sum()
+    return Space.from_dict({c: int(k) for c, k in zip(cs, n) if k > 0}, modulus)
+
+
+class FiniteMPS:
+    """gauge bookkeeping of finitemps.jl / orthoview.jl on dense charged tensors (0-based sites)."""
+
+    def __init__(self, As, Vs, pspace: Space, normalize=True):
+        # finitemps.jl:143-170: left-canonicalise with QRpos, keep last C
+        self.L = len(As)
+        self.p = pspace
+        self.pq = pspace.index_charges()
+        self.V = list(Vs)
+        self.AL = [None] * self.L
+        self.AR = [None] * self.L
+        self.AC = [None] * self.L
+        self.CL = [None] * (self.L + 1)   # CL[i] sits to the left of site i; CR[i] = CL[i+1]
+        As = [np.array(a) for a in As]
+        for i in range(self.L):
+            Q, R, newV = self._leftorth(As[i], self.V[i], self.V[i + 1])
+            As[i] = Q
+            if normalize:
+                R = R / np.linalg.norm(R)
+            self.V[i + 1] = newV if i < self.L - 1 else self.V[i + 1]
+            if i < self.L - 1:
+                As[i + 1] = np.einsum('ab,bpc->apc', R, As[i + 1])
+        self.AL = As
+        self.CL[self.L] = R
+
+    @staticmethod
+    def random(rng, pspace, L, maxV, dtype=np.complex128, left=None, right=None):
+        V = virtual_spaces(pspace, L, maxV, left, right)
+        As = []
+        for i in range(L):
+            m = mask3(V[i], pspace.index_charges(), V[i + 1])
+            a = rng.standard_normal(m.shape)
+            if np.dtype(dtype).kind == "c":
+                a = a + 1j * rng.standard_normal(m.shape)
+            As.append((a * m).astype(dtype))
+        return FiniteMPS(As, V, pspace)
+
+    # --- per-sector factorizations on (l p; r) / (l; p r) groupings
+    def _rowq(self, Vl):
+        return (Vl.index_charges()[:, None] + self.pq[None, :]).reshape(-1)
+
+    def _leftorth(self, A, Vl, Vr):
+        Dl, d, Dr = A.shape
+        Q, R, newV = qrpos(A.reshape(Dl * d, Dr), self._rowq(Vl), Vr.index_charges(), self.p.modulus)
+        return Q.reshape(Dl, d, newV.dim), R, newV
+
+    def _rightorth(self, A, Vl, Vr):
+        Dl, d, Dr = A.shape
+        colq = (Vr.index_charges()[None, :] - self.pq[:, None]).reshape(-1)  # (p, r) order
+        Lm, Q, newV = lqpos(A.reshape(Dl, d * Dr), Vl.index_charges(), colq, self.p.modulus)
+        return Lm, Q.reshape(newV.dim, d, Dr), newV
+
+    # --- orthoview.jl getters (lazy gauge)
+    def get_CR(self, i):
+        """CR[i] = bond matrix right of site i (i = -1 .. L-1); orthoview.jl:49-60"""
+        if self.CL[i + 1] is None:
+            if i == -1 or self.AL[i] is not None:
+                Lm, Q, _ = self._rightorth(self.get_AC(i + 1), self.V[i + 1], self.V[i + 2])
+                self.CL[i + 1] = Lm
+                self.AR[i + 1] = Q
+            else:
+                Q, R, _ = self._leftorth(self.get_AC(i), self.V[i], self.V[i + 1])
+                self.AL[i] = Q
+                self.CL[i + 1] = R
+        return self.CL[i + 1]
+
+    def get_AC(self, i):
+        """orthoview.jl:95-106"""
+        if self.AC[i] is None and self.AR[i] is not None:
+            self.AC[i] = np.einsum('ab,bpc->apc', self.get_CR(i - 1), self.AR[i])
+        elif self.AC[i] is None and self.AL[i] is not None:
+            self.AC[i] = np.einsum('apb,bc->apc', self.AL[i], self.get_CR(i))
+        return self.AC[i]
+
+    def get_AL(self, i):
+        if self.AL[i] is None:
+            self.get_AL(i - 1) if i > 0 and self.AL[i - 1] is None else None
+            self.get_CR(i)  # triggers leftorth of AC[i] when AL[i] is missing and AL[i-1] present
+            if self.AL[i] is None:
+                Q, R, _ = self._leftorth(self.get_AC(i), self.V[i], self.V[i + 1])
+                self.AL[i], self.CL[i + 1] = Q, R
+        return self.AL[i]
+
+    def get_AR(self, i):
+        if self.AR[i] is None:
+            if i < self.L - 1 and self.AR[i + 1] is None:
+                self.get_AR(i + 1)
+            Lm, Q, _ = self._rightorth(self.get_AC(i), self.V[i], self.V[i + 1])
+            self.CL[i], self.AR[i] = Lm, Q
+        return self.AR[i]
+
+    # --- orthoview.jl:108-143 setters
+    def _invalidate(self, i):
+        self.AC = [None] * self.L
+        self.CL = [None] * (self.L + 1)
+        for k in range(i, self.L):
+            self.AL[k] = None
+        for k in range(0, i + 1):
+            self.AR[k] = None
+
+    def set_AC(self, i, vec):
+        if self.AC[i] is None:
+            if i < self.L - 1:
+                self.get_AR(i + 1)
+            if i > 0:
+                self.get_AL(i - 1)
+        self._invalidate(i)
+        self.AC[i] = vec
+
+    def set_AC_alc(self, i, al, c, newV):
+        """ψ.AC[i] = (al, c): orthoview.jl:121-143 (b is the bond tensor)"""
+        if self.AC[i] is None:
+            if i < self.L - 1:
+                self.get_AR(i + 1)
+            if i > 0:
+                self.get_AL(i - 1)
+        self._invalidate(i)
+        self.V[i + 1] = newV
+        self.CL[i + 1] = c
+        self.AL[i] = al
+
+    def set_AC_car(self, i, c, ar, newV):
+        """ψ.AC[i] = (c, ar)"""
+        if self.AC[i] is None:
+            if i < self.L - 1:
+                self.get_AR(i + 1)
+            if i > 0:
+                self.get_AL(i - 1)
+        self._invalidate(i)
+        self.V[i] = newV
+        self.CL[i] = c
+        self.AR[i] = ar
+
+    def entanglement_spectrum(self, i):
+        """toolbox.jl:65-69: per-sector singular values of CR[i]."""
+        C = self.get_CR(i)
+        V = self.V[i + 1]
+        q = V.index_charges()
+        return {c: np.linalg.svd(C[np.ix_(q == c, q == c)], compute_uv=False) for c in V.charges}
+
+
+class FinEnv:
+    """FinEnv.jl:9-145 with identity-based staleness (`===`)."""
+
+    def __init__(self, psi: FiniteMPS, H: MPOHamiltonian):
+        self.opp = H
+        L = psi.L
+        odim = H.odim
+        # FinEnv.jl:41-70: l_LL (x) 1 on level 1, r_RR (x) 1 on level odim (MPOHamiltonian)
+        D0, DL = psi.V[0].dim, psi.V[L].dim
+        ls = np.zeros((D0, odim, D0), dtype=np.complex128); ls[:, 0, :] = np.eye(D0)
+        rs = np.zeros((DL, odim, DL), dtype=np.complex128); rs[:, odim - 1, :] = np.eye(DL)
+        self.leftenvs = [ls] + [None] * L
+        self.rightenvs = [None] * L + [rs]
+        self.ldep = [None] * L
+        self.rdep = [None] * L
+
+    def rightenv(self, ind, psi):
+        """FinEnv.jl:114-129: env contractable with the tensor on site ind"""
+        a = None
+        for i in range(psi.L - 1, ind, -1):
+            if psi.get_AR(i) is not self.rdep[i]:
+                a = i
+                break
+        if a is not None:
+            for j in range(a, ind, -1):
+                AR = psi.get_AR(j)
+                self.rightenvs[j] = transfer_right_sparse(self.rightenvs[j + 1], self.opp[j], AR, AR)
+                self.rdep[j] = AR
+        return self.rightenvs[ind + 1]
+
+    def leftenv(self, ind, psi):
+        """FinEnv.jl:131-145"""
+        a = None
+        for i in range(0, ind):
+            if psi.get_AL(i) is not self.ldep[i]:
+                a = i
+                break
+        if a is not None:
+            for j in range(a, ind):
+                AL = psi.get_AL(j)
+                self.leftenvs[j + 1] = transfer_left_sparse(self.leftenvs[j], self.opp[j], AL, AL)
+                self.ldep[j] = AL
+        return self.leftenvs[ind]
+
+
+def expectation_value(psi, H, envs):
+    """expval.jl:92-109: per-site energies with the half-weight rule for boundary-row/column entries."""
+    ens = np.zeros(psi.L, dtype=np.complex128)
+    for i in range(psi.L):
+        AC = psi.get_AC(i)
+        GL, GR = envs.leftenv(i, psi), envs.rightenv(i, psi)
+        for (j, k) in H[i].keys():
+            if not ((j == 0 and k != 0) or (k == H.odim - 1 and j != H.odim - 1)):
+                continue
+            cur = np.einsum('ac,cpe,ef,aqf,qp->', GL[:, j, :], AC, GR[:, k, :], np.conj(AC), H[i].op(j, k),
+                            optimize=True)
+            if not (j == 0 and k == H.odim - 1):
+                cur = cur / 2
+            ens[i] += cur
+    n = np.linalg.norm(psi.get_AC(psi.L - 1)) ** 2
+    return ens / n
+
+
+def calc_galerkin(psi, pos, envs):
+    """toolbox.jl:17-22"""
+    AC = psi.get_AC(pos)
+    y = dAC_sparse(AC, envs.opp[pos], envs.leftenv(pos, psi), envs.rightenv(pos, psi))
+    y = y / np.linalg.norm(y)
+    AL = psi.get_AL(pos)
+    proj = np.einsum('apb,cqb,cqd->apd', AL, np.conj(AL), y, optimize=True)
+    return float(np.linalg.norm(y - proj))
+
+
+def ac2_space_charges(psi, pos):
+    Vl, Vr = psi.V[pos], psi.V[pos + 2]
+    rowq = (Vl.index_charges()[:, None] + psi.pq[None, :]).reshape(-1)          # (l, p1)
+    colq = (Vr.index_charges()[:, None] - psi.pq[None, :]).reshape(-1)          # (r, p2)
+    return rowq, colq
+
+
+def dmrg2_sweeps(psi: FiniteMPS, H, nsweeps=1, trunc=("truncerr", 1e-6), tol=1e-12, krylovdim=30,
+                 maxiter=100, envs=None, log=None):
+    """dmrg.jl:80-137 (fixed number of outer iterations unless converged to `tol`)."""
+    envs = envs or FinEnv(psi, H)
+    L = psi.L
+    eps_all = 0.0
+    for it in range(nsweeps):
+        eps_s = np.zeros(L)
+        for direction, rng_ in (("lr", range(0, L - 1)), ("rl", range(L - 3, -1, -1))):
+            for pos in rng_:
+                if direction == "lr":
+                    ac2 = np.einsum('apk,kqr->aprq', psi.get_AC(pos), psi.get_AR(pos + 1))
+                else:
+                    ac2 = np.einsum('apk,kqr->aprq', psi.get_AL(pos), psi.get_AC(pos + 1))
+                GL, GR = envs.leftenv(pos, psi), envs.rightenv(pos + 1, psi)
+                f = lambda x: dAC2_sparse(x, H[pos], H[pos + 1], GL, GR)
+                val, new, info = eigsolve_lanczos(f, ac2, "SR", tol, krylovdim, maxiter)
+                Dl, d1, Dr, d2 = new.shape
+                rowq, colq = ac2_space_charges(psi, pos)
+                U, S, Vh, newV, eps_tr, sinfo = tsvd(new.reshape(Dl * d1, Dr * d2), rowq, colq, trunc,
+                                                     psi.p.modulus)
+                S = S / np.linalg.norm(S)
+                al = U.reshape(Dl, d1, newV.dim)
+                ar_t = Vh.reshape(newV.dim, Dr, d2)                         # [k; r p2]
+                c = np.diag(S).astype(np.complex128)
+                v = np.einsum('aprq,apk,k,krq->', ac2, np.conj(al), S, np.conj(ar_t), optimize=True)
+                eps_s[pos] = max(eps_s[pos], abs(1 - abs(v)))
+                ar = ar_t.transpose(0, 2, 1)                                # _transpose_front: [k p2; r]
+                if direction == "lr":
+                    psi.set_AC_alc(pos, al, c, newV)
+                    psi.set_AC_car(pos + 1, c, ar, newV)
+                else:
+                    psi.set_AC_car(pos + 1, c, ar, newV)
+                    psi.set_AC_alc(pos, al, c, newV)
+                if log is not None:
+                    log.append(dict(sweep=it, dir=direction, pos=pos, energy=float(np.real(val)),
+                                    eps_trunc=eps_tr, kept=dict(sinfo["kept"]), numops=info["numops"],
+                                    spectrum={q: s.copy() for q, s in sinfo["spectrum"].items()}))
+        eps_all = eps_s.max()
+        if eps_all <= tol:
+            break
+    return psi, envs, eps_all
+
+
+def dmrg_sweeps(psi: FiniteMPS, H, nsweeps=1, tol=1e-12, krylovdim=30, maxiter=100, envs=None, log=None):
+    """dmrg.jl:22-55 single-site DMRG."""
+    envs = envs or FinEnv(psi, H)
+    L = psi.L
+    eps = 0.0
+    for it in range(nsweeps):
+        eps_s = np.zeros(L)
+        for pos in list(range(0, L - 1)) + list(range(L - 1, 0, -1)):
+            GL, GR = envs.leftenv(pos, psi), envs.rightenv(pos, psi)
+            f = lambda x: dAC_sparse(x, H[pos], GL, GR)
+            val, vec, info = eigsolve_lanczos(f, psi.get_AC(pos), "SR", tol, krylovdim, maxiter)
+            eps_s[pos] = max(eps_s[pos], calc_galerkin(psi, pos, envs))
+            psi.set_AC(pos, vec)
+            if log is not None:
+                log.append(dict(sweep=it, pos=pos, energy=float(np.real(val)), numops=info["numops"]))
+        eps = eps_s.max()
+        if eps <= tol:
+            break
+    return psi, envs, eps
+
+
+def tdvp_step(psi: FiniteMPS, H, dt, envs=None, tol=1e-12, krylovdim=30):
+    """tdvp.jl:61-91: one finite TDVP sweep (left->right then right->left, half steps)."""
+    envs = envs or FinEnv(psi, H)
+    L = psi.L
+    for i in range(0, L - 1):
+        GL, GR = envs.leftenv(i, psi), envs.rightenv(i, psi)
+        f = lambda x: dAC_sparse(x, H[i], GL, GR)
+        ac, _ = exponentiate_lanczos(f, -1j * dt / 2, psi.get_AC(i), tol, krylovdim)
+        psi.set_AC(i, ac)
+        GLn, GRn = envs.leftenv(i + 1, psi), envs.rightenv(i, psi)
+        fc = lambda c: dC_dense(c, GLn, GRn)
+        c, _ = exponentiate_lanczos(fc, +1j * dt / 2, psi.get_CR(i), tol, krylovdim)
+        psi_set_CR(psi, i, c)
+    GL, GR = envs.leftenv(L - 1, psi), envs.rightenv(L - 1, psi)
+    f = lambda x: dAC_sparse(x, H[L - 1], GL, GR)
+    ac, _ = exponentiate_lanczos(f, -1j * dt / 2, psi.get_AC(L - 1), tol, krylovdim)
+    psi.set_AC(L - 1, ac)
+    for i in range(L - 1, 0, -1):
+        GL, GR = envs.leftenv(i, psi), envs.rightenv(i, psi)
+        f = lambda x: dAC_sparse(x, H[i], GL, GR)
+        ac, _ = exponentiate_lanczos(f, -1j * dt / 2, psi.get_AC(i), tol, krylovdim)
+        psi.set_AC(i, ac)
+        GLn, GRn = envs.leftenv(i, psi), envs.rightenv(i - 1, psi)
+        fc = lambda c: dC_dense(c, GLn, GRn)
+        c, _ = exponentiate_lanczos(fc, +1j * dt / 2, psi.get_CR(i - 1), tol, krylovdim)
+        psi_set_CR(psi, i - 1, c)
+    GL, GR = envs.leftenv(0, psi), envs.rightenv(0, psi)
+    f = lambda x: dAC_sparse(x, H[0], GL, GR)
+    ac, _ = exponentiate_lanczos(f, -1j * dt / 2, psi.get_AC(0), tol, krylovdim)
+    psi.set_AC(0, ac)
+    return psi, envs
+
+
+def psi_set_CR(psi: FiniteMPS, i, vec):
+    """orthoview.jl:62-77 CRView setindex!"""
+    if psi.CL[i + 1] is None:
+        psi.get_CR(i)
+    if psi.AL[i] is None:
+        psi.get_AL(i)
+    if i + 1 < psi.L and psi.AR[i + 1] is None:
+        psi.get_AR(i + 1)
+    psi.CL = [None] * (psi.L + 1)
+    psi.AC = [None] * psi.L
+    for k in range(i + 1, psi.L):
+        psi.AL[k] = None
+    for k in range(0, i + 1):
+        psi.AR[k] = None
+    psi.CL[i + 1] = vec

@@ -1,0 +1,188 @@
+"""Sparse MPO slices with width-1 levels and the model Hamiltonians of the configs.
+
+Mirrors ``SparseMPOSlice`` (src/operators/sparsempo/sparseslice.jl:13-106): ``Os[i, j]`` is
+either the number zero (absent), a number (scalar entry c * identity, ``isscal``) or a d x d
+operator ``O[p_out, p_in]``; ``keys``, ``opkeys``, ``scalkeys``, ``contains`` and ``isscal`` have
+the reference semantics (sparseslice.jl:74-106).  Level charges obey
+c_j = c_i + s_{p_out} - s_{p_in} for every non-zero operator element (the TensorMap
+O[wl p_out; p_in wr] of docs/src/man/intro.md:77-83 restricted to width-1 levels).
+``MPOHamiltonian`` structure (upper triangular, Os[1,1] = Os[end,end] = 1) follows
+src/operators/mpohamiltonian.jl:19-31,63-74.
+"""
+from __future__ import annotations
+import numpy as np
+
+
+class SparseMPOSlice:
+    def __init__(self, Os, level_charges_left, level_charges_right, phys_charges):
+        self.odim = len(Os)
+        self.Os = [[Os[i][j] for j in range(self.odim)] for i in range(self.odim)]
+        self.cl = tuple(int(c) for c in level_charges_left)
+        self.cr = tuple(int(c) for c in level_charges_right)
+        self.pch = tuple(int(c) for c in phys_charges)
+        self.d = len(self.pch)
+        for (i, j) in self.keys():
+            if not self.isscal(i, j):
+                O = np.asarray(self.Os[i][j])
+                assert O.shape == (self.d, self.d)
+                for a in range(self.d):
+                    for b in range(self.d):
+                        if O[a, b] != 0:
+                            assert self.cr[j] == self.cl[i] + self.pch[a] - self.pch[b], \
+                                f"entry ({i},{j}) element ({a},{b}) violates charge conservation"
+            else:
+                assert self.cr[j] == self.cl[i]
+
+    # sparseslice.jl:100-106
+    def contains(self, i, j):
+        e = self.Os[i][j]
+        return not (np.isscalar(e) and e == 0)
+
+    def isscal(self, i, j):
+        return np.isscalar(self.Os[i][j]) and self.contains(i, j)
+
+    # sparseslice.jl:74-98 ; product(1:odim,1:odim) iterates the first index fastest
+    def keys(self):
+        return [(i, j) for j in range(self.odim) for i in range(self.odim) if self.contains(i, j)]
+
+    def keys_col(self, k):
+        return [i for i in range(self.odim) if self.contains(i, k)]
+
+    def keys_row(self, j):
+        return [k for k in range(self.odim) if self.contains(j, k)]
+
+    def opkeys(self):
+        return [(i, j) for (i, j) in self.keys() if not self.isscal(i, j)]
+
+    def scalkeys(self):
+        return [(i, j) for (i, j) in self.keys() if self.isscal(i, j)]
+
+    # sparseslice.jl:40-55: getindex materialises scalars as c * (1 (x) 1)
+    def op(self, i, j):
+        e = self.Os[i][j]
+        if np.isscalar(e):
+            return e * np.eye(self.d, dtype=np.complex128)
+        return np.asarray(e, dtype=np.complex128)
+
+    def dense(self):
+        """O[wl, p_out, p_in, wr] (SURVEY.md Appendix A index order)."""
+        out = np.zeros((self.odim, self.d, self.d, self.odim), dtype=np.complex128)
+        for (i, j) in self.keys():
+            out[i, :, :, j] = self.op(i, j)
+        return out
+
+    def kinds(self):
+        """integer bookkeeping compared bit-exactly with the device side: 0 absent, 1 scalar, 2 operator."""
+        return [[0 if not self.contains(i, j) else (1 if self.isscal(i, j) else 2)
+                 for j in range(self.odim)] for i in range(self.odim)]
+
+
+class MPOHamiltonian:
+    """finite/periodic list of slices; ``H[i]`` is the slice at site i (0-based here)."""
+
+    def __init__(self, slices):
+        self.slices = list(slices)
+        self.odim = self.slices[0].odim
+
+    def __len__(self):
+        return len(self.slices)
+
+    def __getitem__(self, i):
+        return self.slices[i % len(self.slices)]
+
+
+# ----------------------------------------------------------------------------- local operators
+def spin_ops(d=2):
+    """S+, S-, Sz for spin (d-1)/2 in the basis m = +S ... -S (charges 2m descending -> we sort ascending)."""
+    S = (d - 1) / 2
+    ms = np.array([-S + k for k in range(d)])  # ascending m  => ascending charge 2m
+    Sz = np.diag(ms)
+    Sp = np.zeros((d, d))
+    for k in range(d - 1):
+        m = ms[k]
+        Sp[k + 1, k] = np.sqrt(S * (S + 1) - m * (m + 1))
+    Sm = Sp.T.copy()
+    charges = tuple(int(round(2 * m)) for m in ms)
+    return Sp, Sm, Sz, charges
+
+
+def fsm_hamiltonian(L, odim, entries, level_charges, phys_charges):
+    """build a uniform upper-triangular FSM MPO from {(i,j): scalar|matrix}."""
+    def one_slice():
+        Os = [[0 for _ in range(odim)] for _ in range(odim)]
+        for (i, j), v in entries.items():
+            Os[i][j] = v
+        return SparseMPOSlice(Os, level_charges, level_charges, phys_charges)
+    return MPOHamiltonian([one_slice() for _ in range(L)])
+
+
+def transverse_field_ising(L, g=1.0):
+    """test/setup.jl:38-44: H = -sum ZZ - g sum X (g/2 per bond side -> g per site in the bulk...).
+
+    The reference builds it from the two-site term  -(Z(x)Z + g/2 (X(x)E + E(x)X)) through
+    ``decompose_localmpo``; the resulting operator on an infinite chain is
+    -sum_i Z_i Z_{i+1} - g sum_i X_i, which is what this FSM encodes (trivial symmetry, chi=3).
+    """
+    X = np.array([[0, 1], [1, 0]], dtype=np.complex128)
+    Z = np.array([[1, 0], [0, -1]], dtype=np.complex128)
+    ent = {(0, 0): 1.0, (2, 2): 1.0, (0, 1): -Z, (1, 2): Z, (0, 2): -g * X}
+    return fsm_hamiltonian(L, 3, ent, (0, 0, 0), (0, 0))
+
+
+def heisenberg_u1(L, d=2, J=1.0):
+    """nearest-neighbour Heisenberg, U(1) FSM: levels (1, S+, S-, Sz, end), charges (0,+2,-2,0,0)
+    (2 scalar + 6 operator entries)."""
+    Sp, Sm, Sz, pch = spin_ops(d)
+    ent = {(0, 0): 1.0, (4, 4): 1.0,
+           (0, 1): Sp, (0, 2): Sm, (0, 3): Sz,
+           (1, 4): 0.5 * J * Sm, (2, 4): 0.5 * J * Sp, (3, 4): J * Sz}
+    # level after S+ (raises: s_out - s_in = +2) carries +2
+    return fsm_hamiltonian(L, 5, ent, (0, 2, -2, 0, 0), pch)
+
+
+def heisenberg_longrange_u1(L, r=6, d=2, power=2.0):
+    """range-r Heisenberg J_k = 1/k^power as a U(1) FSM with chi = 2 + 3r:
+    r=6 -> chi=20, 38 non-zeros (17 scalars, 21 operators)."""
+    Sp, Sm, Sz, pch = spin_ops(d)
+    odim = 2 + 3 * r
+    end = odim - 1
+    ent = {(0, 0): 1.0, (end, end): 1.0}
+    ch = [0] * odim
+    ops_first = [Sp, Sm, Sz]
+    ops_last = [0.5 * Sm, 0.5 * Sp, Sz]
+    qs = [2, -2, 0]
+    for t in range(3):
+        for k in range(r):
+            lev = 1 + t * r + k
+            ch[lev] = qs[t]
+            if k == 0:
+                ent[(0, lev)] = ops_first[t]
+            else:
+                ent[(lev - 1, lev)] = 1.0
+            ent[(lev, end)] = (1.0 / (k + 1) ** power) * ops_last[t]
+    return fsm_hamiltonian(L, odim, ent, ch, pch)
+
+
+def heisenberg_dense(L, d=2, J=1.0):
+    """same operator without symmetry (all charges zero): the dense/trivial path."""
+    H = heisenberg_u1(L, d, J)
+    sl = []
+    for s in H.slices:
+        sl.append(SparseMPOSlice(s.Os, (0,) * s.odim, (0,) * s.odim, (0,) * s.d))
+    return MPOHamiltonian(sl)
+
+
+def dense_hamiltonian(H: MPOHamiltonian):
+    """full 2^L matrix of a finite MPOHamiltonian with the FinEnv boundary vectors
+    (level 1 on the left, level odim on the right; FinEnv.jl:41-70). Exact-diagonalisation anchor."""
+    L = len(H)
+    cur = None
+    for i in range(L):
+        W = H[i].dense()  # wl, po, pi, wr
+        if cur is None:
+            cur = W[0]  # po, pi, wr
+        else:
+            cur = np.einsum('abw,wcdv->acbdv', cur, W)
+            s = cur.shape
+            cur = cur.reshape(s[0] * s[1], s[2] * s[3], s[4])
+    return cur[:, :, -1]
