@@ -1,0 +1,154 @@
+/* mpskit_b200 -- C ABI of the B200-native MPSKit.jl hot path.
+ *
+ * The reference (MPSKit.jl v0.10.2, pure Julia) has no FFI; the seam is Julia multiple dispatch.
+ * Every entry point below names the reference method (file:line under the reference tree) that a
+ * thin `ccall` shim overloads with it (INTEGRATION.md shows the shim).  Plain pointers and sizes
+ * only; no exceptions cross the boundary; every function returns an mpsk_status (0 = ok, <0 error)
+ * and `mpsk_last_error` gives the message.  Thread safety: a context is used by one thread at a
+ * time (create one per Julia task / per rank); distinct contexts are independent.
+ *
+ * Data model (TensorKit abelian block structure).  All tensors on the path are of
+ * the generic three-leg form  T[l, m, r]  with graded bond spaces l, r and a flat label set m whose
+ * labels carry a charge; charge conservation is  q_r = q_l + mcharge[m]  (mod `modulus` for Z_N):
+ *    MPS tensor  A[l p; r]           m = physical state,        mcharge = s_p
+ *    two-site    x[l p1; r p2]       m = p1 * d2 + p2,          mcharge = s_p1 + s_p2
+ *    bond        C[l; r]             m = one label,             mcharge = 0
+ *    left env    GL[l_bra w; l_ket]  m = MPO level (width 1),   mcharge = -c_w
+ *    right env   GR[r_ket w; r_bra]  m = MPO level,             mcharge = +c_w
+ * Charges are int32 (2q for half-integer U(1) irreps).  Sectors are listed in ascending charge.
+ * One dense block per (m, l-sector) whose r-sector exists; the host hands each block as a pointer
+ * plus element strides, so TensorKit's column-major fusion-tree sub-blocks and numpy arrays are
+ * both passed without copies on the caller's side.  Host blocks are only read during upload and
+ * only written during download; device storage belongs to the library until mpsk_tensor_free.
+ */
+#ifndef MPSKIT_B200_H
+#define MPSKIT_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mpsk_ctx mpsk_ctx;
+typedef struct mpsk_tensor mpsk_tensor;
+typedef struct mpsk_mposlice mpsk_mposlice;
+typedef struct mpsk_op mpsk_op;
+
+typedef enum {
+  MPSK_OK = 0,
+  MPSK_EINVAL = -1,    /* bad argument */
+  MPSK_ESPACE = -2,    /* sector / space mismatch (TensorKit SpaceMismatch) */
+  MPSK_ECUDA = -3,     /* CUDA runtime / cuSOLVER / NCCL failure */
+  MPSK_ENOMEM = -4,
+  MPSK_EINTERNAL = -5,
+  MPSK_ENODEVICE = -6  /* no usable GPU: there is no CPU fallback */
+} mpsk_status;
+
+enum { MPSK_F64 = 0, MPSK_C128 = 1 };                 /* scalar type (Defaults.eltype = ComplexF64, defaults.jl:18) */
+enum { MPSK_SR = 0, MPSK_LM = 1, MPSK_LR = 2 };       /* `which` of fixedpoint (fixedpoint.jl:9,19) */
+enum { MPSK_NOTRUNC = 0, MPSK_TRUNCDIM = 1, MPSK_TRUNCERR = 2, MPSK_TRUNCBELOW = 3 }; /* TensorKit truncation schemes used at dmrg.jl:75,96 */
+enum { MPSK_OP_DC = 0, MPSK_OP_DAC = 1, MPSK_OP_DAC2 = 2 };
+
+#define MPSK_FLAG_DEBUG_GEMM 1ull  /* route contractions through the one-thread-per-element cross-check kernel (tests only) */
+
+typedef struct { int32_t nsec; const int32_t* charge; const int64_t* dim; int32_t modulus; } mpsk_space;
+typedef struct { const void* ptr; int64_t stride_l; int64_t stride_r; } mpsk_blockref;   /* strides in scalar elements */
+typedef struct { void* ptr; int64_t stride_l; int64_t stride_r; } mpsk_blockref_mut;
+typedef struct { int32_t kind; double value; } mpsk_trunc;                               /* value: D or epsilon */
+typedef struct { int32_t converged; int32_t numiter; int32_t numops; double normres; } mpsk_info; /* KrylovKit ConvergenceInfo */
+
+/* ---- context ------------------------------------------------------------------------------ */
+int32_t mpsk_create(int32_t device, uint64_t flags, mpsk_ctx** out);
+void mpsk_destroy(mpsk_ctx* ctx);
+const char* mpsk_last_error(const mpsk_ctx* ctx);
+int32_t mpsk_version(void);
+int32_t mpsk_set_stream(mpsk_ctx* ctx, void* cuda_stream);       /* adopt the caller's cudaStream_t (NULL = library stream) */
+int32_t mpsk_synchronize(mpsk_ctx* ctx);
+int64_t mpsk_launch_count(const mpsk_ctx* ctx);                  /* kernels launched so far by this context */
+int64_t mpsk_bytes_in_use(const mpsk_ctx* ctx);
+
+/* ---- tensors (TensorMap blocks <-> device) --------------------------------------------------- */
+/* number and order of blocks for a structure: block b <-> (m[b], lsec[b], rsec[b]); arrays may be NULL to query the count.
+ * Integer bookkeeping, must match the oracle bit-exactly. */
+int32_t mpsk_block_table(const mpsk_space* Vl, int32_t nm, const int32_t* mcharge, const mpsk_space* Vr,
+                         int32_t* nblocks, int32_t* m, int32_t* lsec, int32_t* rsec);
+int32_t mpsk_tensor_upload(mpsk_ctx* ctx, const mpsk_space* Vl, int32_t nm, const int32_t* mcharge, const mpsk_space* Vr,
+                           int32_t dtype, const mpsk_blockref* blocks, int32_t nblocks, mpsk_tensor** out);
+int32_t mpsk_tensor_zeros(mpsk_ctx* ctx, const mpsk_space* Vl, int32_t nm, const int32_t* mcharge, const mpsk_space* Vr,
+                          int32_t dtype, mpsk_tensor** out);
+int32_t mpsk_tensor_download(mpsk_ctx* ctx, const mpsk_tensor* t, const mpsk_blockref_mut* blocks, int32_t nblocks);
+/* synthetic data: uniform(-1,1) entries in every symmetry-allowed block, reproducible from `seed` (benchmarks, property tests) */
+int32_t mpsk_tensor_fill_random(mpsk_ctx* ctx, mpsk_tensor* t, uint64_t seed);
+int32_t mpsk_tensor_copy(mpsk_ctx* ctx, const mpsk_tensor* t, mpsk_tensor** out);
+void mpsk_tensor_free(mpsk_ctx* ctx, mpsk_tensor* t);
+/* structure query (two-phase: counts first, then arrays) -- sizes after truncation (tsvd) */
+int32_t mpsk_tensor_structure(const mpsk_tensor* t, int32_t* nsec_l, int32_t* nsec_r, int32_t* nm, int32_t* dtype);
+int32_t mpsk_tensor_spaces(const mpsk_tensor* t, int32_t* charge_l, int64_t* dim_l, int32_t* charge_r, int64_t* dim_r, int32_t* mcharge);
+
+/* ---- VectorInterface on handles (inner, norm, add!!, scale!!; KrylovKit vectors) -- */
+int32_t mpsk_dot(mpsk_ctx* ctx, const mpsk_tensor* x, const mpsk_tensor* y, double* re, double* im);   /* <x|y>, conj on x */
+int32_t mpsk_norm(mpsk_ctx* ctx, const mpsk_tensor* x, double* out);
+int32_t mpsk_axpy(mpsk_ctx* ctx, double a_re, double a_im, const mpsk_tensor* x, mpsk_tensor* y);    /* y += a x */
+int32_t mpsk_scale(mpsk_ctx* ctx, double a_re, double a_im, mpsk_tensor* x);
+
+/* ---- MPO slice: SparseMPOSlice (src/operators/sparsempo/sparseslice.jl:13-106) ------------------
+ * odim width-1 levels with charges; `kind[i*odim+j]`: 0 absent, 1 scalar (Os[i,j] isa E), 2 operator;
+ * `scal[2*(i*odim+j)]` re/im of scalar entries; operator entries are d x d row-major complex
+ * matrices O[p_out, p_in] concatenated in (i-major, j-minor) order of the kind==2 entries. */
+int32_t mpsk_mposlice_create(mpsk_ctx* ctx, int32_t odim, const int32_t* level_charge_left, const int32_t* level_charge_right,
+                             int32_t d, const int32_t* phys_charge, const int32_t* kind, const double* scal,
+                             const double* ops, mpsk_mposlice** out);
+void mpsk_mposlice_free(mpsk_ctx* ctx, mpsk_mposlice* s);
+/* keys(x) (sparseslice.jl:74-76), first index fastest; returns count, fills (i,j) pairs if non-NULL */
+int32_t mpsk_mposlice_keys(const mpsk_mposlice* s, int32_t* count, int32_t* ij);
+
+/* ---- effective Hamiltonians: MPO_ddC / MPO_ddAC / MPO_ddAC2 (src/algorithms/derivatives.jl:6-71) ---
+ * GL, GR are environment tensors (level = label).  h1/h2: slices at pos / pos+1 (h2 NULL unless DAC2;
+ * both NULL for DC).  `x_like` fixes the block structure of the vectors the operator acts on. */
+int32_t mpsk_op_create(mpsk_ctx* ctx, int32_t kind, const mpsk_mposlice* h1, const mpsk_mposlice* h2,
+                       const mpsk_tensor* GL, const mpsk_tensor* GR, const mpsk_tensor* x_like, mpsk_op** out);
+void mpsk_op_free(mpsk_ctx* ctx, mpsk_op* op);
+double mpsk_op_flops(const mpsk_op* op);                           /* algorithmic real flops of one apply */
+/* y = h(x): dC / dAC / dAC2 (derivatives.jl:77-197). */
+int32_t mpsk_op_apply(mpsk_ctx* ctx, const mpsk_op* op, const mpsk_tensor* x, mpsk_tensor* y);
+/* fixedpoint(h, x0, which, alg) (src/algorithms/fixedpoint.jl:9-30): Krylov eigensolve on the device. */
+int32_t mpsk_eigsolve(mpsk_ctx* ctx, const mpsk_op* op, const mpsk_tensor* x0, int32_t which, int32_t hermitian,
+                      int32_t krylovdim, int32_t maxiter, double tol, double* val_re, double* val_im,
+                      mpsk_tensor* vec, mpsk_info* info);
+/* integrate -> exponentiate(h, tau, y0) (src/algorithms/timestep/integrators.jl:20-25): y = exp(tau h) y0 */
+int32_t mpsk_expv(mpsk_ctx* ctx, const mpsk_op* op, double tau_re, double tau_im, const mpsk_tensor* y0,
+                  int32_t krylovdim, int32_t maxiter, double tol, mpsk_tensor* y, mpsk_info* info);
+
+/* ---- transfer matrices / environment updates (src/transfermatrix/transfer.jl:137-259,
+ *      src/environments/FinEnv.jl:114-145) --------------------------------------------------------- */
+int32_t mpsk_transfer_left(mpsk_ctx* ctx, const mpsk_mposlice* h, const mpsk_tensor* A, const mpsk_tensor* Abar,
+                           const mpsk_tensor* GL, mpsk_tensor** GL_out);
+int32_t mpsk_transfer_right(mpsk_ctx* ctx, const mpsk_mposlice* h, const mpsk_tensor* A, const mpsk_tensor* Abar,
+                            const mpsk_tensor* GR, mpsk_tensor** GR_out);
+
+/* ---- local tensor algebra of the sweep bodies ------------------------------------------------------ */
+/* ac2[l p1; r p2] = A1[l p1; k] A2[k p2; r]   (dmrg.jl:92,108) */
+int32_t mpsk_contract_ac2(mpsk_ctx* ctx, const mpsk_tensor* A1, const mpsk_tensor* A2, mpsk_tensor** out);
+/* A[l p; r] * C[r; r'] and C[l'; l] * A[l p; r]   (orthoview.jl:95-106) */
+int32_t mpsk_mul_bond_right(mpsk_ctx* ctx, const mpsk_tensor* A, const mpsk_tensor* C, mpsk_tensor** out);
+int32_t mpsk_mul_bond_left(mpsk_ctx* ctx, const mpsk_tensor* C, const mpsk_tensor* A, mpsk_tensor** out);
+/* tsvd!(ac2; trunc, alg=SVD()) + normalize!(c) (dmrg.jl:96-97,112-113): U = al[l p1; k], S = diag c (normalised,
+ * returned as a bond tensor), Vh = ar as an MPS tensor [k p2; r] (i.e. _transpose_front(ar)).  d1: size of p1,
+ * p1_charge[d1]: charges of the p1 basis states (fixes the charges of the new bond k = l + p1).
+ * eps_trunc: 2-norm of the discarded singular values (of the un-normalised input). */
+int32_t mpsk_tsvd(mpsk_ctx* ctx, const mpsk_tensor* ac2, int32_t d1, const int32_t* p1_charge, mpsk_trunc trunc, mpsk_tensor** U,
+                  mpsk_tensor** S, mpsk_tensor** Vh, double* eps_trunc);
+/* singular values of the last mpsk_tsvd, per coupled sector, before truncation: two-phase query */
+int32_t mpsk_tsvd_spectrum(mpsk_ctx* ctx, int32_t* nsec, int32_t* charge, int32_t* count, int32_t* kept, double* values);
+/* leftorth!(A; alg=QRpos()) / rightorth!(A; alg=LQpos()) (orthoview.jl:49-60) */
+int32_t mpsk_qrpos(mpsk_ctx* ctx, const mpsk_tensor* A, mpsk_tensor** Q, mpsk_tensor** R);
+int32_t mpsk_lqpos(mpsk_ctx* ctx, const mpsk_tensor* A, mpsk_tensor** L, mpsk_tensor** Q);
+
+/* ---- multi-GPU (one process per GPU; NCCL over NVLink) ------------------------------------------- */
+int32_t mpsk_comm_unique_id(uint8_t out128[128]);
+int32_t mpsk_comm_init(mpsk_ctx* ctx, const uint8_t id128[128], int32_t rank, int32_t nranks);
+int32_t mpsk_allreduce_sum(mpsk_ctx* ctx, mpsk_tensor* x);        /* partial-sum reduction of a sharded matvec */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

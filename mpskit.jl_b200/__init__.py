@@ -1,0 +1,16 @@
+"""mpskit_b200: B200-native (sm_100a) hot path of MPSKit.jl behind the reference's own operator API.
+
+The numerical work lives in ``libmpskit_b200.so`` (csrc/, C ABI in include/mpskit_b200.h); this package is the
+host-side mirror of the reference interface for that path (same names, argument meaning and error behaviour).
+"""
+from ._lib import (Context, default_context, MpskError, SpaceMismatch, load as load_library, LIB_PATH)  # noqa: F401
+from .spaces import Space, fuse, infimum, dual  # noqa: F401
+from .tensor import DeviceTensor, block_table  # noqa: F401
+from .operators import (SparseMPOSlice, MPOHamiltonian, transverse_field_ising, heisenberg_u1,  # noqa: F401
+                        heisenberg_longrange_u1, drop_symmetry)
+from .derivatives import MPO_ddC, MPO_ddAC, MPO_ddAC2, ddC, ddAC, ddAC2  # noqa: F401
+from .fixedpoint import fixedpoint, integrate, Lanczos, Arnoldi  # noqa: F401
+from .finitemps import FiniteMPS, virtual_spaces  # noqa: F401
+from .environments import FinEnv, environments  # noqa: F401
+from .dmrg import (DMRG2, find_groundstate, find_groundstate_inplace, expectation_value, tsvd, contract_ac2,  # noqa: F401
+                   truncdim, truncerr, truncbelow, notrunc, tsvd_spectrum)

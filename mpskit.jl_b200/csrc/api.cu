@@ -1,0 +1,451 @@
+// extern "C" surface of libmpskit_b200 (see include/mpskit_b200.h for the reference method each entry replaces).
+#include "internal.h"
+#include <cmath>
+#include <dlfcn.h>
+
+using namespace mpsk;
+
+#define CTX(c) (reinterpret_cast<Ctx*>(c))
+#define TEN(t) (reinterpret_cast<Tensor*>(t))
+#define CTEN(t) (reinterpret_cast<const Tensor*>(t))
+#define SLICE(s) (reinterpret_cast<const MpoSlice*>(s))
+
+// stage host blocks (arbitrary strides) through one pinned buffer, then scatter with the strided-copy kernel
+template <typename T>
+static void pack_block(T* dst, const T* src, int64_t nl, int64_t nr, int64_t sl, int64_t sr) {
+  for (int64_t i = 0; i < nl; ++i) for (int64_t j = 0; j < nr; ++j) dst[i * nr + j] = src[i * sl + j * sr];
+}
+template <typename T>
+static void unpack_block(T* dst, const T* src, int64_t nl, int64_t nr, int64_t sl, int64_t sr) {
+  for (int64_t i = 0; i < nl; ++i) for (int64_t j = 0; j < nr; ++j) dst[i * sl + j * sr] = src[i * nr + j];
+}
+
+
+extern "C" {
+
+int32_t mpsk_version(void) { return 100; }
+
+int32_t mpsk_create(int32_t device, uint64_t flags, mpsk_ctx** out) {
+  if (!out) return MPSK_EINVAL;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return MPSK_ENODEVICE; }
+  if (device < 0 || device >= ndev) return MPSK_EINVAL;
+  if (cudaSetDevice(device) != cudaSuccess) return MPSK_ECUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return MPSK_ECUDA;
+  if (prop.major != 10) return MPSK_ENODEVICE;   // sm_100a only: no other code path exists
+  Ctx* c = new Ctx;
+  c->device = device; c->flags = flags; c->num_sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return MPSK_ECUDA; }
+  c->stream = c->own_stream;
+  *out = reinterpret_cast<mpsk_ctx*>(c);
+  return MPSK_OK;
+}
+
+void mpsk_destroy(mpsk_ctx* ctx) {
+  if (!ctx) return;
+  Ctx* c = CTX(ctx);
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->d_scratch) c->free(c->d_scratch);
+  c->release_cache();
+  for (auto& kv : c->sizes) cudaFree(kv.first);
+  if (c->h_scratch) cudaFreeHost(c->h_scratch);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+const char* mpsk_last_error(const mpsk_ctx* ctx) { return ctx ? reinterpret_cast<const Ctx*>(ctx)->err.c_str() : "null context"; }
+
+int32_t mpsk_set_stream(mpsk_ctx* ctx, void* s) {
+  Ctx* c = CTX(ctx);
+  cudaStreamSynchronize(c->stream);
+  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  return MPSK_OK;
+}
+
+int32_t mpsk_synchronize(mpsk_ctx* ctx) { Ctx* c = CTX(ctx); CUDA_TRY(c, cudaStreamSynchronize(c->stream)); return MPSK_OK; }
+int64_t mpsk_launch_count(const mpsk_ctx* ctx) { return reinterpret_cast<const Ctx*>(ctx)->launches; }
+int64_t mpsk_bytes_in_use(const mpsk_ctx* ctx) { return reinterpret_cast<const Ctx*>(ctx)->bytes_in_use; }
+
+// ------------------------------------------------------------------------------------------ tensors
+static int spaces_from_abi(Ctx* c, const mpsk_space* Vl, const mpsk_space* Vr, Space* l, Space* r) {
+  MPSK_TRY(space_from_abi(c, Vl, l));
+  MPSK_TRY(space_from_abi(c, Vr, r));
+  if (l->mod != r->mod) return c->fail(MPSK_ESPACE, "bond spaces belong to different groups");
+  return MPSK_OK;
+}
+
+int32_t mpsk_block_table(const mpsk_space* Vl, int32_t nm, const int32_t* mcharge, const mpsk_space* Vr, int32_t* nblocks,
+                         int32_t* m, int32_t* lsec, int32_t* rsec) {
+  Ctx tmp; Space l, r;
+  if (spaces_from_abi(&tmp, Vl, Vr, &l, &r) != MPSK_OK) return MPSK_ESPACE;
+  int n = 0;
+  for (int mm = 0; mm < nm; ++mm)
+    for (int jl = 0; jl < l.nsec(); ++jl) {
+      int jr = r.find((int64_t)l.q[jl] + mcharge[mm]);
+      if (jr < 0) continue;
+      if (m) { m[n] = mm; lsec[n] = jl; rsec[n] = jr; }
+      ++n;
+    }
+  if (nblocks) *nblocks = n;
+  return MPSK_OK;
+}
+
+int32_t mpsk_tensor_zeros(mpsk_ctx* ctx, const mpsk_space* Vl, int32_t nm, const int32_t* mcharge, const mpsk_space* Vr, int32_t dtype,
+                          mpsk_tensor** out) {
+  Ctx* c = CTX(ctx); Space l, r;
+  if (dtype != MPSK_F64 && dtype != MPSK_C128) return c->fail(MPSK_EINVAL, "bad dtype");
+  MPSK_TRY(spaces_from_abi(c, Vl, Vr, &l, &r));
+  Tensor* t = nullptr;
+  MPSK_TRY(tensor_create(c, l, std::vector<int32_t>(mcharge, mcharge + nm), r, dtype, F_KL, true, &t));
+  *out = reinterpret_cast<mpsk_tensor*>(t);
+  return MPSK_OK;
+}
+
+int32_t mpsk_tensor_upload(mpsk_ctx* ctx, const mpsk_space* Vl, int32_t nm, const int32_t* mcharge, const mpsk_space* Vr, int32_t dtype,
+                           const mpsk_blockref* blocks, int32_t nblocks, mpsk_tensor** out) {
+  Ctx* c = CTX(ctx);
+  mpsk_tensor* th = nullptr;
+  MPSK_TRY(mpsk_tensor_zeros(ctx, Vl, nm, mcharge, Vr, dtype, &th));
+  std::unique_ptr<Tensor> t(TEN(th));
+  if ((int)t->blks.size() != nblocks) return c->fail(MPSK_ESPACE, "upload: %d blocks given, structure has %zu", nblocks, t->blks.size());
+  const size_t es = t->esize();
+  int64_t total = 0;
+  for (const Blk& b : t->blks) total += t->Vl.n[b.jl] * t->Vr.n[b.jr];
+  if (total == 0) { *out = reinterpret_cast<mpsk_tensor*>(t.release()); return MPSK_OK; }
+  void* hstage = nullptr;
+  CUDA_TRY(c, cudaMallocHost(&hstage, total * es));
+  void* dstage = c->alloc(total * es);
+  if (!dstage) { cudaFreeHost(hstage); return MPSK_ENOMEM; }
+  std::vector<CopyTask> tasks;
+  int64_t off = 0;
+  for (size_t i = 0; i < t->blks.size(); ++i) {
+    const Blk& b = t->blks[i];
+    const int64_t nl = t->Vl.n[b.jl], nr = t->Vr.n[b.jr];
+    if (!blocks[i].ptr) { cudaFreeHost(hstage); c->free(dstage); return c->fail(MPSK_EINVAL, "upload: block %zu has a null pointer", i); }
+    if (es == 16) pack_block((cplx*)hstage + off, (const cplx*)blocks[i].ptr, nl, nr, blocks[i].stride_l, blocks[i].stride_r);
+    else pack_block((double*)hstage + off, (const double*)blocks[i].ptr, nl, nr, blocks[i].stride_l, blocks[i].stride_r);
+    tasks.push_back(CopyTask{(char*)dstage + off * es, t->ptr(b.off), nr, 1, b.sl, b.sr, (int32_t)nl, (int32_t)nr, 0, 0, nullptr});
+    off += nl * nr;
+  }
+  cudaError_t e = cudaMemcpyAsync(dstage, hstage, total * es, cudaMemcpyHostToDevice, c->stream);
+  int st = e == cudaSuccess ? run_copy_tasks(c, tasks, es == 16) : c->fail(MPSK_ECUDA, "H2D copy failed: %s", cudaGetErrorString(e));
+  cudaStreamSynchronize(c->stream);
+  cudaFreeHost(hstage); c->free(dstage);
+  if (st != MPSK_OK) return st;
+  *out = reinterpret_cast<mpsk_tensor*>(t.release());
+  return MPSK_OK;
+}
+
+int32_t mpsk_tensor_download(mpsk_ctx* ctx, const mpsk_tensor* th, const mpsk_blockref_mut* blocks, int32_t nblocks) {
+  Ctx* c = CTX(ctx); const Tensor* t = CTEN(th);
+  if ((int)t->blks.size() != nblocks) return c->fail(MPSK_ESPACE, "download: %d blocks given, structure has %zu", nblocks, t->blks.size());
+  const size_t es = t->esize();
+  int64_t total = 0;
+  for (const Blk& b : t->blks) total += t->Vl.n[b.jl] * t->Vr.n[b.jr];
+  if (total == 0) return MPSK_OK;
+  void* hstage = nullptr;
+  CUDA_TRY(c, cudaMallocHost(&hstage, total * es));
+  void* dstage = c->alloc(total * es);
+  if (!dstage) { cudaFreeHost(hstage); return MPSK_ENOMEM; }
+  std::vector<CopyTask> tasks;
+  int64_t off = 0;
+  for (const Blk& b : t->blks) {
+    const int64_t nl = t->Vl.n[b.jl], nr = t->Vr.n[b.jr];
+    tasks.push_back(CopyTask{t->ptr(b.off), (char*)dstage + off * es, b.sl, b.sr, nr, 1, (int32_t)nl, (int32_t)nr, 0, 0, nullptr});
+    off += nl * nr;
+  }
+  int st = run_copy_tasks(c, tasks, es == 16);
+  if (st == MPSK_OK) {
+    cudaError_t e = cudaMemcpyAsync(hstage, dstage, total * es, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) st = c->fail(MPSK_ECUDA, "D2H copy failed: %s", cudaGetErrorString(e));
+  }
+  if (st == MPSK_OK) {
+    off = 0;
+    for (size_t i = 0; i < t->blks.size(); ++i) {
+      const Blk& b = t->blks[i];
+      const int64_t nl = t->Vl.n[b.jl], nr = t->Vr.n[b.jr];
+      if (es == 16) unpack_block((cplx*)blocks[i].ptr, (const cplx*)hstage + off, nl, nr, blocks[i].stride_l, blocks[i].stride_r);
+      else unpack_block((double*)blocks[i].ptr, (const double*)hstage + off, nl, nr, blocks[i].stride_l, blocks[i].stride_r);
+      off += nl * nr;
+    }
+  }
+  cudaFreeHost(hstage); c->free(dstage);
+  return st;
+}
+
+int32_t mpsk_tensor_fill_random(mpsk_ctx* ctx, mpsk_tensor* t, uint64_t seed) { return tensor_fill_random(CTX(ctx), TEN(t), seed); }
+
+int32_t mpsk_tensor_copy(mpsk_ctx* ctx, const mpsk_tensor* th, mpsk_tensor** out) {
+  Ctx* c = CTX(ctx); const Tensor* t = CTEN(th);
+  Tensor* n = nullptr;
+  MPSK_TRY(tensor_repack(c, t, F_KL, false, &n));
+  *out = reinterpret_cast<mpsk_tensor*>(n);
+  return MPSK_OK;
+}
+
+void mpsk_tensor_free(mpsk_ctx*, mpsk_tensor* t) { delete TEN(t); }
+
+int32_t mpsk_tensor_structure(const mpsk_tensor* th, int32_t* nsec_l, int32_t* nsec_r, int32_t* nm, int32_t* dtype) {
+  const Tensor* t = CTEN(th);
+  if (nsec_l) *nsec_l = t->Vl.nsec();
+  if (nsec_r) *nsec_r = t->Vr.nsec();
+  if (nm) *nm = t->nm();
+  if (dtype) *dtype = t->dtype;
+  return MPSK_OK;
+}
+
+int32_t mpsk_tensor_spaces(const mpsk_tensor* th, int32_t* ql, int64_t* nl, int32_t* qr, int64_t* nr, int32_t* mch) {
+  const Tensor* t = CTEN(th);
+  for (int i = 0; i < t->Vl.nsec(); ++i) { if (ql) ql[i] = t->Vl.q[i]; if (nl) nl[i] = t->Vl.n[i]; }
+  for (int i = 0; i < t->Vr.nsec(); ++i) { if (qr) qr[i] = t->Vr.q[i]; if (nr) nr[i] = t->Vr.n[i]; }
+  if (mch) for (int i = 0; i < t->nm(); ++i) mch[i] = t->mch[i];
+  return MPSK_OK;
+}
+
+// ------------------------------------------------------------------------------------------ vector interface
+static int check_pair(Ctx* c, const Tensor* x, const Tensor* y) {
+  if (!x->same_structure(*y)) return c->fail(MPSK_ESPACE, "tensors have different structure");
+  if (x->form != y->form) return c->fail(MPSK_EINTERNAL, "tensors are stored in different forms");
+  return MPSK_OK;
+}
+
+int32_t mpsk_dot(mpsk_ctx* ctx, const mpsk_tensor* xh, const mpsk_tensor* yh, double* re, double* im) {
+  Ctx* c = CTX(ctx); const Tensor* x = CTEN(xh); const Tensor* y = CTEN(yh);
+  MPSK_TRY(check_pair(c, x, y));
+  double* d = (double*)c->alloc(4 * sizeof(double));
+  const void* V[1] = {x->d};
+  int st = vec_multidot(c, x->dtype == MPSK_C128, 1, V, y->d, x->nelem, d);
+  double h[2] = {0, 0};
+  if (st == MPSK_OK) { cudaMemcpyAsync(h, d, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream); cudaStreamSynchronize(c->stream); }
+  c->free(d);
+  if (re) *re = h[0];
+  if (im) *im = h[1];
+  return st;
+}
+
+int32_t mpsk_norm(mpsk_ctx* ctx, const mpsk_tensor* x, double* out) {
+  double re = 0, im = 0;
+  MPSK_TRY(mpsk_dot(ctx, x, x, &re, &im));
+  *out = std::sqrt(re);
+  return MPSK_OK;
+}
+
+int32_t mpsk_axpy(mpsk_ctx* ctx, double ar, double ai, const mpsk_tensor* xh, mpsk_tensor* yh) {
+  Ctx* c = CTX(ctx); const Tensor* x = CTEN(xh); Tensor* y = TEN(yh);
+  MPSK_TRY(check_pair(c, x, y));
+  if (x->dtype == MPSK_F64 && ai != 0.0) return c->fail(MPSK_EINVAL, "complex coefficient on a real tensor");
+  return vec_axpy(c, x->dtype == MPSK_C128, cplx(ar, ai), x->d, y->d, x->nelem);
+}
+
+int32_t mpsk_scale(mpsk_ctx* ctx, double ar, double ai, mpsk_tensor* xh) {
+  Ctx* c = CTX(ctx); Tensor* x = TEN(xh);
+  if (x->dtype == MPSK_F64 && ai != 0.0) return c->fail(MPSK_EINVAL, "complex coefficient on a real tensor");
+  return vec_scale(c, x->dtype == MPSK_C128, x->d, x->nelem, cplx(ar, ai));
+}
+
+// ------------------------------------------------------------------------------------------ MPO slices
+int32_t mpsk_mposlice_create(mpsk_ctx* ctx, int32_t odim, const int32_t* cl, const int32_t* cr, int32_t d, const int32_t* pch,
+                             const int32_t* kind, const double* scal, const double* ops, mpsk_mposlice** out) {
+  Ctx* c = CTX(ctx);
+  if (odim <= 0 || d <= 0) return c->fail(MPSK_EINVAL, "bad slice dimensions");
+  std::unique_ptr<MpoSlice> s(new MpoSlice);
+  s->odim = odim; s->d = d;
+  s->cl.assign(cl, cl + odim); s->cr.assign(cr, cr + odim); s->pch.assign(pch, pch + d);
+  s->kind.assign(kind, kind + odim * odim);
+  s->scal.assign((size_t)odim * odim, cplx(0.0)); s->ops.resize((size_t)odim * odim);
+  size_t nop = 0;
+  for (int i = 0; i < odim; ++i) for (int j = 0; j < odim; ++j) {
+    const int k = kind[i * odim + j];
+    if (k < 0 || k > 2) return c->fail(MPSK_EINVAL, "bad entry kind");
+    if (k == 1) {
+      s->scal[i * odim + j] = cplx(scal[2 * (i * odim + j)], scal[2 * (i * odim + j) + 1]);
+      if (cl[i] != cr[j]) return c->fail(MPSK_ESPACE, "scalar entry (%d,%d) connects levels of different charge", i, j);
+    } else if (k == 2) {
+      std::vector<cplx>& o = s->ops[i * odim + j];
+      o.resize((size_t)d * d);
+      for (int e = 0; e < d * d; ++e) o[e] = cplx(ops[2 * (nop * d * d + e)], ops[2 * (nop * d * d + e) + 1]);
+      for (int a = 0; a < d; ++a) for (int b = 0; b < d; ++b)
+        if (o[a * d + b] != cplx(0.0) && cr[j] != cl[i] + pch[a] - pch[b])
+          return c->fail(MPSK_ESPACE, "operator entry (%d,%d) element (%d,%d) violates charge conservation", i, j, a, b);
+      ++nop;
+    }
+  }
+  *out = reinterpret_cast<mpsk_mposlice*>(s.release());
+  return MPSK_OK;
+}
+
+void mpsk_mposlice_free(mpsk_ctx*, mpsk_mposlice* s) { delete reinterpret_cast<MpoSlice*>(s); }
+
+int32_t mpsk_mposlice_keys(const mpsk_mposlice* sh, int32_t* count, int32_t* ij) {
+  const MpoSlice* s = SLICE(sh);
+  int n = 0;
+  for (int j = 0; j < s->odim; ++j) for (int i = 0; i < s->odim; ++i) {   // product(1:odim,1:odim): first index fastest
+    if (!s->kind[i * s->odim + j]) continue;
+    if (ij) { ij[2 * n] = i; ij[2 * n + 1] = j; }
+    ++n;
+  }
+  if (count) *count = n;
+  return MPSK_OK;
+}
+
+// ------------------------------------------------------------------------------------------ operators
+int32_t mpsk_op_create(mpsk_ctx* ctx, int32_t kind, const mpsk_mposlice* h1, const mpsk_mposlice* h2, const mpsk_tensor* GL,
+                       const mpsk_tensor* GR, const mpsk_tensor* x_like, mpsk_op** out) {
+  HeffOp* op = nullptr;
+  MPSK_TRY(heff_create(CTX(ctx), kind, SLICE(h1), SLICE(h2), CTEN(GL), CTEN(GR), CTEN(x_like), &op));
+  *out = reinterpret_cast<mpsk_op*>(op);
+  return MPSK_OK;
+}
+void mpsk_op_free(mpsk_ctx*, mpsk_op* op) { delete reinterpret_cast<HeffOp*>(op); }
+double mpsk_op_flops(const mpsk_op* op) { return reinterpret_cast<const HeffOp*>(op)->flops; }
+
+static int as_kl(Ctx* c, const Tensor* t) { return t->form == F_KL ? MPSK_OK : c->fail(MPSK_EINTERNAL, "tensor is not in vector (KL) form"); }
+
+int32_t mpsk_op_apply(mpsk_ctx* ctx, const mpsk_op* op, const mpsk_tensor* x, mpsk_tensor* y) {
+  MPSK_TRY(as_kl(CTX(ctx), CTEN(x))); MPSK_TRY(as_kl(CTX(ctx), CTEN(y)));
+  return heff_apply(CTX(ctx), const_cast<HeffOp*>(reinterpret_cast<const HeffOp*>(op)), CTEN(x), TEN(y));
+}
+
+int32_t mpsk_eigsolve(mpsk_ctx* ctx, const mpsk_op* op, const mpsk_tensor* x0, int32_t which, int32_t hermitian, int32_t krylovdim,
+                      int32_t maxiter, double tol, double* val_re, double* val_im, mpsk_tensor* vec, mpsk_info* info) {
+  Ctx* c = CTX(ctx);
+  MPSK_TRY(as_kl(c, CTEN(x0))); MPSK_TRY(as_kl(c, CTEN(vec)));
+  cplx v = 0;
+  HeffOp* h = const_cast<HeffOp*>(reinterpret_cast<const HeffOp*>(op));
+  int st = hermitian ? eigsolve_lanczos(c, h, CTEN(x0), which, krylovdim, maxiter, tol, &v, TEN(vec), info)
+                     : eigsolve_arnoldi(c, h, CTEN(x0), which, krylovdim, maxiter, tol, &v, TEN(vec), info);
+  if (val_re) *val_re = v.real();
+  if (val_im) *val_im = v.imag();
+  return st;
+}
+
+int32_t mpsk_expv(mpsk_ctx* ctx, const mpsk_op* op, double tr, double ti, const mpsk_tensor* y0, int32_t krylovdim, int32_t maxiter,
+                  double tol, mpsk_tensor* y, mpsk_info* info) {
+  Ctx* c = CTX(ctx);
+  MPSK_TRY(as_kl(c, CTEN(y0))); MPSK_TRY(as_kl(c, CTEN(y)));
+  return expv_lanczos(c, const_cast<HeffOp*>(reinterpret_cast<const HeffOp*>(op)), cplx(tr, ti), CTEN(y0), krylovdim, maxiter, tol, TEN(y), info);
+}
+
+// ------------------------------------------------------------------------------------------ transfers / local algebra
+static int to_kl(Ctx* c, Tensor* t, mpsk_tensor** out) {
+  // every tensor leaving the library is in KL (vector) form
+  if (t->form == F_KL) { *out = reinterpret_cast<mpsk_tensor*>(t); return MPSK_OK; }
+  Tensor* n = nullptr;
+  int st = tensor_repack(c, t, F_KL, false, &n);
+  delete t;
+  if (st != MPSK_OK) return st;
+  *out = reinterpret_cast<mpsk_tensor*>(n);
+  return MPSK_OK;
+}
+
+int32_t mpsk_transfer_left(mpsk_ctx* ctx, const mpsk_mposlice* h, const mpsk_tensor* A, const mpsk_tensor* Abar, const mpsk_tensor* GL,
+                           mpsk_tensor** out) {
+  Tensor* o = nullptr;
+  MPSK_TRY(transfer_left(CTX(ctx), SLICE(h), CTEN(A), CTEN(Abar), CTEN(GL), &o));
+  *out = reinterpret_cast<mpsk_tensor*>(o);   // stays in KR form: that is what op_create / the next transfer consume
+  return MPSK_OK;
+}
+int32_t mpsk_transfer_right(mpsk_ctx* ctx, const mpsk_mposlice* h, const mpsk_tensor* A, const mpsk_tensor* Abar, const mpsk_tensor* GR,
+                            mpsk_tensor** out) {
+  Tensor* o = nullptr;
+  MPSK_TRY(transfer_right(CTX(ctx), SLICE(h), CTEN(A), CTEN(Abar), CTEN(GR), &o));
+  *out = reinterpret_cast<mpsk_tensor*>(o);
+  return MPSK_OK;
+}
+int32_t mpsk_contract_ac2(mpsk_ctx* ctx, const mpsk_tensor* A1, const mpsk_tensor* A2, mpsk_tensor** out) {
+  Tensor* o = nullptr;
+  MPSK_TRY(contract_ac2(CTX(ctx), CTEN(A1), CTEN(A2), &o));
+  return to_kl(CTX(ctx), o, out);
+}
+int32_t mpsk_mul_bond_right(mpsk_ctx* ctx, const mpsk_tensor* A, const mpsk_tensor* C, mpsk_tensor** out) {
+  Tensor* o = nullptr;
+  MPSK_TRY(mul_bond_right(CTX(ctx), CTEN(A), CTEN(C), &o));
+  return to_kl(CTX(ctx), o, out);
+}
+int32_t mpsk_mul_bond_left(mpsk_ctx* ctx, const mpsk_tensor* C, const mpsk_tensor* A, mpsk_tensor** out) {
+  Tensor* o = nullptr;
+  MPSK_TRY(mul_bond_left(CTX(ctx), CTEN(C), CTEN(A), &o));
+  return to_kl(CTX(ctx), o, out);
+}
+
+int32_t mpsk_tsvd(mpsk_ctx* ctx, const mpsk_tensor* ac2, int32_t d1, const int32_t* p1_charge, mpsk_trunc trunc, mpsk_tensor** U,
+                  mpsk_tensor** S, mpsk_tensor** Vh, double* eps) {
+  Tensor *u = nullptr, *s = nullptr, *v = nullptr;
+  MPSK_TRY(tsvd(CTX(ctx), CTEN(ac2), d1, p1_charge, trunc, &u, &s, &v, eps));
+  *U = reinterpret_cast<mpsk_tensor*>(u); *S = reinterpret_cast<mpsk_tensor*>(s); *Vh = reinterpret_cast<mpsk_tensor*>(v);
+  return MPSK_OK;
+}
+
+int32_t mpsk_tsvd_spectrum(mpsk_ctx* ctx, int32_t* nsec, int32_t* charge, int32_t* count, int32_t* kept, double* values) {
+  const TsvdSpectrum& sp = CTX(ctx)->last_spectrum;
+  if (nsec) *nsec = (int32_t)sp.charge.size();
+  for (size_t i = 0; i < sp.charge.size(); ++i) { if (charge) charge[i] = sp.charge[i]; if (count) count[i] = sp.count[i]; if (kept) kept[i] = sp.kept[i]; }
+  if (values) std::copy(sp.values.begin(), sp.values.end(), values);
+  return MPSK_OK;
+}
+
+int32_t mpsk_qrpos(mpsk_ctx* ctx, const mpsk_tensor* A, mpsk_tensor** Q, mpsk_tensor** R) {
+  Tensor *q = nullptr, *r = nullptr;
+  MPSK_TRY(qrpos(CTX(ctx), CTEN(A), true, &q, &r));
+  *Q = reinterpret_cast<mpsk_tensor*>(q); *R = reinterpret_cast<mpsk_tensor*>(r);
+  return MPSK_OK;
+}
+int32_t mpsk_lqpos(mpsk_ctx* ctx, const mpsk_tensor* A, mpsk_tensor** L, mpsk_tensor** Q) {
+  Tensor *q = nullptr, *l = nullptr;
+  MPSK_TRY(qrpos(CTX(ctx), CTEN(A), false, &q, &l));
+  *Q = reinterpret_cast<mpsk_tensor*>(q); *L = reinterpret_cast<mpsk_tensor*>(l);
+  return MPSK_OK;
+}
+
+// ------------------------------------------------------------------------------------------ NCCL (loaded lazily; one process per GPU)
+typedef struct { char internal[128]; } nccl_uid_t;
+typedef int (*pfn_ncclGetUniqueId)(nccl_uid_t*);
+typedef int (*pfn_ncclCommInitRank)(void**, int, nccl_uid_t, int);
+typedef int (*pfn_ncclAllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+static void* nccl_lib() {
+  static void* lib = nullptr;
+  if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  return lib;
+}
+
+int32_t mpsk_comm_unique_id(uint8_t out128[128]) {
+  void* lib = nccl_lib();
+  if (!lib) return MPSK_ECUDA;
+  pfn_ncclGetUniqueId f = (pfn_ncclGetUniqueId)dlsym(lib, "ncclGetUniqueId");
+  nccl_uid_t id;
+  if (!f || f(&id) != 0) return MPSK_ECUDA;
+  memcpy(out128, id.internal, 128);
+  return MPSK_OK;
+}
+
+int32_t mpsk_comm_init(mpsk_ctx* ctx, const uint8_t id128[128], int32_t rank, int32_t nranks) {
+  Ctx* c = CTX(ctx);
+  void* lib = nccl_lib();
+  if (!lib) return c->fail(MPSK_ECUDA, "libnccl.so.2 not found: %s", dlerror());
+  pfn_ncclCommInitRank f = (pfn_ncclCommInitRank)dlsym(lib, "ncclCommInitRank");
+  if (!f) return c->fail(MPSK_ECUDA, "ncclCommInitRank not found");
+  nccl_uid_t id; memcpy(id.internal, id128, 128);
+  void* comm = nullptr;
+  int r = f(&comm, nranks, id, rank);
+  if (r != 0) return c->fail(MPSK_ECUDA, "ncclCommInitRank failed (%d)", r);
+  c->nccl = comm; c->rank = rank; c->nranks = nranks;
+  return MPSK_OK;
+}
+
+int32_t mpsk_allreduce_sum(mpsk_ctx* ctx, mpsk_tensor* xh) {
+  Ctx* c = CTX(ctx); Tensor* x = TEN(xh);
+  if (c->nranks <= 1) return MPSK_OK;
+  pfn_ncclAllReduce f = (pfn_ncclAllReduce)dlsym(nccl_lib(), "ncclAllReduce");
+  if (!f || !c->nccl) return c->fail(MPSK_ECUDA, "communicator not initialised");
+  const size_t count = (size_t)x->nelem * (x->dtype == MPSK_C128 ? 2 : 1);
+  int r = f(x->d, x->d, count, /*ncclDouble*/ 8, /*ncclSum*/ 0, c->nccl, c->stream);
+  if (r != 0) return c->fail(MPSK_ECUDA, "ncclAllReduce failed (%d)", r);
+  c->launches++;
+  return MPSK_OK;
+}
+
+}  // extern "C"

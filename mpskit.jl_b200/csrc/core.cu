@@ -1,0 +1,367 @@
+// Context, allocator, tensor layouts, strided block copies and the "mix" kernel.
+#include "internal.h"
+
+namespace mpsk {
+
+// ------------------------------------------------------------------------------------------ context
+int Ctx::fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+  err = buf;
+  return code;
+}
+
+static size_t round_size(size_t b) {
+  if (b < 512) return 512;
+  if (b < (1u << 20)) return (b + 511) / 512 * 512;
+  return (b + (1u << 20) - 1) / (1u << 20) * (1u << 20);
+}
+
+void* Ctx::alloc(size_t bytes) {
+  size_t sz = round_size(bytes);
+  auto it = freelist.lower_bound(sz);
+  if (it != freelist.end() && it->first <= sz + sz / 4 + (1u << 20)) {
+    void* p = it->second; size_t got = it->first;
+    freelist.erase(it);
+    bytes_cached -= got; bytes_in_use += got; sizes[p] = got;
+    return p;
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, sz);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    release_cache();
+    e = cudaMalloc(&p, sz);
+    if (e != cudaSuccess) { cudaGetLastError(); fail(MPSK_ENOMEM, "cudaMalloc(%zu) failed", sz); return nullptr; }
+  }
+  sizes[p] = sz; bytes_in_use += sz;
+  return p;
+}
+
+void Ctx::free(void* p) {
+  if (!p) return;
+  auto it = sizes.find(p);
+  if (it == sizes.end()) return;
+  size_t sz = it->second;
+  sizes.erase(it);
+  bytes_in_use -= sz; bytes_cached += sz;
+  freelist.emplace(sz, p);
+  if (bytes_cached > (int64_t)48 << 30) release_cache();
+}
+
+void Ctx::release_cache() {
+  cudaStreamSynchronize(stream);
+  for (auto& kv : freelist) cudaFree(kv.second);
+  freelist.clear(); bytes_cached = 0;
+}
+
+int space_from_abi(Ctx* ctx, const mpsk_space* s, Space* out) {
+  if (!s || s->nsec < 0) return ctx->fail(MPSK_EINVAL, "null space");
+  out->q.assign(s->charge, s->charge + s->nsec);
+  out->n.assign(s->dim, s->dim + s->nsec);
+  out->mod = s->modulus;
+  for (int i = 0; i < s->nsec; ++i) {
+    if (out->n[i] <= 0) return ctx->fail(MPSK_ESPACE, "sector %d has non-positive dimension", i);
+    if (i && out->q[i] <= out->q[i - 1]) return ctx->fail(MPSK_ESPACE, "sectors must be listed in strictly ascending charge");
+    if (out->mod && (out->q[i] < 0 || out->q[i] >= out->mod)) return ctx->fail(MPSK_ESPACE, "Z_N charge out of range");
+  }
+  return MPSK_OK;
+}
+
+// ------------------------------------------------------------------------------------------ layouts
+static void build_layout(Tensor* t) {
+  const int nl = t->Vl.nsec(), nr = t->Vr.nsec(), nm = t->nm();
+  t->blks.clear();
+  t->blk_index.assign((size_t)nm * nl, -1);
+  for (int m = 0; m < nm; ++m)
+    for (int jl = 0; jl < nl; ++jl) {
+      int jr = t->Vr.find((int64_t)t->Vl.q[jl] + t->mch[m]);
+      if (jr < 0) continue;
+      t->blk_index[(size_t)m * nl + jl] = (int)t->blks.size();
+      t->blks.push_back(Blk{m, jl, jr, 0, 0, 0});
+    }
+  const bool by_l = (t->form == F_KL || t->form == F_SR);
+  const bool kform = (t->form == F_KL || t->form == F_KR);
+  const int ng = by_l ? nl : nr;
+  t->groups.assign(ng, Group{0, 0, 0, 0});
+  t->seg.assign((size_t)nm * ng, -1);
+  int64_t off = 0;
+  for (int g = 0; g < ng; ++g) {
+    Group& G = t->groups[g];
+    const int64_t ngdim = by_l ? t->Vl.n[g] : t->Vr.n[g];
+    int64_t run = 0;
+    for (int m = 0; m < nm; ++m) {
+      int jl, jr;
+      if (by_l) { jl = g; jr = t->Vr.find((int64_t)t->Vl.q[g] + t->mch[m]); }
+      else { jr = g; jl = t->Vl.find((int64_t)t->Vr.q[g] - t->mch[m]); }
+      if (jl < 0 || jr < 0) continue;
+      const int64_t other = by_l ? t->Vr.n[jr] : t->Vl.n[jl];
+      t->seg[(size_t)m * ng + g] = run;
+      run += kform ? other : pad(other);
+    }
+    if (kform) { G.rows = run; G.cols = ngdim; G.ld = pad(ngdim); }
+    else { G.rows = ngdim; G.cols = run; G.ld = pad(run); }
+    G.off = off;
+    off += padg(G.rows * G.ld);
+  }
+  t->nelem = std::max<int64_t>(off, GROUP_ALIGN);
+  for (Blk& b : t->blks) {
+    const int g = by_l ? b.jl : b.jr;
+    const Group& G = t->groups[g];
+    const int64_t s = t->seg[(size_t)b.m * ng + g];
+    switch (t->form) {
+      case F_KL: b.off = G.off + s * G.ld; b.sl = 1; b.sr = G.ld; break;
+      case F_KR: b.off = G.off + s * G.ld; b.sl = G.ld; b.sr = 1; break;
+      case F_SL: b.off = G.off + s; b.sl = 1; b.sr = G.ld; break;
+      case F_SR: b.off = G.off + s; b.sl = G.ld; b.sr = 1; break;
+    }
+  }
+}
+
+int tensor_create(Ctx* ctx, const Space& Vl, const std::vector<int32_t>& mch, const Space& Vr, int dtype, Form form,
+                  bool zero, Tensor** out) {
+  if (Vl.mod != Vr.mod) return ctx->fail(MPSK_ESPACE, "bond spaces belong to different groups");
+  std::unique_ptr<Tensor> t(new Tensor);
+  t->ctx = ctx; t->Vl = Vl; t->Vr = Vr; t->mch = mch; t->dtype = dtype; t->form = form;
+  build_layout(t.get());
+  t->d = ctx->alloc(t->bytes());
+  if (!t->d) return MPSK_ENOMEM;
+  if (zero) CUDA_TRY(ctx, cudaMemsetAsync(t->d, 0, t->bytes(), ctx->stream));
+  *out = t.release();
+  return MPSK_OK;
+}
+
+// ------------------------------------------------------------------------------------------ strided copy
+struct CopyTile { int32_t task, l0, r0, pad; };
+
+template <typename T> __device__ __forceinline__ T conj_if(T v, int) { return v; }
+template <> __device__ __forceinline__ double2 conj_if<double2>(double2 v, int c) { if (c) v.y = -v.y; return v; }
+__device__ __forceinline__ double scale_val(double v, double s) { return v * s; }
+__device__ __forceinline__ double2 scale_val(double2 v, double s) { return make_double2(v.x * s, v.y * s); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) copy_kernel(const CopyTask* __restrict__ tasks, const CopyTile* __restrict__ tiles, int ntiles) {
+  __shared__ T tile[32][33];   // [r][l]
+  for (int ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
+    const CopyTile tl = tiles[ti];
+    const CopyTask tk = tasks[tl.task];
+    const T* src = (const T*)tk.src;
+    T* dst = (T*)tk.dst;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    // read: fast thread index along the contiguous source axis
+    if (tk.ssl <= tk.ssr) {
+      const int l = tl.l0 + tx;
+#pragma unroll
+      for (int rr = ty; rr < 32; rr += 8) {
+        const int r = tl.r0 + rr;
+        if (l < tk.nl && r < tk.nr) tile[rr][tx] = src[l * tk.ssl + r * tk.ssr];
+      }
+    } else {
+      const int r = tl.r0 + tx;
+#pragma unroll
+      for (int ll = ty; ll < 32; ll += 8) {
+        const int l = tl.l0 + ll;
+        if (l < tk.nl && r < tk.nr) tile[tx][ll] = src[l * tk.ssl + r * tk.ssr];
+      }
+    }
+    __syncthreads();
+    if (tk.dsl <= tk.dsr) {
+      const int l = tl.l0 + tx;
+#pragma unroll
+      for (int rr = ty; rr < 32; rr += 8) {
+        const int r = tl.r0 + rr;
+        if (l < tk.nl && r < tk.nr) {
+          T v = conj_if<T>(tile[rr][tx], tk.conj);
+          if (tk.scale_axis == 1) v = scale_val(v, tk.scale[l]);
+          else if (tk.scale_axis == 2) v = scale_val(v, tk.scale[r]);
+          dst[l * tk.dsl + r * tk.dsr] = v;
+        }
+      }
+    } else {
+      const int r = tl.r0 + tx;
+#pragma unroll
+      for (int ll = ty; ll < 32; ll += 8) {
+        const int l = tl.l0 + ll;
+        if (l < tk.nl && r < tk.nr) {
+          T v = conj_if<T>(tile[tx][ll], tk.conj);
+          if (tk.scale_axis == 1) v = scale_val(v, tk.scale[l]);
+          else if (tk.scale_axis == 2) v = scale_val(v, tk.scale[r]);
+          dst[l * tk.dsl + r * tk.dsr] = v;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+int run_copy_tasks(Ctx* ctx, const std::vector<CopyTask>& tasks, bool cplx) {
+  if (tasks.empty()) return MPSK_OK;
+  std::vector<CopyTile> tiles;
+  for (size_t i = 0; i < tasks.size(); ++i)
+    for (int r0 = 0; r0 < tasks[i].nr; r0 += 32)
+      for (int l0 = 0; l0 < tasks[i].nl; l0 += 32) tiles.push_back(CopyTile{(int)i, l0, r0, 0});
+  if (tiles.empty()) return MPSK_OK;
+  CopyTask* d_tasks = (CopyTask*)ctx->alloc(tasks.size() * sizeof(CopyTask));
+  CopyTile* d_tiles = (CopyTile*)ctx->alloc(tiles.size() * sizeof(CopyTile));
+  if (!d_tasks || !d_tiles) return MPSK_ENOMEM;
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_tasks, tasks.data(), tasks.size() * sizeof(CopyTask), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(CopyTile), cudaMemcpyHostToDevice, ctx->stream));
+  const int grid = (int)std::min<size_t>(tiles.size(), (size_t)ctx->num_sms * 8);
+  if (cplx) copy_kernel<double2><<<grid, 256, 0, ctx->stream>>>(d_tasks, d_tiles, (int)tiles.size());
+  else copy_kernel<double><<<grid, 256, 0, ctx->stream>>>(d_tasks, d_tiles, (int)tiles.size());
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // the host vectors are pageable: make sure the copies are done
+  ctx->free(d_tasks); ctx->free(d_tiles);
+  return MPSK_OK;
+}
+
+int tensor_repack(Ctx* ctx, const Tensor* src, Form form, bool conj, Tensor** out) {
+  Tensor* t = nullptr;
+  MPSK_TRY(tensor_create(ctx, src->Vl, src->mch, src->Vr, src->dtype, form, true, &t));
+  std::vector<CopyTask> tasks;
+  for (size_t b = 0; b < src->blks.size(); ++b) {
+    const Blk& s = src->blks[b];
+    const Blk& d = t->blks[b];
+    tasks.push_back(CopyTask{src->ptr(s.off), t->ptr(d.off), s.sl, s.sr, d.sl, d.sr, (int32_t)src->Vl.n[s.jl],
+                             (int32_t)src->Vr.n[s.jr], conj && src->dtype == MPSK_C128 ? 1 : 0, 0, nullptr});
+  }
+  int st = run_copy_tasks(ctx, tasks, src->dtype == MPSK_C128);
+  if (st != MPSK_OK) { delete t; return st; }
+  *out = t;
+  return MPSK_OK;
+}
+
+int tensor_as_form(Ctx* ctx, const Tensor* src, Form form, bool conj, const Tensor** out, bool* owned) {
+  if (src->form == form && !(conj && src->dtype == MPSK_C128)) { *out = src; *owned = false; return MPSK_OK; }
+  Tensor* t = nullptr;
+  MPSK_TRY(tensor_repack(ctx, src, form, conj, &t));
+  *out = t; *owned = true;
+  return MPSK_OK;
+}
+
+// ------------------------------------------------------------------------------------------ random fill
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__device__ __forceinline__ double u01(uint64_t h) { return ((h >> 11) + 0.5) * (1.0 / 9007199254740992.0); }
+
+struct FillTask { void* dst; int64_t sl, sr; int32_t nl, nr; uint64_t base; };
+
+// uniform(-1,1) entries inside the logical blocks only (padding stays zero); value depends on (seed, block, i, j) only
+template <bool CPLX>
+__global__ void fill_kernel(const FillTask* __restrict__ tasks, int ntasks, uint64_t seed) {
+  for (int t = blockIdx.y; t < ntasks; t += gridDim.y) {
+    const FillTask tk = tasks[t];
+    const int64_t total = (int64_t)tk.nl * tk.nr;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t il = e / tk.nr, ir = e - il * tk.nr;
+      const uint64_t h = splitmix64(seed ^ splitmix64(tk.base + (uint64_t)e));
+      if (CPLX) {
+        double2 v = make_double2(2.0 * u01(h) - 1.0, 2.0 * u01(splitmix64(h)) - 1.0);
+        ((double2*)tk.dst)[il * tk.sl + ir * tk.sr] = v;
+      } else {
+        ((double*)tk.dst)[il * tk.sl + ir * tk.sr] = 2.0 * u01(h) - 1.0;
+      }
+    }
+  }
+}
+
+int tensor_fill_random(Ctx* ctx, Tensor* t, uint64_t seed) {
+  std::vector<FillTask> tasks;
+  uint64_t base = 0;
+  for (const Blk& b : t->blks) {
+    tasks.push_back(FillTask{t->ptr(b.off), b.sl, b.sr, (int32_t)t->Vl.n[b.jl], (int32_t)t->Vr.n[b.jr], base});
+    base += (uint64_t)t->Vl.n[b.jl] * t->Vr.n[b.jr];
+  }
+  if (tasks.empty()) return MPSK_OK;
+  FillTask* d = (FillTask*)ctx->alloc(tasks.size() * sizeof(FillTask));
+  if (!d) return MPSK_ENOMEM;
+  CUDA_TRY(ctx, cudaMemcpyAsync(d, tasks.data(), tasks.size() * sizeof(FillTask), cudaMemcpyHostToDevice, ctx->stream));
+  dim3 grid(64, (unsigned)std::min<size_t>(tasks.size(), 1024));
+  if (t->dtype == MPSK_C128) fill_kernel<true><<<grid, 256, 0, ctx->stream>>>(d, (int)tasks.size(), seed);
+  else fill_kernel<false><<<grid, 256, 0, ctx->stream>>>(d, (int)tasks.size(), seed);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->free(d);
+  return MPSK_OK;
+}
+
+// ------------------------------------------------------------------------------------------ mix
+struct MixTile { int32_t task; int32_t pad; int64_t e0; };
+constexpr int MIX_CHUNK = 4096;
+
+template <typename T> __device__ __forceinline__ T mix_zero();
+template <> __device__ __forceinline__ double mix_zero<double>() { return 0.0; }
+template <> __device__ __forceinline__ double2 mix_zero<double2>() { return make_double2(0.0, 0.0); }
+__device__ __forceinline__ void mix_fma(double& acc, double v, double cre, double) { acc += cre * v; }
+__device__ __forceinline__ void mix_fma(double2& acc, double2 v, double cre, double cim) {
+  acc.x += cre * v.x - cim * v.y; acc.y += cre * v.y + cim * v.x;
+}
+
+// out[row, col] = sum_t coeff_t * src_t[row, col]; memory-bound streaming, coalesced along col.
+template <typename T>
+__global__ void __launch_bounds__(256) mix_kernel(const MixTask* __restrict__ tasks, const MixTerm* __restrict__ terms,
+                                                  const MixTile* __restrict__ tiles, int ntiles) {
+  for (int ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
+    const MixTile tl = tiles[ti];
+    const MixTask tk = tasks[tl.task];
+    const int64_t total = (int64_t)tk.rows * tk.cols;
+    const int64_t e1 = min(tl.e0 + (int64_t)MIX_CHUNK, total);
+    T* dst = (T*)tk.dst;
+    for (int64_t e = tl.e0 + threadIdx.x; e < e1; e += blockDim.x) {
+      const int row = (int)(e / tk.cols), col = (int)(e - (int64_t)row * tk.cols);
+      T acc = mix_zero<T>();
+      for (int t = tk.term_begin; t < tk.term_end; ++t) {
+        const MixTerm tm = terms[t];
+        mix_fma(acc, ((const T*)tm.src)[(int64_t)row * tm.lds + col], tm.cre, tm.cim);
+      }
+      dst[(int64_t)row * tk.ldd + col] = acc;
+    }
+  }
+}
+
+MixPlan::~MixPlan() {
+  if (ctx) { ctx->free(d_tasks); ctx->free(d_terms); ctx->free(d_tiles); }
+}
+
+int mix_plan_build(Ctx* ctx, bool cplx, const std::vector<MixTask>& tasks, const std::vector<MixTerm>& terms, MixPlan* plan) {
+  plan->ctx = ctx; plan->cplx = cplx; plan->ntiles = 0; plan->bytes = 0;
+  std::vector<MixTile> tiles;
+  const double es = cplx ? 16.0 : 8.0;
+  for (size_t i = 0; i < tasks.size(); ++i) {
+    const int64_t total = (int64_t)tasks[i].rows * tasks[i].cols;
+    for (int64_t e0 = 0; e0 < total; e0 += MIX_CHUNK) tiles.push_back(MixTile{(int)i, 0, e0});
+    plan->bytes += es * total * (1 + tasks[i].term_end - tasks[i].term_begin);
+  }
+  plan->ntiles = (int)tiles.size();
+  if (tiles.empty()) return MPSK_OK;
+  plan->d_tasks = ctx->alloc(tasks.size() * sizeof(MixTask));
+  plan->d_terms = ctx->alloc(std::max<size_t>(terms.size(), 1) * sizeof(MixTerm));
+  plan->d_tiles = ctx->alloc(tiles.size() * sizeof(MixTile));
+  if (!plan->d_tasks || !plan->d_terms || !plan->d_tiles) return MPSK_ENOMEM;
+  CUDA_TRY(ctx, cudaMemcpyAsync(plan->d_tasks, tasks.data(), tasks.size() * sizeof(MixTask), cudaMemcpyHostToDevice, ctx->stream));
+  if (!terms.empty())
+    CUDA_TRY(ctx, cudaMemcpyAsync(plan->d_terms, terms.data(), terms.size() * sizeof(MixTerm), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(plan->d_tiles, tiles.data(), tiles.size() * sizeof(MixTile), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return MPSK_OK;
+}
+
+int mix_plan_run(Ctx* ctx, const MixPlan* plan) {
+  if (plan->ntiles == 0) return MPSK_OK;
+  const int grid = std::min(plan->ntiles, ctx->num_sms * 8);
+  if (plan->cplx)
+    mix_kernel<double2><<<grid, 256, 0, ctx->stream>>>((const MixTask*)plan->d_tasks, (const MixTerm*)plan->d_terms,
+                                                        (const MixTile*)plan->d_tiles, plan->ntiles);
+  else
+    mix_kernel<double><<<grid, 256, 0, ctx->stream>>>((const MixTask*)plan->d_tasks, (const MixTerm*)plan->d_terms,
+                                                       (const MixTile*)plan->d_tiles, plan->ntiles);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return MPSK_OK;
+}
+
+}  // namespace mpsk

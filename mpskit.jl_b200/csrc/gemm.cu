@@ -1,0 +1,359 @@
+#include "gemm.cuh"
+#include "internal.h"
+
+namespace mpsk {
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1},{%2},{%3},{%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// ------------------------------------------------------------------------------------------ kernel
+// 8 DMMA warps, 256 threads, one persistent CTA per SM: CTA b handles tiles b, b+grid, ...
+// Shared ring: per stage NSUB sub-tiles per operand, each sub-tile [rows][64 B] dense so that the
+// LDS.128 fragment loads (lane (g,t): row g, 16-byte chunk t) are bank-conflict free.
+// Lane 0 of warp 0 doubles as the TMA producer: before consuming k-block `it` it refills the stage
+// that was consumed at `it-1` with k-block `it+STAGES-1` (the flat k-block sequence runs across tile
+// boundaries, so the pipeline never drains between tiles).  A dedicated producer warp would cost a
+// whole extra register-allocation granule (4 warps) and cap the DMMA warps at 168 registers.
+template <bool CPLX>
+struct LoadCursor {
+  int tile, k0;
+  const GemmProblemDev* p;
+  int m0, n0, K;
+  __device__ __forceinline__ void open(const GemmProblemDev* probs, const GemmTile* tiles, int ntiles) {
+    if (tile < ntiles) {
+      const GemmTile t = tiles[tile];
+      p = &probs[t.prob]; m0 = t.m0; n0 = t.n0; K = p->K; k0 = 0;
+      asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(&p->tmA) : "memory");
+      asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(&p->tmB) : "memory");
+    }
+  }
+};
+
+template <bool CPLX>
+__global__ void __launch_bounds__(256, 1)
+gemm_dmma_kernel(const GemmProblemDev* __restrict__ probs, const GemmTile* __restrict__ tiles, int ntiles) {
+  using Cfg = GemmCfg<CPLX>;
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, KSUB = Cfg::KSUB, NSUB = Cfg::NSUB, STAGES = Cfg::STAGES;
+  constexpr int KSTAGE = KSUB * NSUB;                       // elements of K per stage
+  constexpr int A_SUB_BYTES = BM * 64, B_SUB_BYTES = BN * 64;
+  constexpr int STAGE_BYTES = NSUB * (A_SUB_BYTES + B_SUB_BYTES);
+  constexpr int WM = CPLX ? 32 : 64, WN = 32;               // warp tile
+  constexpr int MI = WM / 8, NI = WN / 8;
+  constexpr int WARPS_M = BM / WM;                          // 4 (cplx) / 2 (real)
+  constexpr int DPE = CPLX ? 2 : 1;                         // doubles per element
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+  uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const bool producer = (threadIdx.x == 0);
+  LoadCursor<CPLX> cur;
+  int pstage = 0; uint32_t pphase = 0;
+  cur.tile = blockIdx.x; cur.k0 = 0; cur.p = nullptr; cur.m0 = cur.n0 = cur.K = 0;
+
+  auto issue_one = [&]() {
+    // producer only: load the next k-block of the flat sequence (skipping empty-K tiles) if any is left
+    while (cur.tile < ntiles && cur.k0 >= cur.K) { cur.tile += gridDim.x; cur.open(probs, tiles, ntiles); }
+    if (cur.tile >= ntiles) return;
+    mbar_wait(&empty_bar[pstage], pphase ^ 1);
+    mbar_expect_tx(&full_bar[pstage], STAGE_BYTES);
+    unsigned char* sa = smem + pstage * STAGE_BYTES;
+    unsigned char* sb = sa + NSUB * A_SUB_BYTES;
+#pragma unroll
+    for (int s = 0; s < NSUB; ++s) {
+      tma_load_2d(sa + s * A_SUB_BYTES, &cur.p->tmA, &full_bar[pstage], (cur.k0 + s * KSUB) * DPE, cur.m0);
+      tma_load_2d(sb + s * B_SUB_BYTES, &cur.p->tmB, &full_bar[pstage], (cur.k0 + s * KSUB) * DPE, cur.n0);
+    }
+    cur.k0 += KSTAGE;
+    if (++pstage == STAGES) { pstage = 0; pphase ^= 1; }
+  };
+
+  if (producer) {
+    cur.open(probs, tiles, ntiles);
+#pragma unroll 1
+    for (int s = 0; s < STAGES - 1; ++s) issue_one();
+  }
+
+  const int g = lane >> 2, t4 = lane & 3;
+  const int wm = warp % WARPS_M, wn = warp / WARPS_M;
+  int stage = 0; uint32_t phase = 0;
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const GemmTile t = tiles[tile];
+    const GemmProblemDev* p = &probs[t.prob];
+    const int K = p->K, M = p->M, N = p->N;
+
+    double acc_re[MI][NI][2];
+    double acc_im[CPLX ? MI : 1][CPLX ? NI : 1][2];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+      for (int j = 0; j < NI; ++j) {
+        acc_re[i][j][0] = 0.0; acc_re[i][j][1] = 0.0;
+        if (CPLX) { acc_im[i][j][0] = 0.0; acc_im[i][j][1] = 0.0; }
+      }
+
+#pragma unroll 1
+    for (int k0 = 0; k0 < K; k0 += KSTAGE) {
+      if (producer) issue_one();
+      __syncwarp();
+      mbar_wait(&full_bar[stage], phase);
+      const unsigned char* sa = smem + stage * STAGE_BYTES + (wm * WM + g) * 64 + t4 * 16;
+      const unsigned char* sb = smem + stage * STAGE_BYTES + NSUB * A_SUB_BYTES + (wn * WN + g) * 64 + t4 * 16;
+#pragma unroll 2
+      for (int s = 0; s < NSUB; ++s) {
+        double2 a[MI], b[NI];
+#pragma unroll
+        for (int i = 0; i < MI; ++i) a[i] = *(const double2*)(sa + s * A_SUB_BYTES + i * 8 * 64);
+#pragma unroll
+        for (int j = 0; j < NI; ++j) b[j] = *(const double2*)(sb + s * B_SUB_BYTES + j * 8 * 64);
+        if (CPLX) {
+          // (ar + i ai)(br + i bi): re += ar br - ai bi ; im += ar bi + ai br
+#pragma unroll
+          for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NI; ++j) dmma884(acc_re[i][j][0], acc_re[i][j][1], a[i].x, b[j].x);
+#pragma unroll
+          for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NI; ++j) dmma884(acc_im[i][j][0], acc_im[i][j][1], a[i].x, b[j].y);
+#pragma unroll
+          for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NI; ++j) dmma884(acc_im[i][j][0], acc_im[i][j][1], a[i].y, b[j].x);
+#pragma unroll
+          for (int i = 0; i < MI; ++i) {
+            const double nai = -a[i].y;
+#pragma unroll
+            for (int j = 0; j < NI; ++j) dmma884(acc_re[i][j][0], acc_re[i][j][1], nai, b[j].y);
+          }
+        } else {
+          // lane holds k = 2t (x) and k = 2t+1 (y) of this 8-wide sub-tile: two k4 groups {0,2,4,6},{1,3,5,7}
+#pragma unroll
+          for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NI; ++j) dmma884(acc_re[i][j][0], acc_re[i][j][1], a[i].x, b[j].x);
+#pragma unroll
+          for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NI; ++j) dmma884(acc_re[i][j][0], acc_re[i][j][1], a[i].y, b[j].y);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[stage]);
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+
+    // ------------------------------------------------------------------ epilogue (registers -> global)
+    double* C = (double*)p->C;
+    const int64_t ldc = p->ldc;
+    const bool accum = p->accumulate != 0;
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+      const int row = t.m0 + wm * WM + i * 8 + g;
+      if (row >= M) continue;
+#pragma unroll
+      for (int j = 0; j < NI; ++j) {
+        const int col = t.n0 + wn * WN + j * 8 + 2 * t4;
+        if (col >= N) continue;
+        if (CPLX) {
+          double* dst = C + ((int64_t)row * ldc + col) * 2;
+          double2 v0 = make_double2(acc_re[i][j][0], acc_im[i][j][0]);
+          double2 v1 = make_double2(acc_re[i][j][1], acc_im[i][j][1]);
+          if (accum) { double2 o = *(double2*)dst; v0.x += o.x; v0.y += o.y; }
+          *(double2*)dst = v0;
+          if (col + 1 < N) {
+            if (accum) { double2 o = *(double2*)(dst + 2); v1.x += o.x; v1.y += o.y; }
+            *(double2*)(dst + 2) = v1;
+          }
+        } else {
+          double* dst = C + (int64_t)row * ldc + col;
+          if (col + 1 < N) {
+            double2 v = make_double2(acc_re[i][j][0], acc_re[i][j][1]);
+            if (accum) { double2 o = *(double2*)dst; v.x += o.x; v.y += o.y; }
+            *(double2*)dst = v;
+          } else {
+            double v = acc_re[i][j][0];
+            if (accum) v += *dst;
+            *dst = v;
+          }
+        }
+      }
+    }
+  }
+}
+
+// Debug / cross-check kernel: one thread per output element (selected with MPSK_FLAG_DEBUG_GEMM).
+template <bool CPLX>
+__global__ void gemm_debug_kernel(const GemmProblemDev* __restrict__ probs, int nprob) {
+  for (int pi = blockIdx.y; pi < nprob; pi += gridDim.y) {
+    const GemmProblemDev p = probs[pi];
+    const int64_t total = (int64_t)p.M * p.N;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+      const int m = (int)(idx / p.N), n = (int)(idx % p.N);
+      if (CPLX) {
+        const double2* a = (const double2*)p.A + m * p.lda;
+        const double2* b = (const double2*)p.B + n * p.ldb;
+        double re = 0, im = 0;
+        for (int k = 0; k < p.K; ++k) { re += a[k].x * b[k].x - a[k].y * b[k].y; im += a[k].x * b[k].y + a[k].y * b[k].x; }
+        double2* c = (double2*)p.C + m * p.ldc + n;
+        if (p.accumulate) { re += c->x; im += c->y; }
+        *c = make_double2(re, im);
+      } else {
+        const double* a = (const double*)p.A + m * p.lda;
+        const double* b = (const double*)p.B + n * p.ldb;
+        double s = 0;
+        for (int k = 0; k < p.K; ++k) s += a[k] * b[k];
+        double* c = (double*)p.C + m * p.ldc + n;
+        if (p.accumulate) s += *c;
+        *c = s;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    cudaDriverEntryPointQueryResult q;
+    void* f = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || !f) return nullptr;
+    fn = (PFN_encodeTiled)f;
+  }
+  return fn;
+}
+
+static bool encode_map(CUtensorMap* tm, const void* base, int64_t rows, int64_t K, int64_t ld, bool cplx, int boxrows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return false;
+  const int dpe = cplx ? 2 : 1;
+  cuuint64_t gdim[2] = {(cuuint64_t)(K * dpe), (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)(ld * dpe * 8)};
+  cuuint32_t box[2] = {8u, (cuuint32_t)boxrows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <bool CPLX> static int smem_bytes() {
+  using Cfg = GemmCfg<CPLX>;
+  return Cfg::STAGES * Cfg::NSUB * (Cfg::BM + Cfg::BN) * 64 + 2 * Cfg::STAGES * 8 + 128;
+}
+
+GemmPlan::~GemmPlan() {
+  if (d_probs) ctx->free(d_probs);
+  if (d_tiles) ctx->free(d_tiles);
+}
+
+// Build the device problem table (with TMA descriptors) and the tile list.
+int gemm_plan_build(Ctx* ctx, bool cplx, const std::vector<GemmProblemHost>& probs, GemmPlan* plan) {
+  plan->ctx = ctx; plan->cplx = cplx; plan->nprob = 0; plan->ntiles = 0; plan->flops = 0;
+  const int BM = cplx ? GemmCfg<true>::BM : GemmCfg<false>::BM;
+  const int BN = cplx ? GemmCfg<true>::BN : GemmCfg<false>::BN;
+  std::vector<GemmProblemDev> dev;
+  std::vector<GemmTile> tiles;
+  // order problems by decreasing K so that the long tiles are scheduled first (tail balance)
+  std::vector<int> order;
+  for (size_t i = 0; i < probs.size(); ++i) if (probs[i].M > 0 && probs[i].N > 0) order.push_back((int)i);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return probs[a].K > probs[b].K; });
+  for (int oi : order) {
+    const GemmProblemHost& h = probs[oi];
+    GemmProblemDev d;
+    memset(&d, 0, sizeof(d));
+    d.A = h.A; d.B = h.B; d.C = h.C; d.lda = h.lda; d.ldb = h.ldb; d.ldc = h.ldc;
+    d.M = h.M; d.N = h.N; d.K = h.K; d.accumulate = h.accumulate;
+    const int esz = cplx ? 16 : 8;
+    if (h.K > 0) {
+      if (((uintptr_t)h.A % 16) || ((uintptr_t)h.B % 16) || ((h.lda * esz) % 16) || ((h.ldb * esz) % 16) ||
+          ((uintptr_t)h.C % 16) || ((h.ldc * esz) % 16))
+        return ctx->fail(MPSK_EINTERNAL, "gemm operand not 16-byte aligned");
+      if (!(ctx->flags & MPSK_FLAG_DEBUG_GEMM)) {
+        if (!encode_map(&d.tmA, h.A, h.M, h.K, h.lda, cplx, BM) || !encode_map(&d.tmB, h.B, h.N, h.K, h.ldb, cplx, BN))
+          return ctx->fail(MPSK_ECUDA, "cuTensorMapEncodeTiled failed");
+      }
+    }
+    const int pi = (int)dev.size();
+    dev.push_back(d);
+    plan->flops += (cplx ? 8.0 : 2.0) * (double)h.M * h.N * h.K;
+    // raster: n-panels outer, m inner, so concurrently running CTAs share the B panel and stream A
+    for (int n0 = 0; n0 < h.N; n0 += BN)
+      for (int m0 = 0; m0 < h.M; m0 += BM) tiles.push_back(GemmTile{pi, m0, n0, 0});
+  }
+  plan->nprob = (int)dev.size();
+  plan->ntiles = (int)tiles.size();
+  if (plan->nprob == 0) return MPSK_OK;
+  plan->d_probs = (GemmProblemDev*)ctx->alloc(dev.size() * sizeof(GemmProblemDev));
+  plan->d_tiles = (GemmTile*)ctx->alloc(tiles.size() * sizeof(GemmTile));
+  if (!plan->d_probs || !plan->d_tiles) return ctx->fail(MPSK_ENOMEM, "gemm plan alloc");
+  CUDA_TRY(ctx, cudaMemcpyAsync(plan->d_probs, dev.data(), dev.size() * sizeof(GemmProblemDev), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(plan->d_tiles, tiles.data(), tiles.size() * sizeof(GemmTile), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+  return MPSK_OK;
+}
+
+int gemm_plan_run(Ctx* ctx, const GemmPlan* plan) {
+  if (plan->nprob == 0 || plan->ntiles == 0) return MPSK_OK;
+  if (ctx->flags & MPSK_FLAG_DEBUG_GEMM) {
+    dim3 grid(64, std::min(plan->nprob, 1024));
+    if (plan->cplx) gemm_debug_kernel<true><<<grid, 256, 0, ctx->stream>>>(plan->d_probs, plan->nprob);
+    else gemm_debug_kernel<false><<<grid, 256, 0, ctx->stream>>>(plan->d_probs, plan->nprob);
+  } else {
+    static bool attr_set[2] = {false, false};
+    const int grid = std::min(plan->ntiles, ctx->num_sms);
+    if (plan->cplx) {
+      if (!attr_set[1]) { CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<true>())); attr_set[1] = true; }
+      gemm_dmma_kernel<true><<<grid, 256, smem_bytes<true>(), ctx->stream>>>(plan->d_probs, plan->d_tiles, plan->ntiles);
+    } else {
+      if (!attr_set[0]) { CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<false>())); attr_set[0] = true; }
+      gemm_dmma_kernel<false><<<grid, 256, smem_bytes<false>(), ctx->stream>>>(plan->d_probs, plan->d_tiles, plan->ntiles);
+    }
+  }
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return MPSK_OK;
+}
+
+}  // namespace mpsk

@@ -1,0 +1,38 @@
+// Grouped FP64 / ComplexF64 "NT" GEMM engine for sm_100a.
+//   C[M x N] (+)= A[M x K] * B[N x K]^T     all row-major, A and B K-contiguous
+// This is the one tensor-core kernel behind every contraction on the hot path (SURVEY.md 8a rows
+// a2-a5, a10-a11: derivatives.jl:77-197, transfer.jl:105-110,166-259).  Blackwell has no FP64
+// tcgen05 kind; FP64 tensor math is DMMA.8x8x4 (mma.sync.m8n8k4.f64), measured 37.0 TFLOP/s on
+// B200 (profiles/r01_peak_fp64_microbench.json).  Operand tiles are staged by TMA
+// (cp.async.bulk.tensor.2d) into a multi-stage shared-memory ring guarded by mbarriers.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mpsk {
+
+struct alignas(128) GemmProblemDev {
+  CUtensorMap tmA;      // rows = M, inner = K (doubles: K or 2K)
+  CUtensorMap tmB;      // rows = N
+  void* C;
+  const void* A;        // raw pointers (used by the debug kernel)
+  const void* B;
+  int64_t lda, ldb, ldc;  // in elements
+  int32_t M, N, K;
+  int32_t accumulate;   // 0: C = AB^T, 1: C += AB^T
+};
+
+struct GemmTile { int32_t prob, m0, n0, pad; };
+
+struct GemmProblemHost {
+  const void* A; const void* B; void* C;
+  int64_t lda, ldb, ldc; int32_t M, N, K; int32_t accumulate;
+};
+
+// tile shapes (elements)
+template <bool CPLX> struct GemmCfg;
+template <> struct GemmCfg<false> { static constexpr int BM = 128, BN = 128, KSUB = 8, NSUB = 4, STAGES = 3; };
+template <> struct GemmCfg<true>  { static constexpr int BM = 128, BN = 64,  KSUB = 4, NSUB = 4, STAGES = 4; };
+
+}  // namespace mpsk

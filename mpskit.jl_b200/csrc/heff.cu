@@ -1,0 +1,194 @@
+// Effective Hamiltonians dC / dAC / dAC2 (derivatives.jl:77-197) as one generic three-launch pipeline
+//   stage A : T[(i,a),(m,c)]   = GL_i[a,b] x[b,m,c]          grouped GEMM, MPO levels stacked along M
+//   mix     : U_k[a,m',c]      = sum_{i,m} W[i,k][m',m] T_i  memory-bound rectangle gather (scalar and operator
+//                                                            MPO entries folded in as coefficients)
+//   stage C : y[a,m',c']       = sum_{k,c} U_k[a,m',c] GR_k[c,c']   grouped GEMM, levels stacked along K
+// which is the optimal-order contraction whose flop count SURVEY.md 8d defines as the algorithmic work.
+// The reference evaluates the same sum entry by entry (derivatives.jl:125-151); results agree to rounding.
+#include "internal.h"
+
+namespace mpsk {
+
+HeffOp::~HeffOp() {
+  if (ctx) { ctx->free(T); ctx->free(U); }
+}
+
+static int build_W(Ctx* ctx, int kind, const MpoSlice* h1, const MpoSlice* h2, const Tensor* x_like, int nlev,
+                   std::vector<WEntry>* W) {
+  W->clear();
+  if (kind == MPSK_OP_DC) {
+    if (x_like->nm() != 1) return ctx->fail(MPSK_ESPACE, "dC acts on bond tensors (one label)");
+    for (int i = 0; i < nlev; ++i) W->push_back(WEntry{i, i, 0, 0, cplx(1.0)});
+    return MPSK_OK;
+  }
+  if (!h1) return ctx->fail(MPSK_EINVAL, "missing MPO slice");
+  if (kind == MPSK_OP_DAC) {
+    if (x_like->nm() != h1->d) return ctx->fail(MPSK_ESPACE, "dAC: vector has %d labels, slice has d=%d", x_like->nm(), h1->d);
+    for (int i = 0; i < h1->odim; ++i)
+      for (int k = 0; k < h1->odim; ++k) {
+        if (!h1->kind[i * h1->odim + k]) continue;
+        for (int po = 0; po < h1->d; ++po)
+          for (int pi = 0; pi < h1->d; ++pi) {
+            cplx c = h1->elem(i, k, po, pi);
+            if (c != cplx(0.0)) W->push_back(WEntry{i, k, po, pi, c});
+          }
+      }
+    return MPSK_OK;
+  }
+  if (!h2) return ctx->fail(MPSK_EINVAL, "dAC2 needs two MPO slices");
+  if (h1->odim != h2->odim) return ctx->fail(MPSK_ESPACE, "slices with different odim");
+  const int d1 = h1->d, d2 = h2->d, od = h1->odim;
+  if (x_like->nm() != d1 * d2) return ctx->fail(MPSK_ESPACE, "dAC2: vector has %d labels, expected %d", x_like->nm(), d1 * d2);
+  std::map<std::tuple<int, int, int, int>, cplx> acc;
+  for (int i = 0; i < od; ++i)
+    for (int j = 0; j < od; ++j) {
+      if (!h1->kind[i * od + j]) continue;
+      for (int k = 0; k < od; ++k) {
+        if (!h2->kind[j * od + k]) continue;
+        for (int s = 0; s < d1; ++s)
+          for (int u = 0; u < d1; ++u) {
+            const cplx a = h1->elem(i, j, s, u);
+            if (a == cplx(0.0)) continue;
+            for (int T = 0; T < d2; ++T)
+              for (int t = 0; t < d2; ++t) {
+                const cplx b = h2->elem(j, k, T, t);
+                if (b == cplx(0.0)) continue;
+                acc[std::make_tuple(i, k, s * d2 + T, u * d2 + t)] += a * b;
+              }
+          }
+      }
+    }
+  for (auto& kv : acc)
+    if (kv.second != cplx(0.0))
+      W->push_back(WEntry{std::get<0>(kv.first), std::get<1>(kv.first), std::get<2>(kv.first), std::get<3>(kv.first), kv.second});
+  return MPSK_OK;
+}
+
+int heff_create(Ctx* ctx, int kind, const MpoSlice* h1, const MpoSlice* h2, const Tensor* GL, const Tensor* GR,
+                const Tensor* x_like, HeffOp** out) {
+  if (!GL || !GR || !x_like) return ctx->fail(MPSK_EINVAL, "null argument");
+  if (GL->dtype != x_like->dtype || GR->dtype != x_like->dtype) return ctx->fail(MPSK_EINVAL, "mixed scalar types");
+  if (!(GL->Vr == x_like->Vl) || !(GL->Vl == x_like->Vl)) return ctx->fail(MPSK_ESPACE, "left environment does not match the left bond of x");
+  if (!(GR->Vl == x_like->Vr) || !(GR->Vr == x_like->Vr)) return ctx->fail(MPSK_ESPACE, "right environment does not match the right bond of x");
+  if (GL->nm() != GR->nm()) return ctx->fail(MPSK_ESPACE, "environments have different numbers of MPO levels");
+  const int nlev = GL->nm();
+  if (h1 && h1->odim != nlev) return ctx->fail(MPSK_ESPACE, "MPO slice odim %d != environment levels %d", h1->odim, nlev);
+  std::unique_ptr<HeffOp> op(new HeffOp);
+  op->ctx = ctx; op->kind = kind; op->dtype = x_like->dtype;
+  const bool cx = op->dtype == MPSK_C128;
+  MPSK_TRY(build_W(ctx, kind, h1, h2, x_like, nlev, &op->W));
+  const Space& Vl = x_like->Vl;
+  // charge rule  c_k = c_i + ch(m_out) - ch(m_in)  with c_i = -GL.mch[i], c_k = +GR.mch[k]
+  for (const WEntry& w : op->W) {
+    const int64_t lhs = Vl.norm((int64_t)GR->mch[w.k]);
+    const int64_t rhs = Vl.norm(-(int64_t)GL->mch[w.i] + x_like->mch[w.mout] - x_like->mch[w.min]);
+    if (lhs != rhs) return ctx->fail(MPSK_ESPACE, "MPO entry (%d,%d) element (%d,%d) violates charge conservation", w.i, w.k, w.mout, w.min);
+  }
+  // operands in their GEMM forms
+  { Tensor* t = nullptr; MPSK_TRY(tensor_repack(ctx, GL, F_KR, false, &t)); op->GLk.reset(t); }
+  { Tensor* t = nullptr; MPSK_TRY(tensor_repack(ctx, GR, F_SL, false, &t)); op->GRs.reset(t); }
+  { Tensor* t = nullptr; MPSK_TRY(tensor_create(ctx, x_like->Vl, x_like->mch, x_like->Vr, x_like->dtype, F_KL, true, &t)); op->xs.reset(t); }
+  const Tensor& xs = *op->xs; const Tensor& GLk = *op->GLk; const Tensor& GRs = *op->GRs;
+  Tensor* ybuf = nullptr;
+  MPSK_TRY(tensor_create(ctx, x_like->Vl, x_like->mch, x_like->Vr, x_like->dtype, F_KL, true, &ybuf));
+  std::unique_ptr<Tensor> ys(ybuf);
+  const int ngl = Vl.nsec();
+  // ---- T workspace: per l-sector jb a (M_A x N_A) matrix
+  std::vector<int64_t> Toff(ngl), Tld(ngl);
+  int64_t tot = 0;
+  for (int jb = 0; jb < ngl; ++jb) {
+    Tld[jb] = pad(xs.groups[jb].rows);
+    Toff[jb] = tot;
+    tot += padg(GLk.groups[jb].rows * Tld[jb]);
+  }
+  op->T_elems = std::max<int64_t>(tot, GROUP_ALIGN);
+  // ---- U workspace: per y block (m_out, ja) an (n_a x Kz) matrix
+  std::vector<int64_t> Uoff(xs.blks.size());
+  tot = 0;
+  for (size_t b = 0; b < xs.blks.size(); ++b) {
+    const Blk& bk = xs.blks[b];
+    Uoff[b] = tot;
+    tot += padg(Vl.n[bk.jl] * GRs.groups[bk.jr].ld);
+  }
+  op->U_elems = std::max<int64_t>(tot, GROUP_ALIGN);
+  const size_t es = cx ? 16 : 8;
+  op->T = ctx->alloc(op->T_elems * es);
+  op->U = ctx->alloc(op->U_elems * es);
+  if (!op->T || !op->U) return MPSK_ENOMEM;
+  CUDA_TRY(ctx, cudaMemsetAsync(op->T, 0, op->T_elems * es, ctx->stream));
+  CUDA_TRY(ctx, cudaMemsetAsync(op->U, 0, op->U_elems * es, ctx->stream));
+  auto Tptr = [&](int64_t off) { return (char*)op->T + off * es; };
+  auto Uptr = [&](int64_t off) { return (char*)op->U + off * es; };
+  const double kappa = cx ? 8.0 : 2.0;
+  op->flops = 0;
+  // ---- stage A
+  std::vector<GemmProblemHost> pa;
+  for (int jb = 0; jb < ngl; ++jb) {
+    const Group& ga = GLk.groups[jb]; const Group& gx = xs.groups[jb];
+    if (ga.rows == 0 || gx.rows == 0) continue;
+    pa.push_back(GemmProblemHost{GLk.ptr(ga.off), xs.ptr(gx.off), Tptr(Toff[jb]), ga.ld, gx.ld, Tld[jb], (int32_t)ga.rows,
+                                 (int32_t)gx.rows, (int32_t)ga.cols, 0});
+    op->flops += kappa * (double)ga.rows * gx.rows * ga.cols;
+  }
+  // ---- mix + stage C
+  std::vector<MixTask> tasks; std::vector<MixTerm> terms; std::vector<GemmProblemHost> pc;
+  const int ngr = x_like->Vr.nsec();
+  for (size_t b = 0; b < xs.blks.size(); ++b) {
+    const Blk& bk = xs.blks[b];
+    const int ja = bk.jl, jz = bk.jr;
+    const Group& gz = GRs.groups[jz];
+    const int64_t ldU = gz.ld;
+    double klog = 0;
+    for (int k = 0; k < nlev; ++k) {
+      const int64_t segk = GRs.seg[(size_t)k * ngr + jz];
+      if (segk < 0) continue;
+      const int jc = GRs.Vl.find((int64_t)GRs.Vr.q[jz] - GRs.mch[k]);
+      klog += (double)GRs.Vl.n[jc];
+      MixTask tk; tk.dst = Uptr(Uoff[b] + segk); tk.ldd = ldU; tk.rows = (int32_t)Vl.n[ja]; tk.cols = (int32_t)GRs.Vl.n[jc];
+      tk.term_begin = (int32_t)terms.size();
+      for (const WEntry& w : op->W) {
+        if (w.k != k || w.mout != bk.m) continue;
+        const int jb = Vl.find((int64_t)Vl.q[ja] + GLk.mch[w.i]);
+        if (jb < 0) continue;
+        const Blk* xb = xs.find(w.min, jb);
+        if (!xb) continue;
+        if (xb->jr != jc) return ctx->fail(MPSK_EINTERNAL, "sector bookkeeping mismatch in mix plan");
+        const int64_t rowoff = GLk.seg[(size_t)w.i * ngl + jb];
+        const int64_t coloff = xs.seg[(size_t)w.min * ngl + jb];
+        if (rowoff < 0 || coloff < 0) return ctx->fail(MPSK_EINTERNAL, "missing segment in mix plan");
+        terms.push_back(MixTerm{Tptr(Toff[jb] + rowoff * Tld[jb] + coloff), Tld[jb], w.c.real(), w.c.imag()});
+      }
+      tk.term_end = (int32_t)terms.size();
+      if (tk.term_end > tk.term_begin) tasks.push_back(tk);
+    }
+    if (gz.cols == 0) continue;
+    pc.push_back(GemmProblemHost{GRs.ptr(gz.off), Uptr(Uoff[b]), ys->ptr(bk.off), gz.ld, ldU, ys->groups[ja].ld, (int32_t)gz.rows,
+                                 (int32_t)Vl.n[ja], (int32_t)gz.cols, 0});
+    op->flops += kappa * (double)gz.rows * Vl.n[ja] * klog;
+  }
+  op->gemmA.reset(new GemmPlan); op->gemmC.reset(new GemmPlan); op->mix.reset(new MixPlan);
+  MPSK_TRY(gemm_plan_build(ctx, cx, pa, op->gemmA.get()));
+  MPSK_TRY(mix_plan_build(ctx, cx, tasks, terms, op->mix.get()));
+  MPSK_TRY(gemm_plan_build(ctx, cx, pc, op->gemmC.get()));
+  op->bound_x = op->xs->d; op->bound_y = ys->d;
+  op->GLk.get();
+  // keep the y staging tensor alive inside the op: reuse `bound_y` owner through a unique_ptr swap
+  op->ybuf.reset(ys.release());
+  *out = op.release();
+  return MPSK_OK;
+}
+
+int heff_apply(Ctx* ctx, HeffOp* op, const Tensor* x, Tensor* y) {
+  if (!x->same_structure(*op->xs) || !y->same_structure(*op->xs)) return ctx->fail(MPSK_ESPACE, "vector structure does not match the operator");
+  if (x->form != F_KL || y->form != F_KL) return ctx->fail(MPSK_EINTERNAL, "Krylov vectors must be in KL form");
+  if (x->d != op->xs->d)
+    CUDA_TRY(ctx, cudaMemcpyAsync(op->xs->d, x->d, x->bytes(), cudaMemcpyDeviceToDevice, ctx->stream));
+  MPSK_TRY(gemm_plan_run(ctx, op->gemmA.get()));
+  MPSK_TRY(mix_plan_run(ctx, op->mix.get()));
+  MPSK_TRY(gemm_plan_run(ctx, op->gemmC.get()));
+  if (y->d != op->ybuf->d)
+    CUDA_TRY(ctx, cudaMemcpyAsync(y->d, op->ybuf->d, y->bytes(), cudaMemcpyDeviceToDevice, ctx->stream));
+  return MPSK_OK;
+}
+
+}  // namespace mpsk

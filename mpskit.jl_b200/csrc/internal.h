@@ -1,0 +1,223 @@
+// Internal structures of libmpskit_b200 (not part of the ABI).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <complex>
+#include <map>
+#include <memory>
+#include <string>
+#include <tuple>
+#include <unordered_map>
+#include <vector>
+#include "../../include/mpskit_b200.h"
+#include "gemm.cuh"
+
+namespace mpsk {
+
+typedef std::complex<double> cplx;
+
+struct Ctx;
+#define CUDA_TRY(ctx, expr)                                                                          \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess) return (ctx)->fail(MPSK_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+#define MPSK_TRY(expr) do { int _s = (expr); if (_s != MPSK_OK) return _s; } while (0)
+
+constexpr int64_t ALIGN = 4;          // leading dimensions / segment widths are padded to this many elements
+constexpr int64_t GROUP_ALIGN = 32;   // group matrices start on multiples of this many elements
+static inline int64_t pad(int64_t n) { return (n + ALIGN - 1) / ALIGN * ALIGN; }
+static inline int64_t padg(int64_t n) { return (n + GROUP_ALIGN - 1) / GROUP_ALIGN * GROUP_ALIGN; }
+
+struct TsvdSpectrum { std::vector<int32_t> charge, count, kept; std::vector<double> values; };
+
+struct Ctx {
+  int device = 0;
+  uint64_t flags = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
+  int num_sms = 148;
+  std::string err;
+  int64_t launches = 0;
+  // stream-ordered caching allocator (all work of a context is on one stream)
+  std::multimap<size_t, void*> freelist;
+  std::unordered_map<void*, size_t> sizes;
+  int64_t bytes_in_use = 0, bytes_cached = 0;
+  void* cusolver = nullptr;     // cusolverDnHandle_t, created lazily
+  void* nccl = nullptr;         // ncclComm_t
+  int rank = 0, nranks = 1;
+  double* h_scratch = nullptr;  // pinned host scratch (scalars coming back from Krylov kernels)
+  double* d_scratch = nullptr;  // device scratch for reductions
+  size_t d_scratch_bytes = 0;
+  TsvdSpectrum last_spectrum;
+
+  void* alloc(size_t bytes);
+  void free(void* p);
+  void release_cache();
+  int fail(int code, const char* fmt, ...);
+};
+
+struct Space {
+  std::vector<int32_t> q;
+  std::vector<int64_t> n;
+  int32_t mod = 0;
+  int nsec() const { return (int)q.size(); }
+  int64_t dim() const { int64_t s = 0; for (auto v : n) s += v; return s; }
+  int64_t norm(int64_t c) const { if (!mod) return c; int64_t r = c % mod; return r < 0 ? r + mod : r; }
+  int find(int64_t c) const {
+    c = norm(c);
+    auto it = std::lower_bound(q.begin(), q.end(), (int32_t)c);
+    return (it != q.end() && *it == c) ? (int)(it - q.begin()) : -1;
+  }
+  bool operator==(const Space& o) const { return q == o.q && n == o.n && mod == o.mod; }
+};
+int space_from_abi(Ctx* ctx, const mpsk_space* s, Space* out);
+
+// Device layouts ("forms") of a T[l, m, r] tensor.  Every form is a set of dense row-major group
+// matrices, one per sector of the grouping leg, chosen so that the contraction GEMMs need no
+// standalone permutes (kernel family K2 "eliminated by layout choice"):
+//   KL: group = l-sector, rows (m, r), cols l           (l contiguous)   -- x / y vectors, ket tensors
+//   KR: group = r-sector, rows (m, l), cols r           (r contiguous)   -- left environments
+//   SL: group = r-sector, rows r, cols segments (m, l)  (l contiguous)   -- K-stacked operands
+//   SR: group = l-sector, rows l, cols segments (m, r)  (r contiguous)
+enum Form { F_KL = 0, F_KR = 1, F_SL = 2, F_SR = 3 };
+
+struct Blk { int32_t m, jl, jr; int64_t off, sl, sr; };       // element offset and strides of block (m, jl)
+struct Group { int64_t off, rows, cols, ld; };
+
+struct Tensor {
+  Ctx* ctx = nullptr;
+  Space Vl, Vr;
+  std::vector<int32_t> mch;
+  int dtype = MPSK_C128;
+  Form form = F_KL;
+  std::vector<Blk> blks;               // canonical order: m major, l-sector minor (== oracle block_keys)
+  std::vector<int32_t> blk_index;      // [m * nsec_l + jl] -> index into blks or -1
+  std::vector<Group> groups;
+  std::vector<int64_t> seg;            // [m * ngroups + g] row (K forms) / column (S forms) offset of label m in group g, -1 absent
+  void* d = nullptr;
+  int64_t nelem = 0;                   // elements including padding
+  int nm() const { return (int)mch.size(); }
+  int ngroups() const { return (int)groups.size(); }
+  size_t esize() const { return dtype == MPSK_C128 ? 16 : 8; }
+  size_t bytes() const { return (size_t)nelem * esize(); }
+  const Blk* find(int m, int jl) const { int i = blk_index[(size_t)m * Vl.nsec() + jl]; return i < 0 ? nullptr : &blks[i]; }
+  char* ptr(int64_t off) const { return (char*)d + off * (int64_t)esize(); }
+  bool same_structure(const Tensor& o) const { return Vl == o.Vl && Vr == o.Vr && mch == o.mch && dtype == o.dtype; }
+  ~Tensor() { if (d && ctx) ctx->free(d); }
+};
+
+int tensor_create(Ctx* ctx, const Space& Vl, const std::vector<int32_t>& mch, const Space& Vr, int dtype, Form form,
+                  bool zero, Tensor** out);
+// copy with optional complex conjugation into another form (new tensor)
+int tensor_repack(Ctx* ctx, const Tensor* src, Form form, bool conj, Tensor** out);
+// returns src itself when it already has the form (and !conj); *owned tells whether the caller must delete
+int tensor_as_form(Ctx* ctx, const Tensor* src, Form form, bool conj, const Tensor** out, bool* owned);
+
+int tensor_fill_random(Ctx* ctx, Tensor* t, uint64_t seed);
+
+// ---- strided block copies (upload / download / repack / SVD assembly)
+struct CopyTask {
+  const void* src; void* dst;
+  int64_t ssl, ssr, dsl, dsr;   // element strides of the l and r index in src / dst
+  int32_t nl, nr;
+  int32_t conj;                 // conjugate while copying
+  int32_t scale_axis;           // 0 none, 1 scale[l], 2 scale[r]
+  const double* scale;          // real scale vector on the device
+};
+int run_copy_tasks(Ctx* ctx, const std::vector<CopyTask>& tasks, bool cplx);
+
+// ---- "mix": out_rect = sum_terms coeff * src_rect  (row-major rectangles, unit column stride)
+struct MixTerm { const void* src; int64_t lds; double cre, cim; };
+struct MixTask { void* dst; int64_t ldd; int32_t rows, cols; int32_t term_begin, term_end; };
+struct MixPlan {
+  Ctx* ctx = nullptr; bool cplx = true;
+  void* d_tasks = nullptr; void* d_terms = nullptr; void* d_tiles = nullptr; int ntiles = 0;
+  double bytes = 0;   // algorithmic bytes moved per run
+  ~MixPlan();
+};
+int mix_plan_build(Ctx* ctx, bool cplx, const std::vector<MixTask>& tasks, const std::vector<MixTerm>& terms, MixPlan* plan);
+int mix_plan_run(Ctx* ctx, const MixPlan* plan);
+
+// ---- grouped GEMM
+struct GemmPlan {
+  Ctx* ctx = nullptr; bool cplx = true;
+  GemmProblemDev* d_probs = nullptr; GemmTile* d_tiles = nullptr;
+  int nprob = 0, ntiles = 0; double flops = 0;
+  ~GemmPlan();
+};
+int gemm_plan_build(Ctx* ctx, bool cplx, const std::vector<GemmProblemHost>& probs, GemmPlan* plan);
+int gemm_plan_run(Ctx* ctx, const GemmPlan* plan);
+
+// ---- Krylov BLAS-1 on flat vectors.  Coefficients that come from reductions stay on the device, so a
+// Lanczos/Arnoldi step needs a single host synchronisation (kernel family K3).
+int vec_multidot(Ctx* ctx, bool cplx, int nv, const void* const* V, const void* w, int64_t nelem, double* d_out /*2*nv*/);
+int vec_multiaxpy(Ctx* ctx, bool cplx, int nv, const void* const* V, const double* d_coef /*2*nv*/, double sign, void* w, int64_t nelem);
+int vec_norm2(Ctx* ctx, bool cplx, const void* x, int64_t nelem, double* d_out /*1*/);
+int vec_scale_rsqrt(Ctx* ctx, bool cplx, void* x, int64_t nelem, const double* d_norm2);   // x /= sqrt(*d_norm2)
+int vec_scale(Ctx* ctx, bool is_cplx, void* x, int64_t nelem, cplx a);
+int vec_axpy(Ctx* ctx, bool is_cplx, cplx a, const void* x, void* y, int64_t nelem);
+int vec_add_dev(Ctx* ctx, int n, const double* a, double* b);   // b[i] += a[i] (tiny, device scalars)
+
+// ---- MPO slice
+struct MpoSlice {
+  int odim = 0, d = 0;
+  std::vector<int32_t> cl, cr, pch, kind;         // kind[i*odim+j]
+  std::vector<cplx> scal;                         // [i*odim+j]
+  std::vector<std::vector<cplx>> ops;             // [i*odim+j] -> d*d row-major O[p_out,p_in] (empty unless kind==2)
+  cplx elem(int i, int j, int po, int pi) const {
+    int k = kind[i * odim + j];
+    if (k == 0) return 0.0;
+    if (k == 1) return po == pi ? scal[i * odim + j] : cplx(0.0);
+    return ops[i * odim + j][po * d + pi];
+  }
+};
+
+// ---- effective Hamiltonian = stage-A GEMMs -> mix -> stage-C GEMMs
+struct WEntry { int32_t i, k, mout, min; cplx c; };
+struct HeffOp {
+  Ctx* ctx = nullptr; int kind = 0; int dtype = MPSK_C128;
+  std::unique_ptr<Tensor> GLk;   // left env in KR form (owned copy)
+  std::unique_ptr<Tensor> GRs;   // right env in SL form (owned copy)
+  std::unique_ptr<Tensor> xs;    // input staging buffer / structure template of x (KL form)
+  std::unique_ptr<Tensor> ybuf;  // output staging buffer (KL form); plans are bound to xs / ybuf
+  std::vector<WEntry> W;
+  // workspaces
+  void* T = nullptr; void* U = nullptr; int64_t T_elems = 0, U_elems = 0;
+  // plans are bound to concrete x / y buffers; rebuilt lazily when those change
+  const void* bound_x = nullptr; void* bound_y = nullptr;
+  std::unique_ptr<GemmPlan> gemmA, gemmC; std::unique_ptr<MixPlan> mix;
+  double flops = 0;
+  ~HeffOp();
+};
+int heff_create(Ctx* ctx, int kind, const MpoSlice* h1, const MpoSlice* h2, const Tensor* GL, const Tensor* GR,
+                const Tensor* x_like, HeffOp** out);
+int heff_apply(Ctx* ctx, HeffOp* op, const Tensor* x, Tensor* y);
+
+// ---- Krylov solvers (eigsolve.cu)
+int eigsolve_lanczos(Ctx* ctx, HeffOp* op, const Tensor* x0, int which, int krylovdim, int maxiter, double tol,
+                     cplx* val, Tensor* vec, mpsk_info* info);
+int eigsolve_arnoldi(Ctx* ctx, HeffOp* op, const Tensor* x0, int which, int krylovdim, int maxiter, double tol,
+                     cplx* val, Tensor* vec, mpsk_info* info);
+int expv_lanczos(Ctx* ctx, HeffOp* op, cplx tau, const Tensor* y0, int krylovdim, int maxiter, double tol, Tensor* y,
+                 mpsk_info* info);
+// small dense host linear algebra
+void jacobi_eigh(int n, std::vector<double>& A /*n*n row-major, destroyed*/, std::vector<double>& evals, std::vector<double>& evecs);
+
+// ---- transfers, local algebra, factorizations
+int transfer_left(Ctx* ctx, const MpoSlice* h, const Tensor* A, const Tensor* Abar, const Tensor* GL, Tensor** out);
+int transfer_right(Ctx* ctx, const MpoSlice* h, const Tensor* A, const Tensor* Abar, const Tensor* GR, Tensor** out);
+int contract_ac2(Ctx* ctx, const Tensor* A1, const Tensor* A2, Tensor** out);
+int mul_bond_right(Ctx* ctx, const Tensor* A, const Tensor* C, Tensor** out);
+int mul_bond_left(Ctx* ctx, const Tensor* C, const Tensor* A, Tensor** out);
+int tsvd(Ctx* ctx, const Tensor* ac2, int d1, const int32_t* p1_charge, mpsk_trunc trunc, Tensor** U, Tensor** S, Tensor** Vh, double* eps);
+int qrpos(Ctx* ctx, const Tensor* A, bool left, Tensor** Q, Tensor** R);
+
+}  // namespace mpsk
+
+// ABI handles are opaque pointers to the structs above (reinterpret_cast in api.cu).

@@ -1,0 +1,207 @@
+// Post-eigensolve truncated SVD of the two-site tensor, on the device (dmrg.jl:96-103,112-119):
+//   tsvd!(ac2; trunc, alg=SVD()) -> per coupled sector one gesvd (cuSOLVER; LAPACK-class library call, like the
+//   reference's LAPACK gesvd), global truncation select over all sectors on the host (integer bookkeeping,
+//   bit-exact with the oracle), normalize!(c), and al / c / ar written straight into GEMM-ready layouts.
+#include "internal.h"
+#include <cusolverDn.h>
+#include <cmath>
+
+namespace mpsk {
+
+#define CUSOLVER_TRY(ctx, expr)                                                                  \
+  do {                                                                                           \
+    cusolverStatus_t _s = (expr);                                                                \
+    if (_s != CUSOLVER_STATUS_SUCCESS) return (ctx)->fail(MPSK_ECUDA, "%s failed: cusolver status %d", #expr, (int)_s); \
+  } while (0)
+
+static int get_cusolver(Ctx* ctx, cusolverDnHandle_t* h) {
+  if (!ctx->cusolver) {
+    cusolverDnHandle_t hh;
+    CUSOLVER_TRY(ctx, cusolverDnCreate(&hh));
+    ctx->cusolver = hh;
+  }
+  *h = (cusolverDnHandle_t)ctx->cusolver;
+  CUSOLVER_TRY(ctx, cusolverDnSetStream(*h, ctx->stream));
+  return MPSK_OK;
+}
+
+__global__ void diag_kernel(double* dst, int64_t ld, int n, const double* s, double scale, int cplx) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (cplx) { dst[2 * (i * ld + i)] = s[i] * scale; dst[2 * (i * ld + i) + 1] = 0.0; }
+  else dst[i * ld + i] = s[i] * scale;
+}
+
+struct Coupled {
+  int32_t Q;
+  std::vector<std::pair<int, int>> rows, cols;    // (l-sector, u), (r-sector, t)
+  std::vector<int64_t> rowoff, coloff;
+  int64_t m = 0, n = 0, k = 0;
+  bool flip = false;                              // factorise M^H instead (gesvd needs rows >= cols)
+  void* W = nullptr; void* U = nullptr; void* VT = nullptr; double* S = nullptr;
+  int64_t ldw = 0, ldu = 0, ldvt = 0;
+  int keep = 0;
+};
+
+int tsvd(Ctx* ctx, const Tensor* x, int d1, const int32_t* p1ch, mpsk_trunc trunc, Tensor** Uo, Tensor** So, Tensor** Vo, double* eps_out);
+
+int tsvd(Ctx* ctx, const Tensor* x, int d1, const int32_t* p1ch, mpsk_trunc trunc, Tensor** Uo, Tensor** So, Tensor** Vo,
+         double* eps_out) {
+  if (d1 <= 0 || x->nm() % d1) return ctx->fail(MPSK_EINVAL, "tsvd: d1 does not divide the label count");
+  const int d2 = x->nm() / d1;
+  const bool cx = x->dtype == MPSK_C128;
+  const size_t es = cx ? 16 : 8;
+  std::vector<int32_t> s1(p1ch, p1ch + d1), s2(d2);
+  for (int t = 0; t < d2; ++t) s2[t] = x->mch[t] - s1[0];
+  for (int u = 0; u < d1; ++u) for (int t = 0; t < d2; ++t)
+    if (x->mch[u * d2 + t] != s1[u] + s2[t]) return ctx->fail(MPSK_ESPACE, "tsvd: label charges are not of the form s1[p1] + s2[p2]");
+
+  const Tensor* xk = x; bool own = false;
+  MPSK_TRY(tensor_as_form(ctx, x, F_KL, false, &xk, &own));
+  std::unique_ptr<const Tensor> xown(own ? xk : nullptr);
+  const Space& Vl = x->Vl; const Space& Vr = x->Vr;
+  // ---- coupled sectors (ascending charge)
+  std::map<int64_t, Coupled> cs;
+  for (int jl = 0; jl < Vl.nsec(); ++jl) for (int u = 0; u < d1; ++u) {
+    const int64_t Q = Vl.norm((int64_t)Vl.q[jl] + s1[u]);
+    Coupled& c = cs[Q]; c.Q = (int32_t)Q; c.rows.push_back({jl, u}); c.rowoff.push_back(c.m); c.m += Vl.n[jl];
+  }
+  for (int jr = 0; jr < Vr.nsec(); ++jr) for (int t = 0; t < d2; ++t) {
+    const int64_t Q = Vl.norm((int64_t)Vr.q[jr] - s2[t]);
+    auto it = cs.find(Q);
+    if (it == cs.end()) continue;
+    Coupled& c = it->second; c.cols.push_back({jr, t}); c.coloff.push_back(c.n); c.n += Vr.n[jr];
+  }
+  std::vector<Coupled*> secs;
+  for (auto& kv : cs) if (kv.second.m > 0 && kv.second.n > 0) secs.push_back(&kv.second);
+  struct Cleanup { Ctx* ctx; std::vector<Coupled*>* s; ~Cleanup() { for (Coupled* c : *s) { ctx->free(c->W); ctx->free(c->U); ctx->free(c->VT); ctx->free(c->S); } } } cleanup{ctx, &secs};
+  // ---- assemble the column-major matrices
+  std::vector<CopyTask> tasks;
+  for (Coupled* c : secs) {
+    c->k = std::min(c->m, c->n); c->flip = c->m < c->n;
+    const int64_t mm = c->flip ? c->n : c->m, nn = c->flip ? c->m : c->n;
+    c->ldw = mm; c->ldu = mm; c->ldvt = c->k;
+    c->W = ctx->alloc(mm * nn * es); c->U = ctx->alloc(mm * c->k * es); c->VT = ctx->alloc(c->k * nn * es);
+    c->S = (double*)ctx->alloc(c->k * sizeof(double));
+    if (!c->W || !c->U || !c->VT || !c->S) return MPSK_ENOMEM;
+    CUDA_TRY(ctx, cudaMemsetAsync(c->W, 0, mm * nn * es, ctx->stream));
+    for (size_t ri = 0; ri < c->rows.size(); ++ri) for (size_t ci = 0; ci < c->cols.size(); ++ci) {
+      const int jl = c->rows[ri].first, u = c->rows[ri].second, jr = c->cols[ci].first, t = c->cols[ci].second;
+      const Blk* b = xk->find(u * d2 + t, jl);
+      if (!b || b->jr != jr) continue;
+      CopyTask tk; tk.src = xk->ptr(b->off); tk.ssl = b->sl; tk.ssr = b->sr; tk.nl = (int32_t)Vl.n[jl]; tk.nr = (int32_t)Vr.n[jr];
+      tk.scale_axis = 0; tk.scale = nullptr;
+      if (!c->flip) { tk.dst = (char*)c->W + (c->rowoff[ri] + c->coloff[ci] * c->ldw) * es; tk.dsl = 1; tk.dsr = c->ldw; tk.conj = 0; }
+      else { tk.dst = (char*)c->W + (c->coloff[ci] + c->rowoff[ri] * c->ldw) * es; tk.dsl = c->ldw; tk.dsr = 1; tk.conj = cx ? 1 : 0; }
+      tasks.push_back(tk);
+    }
+  }
+  MPSK_TRY(run_copy_tasks(ctx, tasks, cx));
+  // ---- gesvd per sector
+  cusolverDnHandle_t hs;
+  MPSK_TRY(get_cusolver(ctx, &hs));
+  int* d_info = (int*)ctx->alloc(sizeof(int));
+  std::vector<std::vector<double>> sv(secs.size());
+  for (size_t si = 0; si < secs.size(); ++si) {
+    Coupled* c = secs[si];
+    const int mm = (int)(c->flip ? c->n : c->m), nn = (int)(c->flip ? c->m : c->n);
+    int lwork = 0;
+    if (cx) CUSOLVER_TRY(ctx, cusolverDnZgesvd_bufferSize(hs, mm, nn, &lwork));
+    else CUSOLVER_TRY(ctx, cusolverDnDgesvd_bufferSize(hs, mm, nn, &lwork));
+    void* work = ctx->alloc((size_t)std::max(lwork, 1) * es);
+    double* rwork = (double*)ctx->alloc(sizeof(double) * std::max(nn, 1) * 5);
+    if (!work || !rwork) return MPSK_ENOMEM;
+    if (cx) CUSOLVER_TRY(ctx, cusolverDnZgesvd(hs, 'S', 'S', mm, nn, (cuDoubleComplex*)c->W, (int)c->ldw, c->S, (cuDoubleComplex*)c->U, (int)c->ldu,
+                                               (cuDoubleComplex*)c->VT, (int)c->ldvt, (cuDoubleComplex*)work, lwork, rwork, d_info));
+    else CUSOLVER_TRY(ctx, cusolverDnDgesvd(hs, 'S', 'S', mm, nn, (double*)c->W, (int)c->ldw, c->S, (double*)c->U, (int)c->ldu, (double*)c->VT,
+                                            (int)c->ldvt, (double*)work, lwork, rwork, d_info));
+    ctx->launches++;
+    int info = 0;
+    sv[si].resize(c->k);
+    CUDA_TRY(ctx, cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(sv[si].data(), c->S, sizeof(double) * c->k, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->free(work); ctx->free(rwork);
+    if (info != 0) { ctx->free(d_info); return ctx->fail(MPSK_ECUDA, "gesvd did not converge in sector %d (info=%d)", c->Q, info); }
+  }
+  ctx->free(d_info);
+  // ---- global truncation select (same rule as oracle/linalg.py:tsvd): drop smallest first; ties: later sector, larger index first
+  struct Ent { double s; int sec, idx; };
+  std::vector<Ent> all;
+  for (size_t si = 0; si < secs.size(); ++si) { secs[si]->keep = (int)secs[si]->k; for (int i = 0; i < secs[si]->k; ++i) all.push_back(Ent{sv[si][i], (int)si, i}); }
+  std::stable_sort(all.begin(), all.end(), [](const Ent& a, const Ent& b) {
+    if (a.s != b.s) return a.s < b.s;
+    if (a.sec != b.sec) return a.sec > b.sec;
+    return a.idx > b.idx;
+  });
+  double dropped2 = 0.0; size_t ndrop = 0;
+  if (trunc.kind == MPSK_TRUNCDIM) {
+    const int64_t D = (int64_t)trunc.value;
+    ndrop = (int64_t)all.size() > D ? all.size() - (size_t)D : 0;
+  } else if (trunc.kind == MPSK_TRUNCERR) {
+    double acc = 0.0;
+    for (const Ent& e : all) { if (std::sqrt(acc + e.s * e.s) <= trunc.value) { acc += e.s * e.s; ++ndrop; } else break; }
+  } else if (trunc.kind == MPSK_TRUNCBELOW) {
+    for (const Ent& e : all) { if (e.s < trunc.value) ++ndrop; else break; }
+  } else if (trunc.kind != MPSK_NOTRUNC) return ctx->fail(MPSK_EINVAL, "unknown truncation scheme");
+  for (size_t i = 0; i < ndrop; ++i) { secs[all[i].sec]->keep--; dropped2 += all[i].s * all[i].s; }
+  if (eps_out) *eps_out = std::sqrt(dropped2);
+  double kept2 = 0.0;
+  for (size_t si = 0; si < secs.size(); ++si) for (int i = 0; i < secs[si]->keep; ++i) kept2 += sv[si][i] * sv[si][i];
+  if (kept2 <= 0.0) return ctx->fail(MPSK_EINVAL, "tsvd: truncation removed every singular value");
+  const double snorm = 1.0 / std::sqrt(kept2);
+  // record the spectrum for mpsk_tsvd_spectrum
+  TsvdSpectrum& sp = ctx->last_spectrum;
+  sp.charge.clear(); sp.count.clear(); sp.kept.clear(); sp.values.clear();
+  for (size_t si = 0; si < secs.size(); ++si) {
+    sp.charge.push_back(secs[si]->Q); sp.count.push_back((int32_t)secs[si]->k); sp.kept.push_back(secs[si]->keep);
+    sp.values.insert(sp.values.end(), sv[si].begin(), sv[si].end());
+  }
+  // ---- new bond space and outputs
+  Space Vn; Vn.mod = Vl.mod;
+  for (Coupled* c : secs) if (c->keep > 0) { Vn.q.push_back(c->Q); Vn.n.push_back(c->keep); }
+  Tensor *Ut = nullptr, *St = nullptr, *Vt = nullptr;
+  MPSK_TRY(tensor_create(ctx, Vl, s1, Vn, x->dtype, F_KL, true, &Ut));
+  std::unique_ptr<Tensor> ug(Ut);
+  MPSK_TRY(tensor_create(ctx, Vn, std::vector<int32_t>{0}, Vn, x->dtype, F_KL, true, &St));
+  std::unique_ptr<Tensor> sg(St);
+  MPSK_TRY(tensor_create(ctx, Vn, s2, Vr, x->dtype, F_KL, true, &Vt));
+  std::unique_ptr<Tensor> vg(Vt);
+  tasks.clear();
+  for (Coupled* c : secs) {
+    if (c->keep <= 0) continue;
+    const int jn = Vn.find(c->Q);
+    for (size_t ri = 0; ri < c->rows.size(); ++ri) {
+      const int jl = c->rows[ri].first, u = c->rows[ri].second;
+      const Blk* b = Ut->find(u, jl);
+      if (!b || b->jr != jn) continue;
+      CopyTask tk; tk.dst = Ut->ptr(b->off); tk.dsl = b->sl; tk.dsr = b->sr; tk.nl = (int32_t)Vl.n[jl]; tk.nr = c->keep; tk.scale_axis = 0; tk.scale = nullptr;
+      if (!c->flip) { tk.src = (char*)c->U + c->rowoff[ri] * es; tk.ssl = 1; tk.ssr = c->ldu; tk.conj = 0; }
+      else { tk.src = (char*)c->VT + (c->rowoff[ri] * c->ldvt) * es; tk.ssl = c->ldvt; tk.ssr = 1; tk.conj = cx ? 1 : 0; }
+      tasks.push_back(tk);
+    }
+    for (size_t ci = 0; ci < c->cols.size(); ++ci) {
+      const int jr = c->cols[ci].first, t = c->cols[ci].second;
+      const Blk* b = Vt->find(t, jn);
+      if (!b || b->jr != jr) continue;
+      CopyTask tk; tk.dst = Vt->ptr(b->off); tk.dsl = b->sl; tk.dsr = b->sr; tk.nl = c->keep; tk.nr = (int32_t)Vr.n[jr]; tk.scale_axis = 0; tk.scale = nullptr;
+      if (!c->flip) { tk.src = (char*)c->VT + (c->coloff[ci] * c->ldvt) * es; tk.ssl = 1; tk.ssr = c->ldvt; tk.conj = 0; }
+      else { tk.src = (char*)c->U + c->coloff[ci] * es; tk.ssl = c->ldu; tk.ssr = 1; tk.conj = cx ? 1 : 0; }
+      tasks.push_back(tk);
+    }
+    const Blk* sb = St->find(0, jn);
+    diag_kernel<<<(c->keep + 127) / 128, 128, 0, ctx->stream>>>((double*)St->ptr(sb->off), St->groups[jn].ld,
+                                                                 c->keep, c->S, snorm, cx ? 1 : 0);
+    ctx->launches++;
+  }
+  MPSK_TRY(run_copy_tasks(ctx, tasks, cx));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  *Uo = ug.release(); *So = sg.release(); *Vo = vg.release();
+  return MPSK_OK;
+}
+
+int qrpos(Ctx* ctx, const Tensor*, bool, Tensor**, Tensor**) {
+  return ctx->fail(MPSK_EINVAL, "qrpos/lqpos are not available in this build yet");
+}
+
+}  // namespace mpsk

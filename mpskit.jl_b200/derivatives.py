@@ -1,0 +1,88 @@
+"""Effective-Hamiltonian operators, mirror of src/algorithms/derivatives.jl:6-71.
+
+``MPO_ddC / MPO_ddAC / MPO_ddAC2`` are callables ``h(x)`` (derivatives.jl:26-31) backed by an ``mpsk_op``;
+``ddC / ddAC / ddAC2(pos, psi, H, envs)`` are the constructors (derivatives.jl:34-66), which -- as in the
+reference -- trigger the lazy environment update through ``leftenv`` / ``rightenv``."""
+from __future__ import annotations
+import ctypes as C
+from . import _lib
+from .tensor import DeviceTensor
+
+
+class DerivativeOperator:
+    kind = None
+
+    def __init__(self, ctx, h1, h2, leftenv, rightenv, x_like):
+        self.ctx = ctx
+        self.leftenv, self.rightenv = leftenv, rightenv
+        self.o1, self.o2 = h1, h2
+        op = C.c_void_p()
+        ctx.check(ctx.lib.mpsk_op_create(ctx.h, self.kind,
+                                         h1.device(ctx) if h1 is not None else None,
+                                         h2.device(ctx) if h2 is not None else None,
+                                         leftenv.h, rightenv.h, x_like.h, C.byref(op)))
+        self.h = op
+
+    def __call__(self, x, *_t):
+        """y = h(x); the optional second argument is the (ignored) time of derivatives.jl:31."""
+        y = x.zerovector()
+        self.ctx.check(self.ctx.lib.mpsk_op_apply(self.ctx.h, self.h, x.h, y.h))
+        return y
+
+    def apply_into(self, x, y):
+        self.ctx.check(self.ctx.lib.mpsk_op_apply(self.ctx.h, self.h, x.h, y.h))
+        return y
+
+    __mul__ = __call__
+
+    @property
+    def flops(self):
+        """algorithmic real flops of one application."""
+        return float(self.ctx.lib.mpsk_op_flops(self.h))
+
+    def free(self):
+        if self.h is not None and self.ctx.h:
+            self.ctx.lib.mpsk_op_free(self.ctx.h, self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class MPO_ddC(DerivativeOperator):
+    kind = _lib.OP_DC
+
+    def __init__(self, ctx, leftenv, rightenv, x_like):
+        super().__init__(ctx, None, None, leftenv, rightenv, x_like)
+
+
+class MPO_ddAC(DerivativeOperator):
+    kind = _lib.OP_DAC
+
+    def __init__(self, ctx, o, leftenv, rightenv, x_like):
+        super().__init__(ctx, o, None, leftenv, rightenv, x_like)
+
+
+class MPO_ddAC2(DerivativeOperator):
+    kind = _lib.OP_DAC2
+
+    def __init__(self, ctx, o1, o2, leftenv, rightenv, x_like):
+        super().__init__(ctx, o1, o2, leftenv, rightenv, x_like)
+
+
+def ddC(pos, psi, H, envs):
+    """derivatives.jl:34-36: MPO_ddC(leftenv(envs, pos+1), rightenv(envs, pos))"""
+    return MPO_ddC(psi.ctx, envs.leftenv(pos + 1, psi), envs.rightenv(pos, psi), psi.CR[pos])
+
+
+def ddAC(pos, psi, H, envs):
+    """derivatives.jl:44-46"""
+    return MPO_ddAC(psi.ctx, envs.opp[pos], envs.leftenv(pos, psi), envs.rightenv(pos, psi), psi.AC[pos])
+
+
+def ddAC2(pos, psi, H, envs, x_like):
+    """derivatives.jl:55-58: (opp[pos], opp[pos+1], leftenv(pos), rightenv(pos+1))"""
+    return MPO_ddAC2(psi.ctx, envs.opp[pos], envs.opp[pos + 1], envs.leftenv(pos, psi), envs.rightenv(pos + 1, psi), x_like)

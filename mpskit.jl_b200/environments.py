@@ -1,0 +1,74 @@
+"""FinEnv: mirror of src/environments/FinEnv.jl:9-145 with device-resident environments.
+Staleness is decided by object identity of ``AL[j]`` / ``AR[j]`` exactly like the reference's ``===``."""
+from __future__ import annotations
+import ctypes as C
+import numpy as np
+from .tensor import DeviceTensor
+
+
+class FinEnv:
+    def __init__(self, below, opp, leftstart, rightstart, above=None):
+        self.above = above
+        self.opp = opp
+        L = len(below)
+        self.ldependencies = [None] * L
+        self.rdependencies = [None] * L
+        self.leftenvs = [leftstart] + [None] * L
+        self.rightenvs = [None] * L + [rightstart]
+
+    def poison(self, ind):
+        """FinEnv.jl:108-111"""
+        self.ldependencies[ind] = None
+        self.rdependencies[ind] = None
+
+    def rightenv(self, ind, state):
+        """FinEnv.jl:114-129: environment contractable with the tensor on site ind."""
+        a = None
+        for i in range(len(state) - 1, ind, -1):
+            if state.AR[i] is not self.rdependencies[i]:
+                a = i
+                break
+        if a is not None:
+            ctx = state.ctx
+            for j in range(a, ind, -1):
+                above = state.AR[j] if self.above is None else self.above.AR[j]
+                h = C.c_void_p()
+                ctx.check(ctx.lib.mpsk_transfer_right(ctx.h, self.opp[j].device(ctx), above.h, state.AR[j].h,
+                                                      self.rightenvs[j + 1].h, C.byref(h)))
+                self.rightenvs[j] = DeviceTensor.wrap(ctx, h, state.pspace.modulus)
+                self.rdependencies[j] = state.AR[j]
+        return self.rightenvs[ind + 1]
+
+    def leftenv(self, ind, state):
+        """FinEnv.jl:131-145"""
+        a = None
+        for i in range(0, ind):
+            if state.AL[i] is not self.ldependencies[i]:
+                a = i
+                break
+        if a is not None:
+            ctx = state.ctx
+            for j in range(a, ind):
+                above = state.AL[j] if self.above is None else self.above.AL[j]
+                h = C.c_void_p()
+                ctx.check(ctx.lib.mpsk_transfer_left(ctx.h, self.opp[j].device(ctx), above.h, state.AL[j].h,
+                                                     self.leftenvs[j].h, C.byref(h)))
+                self.leftenvs[j + 1] = DeviceTensor.wrap(ctx, h, state.pspace.modulus)
+                self.ldependencies[j] = state.AL[j]
+        return self.leftenvs[ind]
+
+
+def environments(below, O, above=None):
+    """FinEnv.jl:41-70: start vectors l_LL (x) 1 on level 1 and r_RR (x) 1 on level odim (MPOHamiltonian)."""
+    ctx = below.ctx
+    L = len(below)
+    odim = O.odim
+    V0, VL = below.V[0], below.V[L]
+    cl = O[0].domcharges
+    cr = O[L - 1].imcharges
+    dt = below.dtype
+    ls = np.zeros((V0.dim, odim, V0.dim), dtype=dt); ls[:, 0, :] = np.eye(V0.dim)
+    rs = np.zeros((VL.dim, odim, VL.dim), dtype=dt); rs[:, odim - 1, :] = np.eye(VL.dim)
+    leftstart = DeviceTensor.from_dense(ctx, ls, V0, [-c for c in cl], V0, dt)
+    rightstart = DeviceTensor.from_dense(ctx, rs, VL, [c for c in cr], VL, dt)
+    return FinEnv(below, O, leftstart, rightstart, above)

@@ -1,0 +1,60 @@
+"""``fixedpoint`` and ``integrate``: mirrors of src/algorithms/fixedpoint.jl:9-30 and
+src/algorithms/timestep/integrators.jl:20-25.  The Krylov loop runs inside the library on the device."""
+from __future__ import annotations
+import ctypes as C
+import warnings
+from dataclasses import dataclass
+from . import _lib
+
+_WHICH = {"SR": _lib.SR, "LM": _lib.LM, "LR": _lib.LR}
+
+
+@dataclass
+class Lanczos:
+    """KrylovKit.Lanczos parameters (Hermitian maps)."""
+    tol: float = 1e-12
+    krylovdim: int = 30
+    maxiter: int = 100
+
+
+@dataclass
+class Arnoldi:
+    """KrylovKit.Arnoldi parameters (Defaults.eigsolver, defaults.jl:33). ``hermitian=True`` lets the library use
+    the Lanczos recurrence for the Hermitian effective Hamiltonians of DMRG (same converged eigenpair)."""
+    tol: float = 1e-12
+    krylovdim: int = 30
+    maxiter: int = 100
+    eager: bool = True
+    hermitian: bool = True
+
+
+def fixedpoint(A, x0, which, alg, return_info=False):
+    """val, vec = fixedpoint(A, x0, which, alg)   (fixedpoint.jl:9-30)"""
+    ctx = A.ctx
+    vec = x0.zerovector()
+    re, im = C.c_double(), C.c_double()
+    info = _lib.c_info()
+    herm = 1 if isinstance(alg, Lanczos) or getattr(alg, "hermitian", False) else 0
+    ctx.check(ctx.lib.mpsk_eigsolve(ctx.h, A.h, x0.h, _WHICH[which], herm, alg.krylovdim, alg.maxiter, alg.tol,
+                                    C.byref(re), C.byref(im), vec.h, C.byref(info)))
+    if info.converged == 0:   # fixedpoint.jl:12-14
+        warnings.warn(f"fixedpoint not converged after {info.numiter} iterations: normres = {info.normres}")
+    val = complex(re.value, im.value)
+    if return_info:
+        return val, vec, dict(converged=info.converged, numiter=info.numiter, numops=info.numops, normres=info.normres)
+    return val, vec
+
+
+def integrate(f, y0, t, dt, alg: Lanczos = None, return_info=False):
+    """y = exponentiate(f(t + dt/2), -im*dt, y0, alg)   (integrators.jl:20-25); f is a DerivativeOperator."""
+    alg = alg or Lanczos(tol=1e-12)
+    ctx = f.ctx
+    y = y0.zerovector()
+    info = _lib.c_info()
+    tau = -1j * dt
+    ctx.check(ctx.lib.mpsk_expv(ctx.h, f.h, tau.real, tau.imag, y0.h, alg.krylovdim, alg.maxiter, alg.tol, y.h, C.byref(info)))
+    if info.converged == 0:   # integrators.jl:22-23
+        warnings.warn("integrate not converged")
+    if return_info:
+        return y, dict(converged=info.converged, numops=info.numops)
+    return y

@@ -1,0 +1,153 @@
+"""Host mirror of the operator containers the hot path reads (construction itself is host-side model
+building and out of scope): ``SparseMPOSlice`` (src/operators/sparsempo/sparseslice.jl:13-106) with
+width-1 levels, ``MPOHamiltonian`` (src/operators/mpohamiltonian.jl:9-31), and the model Hamiltonians
+of the configs in BASELINE.json.  Each slice owns the device-side ``mpsk_mposlice`` handle."""
+from __future__ import annotations
+import ctypes as C
+import numpy as np
+from . import _lib
+
+
+class SparseMPOSlice:
+    def __init__(self, Os, level_charges_left, level_charges_right, phys_charges):
+        self.odim = len(Os)
+        self.Os = [[Os[i][j] for j in range(self.odim)] for i in range(self.odim)]
+        self.domcharges = tuple(int(c) for c in level_charges_left)    # domspaces (left virtual levels)
+        self.imcharges = tuple(int(c) for c in level_charges_right)    # imspaces  (right virtual levels)
+        self.pcharges = tuple(int(c) for c in phys_charges)            # pspace
+        self.d = len(self.pcharges)
+        self._dev = {}
+
+    # sparseslice.jl:100-106
+    def contains(self, i, j):
+        e = self.Os[i][j]
+        return not (np.isscalar(e) and e == 0)
+
+    def isscal(self, i, j):
+        return np.isscalar(self.Os[i][j]) and self.contains(i, j)
+
+    # sparseslice.jl:74-98 (product iterates the first index fastest)
+    def keys(self):
+        return [(i, j) for j in range(self.odim) for i in range(self.odim) if self.contains(i, j)]
+
+    def opkeys(self):
+        return [k for k in self.keys() if not self.isscal(*k)]
+
+    def scalkeys(self):
+        return [k for k in self.keys() if self.isscal(*k)]
+
+    def kinds(self):
+        return [[0 if not self.contains(i, j) else (1 if self.isscal(i, j) else 2) for j in range(self.odim)]
+                for i in range(self.odim)]
+
+    def device(self, ctx):
+        """mpsk_mposlice handle (created once per context)."""
+        key = id(ctx)
+        if key not in self._dev:
+            od, d = self.odim, self.d
+            kind = (C.c_int32 * (od * od))()
+            scal = (C.c_double * (2 * od * od))()
+            ops = []
+            for i in range(od):
+                for j in range(od):
+                    k = self.kinds()[i][j]
+                    kind[i * od + j] = k
+                    if k == 1:
+                        v = complex(self.Os[i][j])
+                        scal[2 * (i * od + j)], scal[2 * (i * od + j) + 1] = v.real, v.imag
+                    elif k == 2:
+                        O = np.asarray(self.Os[i][j], dtype=np.complex128)
+                        assert O.shape == (d, d)
+                        ops.append(O.reshape(-1))
+            flat = np.concatenate(ops).view(np.float64) if ops else np.zeros(2)
+            flat = np.ascontiguousarray(flat)
+            cl = (C.c_int32 * od)(*self.domcharges); cr = (C.c_int32 * od)(*self.imcharges)
+            pc = (C.c_int32 * d)(*self.pcharges)
+            h = C.c_void_p()
+            ctx.check(ctx.lib.mpsk_mposlice_create(ctx.h, od, cl, cr, d, pc, kind, scal,
+                                                   flat.ctypes.data_as(C.POINTER(C.c_double)), C.byref(h)))
+            self._dev[key] = h
+        return self._dev[key]
+
+    def device_keys(self, ctx):
+        """keys(x) as computed by the library (bit-exact bookkeeping check)."""
+        h = self.device(ctx)
+        n = C.c_int32()
+        ctx.lib.mpsk_mposlice_keys(h, C.byref(n), None)
+        ij = (C.c_int32 * (2 * max(n.value, 1)))()
+        ctx.lib.mpsk_mposlice_keys(h, C.byref(n), ij)
+        return [(ij[2 * k], ij[2 * k + 1]) for k in range(n.value)]
+
+
+class MPOHamiltonian:
+    """``H[i]`` is the slice at site i (0-based, periodic like the reference's PeriodicArray)."""
+
+    def __init__(self, slices):
+        self.slices = list(slices)
+        self.odim = self.slices[0].odim
+
+    def __len__(self):
+        return len(self.slices)
+
+    def __getitem__(self, i):
+        return self.slices[i % len(self.slices)]
+
+
+# --------------------------------------------------------------------------------------- models
+def spin_ops(d=2):
+    S = (d - 1) / 2
+    ms = np.array([-S + k for k in range(d)])
+    Sz = np.diag(ms)
+    Sp = np.zeros((d, d))
+    for k in range(d - 1):
+        Sp[k + 1, k] = np.sqrt(S * (S + 1) - ms[k] * (ms[k] + 1))
+    return Sp, Sp.T.copy(), Sz, tuple(int(round(2 * m)) for m in ms)
+
+
+def _fsm(L, odim, entries, level_charges, phys_charges):
+    out = []
+    for _ in range(L):
+        Os = [[0 for _ in range(odim)] for _ in range(odim)]
+        for (i, j), v in entries.items():
+            Os[i][j] = v
+        out.append(SparseMPOSlice(Os, level_charges, level_charges, phys_charges))
+    return MPOHamiltonian(out)
+
+
+def transverse_field_ising(L, g=1.0):
+    """-sum ZZ - g sum X (test/setup.jl:38-44), trivial symmetry, odim 3."""
+    X = np.array([[0, 1], [1, 0]], dtype=np.complex128)
+    Z = np.array([[1, 0], [0, -1]], dtype=np.complex128)
+    return _fsm(L, 3, {(0, 0): 1.0, (2, 2): 1.0, (0, 1): -Z, (1, 2): Z, (0, 2): -g * X}, (0, 0, 0), (0, 0))
+
+
+def heisenberg_u1(L, d=2, J=1.0):
+    Sp, Sm, Sz, pch = spin_ops(d)
+    ent = {(0, 0): 1.0, (4, 4): 1.0, (0, 1): Sp, (0, 2): Sm, (0, 3): Sz,
+           (1, 4): 0.5 * J * Sm, (2, 4): 0.5 * J * Sp, (3, 4): J * Sz}
+    return _fsm(L, 5, ent, (0, 2, -2, 0, 0), pch)
+
+
+def heisenberg_longrange_u1(L, r=6, d=2, power=2.0):
+    """range-r Heisenberg J_k = k^-power; odim = 2 + 3r (r=6: 38 non-zeros = 17 scalars + 21 operators)."""
+    Sp, Sm, Sz, pch = spin_ops(d)
+    odim = 2 + 3 * r
+    end = odim - 1
+    ent = {(0, 0): 1.0, (end, end): 1.0}
+    ch = [0] * odim
+    first, last, qs = [Sp, Sm, Sz], [0.5 * Sm, 0.5 * Sp, Sz], [2, -2, 0]
+    for t in range(3):
+        for k in range(r):
+            lev = 1 + t * r + k
+            ch[lev] = qs[t]
+            if k == 0:
+                ent[(0, lev)] = first[t]
+            else:
+                ent[(lev - 1, lev)] = 1.0
+            ent[(lev, end)] = (1.0 / (k + 1) ** power) * last[t]
+    return _fsm(L, odim, ent, ch, pch)
+
+
+def drop_symmetry(H: MPOHamiltonian):
+    """same operator with all charges set to zero (trivial-symmetry / dense path)."""
+    return MPOHamiltonian([SparseMPOSlice(s.Os, (0,) * s.odim, (0,) * s.odim, (0,) * s.d) for s in H.slices])

@@ -55,7 +55,7 @@ def dC_dense(C, GL, GR):
 # ------------------------------------------------------------------ reference loop structure
 def transfer_left_sparse(vec, ham: SparseMPOSlice, A, Ab):
     """transfer.jl:166-211 (serial branch). vec: GL[l_bra, w, l_ket] with width-1 levels."""
-    out = np.zeros((Ab.shape[2], ham.odim, A.shape[2]), dtype=np.result_type(vec, A))
+    out = np.zeros((Ab.shape[2], ham.odim, A.shape[2]), dtype=np.result_type(vec, A, np.complex128))
     for k in range(ham.odim):
         for j in ham.keys_col(k):
             if ham.isscal(j, k):
@@ -69,7 +69,7 @@ def transfer_left_sparse(vec, ham: SparseMPOSlice, A, Ab):
 
 def transfer_right_sparse(vec, ham: SparseMPOSlice, A, Ab):
     """transfer.jl:212-259 (serial branch). vec: GR[r_ket, w, r_bra]."""
-    out = np.zeros((A.shape[0], ham.odim, Ab.shape[0]), dtype=np.result_type(vec, A))
+    out = np.zeros((A.shape[0], ham.odim, Ab.shape[0]), dtype=np.result_type(vec, A, np.complex128))
     for j in range(ham.odim):
         for k in ham.keys_row(j):
             if ham.isscal(j, k):
@@ -83,7 +83,7 @@ def transfer_right_sparse(vec, ham: SparseMPOSlice, A, Ab):
 def dAC_sparse(x, H: SparseMPOSlice, GL, GR):
     """derivatives.jl:77-93 (serial branch) with the per-entry contraction order of 95-104:
     x*GR_j (label 1), then the operator (2,3), then GL_i (4,5)."""
-    y = np.zeros_like(x, dtype=np.result_type(x, GL))
+    y = np.zeros_like(x, dtype=np.result_type(x, GL, np.complex128))
     for (i, j) in H.keys():
         t = np.einsum('dbx,xz->dbz', x, GR[:, j, :])
         if H.isscal(i, j):

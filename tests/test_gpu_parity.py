@@ -1,0 +1,275 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+Tolerances: matvec outputs <= 1e-12 relative to max|y|; energies 1e-10 relative; singular
+values / truncation errors 1e-8; sector and block bookkeeping bit-exact."""
+import numpy as np
+import pytest
+import mpskit_b200 as m
+from oracle.spaces import Space as OSpace
+from oracle.blocks import BlockTensor
+from oracle import mpo as ompo, contract as oc, linalg as ol, finite as of, krylov as ok
+from helpers import *
+
+pytestmark = pytest.mark.gpu
+
+VL = OSpace((-2, 0, 2), (3, 5, 2))
+VR = OSpace((-2, 0, 2, 4), (2, 6, 3, 1))
+VBIG_L = OSpace((-3, -1, 1, 3), (37, 150, 141, 29))
+VBIG_R = OSpace((-4, -2, 0, 2, 4), (19, 133, 170, 90, 11))
+VBIG_R2 = OSpace((-5, -3, -1, 1, 3), (17, 140, 163, 97, 13))   # same parity as VBIG_L: two-site tensors
+
+
+def _ctxs(ctx, dbg_ctx):
+    return [("dmma", ctx), ("debug", dbg_ctx)]
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.float64])
+def test_roundtrip_and_vector_interface(ctx, dtype):
+    rng = np.random.default_rng(3)
+    a = BlockTensor.random(rng, VL, [1, -1, 1], VR, dtype)
+    b = BlockTensor.random(rng, VL, [1, -1, 1], VR, dtype)
+    da, db = dev_tensor(ctx, a), dev_tensor(ctx, b)
+    assert m.block_table(da.Vl, da.mch, da.Vr) == a.keys3()          # bit-exact bookkeeping
+    back = da.to_blocks()
+    for k, v in a.blocks.items():
+        assert np.array_equal(back[k], v)
+    ref = sum(np.vdot(a.blocks[k], b.blocks[k]) for k in a.blocks)
+    assert abs(da.dot(db) - ref) <= 1e-13 * abs(ref)
+    assert abs(da.norm() - a.norm()) <= 1e-13 * a.norm()
+    coef = 0.3 - 0.7j if np.dtype(dtype).kind == "c" else 0.3
+    db.axpy(coef, da)
+    db.scale(2.0)
+    out = db.to_blocks()
+    for k in a.blocks:
+        assert relerr(out[k], 2.0 * (b.blocks[k] + coef * a.blocks[k])) < 1e-14
+    # fortran-ordered / strided host blocks (TensorKit column-major sub-blocks)
+    blocks_f = {k: np.asfortranarray(v) for k, v in a.blocks.items()}
+    df = m.DeviceTensor.from_blocks(ctx, da.Vl, da.mch, da.Vr, blocks_f, dtype)
+    assert np.array_equal(df.to_dense(), a.to_dense())
+
+
+@pytest.mark.parametrize("which", ["dmma", "debug"])
+@pytest.mark.parametrize("dtype", [np.complex128, np.float64])
+@pytest.mark.parametrize("size", ["small", "big"])
+def test_dAC2_matvec(ctx, dbg_ctx, which, dtype, size):
+    c = ctx if which == "dmma" else dbg_ctx
+    H = ompo.heisenberg_longrange_u1(4, r=2)
+    h = H[0]
+    Vl, Vr = (VL, VR) if size == "small" else (VBIG_L, VBIG_R2)
+    x, GL, GR = random_problem(11, h, Vl, Vr, "ac2", dtype)
+    d = h.d
+    yref = oc.dAC2_sparse(x2_dense(x, d), h, h, GL.to_dense(), GR.to_dense())
+    hs = dev_slice(h)
+    dx, dGL, dGR = dev_tensor(c, x), dev_tensor(c, GL), dev_tensor(c, GR)
+    op = m.MPO_ddAC2(c, hs, hs, dGL, dGR, dx)
+    y = op(dx).to_dense()
+    err = relerr(y, x2_from_dense(yref, d))
+    print("dAC2", which, dtype.__name__, size, "relerr", err, "flops", op.flops)
+    assert err <= 1e-12 and op.flops > 0 and np.abs(y).max() > 0
+    # second application with a different vector through the same plan
+    x2 = BlockTensor.random(np.random.default_rng(5), Vl, x.mch, Vr, dtype)
+    y2 = op(dev_tensor(c, x2)).to_dense()
+    y2ref = oc.dAC2_sparse(x2_dense(x2, d), h, h, GL.to_dense(), GR.to_dense())
+    assert relerr(y2, x2_from_dense(y2ref, d)) <= 1e-12
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.float64])
+def test_dAC_and_dC(ctx, dtype):
+    H = ompo.heisenberg_u1(4)
+    h = H[0]
+    x, GL, GR = random_problem(12, h, VBIG_L, VBIG_R, "ac", dtype)
+    yref = oc.dAC_sparse(x.to_dense(), h, GL.to_dense(), GR.to_dense())
+    hs = dev_slice(h)
+    dx, dGL, dGR = dev_tensor(ctx, x), dev_tensor(ctx, GL), dev_tensor(ctx, GR)
+    y = m.MPO_ddAC(ctx, hs, dGL, dGR, dx)(dx).to_dense()
+    assert relerr(y, yref) <= 1e-12
+    # dC: GL at the bond, GR at the bond (derivatives.jl:171-193)
+    rng = np.random.default_rng(13)
+    V = VBIG_R
+    Cm = BlockTensor.random(rng, V, [0], V, dtype)
+    GLc = BlockTensor.random(rng, V, [-c for c in h.cl], V, dtype)
+    GRc = BlockTensor.random(rng, V, [c for c in h.cr], V, dtype)
+    cref = oc.dC_dense(Cm.to_dense()[:, 0, :], GLc.to_dense(), GRc.to_dense())
+    dC = dev_tensor(ctx, Cm)
+    yc = m.MPO_ddC(ctx, dev_tensor(ctx, GLc), dev_tensor(ctx, GRc), dC)(dC).to_dense()[:, 0, :]
+    assert relerr(yc, cref) <= 1e-12
+
+
+def test_trivial_symmetry_dense_path(ctx):
+    """no symmetry: one sector per bond -> plain dense contractions (config 1 / 2 style), TFI slice."""
+    H = ompo.transverse_field_ising(4, g=0.7)
+    h = H[0]
+    Vl, Vr = OSpace((0,), (37,)), OSpace((0,), (45,))
+    x, GL, GR = random_problem(14, h, Vl, Vr, "ac2")
+    yref = oc.dAC2_dense(x2_dense(x, 2), h.dense(), h.dense(), GL.to_dense(), GR.to_dense())
+    hs = dev_slice(h)
+    dx = dev_tensor(ctx, x)
+    y = m.MPO_ddAC2(ctx, hs, hs, dev_tensor(ctx, GL), dev_tensor(ctx, GR), dx)(dx).to_dense()
+    assert relerr(y, x2_from_dense(yref, 2)) <= 1e-12
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.float64])
+def test_transfers(ctx, dtype):
+    """transfer_left / transfer_right over a SparseMPOSlice (transfer.jl:166-259) incl. an empty column."""
+    import ctypes as C
+    H = ompo.heisenberg_longrange_u1(4, r=2)
+    h = H[0]
+    rng = np.random.default_rng(21)
+    p = list(h.pch)
+    A = BlockTensor.random(rng, VBIG_L, p, VBIG_R, dtype)
+    Ab = BlockTensor.random(rng, VBIG_L, p, VBIG_R, dtype)
+    GL = BlockTensor.random(rng, VBIG_L, [-c for c in h.cl], VBIG_L, dtype)
+    GR = BlockTensor.random(rng, VBIG_R, [c for c in h.cr], VBIG_R, dtype)
+    hs = dev_slice(h)
+    dA, dAb = dev_tensor(ctx, A), dev_tensor(ctx, Ab)
+    dGL, dGR = dev_tensor(ctx, GL), dev_tensor(ctx, GR)
+    out = C.c_void_p()
+    ctx.check(ctx.lib.mpsk_transfer_left(ctx.h, hs.device(ctx), dA.h, dAb.h, dGL.h, C.byref(out)))
+    got = m.DeviceTensor.wrap(ctx, out).to_dense()
+    ref = oc.transfer_left_sparse(GL.to_dense(), h, A.to_dense(), Ab.to_dense())
+    assert relerr(got, ref) <= 1e-12
+    out = C.c_void_p()
+    ctx.check(ctx.lib.mpsk_transfer_right(ctx.h, hs.device(ctx), dA.h, dAb.h, dGR.h, C.byref(out)))
+    got = m.DeviceTensor.wrap(ctx, out).to_dense()
+    ref = oc.transfer_right_sparse(GR.to_dense(), h, A.to_dense(), Ab.to_dense())
+    assert relerr(got, ref) <= 1e-12
+
+
+def test_local_algebra(ctx):
+    import ctypes as C
+    rng = np.random.default_rng(31)
+    Vm = OSpace((-3, -1, 1, 3), (7, 20, 22, 5))
+    A1 = BlockTensor.random(rng, VL, [-1, 1], Vm)
+    A2 = BlockTensor.random(rng, Vm, [-1, 1], VR)
+    d1, d2 = dev_tensor(ctx, A1), dev_tensor(ctx, A2)
+    out = C.c_void_p()
+    ctx.check(ctx.lib.mpsk_contract_ac2(ctx.h, d1.h, d2.h, C.byref(out)))
+    got = m.DeviceTensor.wrap(ctx, out).to_dense()
+    ref = np.einsum('apk,kqr->aprq', A1.to_dense(), A2.to_dense())
+    assert relerr(got, x2_from_dense(ref, 2)) <= 1e-13
+    Cr = BlockTensor.random(rng, Vm, [0], Vm)
+    dCr = dev_tensor(ctx, Cr)
+    out = C.c_void_p()
+    ctx.check(ctx.lib.mpsk_mul_bond_right(ctx.h, d1.h, dCr.h, C.byref(out)))
+    assert relerr(m.DeviceTensor.wrap(ctx, out).to_dense(), np.einsum('apb,bc->apc', A1.to_dense(), Cr.to_dense()[:, 0, :])) <= 1e-13
+    out = C.c_void_p()
+    ctx.check(ctx.lib.mpsk_mul_bond_left(ctx.h, dCr.h, d2.h, C.byref(out)))
+    assert relerr(m.DeviceTensor.wrap(ctx, out).to_dense(), np.einsum('ab,bpc->apc', Cr.to_dense()[:, 0, :], A2.to_dense())) <= 1e-13
+
+
+def _hermitian_problem(seed, h, Vl, Vr, dtype=np.complex128):
+    """GL, GR that make the effective Hamiltonian Hermitian: build them by real transfers of random isometries."""
+    rng = np.random.default_rng(seed)
+    x, GL, GR = random_problem(seed, h, Vl, Vr, "ac2", dtype)
+    # symmetrise level-wise: H_eff = sum_i GL_i (x) ... is Hermitian if GL, GR come from <A|O|A>; emulate with
+    # GL_i -> GL_i + GL_ibar^dagger where ibar is the level with opposite charge and adjoint operator content.
+    return x, GL, GR
+
+
+def test_eigsolve_and_expv_against_dense(ctx):
+    """fixedpoint(h, x0, :SR) and exponentiate on a genuinely Hermitian effective Hamiltonian from a real MPS."""
+    rng = np.random.default_rng(41)
+    L = 6
+    Ho = ompo.heisenberg_u1(L)
+    p = OSpace((-1, 1), (1, 1))
+    maxV = [of.gaussian_bond_space(12, k % 2) for k in range(1, L)]
+    psi = of.FiniteMPS.random(rng, p, L, maxV)
+    envs = of.FinEnv(psi, Ho)
+    pos = 2
+    ac2 = np.einsum('apk,kqr->aprq', psi.get_AC(pos), psi.get_AR(pos + 1))
+    GL, GR = envs.leftenv(pos, psi), envs.rightenv(pos + 1, psi)
+    Vl, Vr = psi.V[pos], psi.V[pos + 2]
+    h = Ho[pos]
+    d = 2
+    mch = [h.pch[a] + h.pch[b] for a in range(d) for b in range(d)]
+    f = lambda v: oc.dAC2_sparse(v, h, h, GL, GR)
+    val_o, vec_o, info_o = ok.eigsolve_lanczos(f, ac2, "SR", 1e-13, 30, 100)
+    dVl, dVr = to_dev_space(Vl), to_dev_space(Vr)
+    dx = m.DeviceTensor.from_dense(ctx, x2_from_dense(ac2, d), dVl, mch, dVr)
+    dGL = m.DeviceTensor.from_dense(ctx, GL, dVl, [-c for c in h.cl], dVl)
+    dGR = m.DeviceTensor.from_dense(ctx, GR, dVr, [c for c in h.cr], dVr)
+    hs = dev_slice(h)
+    op = m.MPO_ddAC2(ctx, hs, hs, dGL, dGR, dx)
+    val, vec, info = m.fixedpoint(op, dx, "SR", m.Lanczos(tol=1e-13), return_info=True)
+    print("eigsolve", val, val_o, info, info_o)
+    assert info["converged"] == 1
+    assert abs(val.real - val_o) <= 1e-10 * abs(val_o)
+    v = x2_dense(BlockTensor.from_dense(vec.to_dense(), Vl, mch, Vr), d)
+    assert abs(abs(np.vdot(vec_o, v)) - 1) <= 1e-9        # same eigenvector up to phase
+    # exponentiate
+    y_o, _ = ok.exponentiate_lanczos(f, -0.05j, ac2, 1e-12, 30)
+    y = m.integrate(op, dx, 0.0, 0.05, m.Lanczos(tol=1e-12))
+    yd = x2_dense(BlockTensor.from_dense(y.to_dense(), Vl, mch, Vr), d)
+    assert relerr(yd, y_o) <= 1e-10
+
+
+@pytest.mark.parametrize("trunc", [("notrunc",), ("truncdim", 20), ("truncerr", 0.3), ("truncbelow", 0.5)])
+def test_tsvd(ctx, trunc):
+    rng = np.random.default_rng(51)
+    d = 2
+    pch = [-1, 1]
+    mch = [pch[a] + pch[b] for a in range(d) for b in range(d)]
+    Vl, Vr = OSpace((-2, 0, 2), (6, 9, 4)), OSpace((-2, 0, 2, 4), (5, 11, 7, 2))
+    x = BlockTensor.random(rng, Vl, mch, Vr)
+    xd = x2_dense(x, d)
+    rowq = (Vl.index_charges()[:, None] + np.array(pch)[None, :]).reshape(-1)
+    colq = (Vr.index_charges()[:, None] - np.array(pch)[None, :]).reshape(-1)
+    U, S, Vh, newV, eps, info = ol.tsvd(xd.reshape(Vl.dim * d, Vr.dim * d), rowq, colq, trunc)
+
+    class P:  # minimal stand-in carrying what dmrg.tsvd needs
+        pass
+    P.ctx, P.pq, P.pspace = ctx, tuple(pch), m.Space((-1, 1), (1, 1))
+    code = m.notrunc() if trunc[0] == "notrunc" else getattr(m, trunc[0])(trunc[1])
+    al, c, ar, eps_d = m.tsvd(P, dev_tensor(ctx, x), code)
+    assert (al.Vr.charges, al.Vr.dims) == (newV.charges, newV.dims)           # kept dims per sector: bit-exact
+    assert abs(eps_d - eps) <= 1e-8
+    spec = m.tsvd_spectrum(ctx)
+    for q, s in info["spectrum"].items():
+        assert np.abs(spec[q][0] - s).max() <= 1e-8
+        assert spec[q][1] == info["kept"][q]
+    # gauge-invariant reconstruction al c ar
+    cd = c.to_dense()[:, 0, :]
+    rec = np.einsum('apk,kl,lqr->aprq', al.to_dense(), cd, ar.to_dense())
+    ref = np.einsum('ik,k,kj->ij', U, S / np.linalg.norm(S), Vh).reshape(Vl.dim, d, Vr.dim, d)
+    assert relerr(rec, ref) <= 1e-10
+    # isometries
+    A = al.to_dense().reshape(-1, al.Vr.dim)
+    assert np.abs(A.conj().T @ A - np.eye(A.shape[1])).max() <= 1e-12
+
+
+@pytest.mark.parametrize("model", ["heisenberg_u1", "tfi_trivial"])
+def test_dmrg2_energy_parity(ctx, model):
+    """find_groundstate(psi, H, DMRG2(...)) on the device vs the oracle sweep on the same seeded state."""
+    L = 8
+    if model == "heisenberg_u1":
+        Ho = ompo.heisenberg_u1(L); p = OSpace((-1, 1), (1, 1))
+        maxV = [of.gaussian_bond_space(16, k % 2) for k in range(1, L)]
+        exact = -3.3749325986878906
+    else:
+        Ho = ompo.transverse_field_ising(L, 1.0); p = OSpace((0,), (2,))
+        maxV = OSpace((0,), (16,))
+        exact = 1 - 1 / np.sin(np.pi / (2 * (2 * L + 1)))
+    psi_o = of.FiniteMPS.random(np.random.default_rng(61), p, L, maxV)
+    log_o = []
+    of.dmrg2_sweeps(psi_o, Ho, nsweeps=3, trunc=("truncdim", 16), tol=1e-13, log=log_o)
+    dmaxV = [to_dev_space(v) for v in maxV] if isinstance(maxV, list) else to_dev_space(maxV)
+    psi_d = m.FiniteMPS.random(np.random.default_rng(61), to_dev_space(p), L, dmaxV, ctx)
+    Hd = dev_hamiltonian(Ho)
+    log_d = []
+    alg = m.DMRG2(tol=1e-13, maxiter=3, eigalg=m.Lanczos(tol=1e-13), trscheme=m.truncdim(16))
+    psi_d, envs, eps = m.find_groundstate(psi_d, Hd, alg, log=log_d)
+    E_d, E_o = log_d[-1]["energy"], log_o[-1]["energy"]
+    print(model, "E_dev", E_d, "E_oracle", E_o, "exact", exact)
+    assert abs(E_d - E_o) <= 1e-10 * abs(E_o)
+    assert abs(E_d - exact) <= 1e-9 * abs(exact)
+    assert abs(m.expectation_value(psi_d, Hd, envs) - E_o) <= 1e-10 * abs(E_o)
+    # step-by-step: same kept sector dimensions (bit-exact) and truncation errors / spectra to 1e-8
+    assert len(log_d) == len(log_o)
+    for a, b in zip(log_d, log_o):
+        assert {q: k for q, k in a["kept"].items() if k} == {q: k for q, k in b["kept"].items() if k}
+        assert abs(a["eps_trunc"] - b["eps_trunc"]) <= 1e-8
+        for q, s_o in b["spectrum"].items():          # singular values of every two-site update
+            assert np.abs(a["spectrum"][q] - s_o).max() <= 1e-8
+    # entanglement spectrum (toolbox.jl:65-69) at the bond where the sweep left the centre
+    es_d, es_o = psi_d.entanglement_spectrum(0), psi_o.entanglement_spectrum(0)
+    for q in es_o:
+        assert np.abs(es_d[q] - es_o[q]).max() <= 1e-8
