@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""Benchmark of the north-star hot path: the two-site effective-Hamiltonian (ddAC2) matvec of config 3(ii)
+(finite spin-1/2 Heisenberg, U(1), D=4096, range-6 MPO with chi=20), complex128.
+
+One step = one matvec y = H_eff x through the C ABI of libmpskit_b200 (3 kernel launches + 2 staging copies).
+`value`: inputs resident in HBM.  `e2e`: host x -> upload -> matvec -> download y inside the timed region.
+`--impl reference`: the CPU oracle port (numpy/OpenBLAS block-sparse restatement in the reference's own
+contraction order) on the box's host cores; Julia is not available so the reference itself cannot run.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ddAC2_matvec_fp64_tflops"
+UNIT = "TFLOP/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--D", type=int, default=4096)
+    ap.add_argument("--range", type=int, default=6, dest="r")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(D, r):
+    return (f"config 3(ii): finite spin-1/2 Heisenberg L=100 U(1) DMRG2, centre-bond ddAC2 matvec, D={D}, "
+            f"range-{r} MPO chi={2 + 3 * r}, sigma=1.5 sector recipe")
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().strip().splitlines():
+            c = [t.strip() for t in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            busy = [s for s in sm if s > 0.5 * max(sm)] or sm
+            out = {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+def oracle_problem(w, d=2):
+    """device inputs -> oracle BlockTensors (same numbers) + oracle slice"""
+    from oracle.spaces import Space as OSpace
+    from oracle.blocks import BlockTensor
+    from oracle import mpo as ompo
+
+    def conv(t):
+        Vl = OSpace(t.Vl.charges, t.Vl.dims, t.Vl.modulus); Vr = OSpace(t.Vr.charges, t.Vr.dims, t.Vr.modulus)
+        return BlockTensor(Vl, t.mch, Vr, t.dtype, t.to_blocks())
+    h = w["h"]
+    oh = ompo.SparseMPOSlice(h.Os, h.domcharges, h.imcharges, h.pcharges)
+    return conv(w["x"]), conv(w["GL"]), conv(w["GR"]), oh
+
+
+def cpu_matvec_time(x, GL, GR, oh, reps=1):
+    from oracle.contract import dAC2_blocks
+    best = 1e30
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        y = dAC2_blocks(x, oh, oh, GL, GR)
+        best = min(best, time.perf_counter() - t0)
+    return best, y
+
+
+def run_reference(args):
+    """CPU arm: the oracle port of the reference algorithm, all host threads (OpenBLAS), bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle.spaces import Space as OSpace
+    from oracle.blocks import BlockTensor
+    from oracle import mpo as ompo
+    from oracle.contract import dAC2_blocks
+    sys.path.insert(0, os.path.join(ROOT, "mpskit.jl_b200"))
+    # bounded sample: largest D <= args.D of the same recipe whose (warmup + steps) matvecs fit in ~150 s of CPU time
+    per1024 = 1.3 * 8.0 / max(os.cpu_count() or 8, 1)
+    Ds = args.D
+    while Ds > 512 and (args.steps + args.warmup) * per1024 * (Ds / 1024.0) ** 3 > 150.0:
+        Ds //= 2
+    cs = [c for c in range(-10, 11) if c % 2 == 0]
+    g = np.array([np.exp(-(c / 2) ** 2 / (2 * 1.5 ** 2)) for c in cs])
+    n = np.rint(Ds * g / g.sum()).astype(int)
+    n[int(np.argmin(np.abs(np.array(cs))))] += Ds - n.sum()
+    V = OSpace.from_dict({c: int(k) for c, k in zip(cs, n) if k > 0})
+    H = ompo.heisenberg_longrange_u1(2, r=args.r)
+    h = H[0]
+    rng = np.random.default_rng(20240213 + 3000)
+    mch = [h.pch[a] + h.pch[b] for a in range(2) for b in range(2)]
+    x = BlockTensor.random(rng, V, mch, V)
+    GL = BlockTensor.random(rng, V, [-c for c in h.cl], V)
+    GR = BlockTensor.random(rng, V, [c for c in h.cr], V)
+    flops = algorithmic_flops(V, h, mch)
+    for _ in range(args.warmup):
+        dAC2_blocks(x, h, h, GL, GR)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        dAC2_blocks(x, h, h, GL, GR)
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    val = flops / dt / 1e12
+    sample = f"same workload recipe at D={Ds} (algorithmic flops {flops:.3e} per matvec), numpy/OpenBLAS block-sparse port in reference contraction order"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "c128", "data": "synthetic", "config": {"workload": workload_name(args.D, args.r), "sample_D": Ds},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def algorithmic_flops(V, h, mch):
+    """SURVEY.md 8d F_AC2 for square centre-bond spaces: optimal-order GEMM flops (complex: kappa = 8)."""
+    q = dict(zip(V.charges, V.dims))
+    cl = h.cl if hasattr(h, "cl") else h.domcharges
+    cr = h.cr if hasattr(h, "cr") else h.imcharges
+    F = 0.0
+    for qb, nb in q.items():
+        MA = sum(q.get(qb + c, 0) for c in cl)
+        NA = sum(q.get(qb + s, 0) for s in mch)
+        F += 8.0 * MA * NA * nb
+    for qa, na in q.items():
+        for s in mch:
+            nz = q.get(qa + s, 0)
+            if not nz:
+                continue
+            K = sum(q.get(qa + s - c, 0) for c in cr)
+            F += 8.0 * nz * na * K
+    return F
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import mpskit_b200 as m
+    from mpskit_b200.workloads import cfg3_matvec
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = m.Context(local)
+    stream = torch.cuda.Stream()          # a real (non-default) stream: torch events and the library share it
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+
+    # N > 1: the sector-row panels of y are sharded over ranks; until that lands each rank runs a replica
+    w = cfg3_matvec(ctx, args.D, r=args.r)
+    op, x = w["op"], w["x"]
+    y = x.zerovector()
+    flops = op.flops
+    for _ in range(max(args.warmup, 3)):
+        op.apply_into(x, y)
+    ctx.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = ctx.launch_count()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        op.apply_into(x, y)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = ctx.launch_count() - l0
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop() if sampler else None
+    value = world * flops / (ms * 1e-3) / 1e12     # replicas: every rank applies the full operator
+
+    # per-kernel timing of the dominant kernel (grouped DMMA GEMM): time stage A + stage C launches alone
+    e2e = None
+    if rank == 0 and not args.no_e2e:
+        xb = {k: torch.from_numpy(v).pin_memory().numpy() for k, v in x.to_blocks().items()}   # pinned host blocks
+        yb = {k: torch.from_numpy(np.empty_like(v)).pin_memory().numpy() for k, v in xb.items()}
+        bytes_x = sum(b.nbytes for b in xb.values())
+        for _ in range(2):
+            xd = m.DeviceTensor.from_blocks(ctx, x.Vl, x.mch, x.Vr, xb); op.apply_into(xd, y); y.to_blocks(yb); xd.free()
+        nrep = max(3, min(args.steps, 10))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(nrep):
+            xd = m.DeviceTensor.from_blocks(ctx, x.Vl, x.mch, x.Vr, xb)
+            op.apply_into(xd, y)
+            y.to_blocks(yb)
+            xd.free()
+        dt = (time.perf_counter() - t0) / nrep
+        e2e = {"value": flops / dt / 1e12, "unit": UNIT, "h2d_bytes_per_step": bytes_x, "d2h_bytes_per_step": bytes_x,
+               "ms_per_step": dt * 1e3}
+
+    # roofline denominator: FP64 tensor (DMMA) peak is not in MEASURED_PEAKS.json -> measure cuBLAS zgemm live
+    roofline = None
+    if rank == 0:
+        n = 4096
+        a = torch.randn(n, n, dtype=torch.complex128, device="cuda"); b = torch.randn(n, n, dtype=torch.complex128, device="cuda")
+        (a @ b); torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(3):
+            s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
+            s0.record(); (a @ b); s1.record(); torch.cuda.synchronize()
+            best = min(best, s0.elapsed_time(s1))
+        peak = 8.0 * n ** 3 / (best * 1e-3) / 1e12
+        del a, b
+        # the two GEMM launches carry all the algorithmic flops; time them in isolation over the same inputs
+        gm = gemm_only_ms(ctx, op, x, y, stream, torch, max(3, min(args.steps, 10)))
+        roofline = {"bound": "tensor", "kernel": "gemm_dmma_kernel<complex> (stage A + stage C of one matvec)",
+                    "achieved": flops / (gm * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                    "frac": flops / (gm * 1e-3) / 1e12 / peak, "traffic": None,
+                    "peak_source": "live torch.matmul complex128 4096^3 (cuBLAS zgemm) on this GPU; DMMA microbenchmark "
+                                   "profiles/r01_peak_fp64_microbench.json gives 36.99; MEASURED_PEAKS.json has no FP64 entry",
+                    "gemm_ms_per_matvec": gm, "share_of_step": gm / ms}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        try:
+            ox, oGL, oGR, oh = oracle_problem(w)
+            t, yo = cpu_matvec_time(ox, oGL, oGR, oh)
+            yd = y.to_blocks()
+            err = max(float(np.abs(yd[k] - v).max()) for k, v in yo.blocks.items()) / max(float(np.abs(v).max()) for v in yo.blocks.values())
+            cpu = {"value": flops / t / 1e12, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                   "sample": f"one full-size matvec of the same inputs ({t:.1f} s), numpy/OpenBLAS block-sparse port in the reference's "
+                             f"contraction order; max rel. deviation GPU vs CPU {err:.2e}"}
+        except MemoryError:
+            cpu = None
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak" if world > 1 else "strong", "vs_baseline": None, "dtype": "c128",
+                "data": "synthetic",
+                "config": {"workload": workload_name(args.D, args.r), "D": args.D, "chi": 2 + 3 * args.r, "flops_per_matvec": flops,
+                           "l2": "inputs larger than L2 (x 192 MB, environments 2 x 0.97 GB, intermediates 7.6 GB)",
+                           "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (row-panel sharding: see DESIGN.md)"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def gemm_only_ms(ctx, op, x, y, stream, torch, reps):
+    """average duration of the GEMM launches of one matvec (CUDA events on the launching stream)."""
+    import ctypes as C
+    lib = ctx.lib
+    if not hasattr(lib, "mpsk_op_time_gemms"):
+        return float("nan")
+    lib.mpsk_op_time_gemms.restype = C.c_int32
+    lib.mpsk_op_time_gemms.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_double)]
+    out = C.c_double()
+    ctx.check(lib.mpsk_op_time_gemms(ctx.h, op.h, reps, C.byref(out)))
+    return out.value
+
+
+if __name__ == "__main__":
+    main()

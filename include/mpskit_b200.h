@@ -108,6 +108,8 @@ int32_t mpsk_op_create(mpsk_ctx* ctx, int32_t kind, const mpsk_mposlice* h1, con
                        const mpsk_tensor* GL, const mpsk_tensor* GR, const mpsk_tensor* x_like, mpsk_op** out);
 void mpsk_op_free(mpsk_ctx* ctx, mpsk_op* op);
 double mpsk_op_flops(const mpsk_op* op);                           /* algorithmic real flops of one apply */
+/* measurement hook: mean device time (ms) of the grouped-GEMM launches of one apply (CUDA events on the context stream) */
+int32_t mpsk_op_time_gemms(mpsk_ctx* ctx, const mpsk_op* op, int32_t reps, double* ms_out);
 /* y = h(x): dC / dAC / dAC2 (derivatives.jl:77-197). */
 int32_t mpsk_op_apply(mpsk_ctx* ctx, const mpsk_op* op, const mpsk_tensor* x, mpsk_tensor* y);
 /* fixedpoint(h, x0, which, alg) (src/algorithms/fixedpoint.jl:9-30): Krylov eigensolve on the device. */

@@ -77,6 +77,7 @@ PROTOTYPES = {
     "mpsk_op_create": (C.c_int32, [_P, C.c_int32, _P, _P, _P, _P, _P, _PP]),
     "mpsk_op_free": (None, [_P, _P]),
     "mpsk_op_flops": (C.c_double, [_P]),
+    "mpsk_op_time_gemms": (C.c_int32, [_P, _P, C.c_int32, _DP]),
     "mpsk_op_apply": (C.c_int32, [_P, _P, _P, _P]),
     "mpsk_eigsolve": (C.c_int32, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, _DP, _DP, _P, C.POINTER(c_info)]),
     "mpsk_expv": (C.c_int32, [_P, _P, C.c_double, C.c_double, _P, C.c_int32, C.c_int32, C.c_double, _P, C.POINTER(c_info)]),

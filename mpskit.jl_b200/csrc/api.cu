@@ -52,6 +52,7 @@ void mpsk_destroy(mpsk_ctx* ctx) {
   c->release_cache();
   for (auto& kv : c->sizes) cudaFree(kv.first);
   if (c->h_scratch) cudaFreeHost(c->h_scratch);
+  if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
 }
@@ -104,6 +105,20 @@ int32_t mpsk_tensor_zeros(mpsk_ctx* ctx, const mpsk_space* Vl, int32_t nm, const
   return MPSK_OK;
 }
 
+static bool contiguous_rm(int64_t nl, int64_t nr, int64_t sl, int64_t sr) { return sr == 1 && (sl == nr || nl == 1); }
+static bool contiguous_cm(int64_t nl, int64_t nr, int64_t sl, int64_t sr) { return sl == 1 && (sr == nl || nr == 1); }
+
+static void* pinned_stage(Ctx* c, size_t bytes) {
+  if (c->h_stage_bytes < bytes) {
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    c->h_stage = nullptr; c->h_stage_bytes = 0;
+    size_t want = bytes + bytes / 4;
+    if (cudaMallocHost(&c->h_stage, want) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    c->h_stage_bytes = want;
+  }
+  return c->h_stage;
+}
+
 int32_t mpsk_tensor_upload(mpsk_ctx* ctx, const mpsk_space* Vl, int32_t nm, const int32_t* mcharge, const mpsk_space* Vr, int32_t dtype,
                            const mpsk_blockref* blocks, int32_t nblocks, mpsk_tensor** out) {
   Ctx* c = CTX(ctx);
@@ -112,28 +127,45 @@ int32_t mpsk_tensor_upload(mpsk_ctx* ctx, const mpsk_space* Vl, int32_t nm, cons
   std::unique_ptr<Tensor> t(TEN(th));
   if ((int)t->blks.size() != nblocks) return c->fail(MPSK_ESPACE, "upload: %d blocks given, structure has %zu", nblocks, t->blks.size());
   const size_t es = t->esize();
-  int64_t total = 0;
-  for (const Blk& b : t->blks) total += t->Vl.n[b.jl] * t->Vr.n[b.jr];
-  if (total == 0) { *out = reinterpret_cast<mpsk_tensor*>(t.release()); return MPSK_OK; }
-  void* hstage = nullptr;
-  CUDA_TRY(c, cudaMallocHost(&hstage, total * es));
-  void* dstage = c->alloc(total * es);
-  if (!dstage) { cudaFreeHost(hstage); return MPSK_ENOMEM; }
-  std::vector<CopyTask> tasks;
-  int64_t off = 0;
+  int64_t total = 0, need_pack = 0;
   for (size_t i = 0; i < t->blks.size(); ++i) {
     const Blk& b = t->blks[i];
     const int64_t nl = t->Vl.n[b.jl], nr = t->Vr.n[b.jr];
-    if (!blocks[i].ptr) { cudaFreeHost(hstage); c->free(dstage); return c->fail(MPSK_EINVAL, "upload: block %zu has a null pointer", i); }
-    if (es == 16) pack_block((cplx*)hstage + off, (const cplx*)blocks[i].ptr, nl, nr, blocks[i].stride_l, blocks[i].stride_r);
-    else pack_block((double*)hstage + off, (const double*)blocks[i].ptr, nl, nr, blocks[i].stride_l, blocks[i].stride_r);
-    tasks.push_back(CopyTask{(char*)dstage + off * es, t->ptr(b.off), nr, 1, b.sl, b.sr, (int32_t)nl, (int32_t)nr, 0, 0, nullptr});
+    if (!blocks[i].ptr) return c->fail(MPSK_EINVAL, "upload: block %zu has a null pointer", i);
+    total += nl * nr;
+    if (!contiguous_rm(nl, nr, blocks[i].stride_l, blocks[i].stride_r) && !contiguous_cm(nl, nr, blocks[i].stride_l, blocks[i].stride_r)) need_pack += nl * nr;
+  }
+  if (total == 0) { *out = reinterpret_cast<mpsk_tensor*>(t.release()); return MPSK_OK; }
+  void* hstage = need_pack ? pinned_stage(c, need_pack * es) : nullptr;
+  if (need_pack && !hstage) return c->fail(MPSK_ENOMEM, "pinned staging allocation failed");
+  void* dstage = c->alloc(total * es);
+  if (!dstage) return MPSK_ENOMEM;
+  std::vector<CopyTask> tasks;
+  int64_t off = 0, hoff = 0;
+  for (size_t i = 0; i < t->blks.size(); ++i) {
+    const Blk& b = t->blks[i];
+    const int64_t nl = t->Vl.n[b.jl], nr = t->Vr.n[b.jr];
+    const int64_t sl = blocks[i].stride_l, sr = blocks[i].stride_r;
+    char* dptr = (char*)dstage + off * es;
+    if (contiguous_rm(nl, nr, sl, sr)) {
+      CUDA_TRY(c, cudaMemcpyAsync(dptr, blocks[i].ptr, nl * nr * es, cudaMemcpyHostToDevice, c->stream));
+      tasks.push_back(CopyTask{dptr, t->ptr(b.off), nr, 1, b.sl, b.sr, (int32_t)nl, (int32_t)nr, 0, 0, nullptr});
+    } else if (contiguous_cm(nl, nr, sl, sr)) {
+      CUDA_TRY(c, cudaMemcpyAsync(dptr, blocks[i].ptr, nl * nr * es, cudaMemcpyHostToDevice, c->stream));
+      tasks.push_back(CopyTask{dptr, t->ptr(b.off), 1, nl, b.sl, b.sr, (int32_t)nl, (int32_t)nr, 0, 0, nullptr});
+    } else {
+      char* hp = (char*)hstage + hoff * es;
+      if (es == 16) pack_block((cplx*)hp, (const cplx*)blocks[i].ptr, nl, nr, sl, sr);
+      else pack_block((double*)hp, (const double*)blocks[i].ptr, nl, nr, sl, sr);
+      CUDA_TRY(c, cudaMemcpyAsync(dptr, hp, nl * nr * es, cudaMemcpyHostToDevice, c->stream));
+      tasks.push_back(CopyTask{dptr, t->ptr(b.off), nr, 1, b.sl, b.sr, (int32_t)nl, (int32_t)nr, 0, 0, nullptr});
+      hoff += nl * nr;
+    }
     off += nl * nr;
   }
-  cudaError_t e = cudaMemcpyAsync(dstage, hstage, total * es, cudaMemcpyHostToDevice, c->stream);
-  int st = e == cudaSuccess ? run_copy_tasks(c, tasks, es == 16) : c->fail(MPSK_ECUDA, "H2D copy failed: %s", cudaGetErrorString(e));
+  int st = run_copy_tasks(c, tasks, es == 16);
   cudaStreamSynchronize(c->stream);
-  cudaFreeHost(hstage); c->free(dstage);
+  c->free(dstage);
   if (st != MPSK_OK) return st;
   *out = reinterpret_cast<mpsk_tensor*>(t.release());
   return MPSK_OK;
@@ -143,38 +175,53 @@ int32_t mpsk_tensor_download(mpsk_ctx* ctx, const mpsk_tensor* th, const mpsk_bl
   Ctx* c = CTX(ctx); const Tensor* t = CTEN(th);
   if ((int)t->blks.size() != nblocks) return c->fail(MPSK_ESPACE, "download: %d blocks given, structure has %zu", nblocks, t->blks.size());
   const size_t es = t->esize();
-  int64_t total = 0;
-  for (const Blk& b : t->blks) total += t->Vl.n[b.jl] * t->Vr.n[b.jr];
+  int64_t total = 0, need_pack = 0;
+  for (size_t i = 0; i < t->blks.size(); ++i) {
+    const Blk& b = t->blks[i];
+    const int64_t nl = t->Vl.n[b.jl], nr = t->Vr.n[b.jr];
+    total += nl * nr;
+    if (!contiguous_rm(nl, nr, blocks[i].stride_l, blocks[i].stride_r) && !contiguous_cm(nl, nr, blocks[i].stride_l, blocks[i].stride_r)) need_pack += nl * nr;
+  }
   if (total == 0) return MPSK_OK;
-  void* hstage = nullptr;
-  CUDA_TRY(c, cudaMallocHost(&hstage, total * es));
+  void* hstage = need_pack ? pinned_stage(c, need_pack * es) : nullptr;
+  if (need_pack && !hstage) return c->fail(MPSK_ENOMEM, "pinned staging allocation failed");
   void* dstage = c->alloc(total * es);
-  if (!dstage) { cudaFreeHost(hstage); return MPSK_ENOMEM; }
+  if (!dstage) return MPSK_ENOMEM;
   std::vector<CopyTask> tasks;
   int64_t off = 0;
-  for (const Blk& b : t->blks) {
+  for (size_t i = 0; i < t->blks.size(); ++i) {
+    const Blk& b = t->blks[i];
     const int64_t nl = t->Vl.n[b.jl], nr = t->Vr.n[b.jr];
-    tasks.push_back(CopyTask{t->ptr(b.off), (char*)dstage + off * es, b.sl, b.sr, nr, 1, (int32_t)nl, (int32_t)nr, 0, 0, nullptr});
+    const bool cm = !contiguous_rm(nl, nr, blocks[i].stride_l, blocks[i].stride_r) && contiguous_cm(nl, nr, blocks[i].stride_l, blocks[i].stride_r);
+    if (cm) tasks.push_back(CopyTask{t->ptr(b.off), (char*)dstage + off * es, b.sl, b.sr, 1, nl, (int32_t)nl, (int32_t)nr, 0, 0, nullptr});
+    else tasks.push_back(CopyTask{t->ptr(b.off), (char*)dstage + off * es, b.sl, b.sr, nr, 1, (int32_t)nl, (int32_t)nr, 0, 0, nullptr});
     off += nl * nr;
   }
   int st = run_copy_tasks(c, tasks, es == 16);
-  if (st == MPSK_OK) {
-    cudaError_t e = cudaMemcpyAsync(hstage, dstage, total * es, cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    if (e != cudaSuccess) st = c->fail(MPSK_ECUDA, "D2H copy failed: %s", cudaGetErrorString(e));
+  if (st != MPSK_OK) { c->free(dstage); return st; }
+  off = 0; int64_t hoff = 0;
+  std::vector<std::pair<size_t, int64_t>> packed;   // (block, offset in hstage)
+  for (size_t i = 0; i < t->blks.size(); ++i) {
+    const Blk& b = t->blks[i];
+    const int64_t nl = t->Vl.n[b.jl], nr = t->Vr.n[b.jr];
+    const int64_t sl = blocks[i].stride_l, sr = blocks[i].stride_r;
+    const char* dptr = (const char*)dstage + off * es;
+    cudaError_t e;
+    if (contiguous_rm(nl, nr, sl, sr) || contiguous_cm(nl, nr, sl, sr)) e = cudaMemcpyAsync(blocks[i].ptr, dptr, nl * nr * es, cudaMemcpyDeviceToHost, c->stream);
+    else { e = cudaMemcpyAsync((char*)hstage + hoff * es, dptr, nl * nr * es, cudaMemcpyDeviceToHost, c->stream); packed.push_back({i, hoff}); hoff += nl * nr; }
+    if (e != cudaSuccess) { c->free(dstage); return c->fail(MPSK_ECUDA, "D2H copy failed: %s", cudaGetErrorString(e)); }
+    off += nl * nr;
   }
-  if (st == MPSK_OK) {
-    off = 0;
-    for (size_t i = 0; i < t->blks.size(); ++i) {
-      const Blk& b = t->blks[i];
-      const int64_t nl = t->Vl.n[b.jl], nr = t->Vr.n[b.jr];
-      if (es == 16) unpack_block((cplx*)blocks[i].ptr, (const cplx*)hstage + off, nl, nr, blocks[i].stride_l, blocks[i].stride_r);
-      else unpack_block((double*)blocks[i].ptr, (const double*)hstage + off, nl, nr, blocks[i].stride_l, blocks[i].stride_r);
-      off += nl * nr;
-    }
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  c->free(dstage);
+  if (e != cudaSuccess) return c->fail(MPSK_ECUDA, "D2H copy failed: %s", cudaGetErrorString(e));
+  for (auto& pk : packed) {
+    const Blk& b = t->blks[pk.first];
+    const int64_t nl = t->Vl.n[b.jl], nr = t->Vr.n[b.jr];
+    if (es == 16) unpack_block((cplx*)blocks[pk.first].ptr, (const cplx*)hstage + pk.second, nl, nr, blocks[pk.first].stride_l, blocks[pk.first].stride_r);
+    else unpack_block((double*)blocks[pk.first].ptr, (const double*)hstage + pk.second, nl, nr, blocks[pk.first].stride_l, blocks[pk.first].stride_r);
   }
-  cudaFreeHost(hstage); c->free(dstage);
-  return st;
+  return MPSK_OK;
 }
 
 int32_t mpsk_tensor_fill_random(mpsk_ctx* ctx, mpsk_tensor* t, uint64_t seed) { return tensor_fill_random(CTX(ctx), TEN(t), seed); }
@@ -302,6 +349,33 @@ int32_t mpsk_op_create(mpsk_ctx* ctx, int32_t kind, const mpsk_mposlice* h1, con
 }
 void mpsk_op_free(mpsk_ctx*, mpsk_op* op) { delete reinterpret_cast<HeffOp*>(op); }
 double mpsk_op_flops(const mpsk_op* op) { return reinterpret_cast<const HeffOp*>(op)->flops; }
+
+// measurement hook for bench.py: average device time (ms) of the two grouped-GEMM launches of one matvec,
+// CUDA events on the launching stream, inputs as left by the last apply.
+int32_t mpsk_op_time_gemms(mpsk_ctx* ctx, const mpsk_op* oph, int32_t reps, double* ms_out) {
+  Ctx* c = CTX(ctx); const HeffOp* op = reinterpret_cast<const HeffOp*>(oph);
+  cudaEvent_t e0, e1;
+  CUDA_TRY(c, cudaEventCreate(&e0)); CUDA_TRY(c, cudaEventCreate(&e1));
+  double tot = 0;
+  for (int r = 0; r < reps; ++r) {
+    float a = 0, b = 0;
+    CUDA_TRY(c, cudaEventRecord(e0, c->stream));
+    MPSK_TRY(gemm_plan_run(c, op->gemmA.get()));
+    CUDA_TRY(c, cudaEventRecord(e1, c->stream));
+    CUDA_TRY(c, cudaEventSynchronize(e1));
+    CUDA_TRY(c, cudaEventElapsedTime(&a, e0, e1));
+    MPSK_TRY(mix_plan_run(c, op->mix.get()));
+    CUDA_TRY(c, cudaEventRecord(e0, c->stream));
+    MPSK_TRY(gemm_plan_run(c, op->gemmC.get()));
+    CUDA_TRY(c, cudaEventRecord(e1, c->stream));
+    CUDA_TRY(c, cudaEventSynchronize(e1));
+    CUDA_TRY(c, cudaEventElapsedTime(&b, e0, e1));
+    tot += a + b;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *ms_out = tot / reps;
+  return MPSK_OK;
+}
 
 static int as_kl(Ctx* c, const Tensor* t) { return t->form == F_KL ? MPSK_OK : c->fail(MPSK_EINTERNAL, "tensor is not in vector (KL) form"); }
 

@@ -52,6 +52,8 @@ struct Ctx {
   void* nccl = nullptr;         // ncclComm_t
   int rank = 0, nranks = 1;
   double* h_scratch = nullptr;  // pinned host scratch (scalars coming back from Krylov kernels)
+  void* h_stage = nullptr;      // cached pinned staging buffer for strided host blocks
+  size_t h_stage_bytes = 0;
   double* d_scratch = nullptr;  // device scratch for reductions
   size_t d_scratch_bytes = 0;
   TsvdSpectrum last_spectrum;

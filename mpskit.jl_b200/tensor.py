@@ -98,12 +98,15 @@ class DeviceTensor:
         return DeviceTensor(ctx, handle, Vl, list(mc)[:nm.value], Vr, np.complex128 if dt.value == _lib.C128 else np.float64)
 
     # ---- host transfer ------------------------------------------------------------------------
-    def to_blocks(self):
+    def to_blocks(self, out=None):
+        """download into {(m, l-sector): ndarray}; `out` may hold preallocated (e.g. pinned) blocks of any strides"""
         table = block_table(self.Vl, self.mch, self.Vr)
-        out = {}
+        out = {} if out is None else out
         refs = (_lib.c_blockref * max(len(table), 1))()
         for i, (m, jl, jr) in enumerate(table):
-            b = np.empty((self.Vl.dims[jl], self.Vr.dims[jr]), dtype=self.dtype)
+            b = out.get((m, jl))
+            if b is None:
+                b = np.empty((self.Vl.dims[jl], self.Vr.dims[jr]), dtype=self.dtype)
             out[(m, jl)] = b
             refs[i] = _lib.c_blockref(b.ctypes.data, b.strides[0] // b.itemsize, b.strides[1] // b.itemsize)
         self.ctx.check(self.ctx.lib.mpsk_tensor_download(self.ctx.h, self.h, refs, len(table)))
