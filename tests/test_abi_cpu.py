@@ -1,0 +1,101 @@
+"""CPU tests of the boundary: the C-ABI library loads, exports every symbol the header declares, and its integer
+bookkeeping matches the oracle bit-exactly.  No compute calls (no GPU here)."""
+import ctypes as C
+import os
+import re
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "mpskit_b200.h")).read()
+    return sorted(set(re.findall(r"^(?:int32_t|int64_t|void|double|const char\*)\s+(mpsk_[a-z0-9_]+)\s*\(", src, re.M)))
+
+
+def test_library_exports_every_declared_symbol():
+    import mpskit_b200 as m
+    from mpskit_b200 import _lib
+    lib = m.load_library()
+    syms = header_symbols()
+    assert len(syms) >= 40
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/mpskit_b200.h but not exported"
+        assert s in _lib.PROTOTYPES, f"{s} has no ctypes prototype"
+    assert lib.mpsk_version() >= 100
+
+
+def test_no_cpu_fallback():
+    """without a GPU context creation must fail loudly (MPSK_ENODEVICE), never fall back to the CPU"""
+    import mpskit_b200 as m
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("GPU present")
+    except ImportError:
+        pass
+    with pytest.raises(m.MpskError) as e:
+        m.Context(0)
+    assert e.value.code == -6
+
+
+def test_product_package_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "mpskit.jl_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "import oracle" not in src and "from oracle" not in src, fn
+
+
+def test_block_table_matches_oracle_bit_exactly():
+    import mpskit_b200 as m
+    from oracle.spaces import Space as OSpace
+    from oracle.blocks import BlockTensor
+    rng = np.random.default_rng(0)
+    for trial in range(50):
+        def rs():
+            k = rng.integers(1, 7)
+            ch = np.sort(rng.choice(np.arange(-8, 9), size=k, replace=False))
+            return OSpace(tuple(ch), tuple(rng.integers(1, 9, size=k)))
+        Vl, Vr = rs(), rs()
+        mch = [int(c) for c in rng.integers(-3, 4, size=rng.integers(1, 6))]
+        ref = BlockTensor.block_keys(Vl, mch, Vr)
+        got = m.block_table(m.Space(Vl.charges, Vl.dims), mch, m.Space(Vr.charges, Vr.dims))
+        assert got == [tuple(int(v) for v in t) for t in ref]
+    Vl = OSpace((0, 1), (3, 2), 2); Vr = OSpace((0, 1), (1, 4), 2)
+    assert m.block_table(m.Space((0, 1), (3, 2), 2), [1, 0], m.Space((0, 1), (1, 4), 2)) == \
+        [tuple(int(v) for v in t) for t in BlockTensor.block_keys(Vl, [1, 0], Vr)]
+
+
+def test_host_mirror_bookkeeping():
+    import mpskit_b200 as m
+    from oracle import mpo as ompo
+    for r in (1, 2, 6):
+        so = ompo.heisenberg_longrange_u1(4, r=r)[0]
+        sd = m.heisenberg_longrange_u1(4, r=r)[0]
+        assert sd.keys() == so.keys() and sd.kinds() == so.kinds()
+        assert sd.opkeys() == so.opkeys() and sd.scalkeys() == so.scalkeys()
+        assert sd.domcharges == so.cl and sd.pcharges == so.pch
+    from oracle import finite as of
+    from oracle.spaces import Space as OSpace
+    from mpskit_b200.workloads import gaussian_bond_space
+    for D in (16, 256, 4096):
+        for par in (0, 1):
+            assert gaussian_bond_space(D, par).as_dict() == of.gaussian_bond_space(D, par).as_dict()
+    p = m.Space((-1, 1), (1, 1))
+    Vd = m.virtual_spaces(p, 10, [gaussian_bond_space(16, k % 2) for k in range(1, 10)])
+    Vo = of.virtual_spaces(OSpace((-1, 1), (1, 1)), 10, [of.gaussian_bond_space(16, k % 2) for k in range(1, 10)])
+    assert [v.as_dict() for v in Vd] == [v.as_dict() for v in Vo]
+
+
+def test_bad_spaces_are_rejected_without_a_gpu():
+    import mpskit_b200 as m
+    from mpskit_b200 import _lib
+    lib = m.load_library()
+    q = (C.c_int32 * 2)(3, 1); n = (C.c_int64 * 2)(1, 1)         # not ascending
+    bad = _lib.c_space(2, q, n, 0)
+    good, keep = m.Space((0,), (1,)).c_struct()
+    mc = (C.c_int32 * 1)(0)
+    cnt = C.c_int32()
+    assert lib.mpsk_block_table(C.byref(bad), 1, mc, C.byref(good), C.byref(cnt), None, None, None) == _lib.ESPACE

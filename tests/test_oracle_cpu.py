@@ -1,0 +1,171 @@
+"""CPU tests (no GPU): the oracle against known answers, against itself (independent implementations) and against
+the committed golden vectors."""
+import os
+import numpy as np
+import scipy.linalg as sla
+from oracle.spaces import Space, fuse, infimum, dual
+from oracle.blocks import BlockTensor
+from oracle import mpo as ompo, contract as oc, linalg as ol, finite as of, krylov as ok
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def tfi_obc_energy(L, g):
+    """free-fermion ground energy of -sum ZZ - g sum X on an open chain"""
+    M = np.zeros((L, L))
+    for i in range(L):
+        M[i, i] = g
+        if i + 1 < L:
+            M[i + 1, i] = 1.0
+    return -np.linalg.svd(M, compute_uv=False).sum()
+
+
+def test_reference_logged_energy_tfi_L20():
+    """docs/src/examples/quantum1d/3.ising-dqpt/index.md:35-48: DMRG, L=20, D=10, g=-0.5 -> E = -20.40021786703
+    (a number produced by the reference itself); the sign of g is a gauge choice."""
+    H = ompo.transverse_field_ising(20, 0.5)
+    psi = of.FiniteMPS.random(np.random.default_rng(1), Space((0,), (2,)), 20, Space((0,), (10,)))
+    log = []
+    psi, envs, eps = of.dmrg_sweeps(psi, H, nsweeps=5, log=log)
+    assert abs(log[-1]["energy"] - (-20.40021786703)) < 2e-11
+    assert abs(log[-1]["energy"] - tfi_obc_energy(20, 0.5)) < 1e-10
+    assert abs(sum(of.expectation_value(psi, H, envs)).real - log[-1]["energy"]) < 1e-10
+
+
+def test_dmrg2_equals_exact_diagonalisation():
+    """test/algorithms.jl:512-540 pins DMRG == ED (atol 1e-5 there); here to 1e-12 with U(1) symmetry."""
+    L = 8
+    H = ompo.heisenberg_u1(L)
+    E0 = np.linalg.eigvalsh(ompo.dense_hamiltonian(H))[0]
+    psi = of.FiniteMPS.random(np.random.default_rng(7), Space((-1, 1), (1, 1)), L, [of.gaussian_bond_space(16, k % 2) for k in range(1, L)])
+    log = []
+    of.dmrg2_sweeps(psi, H, nsweeps=3, trunc=("truncdim", 16), log=log)
+    assert abs(log[-1]["energy"] - E0) < 1e-12
+    assert abs(E0 - (-3.3749325986878906)) < 1e-12
+
+
+def test_mpo_structure_bookkeeping():
+    """chi = 20, 38 non-zeros = 17 scalars + 21 operators; keys() iterates i fastest."""
+    s = ompo.heisenberg_longrange_u1(4, r=6)[0]
+    assert (s.odim, len(s.keys()), len(s.scalkeys()), len(s.opkeys())) == (20, 38, 17, 21)
+    assert s.keys()[:3] == [(0, 0), (0, 1), (1, 2)]
+    assert s.isscal(0, 0) and not s.isscal(0, 1) and not s.contains(1, 0)
+    L = 6
+    Hd = ompo.dense_hamiltonian(ompo.heisenberg_longrange_u1(L, r=2))
+    Sp, Sm, Sz, _ = ompo.spin_ops(2)
+
+    def site(op, i):
+        out = np.eye(1)
+        for k in range(L):
+            out = np.kron(out, op if k == i else np.eye(2))
+        return out
+    ref = np.zeros((2 ** L, 2 ** L))
+    for i in range(L):
+        for r in (1, 2):
+            if i + r < L:
+                ref += (1.0 / r ** 2) * (0.5 * (site(Sp, i) @ site(Sm, i + r) + site(Sm, i) @ site(Sp, i + r)) + site(Sz, i) @ site(Sz, i + r))
+    assert np.abs(Hd - ref).max() < 1e-13
+
+
+def test_three_implementations_agree():
+    h = ompo.heisenberg_longrange_u1(4, r=2)[0]
+    Vl, Vr = Space((-2, 0, 2), (3, 5, 2)), Space((-2, 0, 2, 4), (2, 6, 3, 1))
+    rng = np.random.default_rng(1)
+    d = 2
+    x = BlockTensor.random(rng, Vl, [h.pch[a] + h.pch[b] for a in range(d) for b in range(d)], Vr)
+    GL = BlockTensor.random(rng, Vl, [-c for c in h.cl], Vl)
+    GR = BlockTensor.random(rng, Vr, [c for c in h.cr], Vr)
+    xd = x.to_dense().reshape(Vl.dim, d, d, Vr.dim).transpose(0, 1, 3, 2)
+    y1 = oc.dAC2_dense(xd, h.dense(), h.dense(), GL.to_dense(), GR.to_dense())
+    y2 = oc.dAC2_sparse(xd, h, h, GL.to_dense(), GR.to_dense())
+    y3 = oc.dAC2_blocks(x, h, h, GL, GR).to_dense().reshape(Vl.dim, d, d, Vr.dim).transpose(0, 1, 3, 2)
+    assert np.abs(y1 - y2).max() < 1e-12 and np.abs(y1 - y3).max() < 1e-12
+    A = BlockTensor.random(rng, Vl, list(h.pch), Space((-3, -1, 1, 3), (2, 4, 4, 2)))
+    tl1 = oc.transfer_left_dense(GL.to_dense(), h.dense(), A.to_dense(), A.to_dense())
+    tl2 = oc.transfer_left_sparse(GL.to_dense(), h, A.to_dense(), A.to_dense())
+    assert np.abs(tl1 - tl2).max() < 1e-12
+    Vm = A.Vr
+    GRm = BlockTensor.random(rng, Vm, [c for c in h.cr], Vm)
+    tr1 = oc.transfer_right_dense(GRm.to_dense(), h.dense(), A.to_dense(), A.to_dense())
+    tr2 = oc.transfer_right_sparse(GRm.to_dense(), h, A.to_dense(), A.to_dense())
+    assert np.abs(tr1 - tr2).max() < 1e-12
+    y1 = oc.dAC_dense(A.to_dense(), h.dense(), GL.to_dense(), GRm.to_dense())
+    assert np.abs(y1 - oc.dAC_sparse(A.to_dense(), h, GL.to_dense(), GRm.to_dense())).max() < 1e-12
+
+
+def test_effective_hamiltonian_is_hermitian_and_reproduces_energy():
+    """<AC2|dAC2|AC2> from transfer-built environments equals <psi|H|psi>."""
+    L = 6
+    H = ompo.heisenberg_u1(L)
+    psi = of.FiniteMPS.random(np.random.default_rng(3), Space((-1, 1), (1, 1)), L, [of.gaussian_bond_space(8, k % 2) for k in range(1, L)])
+    envs = of.FinEnv(psi, H)
+    pos = 2
+    ac2 = np.einsum('apk,kqr->aprq', psi.get_AC(pos), psi.get_AR(pos + 1))
+    GL, GR = envs.leftenv(pos, psi), envs.rightenv(pos + 1, psi)
+    f = lambda v: oc.dAC2_sparse(v, H[pos], H[pos + 1], GL, GR)
+    n = ac2.size
+    M = np.stack([f(e.reshape(ac2.shape)).reshape(-1) for e in np.eye(n, dtype=complex)], axis=1)
+    assert np.abs(M - M.conj().T).max() < 1e-12
+    T = psi.get_AC(0)
+    for i in range(1, L):
+        T = np.tensordot(T, psi.get_AR(i), axes=([-1], [0]))
+    v = T.reshape(-1)
+    Eref = np.vdot(v, ompo.dense_hamiltonian(H) @ v).real / np.vdot(v, v).real
+    assert abs(np.vdot(ac2, f(ac2)).real / np.vdot(ac2, ac2).real - Eref) < 1e-12
+
+
+def test_krylov_against_scipy():
+    rng = np.random.default_rng(5)
+    n = 60
+    A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)); A = A + A.conj().T
+    x0 = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    val, vec, info = ok.eigsolve_lanczos(lambda v: A @ v, x0, "SR", 1e-12, 30, 200)
+    assert info["converged"] and abs(val - np.linalg.eigvalsh(A)[0]) < 1e-10
+    y, info = ok.exponentiate_lanczos(lambda v: A @ v, -0.1j, x0, 1e-12, 30)
+    assert np.abs(y - sla.expm(-0.1j * A) @ x0).max() < 1e-9
+    B = rng.standard_normal((n, n)) * 0.1
+    lam, v, info = ok.eigsolve_arnoldi(lambda u: B @ u, x0, "LM", 1e-10, 30, 300)
+    assert abs(abs(lam) - np.abs(np.linalg.eigvals(B)).max()) < 1e-8
+    b = rng.standard_normal(n) + 0j
+    xs, info = ok.linsolve_gmres(lambda u: B @ u, b, np.zeros(n, complex), 1.0, -1.0, 1e-12, 30, 100)
+    assert np.abs((np.eye(n) - B) @ xs - b).max() < 1e-9
+
+
+def test_tsvd_and_qr_semantics():
+    rng = np.random.default_rng(9)
+    rowq = np.array([0, 0, 0, 2, 2, -2]); colq = np.array([0, 0, 2, 2, 2, 4])
+    M = (rng.standard_normal((6, 6)) + 1j * rng.standard_normal((6, 6))) * (rowq[:, None] == colq[None, :])
+    U, S, Vh, newV, eps, info = ol.tsvd(M, rowq, colq, ("notrunc",))
+    assert np.abs(U @ np.diag(S) @ Vh - M).max() < 1e-13 and eps == 0
+    assert newV.as_dict() == {0: 2, 2: 2}
+    U, S, Vh, newV, eps, info = ol.tsvd(M, rowq, colq, ("truncdim", 3))
+    allS = np.sort(np.concatenate(list(info["spectrum"].values())))
+    assert newV.dim == 3 and abs(eps - allS[0]) < 1e-14
+    Q, R, nv = ol.qrpos(M, rowq, colq)
+    assert np.abs(Q @ R - M).max() < 1e-13
+    Lm, Qm, nv = ol.lqpos(M, rowq, colq)
+    assert np.abs(Lm @ Qm - M).max() < 1e-13
+
+
+def test_spaces():
+    p = Space((-1, 1), (1, 1))
+    V = fuse(Space((0,), (1,)), p)
+    assert V.as_dict() == {-1: 1, 1: 1}
+    assert fuse(V, p).as_dict() == {-2: 1, 0: 2, 2: 1}
+    assert infimum(fuse(V, p), Space((0, 2), (1, 5))).as_dict() == {0: 1, 2: 1}
+    assert dual(Space((1, 3), (2, 4))).as_dict() == {-1: 2, -3: 4}
+    Vs = of.virtual_spaces(p, 6, Space.from_dict({c: 100 for c in range(-6, 7)}))
+    assert [v.dim for v in Vs] == [1, 2, 4, 8, 4, 2, 1]
+    assert of.gaussian_bond_space(4096, 0).as_dict() == {-10: 4, -8: 31, -6: 147, -4: 448, -2: 872, 0: 1092, 2: 872, 4: 448, 6: 147, 8: 31, 10: 4}
+
+
+def test_golden_vectors_are_reproduced():
+    g = np.load(os.path.join(GOLD, "contractions_u1.npz"))
+    h = ompo.heisenberg_longrange_u1(4, r=int(g["r"]))[0]
+    Vl = Space(*g["Vl"]); Vr = Space(*g["Vr"])
+    x2d = g["x2"].reshape(Vl.dim, 2, 2, Vr.dim).transpose(0, 1, 3, 2)
+    y2 = oc.dAC2_sparse(x2d, h, h, g["GL"], g["GR2"]).transpose(0, 1, 3, 2).reshape(Vl.dim, 4, Vr.dim)
+    assert np.abs(y2 - g["y2"]).max() <= 1e-13 * np.abs(g["y2"]).max()
+    assert np.abs(oc.transfer_left_sparse(g["GL"], h, g["A"], g["Ab"]) - g["tl"]).max() <= 1e-13 * np.abs(g["tl"]).max()
+    d = np.load(os.path.join(GOLD, "dmrg2_heisenberg_u1_L8_D16.npz"))
+    assert abs(d["energy"][-1] - (-3.3749325986878906)) < 1e-12
