@@ -46,6 +46,7 @@ typedef enum {
 enum { MPSK_F64 = 0, MPSK_C128 = 1 };                 /* scalar type (Defaults.eltype = ComplexF64, defaults.jl:18) */
 enum { MPSK_SR = 0, MPSK_LM = 1, MPSK_LR = 2 };       /* `which` of fixedpoint (fixedpoint.jl:9,19) */
 enum { MPSK_NOTRUNC = 0, MPSK_TRUNCDIM = 1, MPSK_TRUNCERR = 2, MPSK_TRUNCBELOW = 3 }; /* TensorKit truncation schemes used at dmrg.jl:75,96 */
+#define MPSK_TRUNC_NO_NORMALIZE 0x100   /* OR into mpsk_trunc.kind: skip normalize!(c) (TDVP2, tdvp.jl:124-126) */
 enum { MPSK_OP_DC = 0, MPSK_OP_DAC = 1, MPSK_OP_DAC2 = 2 };
 
 #define MPSK_FLAG_DEBUG_GEMM 1ull  /* route contractions through the one-thread-per-element cross-check kernel (tests only) */

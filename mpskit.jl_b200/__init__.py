@@ -10,7 +10,9 @@ from .operators import (SparseMPOSlice, MPOHamiltonian, transverse_field_ising, 
                         heisenberg_longrange_u1, drop_symmetry)
 from .derivatives import MPO_ddC, MPO_ddAC, MPO_ddAC2, ddC, ddAC, ddAC2  # noqa: F401
 from .fixedpoint import fixedpoint, integrate, Lanczos, Arnoldi  # noqa: F401
-from .finitemps import FiniteMPS, virtual_spaces  # noqa: F401
+from .finitemps import FiniteMPS, virtual_spaces, qrpos, lqpos  # noqa: F401
 from .environments import FinEnv, environments  # noqa: F401
-from .dmrg import (DMRG2, find_groundstate, find_groundstate_inplace, expectation_value, tsvd, contract_ac2,  # noqa: F401
+from .dmrg import (DMRG2, find_groundstate_inplace, expectation_value, tsvd, contract_ac2,  # noqa: F401
                    truncdim, truncerr, truncbelow, notrunc, tsvd_spectrum)
+from .algorithms import (DMRG, TDVP, TDVP2, find_groundstate, find_groundstate_dmrg_inplace, calc_galerkin,  # noqa: F401
+                         timestep, timestep_inplace)

@@ -1,0 +1,162 @@
+"""Single-site DMRG (src/algorithms/groundstate/dmrg.jl:14-55), calc_galerkin (src/algorithms/toolbox.jl:17-22) and
+finite TDVP / TDVP2 (src/algorithms/timestep/tdvp.jl:61-151) on device handles."""
+from __future__ import annotations
+import ctypes as C
+from dataclasses import dataclass, field
+import numpy as np
+from . import _lib
+from .tensor import DeviceTensor
+from .operators import SparseMPOSlice
+from .derivatives import ddAC, ddC, ddAC2
+from .fixedpoint import fixedpoint, integrate, Arnoldi, Lanczos
+from .environments import environments
+from .dmrg import tsvd, contract_ac2, truncerr, DMRG2, find_groundstate_inplace as _dmrg2_inplace
+
+
+@dataclass
+class DMRG:
+    """dmrg.jl:14-20"""
+    tol: float = 1e-12
+    maxiter: int = 100
+    eigalg: object = field(default_factory=Arnoldi)
+    verbosity: int = 0
+    finalize: object = None
+
+
+@dataclass
+class TDVP:
+    """tdvp.jl:14-19"""
+    integrator: object = field(default_factory=lambda: Lanczos(tol=1e-12))
+    tolgauge: float = 1e-14
+    gaugemaxiter: int = 100
+    finalize: object = None
+
+
+@dataclass
+class TDVP2:
+    """tdvp.jl:107-113"""
+    integrator: object = field(default_factory=lambda: Lanczos(tol=1e-12))
+    trscheme: tuple = field(default_factory=lambda: truncerr(1e-3))
+    finalize: object = None
+
+
+_unit_slices = {}
+
+
+def _overlap(psi, A, Abar):
+    """(Abar^dagger A)[a'; b'] = sum_{a,s} conj(Abar[a s; a']) A[a s; b'] -- the MPO-free transfer of the identity
+    (transfer.jl:18-25) expressed through the sparse-slice transfer with a one-level unit MPO."""
+    ctx = psi.ctx
+    key = (psi.pq, psi.pspace.modulus)
+    if key not in _unit_slices:
+        _unit_slices[key] = SparseMPOSlice([[1.0]], (0,), (0,), psi.pq)
+    sl = _unit_slices[key]
+    V = A.Vl
+    eye = np.zeros((V.dim, 1, V.dim), dtype=psi.dtype)
+    eye[:, 0, :] = np.eye(V.dim)
+    one = DeviceTensor.from_dense(ctx, eye, V, (0,), V, psi.dtype)
+    h = C.c_void_p()
+    ctx.check(ctx.lib.mpsk_transfer_left(ctx.h, sl.device(ctx), A.h, Abar.h, one.h, C.byref(h)))
+    out = DeviceTensor.wrap(ctx, h, psi.pspace.modulus)
+    one.free()
+    return out
+
+
+def calc_galerkin(psi, loc, envs):
+    """toolbox.jl:17-22: || AC' - AL AL^dagger AC' || with AC' = normalize(ddAC * AC)"""
+    h = ddAC(loc, psi, envs.opp, envs)
+    ac = h(psi.AC[loc])
+    h.free()
+    ac.scale(1.0 / ac.norm())
+    AL = psi.AL[loc]
+    ov = _overlap(psi, ac, AL)                       # AL^dagger AC'   [k; r]
+    hh = C.c_void_p()
+    psi.ctx.check(psi.ctx.lib.mpsk_mul_bond_right(psi.ctx.h, AL.h, ov.h, C.byref(hh)))
+    proj = DeviceTensor.wrap(psi.ctx, hh, psi.pspace.modulus)
+    ac.axpy(-1.0, proj)
+    out = ac.norm()
+    for t in (ac, ov, proj):
+        t.free()
+    return out
+
+
+def find_groundstate_dmrg_inplace(psi, H, alg: DMRG, envs=None, log=None):
+    """find_groundstate!(psi, H, alg::DMRG, envs) (dmrg.jl:22-55)"""
+    envs = envs if envs is not None else environments(psi, H)
+    L = len(psi)
+    eps = max(calc_galerkin(psi, pos, envs) for pos in range(L))
+    for it in range(alg.maxiter):
+        eps_s = np.zeros(L)
+        for pos in list(range(0, L - 1)) + list(range(L - 1, 0, -1)):
+            h = ddAC(pos, psi, H, envs)
+            val, vec, info = fixedpoint(h, psi.AC[pos], "SR", alg.eigalg, return_info=True)
+            h.free()
+            eps_s[pos] = max(eps_s[pos], calc_galerkin(psi, pos, envs))
+            psi.AC[pos] = vec
+            if log is not None:
+                log.append(dict(sweep=it, pos=pos, energy=val.real, numops=info["numops"]))
+        eps = eps_s.max()
+        if alg.finalize is not None:
+            psi, envs = alg.finalize(it, psi, H, envs)
+        if eps <= alg.tol:
+            break
+    return psi, envs, eps
+
+
+def find_groundstate(psi, H, alg, envs=None, log=None):
+    """find_groundstate(psi, H, alg) = find_groundstate!(copy(psi), H, alg, envs) (dmrg.jl:139-141)"""
+    if isinstance(alg, DMRG2):
+        return _dmrg2_inplace(psi.copy(), H, alg, envs, log)
+    if isinstance(alg, DMRG):
+        return find_groundstate_dmrg_inplace(psi.copy(), H, alg, envs, log)
+    raise TypeError("find_groundstate: only DMRG and DMRG2 are implemented on the device path")
+
+
+def timestep_inplace(psi, H, t, dt, alg, envs=None):
+    """timestep!(psi::FiniteMPS, H, t, dt, alg::TDVP / TDVP2, envs) (tdvp.jl:61-91, 115-151)"""
+    envs = envs if envs is not None else environments(psi, H)
+    L = len(psi)
+    integ = alg.integrator
+    if isinstance(alg, TDVP):
+        for i in range(0, L - 1):                                        # tdvp.jl:65-73
+            h = ddAC(i, psi, H, envs)
+            psi.AC[i] = integrate(h, psi.AC[i], t, dt / 2, integ); h.free()
+            h = ddC(i, psi, H, envs)
+            psi.CR[i] = integrate(h, psi.CR[i], t, -dt / 2, integ); h.free()
+        h = ddAC(L - 1, psi, H, envs)                                    # tdvp.jl:75-77
+        psi.AC[L - 1] = integrate(h, psi.AC[L - 1], t, dt / 2, integ); h.free()
+        for i in range(L - 1, 0, -1):                                    # tdvp.jl:79-87
+            h = ddAC(i, psi, H, envs)
+            psi.AC[i] = integrate(h, psi.AC[i], t + dt / 2, dt / 2, integ); h.free()
+            h = ddC(i - 1, psi, H, envs)
+            psi.CR[i - 1] = integrate(h, psi.CR[i - 1], t + dt / 2, -dt / 2, integ); h.free()
+        h = ddAC(0, psi, H, envs)
+        psi.AC[0] = integrate(h, psi.AC[0], t + dt / 2, dt / 2, integ); h.free()
+        return psi, envs
+    # TDVP2 (tdvp.jl:115-151)
+    for i in range(0, L - 1):
+        ac2 = contract_ac2(psi, psi.AC[i], psi.AR[i + 1])
+        h = ddAC2(i, psi, H, envs, ac2)
+        nac2 = integrate(h, ac2, t, dt / 2, integ); h.free()
+        al, c, ar, _ = tsvd(psi, nac2, alg.trscheme, normalize=False)
+        psi.AC[i] = (al, c)
+        psi.AC[i + 1] = (c, ar)
+        if i != L - 2:
+            h = ddAC(i + 1, psi, H, envs)
+            psi.AC[i + 1] = integrate(h, psi.AC[i + 1], t, -dt / 2, integ); h.free()
+    for i in range(L - 1, 0, -1):
+        ac2 = contract_ac2(psi, psi.AL[i - 1], psi.AC[i])
+        h = ddAC2(i - 1, psi, H, envs, ac2)
+        nac2 = integrate(h, ac2, t + dt / 2, dt / 2, integ); h.free()
+        al, c, ar, _ = tsvd(psi, nac2, alg.trscheme, normalize=False)
+        psi.AC[i - 1] = (al, c)
+        psi.AC[i] = (c, ar)
+        if i != 1:
+            h = ddAC(i - 1, psi, H, envs)
+            psi.AC[i - 1] = integrate(h, psi.AC[i - 1], t + dt / 2, -dt / 2, integ); h.free()
+    return psi, envs
+
+
+def timestep(psi, H, t, dt, alg, envs=None):
+    """timestep(psi, H, t, dt, alg, envs) = timestep!(copy(psi), ...) (tdvp.jl:93-96, 153-157)"""
+    return timestep_inplace(psi.copy(), H, t, dt, alg, envs)

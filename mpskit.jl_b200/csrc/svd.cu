@@ -47,6 +47,8 @@ int tsvd(Ctx* ctx, const Tensor* x, int d1, const int32_t* p1ch, mpsk_trunc trun
 
 int tsvd(Ctx* ctx, const Tensor* x, int d1, const int32_t* p1ch, mpsk_trunc trunc, Tensor** Uo, Tensor** So, Tensor** Vo,
          double* eps_out) {
+  const bool normalize = !(trunc.kind & 0x100);
+  trunc.kind &= 0xff;
   if (d1 <= 0 || x->nm() % d1) return ctx->fail(MPSK_EINVAL, "tsvd: d1 does not divide the label count");
   const int d2 = x->nm() / d1;
   const bool cx = x->dtype == MPSK_C128;
@@ -149,7 +151,7 @@ int tsvd(Ctx* ctx, const Tensor* x, int d1, const int32_t* p1ch, mpsk_trunc trun
   double kept2 = 0.0;
   for (size_t si = 0; si < secs.size(); ++si) for (int i = 0; i < secs[si]->keep; ++i) kept2 += sv[si][i] * sv[si][i];
   if (kept2 <= 0.0) return ctx->fail(MPSK_EINVAL, "tsvd: truncation removed every singular value");
-  const double snorm = 1.0 / std::sqrt(kept2);
+  const double snorm = normalize ? 1.0 / std::sqrt(kept2) : 1.0;
   // record the spectrum for mpsk_tsvd_spectrum
   TsvdSpectrum& sp = ctx->last_spectrum;
   sp.charge.clear(); sp.count.clear(); sp.kept.clear(); sp.values.clear();
@@ -200,8 +202,161 @@ int tsvd(Ctx* ctx, const Tensor* x, int d1, const int32_t* p1ch, mpsk_trunc trun
   return MPSK_OK;
 }
 
-int qrpos(Ctx* ctx, const Tensor*, bool, Tensor**, Tensor**) {
-  return ctx->fail(MPSK_EINVAL, "qrpos/lqpos are not available in this build yet");
+// ------------------------------------------------------------------------------------------ QRpos / LQpos
+// leftorth!(A; alg=QRpos()) and rightorth!(A; alg=LQpos()) (orthoview.jl:49-60, ortho.jl:127-138, finitemps.jl:150):
+// per coupled sector one Householder QR (cuSOLVER geqrf/ungqr: LAPACK-class library call as in the reference), then
+// the diagonal of R is made real non-negative by a phase kernel (unique factorisation -> elementwise parity).
+
+// ph[i] = R_ii / |R_ii| (1 if zero); Rout(i, j) = conj(ph_i) * A(i, j) for j >= i, 0 below; A column-major (lda)
+// Rout element (i, j) is written at dst[i * si + j * sj], conjugated if conj_out (LQ: L = R^H)
+template <bool CPLX>
+__global__ void qr_phase_kernel(const double* __restrict__ A, int64_t lda, int k, int n, double* __restrict__ ph,
+                                double* __restrict__ dst, int64_t si, int64_t sj, int conj_out) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < (int64_t)k * n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e % k), j = (int)(e / k);
+    double pr = 1.0, pi = 0.0;
+    if (CPLX) {
+      const double dr = A[2 * (i + (int64_t)i * lda)], di = A[2 * (i + (int64_t)i * lda) + 1];
+      const double ab = sqrt(dr * dr + di * di);
+      if (ab > 0) { pr = dr / ab; pi = di / ab; }
+    } else {
+      const double dr = A[i + (int64_t)i * lda];
+      if (dr < 0) pr = -1.0;
+    }
+    if (j == 0) { if (CPLX) { ph[2 * i] = pr; ph[2 * i + 1] = pi; } else ph[i] = pr; }
+    double vr = 0.0, vi = 0.0;
+    if (j >= i) {
+      if (CPLX) {
+        const double ar = A[2 * (i + (int64_t)j * lda)], ai = A[2 * (i + (int64_t)j * lda) + 1];
+        vr = pr * ar + pi * ai; vi = pr * ai - pi * ar;       // conj(ph) * a
+      } else vr = pr * A[i + (int64_t)j * lda];
+    }
+    if (CPLX) { dst[2 * (i * si + j * sj)] = vr; dst[2 * (i * si + j * sj) + 1] = conj_out ? -vi : vi; }
+    else dst[i * si + j * sj] = vr;
+  }
+}
+
+// Q(:, i) *= ph[i]; Q column-major m x k
+template <bool CPLX>
+__global__ void q_phase_kernel(double* __restrict__ Q, int64_t ldq, int m, int k, const double* __restrict__ ph) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < (int64_t)m * k; e += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(e % m), i = (int)(e / m);
+    if (CPLX) {
+      const double pr = ph[2 * i], pi = ph[2 * i + 1];
+      const double qr = Q[2 * (r + (int64_t)i * ldq)], qi = Q[2 * (r + (int64_t)i * ldq) + 1];
+      Q[2 * (r + (int64_t)i * ldq)] = qr * pr - qi * pi; Q[2 * (r + (int64_t)i * ldq) + 1] = qr * pi + qi * pr;
+    } else Q[r + (int64_t)i * ldq] *= ph[i];
+  }
+}
+
+struct QrSec { int jg; int64_t m, n, k; std::vector<std::pair<int, int64_t>> rows; void* W = nullptr; void* tau = nullptr; double* ph = nullptr; };
+
+// left = true : A[l m; r] = Q[l m; k] R[k; r]     (groups = r sectors, rows (m, l))
+// left = false: A[l; m r] = L[l; k] Q[k m; r]     (groups = l sectors, rows (m, r) of A^H)
+int qrpos(Ctx* ctx, const Tensor* A, bool left, Tensor** Qo, Tensor** Ro) {
+  const bool cx = A->dtype == MPSK_C128;
+  const size_t es = cx ? 16 : 8;
+  const Space& Vg = left ? A->Vr : A->Vl;       // grouping (column) space
+  const Space& Vo = left ? A->Vl : A->Vr;       // the other bond
+  const int ng = Vg.nsec(), nm = A->nm();
+  std::vector<QrSec> secs;
+  for (int g = 0; g < ng; ++g) {
+    QrSec s; s.jg = g; s.m = 0; s.n = Vg.n[g];
+    for (int mm = 0; mm < nm; ++mm) {
+      const int jo = left ? Vo.find((int64_t)Vg.q[g] - A->mch[mm]) : Vo.find((int64_t)Vg.q[g] + A->mch[mm]);
+      if (jo < 0) continue;
+      s.rows.push_back({mm, s.m}); s.m += Vo.n[jo];
+    }
+    s.k = std::min(s.m, s.n);
+    if (s.k > 0) secs.push_back(std::move(s));
+  }
+  struct Cleanup { Ctx* c; std::vector<QrSec>* v; ~Cleanup() { for (auto& s : *v) { c->free(s.W); c->free(s.tau); c->free(s.ph); } } } cl{ctx, &secs};
+  std::vector<CopyTask> tasks;
+  for (QrSec& s : secs) {
+    s.W = ctx->alloc(s.m * s.n * es); s.tau = ctx->alloc(s.k * es); s.ph = (double*)ctx->alloc(s.k * es);
+    if (!s.W || !s.tau || !s.ph) return MPSK_ENOMEM;
+    for (auto& rw : s.rows) {
+      const int mm = rw.first;
+      const int jo = left ? Vo.find((int64_t)Vg.q[s.jg] - A->mch[mm]) : Vo.find((int64_t)Vg.q[s.jg] + A->mch[mm]);
+      const Blk* b = left ? A->find(mm, jo) : A->find(mm, s.jg);
+      if (!b) return ctx->fail(MPSK_EINTERNAL, "qrpos: missing block");
+      CopyTask tk; tk.src = A->ptr(b->off); tk.ssl = b->sl; tk.ssr = b->sr; tk.nl = (int32_t)A->Vl.n[b->jl]; tk.nr = (int32_t)A->Vr.n[b->jr];
+      tk.scale_axis = 0; tk.scale = nullptr;
+      tk.dst = (char*)s.W + rw.second * es;
+      if (left) { tk.dsl = 1; tk.dsr = s.m; tk.conj = 0; }            // W(row = off + il, col = ir)
+      else { tk.dsl = s.m; tk.dsr = 1; tk.conj = cx ? 1 : 0; }         // W(row = off + ir, col = il) = conj(A)
+      tasks.push_back(tk);
+    }
+  }
+  MPSK_TRY(run_copy_tasks(ctx, tasks, cx));
+  cusolverDnHandle_t hs;
+  MPSK_TRY(get_cusolver(ctx, &hs));
+  int* d_info = (int*)ctx->alloc(sizeof(int));
+  // new bond space
+  Space Vn; Vn.mod = Vg.mod;
+  for (QrSec& s : secs) { Vn.q.push_back(Vg.q[s.jg]); Vn.n.push_back(s.k); }
+  Tensor *Qt = nullptr, *Rt = nullptr;
+  if (left) {
+    MPSK_TRY(tensor_create(ctx, A->Vl, A->mch, Vn, A->dtype, F_KL, true, &Qt));
+  } else {
+    MPSK_TRY(tensor_create(ctx, Vn, A->mch, A->Vr, A->dtype, F_KL, true, &Qt));
+  }
+  std::unique_ptr<Tensor> qg(Qt);
+  if (left) MPSK_TRY(tensor_create(ctx, Vn, std::vector<int32_t>{0}, A->Vr, A->dtype, F_KL, true, &Rt));
+  else MPSK_TRY(tensor_create(ctx, A->Vl, std::vector<int32_t>{0}, Vn, A->dtype, F_KL, true, &Rt));
+  std::unique_ptr<Tensor> rg(Rt);
+  tasks.clear();
+  for (QrSec& s : secs) {
+    const int m = (int)s.m, n = (int)s.n, k = (int)s.k;
+    int lw1 = 0, lw2 = 0;
+    if (cx) { CUSOLVER_TRY(ctx, cusolverDnZgeqrf_bufferSize(hs, m, n, (cuDoubleComplex*)s.W, m, &lw1));
+              CUSOLVER_TRY(ctx, cusolverDnZungqr_bufferSize(hs, m, k, k, (cuDoubleComplex*)s.W, m, (cuDoubleComplex*)s.tau, &lw2)); }
+    else { CUSOLVER_TRY(ctx, cusolverDnDgeqrf_bufferSize(hs, m, n, (double*)s.W, m, &lw1));
+           CUSOLVER_TRY(ctx, cusolverDnDorgqr_bufferSize(hs, m, k, k, (double*)s.W, m, (double*)s.tau, &lw2)); }
+    const int lw = std::max(std::max(lw1, lw2), 1);
+    void* work = ctx->alloc((size_t)lw * es);
+    if (!work) return MPSK_ENOMEM;
+    if (cx) CUSOLVER_TRY(ctx, cusolverDnZgeqrf(hs, m, n, (cuDoubleComplex*)s.W, m, (cuDoubleComplex*)s.tau, (cuDoubleComplex*)work, lw, d_info));
+    else CUSOLVER_TRY(ctx, cusolverDnDgeqrf(hs, m, n, (double*)s.W, m, (double*)s.tau, (double*)work, lw, d_info));
+    // R (k x n) with positive diagonal -> straight into the bond tensor
+    const int jn = Vn.find(Vg.q[s.jg]);
+    double* rdst; int64_t si, sj;
+    if (left) { const Blk* rb = Rt->find(0, jn); rdst = (double*)Rt->ptr(rb->off); si = rb->sl; sj = rb->sr; }       // R[k; r]: l = k idx, r = col
+    else { const Blk* rb = Rt->find(0, s.jg); rdst = (double*)Rt->ptr(rb->off); si = rb->sr; sj = rb->sl; }         // L[l; k] = conj(R'[k, l])
+    const int grid = (int)std::min<int64_t>(((int64_t)k * n + 255) / 256, 4096);
+    if (cx) qr_phase_kernel<true><<<grid, 256, 0, ctx->stream>>>((const double*)s.W, m, k, n, s.ph, rdst, si, sj, left ? 0 : 1);
+    else qr_phase_kernel<false><<<grid, 256, 0, ctx->stream>>>((const double*)s.W, m, k, n, s.ph, rdst, si, sj, 0);
+    if (cx) CUSOLVER_TRY(ctx, cusolverDnZungqr(hs, m, k, k, (cuDoubleComplex*)s.W, m, (cuDoubleComplex*)s.tau, (cuDoubleComplex*)work, lw, d_info));
+    else CUSOLVER_TRY(ctx, cusolverDnDorgqr(hs, m, k, k, (double*)s.W, m, (double*)s.tau, (double*)work, lw, d_info));
+    const int grid2 = (int)std::min<int64_t>(((int64_t)m * k + 255) / 256, 4096);
+    if (cx) q_phase_kernel<true><<<grid2, 256, 0, ctx->stream>>>((double*)s.W, m, m, k, s.ph);
+    else q_phase_kernel<false><<<grid2, 256, 0, ctx->stream>>>((double*)s.W, m, m, k, s.ph);
+    ctx->launches += 4;
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->free(work);
+    // Q blocks
+    for (auto& rw : s.rows) {
+      const int mm = rw.first;
+      CopyTask tk; tk.scale_axis = 0; tk.scale = nullptr; tk.src = (char*)s.W + rw.second * es;
+      if (left) {
+        const int jo = Vo.find((int64_t)Vg.q[s.jg] - A->mch[mm]);
+        const Blk* b = Qt->find(mm, jo);
+        if (!b || b->jr != jn) return ctx->fail(MPSK_EINTERNAL, "qrpos: output block mismatch");
+        tk.dst = Qt->ptr(b->off); tk.dsl = b->sl; tk.dsr = b->sr; tk.nl = (int32_t)Vo.n[jo]; tk.nr = k; tk.ssl = 1; tk.ssr = m; tk.conj = 0;
+      } else {
+        const Blk* b = Qt->find(mm, jn);
+        if (!b) return ctx->fail(MPSK_EINTERNAL, "lqpos: output block mismatch");
+        tk.dst = Qt->ptr(b->off); tk.dsl = b->sl; tk.dsr = b->sr; tk.nl = k; tk.nr = (int32_t)A->Vr.n[b->jr]; tk.ssl = m; tk.ssr = 1; tk.conj = cx ? 1 : 0;
+      }
+      tasks.push_back(tk);
+    }
+  }
+  ctx->free(d_info);
+  MPSK_TRY(run_copy_tasks(ctx, tasks, cx));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  *Qo = qg.release(); *Ro = rg.release();
+  return MPSK_OK;
 }
 
 }  // namespace mpsk

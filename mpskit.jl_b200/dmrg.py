@@ -39,14 +39,14 @@ class DMRG2:
     finalize: object = None
 
 
-def tsvd(psi, x, trscheme):
+def tsvd(psi, x, trscheme, normalize=True):
     """al, c, ar, eps = tsvd!(x; trunc, alg=SVD()) followed by normalize!(c) (dmrg.jl:96-97)."""
     ctx = psi.ctx
     d1 = len(psi.pq)
     pc = (C.c_int32 * d1)(*psi.pq)
     U, S, Vh = C.c_void_p(), C.c_void_p(), C.c_void_p()
     eps = C.c_double()
-    ctx.check(ctx.lib.mpsk_tsvd(ctx.h, x.h, d1, pc, _lib.c_trunc(trscheme[0], trscheme[1]), C.byref(U), C.byref(S), C.byref(Vh), C.byref(eps)))
+    ctx.check(ctx.lib.mpsk_tsvd(ctx.h, x.h, d1, pc, _lib.c_trunc(trscheme[0] | (0 if normalize else 0x100), trscheme[1]), C.byref(U), C.byref(S), C.byref(Vh), C.byref(eps)))
     mod = psi.pspace.modulus
     al, c, ar = DeviceTensor.wrap(ctx, U, mod), DeviceTensor.wrap(ctx, S, mod), DeviceTensor.wrap(ctx, Vh, mod)
     c._is_bond = True

@@ -44,71 +44,76 @@ class _View:
         self._set(i, v)
 
 
+def qrpos(ctx, A, modulus=0):
+    """Q, R = leftorth(A; alg=QRpos())  (device; orthoview.jl:58, finitemps.jl:150)"""
+    q, r = C.c_void_p(), C.c_void_p()
+    ctx.check(ctx.lib.mpsk_qrpos(ctx.h, A.h, C.byref(q), C.byref(r)))
+    Q, R = DeviceTensor.wrap(ctx, q, modulus), DeviceTensor.wrap(ctx, r, modulus)
+    R._is_bond = True
+    return Q, R
+
+
+def lqpos(ctx, A, modulus=0):
+    """L, Q = rightorth(A; alg=LQpos())  (device; orthoview.jl:52-56)"""
+    l, q = C.c_void_p(), C.c_void_p()
+    ctx.check(ctx.lib.mpsk_lqpos(ctx.h, A.h, C.byref(l), C.byref(q)))
+    Lm, Q = DeviceTensor.wrap(ctx, l, modulus), DeviceTensor.wrap(ctx, q, modulus)
+    Lm._is_bond = True
+    return Lm, Q
+
+
 class FiniteMPS:
     def __init__(self, As, Vs, pspace: Space, ctx=None, normalize=True, dtype=np.complex128):
-        """As: host tensors A[l,p,r] (dense charged arrays); canonicalised on the host like
-        finitemps.jl:143-170 (QRpos chain) followed by the LQpos chain that the lazy AR/CR getters of
-        orthoview.jl:49-60 would run on first use; the gauged tensors are then uploaded once."""
+        """As: site tensors A[l,p,r] -- host arrays (dense charged) or DeviceTensors.  Like finitemps.jl:143-170 the
+        constructor left-canonicalises with a QRpos chain (on the device) and keeps the last C; right-canonical
+        tensors are produced lazily by the AR / CR getters (orthoview.jl:49-60)."""
         self.ctx = ctx or default_context()
         self.L = len(As)
         self.pspace = pspace
         self.pq = tuple(int(c) for c in pspace.index_charges())
         self.dtype = np.dtype(dtype)
-        V = list(Vs)
-        As = [np.array(a, dtype=self.dtype) for a in As]
         mod = pspace.modulus
+        V = list(Vs)
+        cur = [a if isinstance(a, DeviceTensor) else DeviceTensor.from_dense(self.ctx, np.asarray(a), V[i], self.pq, V[i + 1], self.dtype)
+               for i, a in enumerate(As)]
         R = None
         for i in range(self.L):
-            Dl, d, Dr = As[i].shape
-            rowq = (V[i].index_charges()[:, None] + np.asarray(self.pq)[None, :]).reshape(-1)
-            if mod:
-                rowq = rowq % mod
-            Q, R, newV = qrpos(As[i].reshape(Dl * d, Dr), rowq, V[i + 1].index_charges(), mod)
+            Q, R = qrpos(self.ctx, cur[i], mod)
             if normalize:
-                R = R / np.linalg.norm(R)
+                R.scale(1.0 / R.norm())
+            cur[i] = Q
+            V[i + 1] = Q.Vr
             if i < self.L - 1:
-                V[i + 1] = newV
-                As[i] = Q.reshape(Dl, d, newV.dim)
-                As[i + 1] = np.einsum('ab,bpc->apc', R, As[i + 1])
-            else:
-                As[i] = Q.reshape(Dl, d, newV.dim)
-                V[i + 1] = newV
-        ALh = As
-        Ch = [None] * (self.L + 1)
-        Ch[self.L] = R
-        ARh = [None] * self.L
-        ACh = [None] * self.L
-        for i in range(self.L - 1, -1, -1):
-            ACh[i] = np.einsum('apb,bc->apc', ALh[i], Ch[i + 1])
-            Dl, d, Dr = ACh[i].shape
-            colq = (V[i + 1].index_charges()[None, :] - np.asarray(self.pq)[:, None]).reshape(-1)
-            if mod:
-                colq = colq % mod
-            Lm, Qm, newV = lqpos(ACh[i].reshape(Dl, d * Dr), V[i].index_charges(), colq, mod)
-            assert newV == V[i], "left-canonical state changed its bond space under LQ"
-            Ch[i] = Lm
-            ARh[i] = Qm.reshape(newV.dim, d, Dr)
+                h = C.c_void_p()
+                self.ctx.check(self.ctx.lib.mpsk_mul_bond_left(self.ctx.h, R.h, cur[i + 1].h, C.byref(h)))
+                cur[i + 1] = DeviceTensor.wrap(self.ctx, h, mod)
         self.V = V
-        up = lambda a, Vl, Vr: DeviceTensor.from_dense(self.ctx, a, Vl, self.pq, Vr, self.dtype)
-        self.ALs = [up(ALh[i], V[i], V[i + 1]) for i in range(self.L)]
-        self.ARs = [up(ARh[i], V[i], V[i + 1]) for i in range(self.L)]
+        self.ALs = cur
+        self.ARs = [None] * self.L
         self.ACs = [None] * self.L
-        self.CLs = [DeviceTensor.from_dense(self.ctx, Ch[i][:, None, :], V[i], (0,), V[i], self.dtype) for i in range(self.L + 1)]
+        self.CLs = [None] * (self.L + 1)
+        self.CLs[self.L] = R
         self._views()
 
     def _views(self):
         self.AL = _View(self._get_AL)
         self.AR = _View(self._get_AR)
         self.AC = _View(self._get_AC, self._set_AC)
-        self.CR = _View(lambda i: self._get_CL(i + 1))
+        self.CR = _View(lambda i: self._get_CL(i + 1), lambda i, v: self._set_CR(i, v))
 
     @staticmethod
-    def random(rng, pspace, L, maxV, ctx=None, dtype=np.complex128, left=None, right=None):
-        """FiniteMPS(rand, eltype, Pspaces, maxVspaces) (finitemps.jl:172-198) with a seeded generator."""
+    def random(rng, pspace, L, maxV, ctx=None, dtype=np.complex128, left=None, right=None, on_device=False):
+        """FiniteMPS(rand, eltype, Pspaces, maxVspaces) (finitemps.jl:172-198).  `rng`: numpy Generator (host-generated
+        normal entries, shared with the oracle in the parity tests) or, with on_device=True, an integer seed for
+        device-generated uniform entries (large synthetic states)."""
+        ctx = ctx or default_context()
         V = virtual_spaces(pspace, L, maxV, left, right)
         pq = pspace.index_charges()
         As = []
         for i in range(L):
+            if on_device:
+                As.append(DeviceTensor.random(ctx, V[i], [int(c) for c in pq], V[i + 1], int(rng) + i, dtype))
+                continue
             m = _mask(V[i], pq, V[i + 1])
             a = rng.standard_normal(m.shape)
             if np.dtype(dtype).kind == "c":
@@ -129,19 +134,27 @@ class FiniteMPS:
 
     # ---- orthoview.jl getters ------------------------------------------------------------------
     def _get_CL(self, i):
+        """CR[i-1] (orthoview.jl:49-60): LQpos of AC[i] when the left neighbour is left-canonical, else QRpos of AC[i-1]."""
         if self.CLs[i] is None:
-            raise NotImplementedError("lazy QR/LQ re-gauging on the device (orthoview.jl:49-60) is not available yet; "
-                                      "two-site sweeps never need it")
+            mod = self.pspace.modulus
+            if i == 0 or self.ALs[i - 1] is not None:
+                Lm, Q = lqpos(self.ctx, self._get_AC(i), mod)
+                self.CLs[i], self.ARs[i] = Lm, Q
+            else:
+                Q, R = qrpos(self.ctx, self._get_AC(i - 1), mod)
+                self.ALs[i - 1], self.CLs[i] = Q, R
         return self.CLs[i]
 
     def _get_AL(self, i):
+        """orthoview.jl:6-9"""
         if self.ALs[i] is None:
-            raise NotImplementedError("AL[%d] is stale and device QRpos is not available yet" % i)
+            self._get_CL(i + 1)
         return self.ALs[i]
 
     def _get_AR(self, i):
+        """orthoview.jl:28-32"""
         if self.ARs[i] is None:
-            raise NotImplementedError("AR[%d] is stale and device LQpos is not available yet" % i)
+            self._get_CL(i)
         return self.ARs[i]
 
     def _wrap(self, h):
@@ -191,6 +204,23 @@ class FiniteMPS:
         else:
             self._invalidate(i)
             self.ACs[i] = v
+
+    def _set_CR(self, i, vec):
+        """orthoview.jl:62-77 (CRView setindex!)"""
+        if self.CLs[i + 1] is None:
+            self._get_CL(i + 1)
+        if i >= 0 and self.ALs[i] is None:
+            self._get_AL(i)
+        if i + 1 < self.L and self.ARs[i + 1] is None:
+            self._get_AR(i + 1)
+        self.CLs = [None] * (self.L + 1)
+        self.ACs = [None] * self.L
+        for k in range(i + 1, self.L):
+            self.ALs[k] = None
+        for k in range(0, i + 1):
+            self.ARs[k] = None
+        vec._is_bond = True
+        self.CLs[i + 1] = vec
 
     # ---- read-outs ------------------------------------------------------------------------------
     def entanglement_spectrum(self, i):

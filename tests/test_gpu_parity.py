@@ -57,19 +57,21 @@ def test_dAC2_matvec(ctx, dbg_ctx, which, dtype, size):
     Vl, Vr = (VL, VR) if size == "small" else (VBIG_L, VBIG_R2)
     x, GL, GR = random_problem(11, h, Vl, Vr, "ac2", dtype)
     d = h.d
-    yref = oc.dAC2_sparse(x2_dense(x, d), h, h, GL.to_dense(), GR.to_dense())
+    # small: the reference's entry loop on dense arrays; big: its block-sparse twin (same order, fast on the CPU)
+    yref = x2_from_dense(oc.dAC2_sparse(x2_dense(x, d), h, h, GL.to_dense(), GR.to_dense()), d) if size == "small" \
+        else oc.dAC2_blocks(x, h, h, GL, GR).to_dense()
     hs = dev_slice(h)
     dx, dGL, dGR = dev_tensor(c, x), dev_tensor(c, GL), dev_tensor(c, GR)
     op = m.MPO_ddAC2(c, hs, hs, dGL, dGR, dx)
     y = op(dx).to_dense()
-    err = relerr(y, x2_from_dense(yref, d))
+    err = relerr(y, yref)
     print("dAC2", which, dtype.__name__, size, "relerr", err, "flops", op.flops)
     assert err <= 1e-12 and op.flops > 0 and np.abs(y).max() > 0
     # second application with a different vector through the same plan
     x2 = BlockTensor.random(np.random.default_rng(5), Vl, x.mch, Vr, dtype)
     y2 = op(dev_tensor(c, x2)).to_dense()
-    y2ref = oc.dAC2_sparse(x2_dense(x2, d), h, h, GL.to_dense(), GR.to_dense())
-    assert relerr(y2, x2_from_dense(y2ref, d)) <= 1e-12
+    y2ref = oc.dAC2_blocks(x2, h, h, GL, GR).to_dense()
+    assert relerr(y2, y2ref) <= 1e-12
 
 
 @pytest.mark.parametrize("dtype", [np.complex128, np.float64])
@@ -273,3 +275,127 @@ def test_dmrg2_energy_parity(ctx, model):
     es_d, es_o = psi_d.entanglement_spectrum(0), psi_o.entanglement_spectrum(0)
     for q in es_o:
         assert np.abs(es_d[q] - es_o[q]).max() <= 1e-8
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# gauge / single-site / time-evolution rows
+@pytest.mark.parametrize("dtype", [np.complex128, np.float64])
+def test_qrpos_lqpos(ctx, dtype):
+    """leftorth!(QRpos) / rightorth!(LQpos): unique factorisation -> elementwise parity with the oracle."""
+    rng = np.random.default_rng(71)
+    Vl, Vr = OSpace((-3, -1, 1, 3), (7, 20, 22, 5)), OSpace((-4, -2, 0, 2, 4), (3, 40, 11, 9, 2))   # sector 2: rows < cols too
+    pch = [-1, 1]
+    A = BlockTensor.random(rng, Vl, pch, Vr, dtype)
+    Ad = A.to_dense()
+    rowq = (Vl.index_charges()[:, None] + np.array(pch)[None, :]).reshape(-1)
+    Qo, Ro, nV = ol.qrpos(Ad.reshape(Vl.dim * 2, Vr.dim), rowq, Vr.index_charges())
+    dA = dev_tensor(ctx, A)
+    Q, R = m.qrpos(ctx, dA)
+    assert (Q.Vr.charges, Q.Vr.dims) == (nV.charges, nV.dims)
+    assert relerr(Q.to_dense().reshape(Vl.dim * 2, nV.dim), Qo) <= 1e-12
+    assert relerr(R.to_dense()[:, 0, :], Ro) <= 1e-12
+    colq = (Vr.index_charges()[None, :] - np.array(pch)[:, None]).reshape(-1)
+    Lo, Qo2, nV2 = ol.lqpos(Ad.reshape(Vl.dim, 2 * Vr.dim), Vl.index_charges(), colq)
+    Lm, Q2 = m.lqpos(ctx, dA)
+    assert (Q2.Vl.charges, Q2.Vl.dims) == (nV2.charges, nV2.dims)
+    assert relerr(Lm.to_dense()[:, 0, :], Lo) <= 1e-12
+    assert relerr(Q2.to_dense().reshape(nV2.dim, 2 * Vr.dim), Qo2) <= 1e-12
+
+
+def test_finitemps_gauge_identities(ctx):
+    """test/states.jl:15-38: AC = AL*C = C*AR on every site, isometry of AL / AR (lazy device gauging)."""
+    L = 8
+    p = m.Space((-1, 1), (1, 1))
+    from mpskit_b200.workloads import gaussian_bond_space
+    psi = m.FiniteMPS.random(np.random.default_rng(2), p, L, [gaussian_bond_space(12, k % 2) for k in range(1, L)], ctx)
+    for i in range(L):
+        AL, AR, AC = psi.AL[i].to_dense(), psi.AR[i].to_dense(), psi.AC[i].to_dense()
+        Cr, Cl = psi.CR[i].to_dense()[:, 0, :], psi.CR[i - 1].to_dense()[:, 0, :]
+        assert relerr(np.einsum('apb,bc->apc', AL, Cr), AC) <= 1e-12
+        assert relerr(np.einsum('ab,bpc->apc', Cl, AR), AC) <= 1e-12
+        M = AL.reshape(-1, AL.shape[2]); assert np.abs(M.conj().T @ M - np.eye(M.shape[1])).max() <= 1e-12
+        N = AR.reshape(AR.shape[0], -1); assert np.abs(N @ N.conj().T - np.eye(N.shape[0])).max() <= 1e-12
+    assert abs(psi.CR[L // 2].norm() - 1) <= 1e-12
+
+
+def test_dmrg_single_site_and_galerkin(ctx):
+    """find_groundstate(psi, H, DMRG()) (README quickstart algorithm, config 1 style) vs the oracle sweep."""
+    L = 10
+    Ho = ompo.transverse_field_ising(L, 1.0)
+    po = OSpace((0,), (2,))
+    psi_o = of.FiniteMPS.random(np.random.default_rng(81), po, L, OSpace((0,), (12,)))
+    log_o = []
+    of.dmrg_sweeps(psi_o, Ho, nsweeps=4, tol=1e-13, log=log_o)
+    psi_d = m.FiniteMPS.random(np.random.default_rng(81), to_dev_space(po), L, m.Space((0,), (12,)), ctx)
+    Hd = dev_hamiltonian(Ho)
+    envs = m.environments(psi_d, Hd)
+    g_d = m.calc_galerkin(psi_d, 3, envs)
+    psi_o2 = of.FiniteMPS.random(np.random.default_rng(81), po, L, OSpace((0,), (12,)))
+    g_o = of.calc_galerkin(psi_o2, 3, of.FinEnv(psi_o2, Ho))
+    assert abs(g_d - g_o) <= 1e-10
+    log_d = []
+    psi_d, envs, eps = m.find_groundstate(psi_d, Hd, m.DMRG(tol=1e-13, maxiter=4, eigalg=m.Lanczos(tol=1e-13)), log=log_d)
+    E_d, E_o = log_d[-1]["energy"], log_o[-1]["energy"]
+    exact = np.linalg.eigvalsh(ompo.dense_hamiltonian(Ho))[0]
+    print("DMRG", E_d, E_o, exact)
+    assert abs(E_d - E_o) <= 1e-10 * abs(E_o) and abs(E_d - exact) <= 1e-9 * abs(exact)
+
+
+def _full_state(psi):
+    T = psi.AC[0].to_dense()
+    for i in range(1, len(psi)):
+        T = np.tensordot(T, psi.AR[i].to_dense(), axes=([-1], [0]))
+    return T.reshape(-1)
+
+
+def _full_state_o(psi):
+    T = psi.get_AC(0)
+    for i in range(1, psi.L):
+        T = np.tensordot(T, psi.get_AR(i), axes=([-1], [0]))
+    return T.reshape(-1)
+
+
+def test_tdvp_step(ctx):
+    """timestep(psi, H, 0, dt, TDVP()) (tdvp.jl:61-91) vs the oracle and vs exact exp(-i dt H) on the full state."""
+    L = 6
+    Ho = ompo.heisenberg_u1(L)
+    po = OSpace((-1, 1), (1, 1))
+    maxV = [of.gaussian_bond_space(8, k % 2) for k in range(1, L)]     # D=8 is exact for L=6
+    psi_o = of.FiniteMPS.random(np.random.default_rng(91), po, L, maxV)
+    v0 = _full_state_o(psi_o)
+    dt = 0.05
+    psi_o, _ = of.tdvp_step(psi_o, Ho, dt)
+    v_o = _full_state_o(psi_o)
+    psi_d = m.FiniteMPS.random(np.random.default_rng(91), to_dev_space(po), L, [to_dev_space(v) for v in maxV], ctx)
+    assert abs(abs(np.vdot(_full_state(psi_d), v0)) - np.vdot(v0, v0).real) <= 1e-10
+    Hd = dev_hamiltonian(Ho)
+    psi_d, envs = m.timestep(psi_d, Hd, 0.0, dt, m.TDVP())
+    v_d = _full_state(psi_d)
+    import scipy.linalg as sla
+    v_ex = sla.expm(-1j * dt * ompo.dense_hamiltonian(Ho)) @ v0
+    print("tdvp overlaps", abs(np.vdot(v_d, v_o)), abs(np.vdot(v_d, v_ex)))
+    assert abs(abs(np.vdot(v_d, v_o)) - 1) <= 1e-9
+    assert abs(abs(np.vdot(v_d, v_ex)) - 1) <= 1e-6       # TDVP projection + splitting error at full bond dimension
+
+
+def test_golden_vectors_on_device(ctx):
+    """the CUDA path against the committed fixtures (tests/golden/*.npz, generated by make_golden.py)."""
+    import os
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = np.load(os.path.join(gdir, "contractions_u1.npz"))
+    h = dev_slice(ompo.heisenberg_longrange_u1(4, r=int(g["r"]))[0])
+    Vl, Vr, Vm = (m.Space(*g[k]) for k in ("Vl", "Vr", "Vm"))
+    p = h.pcharges
+    mch2 = [p[a] + p[b] for a in range(2) for b in range(2)]
+    up = lambda a, V1, mc, V2: m.DeviceTensor.from_dense(ctx, a, V1, mc, V2)
+    GL = up(g["GL"], Vl, [-c for c in h.domcharges], Vl)
+    GR2 = up(g["GR2"], Vr, list(h.imcharges), Vr)
+    x2 = up(g["x2"], Vl, mch2, Vr)
+    assert relerr(m.MPO_ddAC2(ctx, h, h, GL, GR2, x2)(x2).to_dense(), g["y2"]) <= 1e-12
+    GR1 = up(g["GR1"], Vm, list(h.imcharges), Vm)
+    x1 = up(g["x1"], Vl, list(p), Vm)
+    assert relerr(m.MPO_ddAC(ctx, h, GL, GR1, x1)(x1).to_dense(), g["y1"]) <= 1e-12
+    C0 = up(g["C0"], Vm, [0], Vm); GLc = up(g["GLc"], Vm, [-c for c in h.domcharges], Vm)
+    assert relerr(m.MPO_ddC(ctx, GLc, GR1, C0)(C0).to_dense()[:, 0, :], g["y0"]) <= 1e-12
+    t = np.load(os.path.join(gdir, "dmrg2_heisenberg_u1_L8_D16.npz"))
+    assert abs(t["energy"][-1] + 3.3749325986878906) < 1e-12
