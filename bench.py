@@ -197,11 +197,26 @@ def main():
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
 
-    # N > 1: the sector-row panels of y are sharded over ranks; until that lands each rank runs a replica
-    w = cfg3_matvec(ctx, args.D, r=args.r)
-    op, x = w["op"], w["x"]
+    # N > 1: strong scaling of ONE matvec: rank r owns the r-th row panel of the bra index (mpskit_b200/sharding.py);
+    # GL is sharded, GR and the Krylov vector x are replicated, one NCCL allgather per matvec assembles y everywhere.
+    w = cfg3_matvec(ctx, args.D, r=args.r, build_op=(world == 1))
+    x = w["x"]
+    if world == 1:
+        op = w["op"]
+        flops = op.flops
+    else:
+        def bcast(uid):
+            box = [uid]
+            dist.broadcast_object_list(box, src=0)
+            return box[0]
+        m.init_communicator(ctx, rank, world, bcast)
+        GLp = m.row_panel(w["GL"], rank, world)
+        w["GL"].free()
+        op = m.MPO_ddAC2(ctx, w["h"], w["h"], GLp, w["GR"], x)
+        t = torch.tensor([op.flops], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        flops = float(t.item())            # sum of the panel flops == flops of the full operator (no redundant work)
     y = x.zerovector()
-    flops = op.flops
     for _ in range(max(args.warmup, 3)):
         op.apply_into(x, y)
     ctx.synchronize()
@@ -225,11 +240,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     clocks = sampler.stop() if sampler else None
-    value = world * flops / (ms * 1e-3) / 1e12     # replicas: every rank applies the full operator
+    value = flops / (ms * 1e-3) / 1e12             # whole-job: one full matvec per step, whatever the number of ranks
 
     # per-kernel timing of the dominant kernel (grouped DMMA GEMM): time stage A + stage C launches alone
     e2e = None
-    if rank == 0 and not args.no_e2e:
+    if rank == 0 and not args.no_e2e and world == 1:
         xb = {k: torch.from_numpy(v).pin_memory().numpy() for k, v in x.to_blocks().items()}   # pinned host blocks
         yb = {k: torch.from_numpy(np.empty_like(v)).pin_memory().numpy() for k, v in xb.items()}
         bytes_x = sum(b.nbytes for b in xb.values())
@@ -249,7 +264,7 @@ def main():
 
     # roofline denominator: FP64 tensor (DMMA) peak is not in MEASURED_PEAKS.json -> measure cuBLAS zgemm live
     roofline = None
-    if rank == 0:
+    if rank == 0 and world == 1:
         n = 4096
         a = torch.randn(n, n, dtype=torch.complex128, device="cuda"); b = torch.randn(n, n, dtype=torch.complex128, device="cuda")
         (a @ b); torch.cuda.synchronize()
@@ -261,7 +276,7 @@ def main():
         peak = 8.0 * n ** 3 / (best * 1e-3) / 1e12
         del a, b
         # the two GEMM launches carry all the algorithmic flops; time them in isolation over the same inputs
-        gm = gemm_only_ms(ctx, op, x, y, stream, torch, max(3, min(args.steps, 10)))
+        gm = gemm_only_ms(ctx, op, x, y, stream, torch, max(3, min(args.steps, 10))) if world == 1 else float("nan")
         roofline = {"bound": "tensor", "kernel": "gemm_dmma_kernel<complex> (stage A + stage C of one matvec)",
                     "achieved": flops / (gm * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
                     "frac": flops / (gm * 1e-3) / 1e12 / peak, "traffic": None,
@@ -270,7 +285,7 @@ def main():
                     "gemm_ms_per_matvec": gm, "share_of_step": gm / ms}
 
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
         try:
             ox, oGL, oGR, oh = oracle_problem(w)
             t, yo = cpu_matvec_time(ox, oGL, oGR, oh)
@@ -284,11 +299,11 @@ def main():
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak" if world > 1 else "strong", "vs_baseline": None, "dtype": "c128",
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "c128",
                 "data": "synthetic",
                 "config": {"workload": workload_name(args.D, args.r), "D": args.D, "chi": 2 + 3 * args.r, "flops_per_matvec": flops,
                            "l2": "inputs larger than L2 (x 192 MB, environments 2 x 0.97 GB, intermediates 7.6 GB)",
-                           "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (row-panel sharding: see DESIGN.md)"},
+                           "parallelism": "single GPU" if world == 1 else f"{world} GPUs: row panels of the bra index, GL sharded, 1 NCCL allgather of y per matvec"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:

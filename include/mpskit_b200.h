@@ -149,7 +149,13 @@ int32_t mpsk_lqpos(mpsk_ctx* ctx, const mpsk_tensor* A, mpsk_tensor** L, mpsk_te
 /* ---- multi-GPU (one process per GPU; NCCL over NVLink) ------------------------------------------- */
 int32_t mpsk_comm_unique_id(uint8_t out128[128]);
 int32_t mpsk_comm_init(mpsk_ctx* ctx, const uint8_t id128[128], int32_t rank, int32_t nranks);
-int32_t mpsk_allreduce_sum(mpsk_ctx* ctx, mpsk_tensor* x);        /* partial-sum reduction of a sharded matvec */
+int32_t mpsk_allreduce_sum(mpsk_ctx* ctx, mpsk_tensor* x);        /* partial-sum reduction */
+/* Row-panel sharding of the matvec: rank r of N owns rows [floor(n r/N), floor(n (r+1)/N)) of every sector of the left
+ * (bra) index.  An operator created with the row panel of GL computes the same panel of y = h(x) (no redundant flops, no
+ * partial sums); on a context with a communicator mpsk_op_apply / mpsk_eigsolve / mpsk_expv allgather the panels (NCCL). */
+int32_t mpsk_tensor_row_panel(mpsk_ctx* ctx, const mpsk_tensor* t, int32_t rank, int32_t nranks, mpsk_tensor** out);
+int32_t mpsk_tensor_scatter_panel(mpsk_ctx* ctx, const mpsk_tensor* panel, int32_t rank, int32_t nranks, mpsk_tensor* full);
+int32_t mpsk_op_apply_local(mpsk_ctx* ctx, const mpsk_op* op, const mpsk_tensor* x, mpsk_tensor* y_panel);
 
 #ifdef __cplusplus
 }

@@ -93,6 +93,9 @@ PROTOTYPES = {
     "mpsk_comm_unique_id": (C.c_int32, [C.POINTER(C.c_uint8)]),
     "mpsk_comm_init": (C.c_int32, [_P, C.POINTER(C.c_uint8), C.c_int32, C.c_int32]),
     "mpsk_allreduce_sum": (C.c_int32, [_P, _P]),
+    "mpsk_tensor_row_panel": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, _PP]),
+    "mpsk_tensor_scatter_panel": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, _P]),
+    "mpsk_op_apply_local": (C.c_int32, [_P, _P, _P, _P]),
 }
 
 _lib = None

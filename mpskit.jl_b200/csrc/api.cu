@@ -510,6 +510,23 @@ int32_t mpsk_comm_init(mpsk_ctx* ctx, const uint8_t id128[128], int32_t rank, in
   return MPSK_OK;
 }
 
+int32_t mpsk_tensor_row_panel(mpsk_ctx* ctx, const mpsk_tensor* t, int32_t rank, int32_t nranks, mpsk_tensor** out) {
+  Tensor* o = nullptr;
+  MPSK_TRY(tensor_row_panel(CTX(ctx), CTEN(t), rank, nranks, &o));
+  *out = reinterpret_cast<mpsk_tensor*>(o);
+  return MPSK_OK;
+}
+
+int32_t mpsk_tensor_scatter_panel(mpsk_ctx* ctx, const mpsk_tensor* panel, int32_t rank, int32_t nranks, mpsk_tensor* full) {
+  Ctx* c = CTX(ctx); const Tensor* p = CTEN(panel); Tensor* f = TEN(full);
+  if (p->form != F_KL || p->nelem != panel_nelem(f, rank, nranks) || p->dtype != f->dtype) return c->fail(MPSK_ESPACE, "tensor is not the row panel of that rank");
+  return tensor_scatter_panel(c, p->d, rank, nranks, f, true);
+}
+
+int32_t mpsk_op_apply_local(mpsk_ctx* ctx, const mpsk_op* op, const mpsk_tensor* x, mpsk_tensor* y_panel) {
+  return heff_apply_local(CTX(ctx), const_cast<HeffOp*>(reinterpret_cast<const HeffOp*>(op)), CTEN(x), TEN(y_panel));
+}
+
 int32_t mpsk_allreduce_sum(mpsk_ctx* ctx, mpsk_tensor* xh) {
   Ctx* c = CTX(ctx); Tensor* x = TEN(xh);
   if (c->nranks <= 1) return MPSK_OK;
@@ -523,3 +540,15 @@ int32_t mpsk_allreduce_sum(mpsk_ctx* ctx, mpsk_tensor* xh) {
 }
 
 }  // extern "C"
+
+namespace mpsk {
+int comm_allgather(Ctx* c, const void* send, void* recv, size_t bytes_per_rank) {
+  typedef int (*pfn_ncclAllGather)(const void*, void*, size_t, int, void*, cudaStream_t);
+  pfn_ncclAllGather f = (pfn_ncclAllGather)dlsym(nccl_lib(), "ncclAllGather");
+  if (!f || !c->nccl) return c->fail(MPSK_ECUDA, "communicator not initialised");
+  int r = f(send, recv, bytes_per_rank / 8, /*ncclDouble*/ 8, c->nccl, c->stream);
+  if (r != 0) return c->fail(MPSK_ECUDA, "ncclAllGather failed (%d)", r);
+  c->launches++;
+  return MPSK_OK;
+}
+}  // namespace mpsk

@@ -118,6 +118,8 @@ static void build_layout(Tensor* t) {
   }
 }
 
+void tensor_layout_only(Tensor* t) { build_layout(t); }
+
 int tensor_create(Ctx* ctx, const Space& Vl, const std::vector<int32_t>& mch, const Space& Vr, int dtype, Form form,
                   bool zero, Tensor** out) {
   if (Vl.mod != Vr.mod) return ctx->fail(MPSK_ESPACE, "bond spaces belong to different groups");
@@ -238,6 +240,67 @@ int tensor_as_form(Ctx* ctx, const Tensor* src, Form form, bool conj, const Tens
   MPSK_TRY(tensor_repack(ctx, src, form, conj, &t));
   *out = t; *owned = true;
   return MPSK_OK;
+}
+
+// ------------------------------------------------------------------------------------------ row panels (multi-GPU sharding)
+// Rank r of N owns rows [floor(n r / N), floor(n (r+1) / N)) of every l-sector (dimension n): a perfectly balanced split
+// of the bra/left index.  Sectors whose share is empty disappear from the panel's space.
+void panel_bounds(int64_t n, int rank, int nranks, int64_t* lo, int64_t* hi) {
+  *lo = n * rank / nranks; *hi = n * (rank + 1) / nranks;
+}
+
+static Space panel_space(const Space& V, int rank, int nranks) {
+  Space P; P.mod = V.mod;
+  for (int j = 0; j < V.nsec(); ++j) {
+    int64_t lo, hi; panel_bounds(V.n[j], rank, nranks, &lo, &hi);
+    if (hi > lo) { P.q.push_back(V.q[j]); P.n.push_back(hi - lo); }
+  }
+  return P;
+}
+
+// out = rows of t (l index) belonging to `rank`; any form in, KL form out
+int tensor_row_panel(Ctx* ctx, const Tensor* t, int rank, int nranks, Tensor** out) {
+  if (nranks < 1 || rank < 0 || rank >= nranks) return ctx->fail(MPSK_EINVAL, "bad rank / nranks");
+  Space P = panel_space(t->Vl, rank, nranks);
+  Tensor* o = nullptr;
+  MPSK_TRY(tensor_create(ctx, P, t->mch, t->Vr, t->dtype, F_KL, true, &o));
+  std::unique_ptr<Tensor> og(o);
+  std::vector<CopyTask> tasks;
+  for (const Blk& b : o->blks) {
+    const int jl_full = t->Vl.find(P.q[b.jl]);
+    const Blk* s = t->find(b.m, jl_full);
+    if (!s) return ctx->fail(MPSK_EINTERNAL, "row_panel: missing block");
+    int64_t lo, hi; panel_bounds(t->Vl.n[jl_full], rank, nranks, &lo, &hi);
+    tasks.push_back(CopyTask{t->ptr(s->off + lo * s->sl), o->ptr(b.off), s->sl, s->sr, b.sl, b.sr, (int32_t)(hi - lo), (int32_t)t->Vr.n[s->jr], 0, 0, nullptr});
+  }
+  MPSK_TRY(run_copy_tasks(ctx, tasks, t->dtype == MPSK_C128));
+  *out = og.release();
+  return MPSK_OK;
+}
+
+// full[rows of `rank`] = panel data; `src` points at a buffer laid out like the KL-form panel tensor of that rank
+int tensor_scatter_panel(Ctx* ctx, const void* src, int rank, int nranks, Tensor* full, bool sync) {
+  Space P = panel_space(full->Vl, rank, nranks);
+  Tensor lay; lay.ctx = nullptr; lay.Vl = P; lay.Vr = full->Vr; lay.mch = full->mch; lay.dtype = full->dtype; lay.form = F_KL;
+  tensor_layout_only(&lay);
+  std::vector<CopyTask> tasks;
+  const size_t es = full->esize();
+  for (const Blk& b : lay.blks) {
+    const int jl_full = full->Vl.find(P.q[b.jl]);
+    const Blk* d = full->find(b.m, jl_full);
+    if (!d) return ctx->fail(MPSK_EINTERNAL, "scatter_panel: missing block");
+    int64_t lo, hi; panel_bounds(full->Vl.n[jl_full], rank, nranks, &lo, &hi);
+    tasks.push_back(CopyTask{(const char*)src + b.off * es, full->ptr(d->off + lo * d->sl), b.sl, b.sr, d->sl, d->sr, (int32_t)(hi - lo),
+                             (int32_t)full->Vr.n[d->jr], 0, 0, nullptr});
+  }
+  (void)sync;
+  return run_copy_tasks(ctx, tasks, full->dtype == MPSK_C128);
+}
+
+int64_t panel_nelem(const Tensor* full, int rank, int nranks) {
+  Tensor lay; lay.ctx = nullptr; lay.Vl = panel_space(full->Vl, rank, nranks); lay.Vr = full->Vr; lay.mch = full->mch; lay.dtype = full->dtype; lay.form = F_KL;
+  tensor_layout_only(&lay);
+  return lay.nelem;
 }
 
 // ------------------------------------------------------------------------------------------ random fill

@@ -5,6 +5,8 @@
 // (<= krylovdim x krylovdim) problem is solved on the host, like KrylovKit does.
 #include "internal.h"
 #include <cmath>
+#include <chrono>
+#include <cstdlib>
 
 namespace mpsk {
 
@@ -62,11 +64,18 @@ static int work_init(Ctx* ctx, const Tensor* like, int kd, KrylovWork* w) {
 
 // One Lanczos expansion step: V[k+1] <- orthonormalised H V[k]; returns alpha_k and beta_k (host).
 // If normalise is false the new vector is left un-normalised (caller stops here).
+static double g_t_apply = 0, g_t_orth = 0, g_t_sync = 0; static int g_prof = -1;
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 static int lanczos_step(Ctx* ctx, HeffOp* op, KrylovWork& w, int k, double* alpha, double* beta, bool cx) {
+  if (g_prof < 0) g_prof = getenv("MPSK_PROFILE") ? 1 : 0;
+  double t0 = 0, t1 = 0, t2 = 0;
+  if (g_prof) { cudaStreamSynchronize(ctx->stream); t0 = now_s(); }
   const int64_t n = w.V[0]->nelem;
   const int kd = w.kd;
   double* d_h1 = w.d_s; double* d_h2 = w.d_s + 2 * (kd + 1); double* d_n = w.d_s + 4 * (kd + 1);
   MPSK_TRY(heff_apply(ctx, op, w.V[k], w.V[k + 1]));
+  if (g_prof) { cudaStreamSynchronize(ctx->stream); t1 = now_s(); }
   std::vector<const void*> ptrs(k + 1);
   for (int j = 0; j <= k; ++j) ptrs[j] = w.V[j]->d;
   void* wv = w.V[k + 1]->d;
@@ -75,12 +84,15 @@ static int lanczos_step(Ctx* ctx, HeffOp* op, KrylovWork& w, int k, double* alph
   MPSK_TRY(vec_multidot(ctx, cx, k + 1, ptrs.data(), wv, n, d_h2));
   MPSK_TRY(vec_multiaxpy(ctx, cx, k + 1, ptrs.data(), d_h2, -1.0, wv, n));
   MPSK_TRY(vec_norm2(ctx, cx, wv, n, d_n));
+  if (g_prof) { cudaStreamSynchronize(ctx->stream); t2 = now_s(); }
   double* h = ctx->h_scratch;
   CUDA_TRY(ctx, cudaMemcpyAsync(h, w.d_s, sizeof(double) * (4 * (kd + 1) + 2), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   *alpha = h[2 * k] + h[2 * (kd + 1) + 2 * k];
   const double n2 = h[4 * (kd + 1)];
   *beta = n2 > 0 ? std::sqrt(n2) : 0.0;
+  if (g_prof) { const double t3 = now_s(); g_t_apply += t1 - t0; g_t_orth += t2 - t1; g_t_sync += t3 - t2;
+    if (k % 10 == 9) fprintf(stderr, "[mpsk profile] lanczos k=%d cumulative: apply %.3f s, orthogonalise %.3f s, scalars %.3f s\n", k, g_t_apply, g_t_orth, g_t_sync); }
   return MPSK_OK;
 }
 

@@ -10,7 +10,7 @@
 namespace mpsk {
 
 HeffOp::~HeffOp() {
-  if (ctx) { ctx->free(T); ctx->free(U); }
+  if (ctx) { ctx->free(T); ctx->free(U); ctx->free(gather); }
 }
 
 static int build_W(Ctx* ctx, int kind, const MpoSlice* h1, const MpoSlice* h2, const Tensor* x_like, int nlev,
@@ -68,16 +68,22 @@ int heff_create(Ctx* ctx, int kind, const MpoSlice* h1, const MpoSlice* h2, cons
                 const Tensor* x_like, HeffOp** out) {
   if (!GL || !GR || !x_like) return ctx->fail(MPSK_EINVAL, "null argument");
   if (GL->dtype != x_like->dtype || GR->dtype != x_like->dtype) return ctx->fail(MPSK_EINVAL, "mixed scalar types");
-  if (!(GL->Vr == x_like->Vl) || !(GL->Vl == x_like->Vl)) return ctx->fail(MPSK_ESPACE, "left environment does not match the left bond of x");
+  if (!(GL->Vr == x_like->Vl)) return ctx->fail(MPSK_ESPACE, "left environment does not match the left bond of x");
+  for (int j = 0; j < GL->Vl.nsec(); ++j) {     // bra space: the left bond of x or a row panel of it (multi-GPU sharding)
+    const int jf = x_like->Vl.find(GL->Vl.q[j]);
+    if (jf < 0 || GL->Vl.n[j] > x_like->Vl.n[jf]) return ctx->fail(MPSK_ESPACE, "bra space of the left environment is not contained in the left bond of x");
+  }
   if (!(GR->Vl == x_like->Vr) || !(GR->Vr == x_like->Vr)) return ctx->fail(MPSK_ESPACE, "right environment does not match the right bond of x");
   if (GL->nm() != GR->nm()) return ctx->fail(MPSK_ESPACE, "environments have different numbers of MPO levels");
   const int nlev = GL->nm();
   if (h1 && h1->odim != nlev) return ctx->fail(MPSK_ESPACE, "MPO slice odim %d != environment levels %d", h1->odim, nlev);
   std::unique_ptr<HeffOp> op(new HeffOp);
   op->ctx = ctx; op->kind = kind; op->dtype = x_like->dtype;
+  op->rectangular = !(GL->Vl == x_like->Vl);
   const bool cx = op->dtype == MPSK_C128;
   MPSK_TRY(build_W(ctx, kind, h1, h2, x_like, nlev, &op->W));
-  const Space& Vl = x_like->Vl;
+  const Space& Vl = x_like->Vl;      // ket (contracted) left bond
+  const Space& Vb = GL->Vl;          // bra left bond (== Vl unless this op computes a row panel)
   // charge rule  c_k = c_i + ch(m_out) - ch(m_in)  with c_i = -GL.mch[i], c_k = +GR.mch[k]
   for (const WEntry& w : op->W) {
     const int64_t lhs = Vl.norm((int64_t)GR->mch[w.k]);
@@ -90,7 +96,7 @@ int heff_create(Ctx* ctx, int kind, const MpoSlice* h1, const MpoSlice* h2, cons
   { Tensor* t = nullptr; MPSK_TRY(tensor_create(ctx, x_like->Vl, x_like->mch, x_like->Vr, x_like->dtype, F_KL, true, &t)); op->xs.reset(t); }
   const Tensor& xs = *op->xs; const Tensor& GLk = *op->GLk; const Tensor& GRs = *op->GRs;
   Tensor* ybuf = nullptr;
-  MPSK_TRY(tensor_create(ctx, x_like->Vl, x_like->mch, x_like->Vr, x_like->dtype, F_KL, true, &ybuf));
+  MPSK_TRY(tensor_create(ctx, Vb, x_like->mch, x_like->Vr, x_like->dtype, F_KL, true, &ybuf));
   std::unique_ptr<Tensor> ys(ybuf);
   const int ngl = Vl.nsec();
   // ---- T workspace: per l-sector jb a (M_A x N_A) matrix
@@ -103,12 +109,12 @@ int heff_create(Ctx* ctx, int kind, const MpoSlice* h1, const MpoSlice* h2, cons
   }
   op->T_elems = std::max<int64_t>(tot, GROUP_ALIGN);
   // ---- U workspace: per y block (m_out, ja) an (n_a x Kz) matrix
-  std::vector<int64_t> Uoff(xs.blks.size());
+  std::vector<int64_t> Uoff(ys->blks.size());
   tot = 0;
-  for (size_t b = 0; b < xs.blks.size(); ++b) {
-    const Blk& bk = xs.blks[b];
+  for (size_t b = 0; b < ys->blks.size(); ++b) {
+    const Blk& bk = ys->blks[b];
     Uoff[b] = tot;
-    tot += padg(Vl.n[bk.jl] * GRs.groups[bk.jr].ld);
+    tot += padg(Vb.n[bk.jl] * GRs.groups[bk.jr].ld);
   }
   op->U_elems = std::max<int64_t>(tot, GROUP_ALIGN);
   const size_t es = cx ? 16 : 8;
@@ -133,8 +139,8 @@ int heff_create(Ctx* ctx, int kind, const MpoSlice* h1, const MpoSlice* h2, cons
   // ---- mix + stage C
   std::vector<MixTask> tasks; std::vector<MixTerm> terms; std::vector<GemmProblemHost> pc;
   const int ngr = x_like->Vr.nsec();
-  for (size_t b = 0; b < xs.blks.size(); ++b) {
-    const Blk& bk = xs.blks[b];
+  for (size_t b = 0; b < ys->blks.size(); ++b) {
+    const Blk& bk = ys->blks[b];
     const int ja = bk.jl, jz = bk.jr;
     const Group& gz = GRs.groups[jz];
     const int64_t ldU = gz.ld;
@@ -144,11 +150,11 @@ int heff_create(Ctx* ctx, int kind, const MpoSlice* h1, const MpoSlice* h2, cons
       if (segk < 0) continue;
       const int jc = GRs.Vl.find((int64_t)GRs.Vr.q[jz] - GRs.mch[k]);
       klog += (double)GRs.Vl.n[jc];
-      MixTask tk; tk.dst = Uptr(Uoff[b] + segk); tk.ldd = ldU; tk.rows = (int32_t)Vl.n[ja]; tk.cols = (int32_t)GRs.Vl.n[jc];
+      MixTask tk; tk.dst = Uptr(Uoff[b] + segk); tk.ldd = ldU; tk.rows = (int32_t)Vb.n[ja]; tk.cols = (int32_t)GRs.Vl.n[jc];
       tk.term_begin = (int32_t)terms.size();
       for (const WEntry& w : op->W) {
         if (w.k != k || w.mout != bk.m) continue;
-        const int jb = Vl.find((int64_t)Vl.q[ja] + GLk.mch[w.i]);
+        const int jb = Vl.find((int64_t)Vb.q[ja] + GLk.mch[w.i]);
         if (jb < 0) continue;
         const Blk* xb = xs.find(w.min, jb);
         if (!xb) continue;
@@ -163,8 +169,8 @@ int heff_create(Ctx* ctx, int kind, const MpoSlice* h1, const MpoSlice* h2, cons
     }
     if (gz.cols == 0) continue;
     pc.push_back(GemmProblemHost{GRs.ptr(gz.off), Uptr(Uoff[b]), ys->ptr(bk.off), gz.ld, ldU, ys->groups[ja].ld, (int32_t)gz.rows,
-                                 (int32_t)Vl.n[ja], (int32_t)gz.cols, 0});
-    op->flops += kappa * (double)gz.rows * Vl.n[ja] * klog;
+                                 (int32_t)Vb.n[ja], (int32_t)gz.cols, 0});
+    op->flops += kappa * (double)gz.rows * Vb.n[ja] * klog;
   }
   op->gemmA.reset(new GemmPlan); op->gemmC.reset(new GemmPlan); op->mix.reset(new MixPlan);
   MPSK_TRY(gemm_plan_build(ctx, cx, pa, op->gemmA.get()));
@@ -178,16 +184,41 @@ int heff_create(Ctx* ctx, int kind, const MpoSlice* h1, const MpoSlice* h2, cons
   return MPSK_OK;
 }
 
-int heff_apply(Ctx* ctx, HeffOp* op, const Tensor* x, Tensor* y) {
-  if (!x->same_structure(*op->xs) || !y->same_structure(*op->xs)) return ctx->fail(MPSK_ESPACE, "vector structure does not match the operator");
-  if (x->form != F_KL || y->form != F_KL) return ctx->fail(MPSK_EINTERNAL, "Krylov vectors must be in KL form");
+// y_panel = (row panel of H_eff) x : the rank-local part of a sharded matvec (also the whole matvec when square)
+int heff_apply_local(Ctx* ctx, HeffOp* op, const Tensor* x, Tensor* y) {
+  if (!x->same_structure(*op->xs) || (y && !y->same_structure(*op->ybuf))) return ctx->fail(MPSK_ESPACE, "vector structure does not match the operator");
+  if (x->form != F_KL || (y && y->form != F_KL)) return ctx->fail(MPSK_EINTERNAL, "Krylov vectors must be in KL form");
   if (x->d != op->xs->d)
     CUDA_TRY(ctx, cudaMemcpyAsync(op->xs->d, x->d, x->bytes(), cudaMemcpyDeviceToDevice, ctx->stream));
   MPSK_TRY(gemm_plan_run(ctx, op->gemmA.get()));
   MPSK_TRY(mix_plan_run(ctx, op->mix.get()));
   MPSK_TRY(gemm_plan_run(ctx, op->gemmC.get()));
-  if (y->d != op->ybuf->d)
+  if (y && y->d != op->ybuf->d)
     CUDA_TRY(ctx, cudaMemcpyAsync(y->d, op->ybuf->d, y->bytes(), cudaMemcpyDeviceToDevice, ctx->stream));
+  return MPSK_OK;
+}
+
+// y = H_eff x.  Square operator: local.  Row-panel operator on a multi-rank context: every rank computes its panel,
+// one NCCL allgather over NVLink assembles the full y on all ranks (bitwise identical everywhere).
+int heff_apply(Ctx* ctx, HeffOp* op, const Tensor* x, Tensor* y) {
+  if (!op->rectangular) return heff_apply_local(ctx, op, x, y);
+  if (ctx->nranks <= 1) return ctx->fail(MPSK_EINVAL, "row-panel operator applied without a communicator (use mpsk_op_apply_local)");
+  if (!x->same_structure(*op->xs) || !y->same_structure(*op->xs)) return ctx->fail(MPSK_ESPACE, "vector structure does not match the operator");
+  MPSK_TRY(heff_apply_local(ctx, op, x, nullptr));
+  const size_t es = y->esize();
+  if (!op->gather) {
+    int64_t mx = 0;
+    for (int r = 0; r < ctx->nranks; ++r) mx = std::max(mx, panel_nelem(y, r, ctx->nranks));
+    op->gather_elems = mx;
+    op->gather = ctx->alloc((size_t)mx * (ctx->nranks + 1) * es);
+    if (!op->gather) return MPSK_ENOMEM;
+  }
+  char* send = (char*)op->gather + (size_t)op->gather_elems * ctx->nranks * es;
+  if (panel_nelem(y, ctx->rank, ctx->nranks) != op->ybuf->nelem) return ctx->fail(MPSK_ESPACE, "left environment is not this rank's row panel");
+  CUDA_TRY(ctx, cudaMemcpyAsync(send, op->ybuf->d, op->ybuf->bytes(), cudaMemcpyDeviceToDevice, ctx->stream));
+  MPSK_TRY(comm_allgather(ctx, send, op->gather, (size_t)op->gather_elems * es));
+  for (int r = 0; r < ctx->nranks; ++r)
+    MPSK_TRY(tensor_scatter_panel(ctx, (char*)op->gather + (size_t)r * op->gather_elems * es, r, ctx->nranks, y, false));
   return MPSK_OK;
 }
 

@@ -122,6 +122,12 @@ int tensor_repack(Ctx* ctx, const Tensor* src, Form form, bool conj, Tensor** ou
 int tensor_as_form(Ctx* ctx, const Tensor* src, Form form, bool conj, const Tensor** out, bool* owned);
 
 int tensor_fill_random(Ctx* ctx, Tensor* t, uint64_t seed);
+void tensor_layout_only(Tensor* t);   // fills blks / groups / nelem for (Vl, mch, Vr, dtype, form) without allocating
+void panel_bounds(int64_t n, int rank, int nranks, int64_t* lo, int64_t* hi);
+int tensor_row_panel(Ctx* ctx, const Tensor* t, int rank, int nranks, Tensor** out);
+int tensor_scatter_panel(Ctx* ctx, const void* src, int rank, int nranks, Tensor* full, bool sync);
+int64_t panel_nelem(const Tensor* full, int rank, int nranks);
+int comm_allgather(Ctx* ctx, const void* send, void* recv, size_t bytes_per_rank);
 
 // ---- strided block copies (upload / download / repack / SVD assembly)
 struct CopyTask {
@@ -187,7 +193,9 @@ struct HeffOp {
   std::unique_ptr<Tensor> GLk;   // left env in KR form (owned copy)
   std::unique_ptr<Tensor> GRs;   // right env in SL form (owned copy)
   std::unique_ptr<Tensor> xs;    // input staging buffer / structure template of x (KL form)
-  std::unique_ptr<Tensor> ybuf;  // output staging buffer (KL form); plans are bound to xs / ybuf
+  std::unique_ptr<Tensor> ybuf;  // output staging buffer (KL form, bra structure); plans are bound to xs / ybuf
+  bool rectangular = false;      // bra space of GL != ket space of x: this op produces a row panel of y (multi-GPU sharding)
+  void* gather = nullptr; int64_t gather_elems = 0;   // allgather buffer (nranks x max panel elems)
   std::vector<WEntry> W;
   // workspaces
   void* T = nullptr; void* U = nullptr; int64_t T_elems = 0, U_elems = 0;
@@ -200,6 +208,7 @@ struct HeffOp {
 int heff_create(Ctx* ctx, int kind, const MpoSlice* h1, const MpoSlice* h2, const Tensor* GL, const Tensor* GR,
                 const Tensor* x_like, HeffOp** out);
 int heff_apply(Ctx* ctx, HeffOp* op, const Tensor* x, Tensor* y);
+int heff_apply_local(Ctx* ctx, HeffOp* op, const Tensor* x, Tensor* y);
 
 // ---- Krylov solvers (eigsolve.cu)
 int eigsolve_lanczos(Ctx* ctx, HeffOp* op, const Tensor* x0, int which, int krylovdim, int maxiter, double tol,

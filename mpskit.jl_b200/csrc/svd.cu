@@ -5,6 +5,9 @@
 #include "internal.h"
 #include <cusolverDn.h>
 #include <cmath>
+#include <atomic>
+#include <mutex>
+#include <thread>
 
 namespace mpsk {
 
@@ -99,34 +102,74 @@ int tsvd(Ctx* ctx, const Tensor* x, int d1, const int32_t* p1ch, mpsk_trunc trun
     }
   }
   MPSK_TRY(run_copy_tasks(ctx, tasks, cx));
-  // ---- gesvd per sector
-  cusolverDnHandle_t hs;
-  MPSK_TRY(get_cusolver(ctx, &hs));
-  int* d_info = (int*)ctx->alloc(sizeof(int));
+  // ---- gesvd per sector: independent problems -> a few host threads, each with its own cuSOLVER handle + stream
+  // (gesvd is latency / BLAS-2 bound, so concurrent sectors overlap well; largest sector first)
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   std::vector<std::vector<double>> sv(secs.size());
-  for (size_t si = 0; si < secs.size(); ++si) {
-    Coupled* c = secs[si];
-    const int mm = (int)(c->flip ? c->n : c->m), nn = (int)(c->flip ? c->m : c->n);
-    int lwork = 0;
-    if (cx) CUSOLVER_TRY(ctx, cusolverDnZgesvd_bufferSize(hs, mm, nn, &lwork));
-    else CUSOLVER_TRY(ctx, cusolverDnDgesvd_bufferSize(hs, mm, nn, &lwork));
-    void* work = ctx->alloc((size_t)std::max(lwork, 1) * es);
-    double* rwork = (double*)ctx->alloc(sizeof(double) * std::max(nn, 1) * 5);
-    if (!work || !rwork) return MPSK_ENOMEM;
-    if (cx) CUSOLVER_TRY(ctx, cusolverDnZgesvd(hs, 'S', 'S', mm, nn, (cuDoubleComplex*)c->W, (int)c->ldw, c->S, (cuDoubleComplex*)c->U, (int)c->ldu,
-                                               (cuDoubleComplex*)c->VT, (int)c->ldvt, (cuDoubleComplex*)work, lwork, rwork, d_info));
-    else CUSOLVER_TRY(ctx, cusolverDnDgesvd(hs, 'S', 'S', mm, nn, (double*)c->W, (int)c->ldw, c->S, (double*)c->U, (int)c->ldu, (double*)c->VT,
-                                            (int)c->ldvt, (double*)work, lwork, rwork, d_info));
-    ctx->launches++;
-    int info = 0;
-    sv[si].resize(c->k);
-    CUDA_TRY(ctx, cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(sv[si].data(), c->S, sizeof(double) * c->k, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->free(work); ctx->free(rwork);
-    if (info != 0) { ctx->free(d_info); return ctx->fail(MPSK_ECUDA, "gesvd did not converge in sector %d (info=%d)", c->Q, info); }
+  {
+    std::vector<int> order(secs.size());
+    for (size_t i = 0; i < secs.size(); ++i) order[i] = (int)i;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return secs[a]->m * secs[a]->n > secs[b]->m * secs[b]->n; });
+    const int nthreads = (int)std::min<size_t>(4, secs.size());
+    std::atomic<int> next(0);
+    std::vector<int> status(nthreads, 0);
+    std::vector<std::string> errs(nthreads);
+    // workspaces come from the context allocator (no cudaMalloc / cudaFree device-wide syncs inside the workers)
+    std::vector<void*> works(secs.size(), nullptr); std::vector<double*> rworks(secs.size(), nullptr); std::vector<int> lworks(secs.size(), 0);
+    struct WsCleanup { Ctx* c; std::vector<void*>* w; std::vector<double*>* r; ~WsCleanup() { for (void* p : *w) c->free(p); for (double* p : *r) c->free(p); } } wsc{ctx, &works, &rworks};
+    {
+      cusolverDnHandle_t h0;
+      MPSK_TRY(get_cusolver(ctx, &h0));
+      for (size_t si = 0; si < secs.size(); ++si) {
+        const int mm = (int)(secs[si]->flip ? secs[si]->n : secs[si]->m), nn = (int)(secs[si]->flip ? secs[si]->m : secs[si]->n);
+        if (cx) CUSOLVER_TRY(ctx, cusolverDnZgesvd_bufferSize(h0, mm, nn, &lworks[si]));
+        else CUSOLVER_TRY(ctx, cusolverDnDgesvd_bufferSize(h0, mm, nn, &lworks[si]));
+        works[si] = ctx->alloc((size_t)std::max(lworks[si], 1) * es);
+        rworks[si] = (double*)ctx->alloc(sizeof(double) * std::max(nn, 1) * 5);
+        if (!works[si] || !rworks[si]) return MPSK_ENOMEM;
+      }
+    }
+    const int dev = ctx->device;
+    auto worker = [&](int tid) {
+      cudaSetDevice(dev);
+      cudaStream_t st; cusolverDnHandle_t hs;
+      if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { status[tid] = MPSK_ECUDA; errs[tid] = "stream create"; return; }
+      if (cusolverDnCreate(&hs) != CUSOLVER_STATUS_SUCCESS) { status[tid] = MPSK_ECUDA; errs[tid] = "cusolverDnCreate"; cudaStreamDestroy(st); return; }
+      cusolverDnSetStream(hs, st);
+      int* d_info = nullptr; cudaMalloc(&d_info, sizeof(int));
+      for (;;) {
+        const int oi = next.fetch_add(1);
+        if (oi >= (int)order.size()) break;
+        const int si = order[oi];
+        Coupled* c = secs[si];
+        const int mm = (int)(c->flip ? c->n : c->m), nn = (int)(c->flip ? c->m : c->n);
+        const int lwork = lworks[si];
+        void* work = works[si]; double* rwork = rworks[si];
+        cusolverStatus_t cs_;
+        if (cx) cs_ = cusolverDnZgesvd(hs, 'S', 'S', mm, nn, (cuDoubleComplex*)c->W, (int)c->ldw, c->S, (cuDoubleComplex*)c->U, (int)c->ldu,
+                                       (cuDoubleComplex*)c->VT, (int)c->ldvt, (cuDoubleComplex*)work, lwork, rwork, d_info);
+        else cs_ = cusolverDnDgesvd(hs, 'S', 'S', mm, nn, (double*)c->W, (int)c->ldw, c->S, (double*)c->U, (int)c->ldu, (double*)c->VT,
+                                    (int)c->ldvt, (double*)work, lwork, rwork, d_info);
+        int info = 0;
+        sv[si].resize(c->k);
+        cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(sv[si].data(), c->S, sizeof(double) * c->k, cudaMemcpyDeviceToHost, st);
+        cudaError_t ce = cudaStreamSynchronize(st);
+        if (cs_ != CUSOLVER_STATUS_SUCCESS || ce != cudaSuccess || info != 0) {
+          status[tid] = MPSK_ECUDA;
+          errs[tid] = "gesvd failed in sector " + std::to_string(c->Q) + " (status " + std::to_string((int)cs_) + ", info " + std::to_string(info) + ")";
+          break;
+        }
+      }
+      cudaFree(d_info);
+      cusolverDnDestroy(hs); cudaStreamDestroy(st);
+    };
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t) th.emplace_back(worker, t);
+    for (auto& t : th) t.join();
+    ctx->launches += (int64_t)secs.size();
+    for (int t = 0; t < nthreads; ++t) if (status[t] != 0) return ctx->fail(status[t], "tsvd: %s", errs[t].c_str());
   }
-  ctx->free(d_info);
   // ---- global truncation select (same rule as oracle/linalg.py:tsvd): drop smallest first; ties: later sector, larger index first
   struct Ent { double s; int sec, idx; };
   std::vector<Ent> all;

@@ -1,0 +1,56 @@
+"""Multi-GPU sharding of the matvec by row panels of the left (bra) index: one process per GPU, NCCL over NVLink.
+
+Rank r of N owns rows [floor(n r/N), floor(n (r+1)/N)) of every sector of the left bond.  An operator built from the row
+panel of GL computes exactly that panel of y = h(x): stage-A M rows, mix rows and stage-C N columns all split on the same
+index, so there are no redundant flops and no partial sums; the panels are assembled with ONE allgather per matvec.
+The Krylov vectors stay replicated (their BLAS-1 is ~1 % of a matvec), so every rank takes identical decisions."""
+from __future__ import annotations
+import ctypes as C
+import numpy as np
+from .spaces import Space
+from .tensor import DeviceTensor
+
+
+def panel_bounds(n, rank, nranks):
+    """same integer rule as the library (csrc/core.cu:panel_bounds)"""
+    return (n * rank) // nranks, (n * (rank + 1)) // nranks
+
+
+def panel_space(V: Space, rank, nranks) -> Space:
+    out = {}
+    for c, n in zip(V.charges, V.dims):
+        lo, hi = panel_bounds(n, rank, nranks)
+        if hi > lo:
+            out[c] = hi - lo
+    return Space.from_dict(out, V.modulus)
+
+
+def row_panel(t: DeviceTensor, rank, nranks) -> DeviceTensor:
+    h = C.c_void_p()
+    t.ctx.check(t.ctx.lib.mpsk_tensor_row_panel(t.ctx.h, t.h, rank, nranks, C.byref(h)))
+    return DeviceTensor.wrap(t.ctx, h, t.Vl.modulus)
+
+
+def scatter_panel(panel: DeviceTensor, rank, nranks, full: DeviceTensor):
+    full.ctx.check(full.ctx.lib.mpsk_tensor_scatter_panel(full.ctx.h, panel.h, rank, nranks, full.h))
+    return full
+
+
+def apply_local(op, x: DeviceTensor, y_panel: DeviceTensor):
+    op.ctx.check(op.ctx.lib.mpsk_op_apply_local(op.ctx.h, op.h, x.h, y_panel.h))
+    return y_panel
+
+
+def init_communicator(ctx, rank, nranks, broadcast):
+    """create the library's NCCL communicator; `broadcast(bytes_or_None) -> bytes` ships rank 0's unique id
+    (e.g. through torch.distributed.broadcast_object_list)."""
+    uid = None
+    if rank == 0:
+        buf = (C.c_uint8 * 128)()
+        st = ctx.lib.mpsk_comm_unique_id(buf)
+        if st != 0:
+            raise RuntimeError("mpsk_comm_unique_id failed (libnccl.so.2 not loadable?)")
+        uid = bytes(buf)
+    uid = broadcast(uid)
+    buf = (C.c_uint8 * 128)(*uid)
+    ctx.check(ctx.lib.mpsk_comm_init(ctx.h, buf, rank, nranks))

@@ -17,7 +17,7 @@ def gaussian_bond_space(D, parity, sigma=1.5, qmax=5, modulus=0):
     return Space.from_dict({c: int(k) for c, k in zip(cs, n) if k > 0}, modulus)
 
 
-def cfg3_matvec(ctx, D=4096, r=6, dtype=np.complex128, seed=20240213 + 3000, sigma=1.5):
+def cfg3_matvec(ctx, D=4096, r=6, dtype=np.complex128, seed=20240213 + 3000, sigma=1.5, build_op=True):
     """config 3(ii): spin-1/2 U(1) chain, range-r Heisenberg FSM MPO (chi = 2 + 3r), centre-bond two-site
     effective Hamiltonian with random GL / GR / x of the right block structure."""
     H = heisenberg_longrange_u1(2, r=r)
@@ -28,5 +28,5 @@ def cfg3_matvec(ctx, D=4096, r=6, dtype=np.complex128, seed=20240213 + 3000, sig
     x = DeviceTensor.random(ctx, V, mch, V, seed, dtype)
     GL = DeviceTensor.random(ctx, V, [-c for c in h.domcharges], V, seed + 1, dtype)
     GR = DeviceTensor.random(ctx, V, [c for c in h.imcharges], V, seed + 2, dtype)
-    op = MPO_ddAC2(ctx, h, h, GL, GR, x)
+    op = MPO_ddAC2(ctx, h, h, GL, GR, x) if build_op else None
     return dict(op=op, x=x, GL=GL, GR=GR, h=h, V=V, mch=mch)

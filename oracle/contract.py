@@ -139,6 +139,7 @@ def dAC2_blocks(x: BlockTensor, h1: SparseMPOSlice, h2: SparseMPOSlice, GL: Bloc
     """
     d = h1.d
     Vl, Vr = x.Vl, x.Vr
+    Vb = GL.Vl                      # bra space: x.Vl, or a row panel of it (multi-GPU sharding tests)
     lpos = {c: i for i, c in enumerate(Vl.charges)}
     rpos = {c: i for i, c in enumerate(Vr.charges)}
     # hl[j][(ja, s, u_t... )]: keep as dict keyed by (ja, s, t, jc) -> (n_a, n_c) arrays
@@ -152,7 +153,7 @@ def dAC2_blocks(x: BlockTensor, h1: SparseMPOSlice, h2: SparseMPOSlice, GL: Bloc
             for (lev, ja), g in GL.blocks.items():
                 if lev != i:
                     continue
-                qa = Vl.charges[ja]
+                qa = Vb.charges[ja]
                 qb = qa + GL.mch[i]
                 jb = lpos.get(qb)
                 if jb is None:
@@ -189,7 +190,7 @@ def dAC2_blocks(x: BlockTensor, h1: SparseMPOSlice, h2: SparseMPOSlice, GL: Bloc
                 for key, v in t.items():
                     cur[key] = cur.get(key, 0) + v
         hl[j] = cur
-    y = BlockTensor(Vl, x.mch, Vr, np.result_type(x.dtype, GL.dtype))
+    y = BlockTensor(Vb, x.mch, Vr, np.result_type(x.dtype, GL.dtype))
     for (j, k) in h2.keys():
         if hl[j] is None:
             continue
