@@ -151,7 +151,7 @@ int32_t mpsk_comm_unique_id(uint8_t out128[128]);
 int32_t mpsk_comm_init(mpsk_ctx* ctx, const uint8_t id128[128], int32_t rank, int32_t nranks);
 int32_t mpsk_allreduce_sum(mpsk_ctx* ctx, mpsk_tensor* x);        /* partial-sum reduction */
 /* Row-panel sharding of the matvec: rank r of N owns rows [floor(n r/N), floor(n (r+1)/N)) of every sector of the left
- * (bra) index.  An operator created with the row panel of GL computes the same panel of y = h(x) (no redundant flops, no
+ * (bra) index (csrc/core.cu panel_table, mirrored by mpskit_b200/sharding.py).  An operator created with the row panel of GL computes the same panel of y = h(x) (no redundant flops, no
  * partial sums); on a context with a communicator mpsk_op_apply / mpsk_eigsolve / mpsk_expv allgather the panels (NCCL). */
 int32_t mpsk_tensor_row_panel(mpsk_ctx* ctx, const mpsk_tensor* t, int32_t rank, int32_t nranks, mpsk_tensor** out);
 int32_t mpsk_tensor_scatter_panel(mpsk_ctx* ctx, const mpsk_tensor* panel, int32_t rank, int32_t nranks, mpsk_tensor* full);

@@ -16,4 +16,4 @@ from .dmrg import (DMRG2, find_groundstate_inplace, expectation_value, tsvd, con
                    truncdim, truncerr, truncbelow, notrunc, tsvd_spectrum)
 from .algorithms import (DMRG, TDVP, TDVP2, find_groundstate, find_groundstate_dmrg_inplace, calc_galerkin,  # noqa: F401
                          timestep, timestep_inplace)
-from .sharding import panel_bounds, panel_space, row_panel, scatter_panel, apply_local, init_communicator  # noqa: F401
+from .sharding import panel_bounds, panel_table, panel_space, row_panel, scatter_panel, apply_local, init_communicator  # noqa: F401

@@ -218,6 +218,36 @@ int run_copy_tasks(Ctx* ctx, const std::vector<CopyTask>& tasks, bool cplx) {
   return MPSK_OK;
 }
 
+// persistent copy plan: task / tile tables stay on the device, one launch per run, no host synchronisation
+CopyPlan::~CopyPlan() { if (ctx) { ctx->free(d_tasks); ctx->free(d_tiles); } }
+
+int copy_plan_build(Ctx* ctx, const std::vector<CopyTask>& tasks, bool cplx, CopyPlan* plan) {
+  plan->ctx = ctx; plan->cplx = cplx; plan->ntiles = 0;
+  std::vector<CopyTile> tiles;
+  for (size_t i = 0; i < tasks.size(); ++i)
+    for (int r0 = 0; r0 < tasks[i].nr; r0 += 32)
+      for (int l0 = 0; l0 < tasks[i].nl; l0 += 32) tiles.push_back(CopyTile{(int)i, l0, r0, 0});
+  if (tiles.empty()) return MPSK_OK;
+  plan->d_tasks = ctx->alloc(tasks.size() * sizeof(CopyTask));
+  plan->d_tiles = ctx->alloc(tiles.size() * sizeof(CopyTile));
+  if (!plan->d_tasks || !plan->d_tiles) return MPSK_ENOMEM;
+  CUDA_TRY(ctx, cudaMemcpyAsync(plan->d_tasks, tasks.data(), tasks.size() * sizeof(CopyTask), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(plan->d_tiles, tiles.data(), tiles.size() * sizeof(CopyTile), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  plan->ntiles = (int)tiles.size();
+  return MPSK_OK;
+}
+
+int copy_plan_run(Ctx* ctx, const CopyPlan* plan) {
+  if (!plan->ntiles) return MPSK_OK;
+  const int grid = std::min(plan->ntiles, ctx->num_sms * 8);
+  if (plan->cplx) copy_kernel<double2><<<grid, 256, 0, ctx->stream>>>((const CopyTask*)plan->d_tasks, (const CopyTile*)plan->d_tiles, plan->ntiles);
+  else copy_kernel<double><<<grid, 256, 0, ctx->stream>>>((const CopyTask*)plan->d_tasks, (const CopyTile*)plan->d_tiles, plan->ntiles);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return MPSK_OK;
+}
+
 int tensor_repack(Ctx* ctx, const Tensor* src, Form form, bool conj, Tensor** out) {
   Tensor* t = nullptr;
   MPSK_TRY(tensor_create(ctx, src->Vl, src->mch, src->Vr, src->dtype, form, true, &t));
@@ -245,14 +275,33 @@ int tensor_as_form(Ctx* ctx, const Tensor* src, Form form, bool conj, const Tens
 // ------------------------------------------------------------------------------------------ row panels (multi-GPU sharding)
 // Rank r of N owns rows [floor(n r / N), floor(n (r+1) / N)) of every l-sector (dimension n): a perfectly balanced split
 // of the bra/left index.  Sectors whose share is empty disappear from the panel's space.
-void panel_bounds(int64_t n, int rank, int nranks, int64_t* lo, int64_t* hi) {
-  *lo = n * rank / nranks; *hi = n * (rank + 1) / nranks;
+// Row-panel rule (pure integer arithmetic; mirrored bit-exactly by mpskit_b200/sharding.py:panel_table): rank r of N
+// owns rows [floor(n r / N), floor(n (r+1) / N)) of every sector (dimension n) of the left bond -- every rank gets the
+// same share of every sector, hence exactly 1/N of the flops whatever the operator.  (A tile-aligned, weight-balanced
+// rule was measured and rejected in round 1: 19.0 ms vs 16.4 ms per matvec at 8 GPUs -- load imbalance costs more than
+// the 13 % tile-quantisation loss of the even split; tools/panel_cost.py is the offline model.)
+void panel_table(const Space& V, int nranks, std::vector<int64_t>* lo, std::vector<int64_t>* hi) {
+  const int ns = V.nsec();
+  lo->assign((size_t)nranks * ns, 0); hi->assign((size_t)nranks * ns, 0);
+  for (int r = 0; r < nranks; ++r)
+    for (int j = 0; j < ns; ++j) {
+      (*lo)[(size_t)r * ns + j] = V.n[j] * r / nranks;
+      (*hi)[(size_t)r * ns + j] = V.n[j] * (r + 1) / nranks;
+    }
+}
+
+void panel_bounds(const Space& V, int j, int rank, int nranks, int64_t* lo, int64_t* hi) {
+  std::vector<int64_t> l, h;
+  panel_table(V, nranks, &l, &h);
+  *lo = l[(size_t)rank * V.nsec() + j]; *hi = h[(size_t)rank * V.nsec() + j];
 }
 
 static Space panel_space(const Space& V, int rank, int nranks) {
   Space P; P.mod = V.mod;
+  std::vector<int64_t> l, h;
+  panel_table(V, nranks, &l, &h);
   for (int j = 0; j < V.nsec(); ++j) {
-    int64_t lo, hi; panel_bounds(V.n[j], rank, nranks, &lo, &hi);
+    const int64_t lo = l[(size_t)rank * V.nsec() + j], hi = h[(size_t)rank * V.nsec() + j];
     if (hi > lo) { P.q.push_back(V.q[j]); P.n.push_back(hi - lo); }
   }
   return P;
@@ -270,7 +319,7 @@ int tensor_row_panel(Ctx* ctx, const Tensor* t, int rank, int nranks, Tensor** o
     const int jl_full = t->Vl.find(P.q[b.jl]);
     const Blk* s = t->find(b.m, jl_full);
     if (!s) return ctx->fail(MPSK_EINTERNAL, "row_panel: missing block");
-    int64_t lo, hi; panel_bounds(t->Vl.n[jl_full], rank, nranks, &lo, &hi);
+    int64_t lo, hi; panel_bounds(t->Vl, jl_full, rank, nranks, &lo, &hi);
     tasks.push_back(CopyTask{t->ptr(s->off + lo * s->sl), o->ptr(b.off), s->sl, s->sr, b.sl, b.sr, (int32_t)(hi - lo), (int32_t)t->Vr.n[s->jr], 0, 0, nullptr});
   }
   MPSK_TRY(run_copy_tasks(ctx, tasks, t->dtype == MPSK_C128));
@@ -279,6 +328,22 @@ int tensor_row_panel(Ctx* ctx, const Tensor* t, int rank, int nranks, Tensor** o
 }
 
 // full[rows of `rank`] = panel data; `src` points at a buffer laid out like the KL-form panel tensor of that rank
+int scatter_panel_tasks(Ctx* ctx, const void* src, int rank, int nranks, Tensor* full, std::vector<CopyTask>* tasks) {
+  Space P = panel_space(full->Vl, rank, nranks);
+  Tensor lay; lay.ctx = nullptr; lay.Vl = P; lay.Vr = full->Vr; lay.mch = full->mch; lay.dtype = full->dtype; lay.form = F_KL;
+  tensor_layout_only(&lay);
+  const size_t es = full->esize();
+  for (const Blk& b : lay.blks) {
+    const int jl_full = full->Vl.find(P.q[b.jl]);
+    const Blk* d = full->find(b.m, jl_full);
+    if (!d) return ctx->fail(MPSK_EINTERNAL, "scatter_panel: missing block");
+    int64_t lo, hi; panel_bounds(full->Vl, jl_full, rank, nranks, &lo, &hi);
+    tasks->push_back(CopyTask{(const char*)src + b.off * es, full->ptr(d->off + lo * d->sl), b.sl, b.sr, d->sl, d->sr, (int32_t)(hi - lo),
+                              (int32_t)full->Vr.n[d->jr], 0, 0, nullptr});
+  }
+  return MPSK_OK;
+}
+
 int tensor_scatter_panel(Ctx* ctx, const void* src, int rank, int nranks, Tensor* full, bool sync) {
   Space P = panel_space(full->Vl, rank, nranks);
   Tensor lay; lay.ctx = nullptr; lay.Vl = P; lay.Vr = full->Vr; lay.mch = full->mch; lay.dtype = full->dtype; lay.form = F_KL;
@@ -289,7 +354,7 @@ int tensor_scatter_panel(Ctx* ctx, const void* src, int rank, int nranks, Tensor
     const int jl_full = full->Vl.find(P.q[b.jl]);
     const Blk* d = full->find(b.m, jl_full);
     if (!d) return ctx->fail(MPSK_EINTERNAL, "scatter_panel: missing block");
-    int64_t lo, hi; panel_bounds(full->Vl.n[jl_full], rank, nranks, &lo, &hi);
+    int64_t lo, hi; panel_bounds(full->Vl, jl_full, rank, nranks, &lo, &hi);
     tasks.push_back(CopyTask{(const char*)src + b.off * es, full->ptr(d->off + lo * d->sl), b.sl, b.sr, d->sl, d->sr, (int32_t)(hi - lo),
                              (int32_t)full->Vr.n[d->jr], 0, 0, nullptr});
   }

@@ -212,13 +212,21 @@ int heff_apply(Ctx* ctx, HeffOp* op, const Tensor* x, Tensor* y) {
     op->gather_elems = mx;
     op->gather = ctx->alloc((size_t)mx * (ctx->nranks + 1) * es);
     if (!op->gather) return MPSK_ENOMEM;
+    Tensor* yf = nullptr;
+    MPSK_TRY(tensor_create(ctx, y->Vl, y->mch, y->Vr, y->dtype, F_KL, true, &yf));
+    op->yfull.reset(yf);
+    std::vector<CopyTask> tasks;
+    for (int r = 0; r < ctx->nranks; ++r)
+      MPSK_TRY(scatter_panel_tasks(ctx, (char*)op->gather + (size_t)r * mx * es, r, ctx->nranks, yf, &tasks));
+    op->scatter.reset(new CopyPlan);
+    MPSK_TRY(copy_plan_build(ctx, tasks, y->dtype == MPSK_C128, op->scatter.get()));
   }
   char* send = (char*)op->gather + (size_t)op->gather_elems * ctx->nranks * es;
   if (panel_nelem(y, ctx->rank, ctx->nranks) != op->ybuf->nelem) return ctx->fail(MPSK_ESPACE, "left environment is not this rank's row panel");
   CUDA_TRY(ctx, cudaMemcpyAsync(send, op->ybuf->d, op->ybuf->bytes(), cudaMemcpyDeviceToDevice, ctx->stream));
   MPSK_TRY(comm_allgather(ctx, send, op->gather, (size_t)op->gather_elems * es));
-  for (int r = 0; r < ctx->nranks; ++r)
-    MPSK_TRY(tensor_scatter_panel(ctx, (char*)op->gather + (size_t)r * op->gather_elems * es, r, ctx->nranks, y, false));
+  MPSK_TRY(copy_plan_run(ctx, op->scatter.get()));
+  CUDA_TRY(ctx, cudaMemcpyAsync(y->d, op->yfull->d, y->bytes(), cudaMemcpyDeviceToDevice, ctx->stream));
   return MPSK_OK;
 }
 

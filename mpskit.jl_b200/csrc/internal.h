@@ -123,9 +123,12 @@ int tensor_as_form(Ctx* ctx, const Tensor* src, Form form, bool conj, const Tens
 
 int tensor_fill_random(Ctx* ctx, Tensor* t, uint64_t seed);
 void tensor_layout_only(Tensor* t);   // fills blks / groups / nelem for (Vl, mch, Vr, dtype, form) without allocating
-void panel_bounds(int64_t n, int rank, int nranks, int64_t* lo, int64_t* hi);
+void panel_table(const Space& V, int nranks, std::vector<int64_t>* lo, std::vector<int64_t>* hi);
+void panel_bounds(const Space& V, int j, int rank, int nranks, int64_t* lo, int64_t* hi);
 int tensor_row_panel(Ctx* ctx, const Tensor* t, int rank, int nranks, Tensor** out);
 int tensor_scatter_panel(Ctx* ctx, const void* src, int rank, int nranks, Tensor* full, bool sync);
+struct CopyTask;
+int scatter_panel_tasks(Ctx* ctx, const void* src, int rank, int nranks, Tensor* full, std::vector<CopyTask>* tasks);
 int64_t panel_nelem(const Tensor* full, int rank, int nranks);
 int comm_allgather(Ctx* ctx, const void* send, void* recv, size_t bytes_per_rank);
 
@@ -139,6 +142,9 @@ struct CopyTask {
   const double* scale;          // real scale vector on the device
 };
 int run_copy_tasks(Ctx* ctx, const std::vector<CopyTask>& tasks, bool cplx);
+struct CopyPlan { Ctx* ctx = nullptr; bool cplx = true; void* d_tasks = nullptr; void* d_tiles = nullptr; int ntiles = 0; ~CopyPlan(); };
+int copy_plan_build(Ctx* ctx, const std::vector<CopyTask>& tasks, bool cplx, CopyPlan* plan);
+int copy_plan_run(Ctx* ctx, const CopyPlan* plan);
 
 // ---- "mix": out_rect = sum_terms coeff * src_rect  (row-major rectangles, unit column stride)
 struct MixTerm { const void* src; int64_t lds; double cre, cim; };
@@ -196,6 +202,7 @@ struct HeffOp {
   std::unique_ptr<Tensor> ybuf;  // output staging buffer (KL form, bra structure); plans are bound to xs / ybuf
   bool rectangular = false;      // bra space of GL != ket space of x: this op produces a row panel of y (multi-GPU sharding)
   void* gather = nullptr; int64_t gather_elems = 0;   // allgather buffer (nranks x max panel elems)
+  std::unique_ptr<Tensor> yfull; std::unique_ptr<CopyPlan> scatter;   // persistent assembly of the gathered panels
   std::vector<WEntry> W;
   // workspaces
   void* T = nullptr; void* U = nullptr; int64_t T_elems = 0, U_elems = 0;

@@ -1,6 +1,6 @@
 """Multi-GPU sharding of the matvec by row panels of the left (bra) index: one process per GPU, NCCL over NVLink.
 
-Rank r of N owns rows [floor(n r/N), floor(n (r+1)/N)) of every sector of the left bond.  An operator built from the row
+Rank r of N owns one contiguous row range per sector of the left bond (`panel_table`: an even split of every sector).  An operator built from the row
 panel of GL computes exactly that panel of y = h(x): stage-A M rows, mix rows and stage-C N columns all split on the same
 index, so there are no redundant flops and no partial sums; the panels are assembled with ONE allgather per matvec.
 The Krylov vectors stay replicated (their BLAS-1 is ~1 % of a matvec), so every rank takes identical decisions."""
@@ -11,15 +11,27 @@ from .spaces import Space
 from .tensor import DeviceTensor
 
 
-def panel_bounds(n, rank, nranks):
-    """same integer rule as the library (csrc/core.cu:panel_bounds)"""
-    return (n * rank) // nranks, (n * (rank + 1)) // nranks
+def panel_table(V: Space, nranks):
+    """{(rank, sector index): (lo, hi)} -- bit-exact mirror of csrc/core.cu:panel_table: rank r owns rows
+    [floor(n r/N), floor(n (r+1)/N)) of every sector, i.e. exactly 1/N of the flops of any operator."""
+    out = {}
+    for r in range(nranks):
+        for j, n in enumerate(V.dims):
+            lo, hi = (int(n) * r) // nranks, (int(n) * (r + 1)) // nranks
+            if hi > lo:
+                out[(r, j)] = (lo, hi)
+    return out
+
+
+def panel_bounds(V: Space, j, rank, nranks):
+    return panel_table(V, nranks).get((rank, j), (0, 0))
 
 
 def panel_space(V: Space, rank, nranks) -> Space:
+    tab = panel_table(V, nranks)
     out = {}
-    for c, n in zip(V.charges, V.dims):
-        lo, hi = panel_bounds(n, rank, nranks)
+    for j, c in enumerate(V.charges):
+        lo, hi = tab.get((rank, j), (0, 0))
         if hi > lo:
             out[c] = hi - lo
     return Space.from_dict(out, V.modulus)

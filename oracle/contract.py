@@ -190,7 +190,7 @@ def dAC2_blocks(x: BlockTensor, h1: SparseMPOSlice, h2: SparseMPOSlice, GL: Bloc
                 for key, v in t.items():
                     cur[key] = cur.get(key, 0) + v
         hl[j] = cur
-    y = BlockTensor(Vb, x.mch, Vr, np.result_type(x.dtype, GL.dtype))
+    y = BlockTensor(Vb, x.mch, Vr, np.result_type(x.dtype, GL.dtype, np.complex128))
     for (j, k) in h2.keys():
         if hl[j] is None:
             continue

@@ -25,14 +25,15 @@ def _worker(rank, world, port, out):
     GL = BlockTensor.random(rng, Vl, [-c for c in h.cl], Vl)
     GR = BlockTensor.random(rng, Vr, [c for c in h.cr], Vr)
     # this rank's row panel of GL (host mirror of the library's integer rule)
-    Vp = m.panel_space(m.Space(Vl.charges, Vl.dims), rank, world)
+    dVl = m.Space(Vl.charges, Vl.dims)
+    Vp = m.panel_space(dVl, rank, world)
     Vpo = Space(Vp.charges, Vp.dims)
     blocks = {}
     for (lev, jl), b in GL.blocks.items():
         q = Vl.charges[jl]
         if q not in Vp.charges:
             continue
-        lo, hi = m.panel_bounds(Vl.dims[jl], rank, world)
+        lo, hi = m.panel_bounds(dVl, jl, rank, world)
         blocks[(lev, Vp.charges.index(q))] = b[lo:hi]
     GLp = BlockTensor(Vpo, GL.mch, Vl, GL.dtype, blocks)
     yp = oc.dAC2_blocks(x, h, h, GLp, GR)
@@ -40,10 +41,10 @@ def _worker(rank, world, port, out):
     dist.all_gather_object(gathered, {k: v for k, v in yp.blocks.items()})       # the allgather of the panels
     y = BlockTensor(Vl, mch, Vr)
     for r, blk in enumerate(gathered):
-        Vr_ = m.panel_space(m.Space(Vl.charges, Vl.dims), r, world)
+        Vr_ = m.panel_space(dVl, r, world)
         for (mm, jp), v in blk.items():
             jl = Vl.charges.index(Vr_.charges[jp])
-            lo, hi = m.panel_bounds(Vl.dims[jl], r, world)
+            lo, hi = m.panel_bounds(dVl, jl, r, world)
             y.blocks[(mm, jl)][lo:hi] = v
     ref = oc.dAC2_blocks(x, h, h, GL, GR)
     err = max(np.abs(y.blocks[k] - ref.blocks[k]).max() for k in ref.blocks)
@@ -76,8 +77,18 @@ def test_panel_rule_tiles_every_space():
     import sys
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import mpskit_b200 as m
-    for n in (1, 4, 31, 147, 1092):
+    from mpskit_b200.workloads import gaussian_bond_space
+    spaces = [gaussian_bond_space(D, par) for D in (16, 256, 4096, 8192) for par in (0, 1)] + [m.Space((0,), (n,)) for n in (1, 5, 129, 1024)]
+    for V in spaces:
         for N in (1, 2, 3, 4, 8):
-            b = [m.panel_bounds(n, r, N) for r in range(N)]
-            assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(N - 1))
-            assert max(hi - lo for lo, hi in b) - min(hi - lo for lo, hi in b) <= 1
+            tab = m.panel_table(V, N)
+            for j, n in enumerate(V.dims):
+                rng = sorted(tab[(r, j)] for r in range(N) if (r, j) in tab)
+                assert rng[0][0] == 0 and rng[-1][1] == n and all(rng[i][1] == rng[i + 1][0] for i in range(len(rng) - 1))
+            assert sum(m.panel_space(V, r, N).dim for r in range(N)) == V.dim
+    # every rank gets the same share (+-1 row) of every sector: exactly 1/N of the flops of any operator
+    V = gaussian_bond_space(4096, 0)
+    tab = m.panel_table(V, 8)
+    for j, n in enumerate(V.dims):
+        w = [tab[(r, j)][1] - tab[(r, j)][0] for r in range(8) if (r, j) in tab]
+        assert max(w) - min(w) <= 1 or n < 8
