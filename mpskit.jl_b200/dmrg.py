@@ -116,6 +116,7 @@ def find_groundstate_inplace(psi, H, alg: DMRG2, envs=None, log=None):
                     psi.AC[pos] = (al, c)
                 for t in (ac2, new, alc, rec):
                     t.free()
+                envs.drop_stale(psi)
         eps = eps_s.max()
         if alg.finalize is not None:
             psi, envs = alg.finalize(it, psi, H, envs)

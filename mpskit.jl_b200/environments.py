@@ -21,6 +21,17 @@ class FinEnv:
         self.ldependencies[ind] = None
         self.rdependencies[ind] = None
 
+    def drop_stale(self, state):
+        """free environments whose dependency is gone (the reference keeps them allocated until they are overwritten,
+        FinEnv.jl:28-37; at D=4096 that is ~190 GB, so stale ones are released eagerly -- semantics are unchanged because a
+        stale entry is always recomputed before use)."""
+        L = len(state)
+        for j in range(L):
+            if self.rightenvs[j] is not None and self.rdependencies[j] is not state.ARs[j]:
+                self.rightenvs[j].free(); self.rightenvs[j] = None; self.rdependencies[j] = None
+            if self.leftenvs[j + 1] is not None and self.ldependencies[j] is not state.ALs[j]:
+                self.leftenvs[j + 1].free(); self.leftenvs[j + 1] = None; self.ldependencies[j] = None
+
     def rightenv(self, ind, state):
         """FinEnv.jl:114-129: environment contractable with the tensor on site ind."""
         a = None
