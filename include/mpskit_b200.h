@@ -77,6 +77,11 @@ int32_t mpsk_tensor_upload(mpsk_ctx* ctx, const mpsk_space* Vl, int32_t nm, cons
 int32_t mpsk_tensor_zeros(mpsk_ctx* ctx, const mpsk_space* Vl, int32_t nm, const int32_t* mcharge, const mpsk_space* Vr,
                           int32_t dtype, mpsk_tensor** out);
 int32_t mpsk_tensor_download(mpsk_ctx* ctx, const mpsk_tensor* t, const mpsk_blockref_mut* blocks, int32_t nblocks);
+/* label algebra: environments are vectors of MPO levels (mpohaminfenv.jl:76-215 works level by level, the matvec on the whole vector) */
+int32_t mpsk_tensor_stack_labels(mpsk_ctx* ctx, const mpsk_tensor* const* ts, int32_t n, mpsk_tensor** out);
+int32_t mpsk_tensor_select_labels(mpsk_ctx* ctx, const mpsk_tensor* t, const int32_t* labels, int32_t n, mpsk_tensor** out);
+/* out[r, m, l] = conj(t[l, m, r]), label charges negated (adjoint of a bond tensor: ortho.jl:127-131 Q_C') */
+int32_t mpsk_tensor_adjoint(mpsk_ctx* ctx, const mpsk_tensor* t, mpsk_tensor** out);
 /* synthetic data: uniform(-1,1) entries in every symmetry-allowed block, reproducible from `seed` (benchmarks, property tests) */
 int32_t mpsk_tensor_fill_random(mpsk_ctx* ctx, mpsk_tensor* t, uint64_t seed);
 int32_t mpsk_tensor_copy(mpsk_ctx* ctx, const mpsk_tensor* t, mpsk_tensor** out);

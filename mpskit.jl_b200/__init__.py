@@ -8,7 +8,9 @@ from .spaces import Space, fuse, infimum, dual  # noqa: F401
 from .tensor import DeviceTensor, block_table  # noqa: F401
 from .operators import (SparseMPOSlice, MPOHamiltonian, transverse_field_ising, heisenberg_u1,  # noqa: F401
                         heisenberg_longrange_u1, drop_symmetry)
-from .derivatives import MPO_ddC, MPO_ddAC, MPO_ddAC2, ddC, ddAC, ddAC2  # noqa: F401
+from .derivatives import (MPO_ddC, MPO_ddAC, MPO_ddAC2, ddC, ddAC, ddAC2, LazySumOp, MultipliedOp,  # noqa: F401
+                          LinearCombinationOp)
+from .krylov import RecursiveVec, eigsolve_arnoldi, linsolve_gmres  # noqa: F401
 from .fixedpoint import fixedpoint, integrate, Lanczos, Arnoldi  # noqa: F401
 from .finitemps import FiniteMPS, virtual_spaces, qrpos, lqpos  # noqa: F401
 from .environments import FinEnv, environments  # noqa: F401
@@ -17,3 +19,6 @@ from .dmrg import (DMRG2, find_groundstate_inplace, expectation_value, tsvd, con
 from .algorithms import (DMRG, TDVP, TDVP2, find_groundstate, find_groundstate_dmrg_inplace, calc_galerkin,  # noqa: F401
                          timestep, timestep_inplace)
 from .sharding import panel_bounds, panel_table, panel_space, row_panel, scatter_panel, apply_local, init_communicator  # noqa: F401
+from .infinite import (InfiniteMPS, TransferMatrix, regularize, MPOHamInfEnv, VUMPS, find_groundstate_vumps,  # noqa: F401
+                       uniform_leftorth, uniform_rightorth, regauge)
+from . import infinite  # noqa: F401

@@ -62,6 +62,9 @@ PROTOTYPES = {
     "mpsk_tensor_upload": (C.c_int32, [_P, _SP, C.c_int32, _I32P, _SP, C.c_int32, C.POINTER(c_blockref), C.c_int32, _PP]),
     "mpsk_tensor_zeros": (C.c_int32, [_P, _SP, C.c_int32, _I32P, _SP, C.c_int32, _PP]),
     "mpsk_tensor_download": (C.c_int32, [_P, _P, C.POINTER(c_blockref), C.c_int32]),
+    "mpsk_tensor_stack_labels": (C.c_int32, [_P, _PP, C.c_int32, _PP]),
+    "mpsk_tensor_select_labels": (C.c_int32, [_P, _P, _I32P, C.c_int32, _PP]),
+    "mpsk_tensor_adjoint": (C.c_int32, [_P, _P, _PP]),
     "mpsk_tensor_fill_random": (C.c_int32, [_P, _P, C.c_uint64]),
     "mpsk_tensor_copy": (C.c_int32, [_P, _P, _PP]),
     "mpsk_tensor_free": (None, [_P, _P]),

@@ -224,6 +224,27 @@ int32_t mpsk_tensor_download(mpsk_ctx* ctx, const mpsk_tensor* th, const mpsk_bl
   return MPSK_OK;
 }
 
+int32_t mpsk_tensor_stack_labels(mpsk_ctx* ctx, const mpsk_tensor* const* ts, int32_t n, mpsk_tensor** out) {
+  std::vector<const Tensor*> v;
+  for (int i = 0; i < n; ++i) v.push_back(CTEN(ts[i]));
+  Tensor* o = nullptr;
+  MPSK_TRY(tensor_stack_labels(CTX(ctx), v, &o));
+  *out = reinterpret_cast<mpsk_tensor*>(o);
+  return MPSK_OK;
+}
+int32_t mpsk_tensor_select_labels(mpsk_ctx* ctx, const mpsk_tensor* t, const int32_t* labels, int32_t n, mpsk_tensor** out) {
+  Tensor* o = nullptr;
+  MPSK_TRY(tensor_select_labels(CTX(ctx), CTEN(t), labels, n, &o));
+  *out = reinterpret_cast<mpsk_tensor*>(o);
+  return MPSK_OK;
+}
+int32_t mpsk_tensor_adjoint(mpsk_ctx* ctx, const mpsk_tensor* t, mpsk_tensor** out) {
+  Tensor* o = nullptr;
+  MPSK_TRY(tensor_adjoint(CTX(ctx), CTEN(t), &o));
+  *out = reinterpret_cast<mpsk_tensor*>(o);
+  return MPSK_OK;
+}
+
 int32_t mpsk_tensor_fill_random(mpsk_ctx* ctx, mpsk_tensor* t, uint64_t seed) { return tensor_fill_random(CTX(ctx), TEN(t), seed); }
 
 int32_t mpsk_tensor_copy(mpsk_ctx* ctx, const mpsk_tensor* th, mpsk_tensor** out) {

@@ -272,6 +272,71 @@ int tensor_as_form(Ctx* ctx, const Tensor* src, Form form, bool conj, const Tens
   return MPSK_OK;
 }
 
+// ------------------------------------------------------------------------------------------ label algebra / adjoint
+// out[l, (labels of all inputs), r]: environments are handled level by level in the infinite-MPS solvers
+// (mpohaminfenv.jl:76-215) and as one stacked tensor by the matvec
+int tensor_stack_labels(Ctx* ctx, const std::vector<const Tensor*>& ts, Tensor** out) {
+  if (ts.empty()) return ctx->fail(MPSK_EINVAL, "stack: no tensors");
+  std::vector<int32_t> mch;
+  for (const Tensor* t : ts) {
+    if (!(t->Vl == ts[0]->Vl) || !(t->Vr == ts[0]->Vr) || t->dtype != ts[0]->dtype) return ctx->fail(MPSK_ESPACE, "stack: tensors differ in their bond spaces");
+    mch.insert(mch.end(), t->mch.begin(), t->mch.end());
+  }
+  Tensor* o = nullptr;
+  MPSK_TRY(tensor_create(ctx, ts[0]->Vl, mch, ts[0]->Vr, ts[0]->dtype, F_KL, true, &o));
+  std::unique_ptr<Tensor> og(o);
+  std::vector<CopyTask> tasks;
+  int base = 0;
+  for (const Tensor* t : ts) {
+    for (const Blk& b : t->blks) {
+      const Blk* d = o->find(base + b.m, b.jl);
+      if (!d) return ctx->fail(MPSK_EINTERNAL, "stack: missing block");
+      tasks.push_back(CopyTask{t->ptr(b.off), o->ptr(d->off), b.sl, b.sr, d->sl, d->sr, (int32_t)t->Vl.n[b.jl], (int32_t)t->Vr.n[b.jr], 0, 0, nullptr});
+    }
+    base += t->nm();
+  }
+  MPSK_TRY(run_copy_tasks(ctx, tasks, o->dtype == MPSK_C128));
+  *out = og.release();
+  return MPSK_OK;
+}
+
+int tensor_select_labels(Ctx* ctx, const Tensor* t, const int32_t* labels, int n, Tensor** out) {
+  std::vector<int32_t> mch(n);
+  for (int i = 0; i < n; ++i) { if (labels[i] < 0 || labels[i] >= t->nm()) return ctx->fail(MPSK_EINVAL, "select: label out of range"); mch[i] = t->mch[labels[i]]; }
+  Tensor* o = nullptr;
+  MPSK_TRY(tensor_create(ctx, t->Vl, mch, t->Vr, t->dtype, F_KL, true, &o));
+  std::unique_ptr<Tensor> og(o);
+  std::vector<CopyTask> tasks;
+  for (const Blk& d : o->blks) {
+    const Blk* b = t->find(labels[d.m], d.jl);
+    if (!b) return ctx->fail(MPSK_EINTERNAL, "select: missing block");
+    tasks.push_back(CopyTask{t->ptr(b->off), o->ptr(d.off), b->sl, b->sr, d.sl, d.sr, (int32_t)t->Vl.n[b->jl], (int32_t)t->Vr.n[b->jr], 0, 0, nullptr});
+  }
+  MPSK_TRY(run_copy_tasks(ctx, tasks, o->dtype == MPSK_C128));
+  *out = og.release();
+  return MPSK_OK;
+}
+
+// out[r, m, l] = conj(t[l, m, r]) with label charges negated (adjoint of bond matrices and of single env levels)
+int tensor_adjoint(Ctx* ctx, const Tensor* t, Tensor** out) {
+  std::vector<int32_t> mch(t->nm());
+  for (int i = 0; i < t->nm(); ++i) mch[i] = -t->mch[i];
+  Tensor* o = nullptr;
+  MPSK_TRY(tensor_create(ctx, t->Vr, mch, t->Vl, t->dtype, F_KL, true, &o));
+  std::unique_ptr<Tensor> og(o);
+  std::vector<CopyTask> tasks;
+  for (const Blk& b : t->blks) {
+    const Blk* d = o->find(b.m, b.jr);
+    if (!d || d->jr != b.jl) return ctx->fail(MPSK_EINTERNAL, "adjoint: missing block");
+    // d is indexed (l' = r idx, r' = l idx): element (il, ir) of b goes to (l' = ir, r' = il)
+    tasks.push_back(CopyTask{t->ptr(b.off), o->ptr(d->off), b.sl, b.sr, d->sr, d->sl, (int32_t)t->Vl.n[b.jl], (int32_t)t->Vr.n[b.jr],
+                             t->dtype == MPSK_C128 ? 1 : 0, 0, nullptr});
+  }
+  MPSK_TRY(run_copy_tasks(ctx, tasks, o->dtype == MPSK_C128));
+  *out = og.release();
+  return MPSK_OK;
+}
+
 // ------------------------------------------------------------------------------------------ row panels (multi-GPU sharding)
 // Rank r of N owns rows [floor(n r / N), floor(n (r+1) / N)) of every l-sector (dimension n): a perfectly balanced split
 // of the bra/left index.  Sectors whose share is empty disappear from the panel's space.

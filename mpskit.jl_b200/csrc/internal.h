@@ -122,6 +122,9 @@ int tensor_repack(Ctx* ctx, const Tensor* src, Form form, bool conj, Tensor** ou
 int tensor_as_form(Ctx* ctx, const Tensor* src, Form form, bool conj, const Tensor** out, bool* owned);
 
 int tensor_fill_random(Ctx* ctx, Tensor* t, uint64_t seed);
+int tensor_stack_labels(Ctx* ctx, const std::vector<const Tensor*>& ts, Tensor** out);
+int tensor_select_labels(Ctx* ctx, const Tensor* t, const int32_t* labels, int n, Tensor** out);
+int tensor_adjoint(Ctx* ctx, const Tensor* t, Tensor** out);
 void tensor_layout_only(Tensor* t);   // fills blks / groups / nelem for (Vl, mch, Vr, dtype, form) without allocating
 void panel_table(const Space& V, int nranks, std::vector<int64_t>* lo, std::vector<int64_t>* hi);
 void panel_bounds(const Space& V, int j, int rank, int nranks, int64_t* lo, int64_t* hi);

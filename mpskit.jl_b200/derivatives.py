@@ -86,3 +86,37 @@ def ddAC(pos, psi, H, envs):
 def ddAC2(pos, psi, H, envs, x_like):
     """derivatives.jl:55-58: (opp[pos], opp[pos+1], leftenv(pos), rightenv(pos+1))"""
     return MPO_ddAC2(psi.ctx, envs.opp[pos], envs.opp[pos + 1], envs.leftenv(pos, psi), envs.rightenv(pos + 1, psi), x_like)
+
+
+# ---- operator algebra on derivatives (derivatives.jl:234-247, 283-323) ---------------------------------------------
+class MultipliedOp:
+    """MultipliedOperator of a derivative: f * h, with f a number or a function of time (derivatives.jl:311-323)."""
+
+    def __init__(self, op, f):
+        self.op, self.f, self.ctx = op, f, op.ctx
+
+    def __call__(self, x, t=None):
+        c = self.f(t) if callable(self.f) else self.f
+        return self.op(x).scale(c)
+
+
+class LazySumOp:
+    """LazySum of derivative operators: (sum_n h_n)(x) = sum_n h_n(x) (derivatives.jl:283-309)."""
+
+    def __init__(self, ops):
+        self.ops, self.ctx = list(ops), ops[0].ctx
+
+    def __call__(self, x, t=None):
+        y = self.ops[0](x, t) if t is not None else self.ops[0](x)
+        for o in self.ops[1:]:
+            z = o(x, t) if t is not None else o(x)
+            y.axpy(1.0, z)
+            z.free()
+        return y
+
+
+class LinearCombinationOp(LazySumOp):
+    """LinearCombination: sum_n c_n h_n (derivatives.jl:234-247)."""
+
+    def __init__(self, ops, coeffs):
+        super().__init__([MultipliedOp(o, c) for o, c in zip(ops, coeffs)])

@@ -30,11 +30,19 @@ class Arnoldi:
 
 def fixedpoint(A, x0, which, alg, return_info=False):
     """val, vec = fixedpoint(A, x0, which, alg)   (fixedpoint.jl:9-30)"""
+    herm = 1 if isinstance(alg, Lanczos) or getattr(alg, "hermitian", False) else 0
+    if not (herm and hasattr(A, "h") and hasattr(x0, "h")):
+        # not a single Hermitian device operator: host-driven Krylov over the VectorInterface (krylov.py), as KrylovKit does
+        from . import krylov
+        solver = krylov.eigsolve_lanczos if herm else krylov.eigsolve_arnoldi
+        val, vec, info = solver(A, x0, which, alg.tol, alg.krylovdim, alg.maxiter)
+        if info["converged"] == 0:
+            warnings.warn(f"fixedpoint not converged after {info['numiter']} iterations: normres = {info['normres']}")
+        return (complex(val), vec, info) if return_info else (complex(val), vec)
     ctx = A.ctx
     vec = x0.zerovector()
     re, im = C.c_double(), C.c_double()
     info = _lib.c_info()
-    herm = 1 if isinstance(alg, Lanczos) or getattr(alg, "hermitian", False) else 0
     ctx.check(ctx.lib.mpsk_eigsolve(ctx.h, A.h, x0.h, _WHICH[which], herm, alg.krylovdim, alg.maxiter, alg.tol,
                                     C.byref(re), C.byref(im), vec.h, C.byref(info)))
     if info.converged == 0:   # fixedpoint.jl:12-14

@@ -1,0 +1,468 @@
+"""Infinite-MPS side of the path on device handles: uniform gauge (src/states/ortho.jl:127-257,
+src/states/infinitemps.jl:139-204), TransferMatrix (src/transfermatrix/transfermatrix.jl:4-90), MPOHamInfEnv
+(src/environments/mpohaminfenv.jl:4-215), VUMPS (src/algorithms/groundstate/vumps.jl:18-92), the infinite
+expectation value (src/algorithms/expval.jl:111-124) and calc_galerkin (src/algorithms/toolbox.jl:17-25).
+Every tensor operation is a libmpskit_b200 call; Krylov solves on non-Hermitian maps and linear systems are
+host-driven over the VectorInterface (krylov.py) exactly like KrylovKit drives the reference."""
+from __future__ import annotations
+import ctypes as C
+import warnings
+from dataclasses import dataclass, field
+import numpy as np
+from ._lib import default_context
+from .spaces import Space
+from .tensor import DeviceTensor
+from .operators import SparseMPOSlice, MPOHamiltonian
+from .finitemps import qrpos, lqpos, _mask
+from .derivatives import MPO_ddAC, MPO_ddC
+from .fixedpoint import fixedpoint, Arnoldi, Lanczos
+from . import krylov
+
+TOLGAUGE = 1e-14
+
+
+def dyn_tol(eps, it, tol_min, tol_max, factor):
+    """updatetol(::DynamicTol, iter, eps) (dynamictols.jl:50-53)"""
+    return float(np.clip(eps * factor / np.sqrt(it), tol_min, tol_max))
+
+
+# ------------------------------------------------------------------------------------------ small helpers
+def _call2(ctx, fn, a, b, mod):
+    h = C.c_void_p()
+    ctx.check(fn(ctx.h, a.h, b.h, C.byref(h)))
+    return DeviceTensor.wrap(ctx, h, mod)
+
+
+def mul_right(A, Cm):
+    return _call2(A.ctx, A.ctx.lib.mpsk_mul_bond_right, A, Cm, A.Vl.modulus)
+
+
+def mul_left(Cm, A):
+    return _call2(A.ctx, A.ctx.lib.mpsk_mul_bond_left, Cm, A, A.Vl.modulus)
+
+
+def identity_bond(ctx, V: Space, dtype):
+    eye = np.zeros((V.dim, 1, V.dim), dtype=dtype)
+    eye[:, 0, :] = np.eye(V.dim)
+    t = DeviceTensor.from_dense(ctx, eye, V, (0,), V, dtype)
+    t._is_bond = True
+    return t
+
+
+_slices = {}
+
+
+def _entry_slice(sl: SparseMPOSlice, j, k):
+    """1 x 1 slice holding entry (j, k) (None: the unit MPO, i.e. an MPO-free transfer, transfer.jl:18-45)"""
+    key = (id(sl), j, k)
+    if key not in _slices:
+        if j is None:
+            _slices[key] = SparseMPOSlice([[1.0]], (0,), (0,), sl.pcharges)
+        else:
+            _slices[key] = SparseMPOSlice([[sl.Os[j][k]]], (sl.domcharges[j],), (sl.imcharges[k],), sl.pcharges)
+        _slices[key]._parent = sl          # keep the parent alive so that id() stays unique
+    return _slices[key]
+
+
+def transfer_left(v, sl1, A, Ab):
+    """v * TransferMatrix(A, O, Ab) for a single level tensor v and a 1x1 slice (transfer.jl:18-25,105-107)"""
+    ctx = A.ctx
+    h = C.c_void_p()
+    ctx.check(ctx.lib.mpsk_transfer_left(ctx.h, sl1.device(ctx), A.h, Ab.h, v.h, C.byref(h)))
+    return DeviceTensor.wrap(ctx, h, A.Vl.modulus)
+
+
+def transfer_right(v, sl1, A, Ab):
+    ctx = A.ctx
+    h = C.c_void_p()
+    ctx.check(ctx.lib.mpsk_transfer_right(ctx.h, sl1.device(ctx), A.h, Ab.h, v.h, C.byref(h)))
+    return DeviceTensor.wrap(ctx, h, A.Vl.modulus)
+
+
+class TransferMatrix:
+    """TransferMatrix(above, middle, below) over a unit cell; `tm * v` / `v * tm` (transfermatrix.jl:43-66).
+    above / below: lists of site tensors; middle: list of 1x1 slices (or None)."""
+
+    def __init__(self, above, middle, below, isflipped=False):
+        self.above = above if isinstance(above, (list, tuple)) else [above]
+        self.below = below if isinstance(below, (list, tuple)) else [below]
+        mid = middle if isinstance(middle, (list, tuple)) else [middle] * len(self.above)
+        self.middle = list(mid)
+        self.isflipped = isflipped
+        self._unit = None
+
+    def _sl(self, i):
+        if self.middle[i] is not None:
+            return self.middle[i]
+        if self._unit is None:
+            pq = self.above[0].mch
+            self._unit = SparseMPOSlice([[1.0]], (0,), (0,), pq)
+        return self._unit
+
+    def flip(self):
+        return TransferMatrix(self.above, self.middle, self.below, not self.isflipped)
+
+    def __call__(self, v):
+        if self.isflipped:                      # v * tm: sweep left -> right
+            for i in range(len(self.above)):
+                v = transfer_left(v, self._sl(i), self.above[i], self.below[i])
+        else:                                   # tm * v: sweep right -> left
+            for i in range(len(self.above) - 1, -1, -1):
+                v = transfer_right(v, self._sl(i), self.above[i], self.below[i])
+        return v
+
+    def __mul__(self, v):
+        return self(v)
+
+    def __rmul__(self, v):
+        return self.flip()(v)
+
+
+def regularize(tm, lvec, rvec):
+    """RegTransferMatrix (transfermatrix.jl:28-33,55,68-76): v -> tm(v) - <lvec, tm(v)> rvec with
+    <l, v> = sum l[1;2] v[2;1]"""
+    ladj = lvec.adjoint()
+
+    def f(v):
+        w = tm(v)
+        s = ladj.dot(w)
+        w.axpy(-s, rvec)
+        return w
+    return f
+
+
+# ------------------------------------------------------------------------------------------ InfiniteMPS
+class InfiniteMPS:
+    def __init__(self, AL, AR, CR, AC, V, pspace, ctx):
+        self.AL, self.AR, self.CR, self.AC = AL, AR, CR, AC      # lists over the unit cell; CR[i] right of site i
+        self.V, self.pspace, self.ctx = V, pspace, ctx
+        self.pq = tuple(int(c) for c in pspace.index_charges())
+        self.N = len(AL)
+        self.dtype = AL[0].dtype
+
+    def __len__(self):
+        return self.N
+
+    @staticmethod
+    def from_tensors(A, V, pspace, ctx=None, C0=None, tol=TOLGAUGE, maxiter=100):
+        """InfiniteMPS(A::Vector) (infinitemps.jl:139-171): gaugefix! order :LR, AC = AL * CR"""
+        ctx = ctx or default_context()
+        N = len(A)
+        C0 = C0 if C0 is not None else identity_bond(ctx, V[0], A[0].dtype)
+        AL, CR = uniform_leftorth(A, C0, tol, maxiter)
+        AR, CR = uniform_rightorth(AL, CR[N - 1], tol, maxiter)
+        AC = [mul_right(AL[i], CR[i]) for i in range(N)]
+        return InfiniteMPS(AL, AR, CR, AC, V, pspace, ctx)
+
+    @staticmethod
+    def from_AL(AL, C0, V, pspace, ctx, tol=TOLGAUGE, maxiter=100):
+        """InfiniteMPS(AL, C0) (infinitemps.jl:173-187): gaugefix! order :R"""
+        N = len(AL)
+        AR, CR = uniform_rightorth(AL, C0, tol, maxiter)
+        AC = [mul_right(AL[i], CR[i]) for i in range(N)]
+        return InfiniteMPS(list(AL), AR, CR, AC, V, pspace, ctx)
+
+    @staticmethod
+    def random(rng, pspace: Space, Vs, ctx=None, dtype=np.complex128):
+        ctx = ctx or default_context()
+        N = len(Vs)
+        pq = pspace.index_charges()
+        A = []
+        for i in range(N):
+            Vl, Vr = Vs[i], Vs[(i + 1) % N]
+            msk = _mask(Vl, pq, Vr)
+            a = rng.standard_normal(msk.shape) + 1j * rng.standard_normal(msk.shape)
+            A.append(DeviceTensor.from_dense(ctx, (a * msk).astype(dtype), Vl, [int(c) for c in pq], Vr, dtype))
+        return InfiniteMPS.from_tensors(A, list(Vs), pspace, ctx)
+
+
+def _normalize(t):
+    t.scale(1.0 / t.norm())
+    return t
+
+
+def uniform_leftorth(A, C0, tol=TOLGAUGE, maxiter=100, eig_miniter=10):
+    """ortho.jl:143-201 (LeftCanonical): QRpos sweeps, Arnoldi fixed point of flip(TransferMatrix(A, AL)) after 10 sweeps"""
+    ctx = A[0].ctx
+    mod = A[0].Vl.modulus
+    N = len(A)
+    CR = [None] * N
+    CR[N - 1] = _normalize(C0.copy())
+    AL = [None] * N
+    eps = np.inf
+    for it in range(maxiter + 2):
+        if it >= eig_miniter:
+            etol = dyn_tol(eps ** 2, 1, TOLGAUGE / 10, np.inf, 1)
+            tm = TransferMatrix(list(A), None, list(AL)).flip()
+            _, vec = fixedpoint(tm, CR[N - 1], "LM", Arnoldi(tol=etol, krylovdim=30, hermitian=False))
+            _, CR[N - 1] = qrpos(ctx, vec, mod)
+        Cprev = CR[N - 1]
+        for i in range(N):
+            CA = mul_left(CR[(i - 1) % N], A[i])
+            AL[i], CR[i] = qrpos(ctx, CA, mod)
+        _normalize(CR[N - 1])
+        d = Cprev.copy(); d.axpy(-1.0, CR[N - 1]); eps = d.norm()
+        if eps < tol or it + 1 > maxiter:
+            break
+    return AL, CR
+
+
+def uniform_rightorth(A, C0, tol=TOLGAUGE, maxiter=100, eig_miniter=10):
+    """ortho.jl:203-257 (RightCanonical)"""
+    ctx = A[0].ctx
+    mod = A[0].Vl.modulus
+    N = len(A)
+    CR = [None] * N
+    CR[N - 1] = _normalize(C0.copy())
+    AR = [None] * N
+    eps = np.inf
+    for it in range(maxiter + 2):
+        if it >= eig_miniter:
+            etol = dyn_tol(eps ** 2, 1, TOLGAUGE / 10, np.inf, 1)
+            tm = TransferMatrix(list(A), None, list(AR))
+            _, vec = fixedpoint(tm, CR[N - 1], "LM", Arnoldi(tol=etol, krylovdim=30, hermitian=False))
+            CR[N - 1], _ = lqpos(ctx, vec, mod)
+        Cprev = CR[N - 1]
+        for i in range(N - 1, -1, -1):
+            AC = mul_right(A[i], CR[i])
+            CR[(i - 1) % N], AR[i] = lqpos(ctx, AC, mod)
+        _normalize(CR[N - 1])
+        d = Cprev.copy(); d.axpy(-1.0, CR[N - 1]); eps = d.norm()
+        if eps < tol or it + 1 > maxiter:
+            break
+    return AR, CR
+
+
+def regauge(AC, Cm):
+    """regauge!(AC, CR) (ortho.jl:127-131): AL = Q_AC * Q_C'"""
+    ctx, mod = AC.ctx, AC.Vl.modulus
+    Qac, _ = qrpos(ctx, AC, mod)
+    Qc, _ = qrpos(ctx, Cm, mod)
+    return mul_right(Qac, Qc.adjoint())
+
+
+# ------------------------------------------------------------------------------------------ MPOHamInfEnv
+def _isid(H: MPOHamiltonian, i):
+    return all(s.isscal(i, i) and abs(s.Os[i][i] - 1) < 1e-14 for s in H.slices)
+
+
+class MPOHamInfEnv:
+    """mpohaminfenv.jl:4-74; lw[j][i] / rw[j][i]: level-j environments at site i (single-label tensors)"""
+
+    def __init__(self, psi: InfiniteMPS, H: MPOHamiltonian, tol=1e-12, maxiter=100):
+        self.opp, self.tol, self.maxiter = H, tol, maxiter
+        N, od = psi.N, H.odim
+        ctx = psi.ctx
+        self.lw = [[DeviceTensor.zeros(ctx, psi.V[i], (-H[i].domcharges[j],), psi.V[i], psi.dtype) for i in range(N)] for j in range(od)]
+        self.rw = [[DeviceTensor.zeros(ctx, psi.V[(i + 1) % N], (H[i].imcharges[j],), psi.V[(i + 1) % N], psi.dtype) for i in range(N)] for j in range(od)]
+        self.dependency = None
+        self._stacked = {}
+        self.recalculate(psi)
+
+    def recalculate(self, psi, tol=None):
+        tol = self.tol if tol is None else tol
+        calclw(self.lw, psi, self.opp, tol, self.maxiter)
+        calcrw(self.rw, psi, self.opp, tol, self.maxiter)
+        self.dependency = psi
+        self._stacked = {}
+        return self
+
+    def leftenv(self, pos, psi):
+        """vector of levels as ONE stacked environment tensor (what the matvec consumes)"""
+        if self.dependency is not psi:
+            self.recalculate(psi)
+        key = ("l", pos % psi.N)
+        if key not in self._stacked:
+            self._stacked[key] = DeviceTensor.stack([self.lw[j][pos % psi.N] for j in range(self.opp.odim)])
+        return self._stacked[key]
+
+    def rightenv(self, pos, psi):
+        if self.dependency is not psi:
+            self.recalculate(psi)
+        key = ("r", pos % psi.N)
+        if key not in self._stacked:
+            self._stacked[key] = DeviceTensor.stack([self.rw[j][pos % psi.N] for j in range(self.opp.odim)])
+        return self._stacked[key]
+
+
+def environments(psi: InfiniteMPS, H: MPOHamiltonian, tol=1e-12, maxiter=100):
+    """environments(psi::InfiniteMPS, H::MPOHamiltonian; solver) (mpohaminfenv.jl:40-45)"""
+    return MPOHamInfEnv(psi, H, tol, maxiter)
+
+
+def _left_cyclethrough(index, fp, H, st):
+    """mpohaminfenv.jl:177-195"""
+    N = st.N
+    for i in range(N):
+        nxt = (i + 1) % N
+        acc = None
+        for j in range(index, -1, -1):
+            if not H[i].contains(j, index):
+                continue
+            t = transfer_left(fp[j][i], _entry_slice(H[i], j, index), st.AL[i], st.AL[i])
+            if acc is None:
+                acc = t
+            else:
+                acc.axpy(1.0, t); t.free()
+        fp[index][nxt] = acc if acc is not None else fp[index][nxt].zerovector()
+
+
+def _right_cyclethrough(index, fp, H, st):
+    """mpohaminfenv.jl:197-215"""
+    N = st.N
+    for i in range(N - 1, -1, -1):
+        prv = (i - 1) % N
+        acc = None
+        for j in range(index, len(fp)):
+            if not H[i].contains(index, j):
+                continue
+            t = transfer_right(fp[j][i], _entry_slice(H[i], index, j), st.AR[i], st.AR[i])
+            if acc is None:
+                acc = t
+            else:
+                acc.axpy(1.0, t); t.free()
+        fp[index][prv] = acc if acc is not None else fp[index][prv].zerovector()
+
+
+def _gmres(f, b, x0, tol, maxiter):
+    x, info = krylov.linsolve_gmres(f, b, x0, 1.0, -1.0, tol, 30, maxiter)
+    if info["converged"] == 0:
+        warnings.warn(f"environment linsolve failed to converge: normres = {info['normres']}")
+    return x
+
+
+def calclw(fp, st: InfiniteMPS, H, tol, maxiter):
+    """mpohaminfenv.jl:76-125"""
+    N, od = st.N, H.odim
+    ctx = st.ctx
+    ident = [identity_bond(ctx, st.V[i], st.dtype) for i in range(N)]                   # l_LL(st, i)
+    rho = [mul_right_bond(st.CR[i], st.CR[i].adjoint()) for i in range(N)]              # r_LL(st, i) = CR CR'
+    fp[0][0] = ident[0].copy()
+    if N > 1:
+        _left_cyclethrough(0, fp, H, st)
+    for i in range(1, od):
+        prev = fp[i][0]
+        fp[i][0] = prev.zerovector()
+        _left_cyclethrough(i, fp, H, st)
+        if _isid(H, i):
+            tm = regularize(TransferMatrix(st.AL, None, st.AL).flip(), rho[N - 1], ident[0])
+            fp[i][0] = _gmres(tm, fp[i][0], prev, tol, maxiter)
+            if N > 1:
+                _left_cyclethrough(i, fp, H, st)
+            for s in range(N):                                                          # mpohaminfenv.jl:102-107
+                sc = rho[(s - 1) % N].adjoint().dot(fp[i][s])
+                fp[i][s].axpy(-sc, ident[s])
+        else:
+            if all(sl.contains(i, i) for sl in H.slices):
+                tm = TransferMatrix(st.AL, [_entry_slice(H[s], i, i) for s in range(N)], st.AL).flip()
+                fp[i][0] = _gmres(tm, fp[i][0], prev, tol, maxiter)
+            if N > 1:
+                _left_cyclethrough(i, fp, H, st)
+    return fp
+
+
+def calcrw(fp, st: InfiniteMPS, H, tol, maxiter):
+    """mpohaminfenv.jl:127-175"""
+    N, od = st.N, H.odim
+    ctx = st.ctx
+    ident = [identity_bond(ctx, st.V[(i + 1) % N], st.dtype) for i in range(N)]         # r_RR(st, i)
+    lrr = [mul_right_bond(st.CR[(i - 1) % N].adjoint(), st.CR[(i - 1) % N]) for i in range(N)]   # l_RR(st, i) = CR[i-1]' CR[i-1]
+    fp[od - 1][N - 1] = ident[N - 1].copy()
+    if N > 1:
+        _right_cyclethrough(od - 1, fp, H, st)
+    for i in range(od - 2, -1, -1):
+        prev = fp[i][N - 1]
+        fp[i][N - 1] = prev.zerovector()
+        _right_cyclethrough(i, fp, H, st)
+        if _isid(H, i):
+            tm = regularize(TransferMatrix(st.AR, None, st.AR), lrr[0], ident[N - 1])
+            fp[i][N - 1] = _gmres(tm, fp[i][N - 1], prev, tol, maxiter)
+            if N > 1:
+                _right_cyclethrough(i, fp, H, st)
+            for s in range(N):                                                          # mpohaminfenv.jl:153-159
+                sc = lrr[(s + 1) % N].adjoint().dot(fp[i][s])
+                fp[i][s].axpy(-sc, ident[s])
+        else:
+            if all(sl.contains(i, i) for sl in H.slices):
+                tm = TransferMatrix(st.AR, [_entry_slice(H[s], i, i) for s in range(N)], st.AR)
+                fp[i][N - 1] = _gmres(tm, fp[i][N - 1], prev, tol, maxiter)
+            if N > 1:
+                _right_cyclethrough(i, fp, H, st)
+    return fp
+
+
+def mul_right_bond(A, B):
+    """bond * bond"""
+    return mul_right(A, B)
+
+
+# ------------------------------------------------------------------------------------------ read-outs / VUMPS
+def expectation_value(st: InfiniteMPS, H, envs: MPOHamInfEnv):
+    """expval.jl:111-124: energy density per site"""
+    N, od = st.N, H.odim
+    ens = np.zeros(N, dtype=np.complex128)
+    for i in range(N):
+        if envs.dependency is not st:
+            envs.recalculate(st)
+        rho_adj = mul_right_bond(st.CR[i], st.CR[i].adjoint()).adjoint()
+        for j in range(od - 1, -1, -1):
+            if not H[i].contains(j, od - 1):
+                continue
+            apl = transfer_left(envs.lw[j][i], _entry_slice(H[i], j, od - 1), st.AL[i], st.AL[i])
+            ens[i] += rho_adj.dot(apl)
+    return ens
+
+
+def calc_galerkin(st: InfiniteMPS, loc, envs):
+    """toolbox.jl:17-22"""
+    from .algorithms import _overlap
+
+    class _P:       # what _overlap needs
+        pass
+    P = _P(); P.ctx, P.pq, P.pspace, P.dtype = st.ctx, st.pq, st.pspace, st.dtype
+    h = MPO_ddAC(st.ctx, envs.opp[loc], envs.leftenv(loc, st), envs.rightenv(loc, st), st.AC[loc])
+    ac = h(st.AC[loc]); h.free()
+    ac.scale(1.0 / ac.norm())
+    AL = st.AL[loc]
+    ov = _overlap(P, ac, AL)
+    proj = mul_right(AL, ov)
+    ac.axpy(-1.0, proj)
+    return ac.norm()
+
+
+@dataclass
+class VUMPS:
+    """vumps.jl:18-27 with the default dynamic tolerances of defaults.jl:38-57"""
+    tol: float = 1e-12
+    maxiter: int = 100
+    verbosity: int = 0
+    finalize: object = None
+
+
+def find_groundstate_vumps(st: InfiniteMPS, H, alg: VUMPS = None, envs=None, log=None):
+    """find_groundstate(psi::InfiniteMPS, H, alg::VUMPS, envs) (vumps.jl:29-92)"""
+    alg = alg or VUMPS()
+    envs = envs or environments(st, H)
+    N = st.N
+    eps = max(calc_galerkin(st, i, envs) for i in range(N))
+    for it in range(1, alg.maxiter + 1):
+        etol = dyn_tol(eps, it, 1e-12, 1e-5, 1e-5)
+        eig = Lanczos(tol=etol, krylovdim=30, maxiter=100)
+        newAL = []
+        for loc in range(N):                                       # _vumps_localupdate (vumps.jl:77-92)
+            hac = MPO_ddAC(st.ctx, H[loc], envs.leftenv(loc, st), envs.rightenv(loc, st), st.AC[loc])
+            _, ac = fixedpoint(hac, st.AC[loc], "SR", eig); hac.free()
+            hc = MPO_ddC(st.ctx, envs.leftenv(loc + 1, st), envs.rightenv(loc, st), st.CR[loc])
+            _, c = fixedpoint(hc, st.CR[loc], "SR", eig); hc.free()
+            newAL.append(regauge(ac, c))
+        gtol = dyn_tol(eps, it, TOLGAUGE, 1e-5, 1e-8)
+        st = InfiniteMPS.from_AL(newAL, st.CR[N - 1], st.V, st.pspace, st.ctx, gtol, 100)     # vumps.jl:52
+        envs.recalculate(st, dyn_tol(eps, it, 1e-12, 1e-5, 1e-5))                               # vumps.jl:54-55
+        if alg.finalize is not None:
+            st, envs = alg.finalize(it, st, H, envs)
+        eps = max(calc_galerkin(st, i, envs) for i in range(N))
+        if log is not None:
+            log.append(dict(iter=it, eps=eps, energy=float(np.sum(expectation_value(st, H, envs)).real)))
+        if eps <= alg.tol:
+            break
+    return st, envs, eps

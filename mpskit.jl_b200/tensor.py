@@ -120,6 +120,26 @@ class DeviceTensor:
             out[lo[jl]:lo[jl + 1], m, ro[jr]:ro[jr + 1]] = blocks[(m, jl)]
         return out
 
+    # ---- label algebra ----------------------------------------------------------------------------
+    @staticmethod
+    def stack(ts):
+        ctx = ts[0].ctx
+        arr = (C.c_void_p * len(ts))(*[t.h for t in ts])
+        h = C.c_void_p()
+        ctx.check(ctx.lib.mpsk_tensor_stack_labels(ctx.h, arr, len(ts), C.byref(h)))
+        return DeviceTensor.wrap(ctx, h, ts[0].Vl.modulus)
+
+    def select(self, labels):
+        lab = (C.c_int32 * len(labels))(*[int(x) for x in labels])
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.mpsk_tensor_select_labels(self.ctx.h, self.h, lab, len(labels), C.byref(h)))
+        return DeviceTensor.wrap(self.ctx, h, self.Vl.modulus)
+
+    def adjoint(self):
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.mpsk_tensor_adjoint(self.ctx.h, self.h, C.byref(h)))
+        return DeviceTensor.wrap(self.ctx, h, self.Vl.modulus)
+
     # ---- VectorInterface ----------------------------------------------------------------------
     def copy(self):
         h = C.c_void_p()

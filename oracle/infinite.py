@@ -1,0 +1,338 @@
+"""Infinite-MPS algorithms of the reference restated on dense (charged) tensors: uniform gauge
+(src/states/ortho.jl:127-257, src/states/infinitemps.jl:139-204), MPOHamInfEnv (src/environments/mpohaminfenv.jl:56-215),
+VUMPS (src/algorithms/groundstate/vumps.jl:29-92), infinite expectation values (src/algorithms/expval.jl:111-124) and
+calc_galerkin (src/algorithms/toolbox.jl:23-25).  Sites are 0-based and periodic; environments are stored per MPO level
+as bond matrices lw[j][i][bra, ket] (width-1 levels), rw[j][i][ket, bra]."""
+from __future__ import annotations
+import numpy as np
+from .spaces import Space
+from .linalg import qrpos, lqpos
+from .krylov import eigsolve_arnoldi, eigsolve_lanczos, linsolve_gmres
+from .contract import transfer_left_bond, transfer_right_bond, dAC_sparse, dC_dense
+from .mpo import MPOHamiltonian
+
+TOLGAUGE = 1e-14
+
+
+def dyn_tol(eps, it, tol_min, tol_max, factor):
+    """updatetol (dynamictols.jl:50-53)"""
+    return float(np.clip(eps * factor / np.sqrt(it), tol_min, tol_max))
+
+
+class InfiniteMPS:
+    def __init__(self, AL, AR, CR, AC, V, pq, modulus=0):
+        self.AL, self.AR, self.CR, self.AC = AL, AR, CR, AC    # CR[i]: bond right of site i; CR[-1] == CR[N-1]
+        self.V, self.pq, self.modulus = V, np.asarray(pq), modulus   # V[i]: bond space left of site i
+        self.N = len(AL)
+
+    # --- per-sector factorisations
+    def _rowq(self, Vl):
+        return (Vl.index_charges()[:, None] + self.pq[None, :]).reshape(-1)
+
+    @staticmethod
+    def leftorth(A, Vl, Vr, pq, mod=0):
+        Dl, d, Dr = A.shape
+        rowq = (Vl.index_charges()[:, None] + np.asarray(pq)[None, :]).reshape(-1)
+        Q, R, nV = qrpos(A.reshape(Dl * d, Dr), rowq, Vr.index_charges(), mod)
+        return Q.reshape(Dl, d, nV.dim), R
+
+    @staticmethod
+    def rightorth(A, Vl, Vr, pq, mod=0):
+        Dl, d, Dr = A.shape
+        colq = (Vr.index_charges()[None, :] - np.asarray(pq)[:, None]).reshape(-1)
+        Lm, Q, nV = lqpos(A.reshape(Dl, d * Dr), Vl.index_charges(), colq, mod)
+        return Lm, Q.reshape(nV.dim, d, Dr)
+
+    @staticmethod
+    def from_tensors(A, V, pq, C0=None, tol=TOLGAUGE, maxiter=100, mod=0):
+        """InfiniteMPS(A::Vector) (infinitemps.jl:139-171): gaugefix! order :LR, then AC = AL * CR"""
+        N = len(A)
+        D0 = A[0].shape[0]
+        C0 = np.eye(D0, dtype=np.complex128) if C0 is None else C0
+        AL, CR = uniform_leftorth(A, C0, V, pq, tol, maxiter, mod)
+        AR, CR = uniform_rightorth(AL, CR[N - 1], V, pq, tol, maxiter, mod)
+        AC = [np.einsum('apb,bc->apc', AL[i], CR[i]) for i in range(N)]
+        return InfiniteMPS(AL, AR, CR, AC, V, pq, mod)
+
+    @staticmethod
+    def from_AL(AL, C0, V, pq, tol=TOLGAUGE, maxiter=100, mod=0):
+        """InfiniteMPS(AL, C0) (infinitemps.jl:173-187): gaugefix! order :R"""
+        N = len(AL)
+        AL = [a.copy() for a in AL]
+        AR, CR = uniform_rightorth(AL, C0, V, pq, tol, maxiter, mod)
+        AC = [np.einsum('apb,bc->apc', AL[i], CR[i]) for i in range(N)]
+        return InfiniteMPS(AL, AR, CR, AC, V, pq, mod)
+
+    @staticmethod
+    def random(rng, pspace: Space, Vs, dtype=np.complex128):
+        from .blocks import mask3
+        N = len(Vs)
+        pq = pspace.index_charges()
+        A = []
+        for i in range(N):
+            Vl, Vr = Vs[i], Vs[(i + 1) % N]
+            msk = mask3(Vl, pq, Vr)
+            a = rng.standard_normal(msk.shape) + 1j * rng.standard_normal(msk.shape)
+            A.append((a * msk).astype(dtype))
+        return InfiniteMPS.from_tensors(A, list(Vs), pq, mod=pspace.modulus)
+
+
+def _transfer_left_cell(v, A, B):
+    for a, b in zip(A, B):
+        v = transfer_left_bond(v, a, b)
+    return v
+
+
+def _transfer_right_cell(v, A, B):
+    for a, b in zip(reversed(A), reversed(B)):
+        v = transfer_right_bond(v, a, b)
+    return v
+
+
+def uniform_leftorth(A, C0, V, pq, tol=TOLGAUGE, maxiter=100, mod=0, eig_miniter=10):
+    """ortho.jl:143-201"""
+    N = len(A)
+    CR = [None] * N
+    CR[N - 1] = C0 / np.linalg.norm(C0)
+    AL = [None] * N
+    eps = np.inf
+    for it in range(maxiter + 2):
+        # gauge_eigsolve_step!
+        if it >= eig_miniter:
+            etol = dyn_tol(eps ** 2, 1, TOLGAUGE / 10, np.inf, 1)
+            _, vec, _ = eigsolve_arnoldi(lambda v: _transfer_left_cell(v, A, AL), CR[N - 1], "LM", etol, 30, 100)
+            Vb = V[0]
+            _, R, _ = qrpos(vec, Vb.index_charges(), Vb.index_charges(), mod)
+            CR[N - 1] = R
+        Cprev = CR[N - 1]
+        # gauge_orth_step!
+        for i in range(N):
+            CA = np.einsum('ab,bpc->apc', CR[(i - 1) % N], A[i])
+            AL[i], CR[i] = InfiniteMPS.leftorth(CA, V[i], V[(i + 1) % N], pq, mod)
+        CR[N - 1] = CR[N - 1] / np.linalg.norm(CR[N - 1])
+        eps = np.linalg.norm(Cprev - CR[N - 1])
+        if eps < tol or it + 1 > maxiter:
+            break
+    return AL, CR
+
+
+def uniform_rightorth(A, C0, V, pq, tol=TOLGAUGE, maxiter=100, mod=0, eig_miniter=10):
+    """ortho.jl:203-257"""
+    N = len(A)
+    CR = [None] * N
+    CR[N - 1] = C0 / np.linalg.norm(C0)
+    AR = [None] * N
+    eps = np.inf
+    for it in range(maxiter + 2):
+        if it >= eig_miniter:
+            etol = dyn_tol(eps ** 2, 1, TOLGAUGE / 10, np.inf, 1)
+            _, vec, _ = eigsolve_arnoldi(lambda v: _transfer_right_cell(v, A, AR), CR[N - 1], "LM", etol, 30, 100)
+            Vb = V[0]
+            Lm, _, _ = lqpos(vec, Vb.index_charges(), Vb.index_charges(), mod)
+            CR[N - 1] = Lm
+        Cprev = CR[N - 1]
+        for i in range(N - 1, -1, -1):
+            AC = np.einsum('apb,bc->apc', A[i], CR[i])
+            CR[(i - 1) % N], AR[i] = InfiniteMPS.rightorth(AC, V[i], V[(i + 1) % N], pq, mod)
+        CR[N - 1] = CR[N - 1] / np.linalg.norm(CR[N - 1])
+        eps = np.linalg.norm(Cprev - CR[N - 1])
+        if eps < tol or it + 1 > maxiter:
+            break
+    return AR, CR
+
+
+# ------------------------------------------------------------------------------------------ MPOHamInfEnv
+def _isid(H: MPOHamiltonian, i):
+    """mpohamiltonian.jl:52-57"""
+    return all(np.isscalar(s.Os[i][i]) and abs(s.Os[i][i] - 1) < 1e-14 for s in H.slices)
+
+
+def _tl_entry(v, sl, j, k, A):
+    """fp[j] * TransferMatrix(A, H[j,k], A)"""
+    if sl.isscal(j, k):
+        return sl.Os[j][k] * transfer_left_bond(v, A, A)
+    return np.einsum('ad,dec,fe,afh->hc', v, A, sl.op(j, k), np.conj(A), optimize=True)
+
+
+def _tr_entry(v, sl, j, k, A):
+    """TransferMatrix(A, H[j,k], A) * fp[k]"""
+    if sl.isscal(j, k):
+        return sl.Os[j][k] * transfer_right_bond(v, A, A)
+    return np.einsum('xba,db,zde,ae->xz', A, sl.op(j, k), np.conj(A), v, optimize=True)
+
+
+class MPOHamInfEnv:
+    def __init__(self, psi: InfiniteMPS, H: MPOHamiltonian, tol=1e-12, maxiter=100):
+        self.opp, self.tol, self.maxiter = H, tol, maxiter
+        N, od = psi.N, H.odim
+        rng = np.random.default_rng(0)
+        D = [psi.AL[i].shape[0] for i in range(N)]
+        self.lw = [[np.zeros((D[i], D[i]), dtype=np.complex128) for i in range(N)] for _ in range(od)]
+        self.rw = [[np.zeros((psi.AR[i].shape[2], psi.AR[i].shape[2]), dtype=np.complex128) for i in range(N)] for _ in range(od)]
+        self.dependency = None
+        self.recalculate(psi)
+
+    def recalculate(self, psi, tol=None):
+        tol = self.tol if tol is None else tol
+        calclw(self.lw, psi, self.opp, tol, self.maxiter)
+        calcrw(self.rw, psi, self.opp, tol, self.maxiter)
+        self.dependency = psi
+        return self
+
+    def leftenv(self, pos, psi):
+        if self.dependency is not psi:
+            self.recalculate(psi)
+        return np.stack([self.lw[j][pos % psi.N] for j in range(self.opp.odim)], axis=1)     # [bra, w, ket]
+
+    def rightenv(self, pos, psi):
+        if self.dependency is not psi:
+            self.recalculate(psi)
+        return np.stack([self.rw[j][pos % psi.N] for j in range(self.opp.odim)], axis=1)     # [ket, w, bra]
+
+
+def _left_cyclethrough(index, fp, H, st):
+    N = st.N
+    for i in range(N):
+        nxt = (i + 1) % N
+        fp[index][nxt] = np.zeros_like(fp[index][nxt])
+        for j in range(index, -1, -1):
+            if not H[i].contains(j, index):
+                continue
+            fp[index][nxt] = fp[index][nxt] + _tl_entry(fp[j][i], H[i], j, index, st.AL[i])
+
+
+def _right_cyclethrough(index, fp, H, st):
+    N = st.N
+    for i in range(N - 1, -1, -1):
+        prv = (i - 1) % N
+        fp[index][prv] = np.zeros_like(fp[index][prv])
+        for j in range(index, len(fp)):
+            if not H[i].contains(index, j):
+                continue
+            fp[index][prv] = fp[index][prv] + _tr_entry(fp[j][i], H[i], index, j, st.AR[i])
+
+
+def calclw(fp, st: InfiniteMPS, H, tol, maxiter):
+    """mpohaminfenv.jl:76-125.  fp[j][i]: left env of level j at site i ([bra; ket])"""
+    N, od = st.N, H.odim
+    D0 = st.AL[0].shape[0]
+    fp[0][0] = np.eye(D0, dtype=np.complex128)                      # l_LL (x) 1
+    if N > 1:
+        _left_cyclethrough(0, fp, H, st)
+    rho = [st.CR[i] @ st.CR[i].conj().T for i in range(N)]          # r_LL(st, i)
+    for i in range(1, od):
+        prev = fp[i][0].copy()
+        fp[i][0] = np.zeros_like(fp[i][0])
+        _left_cyclethrough(i, fp, H, st)
+        if _isid(H, i):
+            r_end = rho[N - 1]
+
+            def tm(v):                                              # flip(regularize(TransferMatrix(AL, AL), l_LL, r_LL))
+                w = _transfer_left_cell(v, st.AL, st.AL)
+                return w - np.einsum('ab,ba->', r_end, w) * np.eye(D0)
+            fp[i][0], info = linsolve_gmres(tm, fp[i][0], prev, 1.0, -1.0, tol, 30, maxiter)
+            if N > 1:
+                _left_cyclethrough(i, fp, H, st)
+            for s in range(N):                                      # subtract the fixed-point component on every site
+                fp[i][s] = fp[i][s] - np.einsum('ab,ba->', fp[i][s], rho[(s - 1) % N]) * np.eye(fp[i][s].shape[0])
+        else:
+            if all(sl.contains(i, i) for sl in H.slices):
+                def tm(v):
+                    for s in range(N):
+                        v = _tl_entry(v, H[s], i, i, st.AL[s])
+                    return v
+                fp[i][0], info = linsolve_gmres(tm, fp[i][0], prev, 1.0, -1.0, tol, 30, maxiter)
+            if N > 1:
+                _left_cyclethrough(i, fp, H, st)
+    return fp
+
+
+def calcrw(fp, st: InfiniteMPS, H, tol, maxiter):
+    """mpohaminfenv.jl:127-175.  fp[j][i]: right env of level j at site i ([ket; bra])"""
+    N, od = st.N, H.odim
+    De = st.AR[N - 1].shape[2]
+    fp[od - 1][N - 1] = np.eye(De, dtype=np.complex128)
+    if N > 1:
+        _right_cyclethrough(od - 1, fp, H, st)
+    lrr = [st.CR[(i - 1) % N].conj().T @ st.CR[(i - 1) % N] for i in range(N)]     # l_RR(st, i)
+    for i in range(od - 2, -1, -1):
+        prev = fp[i][N - 1].copy()
+        fp[i][N - 1] = np.zeros_like(fp[i][N - 1])
+        _right_cyclethrough(i, fp, H, st)
+        if _isid(H, i):
+            l0 = lrr[0]
+
+            def tm(v):                                              # regularize(TransferMatrix(AR, AR), l_RR, r_RR)
+                w = _transfer_right_cell(v, st.AR, st.AR)
+                return w - np.einsum('ab,ba->', l0, w) * np.eye(De)
+            fp[i][N - 1], info = linsolve_gmres(tm, fp[i][N - 1], prev, 1.0, -1.0, tol, 30, maxiter)
+            if N > 1:
+                _right_cyclethrough(i, fp, H, st)
+            for s in range(N):
+                fp[i][s] = fp[i][s] - np.einsum('ab,ba->', fp[i][s], lrr[(s + 1) % N]) * np.eye(fp[i][s].shape[0])
+        else:
+            if all(sl.contains(i, i) for sl in H.slices):
+                def tm(v):
+                    for s in range(N - 1, -1, -1):
+                        v = _tr_entry(v, H[s], i, i, st.AR[s])
+                    return v
+                fp[i][N - 1], info = linsolve_gmres(tm, fp[i][N - 1], prev, 1.0, -1.0, tol, 30, maxiter)
+            if N > 1:
+                _right_cyclethrough(i, fp, H, st)
+    return fp
+
+
+def expectation_value(st: InfiniteMPS, H, envs: MPOHamInfEnv):
+    """expval.jl:111-124: energy density per site"""
+    N, od = st.N, H.odim
+    ens = np.zeros(N, dtype=np.complex128)
+    for i in range(N):
+        GL = envs.leftenv(i, st)
+        rho = st.CR[i] @ st.CR[i].conj().T
+        for j in range(od - 1, -1, -1):
+            if not H[i].contains(j, od - 1):
+                continue
+            apl = _tl_entry(GL[:, j, :], H[i], j, od - 1, st.AL[i])
+            ens[i] += np.einsum('ab,ba->', apl, rho)
+    return ens
+
+
+def calc_galerkin(st: InfiniteMPS, loc, envs):
+    """toolbox.jl:17-22"""
+    y = dAC_sparse(st.AC[loc], envs.opp[loc], envs.leftenv(loc, st), envs.rightenv(loc, st))
+    y = y / np.linalg.norm(y)
+    AL = st.AL[loc]
+    return float(np.linalg.norm(y - np.einsum('apb,cqb,cqd->apd', AL, np.conj(AL), y, optimize=True)))
+
+
+def regauge(AC, C, Vl, Vr, pq, mod=0):
+    """ortho.jl:127-131: AL = Q_AC * Q_C'"""
+    Qac, _ = InfiniteMPS.leftorth(AC, Vl, Vr, pq, mod)
+    Qc, _, _ = qrpos(C, Vr.index_charges(), Vr.index_charges(), mod)
+    return np.einsum('apb,cb->apc', Qac, np.conj(Qc))
+
+
+def vumps(st: InfiniteMPS, H, tol=1e-12, maxiter=100, envs=None, log=None):
+    """find_groundstate(psi::InfiniteMPS, H, VUMPS()) (vumps.jl:29-92) with the default dynamic tolerances"""
+    envs = envs or MPOHamInfEnv(st, H)
+    N = st.N
+    eps = max(calc_galerkin(st, i, envs) for i in range(N))
+    for it in range(1, maxiter + 1):
+        etol = dyn_tol(eps, it, 1e-12, 1e-5, 1e-5)
+        newAL = []
+        for loc in range(N):
+            GL, GR = envs.leftenv(loc, st), envs.rightenv(loc, st)
+            _, ac, _ = eigsolve_lanczos(lambda x: dAC_sparse(x, H[loc], GL, GR), st.AC[loc], "SR", etol, 30, 100)
+            GLc, GRc = envs.leftenv(loc + 1, st), envs.rightenv(loc, st)
+            _, c, _ = eigsolve_lanczos(lambda x: dC_dense(x, GLc, GRc), st.CR[loc], "SR", etol, 30, 100)
+            newAL.append(regauge(ac, c, st.V[loc], st.V[(loc + 1) % N], st.pq, st.modulus))
+        gtol = dyn_tol(eps, it, TOLGAUGE, 1e-5, 1e-8)
+        st = InfiniteMPS.from_AL(newAL, st.CR[N - 1], st.V, st.pq, gtol, 100, st.modulus)
+        envtol = dyn_tol(eps, it, 1e-12, 1e-5, 1e-5)
+        envs.recalculate(st, envtol)
+        eps = max(calc_galerkin(st, i, envs) for i in range(N))
+        if log is not None:
+            log.append(dict(iter=it, eps=eps, energy=float(np.sum(expectation_value(st, H, envs)).real)))
+        if eps <= tol:
+            break
+    return st, envs, eps
