@@ -49,6 +49,8 @@ enum { MPSK_NOTRUNC = 0, MPSK_TRUNCDIM = 1, MPSK_TRUNCERR = 2, MPSK_TRUNCBELOW =
 #define MPSK_TRUNC_NO_NORMALIZE 0x100   /* OR into mpsk_trunc.kind: skip normalize!(c) (TDVP2, tdvp.jl:124-126) */
 enum { MPSK_OP_DC = 0, MPSK_OP_DAC = 1, MPSK_OP_DAC2 = 2 };
 
+#define MPSK_FLAG_EXACT_SVD 2ull      /* tsvd: cuSOLVER gesvd for every sector (default: Gram + heevd + QR route for sectors >= 256) */
+#define MPSK_FLAG_FAST_SVD_ALL 4ull   /* tsvd: Gram route for every sector (tests) */
 #define MPSK_FLAG_DEBUG_GEMM 1ull  /* route contractions through the one-thread-per-element cross-check kernel (tests only) */
 
 typedef struct { int32_t nsec; const int32_t* charge; const int64_t* dim; int32_t modulus; } mpsk_space;

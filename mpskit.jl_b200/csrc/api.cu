@@ -441,15 +441,13 @@ int32_t mpsk_transfer_left(mpsk_ctx* ctx, const mpsk_mposlice* h, const mpsk_ten
                            mpsk_tensor** out) {
   Tensor* o = nullptr;
   MPSK_TRY(transfer_left(CTX(ctx), SLICE(h), CTEN(A), CTEN(Abar), CTEN(GL), &o));
-  *out = reinterpret_cast<mpsk_tensor*>(o);   // stays in KR form: that is what op_create / the next transfer consume
-  return MPSK_OK;
+  return to_kl(CTX(ctx), o, out);
 }
 int32_t mpsk_transfer_right(mpsk_ctx* ctx, const mpsk_mposlice* h, const mpsk_tensor* A, const mpsk_tensor* Abar, const mpsk_tensor* GR,
                             mpsk_tensor** out) {
   Tensor* o = nullptr;
   MPSK_TRY(transfer_right(CTX(ctx), SLICE(h), CTEN(A), CTEN(Abar), CTEN(GR), &o));
-  *out = reinterpret_cast<mpsk_tensor*>(o);
-  return MPSK_OK;
+  return to_kl(CTX(ctx), o, out);
 }
 int32_t mpsk_contract_ac2(mpsk_ctx* ctx, const mpsk_tensor* A1, const mpsk_tensor* A2, mpsk_tensor** out) {
   Tensor* o = nullptr;

@@ -425,3 +425,112 @@ def test_row_panel_sharding_single_gpu_emulation(ctx, nranks):
     assert relerr(y.to_dense(), yfull) <= 1e-13
     assert relerr(y.to_dense(), oc.dAC2_blocks(x, h, h, GL, GR).to_dense()) <= 1e-12
     assert abs(flops - full.flops) <= 1e-9 * full.flops            # no redundant work
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# infinite-MPS rows (8f item 2) and operator algebra (a6)
+def test_uniform_gauge_and_transfer_fixed_points(ctx):
+    """test/states.jl:49-72: AC = AL*C = C*AR and l * TransferMatrix(AL, AL) = l, TransferMatrix(AR, AR) * r = r."""
+    from oracle import infinite as oi
+    rng = np.random.default_rng(111)
+    p = m.Space((-1, 0, 1), (1, 1, 1))                     # spin-1, U(1)
+    Vs = [m.Space((-1, 0, 1), (5, 8, 5)), m.Space((-1, 0, 1), (6, 7, 6))]
+    psi = m.InfiniteMPS.random(rng, p, Vs, ctx)
+    for i in range(2):
+        AL, AR, AC = psi.AL[i].to_dense(), psi.AR[i].to_dense(), psi.AC[i].to_dense()
+        Cr, Cl = psi.CR[i].to_dense()[:, 0, :], psi.CR[i - 1].to_dense()[:, 0, :]
+        assert relerr(np.einsum('apb,bc->apc', AL, Cr), AC) <= 1e-11
+        assert relerr(np.einsum('ab,bpc->apc', Cl, AR), AC) <= 1e-11
+        M = AL.reshape(-1, AL.shape[2]); assert np.abs(M.conj().T @ M - np.eye(M.shape[1])).max() <= 1e-12
+    from mpskit_b200.infinite import identity_bond, mul_right_bond
+    l = identity_bond(ctx, psi.V[0], psi.dtype)
+    out = l * m.TransferMatrix(psi.AL, None, psi.AL)                 # v * tm (transfermatrix.jl:44)
+    assert relerr(out.to_dense(), l.to_dense()) <= 1e-12
+    r = mul_right_bond(psi.CR[1], psi.CR[1].adjoint())               # r_LL = C C'
+    out = m.TransferMatrix(psi.AL, None, psi.AL) * r
+    assert relerr(out.to_dense(), r.to_dense()) <= 1e-10
+
+
+def test_vumps_tfi_reference_logged_energy(ctx):
+    """docs/src/examples/quantum1d/3.ising-dqpt/index.md:107-118: VUMPS, TFI g=-0.5, D=10 -> E = -1.063544409973
+    (logged by the reference itself, 7 iterations); device VUMPS vs that number and vs the oracle VUMPS."""
+    from oracle import infinite as oi
+    Ho = ompo.transverse_field_ising(1, 0.5)
+    psi_o = oi.InfiniteMPS.random(np.random.default_rng(3), OSpace((0,), (2,)), [OSpace((0,), (10,))])
+    log_o = []
+    oi.vumps(psi_o, Ho, tol=1e-12, maxiter=30, log=log_o)
+    psi_d = m.InfiniteMPS.random(np.random.default_rng(3), m.Space((0,), (2,)), [m.Space((0,), (10,))], ctx)
+    log_d = []
+    psi_d, envs, eps = m.find_groundstate_vumps(psi_d, dev_hamiltonian(Ho), m.VUMPS(tol=1e-12, maxiter=30), log=log_d)
+    print("VUMPS", log_d[-1], log_o[-1], len(log_d), len(log_o))
+    assert eps <= 1e-11
+    assert abs(log_d[-1]["energy"] - (-1.063544409973)) <= 2e-11
+    assert abs(log_d[-1]["energy"] - log_o[-1]["energy"]) <= 1e-10
+
+
+def test_vumps_two_site_unit_cell_u1(ctx):
+    """spin-1/2 Heisenberg, 2-site unit cell with U(1) symmetry (config 2 style): device vs oracle energy density."""
+    from oracle import infinite as oi
+    Ho = ompo.heisenberg_u1(2)
+    Vo = [OSpace((-2, 0, 2), (3, 6, 3)), OSpace((-3, -1, 1, 3), (1, 5, 5, 1))]
+    psi_o = oi.InfiniteMPS.random(np.random.default_rng(5), OSpace((-1, 1), (1, 1)), Vo)
+    log_o = []
+    oi.vumps(psi_o, Ho, tol=1e-8, maxiter=6, log=log_o)
+    psi_d = m.InfiniteMPS.random(np.random.default_rng(5), m.Space((-1, 1), (1, 1)), [to_dev_space(v) for v in Vo], ctx)
+    log_d = []
+    m.find_groundstate_vumps(psi_d, dev_hamiltonian(Ho), m.VUMPS(tol=1e-8, maxiter=6), log=log_d)
+    print("VUMPS U1", log_d[-1], log_o[-1])
+    assert abs(log_d[-1]["energy"] - log_o[-1]["energy"]) <= 1e-7 * abs(log_o[-1]["energy"])
+    assert abs(log_d[-1]["energy"] / 2 - (0.25 - np.log(2))) < 5e-3       # Bethe ansatz, D = 12, 6 iterations
+
+
+def test_derivative_linearity_lazysum(ctx):
+    """test/operators.jl:207-225: the derivative of a LazySum equals the sum of the derivatives."""
+    H = ompo.heisenberg_u1(4)
+    h = H[0]
+    x, GL, GR = random_problem(121, h, VBIG_L, VBIG_R, "ac")
+    _, GL2, GR2 = random_problem(122, h, VBIG_L, VBIG_R, "ac")
+    hs = dev_slice(h)
+    dx = dev_tensor(ctx, x)
+    t = [dev_tensor(ctx, v) for v in (GL, GR, GL2, GR2)]
+    op1 = m.MPO_ddAC(ctx, hs, t[0], t[1], dx)
+    op2 = m.MPO_ddAC(ctx, hs, t[2], t[3], dx)
+    ysum = m.LazySumOp([op1, m.MultipliedOp(op2, 0.5 - 2j)])(dx).to_dense()
+    ref = oc.dAC_sparse(x.to_dense(), h, GL.to_dense(), GR.to_dense()) + (0.5 - 2j) * oc.dAC_sparse(x.to_dense(), h, GL2.to_dense(), GR2.to_dense())
+    assert relerr(ysum, ref) <= 1e-12
+
+
+@pytest.mark.parametrize("trunc", [("notrunc",), ("truncdim", 20), ("truncerr", 0.3)])
+def test_tsvd_gram_route(trunc):
+    """the GEMM-rich SVD route used for large sectors (G = W^H W, heevd, B = W V, QR clean-up), forced on every sector:
+    singular values, truncation decisions and the reconstruction against the oracle; exact isometries."""
+    from mpskit_b200 import _lib
+    c = m.Context(0, 4)                      # MPSK_FLAG_FAST_SVD_ALL
+    rng = np.random.default_rng(51)
+    d = 2
+    pch = [-1, 1]
+    mch = [pch[a] + pch[b] for a in range(d) for b in range(d)]
+    Vl, Vr = OSpace((-2, 0, 2), (60, 90, 40)), OSpace((-2, 0, 2, 4), (50, 110, 70, 20))
+    x = BlockTensor.random(rng, Vl, mch, Vr)
+    xd = x2_dense(x, d)
+    rowq = (Vl.index_charges()[:, None] + np.array(pch)[None, :]).reshape(-1)
+    colq = (Vr.index_charges()[:, None] - np.array(pch)[None, :]).reshape(-1)
+    U, S, Vh, newV, eps, info = ol.tsvd(xd.reshape(Vl.dim * d, Vr.dim * d), rowq, colq, trunc)
+
+    class P:
+        pass
+    P.ctx, P.pq, P.pspace = c, tuple(pch), m.Space((-1, 1), (1, 1))
+    code = m.notrunc() if trunc[0] == "notrunc" else getattr(m, trunc[0])(trunc[1])
+    al, cc, ar, eps_d = m.tsvd(P, dev_tensor(c, x), code)
+    assert (al.Vr.charges, al.Vr.dims) == (newV.charges, newV.dims)
+    assert abs(eps_d - eps) <= 1e-8
+    spec = m.tsvd_spectrum(c)
+    for q, s in info["spectrum"].items():
+        assert np.abs(spec[q][0] - s).max() <= 1e-8
+    rec = np.einsum('apk,kl,lqr->aprq', al.to_dense(), cc.to_dense()[:, 0, :], ar.to_dense())
+    ref = np.einsum('ik,k,kj->ij', U, S / np.linalg.norm(S), Vh).reshape(Vl.dim, d, Vr.dim, d)
+    assert relerr(rec, ref) <= 1e-10
+    A = al.to_dense().reshape(-1, al.Vr.dim)
+    assert np.abs(A.conj().T @ A - np.eye(A.shape[1])).max() <= 1e-12
+    B = ar.to_dense().reshape(ar.Vl.dim, -1)
+    assert np.abs(B @ B.conj().T - np.eye(B.shape[0])).max() <= 1e-12

@@ -169,3 +169,46 @@ def test_golden_vectors_are_reproduced():
     assert np.abs(oc.transfer_left_sparse(g["GL"], h, g["A"], g["Ab"]) - g["tl"]).max() <= 1e-13 * np.abs(g["tl"]).max()
     d = np.load(os.path.join(GOLD, "dmrg2_heisenberg_u1_L8_D16.npz"))
     assert abs(d["energy"][-1] - (-3.3749325986878906)) < 1e-12
+
+
+def test_reference_logged_vumps_energy():
+    """docs/src/examples/quantum1d/3.ising-dqpt/index.md:107-118: VUMPS TFI g=-0.5 D=10: E = -1.063544409973 in 7
+    iterations (logged by the reference itself); also the exact infinite-chain energy density."""
+    from oracle import infinite as oi
+    H = ompo.transverse_field_ising(1, 0.5)
+    psi = oi.InfiniteMPS.random(np.random.default_rng(3), Space((0,), (2,)), [Space((0,), (10,))])
+    log = []
+    psi, envs, eps = oi.vumps(psi, H, tol=1e-12, maxiter=30, log=log)
+    assert abs(log[-1]["energy"] - (-1.063544409973)) < 2e-12 and len(log) <= 10
+    import scipy.integrate as si
+    g = 0.5
+    exact = -si.quad(lambda k: np.sqrt(1 + g * g + 2 * g * np.cos(k)), 0, np.pi)[0] / np.pi
+    assert abs(log[-1]["energy"] - exact) < 1e-8
+
+
+def test_host_krylov_on_numpy_vectors():
+    """mpskit_b200/krylov.py (host-driven Arnoldi / Lanczos / GMRES over the VectorInterface) on a numpy-backed vector"""
+    from mpskit_b200 import krylov
+
+    class Vec:
+        def __init__(self, a): self.a = np.array(a, dtype=complex)
+        def copy(self): return Vec(self.a.copy())
+        def zerovector(self): return Vec(np.zeros_like(self.a))
+        def dot(self, o): return np.vdot(self.a, o.a)
+        def norm(self): return float(np.linalg.norm(self.a))
+        def axpy(self, c, x): self.a = self.a + c * x.a; return self
+        def scale(self, c): self.a = self.a * c; return self
+    rng = np.random.default_rng(2)
+    n = 50
+    B = rng.standard_normal((n, n)) * 0.1 + 0.05j * rng.standard_normal((n, n))
+    x0 = Vec(rng.standard_normal(n))
+    lam, v, info = krylov.eigsolve_arnoldi(lambda u: Vec(B @ u.a), x0, "LM", 1e-10, 30, 200)
+    assert info["converged"] and abs(abs(lam) - np.abs(np.linalg.eigvals(B)).max()) < 1e-8
+    A = B + B.conj().T
+    lam, v, info = krylov.eigsolve_lanczos(lambda u: Vec(A @ u.a), x0, "SR", 1e-11, 30, 200)
+    assert abs(lam - np.linalg.eigvalsh(A)[0]) < 1e-9
+    b = Vec(rng.standard_normal(n))
+    xs, info = krylov.linsolve_gmres(lambda u: Vec(B @ u.a), b, Vec(np.zeros(n)), 1.0, -1.0, 1e-12, 30, 100)
+    assert np.abs((np.eye(n) - B) @ xs.a - b.a).max() < 1e-9
+    rv = krylov.RecursiveVec([Vec([1, 2]), Vec([3j])])
+    assert abs(rv.norm() - np.sqrt(14)) < 1e-14 and abs(rv.dot(rv) - 14) < 1e-14
