@@ -33,6 +33,7 @@ def parse():
     ap.add_argument("--range", type=int, default=6, dest="r")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sweep-steps", type=int, default=3, help="DMRG2 centre steps timed for the sweep estimate (0: skip)")
     return ap.parse_args()
 
 
@@ -297,6 +298,13 @@ def main():
         except MemoryError:
             cpu = None
 
+    sweep = None
+    if rank == 0 and world == 1 and args.sweep_steps > 0:
+        for t in (w.get("op"), w.get("GL"), w.get("GR")):
+            if t is not None:
+                t.free()
+        sweep = sweep_window(ctx, m, args.D, args.r, args.sweep_steps)
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "c128",
@@ -304,10 +312,51 @@ def main():
                 "config": {"workload": workload_name(args.D, args.r), "D": args.D, "chi": 2 + 3 * args.r, "flops_per_matvec": flops,
                            "l2": "inputs larger than L2 (x 192 MB, environments 2 x 0.97 GB, intermediates 7.6 GB)",
                            "parallelism": "single GPU" if world == 1 else f"{world} GPUs: row panels of the bra index, GL sharded, 1 NCCL allgather of y per matvec"},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "dmrg2_sweep": sweep}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def sweep_window(ctx, m, D, r, nsteps):
+    """DMRG2 sweep-time estimate: `nsteps` consecutive two-site updates at the centre of an L=36 chain of the same
+    recipe (full bond dimension D there), each = ac2 build + environment update + Lanczos eigsolve (krylovdim 15, one
+    cycle) + truncated SVD + state update; extrapolated to the 197 updates of a full L=100 sweep by the measured
+    full-sweep profile (profiles/r01_full_sweep_D4096*.json: 150 of 197 updates run at full D)."""
+    import warnings
+    import numpy as np
+    from mpskit_b200.workloads import gaussian_bond_space
+    from mpskit_b200 import dmrg as dm
+    L = 36
+    p = m.Space((-1, 1), (1, 1))
+    H = m.heisenberg_longrange_u1(L, r=r)
+    psi = m.FiniteMPS.random(20240213 + 3000, p, L, [gaussian_bond_space(D, k % 2) for k in range(1, L)], ctx, on_device=True)
+    envs = m.environments(psi, H)
+    alg = m.Lanczos(tol=1e-10, krylovdim=15, maxiter=1)
+    pos0 = L // 2 - nsteps // 2
+    envs.leftenv(pos0, psi); envs.rightenv(pos0 + 1, psi)
+    # one untimed step absorbs cuSOLVER / allocator warm-up
+    times, matvecs = [], 0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for step in range(nsteps + 1):
+            pos = pos0 - 1 + step
+            ctx.synchronize(); t0 = time.perf_counter()
+            ac2 = dm.contract_ac2(psi, psi.AC[pos], psi.AR[pos + 1])
+            h = m.ddAC2(pos, psi, H, envs, ac2)
+            val, new, info = m.fixedpoint(h, ac2, "SR", alg, return_info=True)
+            h.free()
+            al, c, ar, eps = dm.tsvd(psi, new, m.truncdim(D))
+            psi.AC[pos] = (al, c); psi.AC[pos + 1] = (c, ar)
+            ac2.free(); new.free(); envs.drop_stale(psi)
+            ctx.synchronize()
+            if step > 0:
+                times.append(time.perf_counter() - t0); matvecs += info["numops"]
+    per = float(np.mean(times))
+    return {"seconds_per_centre_update": per, "matvecs_per_update": matvecs / len(times), "timed_updates": len(times),
+            "estimated_sweep_seconds_L100": per * 150 + 0.06 * per * 47,
+            "note": "estimate = 150 full-D updates + 47 edge updates (~6 % of a centre update each, from the measured full sweep); "
+                    "measured full sweeps are in profiles/"}
 
 
 def gemm_only_ms(ctx, op, x, y, stream, torch, reps):

@@ -7,7 +7,7 @@ from ._lib import (Context, default_context, MpskError, SpaceMismatch, load as l
 from .spaces import Space, fuse, infimum, dual  # noqa: F401
 from .tensor import DeviceTensor, block_table  # noqa: F401
 from .operators import (SparseMPOSlice, MPOHamiltonian, transverse_field_ising, heisenberg_u1,  # noqa: F401
-                        heisenberg_longrange_u1, drop_symmetry)
+                        heisenberg_longrange_u1, drop_symmetry, DenseMPO, dense_mpo_slice, classical_ising)
 from .derivatives import (MPO_ddC, MPO_ddAC, MPO_ddAC2, ddC, ddAC, ddAC2, LazySumOp, MultipliedOp,  # noqa: F401
                           LinearCombinationOp)
 from .krylov import RecursiveVec, eigsolve_arnoldi, linsolve_gmres  # noqa: F401
@@ -22,3 +22,5 @@ from .sharding import panel_bounds, panel_table, panel_space, row_panel, scatter
 from .infinite import (InfiniteMPS, TransferMatrix, regularize, MPOHamInfEnv, VUMPS, find_groundstate_vumps,  # noqa: F401
                        uniform_leftorth, uniform_rightorth, regauge)
 from . import infinite  # noqa: F401
+from .statmech import PerMPOInfEnv, leading_boundary  # noqa: F401
+from . import statmech  # noqa: F401

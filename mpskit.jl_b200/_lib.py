@@ -133,6 +133,7 @@ class Context:
             raise MpskError(st, "mpsk_create failed")
         self.h = h
         self.device = device
+        self.rank, self.nranks = 0, 1            # set by sharding.init_communicator
 
     def check(self, st):
         if st != OK:

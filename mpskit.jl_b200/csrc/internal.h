@@ -49,6 +49,9 @@ struct Ctx {
   std::unordered_map<void*, size_t> sizes;
   int64_t bytes_in_use = 0, bytes_cached = 0;
   void* cusolver = nullptr;     // cusolverDnHandle_t, created lazily
+  void* pool_stream[4] = {nullptr, nullptr, nullptr, nullptr};   // worker streams / cuSOLVER handles of the factorisation pool
+  void* pool_solver[4] = {nullptr, nullptr, nullptr, nullptr};
+  int* pool_info[4] = {nullptr, nullptr, nullptr, nullptr};
   void* nccl = nullptr;         // ncclComm_t
   int rank = 0, nranks = 1;
   double* h_scratch = nullptr;  // pinned host scratch (scalars coming back from Krylov kernels)

@@ -232,6 +232,15 @@ int tsvd(Ctx* ctx, const Tensor* x, int d1, const int32_t* p1ch, mpsk_trunc trun
       CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     }
     const int dev = ctx->device;
+    for (int t = 0; t < nthreads; ++t) {     // persistent per-worker stream + cuSOLVER handle (creation costs milliseconds)
+      if (ctx->pool_solver[t]) continue;
+      cudaStream_t st; cusolverDnHandle_t hs; int* di = nullptr;
+      CUDA_TRY(ctx, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+      CUSOLVER_TRY(ctx, cusolverDnCreate(&hs));
+      CUSOLVER_TRY(ctx, cusolverDnSetStream(hs, st));
+      CUDA_TRY(ctx, cudaMalloc(&di, sizeof(int)));
+      ctx->pool_stream[t] = st; ctx->pool_solver[t] = hs; ctx->pool_info[t] = di;
+    }
     std::vector<int> status(nthreads, 0);
     std::vector<std::string> errs(nthreads);
     // phase: 0 = gesvd (slow sectors) + heevd (fast sectors); 1 = QR re-orthonormalisation of U (fast sectors)
@@ -239,11 +248,8 @@ int tsvd(Ctx* ctx, const Tensor* x, int d1, const int32_t* p1ch, mpsk_trunc trun
       std::atomic<int> next(0);
       auto worker = [&](int tid) {
         cudaSetDevice(dev);
-        cudaStream_t st; cusolverDnHandle_t hs;
-        if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { status[tid] = MPSK_ECUDA; errs[tid] = "stream create"; return; }
-        if (cusolverDnCreate(&hs) != CUSOLVER_STATUS_SUCCESS) { status[tid] = MPSK_ECUDA; errs[tid] = "cusolverDnCreate"; cudaStreamDestroy(st); return; }
-        cusolverDnSetStream(hs, st);
-        int* d_info = nullptr; cudaMalloc(&d_info, sizeof(int));
+        cudaStream_t st = (cudaStream_t)ctx->pool_stream[tid]; cusolverDnHandle_t hs = (cusolverDnHandle_t)ctx->pool_solver[tid];
+        int* d_info = ctx->pool_info[tid];
         for (;;) {
           const int oi = next.fetch_add(1);
           if (oi >= (int)order.size()) break;
@@ -283,8 +289,6 @@ int tsvd(Ctx* ctx, const Tensor* x, int d1, const int32_t* p1ch, mpsk_trunc trun
             break;
           }
         }
-        cudaFree(d_info);
-        cusolverDnDestroy(hs); cudaStreamDestroy(st);
       };
       std::vector<std::thread> th;
       for (int t = 0; t < nthreads; ++t) th.emplace_back(worker, t);

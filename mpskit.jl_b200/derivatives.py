@@ -14,8 +14,14 @@ class DerivativeOperator:
 
     def __init__(self, ctx, h1, h2, leftenv, rightenv, x_like):
         self.ctx = ctx
-        self.leftenv, self.rightenv = leftenv, rightenv
         self.o1, self.o2 = h1, h2
+        if getattr(ctx, "nranks", 1) > 1 and leftenv.Vl == x_like.Vl:
+            # multi-GPU: this rank applies the row panel of the operator that belongs to its rows of the bra index;
+            # apply / eigsolve / expv allgather the panels of y inside the library (sharding.py)
+            h = C.c_void_p()
+            ctx.check(ctx.lib.mpsk_tensor_row_panel(ctx.h, leftenv.h, ctx.rank, ctx.nranks, C.byref(h)))
+            leftenv = DeviceTensor.wrap(ctx, h, leftenv.Vl.modulus)
+        self.leftenv, self.rightenv = leftenv, rightenv
         op = C.c_void_p()
         ctx.check(ctx.lib.mpsk_op_create(ctx.h, self.kind,
                                          h1.device(ctx) if h1 is not None else None,

@@ -151,3 +151,43 @@ def heisenberg_longrange_u1(L, r=6, d=2, power=2.0):
 def drop_symmetry(H: MPOHamiltonian):
     """same operator with all charges set to zero (trivial-symmetry / dense path)."""
     return MPOHamiltonian([SparseMPOSlice(s.Os, (0,) * s.odim, (0,) * s.odim, (0,) * s.d) for s in H.slices])
+
+
+# --------------------------------------------------------------------------------------- dense MPOs (classic2d)
+def dense_mpo_slice(O, level_charges=None, phys_charges=None):
+    """DenseMPO tensor O[wl, p_out, p_in, wr] flattened into width-1 levels (chi x chi slice of d x d operator entries)."""
+    O = np.asarray(O)
+    chi, d = O.shape[0], O.shape[1]
+    Os = [[0 for _ in range(chi)] for _ in range(chi)]
+    for i in range(chi):
+        for j in range(chi):
+            blk = np.asarray(O[i, :, :, j], dtype=np.complex128)
+            if np.abs(blk).max() > 0:
+                Os[i][j] = blk
+    lc = tuple(level_charges) if level_charges is not None else (0,) * chi
+    return SparseMPOSlice(Os, lc, lc, tuple(phys_charges) if phys_charges is not None else (0,) * d)
+
+
+def classical_ising(beta=None):
+    """test/setup.jl:78-94: 2D classical Ising transfer MPO at beta_c (default), O[wl, p_out, p_in, wr]."""
+    beta = np.log(1 + np.sqrt(2)) / 2 if beta is None else beta
+    t = np.array([[np.exp(beta), np.exp(-beta)], [np.exp(-beta), np.exp(beta)]])
+    w, v = np.linalg.eigh(t)
+    nt = v @ np.diag(np.sqrt(w)) @ v.T
+    delta = np.zeros((2, 2, 2, 2))
+    delta[0, 0, 0, 0] = delta[1, 1, 1, 1] = 1
+    return np.einsum('abcd,ia,jb,kc,ld->ijkl', delta, nt, nt, nt, nt)
+
+
+class DenseMPO:
+    """src/operators/densempo.jl: periodic list of dense MPO tensors, stored as flattened slices."""
+
+    def __init__(self, tensors, level_charges=None, phys_charges=None):
+        self.slices = [t if isinstance(t, SparseMPOSlice) else dense_mpo_slice(t, level_charges, phys_charges) for t in tensors]
+        self.odim = self.slices[0].odim
+
+    def __len__(self):
+        return len(self.slices)
+
+    def __getitem__(self, i):
+        return self.slices[i % len(self.slices)]

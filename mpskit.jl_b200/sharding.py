@@ -66,3 +66,4 @@ def init_communicator(ctx, rank, nranks, broadcast):
     uid = broadcast(uid)
     buf = (C.c_uint8 * 128)(*uid)
     ctx.check(ctx.lib.mpsk_comm_init(ctx.h, buf, rank, nranks))
+    ctx.rank, ctx.nranks = rank, nranks      # derivative operators built on this context now shard their matvec

@@ -186,3 +186,31 @@ def dense_hamiltonian(H: MPOHamiltonian):
             s = cur.shape
             cur = cur.reshape(s[0] * s[1], s[2] * s[3], s[4])
     return cur[:, :, -1]
+
+
+# ----------------------------------------------------------------------------- dense MPOs (classic2d)
+def dense_mpo_slice(O, level_charges=None, phys_charges=None):
+    """flatten a DenseMPO tensor O[wl, p_out, p_in, wr] (src/operators/densempo.jl) into width-1 levels: a chi x chi
+    SparseMPOSlice whose entries are the d x d operators O[i, :, :, j] (entries that vanish identically are absent)."""
+    chi, d = O.shape[0], O.shape[1]
+    Os = [[0 for _ in range(chi)] for _ in range(chi)]
+    for i in range(chi):
+        for j in range(chi):
+            blk = np.asarray(O[i, :, :, j], dtype=np.complex128)
+            if np.abs(blk).max() > 0:
+                Os[i][j] = blk
+    lc = level_charges if level_charges is not None else (0,) * chi
+    return SparseMPOSlice(Os, lc, lc, phys_charges if phys_charges is not None else (0,) * d)
+
+
+def classical_ising(beta=None):
+    """test/setup.jl:78-94: the 2D classical Ising transfer MPO at beta_c = log(1 + sqrt 2) / 2, O[wl, p_out; p_in, wr]
+    with the reference's leg order (all four legs of dimension 2)."""
+    beta = np.log(1 + np.sqrt(2)) / 2 if beta is None else beta
+    t = np.array([[np.exp(beta), np.exp(-beta)], [np.exp(-beta), np.exp(beta)]])
+    w, v = np.linalg.eigh(t)
+    nt = v @ np.diag(np.sqrt(w)) @ v.T          # test/setup.jl:78-83 uses r.vectors * sqrt(D) * r.vectors (symmetric square root)
+    delta = np.zeros((2, 2, 2, 2))
+    delta[0, 0, 0, 0] = delta[1, 1, 1, 1] = 1
+    o = np.einsum('abcd,ia,jb,kc,ld->ijkl', delta, nt, nt, nt, nt)
+    return o      # legs (1,2;3,4) of the TensorMap: here read as O[wl, p_out, p_in, wr]

@@ -1,0 +1,103 @@
+"""Statistical-mechanics VUMPS for a single-row unit cell (leading_boundary of an InfiniteMPS with a DenseMPO):
+src/algorithms/statmech/vumps.jl:15-84, src/environments/permpoinfenv.jl:23-63,138-189 (mixed_fixpoints),
+src/algorithms/expval.jl:165-173.  Dense restatement; the MPO is given as a list of flattened slices (oracle/mpo.py
+dense_mpo_slice).  Multi-row unit cells (MPSMultiline with more than one row) are not covered."""
+from __future__ import annotations
+import numpy as np
+from .infinite import InfiniteMPS, regauge, dyn_tol, TOLGAUGE
+from .krylov import eigsolve_arnoldi
+from .contract import transfer_left_sparse, transfer_right_sparse, dAC_sparse, dC_dense
+
+
+class PerMPOInfEnv:
+    def __init__(self, psi: InfiniteMPS, slices, tol=1e-12):
+        self.opp, self.tol = slices, tol
+        self.lw = self.rw = None
+        self.dependency = None
+        self.recalculate(psi)
+
+    def recalculate(self, psi, tol=None):
+        tol = self.tol if tol is None else tol
+        N = psi.N
+        chi = self.opp[0].odim
+        D0 = psi.AL[0].shape[0]
+        rng = np.random.default_rng(0)
+        L0 = self.lw[0] if self.lw is not None and self.lw[0].shape[0] == D0 else rng.standard_normal((D0, chi, D0)) + 0j
+        R0 = self.rw[N - 1] if self.rw is not None and self.rw[N - 1].shape[0] == D0 else rng.standard_normal((D0, chi, D0)) + 0j
+
+        def TL(v):
+            for i in range(N):
+                v = transfer_left_sparse(v, self.opp[i], psi.AL[i], psi.AL[i])
+            return v
+
+        def TR(v):
+            for i in range(N - 1, -1, -1):
+                v = transfer_right_sparse(v, self.opp[i], psi.AR[i], psi.AR[i])
+            return v
+        GL = [None] * N
+        GR = [None] * N
+        _, GL[0], _ = eigsolve_arnoldi(TL, L0, "LM", tol, 30, 100)
+        for c in range(1, N):
+            GL[c] = transfer_left_sparse(GL[c - 1], self.opp[c - 1], psi.AL[c - 1], psi.AL[c - 1])
+        _, GR[N - 1], _ = eigsolve_arnoldi(TR, R0, "LM", tol, 30, 100)
+        for c in range(N - 2, -1, -1):
+            GR[c] = transfer_right_sparse(GR[c + 1], self.opp[c + 1], psi.AR[c + 1], psi.AR[c + 1])
+        for c in range(N):                      # permpoinfenv.jl:180-185
+            lam = np.vdot(psi.CR[c], dC_dense(psi.CR[c], GL[(c + 1) % N], GR[c]))
+            # the reference divides both by sqrt(|lam|); the Arnoldi eigenvectors carry an arbitrary phase, which we
+            # remove here as well (lam -> real positive) so that read-outs are gauge independent
+            GL[(c + 1) % N] = GL[(c + 1) % N] * (np.conj(lam) / abs(lam)) / np.sqrt(abs(lam))
+            GR[c] = GR[c] / np.sqrt(abs(lam))
+        self.lw, self.rw, self.dependency = GL, GR, psi
+        return self
+
+    def leftenv(self, pos, psi):
+        if self.dependency is not psi:
+            self.recalculate(psi)
+        return self.lw[pos % psi.N]
+
+    def rightenv(self, pos, psi):
+        if self.dependency is not psi:
+            self.recalculate(psi)
+        return self.rw[pos % psi.N]
+
+
+def expectation_value(psi, envs):
+    """expval.jl:165-173"""
+    out = []
+    for i in range(psi.N):
+        y = dAC_sparse(psi.AC[i], envs.opp[i], envs.leftenv(i, psi), envs.rightenv(i, psi))
+        out.append(np.vdot(psi.AC[i], y))
+    return np.array(out)
+
+
+def calc_galerkin(psi, loc, envs):
+    y = dAC_sparse(psi.AC[loc], envs.opp[loc], envs.leftenv(loc, psi), envs.rightenv(loc, psi))
+    y = y / np.linalg.norm(y)
+    AL = psi.AL[loc]
+    return float(np.linalg.norm(y - np.einsum('apb,cqb,cqd->apd', AL, np.conj(AL), y, optimize=True)))
+
+
+def leading_boundary(psi: InfiniteMPS, slices, tol=1e-10, maxiter=100, log=None):
+    """statmech/vumps.jl:20-84 for one row"""
+    envs = PerMPOInfEnv(psi, slices)
+    N = psi.N
+    eps = max(calc_galerkin(psi, i, envs) for i in range(N))
+    for it in range(1, maxiter + 1):
+        etol = dyn_tol(eps, it, 1e-12, 1e-5, 1e-5)
+        newAL = []
+        for col in range(N):
+            GL, GR = envs.leftenv(col, psi), envs.rightenv(col, psi)
+            _, ac, _ = eigsolve_arnoldi(lambda x: dAC_sparse(x, slices[col], GL, GR), psi.AC[col], "LM", etol, 30, 100)
+            GLc = envs.leftenv(col + 1, psi)
+            _, c, _ = eigsolve_arnoldi(lambda x: dC_dense(x, GLc, GR), psi.CR[col], "LM", etol, 30, 100)
+            newAL.append(regauge(ac, c, psi.V[col], psi.V[(col + 1) % N], psi.pq, psi.modulus))
+        gtol = dyn_tol(eps, it, TOLGAUGE, 1e-5, 1e-8)
+        psi = InfiniteMPS.from_AL(newAL, psi.CR[N - 1], psi.V, psi.pq, gtol, 100, psi.modulus)
+        envs.recalculate(psi, dyn_tol(eps, it, 1e-12, 1e-5, 1e-5))
+        eps = max(calc_galerkin(psi, i, envs) for i in range(N))
+        if log is not None:
+            log.append(dict(iter=it, eps=eps, value=expectation_value(psi, envs)))
+        if eps <= tol:
+            break
+    return psi, envs, eps

@@ -534,3 +534,22 @@ def test_tsvd_gram_route(trunc):
     assert np.abs(A.conj().T @ A - np.eye(A.shape[1])).max() <= 1e-12
     B = ar.to_dense().reshape(ar.Vl.dim, -1)
     assert np.abs(B @ B.conj().T - np.eye(B.shape[0])).max() <= 1e-12
+
+
+def test_leading_boundary_classical_ising(ctx):
+    """test/algorithms.jl:185-201: leading_boundary of the 2D classical Ising MPO at beta_c, expectation value 2.5337
+    (Onsager: 2.533737...), device statmech VUMPS vs the oracle and the known answer (config 4 style, D = 10)."""
+    from oracle import infinite as oi, statmech as osm
+    sl_o = ompo.dense_mpo_slice(ompo.classical_ising())
+    psi_o = oi.InfiniteMPS.random(np.random.default_rng(3), OSpace((0,), (2,)), [OSpace((0,), (10,))])
+    log_o = []
+    osm.leading_boundary(psi_o, [sl_o], tol=1e-6, maxiter=12, log=log_o)
+    mpo = m.DenseMPO([m.classical_ising()])
+    assert mpo[0].kinds() == sl_o.kinds()
+    psi_d = m.InfiniteMPS.random(np.random.default_rng(3), m.Space((0,), (2,)), [m.Space((0,), (10,))], ctx)
+    log_d = []
+    m.leading_boundary(psi_d, mpo, m.VUMPS(tol=1e-6, maxiter=12), log=log_d)
+    v_d, v_o = log_d[-1]["value"][0], log_o[-1]["value"][0]
+    print("classic2d", v_d, v_o, len(log_d), len(log_o))
+    assert abs(v_d - 2.5337) < 1e-3 and abs(v_d.imag) < 1e-9
+    assert abs(v_d - v_o) <= 1e-6 * abs(v_o)

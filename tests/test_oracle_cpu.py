@@ -212,3 +212,17 @@ def test_host_krylov_on_numpy_vectors():
     assert np.abs((np.eye(n) - B) @ xs.a - b.a).max() < 1e-9
     rv = krylov.RecursiveVec([Vec([1, 2]), Vec([3j])])
     assert abs(rv.norm() - np.sqrt(14)) < 1e-14 and abs(rv.dot(rv) - 14) < 1e-14
+
+
+def test_classical_ising_leading_boundary_known_answer():
+    """test/algorithms.jl:185-201: leading_boundary(classical_ising) expectation value 2.5337 (atol 1e-3);
+    Onsager: exp(2G/pi + ln2/2) = 2.533737..."""
+    from oracle import infinite as oi, statmech as osm
+    sl = ompo.dense_mpo_slice(ompo.classical_ising())
+    assert sl.odim == 2 and len(sl.keys()) == 4 and len(sl.scalkeys()) == 0
+    psi = oi.InfiniteMPS.random(np.random.default_rng(3), Space((0,), (2,)), [Space((0,), (10,))])
+    log = []
+    osm.leading_boundary(psi, [sl], tol=1e-7, maxiter=60, log=log)
+    v = log[-1]["value"][0]
+    assert abs(v - 2.5337) < 1e-3 and abs(v.imag) < 1e-10
+    assert abs(v - np.exp(2 * 0.915965594177219 / np.pi + np.log(2) / 2)) < 1e-5
