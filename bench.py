@@ -211,9 +211,8 @@ def main():
             dist.broadcast_object_list(box, src=0)
             return box[0]
         m.init_communicator(ctx, rank, world, bcast)
-        GLp = m.row_panel(w["GL"], rank, world)
+        op = m.MPO_ddAC2(ctx, w["h"], w["h"], w["GL"], w["GR"], x)    # row-panels GL for this rank (derivatives.py)
         w["GL"].free()
-        op = m.MPO_ddAC2(ctx, w["h"], w["h"], GLp, w["GR"], x)
         t = torch.tensor([op.flops], device="cuda", dtype=torch.float64)
         dist.all_reduce(t)
         flops = float(t.item())            # sum of the panel flops == flops of the full operator (no redundant work)

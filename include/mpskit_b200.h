@@ -48,6 +48,7 @@ enum { MPSK_SR = 0, MPSK_LM = 1, MPSK_LR = 2 };       /* `which` of fixedpoint (
 enum { MPSK_NOTRUNC = 0, MPSK_TRUNCDIM = 1, MPSK_TRUNCERR = 2, MPSK_TRUNCBELOW = 3 }; /* TensorKit truncation schemes used at dmrg.jl:75,96 */
 #define MPSK_TRUNC_NO_NORMALIZE 0x100   /* OR into mpsk_trunc.kind: skip normalize!(c) (TDVP2, tdvp.jl:124-126) */
 enum { MPSK_OP_DC = 0, MPSK_OP_DAC = 1, MPSK_OP_DAC2 = 2 };
+#define MPSK_OP_SHARDED 0x100   /* OR into `kind`: GL is this rank's row panel; apply/eigsolve/expv allgather the panels of y */
 
 #define MPSK_FLAG_EXACT_SVD 2ull      /* tsvd: cuSOLVER gesvd for every sector (default: Gram + heevd + QR route for sectors >= 256) */
 #define MPSK_FLAG_FAST_SVD_ALL 4ull   /* tsvd: Gram route for every sector (tests) */

@@ -78,8 +78,12 @@ int heff_create(Ctx* ctx, int kind, const MpoSlice* h1, const MpoSlice* h2, cons
   const int nlev = GL->nm();
   if (h1 && h1->odim != nlev) return ctx->fail(MPSK_ESPACE, "MPO slice odim %d != environment levels %d", h1->odim, nlev);
   std::unique_ptr<HeffOp> op(new HeffOp);
+  // sharded: GL is this rank's row panel and apply must allgather the panels -- an explicit flag, because on small spaces
+  // a rank's panel can coincide with the full space (or be empty) and every rank has to take the same collective path
+  const bool sharded = (kind & MPSK_OP_SHARDED) != 0;
+  kind &= 0xff;
   op->ctx = ctx; op->kind = kind; op->dtype = x_like->dtype;
-  op->rectangular = !(GL->Vl == x_like->Vl);
+  op->rectangular = sharded;
   const bool cx = op->dtype == MPSK_C128;
   MPSK_TRY(build_W(ctx, kind, h1, h2, x_like, nlev, &op->W));
   const Space& Vl = x_like->Vl;      // ket (contracted) left bond

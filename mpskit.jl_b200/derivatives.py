@@ -15,7 +15,9 @@ class DerivativeOperator:
     def __init__(self, ctx, h1, h2, leftenv, rightenv, x_like):
         self.ctx = ctx
         self.o1, self.o2 = h1, h2
+        kind = self.kind
         if getattr(ctx, "nranks", 1) > 1 and leftenv.Vl == x_like.Vl:
+            kind |= 0x100                      # MPSK_OP_SHARDED
             # multi-GPU: this rank applies the row panel of the operator that belongs to its rows of the bra index;
             # apply / eigsolve / expv allgather the panels of y inside the library (sharding.py)
             h = C.c_void_p()
@@ -23,7 +25,7 @@ class DerivativeOperator:
             leftenv = DeviceTensor.wrap(ctx, h, leftenv.Vl.modulus)
         self.leftenv, self.rightenv = leftenv, rightenv
         op = C.c_void_p()
-        ctx.check(ctx.lib.mpsk_op_create(ctx.h, self.kind,
+        ctx.check(ctx.lib.mpsk_op_create(ctx.h, kind,
                                          h1.device(ctx) if h1 is not None else None,
                                          h2.device(ctx) if h2 is not None else None,
                                          leftenv.h, rightenv.h, x_like.h, C.byref(op)))

@@ -7,7 +7,6 @@ from . import _lib
 from ._lib import default_context
 from .spaces import Space, fuse, infimum, dual
 from .tensor import DeviceTensor
-from ._hostlinalg import qrpos, lqpos
 import ctypes as C
 
 

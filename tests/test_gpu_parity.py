@@ -417,7 +417,7 @@ def test_row_panel_sharding_single_gpu_emulation(ctx, nranks):
     for r in range(nranks):
         GLp = m.row_panel(dGL, r, nranks)
         assert GLp.Vl == m.panel_space(dGL.Vl, r, nranks)           # host mirror of the integer rule: bit-exact
-        op = m.MPO_ddAC2(ctx, hs, hs, GLp, dGR, dx)
+        op = m.MPO_ddAC2(ctx, hs, hs, GLp, dGR, dx)        # a panel operator; applied locally (no communicator here)
         yp = m.DeviceTensor.zeros(ctx, GLp.Vl, dx.mch, dx.Vr)
         m.apply_local(op, dx, yp)
         m.scatter_panel(yp, r, nranks, y)
