@@ -286,18 +286,80 @@ template <bool CPLX> static int smem_bytes() {
 GemmPlan::~GemmPlan() {
   if (d_probs) ctx->free(d_probs);
   if (d_tiles) ctx->free(d_tiles);
+  if (partials) ctx->free(partials);
+  delete reduce;
 }
 
 // Build the device problem table (with TMA descriptors) and the tile list.
-int gemm_plan_build(Ctx* ctx, bool cplx, const std::vector<GemmProblemHost>& probs, GemmPlan* plan) {
+// Split-K: when the whole plan has fewer tiles than ~4 waves of the 148 persistent CTAs (small bond dimensions, or a
+// row panel of a sharded matvec: e.g. 175 tiles of K ~ 18000 at 8 GPUs), long-K problems are cut into K-slices.
+// Slice 0 writes C as before; slices s >= 1 write partial products to a scratch buffer that one streaming pass
+// (the mix kernel, C += sum_s P_s) folds back.  Deterministic: no atomics, fixed summation order.
+int gemm_plan_build(Ctx* ctx, bool cplx, const std::vector<GemmProblemHost>& probs_in, GemmPlan* plan) {
   plan->ctx = ctx; plan->cplx = cplx; plan->nprob = 0; plan->ntiles = 0; plan->flops = 0;
   const int BM = cplx ? GemmCfg<true>::BM : GemmCfg<false>::BM;
   const int BN = cplx ? GemmCfg<true>::BN : GemmCfg<false>::BN;
+  const int KSTAGE = cplx ? GemmCfg<true>::KSUB * GemmCfg<true>::NSUB : GemmCfg<false>::KSUB * GemmCfg<false>::NSUB;
+  const size_t esz = cplx ? 16 : 8;
+  // ---- split-K decision
+  int64_t base_tiles = 0; int64_t maxK = 0;
+  for (const GemmProblemHost& h : probs_in) {
+    if (h.M <= 0 || h.N <= 0) continue;
+    base_tiles += (int64_t)((h.M + BM - 1) / BM) * ((h.N + BN - 1) / BN);
+    maxK = std::max<int64_t>(maxK, h.K);
+    plan->flops += (cplx ? 8.0 : 2.0) * (double)h.M * h.N * h.K;
+  }
+  const int64_t want_tiles = 4LL * ctx->num_sms;
+  int S = 1;
+  if (base_tiles > 0 && base_tiles < want_tiles && maxK >= 512 && !(ctx->flags & MPSK_FLAG_DEBUG_GEMM))
+    S = (int)std::min<int64_t>(8, (want_tiles + base_tiles - 1) / base_tiles);
+  std::vector<GemmProblemHost> probs;
+  std::vector<MixTask> rtasks; std::vector<MixTerm> rterms;
+  if (S > 1) {
+    // scratch for the partial products of slices >= 1
+    int64_t pel = 0;
+    std::vector<int> ns(probs_in.size(), 1);
+    for (size_t i = 0; i < probs_in.size(); ++i) {
+      const GemmProblemHost& h = probs_in[i];
+      if (h.M <= 0 || h.N <= 0) continue;
+      int si = (int)std::min<int64_t>(S, h.K / 256);          // keep every slice >= 256 deep
+      ns[i] = std::max(si, 1);
+      pel += (int64_t)(ns[i] - 1) * padg((int64_t)h.M * pad(h.N));
+    }
+    if (pel > 0) {
+      plan->partials = ctx->alloc((size_t)pel * esz);
+      if (!plan->partials) return ctx->fail(MPSK_ENOMEM, "split-K scratch");
+    }
+    int64_t poff = 0;
+    for (size_t i = 0; i < probs_in.size(); ++i) {
+      const GemmProblemHost& h = probs_in[i];
+      if (h.M <= 0 || h.N <= 0) continue;
+      if (ns[i] <= 1) { probs.push_back(h); continue; }
+      const int64_t kchunk = ((h.K + ns[i] - 1) / ns[i] + KSTAGE - 1) / KSTAGE * KSTAGE;
+      MixTask tk; tk.dst = h.C; tk.ldd = h.ldc; tk.rows = h.M; tk.cols = h.N; tk.term_begin = (int32_t)rterms.size();
+      rterms.push_back(MixTerm{h.C, h.ldc, 1.0, 0.0});
+      int s = 0;
+      for (int64_t k0 = 0; k0 < h.K; k0 += kchunk, ++s) {
+        GemmProblemHost q = h;
+        q.A = (const char*)h.A + k0 * esz; q.B = (const char*)h.B + k0 * esz; q.K = (int32_t)std::min<int64_t>(kchunk, h.K - k0);
+        if (s > 0) {
+          q.C = (char*)plan->partials + poff * esz; q.ldc = pad(h.N); q.accumulate = 0;
+          rterms.push_back(MixTerm{q.C, q.ldc, 1.0, 0.0});
+          poff += padg((int64_t)h.M * pad(h.N));
+        }
+        probs.push_back(q);
+      }
+      tk.term_end = (int32_t)rterms.size();
+      if (tk.term_end - tk.term_begin > 1) rtasks.push_back(tk);
+    }
+  } else {
+    for (const GemmProblemHost& h : probs_in) if (h.M > 0 && h.N > 0) probs.push_back(h);
+  }
   std::vector<GemmProblemDev> dev;
   std::vector<GemmTile> tiles;
   // order problems by decreasing K so that the long tiles are scheduled first (tail balance)
   std::vector<int> order;
-  for (size_t i = 0; i < probs.size(); ++i) if (probs[i].M > 0 && probs[i].N > 0) order.push_back((int)i);
+  for (size_t i = 0; i < probs.size(); ++i) order.push_back((int)i);
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return probs[a].K > probs[b].K; });
   for (int oi : order) {
     const GemmProblemHost& h = probs[oi];
@@ -305,7 +367,6 @@ int gemm_plan_build(Ctx* ctx, bool cplx, const std::vector<GemmProblemHost>& pro
     memset(&d, 0, sizeof(d));
     d.A = h.A; d.B = h.B; d.C = h.C; d.lda = h.lda; d.ldb = h.ldb; d.ldc = h.ldc;
     d.M = h.M; d.N = h.N; d.K = h.K; d.accumulate = h.accumulate;
-    const int esz = cplx ? 16 : 8;
     if (h.K > 0) {
       if (((uintptr_t)h.A % 16) || ((uintptr_t)h.B % 16) || ((h.lda * esz) % 16) || ((h.ldb * esz) % 16) ||
           ((uintptr_t)h.C % 16) || ((h.ldc * esz) % 16))
@@ -317,13 +378,13 @@ int gemm_plan_build(Ctx* ctx, bool cplx, const std::vector<GemmProblemHost>& pro
     }
     const int pi = (int)dev.size();
     dev.push_back(d);
-    plan->flops += (cplx ? 8.0 : 2.0) * (double)h.M * h.N * h.K;
     // raster: n-panels outer, m inner, so concurrently running CTAs share the B panel and stream A
     for (int n0 = 0; n0 < h.N; n0 += BN)
       for (int m0 = 0; m0 < h.M; m0 += BM) tiles.push_back(GemmTile{pi, m0, n0, 0});
   }
   plan->nprob = (int)dev.size();
   plan->ntiles = (int)tiles.size();
+  plan->splitk = S;
   if (plan->nprob == 0) return MPSK_OK;
   plan->d_probs = (GemmProblemDev*)ctx->alloc(dev.size() * sizeof(GemmProblemDev));
   plan->d_tiles = (GemmTile*)ctx->alloc(tiles.size() * sizeof(GemmTile));
@@ -331,6 +392,10 @@ int gemm_plan_build(Ctx* ctx, bool cplx, const std::vector<GemmProblemHost>& pro
   CUDA_TRY(ctx, cudaMemcpyAsync(plan->d_probs, dev.data(), dev.size() * sizeof(GemmProblemDev), cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(plan->d_tiles, tiles.data(), tiles.size() * sizeof(GemmTile), cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+  if (!rtasks.empty()) {
+    plan->reduce = new MixPlan;
+    MPSK_TRY(mix_plan_build(ctx, cplx, rtasks, rterms, plan->reduce));
+  }
   return MPSK_OK;
 }
 
@@ -353,6 +418,7 @@ int gemm_plan_run(Ctx* ctx, const GemmPlan* plan) {
   }
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
+  if (plan->reduce) MPSK_TRY(mix_plan_run(ctx, plan->reduce));
   return MPSK_OK;
 }
 

@@ -21,7 +21,13 @@ static int build_W(Ctx* ctx, int kind, const MpoSlice* h1, const MpoSlice* h2, c
     for (int i = 0; i < nlev; ++i) W->push_back(WEntry{i, i, 0, 0, cplx(1.0)});
     return MPSK_OK;
   }
-  if (!h1) return ctx->fail(MPSK_EINVAL, "missing MPO slice");
+  if (!h1) {
+    // dAC(x, nothing, GL, GR) / dAC2(x, nothing, nothing, GL, GR) (derivatives.jl:112-114,159-161): overlap environments,
+    // one level, identity on the physical labels
+    if (nlev != 1) return ctx->fail(MPSK_ESPACE, "MPO-free derivative needs single-level (bond) environments");
+    for (int mm = 0; mm < x_like->nm(); ++mm) W->push_back(WEntry{0, 0, mm, mm, cplx(1.0)});
+    return MPSK_OK;
+  }
   if (kind == MPSK_OP_DAC) {
     if (x_like->nm() != h1->d) return ctx->fail(MPSK_ESPACE, "dAC: vector has %d labels, slice has d=%d", x_like->nm(), h1->d);
     for (int i = 0; i < h1->odim; ++i)

@@ -381,3 +381,39 @@ def psi_set_CR(psi: FiniteMPS, i, vec):
     for k in range(0, i + 1):
         psi.AR[k] = None
     psi.CL[i + 1] = vec
+
+
+def tdvp2_step(psi: FiniteMPS, H, dt, envs=None, trunc=("truncerr", 1e-3), tol=1e-12, krylovdim=30):
+    """tdvp.jl:115-151: one two-site TDVP sweep (no normalisation of the singular values)."""
+    envs = envs or FinEnv(psi, H)
+    L = psi.L
+
+    def two_site(i, ac2, sub_dt):
+        GL, GR = envs.leftenv(i, psi), envs.rightenv(i + 1, psi)
+        f = lambda x: dAC2_sparse(x, H[i], H[i + 1], GL, GR)
+        new, _ = exponentiate_lanczos(f, -1j * sub_dt, ac2, tol, krylovdim)
+        Dl, d1, Dr, d2 = new.shape
+        rowq, colq = ac2_space_charges(psi, i)
+        U, S, Vh, newV, eps, _ = tsvd(new.reshape(Dl * d1, Dr * d2), rowq, colq, trunc, psi.p.modulus)
+        al = U.reshape(Dl, d1, newV.dim)
+        ar = Vh.reshape(newV.dim, Dr, d2).transpose(0, 2, 1)
+        c = np.diag(S).astype(np.complex128)
+        psi.set_AC_alc(i, al, c, newV)
+        psi.set_AC_car(i + 1, c, ar, newV)
+
+    def one_site_back(i, sub_dt):
+        GL, GR = envs.leftenv(i, psi), envs.rightenv(i, psi)
+        f = lambda x: dAC_sparse(x, H[i], GL, GR)
+        ac, _ = exponentiate_lanczos(f, +1j * sub_dt, psi.get_AC(i), tol, krylovdim)
+        psi.set_AC(i, ac)
+    for i in range(0, L - 1):
+        ac2 = np.einsum('apk,kqr->aprq', psi.get_AC(i), psi.get_AR(i + 1))
+        two_site(i, ac2, dt / 2)
+        if i != L - 2:
+            one_site_back(i + 1, dt / 2)
+    for i in range(L - 1, 0, -1):
+        ac2 = np.einsum('apk,kqr->aprq', psi.get_AL(i - 1), psi.get_AC(i))
+        two_site(i - 1, ac2, dt / 2)
+        if i != 1:
+            one_site_back(i - 1, dt / 2)
+    return psi, envs

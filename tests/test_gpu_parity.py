@@ -553,3 +553,43 @@ def test_leading_boundary_classical_ising(ctx):
     print("classic2d", v_d, v_o, len(log_d), len(log_o))
     assert abs(v_d - 2.5337) < 1e-3 and abs(v_d.imag) < 1e-9
     assert abs(v_d - v_o) <= 1e-6 * abs(v_o)
+
+
+def test_tdvp2_step(ctx):
+    """timestep(psi, H, 0, dt, TDVP2(trscheme=truncdim(8))) (tdvp.jl:115-151) vs the oracle sweep and the exact evolution."""
+    import scipy.linalg as sla
+    L = 6
+    Ho = ompo.heisenberg_u1(L)
+    po = OSpace((-1, 1), (1, 1))
+    maxV = [of.gaussian_bond_space(8, k % 2) for k in range(1, L)]
+    psi_o = of.FiniteMPS.random(np.random.default_rng(93), po, L, maxV)
+    v0 = _full_state_o(psi_o)
+    dt = 0.05
+    psi_o, _ = of.tdvp2_step(psi_o, Ho, dt, trunc=("truncdim", 8))
+    v_o = _full_state_o(psi_o)
+    psi_d = m.FiniteMPS.random(np.random.default_rng(93), to_dev_space(po), L, [to_dev_space(v) for v in maxV], ctx)
+    psi_d, envs = m.timestep(psi_d, dev_hamiltonian(Ho), 0.0, dt, m.TDVP2(trscheme=m.truncdim(8)))
+    v_d = _full_state(psi_d)
+    v_ex = sla.expm(-1j * dt * ompo.dense_hamiltonian(Ho)) @ v0
+    print("tdvp2 overlaps", abs(np.vdot(v_d, v_o)), abs(np.vdot(v_d, v_ex)))
+    assert abs(abs(np.vdot(v_d, v_o)) - 1) <= 1e-9
+    assert abs(abs(np.vdot(v_d, v_ex)) - 1) <= 1e-6
+
+
+def test_mpo_free_derivatives(ctx):
+    """dAC2(x, nothing, nothing, GL, GR) = GL x GR and dAC(x, nothing, GL, GR) (derivatives.jl:112-114,159-161)."""
+    rng = np.random.default_rng(131)
+    pch = [-1, 1]
+    mch = [pch[a] + pch[b] for a in range(2) for b in range(2)]
+    x = BlockTensor.random(rng, VBIG_L, mch, VBIG_R2)
+    GL = BlockTensor.random(rng, VBIG_L, [0], VBIG_L)
+    GR = BlockTensor.random(rng, VBIG_R2, [0], VBIG_R2)
+    dx, dGL, dGR = dev_tensor(ctx, x), dev_tensor(ctx, GL), dev_tensor(ctx, GR)
+    y = m.MPO_ddAC2(ctx, None, None, dGL, dGR, dx)(dx).to_dense()
+    ref = np.einsum('ab,bmc,cd->amd', GL.to_dense()[:, 0, :], x.to_dense(), GR.to_dense()[:, 0, :], optimize=True)
+    assert relerr(y, ref) <= 1e-12
+    x1 = BlockTensor.random(rng, VBIG_L, pch, VBIG_R)
+    GR1 = BlockTensor.random(rng, VBIG_R, [0], VBIG_R)
+    d1, dGR1 = dev_tensor(ctx, x1), dev_tensor(ctx, GR1)
+    y1 = m.MPO_ddAC(ctx, None, dGL, dGR1, d1)(d1).to_dense()
+    assert relerr(y1, np.einsum('ab,bmc,cd->amd', GL.to_dense()[:, 0, :], x1.to_dense(), GR1.to_dense()[:, 0, :], optimize=True)) <= 1e-12
