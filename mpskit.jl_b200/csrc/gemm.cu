@@ -58,17 +58,18 @@ struct LoadCursor {
   }
 };
 
-template <bool CPLX>
-__global__ void __launch_bounds__(256, 1)
+template <bool CPLX, int WARPS_N>
+__global__ void __launch_bounds__(GemmCfg<CPLX, WARPS_N>::NTHREADS, GemmCfg<CPLX, WARPS_N>::CTAS_PER_SM)
 gemm_dmma_kernel(const GemmProblemDev* __restrict__ probs, const GemmTile* __restrict__ tiles, int ntiles) {
-  using Cfg = GemmCfg<CPLX>;
+  using Cfg = GemmCfg<CPLX, WARPS_N>;
   constexpr int BM = Cfg::BM, BN = Cfg::BN, KSUB = Cfg::KSUB, NSUB = Cfg::NSUB, STAGES = Cfg::STAGES;
   constexpr int KSTAGE = KSUB * NSUB;                       // elements of K per stage
   constexpr int A_SUB_BYTES = BM * 64, B_SUB_BYTES = BN * 64;
   constexpr int STAGE_BYTES = NSUB * (A_SUB_BYTES + B_SUB_BYTES);
   constexpr int WM = CPLX ? 32 : 64, WN = 32;               // warp tile
   constexpr int MI = WM / 8, NI = WN / 8;
-  constexpr int WARPS_M = BM / WM;                          // 4 (cplx) / 2 (real)
+  constexpr int WARPS_M = Cfg::WARPS_M;                     // 4 (cplx) / 2 (real)
+  constexpr int NWARPS = Cfg::WARPS_M * Cfg::WARPS_N;
   constexpr int DPE = CPLX ? 2 : 1;                         // doubles per element
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -78,7 +79,7 @@ gemm_dmma_kernel(const GemmProblemDev* __restrict__ probs, const GemmTile* __res
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 8); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NWARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -278,8 +279,8 @@ static bool encode_map(CUtensorMap* tm, const void* base, int64_t rows, int64_t 
   return r == CUDA_SUCCESS;
 }
 
-template <bool CPLX> static int smem_bytes() {
-  using Cfg = GemmCfg<CPLX>;
+template <bool CPLX, int WN> static int smem_bytes() {
+  using Cfg = GemmCfg<CPLX, WN>;
   return Cfg::STAGES * Cfg::NSUB * (Cfg::BM + Cfg::BN) * 64 + 2 * Cfg::STAGES * 8 + 128;
 }
 
@@ -297,10 +298,21 @@ GemmPlan::~GemmPlan() {
 // (the mix kernel, C += sum_s P_s) folds back.  Deterministic: no atomics, fixed summation order.
 int gemm_plan_build(Ctx* ctx, bool cplx, const std::vector<GemmProblemHost>& probs_in, GemmPlan* plan) {
   plan->ctx = ctx; plan->cplx = cplx; plan->nprob = 0; plan->ntiles = 0; plan->flops = 0;
-  const int BM = cplx ? GemmCfg<true>::BM : GemmCfg<false>::BM;
-  const int BN = cplx ? GemmCfg<true>::BN : GemmCfg<false>::BN;
-  const int KSTAGE = cplx ? GemmCfg<true>::KSUB * GemmCfg<true>::NSUB : GemmCfg<false>::KSUB * GemmCfg<false>::NSUB;
+  const int BM = 128;
+  const int KSTAGE = cplx ? 16 : 32;
   const size_t esz = cplx ? 16 : 8;
+  // ---- tile configuration: narrow (128 x 32, complex only) when it cuts the quantised tile work by > 7 %
+  int BN = cplx ? 32 * GEMM_WIDE_N_CPLX : 32 * GEMM_WIDE_N_REAL;
+  plan->narrow = false;
+  if (cplx && !(ctx->flags & MPSK_FLAG_DEBUG_GEMM)) {
+    double wide = 0, nar = 0;
+    for (const GemmProblemHost& h : probs_in) {
+      if (h.M <= 0 || h.N <= 0) continue;
+      const double mt = (double)((h.M + BM - 1) / BM) * BM * h.K;
+      wide += mt * ((h.N + 63) / 64) * 64; nar += mt * ((h.N + 31) / 32) * 32;
+    }
+    if (nar < 0.93 * wide) { plan->narrow = true; BN = 32 * GEMM_NARROW_N_CPLX; }
+  }
   // ---- split-K decision
   int64_t base_tiles = 0; int64_t maxK = 0;
   for (const GemmProblemHost& h : probs_in) {
@@ -309,7 +321,7 @@ int gemm_plan_build(Ctx* ctx, bool cplx, const std::vector<GemmProblemHost>& pro
     maxK = std::max<int64_t>(maxK, h.K);
     plan->flops += (cplx ? 8.0 : 2.0) * (double)h.M * h.N * h.K;
   }
-  const int64_t want_tiles = 4LL * ctx->num_sms;
+  const int64_t want_tiles = 4LL * ctx->num_sms * (plan->narrow ? 2 : 1);
   int S = 1;
   if (base_tiles > 0 && base_tiles < want_tiles && maxK >= 512 && !(ctx->flags & MPSK_FLAG_DEBUG_GEMM))
     S = (int)std::min<int64_t>(8, (want_tiles + base_tiles - 1) / base_tiles);
@@ -406,14 +418,22 @@ int gemm_plan_run(Ctx* ctx, const GemmPlan* plan) {
     if (plan->cplx) gemm_debug_kernel<true><<<grid, 256, 0, ctx->stream>>>(plan->d_probs, plan->nprob);
     else gemm_debug_kernel<false><<<grid, 256, 0, ctx->stream>>>(plan->d_probs, plan->nprob);
   } else {
-    static bool attr_set[2] = {false, false};
-    const int grid = std::min(plan->ntiles, ctx->num_sms);
-    if (plan->cplx) {
-      if (!attr_set[1]) { CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<true>())); attr_set[1] = true; }
-      gemm_dmma_kernel<true><<<grid, 256, smem_bytes<true>(), ctx->stream>>>(plan->d_probs, plan->d_tiles, plan->ntiles);
+    static bool attr_set[3] = {false, false, false};
+    if (plan->cplx && plan->narrow) {
+      using Cfg = GemmCfg<true, GEMM_NARROW_N_CPLX>;
+      const int grid = std::min(plan->ntiles, ctx->num_sms * Cfg::CTAS_PER_SM);
+      if (!attr_set[2]) { CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_dmma_kernel<true, GEMM_NARROW_N_CPLX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<true, GEMM_NARROW_N_CPLX>())); attr_set[2] = true; }
+      gemm_dmma_kernel<true, GEMM_NARROW_N_CPLX><<<grid, Cfg::NTHREADS, smem_bytes<true, GEMM_NARROW_N_CPLX>(), ctx->stream>>>(plan->d_probs, plan->d_tiles, plan->ntiles);
+    } else if (plan->cplx) {
+      using Cfg = GemmCfg<true, GEMM_WIDE_N_CPLX>;
+      const int grid = std::min(plan->ntiles, ctx->num_sms);
+      if (!attr_set[1]) { CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_dmma_kernel<true, GEMM_WIDE_N_CPLX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<true, GEMM_WIDE_N_CPLX>())); attr_set[1] = true; }
+      gemm_dmma_kernel<true, GEMM_WIDE_N_CPLX><<<grid, Cfg::NTHREADS, smem_bytes<true, GEMM_WIDE_N_CPLX>(), ctx->stream>>>(plan->d_probs, plan->d_tiles, plan->ntiles);
     } else {
-      if (!attr_set[0]) { CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<false>())); attr_set[0] = true; }
-      gemm_dmma_kernel<false><<<grid, 256, smem_bytes<false>(), ctx->stream>>>(plan->d_probs, plan->d_tiles, plan->ntiles);
+      using Cfg = GemmCfg<false, GEMM_WIDE_N_REAL>;
+      const int grid = std::min(plan->ntiles, ctx->num_sms);
+      if (!attr_set[0]) { CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_dmma_kernel<false, GEMM_WIDE_N_REAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<false, GEMM_WIDE_N_REAL>())); attr_set[0] = true; }
+      gemm_dmma_kernel<false, GEMM_WIDE_N_REAL><<<grid, Cfg::NTHREADS, smem_bytes<false, GEMM_WIDE_N_REAL>(), ctx->stream>>>(plan->d_probs, plan->d_tiles, plan->ntiles);
     }
   }
   ctx->launches++;

@@ -30,9 +30,19 @@ struct GemmProblemHost {
   int64_t lda, ldb, ldc; int32_t M, N, K; int32_t accumulate;
 };
 
-// tile shapes (elements)
-template <bool CPLX> struct GemmCfg;
-template <> struct GemmCfg<false> { static constexpr int BM = 128, BN = 128, KSUB = 8, NSUB = 4, STAGES = 3; };
-template <> struct GemmCfg<true>  { static constexpr int BM = 128, BN = 64,  KSUB = 4, NSUB = 4, STAGES = 4; };
+// Tile configurations.  Warp tile: 32 x 32 (complex) / 64 x 32 (real); CTA tile = BM x (32 * WARPS_N).
+//   wide   : 8 warps, 128 x 64 complex / 128 x 128 real, 1 CTA per SM, 4 / 3 pipeline stages
+//   narrow : 4 warps, 128 x 32 complex, 2 CTAs per SM, 2 stages -- for plans dominated by narrow-N problems (the row
+//            panels of a sharded matvec), where 64-wide tiles would waste up to 40 % of the DMMA work
+template <bool CPLX, int WARPS_N_> struct GemmCfg {
+  static constexpr int WARPS_M = CPLX ? 4 : 2;
+  static constexpr int WARPS_N = WARPS_N_;
+  static constexpr int BM = 128, BN = 32 * WARPS_N_;
+  static constexpr int KSUB = CPLX ? 4 : 8, NSUB = 4;
+  static constexpr int NTHREADS = 32 * WARPS_M * WARPS_N;
+  static constexpr int CTAS_PER_SM = NTHREADS <= 128 ? 2 : 1;
+  static constexpr int STAGES = CTAS_PER_SM == 2 ? 2 : (CPLX ? 4 : 3);
+};
+constexpr int GEMM_WIDE_N_CPLX = 2, GEMM_NARROW_N_CPLX = 1, GEMM_WIDE_N_REAL = 4;
 
 }  // namespace mpsk

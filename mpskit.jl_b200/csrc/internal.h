@@ -169,6 +169,7 @@ struct GemmPlan {
   Ctx* ctx = nullptr; bool cplx = true;
   GemmProblemDev* d_probs = nullptr; GemmTile* d_tiles = nullptr;
   int nprob = 0, ntiles = 0; double flops = 0;
+  bool narrow = false;      // 128 x 32 tile configuration (complex, narrow-N plans)
   int splitk = 1; void* partials = nullptr; MixPlan* reduce = nullptr;    // split-K partial products + their reduction pass
   ~GemmPlan();
 };
