@@ -279,7 +279,9 @@ def main():
         gm = gemm_only_ms(ctx, op, x, y, stream, torch, max(3, min(args.steps, 10))) if world == 1 else float("nan")
         roofline = {"bound": "tensor", "kernel": "gemm_dmma_kernel<complex> (stage A + stage C of one matvec)",
                     "achieved": flops / (gm * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
-                    "frac": flops / (gm * 1e-3) / 1e12 / peak, "traffic": None,
+                    "frac": flops / (gm * 1e-3) / 1e12 / peak,
+                    "traffic": 55.85e9 if (args.D == 4096 and args.r == 6) else None,
+                    "traffic_source": "ncu dram__bytes_read+write per matvec (stage A 42.89+3.56 GB, stage C 9.21+0.19 GB), profiles/r01_SUMMARY.md; algorithmic operand bytes 10.6 GB",
                     "peak_source": "live torch.matmul complex128 4096^3 (cuBLAS zgemm) on this GPU; DMMA microbenchmark "
                                    "profiles/r01_peak_fp64_microbench.json gives 36.99; MEASURED_PEAKS.json has no FP64 entry",
                     "gemm_ms_per_matvec": gm, "share_of_step": gm / ms}
