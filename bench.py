@@ -122,10 +122,11 @@ def run_reference(args):
     from oracle import mpo as ompo
     from oracle.contract import dAC2_blocks
     sys.path.insert(0, os.path.join(ROOT, "mpskit.jl_b200"))
-    # bounded sample: largest D <= args.D of the same recipe whose (warmup + steps) matvecs fit in ~150 s of CPU time
-    per1024 = 1.3 * 8.0 / max(os.cpu_count() or 8, 1)
+    # bounded sample: largest D <= args.D of the same recipe whose (warmup + steps) matvecs fit in ~200 s of CPU time
+    # (measured: 6.6 s per D=4096 matvec on 16 cores, ~cubic in D at these sizes)
+    t4096 = 14.0 * 8.0 / max(os.cpu_count() or 8, 1)
     Ds = args.D
-    while Ds > 512 and (args.steps + args.warmup) * per1024 * (Ds / 1024.0) ** 3 > 150.0:
+    while Ds > 512 and (args.steps + args.warmup) * t4096 * (Ds / 4096.0) ** 3 > 200.0:
         Ds //= 2
     cs = [c for c in range(-10, 11) if c % 2 == 0]
     g = np.array([np.exp(-(c / 2) ** 2 / (2 * 1.5 ** 2)) for c in cs])
