@@ -7,7 +7,8 @@ from ._lib import (Context, default_context, MpskError, SpaceMismatch, load as l
 from .spaces import Space, fuse, infimum, dual  # noqa: F401
 from .tensor import DeviceTensor, block_table  # noqa: F401
 from .operators import (SparseMPOSlice, MPOHamiltonian, transverse_field_ising, heisenberg_u1,  # noqa: F401
-                        heisenberg_longrange_u1, drop_symmetry, DenseMPO, dense_mpo_slice, classical_ising)
+                        heisenberg_longrange_u1, drop_symmetry, DenseMPO, dense_mpo_slice, classical_ising,
+                        periodic_boundary_conditions)
 from .derivatives import (MPO_ddC, MPO_ddAC, MPO_ddAC2, ddC, ddAC, ddAC2, LazySumOp, MultipliedOp,  # noqa: F401
                           LinearCombinationOp)
 from .krylov import RecursiveVec, eigsolve_arnoldi, linsolve_gmres  # noqa: F401

@@ -191,3 +191,60 @@ class DenseMPO:
 
     def __getitem__(self, i):
         return self.slices[i % len(self.slices)]
+
+
+def periodic_boundary_conditions(H: MPOHamiltonian, L=None):
+    """periodic_boundary_conditions(H, L) (src/algorithms/toolbox.jl:186-306) for width-1 levels: relabelled FSM over
+    triples (a, b, c) with charge c_a - c_b + c_c (all fusers are 1 x 1 identities); host-side operator construction."""
+    L = len(H) if L is None else L
+    period = len(H)
+    chi = H.odim
+    top = chi - 1
+    indmap = {}
+    for b in range(top, 0, -1):
+        for c in range(b, chi):
+            indmap[(0, b, c)] = len(indmap)
+    for a in range(1, chi):
+        for b in range(top, a - 1, -1):
+            indmap[(a, b, top)] = len(indmap)
+    chi2 = len(indmap)
+    cl = H[0].domcharges
+    charges = [0] * chi2
+    for (a, b, c), idx in indmap.items():
+        charges[idx] = cl[a] - cl[b] + cl[c]
+
+    def empty():
+        return [[0 for _ in range(chi2)] for _ in range(chi2)]
+
+    def bulk(loc):
+        Os = empty()
+        sl = H[loc]
+        for (j, k) in sl.keys():
+            for i in range(1, chi):
+                if k <= i:
+                    Os[indmap[(j, i, top)]][indmap[(k, i, top)]] = sl.Os[j][k]
+            for l in range(1, top):
+                if l <= j:
+                    Os[indmap[(0, l, j)]][indmap[(0, l, k)]] = sl.Os[j][k]
+        return Os
+    starter = empty()
+    for (j, k) in H[0].keys():
+        if j == 0:
+            starter[0][indmap[(k, top, top)]] = H[0].Os[j][k]
+        if 0 < j < top:
+            starter[0][indmap[(0, j, k)]] = H[0].Os[j][k]
+    starter[0][0] = 1.0
+    starter[chi2 - 1][chi2 - 1] = 1.0
+    ender = empty()
+    last = H[period - 1]
+    for (j, k) in last.keys():
+        if k > 0:
+            ender[indmap[(j, k, top)]][chi2 - 1] = last.Os[j][k]
+    ender[0][0] = 1.0
+    ender[chi2 - 1][chi2 - 1] = 1.0
+    pch = H[0].pcharges
+    slices = [SparseMPOSlice(starter, charges, charges, pch)]
+    for i in range(1, L - 1):
+        slices.append(SparseMPOSlice(bulk(i % period), charges, charges, pch))
+    slices.append(SparseMPOSlice(ender, charges, charges, pch))
+    return MPOHamiltonian(slices)

@@ -593,3 +593,20 @@ def test_mpo_free_derivatives(ctx):
     d1, dGR1 = dev_tensor(ctx, x1), dev_tensor(ctx, GR1)
     y1 = m.MPO_ddAC(ctx, None, dGL, dGR1, d1)(d1).to_dense()
     assert relerr(y1, np.einsum('ab,bmc,cd->amd', GL.to_dense()[:, 0, :], x1.to_dense(), GR1.to_dense()[:, 0, :], optimize=True)) <= 1e-12
+
+
+def test_config1_readme_quickstart_pbc_tfi(ctx):
+    """BASELINE.json config 1 (README quickstart): finite TFI, L=16, D=4, PBC through periodic_boundary_conditions,
+    find_groundstate with single-site DMRG -- device vs oracle on the same seeded state."""
+    L, D, g = 16, 4, 1.0
+    Ho = ompo.periodic_boundary_conditions(ompo.transverse_field_ising(1, g), L)
+    psi_o = of.FiniteMPS.random(np.random.default_rng(141), OSpace((0,), (2,)), L, OSpace((0,), (D,)))
+    log_o = []
+    of.dmrg_sweeps(psi_o, Ho, nsweeps=4, tol=1e-13, log=log_o)
+    Hd = m.periodic_boundary_conditions(m.transverse_field_ising(1, g), L)
+    psi_d = m.FiniteMPS.random(np.random.default_rng(141), m.Space((0,), (2,)), L, m.Space((0,), (D,)), ctx)
+    log_d = []
+    m.find_groundstate(psi_d, Hd, m.DMRG(tol=1e-13, maxiter=4, eigalg=m.Lanczos(tol=1e-13)), log=log_d)
+    print("config1", log_d[-1]["energy"], log_o[-1]["energy"], -2 / np.sin(np.pi / (2 * L)))
+    assert abs(log_d[-1]["energy"] - log_o[-1]["energy"]) <= 1e-8 * abs(log_o[-1]["energy"])
+    assert abs(log_d[-1]["energy"] - (-2 / np.sin(np.pi / (2 * L)))) < 0.05      # D = 4 variational bound vs the exact ring energy
