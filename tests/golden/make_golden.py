@@ -72,6 +72,26 @@ def main():
         np.savez_compressed(os.path.join(OUT, f"dmrg2_{name}.npz"), energy=np.array([s["energy"] for s in log]),
                             eps_trunc=np.array([s["eps_trunc"] for s in log]), pos=np.array([s["pos"] for s in log]),
                             kept=np.array([sum(s["kept"].values()) for s in log]))
+    # ---- infinite-MPS / statmech / time-evolution trajectories (frozen oracle outputs)
+    from oracle import infinite as oi, statmech as osm
+    psi = oi.InfiniteMPS.random(np.random.default_rng(3), Space((0,), (2,)), [Space((0,), (10,))])
+    log = []
+    oi.vumps(psi, ompo.transverse_field_ising(1, 0.5), tol=1e-12, maxiter=30, log=log)
+    np.savez_compressed(os.path.join(OUT, "vumps_tfi_g0.5_D10.npz"), energy=np.array([s["energy"] for s in log]),
+                        eps=np.array([s["eps"] for s in log]))
+    psi = oi.InfiniteMPS.random(np.random.default_rng(3), Space((0,), (2,)), [Space((0,), (10,))])
+    log = []
+    osm.leading_boundary(psi, [ompo.dense_mpo_slice(ompo.classical_ising())], tol=1e-6, maxiter=12, log=log)
+    np.savez_compressed(os.path.join(OUT, "statmech_ising_D10.npz"), value=np.array([s["value"][0] for s in log]),
+                        eps=np.array([s["eps"] for s in log]))
+    L = 6
+    Ho = ompo.heisenberg_u1(L)
+    st = of.FiniteMPS.random(np.random.default_rng(91), Space((-1, 1), (1, 1)), L, [of.gaussian_bond_space(8, k % 2) for k in range(1, L)])
+    st, _ = of.tdvp_step(st, Ho, 0.05)
+    T = st.get_AC(0)
+    for i in range(1, L):
+        T = np.tensordot(T, st.get_AR(i), axes=([-1], [0]))
+    np.savez_compressed(os.path.join(OUT, "tdvp_heisenberg_L6.npz"), state=T.reshape(-1))
     print("golden vectors written to", OUT)
 
 

@@ -276,3 +276,20 @@ def test_transfer_matrix_fixed_points_and_tdvp_energy_conservation():
         st, envs = of.tdvp_step(st, H, 0.05, envs)
     E1 = sum(of.expectation_value(st, H, envs)).real
     assert abs(E1 - E0) < 1e-8
+
+
+def test_golden_trajectories_and_bench_flop_model():
+    """frozen oracle trajectories (tests/golden) and the algorithmic flop count bench.py reports (3.1e12)."""
+    v = np.load(os.path.join(GOLD, "vumps_tfi_g0.5_D10.npz"))
+    assert abs(v["energy"][-1] - (-1.063544409973)) < 2e-12 and len(v["energy"]) == 7
+    s = np.load(os.path.join(GOLD, "statmech_ising_D10.npz"))
+    assert abs(s["value"][-1] - 2.5337) < 1e-3
+    t = np.load(os.path.join(GOLD, "tdvp_heisenberg_L6.npz"))
+    assert abs(np.linalg.norm(t["state"]) - 1) < 1e-10
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(GOLD), "..", "bench.py"))
+    bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)
+    V = of.gaussian_bond_space(4096, 0)
+    h = ompo.heisenberg_longrange_u1(2, 6)[0]
+    F = bench.algorithmic_flops(V, h, [h.pch[a] + h.pch[b] for a in range(2) for b in range(2)])
+    assert F == 3084892580736.0 and abs(F - 3.1e12) < 0.05e12
