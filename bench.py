@@ -245,7 +245,8 @@ def main():
 
     # per-kernel timing of the dominant kernel (grouped DMMA GEMM): time stage A + stage C launches alone
     e2e = None
-    if rank == 0 and not args.no_e2e and world == 1:
+    if not args.no_e2e:
+        # every rank holds the (replicated) Krylov vector in pinned host memory: upload, (sharded) matvec, download
         xb = {k: torch.from_numpy(v).pin_memory().numpy() for k, v in x.to_blocks().items()}   # pinned host blocks
         yb = {k: torch.from_numpy(np.empty_like(v)).pin_memory().numpy() for k, v in xb.items()}
         bytes_x = sum(b.nbytes for b in xb.values())
@@ -253,6 +254,8 @@ def main():
             xd = m.DeviceTensor.from_blocks(ctx, x.Vl, x.mch, x.Vr, xb); op.apply_into(xd, y); y.to_blocks(yb); xd.free()
         nrep = max(3, min(args.steps, 10))
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         t0 = time.perf_counter()
         for _ in range(nrep):
             xd = m.DeviceTensor.from_blocks(ctx, x.Vl, x.mch, x.Vr, xb)
@@ -260,7 +263,11 @@ def main():
             y.to_blocks(yb)
             xd.free()
         dt = (time.perf_counter() - t0) / nrep
-        e2e = {"value": flops / dt / 1e12, "unit": UNIT, "h2d_bytes_per_step": bytes_x, "d2h_bytes_per_step": bytes_x,
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": flops / dt / 1e12, "unit": UNIT, "h2d_bytes_per_step": bytes_x * world, "d2h_bytes_per_step": bytes_x * world,
                "ms_per_step": dt * 1e3}
 
     # roofline denominator: FP64 tensor (DMMA) peak is not in MEASURED_PEAKS.json -> measure cuBLAS zgemm live
