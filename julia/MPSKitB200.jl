@@ -42,12 +42,36 @@ function cspace(V)
     return q[p], Int64[dim(V, c) for c in secs][p]
 end
 
-# A TensorMap with (l ⊗ m...) ← (r ⊗ ...) legs is handed over block by block: for every (label m, l-sector) the shim
-# locates the sub-block inside the coupled-sector matrix `blocks(t)[c]` through the fusion-tree row/column ranges
-# (rows: codomain uncoupled tuples, first leg fastest; cols: domain tuples) and passes pointer + (stride_l, stride_r).
-# For an MPS tensor A[l p; r] the block (p, q_l) lives in blocks(A)[q_r] at rows rowrange(q_l, p), all columns:
-#   ptr = pointer(b, first(rowrange)), stride_l = 1, stride_r = size(b, 1)      (column-major).
-function blockrefs(t::AbstractTensorMap) end   # ~60 lines of fusion-tree bookkeeping, one method per tensor kind
+# A TensorMap is handed over block by block.  TensorKit 0.12 stores one column-major matrix per coupled sector;
+# `t[f1, f2]` is a StridedView of the sub-block of the fusion-tree pair (f1, f2) into that matrix, so its pointer and
+# strides are exactly what the ABI wants -- no data is copied or permuted on the Julia side.
+#
+# MPS tensor A[l p; r]:  f1.uncoupled = (q_l, s_p), f2.uncoupled = (q_r,).  The ABI labels are the physical *basis states*
+# (a charge sector of degeneracy k contributes k labels), blocks are ordered label-major, l-sector-minor.
+function blockrefs(A::MPSTensor)
+    P = space(A, 2)
+    labels = Tuple{eltype(sectors(P)),Int}[]                  # (charge, index inside the degeneracy space)
+    for c in sort(collect(sectors(P)); by=charge2), k in 1:dim(P, c)
+        push!(labels, (c, k))
+    end
+    Vl = space(A, 1)
+    lsecs = sort(collect(sectors(Vl)); by=charge2)
+    refs = BlockRef[]
+    for (c, k) in labels, ql in lsecs
+        for (f1, f2) in fusiontrees(A)
+            f1.uncoupled == (ql, c) || continue
+            sv = A[f1, f2]                                    # size (n_l, dim(P, c), n_r)
+            st = strides(sv)
+            push!(refs, BlockRef(pointer(sv) + (k - 1) * st[2] * sizeof(eltype(A)), st[1], st[3]))
+        end
+    end
+    return refs
+end
+# two-site tensors x[l p1; r p2] (labels (p1, p2), stride_r taken from the r leg of the domain), bond tensors C[l; r]
+# (one label) and environment levels GL_i[l_bra w; l_ket] (label = MPO level, w one-dimensional) follow the same pattern;
+# MPSKit keeps environments as Vectors of such tensors, which map onto `mpsk_tensor_stack_labels`.
+function blockrefs(x::MPOTensor) end
+function blockrefs(C::MPSBondTensor) end
 
 function upload(t::AbstractTensorMap, mch::Vector{Int32}, Vl, Vr)
     ql, nl = cspace(Vl); qr, nr = cspace(Vr)
