@@ -188,12 +188,14 @@ class FiniteMPS:
     def _set_AC(self, i, v):
         if isinstance(v, tuple):
             a, b = v
-            if getattr(a, "_is_bond", False):      # (c, ar)
+            def isbond(t):
+                return getattr(t, "_is_bond", False) or (len(t.mch) == 1 and t.mch[0] == 0 and len(self.pq) != 1)
+            if isbond(a):      # (c, ar)
                 self._invalidate(i)
                 self.V[i] = a.Vr
                 self.CLs[i] = a
                 self.ARs[i] = b
-            elif getattr(b, "_is_bond", False):    # (al, c)
+            elif isbond(b):    # (al, c)
                 self._invalidate(i)
                 self.V[i + 1] = b.Vl
                 self.CLs[i + 1] = b
