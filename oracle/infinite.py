@@ -336,3 +336,37 @@ def vumps(st: InfiniteMPS, H, tol=1e-12, maxiter=100, envs=None, log=None):
         if eps <= tol:
             break
     return st, envs, eps
+
+
+# ------------------------------------------------------------------------------------------ IDMRG1 (next-row preparation)
+def idmrg1(st: InfiniteMPS, H, tol=1e-12, maxiter=100, envs=None, log=None):
+    """find_groundstate(psi::InfiniteMPS, H, IDMRG1()) (src/algorithms/groundstate/idmrg.jl:21-75) with the manually
+    updated IDMRGEnv (src/environments/idmrgenv.jl:6-72).  Oracle only in round 1."""
+    from .contract import transfer_left_sparse, transfer_right_sparse
+    envs0 = envs or MPOHamInfEnv(st, H)
+    N, od = st.N, H.odim
+    lw = [envs0.leftenv(i, st).copy() for i in range(N)]          # IDMRGEnv: deep copies, updated by hand
+    rw = [envs0.rightenv(i, st).copy() for i in range(N)]
+    AL, AR, AC, CR = list(st.AL), list(st.AR), list(st.AC), list(st.CR)
+    eps = np.inf
+    for it in range(1, maxiter + 1):
+        etol = max(tol / 10, 1e-14)
+        Ccur = CR[N - 1]
+        for pos in range(N):                                       # left -> right
+            GL, GR = lw[pos], rw[pos]
+            _, AC[pos], _ = eigsolve_lanczos(lambda x: dAC_sparse(x, H[pos], GL, GR), AC[pos], "SR", etol, 30, 100)
+            AL[pos], CR[pos] = InfiniteMPS.leftorth(AC[pos], st.V[pos], st.V[(pos + 1) % N], st.pq, st.modulus)
+            lw[(pos + 1) % N] = transfer_left_sparse(lw[pos], H[pos], AL[pos], AL[pos])           # update_leftenv!
+        for pos in range(N - 1, -1, -1):                           # right -> left
+            GL, GR = lw[pos], rw[pos]
+            _, AC[pos], _ = eigsolve_lanczos(lambda x: dAC_sparse(x, H[pos], GL, GR), AC[pos], "SR", etol, 30, 100)
+            CR[(pos - 1) % N], AR[pos] = InfiniteMPS.rightorth(AC[pos], st.V[pos], st.V[(pos + 1) % N], st.pq, st.modulus)
+            rw[(pos - 1) % N] = transfer_right_sparse(rw[pos], H[pos], AR[pos], AR[pos])          # update_rightenv!
+        eps = float(np.linalg.norm(Ccur - CR[N - 1]))
+        if log is not None:
+            log.append(dict(iter=it, eps=eps))
+        if eps < tol:
+            break
+    nst = InfiniteMPS.from_tensors(AR, st.V, st.pq, mod=st.modulus)
+    nenvs = MPOHamInfEnv(nst, H)
+    return nst, nenvs, eps

@@ -293,3 +293,13 @@ def test_golden_trajectories_and_bench_flop_model():
     h = ompo.heisenberg_longrange_u1(2, 6)[0]
     F = bench.algorithmic_flops(V, h, [h.pch[a] + h.pch[b] for a in range(2) for b in range(2)])
     assert F == 3084892580736.0 and abs(F - 3.1e12) < 0.05e12
+
+
+def test_idmrg1_oracle_matches_vumps_energy():
+    """idmrg.jl:21-75 (oracle only in round 1): IDMRG1 reaches the same variational energy as VUMPS / the reference log."""
+    from oracle import infinite as oi
+    H = ompo.transverse_field_ising(1, 0.5)
+    psi = oi.InfiniteMPS.random(np.random.default_rng(3), Space((0,), (2,)), [Space((0,), (10,))])
+    st, envs, eps = oi.idmrg1(psi, H, tol=1e-10, maxiter=200)
+    assert eps < 1e-10
+    assert abs(oi.expectation_value(st, H, envs).sum().real - (-1.063544409973)) < 1e-10
