@@ -466,3 +466,72 @@ def find_groundstate_vumps(st: InfiniteMPS, H, alg: VUMPS = None, envs=None, log
         if eps <= alg.tol:
             break
     return st, envs, eps
+
+
+# ------------------------------------------------------------------------------------------ IDMRG1
+@dataclass
+class IDMRG1:
+    """idmrg.jl:13-19"""
+    tol: float = 1e-12
+    tol_gauge: float = TOLGAUGE
+    eigalg: object = field(default_factory=lambda: Lanczos(tol=1e-12))
+    maxiter: int = 100
+    verbosity: int = 0
+
+
+class IDMRGEnv:
+    """idmrgenv.jl:6-15: manually updated copies of the infinite environments (stacked level vectors)"""
+
+    def __init__(self, psi: InfiniteMPS, env: MPOHamInfEnv):
+        if env.dependency is not psi:
+            env.recalculate(psi)
+        self.opp = env.opp
+        self.N = psi.N
+        self.lw = [env.leftenv(i, psi).copy() for i in range(psi.N)]
+        self.rw = [env.rightenv(i, psi).copy() for i in range(psi.N)]
+
+    def leftenv(self, pos, psi=None):
+        return self.lw[pos % self.N]
+
+    def rightenv(self, pos, psi=None):
+        return self.rw[pos % self.N]
+
+
+def update_leftenv(envs: IDMRGEnv, AL_prev, H, pos):
+    """update_leftenv!(envs, st, H, pos) (idmrgenv.jl:68-72): lw[pos] = lw[pos-1] * TransferMatrix(AL[pos-1], H[pos-1], AL[pos-1])"""
+    envs.lw[pos % envs.N] = transfer_left(envs.lw[(pos - 1) % envs.N], H[pos - 1], AL_prev, AL_prev)
+
+
+def update_rightenv(envs: IDMRGEnv, AR_next, H, pos):
+    """update_rightenv!(envs, st, H, pos) (idmrgenv.jl:63-66): rw[pos] = TransferMatrix(AR[pos+1], H[pos+1], AR[pos+1]) * rw[pos+1]"""
+    envs.rw[pos % envs.N] = transfer_right(envs.rw[(pos + 1) % envs.N], H[pos + 1], AR_next, AR_next)
+
+
+def find_groundstate_idmrg1(ost: InfiniteMPS, H, alg: IDMRG1 = None, oenvs=None, log=None):
+    """find_groundstate(ost::InfiniteMPS, H, alg::IDMRG1, oenvs) (idmrg.jl:21-75)"""
+    alg = alg or IDMRG1()
+    oenvs = oenvs or environments(ost, H)
+    ctx, mod, N = ost.ctx, ost.pspace.modulus, ost.N
+    AL, AR, AC, CR = list(ost.AL), list(ost.AR), list(ost.AC), list(ost.CR)
+    envs = IDMRGEnv(ost, oenvs)
+    eps = np.inf
+    for it in range(1, alg.maxiter + 1):
+        Ccur = CR[N - 1]
+        for pos in range(N):                                        # idmrg.jl:35-40
+            h = MPO_ddAC(ctx, H[pos], envs.leftenv(pos), envs.rightenv(pos), AC[pos])
+            _, AC[pos] = fixedpoint(h, AC[pos], "SR", alg.eigalg); h.free()
+            AL[pos], CR[pos] = qrpos(ctx, AC[pos], mod)
+            update_leftenv(envs, AL[pos], H, pos + 1)
+        for pos in range(N - 1, -1, -1):                            # idmrg.jl:43-51
+            h = MPO_ddAC(ctx, H[pos], envs.leftenv(pos), envs.rightenv(pos), AC[pos])
+            _, AC[pos] = fixedpoint(h, AC[pos], "SR", alg.eigalg); h.free()
+            CR[(pos - 1) % N], AR[pos] = lqpos(ctx, AC[pos], mod)
+            update_rightenv(envs, AR[pos], H, pos - 1)
+        d = Ccur.copy(); d.axpy(-1.0, CR[N - 1]); eps = d.norm()
+        if log is not None:
+            log.append(dict(iter=it, eps=eps))
+        if eps < alg.tol:
+            break
+    nst = InfiniteMPS.from_tensors(AR, ost.V, ost.pspace, ctx, tol=alg.tol_gauge)     # idmrg.jl:72
+    nenvs = environments(nst, H)
+    return nst, nenvs, eps

@@ -610,3 +610,22 @@ def test_config1_readme_quickstart_pbc_tfi(ctx):
     print("config1", log_d[-1]["energy"], log_o[-1]["energy"], -2 / np.sin(np.pi / (2 * L)))
     assert abs(log_d[-1]["energy"] - log_o[-1]["energy"]) <= 1e-8 * abs(log_o[-1]["energy"])
     assert abs(log_d[-1]["energy"] - (-2 / np.sin(np.pi / (2 * L)))) < 0.05      # D = 4 variational bound vs the exact ring energy
+
+
+def test_idmrg1_device(ctx):
+    """find_groundstate(psi, H, IDMRG1()) (idmrg.jl:21-75) with the manual IDMRGEnv updates (idmrgenv.jl:63-72): the
+    device run reaches the variational energy logged by the reference for VUMPS at the same bond dimension and agrees
+    with the oracle IDMRG1."""
+    from oracle import infinite as oi
+    from mpskit_b200 import infinite as di
+    Ho = ompo.transverse_field_ising(1, 0.5)
+    psi_o = oi.InfiniteMPS.random(np.random.default_rng(3), OSpace((0,), (2,)), [OSpace((0,), (10,))])
+    st_o, envs_o, eps_o = oi.idmrg1(psi_o, Ho, tol=1e-10, maxiter=200)
+    E_o = oi.expectation_value(st_o, Ho, envs_o).sum().real
+    psi_d = m.InfiniteMPS.random(np.random.default_rng(3), m.Space((0,), (2,)), [m.Space((0,), (10,))], ctx)
+    Hd = dev_hamiltonian(Ho)
+    st_d, envs_d, eps_d = m.find_groundstate_idmrg1(psi_d, Hd, m.IDMRG1(tol=1e-10, maxiter=200))
+    E_d = di.expectation_value(st_d, Hd, envs_d).sum().real
+    print("IDMRG1", E_d, E_o, eps_d, eps_o)
+    assert eps_d < 1e-10
+    assert abs(E_d - E_o) <= 1e-9 and abs(E_d - (-1.063544409973)) <= 1e-9
