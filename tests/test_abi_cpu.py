@@ -99,3 +99,39 @@ def test_bad_spaces_are_rejected_without_a_gpu():
     mc = (C.c_int32 * 1)(0)
     cnt = C.c_int32()
     assert lib.mpsk_block_table(C.byref(bad), 1, mc, C.byref(good), C.byref(cnt), None, None, None) == _lib.ESPACE
+
+
+def test_ac_tuple_setter_bookkeeping_without_gpu():
+    """orthoview.jl:121-143: psi.AC[i] = (al, c) / (c, ar) -- gauge invalidation bookkeeping of the host mirror, exercised
+    on placeholder tensors (no device calls are made on this path)."""
+    import types
+    import mpskit_b200 as m
+    from mpskit_b200.finitemps import FiniteMPS, _View
+
+    def T(mch, Vl="l", Vr="r", bond=False):
+        t = types.SimpleNamespace(mch=tuple(mch), Vl=Vl, Vr=Vr)
+        if bond:
+            t._is_bond = True
+        return t
+    L = 4
+    psi = object.__new__(FiniteMPS)
+    psi.L, psi.pq = L, (-1, 1)
+    psi.V = ["V%d" % i for i in range(L + 1)]
+    psi.ALs = [T((-1, 1)) for _ in range(L)]
+    psi.ARs = [T((-1, 1)) for _ in range(L)]
+    psi.ACs = [T((-1, 1)) for _ in range(L)]
+    psi.CLs = [T((0,), bond=True) for _ in range(L + 1)]
+    psi._views()
+    al, c, ar = T((-1, 1), Vr="new"), T((0,), Vl="new", Vr="new"), T((-1, 1), Vl="new")     # c carries no flag: structural detection
+    keepR = psi.ARs[3]
+    psi.AC[1] = (al, c)
+    assert psi.ALs[1] is al and psi.CLs[2] is c and psi.V[2] == "new"
+    assert psi.ALs[2] is None and psi.ARs[0] is None and psi.ARs[1] is None and psi.ARs[3] is keepR
+    assert all(a is None for a in psi.ACs) and sum(x is not None for x in psi.CLs) == 1
+    psi.ACs[2] = T((-1, 1))            # pretend AC[2] is known so that no lazy gauge is triggered
+    psi.AC[2] = (c, ar)
+    assert psi.ARs[2] is ar and psi.CLs[2] is c and psi.ALs[1] is al and psi.ALs[2] is None
+    import pytest
+    with pytest.raises(ValueError):
+        psi.ACs[2] = T((-1, 1))
+        psi.AC[2] = (al, ar)
