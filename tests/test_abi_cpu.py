@@ -135,3 +135,17 @@ def test_ac_tuple_setter_bookkeeping_without_gpu():
     with pytest.raises(ValueError):
         psi.ACs[2] = T((-1, 1))
         psi.AC[2] = (al, ar)
+
+
+def test_header_is_plain_c99_and_links_from_c(tmp_path):
+    """the boundary is a C ABI: include/mpskit_b200.h must compile as C99 (-pedantic) and link from a plain C program"""
+    import subprocess
+    import mpskit_b200 as m
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "mpskit_b200.h"\nint main(void){ mpsk_ctx* c = 0; return mpsk_version() >= 100 && c == 0 ? 0 : 1; }\n')
+    libdir = os.path.dirname(m.LIB_PATH)
+    exe = tmp_path / "hdr"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                        "-L", libdir, "-lmpskit_b200", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert subprocess.run([str(exe)]).returncode == 0
