@@ -1,11 +1,19 @@
 #!/usr/bin/env python
 """Benchmark of the north-star hot path: the two-site effective-Hamiltonian (ddAC2) matvec of config 3(ii)
-(finite spin-1/2 Heisenberg, U(1), D=4096, range-6 MPO with chi=20), complex128.
+(finite spin-1/2 Heisenberg, U(1), D=4096, range-6 MPO with chi=20), complex128, and the DMRG2 centre
+update built around it.
 
-One step = one matvec y = H_eff x through the C ABI of libmpskit_b200 (3 kernel launches + 2 staging copies).
-`value`: inputs resident in HBM.  `e2e`: host x -> upload -> matvec -> download y inside the timed region.
-`--impl reference`: the CPU oracle port (numpy/OpenBLAS block-sparse restatement in the reference's own
-contraction order) on the box's host cores; Julia is not available so the reference itself cannot run.
+One step = one matvec y = H_eff x through the C ABI of libmpskit_b200.
+  * N = 1: 3 kernel launches (grouped GEMM, mix, grouped GEMM) + 2 staging copies.
+  * N > 1 (strong scaling, one process per GPU): the Krylov vector lives as row panels (rank r owns rows r/N of every
+    sector of the left bond); one step = NCCL allgather of the x panels into the operator input + the rank-local 1/N of
+    the three launches, y stays a panel (exactly the step the sharded eigensolver iterates).
+`value`: inputs resident in HBM.  `e2e`: host buffers -> upload -> matvec -> download inside the timed region (N > 1:
+every rank moves only its own panel).  `dmrg2_sweep`: timed DMRG2 centre updates (ac2 build, environment update, Lanczos
+eigensolve with krylovdim 30 / tol 1e-10, truncated SVD, state update) on all ranks.
+`--impl reference`: the CPU oracle port (numpy/OpenBLAS block-sparse restatement in the reference's own contraction order)
+on the box's host cores with all threads; Julia is not available so the reference itself cannot run.
+`--config 5`: the J1-J2 width-6 cylinder workload (D=8192, chi=32) -- see run_config5.
 """
 import argparse
 import json
@@ -16,11 +24,17 @@ import sys
 import tempfile
 import time
 
+if "--impl" in sys.argv and "reference" in sys.argv:
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm must use every host core (OpenBLAS reads these at import time)
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_k] = str(os.cpu_count() or 1)
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "ddAC2_matvec_fp64_tflops"
 UNIT = "TFLOP/s"
+HBM_PEAK_FALLBACK = 6553.9
 
 
 def parse():
@@ -29,17 +43,66 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--D", type=int, default=4096)
+    ap.add_argument("--config", type=int, default=3, choices=[3, 5])
+    ap.add_argument("--D", type=int, default=None)
     ap.add_argument("--range", type=int, default=6, dest="r")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--sweep-steps", type=int, default=3, help="DMRG2 centre steps timed for the sweep estimate (0: skip)")
-    return ap.parse_args()
+    ap.add_argument("--sweep-steps", type=int, default=3, help="DMRG2 centre updates timed for the sweep figure (0: skip)")
+    ap.add_argument("--sweep-krylovdim", type=int, default=30)
+    ap.add_argument("--sweep-maxiter", type=int, default=3)
+    a = ap.parse_args()
+    if a.D is None:
+        a.D = 4096 if a.config == 3 else 8192
+    return a
 
 
 def workload_name(D, r):
     return (f"config 3(ii): finite spin-1/2 Heisenberg L=100 U(1) DMRG2, centre-bond ddAC2 matvec, D={D}, "
             f"range-{r} MPO chi={2 + 3 * r}, sigma=1.5 sector recipe")
+
+
+def bond_space_dims(D, parity=0, sigma=1.5, qmax=5):
+    """SURVEY.md 8d config 3 recipe (pure python: both arms build the identical config dict from it)"""
+    import math
+    cs = [c for c in range(-2 * qmax, 2 * qmax + 1) if (c % 2) == parity]
+    g = [math.exp(-(c / 2) ** 2 / (2 * sigma ** 2)) for c in cs]
+    tot = sum(g)
+    n = [int(round(D * x / tot)) for x in g]
+    i0 = min(range(len(cs)), key=lambda i: abs(cs[i]))
+    n[i0] += D - sum(n)
+    return {c: k for c, k in zip(cs, n) if k > 0}
+
+
+def algorithmic_flops_cfg3(D, r):
+    """SURVEY.md 8d F_AC2 for the square centre-bond spaces of config 3(ii): optimal-order GEMM flops (complex: kappa = 8)."""
+    q = bond_space_dims(D)
+    qs = [2, -2, 0]
+    cl = [0] + [qs[t] for t in range(3) for _ in range(r)] + [0]
+    mch = [a + b for a in (-1, 1) for b in (-1, 1)]
+    F = 0.0
+    for qb, nb in q.items():
+        MA = sum(q.get(qb + c, 0) for c in cl)
+        NA = sum(q.get(qb + s, 0) for s in mch)
+        F += 8.0 * MA * NA * nb
+    for qa, na in q.items():
+        for s in mch:
+            nz = q.get(qa + s, 0)
+            if not nz:
+                continue
+            K = sum(q.get(qa + s - c, 0) for c in cl)
+            F += 8.0 * nz * na * K
+    return F
+
+
+def config_dict(args):
+    """identical in both arms (the driver compares them)"""
+    n = args.gpus
+    return {"workload": workload_name(args.D, args.r), "D": args.D, "chi": 2 + 3 * args.r,
+            "flops_per_matvec": algorithmic_flops_cfg3(args.D, args.r),
+            "l2": "inputs larger than L2 (x 192 MB, environments 2 x 0.97 GB, intermediates 7.6 GB at D=4096)",
+            "parallelism": "single GPU" if n == 1 else f"{n} GPUs: row panels of the bra index (GL and the Krylov basis sharded), "
+                                                        "1 NCCL allgather of x per matvec"}
 
 
 class ClockSampler:
@@ -87,7 +150,8 @@ class ClockSampler:
         return out
 
 
-def oracle_problem(w, d=2):
+# ------------------------------------------------------------------------------------------------ CPU arm
+def oracle_problem(w):
     """device inputs -> oracle BlockTensors (same numbers) + oracle slice"""
     from oracle.spaces import Space as OSpace
     from oracle.blocks import BlockTensor
@@ -101,6 +165,63 @@ def oracle_problem(w, d=2):
     return conv(w["x"]), conv(w["GL"]), conv(w["GR"]), oh
 
 
+def cpu_problem(D, r, seed=20240213 + 3000):
+    import numpy as np
+    from oracle.spaces import Space as OSpace
+    from oracle.blocks import BlockTensor
+    from oracle import mpo as ompo
+    V = OSpace.from_dict(bond_space_dims(D))
+    h = ompo.heisenberg_longrange_u1(2, r=r)[0]
+    rng = np.random.default_rng(seed)
+    mch = [h.pch[a] + h.pch[b] for a in range(2) for b in range(2)]
+    x = BlockTensor.random(rng, V, mch, V)
+    GL = BlockTensor.random(rng, V, [-c for c in h.cl], V)
+    GR = BlockTensor.random(rng, V, [c for c in h.cr], V)
+    return x, GL, GR, h
+
+
+def run_reference(args):
+    """CPU arm: the oracle port of the reference algorithm, all host threads (OpenBLAS), bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.contract import dAC2_blocks
+    ncores = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(ncores)
+    except Exception:
+        pass
+    # bounded sample: calibrate on a small instance of the same recipe, then take the largest D <= args.D whose
+    # (warmup + steps) matvecs fit in ~150 s of CPU time (cost grows ~ D^3)
+    prob = cpu_problem(512, args.r)
+    dAC2_blocks(prob[0], prob[3], prob[3], prob[1], prob[2])
+    t0 = time.perf_counter()
+    dAC2_blocks(prob[0], prob[3], prob[3], prob[1], prob[2])
+    t512 = time.perf_counter() - t0
+    nrun = args.steps + args.warmup
+    Ds = args.D
+    while Ds > 512 and nrun * t512 * (Ds / 512.0) ** 3 > 150.0:
+        Ds //= 2
+    x, GL, GR, h = cpu_problem(Ds, args.r) if Ds != 512 else prob
+    flops = algorithmic_flops_cfg3(Ds, args.r)
+    for _ in range(args.warmup):
+        dAC2_blocks(x, h, h, GL, GR)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        dAC2_blocks(x, h, h, GL, GR)
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    val = flops / dt / 1e12
+    sample = (f"same workload recipe at D={Ds} (algorithmic flops {flops:.3e} per matvec, {dt:.3f} s each), numpy/OpenBLAS "
+              f"block-sparse port in reference contraction order, {ncores} threads")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "c128", "data": "synthetic", "config": config_dict(args),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": ncores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
 def cpu_matvec_time(x, GL, GR, oh, reps=1):
     from oracle.contract import dAC2_blocks
     best = 1e30
@@ -111,70 +232,21 @@ def cpu_matvec_time(x, GL, GR, oh, reps=1):
     return best, y
 
 
-def run_reference(args):
-    """CPU arm: the oracle port of the reference algorithm, all host threads (OpenBLAS), bounded sample."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    import numpy as np
-    from oracle.spaces import Space as OSpace
-    from oracle.blocks import BlockTensor
-    from oracle import mpo as ompo
-    from oracle.contract import dAC2_blocks
-    sys.path.insert(0, os.path.join(ROOT, "mpskit.jl_b200"))
-    # bounded sample: largest D <= args.D of the same recipe whose (warmup + steps) matvecs fit in ~200 s of CPU time
-    # (measured: 6.6 s per D=4096 matvec on 16 cores, ~cubic in D at these sizes)
-    t4096 = 14.0 * 8.0 / max(os.cpu_count() or 8, 1)
-    Ds = args.D
-    while Ds > 512 and (args.steps + args.warmup) * t4096 * (Ds / 4096.0) ** 3 > 200.0:
-        Ds //= 2
-    cs = [c for c in range(-10, 11) if c % 2 == 0]
-    g = np.array([np.exp(-(c / 2) ** 2 / (2 * 1.5 ** 2)) for c in cs])
-    n = np.rint(Ds * g / g.sum()).astype(int)
-    n[int(np.argmin(np.abs(np.array(cs))))] += Ds - n.sum()
-    V = OSpace.from_dict({c: int(k) for c, k in zip(cs, n) if k > 0})
-    H = ompo.heisenberg_longrange_u1(2, r=args.r)
-    h = H[0]
-    rng = np.random.default_rng(20240213 + 3000)
-    mch = [h.pch[a] + h.pch[b] for a in range(2) for b in range(2)]
-    x = BlockTensor.random(rng, V, mch, V)
-    GL = BlockTensor.random(rng, V, [-c for c in h.cl], V)
-    GR = BlockTensor.random(rng, V, [c for c in h.cr], V)
-    flops = algorithmic_flops(V, h, mch)
-    for _ in range(args.warmup):
-        dAC2_blocks(x, h, h, GL, GR)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        dAC2_blocks(x, h, h, GL, GR)
-    dt = (time.perf_counter() - t0) / max(args.steps, 1)
-    val = flops / dt / 1e12
-    sample = f"same workload recipe at D={Ds} (algorithmic flops {flops:.3e} per matvec), numpy/OpenBLAS block-sparse port in reference contraction order"
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "c128", "data": "synthetic", "config": {"workload": workload_name(args.D, args.r), "sample_D": Ds},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
-            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line))
+# ------------------------------------------------------------------------------------------------ GPU arm
+def hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        return HBM_PEAK_FALLBACK, "fallback 6553.9 GB/s (MEASURED_PEAKS.json absent)"
 
 
-def algorithmic_flops(V, h, mch):
-    """SURVEY.md 8d F_AC2 for square centre-bond spaces: optimal-order GEMM flops (complex: kappa = 8)."""
-    q = dict(zip(V.charges, V.dims))
-    cl = h.cl if hasattr(h, "cl") else h.domcharges
-    cr = h.cr if hasattr(h, "cr") else h.imcharges
-    F = 0.0
-    for qb, nb in q.items():
-        MA = sum(q.get(qb + c, 0) for c in cl)
-        NA = sum(q.get(qb + s, 0) for s in mch)
-        F += 8.0 * MA * NA * nb
-    for qa, na in q.items():
-        for s in mch:
-            nz = q.get(qa + s, 0)
-            if not nz:
-                continue
-            K = sum(q.get(qa + s - c, 0) for c in cr)
-            F += 8.0 * nz * na * K
-    return F
+def ncu_traffic(D, r):
+    """per-matvec DRAM bytes of the GEMM launches from the committed ncu capture (profiles/r02_traffic.json)"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        return t.get(f"D{D}_r{r}"), t.get("source")
+    except Exception:
+        return None, None
 
 
 def main():
@@ -198,28 +270,45 @@ def main():
     stream = torch.cuda.Stream()          # a real (non-default) stream: torch events and the library share it
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
-
-    # N > 1: strong scaling of ONE matvec: rank r owns the r-th row panel of the bra index (mpskit_b200/sharding.py);
-    # GL is sharded, GR and the Krylov vector x are replicated, one NCCL allgather per matvec assembles y everywhere.
-    w = cfg3_matvec(ctx, args.D, r=args.r, build_op=(world == 1))
-    x = w["x"]
-    if world == 1:
-        op = w["op"]
-        flops = op.flops
-    else:
+    if world > 1:
         def bcast(uid):
             box = [uid]
             dist.broadcast_object_list(box, src=0)
             return box[0]
         m.init_communicator(ctx, rank, world, bcast)
-        op = m.MPO_ddAC2(ctx, w["h"], w["h"], w["GL"], w["GR"], x)    # row-panels GL for this rank (derivatives.py)
+    if args.config == 5:
+        from mpskit_b200.config5 import run_config5
+        return run_config5(args, ctx, m, torch, dist, rank, world, local, stream, ClockSampler)
+
+    def allmax(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # N > 1: strong scaling of ONE matvec: rank r owns the r-th row panel of the bra index (mpskit_b200/sharding.py);
+    # GL and the Krylov vectors are sharded, GR is replicated, one NCCL allgather of the x panels per matvec.
+    w = cfg3_matvec(ctx, args.D, r=args.r, build_op=False)
+    x = w["x"]
+    op = m.MPO_ddAC2(ctx, w["h"], w["h"], w["GL"], w["GR"], x)        # N > 1: row-panels GL for this rank (derivatives.py)
+    cfg = config_dict(args)
+    if world == 1:
+        flops = op.flops
+    else:
         w["GL"].free()
         t = torch.tensor([op.flops], device="cuda", dtype=torch.float64)
         dist.all_reduce(t)
         flops = float(t.item())            # sum of the panel flops == flops of the full operator (no redundant work)
-    y = x.zerovector()
+    flops_check = "library flop count == SURVEY.md 8d formula" if abs(flops - cfg["flops_per_matvec"]) <= 1e-9 * flops else \
+        f"MISMATCH: library {flops:.6e} vs SURVEY formula {cfg['flops_per_matvec']:.6e}"
+    xp = m.row_panel(x, rank, world) if world > 1 else x             # this rank's Krylov vector
+    yp = xp.zerovector()
+
+    def step():
+        ctx.check(ctx.lib.mpsk_op_apply_panel(ctx.h, op.h, xp.h, yp.h))
     for _ in range(max(args.warmup, 3)):
-        op.apply_into(x, y)
+        step()
     ctx.synchronize()
     sampler = ClockSampler(local) if rank == 0 else None
     if world > 1:
@@ -229,49 +318,48 @@ def main():
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
-        op.apply_into(x, y)
+        step()
     e1.record(stream)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    ms = e0.elapsed_time(e1) / args.steps
+    ms = allmax(e0.elapsed_time(e1) / args.steps)
     launches = ctx.launch_count() - l0
-    if world > 1:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     clocks = sampler.stop() if sampler else None
     value = flops / (ms * 1e-3) / 1e12             # whole-job: one full matvec per step, whatever the number of ranks
 
-    # per-kernel timing of the dominant kernel (grouped DMMA GEMM): time stage A + stage C launches alone
     e2e = None
     if not args.no_e2e:
-        # every rank holds the (replicated) Krylov vector in pinned host memory: upload, (sharded) matvec, download
-        xb = {k: torch.from_numpy(v).pin_memory().numpy() for k, v in x.to_blocks().items()}   # pinned host blocks
+        # every rank keeps ITS panel of the Krylov vector in pinned host memory: upload it, matvec (allgather inside), download
+        # its panel of y.  Bytes over PCIe per step = |x| in and |y| out summed over the ranks.
+        xb = {k: torch.from_numpy(v).pin_memory().numpy() for k, v in xp.to_blocks().items()}   # pinned host blocks
         yb = {k: torch.from_numpy(np.empty_like(v)).pin_memory().numpy() for k, v in xb.items()}
         bytes_x = sum(b.nbytes for b in xb.values())
+
+        def e2e_step():
+            xd = m.DeviceTensor.from_blocks(ctx, xp.Vl, xp.mch, xp.Vr, xb)
+            ctx.check(ctx.lib.mpsk_op_apply_panel(ctx.h, op.h, xd.h, yp.h))
+            yp.to_blocks(yb)
+            xd.free()
         for _ in range(2):
-            xd = m.DeviceTensor.from_blocks(ctx, x.Vl, x.mch, x.Vr, xb); op.apply_into(xd, y); y.to_blocks(yb); xd.free()
+            e2e_step()
         nrep = max(3, min(args.steps, 10))
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
         for _ in range(nrep):
-            xd = m.DeviceTensor.from_blocks(ctx, x.Vl, x.mch, x.Vr, xb)
-            op.apply_into(xd, y)
-            y.to_blocks(yb)
-            xd.free()
-        dt = (time.perf_counter() - t0) / nrep
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = allmax((time.perf_counter() - t0) / nrep)
+        tb = torch.tensor([float(bytes_x)], device="cuda", dtype=torch.float64)
         if world > 1:
-            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {"value": flops / dt / 1e12, "unit": UNIT, "h2d_bytes_per_step": bytes_x * world, "d2h_bytes_per_step": bytes_x * world,
+            dist.all_reduce(tb)
+        e2e = {"value": flops / dt / 1e12, "unit": UNIT, "h2d_bytes_per_step": int(tb.item()), "d2h_bytes_per_step": int(tb.item()),
                "ms_per_step": dt * 1e3}
 
-    # roofline denominator: FP64 tensor (DMMA) peak is not in MEASURED_PEAKS.json -> measure cuBLAS zgemm live
-    roofline = None
+    # roofline of the dominant kernel (grouped DMMA GEMM): FP64 tensor peak is not in MEASURED_PEAKS.json -> cuBLAS zgemm live
+    roofline = None; roofline_mix = None
     if rank == 0 and world == 1:
         n = 4096
         a = torch.randn(n, n, dtype=torch.complex128, device="cuda"); b = torch.randn(n, n, dtype=torch.complex128, device="cuda")
@@ -283,24 +371,30 @@ def main():
             best = min(best, s0.elapsed_time(s1))
         peak = 8.0 * n ** 3 / (best * 1e-3) / 1e12
         del a, b
-        # the two GEMM launches carry all the algorithmic flops; time them in isolation over the same inputs
-        gm = gemm_only_ms(ctx, op, x, y, stream, torch, max(3, min(args.steps, 10))) if world == 1 else float("nan")
+        reps = max(3, min(args.steps, 10))
+        gm = gemm_only_ms(ctx, op, reps)
+        traffic, tsrc = ncu_traffic(args.D, args.r)
         roofline = {"bound": "tensor", "kernel": "gemm_dmma_kernel<complex> (stage A + stage C of one matvec)",
                     "achieved": flops / (gm * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
-                    "frac": flops / (gm * 1e-3) / 1e12 / peak,
-                    "traffic": 55.85e9 if (args.D == 4096 and args.r == 6) else None,
-                    "traffic_source": "ncu dram__bytes_read+write per matvec (stage A 42.89+3.56 GB, stage C 9.21+0.19 GB), profiles/r01_SUMMARY.md; algorithmic operand bytes 10.6 GB",
-                    "peak_source": "live torch.matmul complex128 4096^3 (cuBLAS zgemm) on this GPU; DMMA microbenchmark "
-                                   "profiles/r01_peak_fp64_microbench.json gives 36.99; MEASURED_PEAKS.json has no FP64 entry",
+                    "frac": flops / (gm * 1e-3) / 1e12 / peak, "traffic": traffic, "traffic_source": tsrc,
+                    "peak_source": "builder-measured: live torch.matmul complex128 4096^3 (cuBLAS zgemm) on this GPU in this run; DMMA "
+                                   "issue microbenchmark profiles/r01_peak_fp64_microbench.json gives 36.99; MEASURED_PEAKS.json has no FP64 entry",
                     "gemm_ms_per_matvec": gm, "share_of_step": gm / ms}
+        mm, mb = mix_only_ms(ctx, op, reps)
+        hp, hsrc = hbm_peak()
+        roofline_mix = {"bound": "hbm", "kernel": "mix_kernel<double2>", "achieved": mb / (mm * 1e-3) / 1e9, "peak": hp, "unit": "GB/s",
+                        "frac": mb / (mm * 1e-3) / 1e9 / hp, "bytes_per_launch": mb, "ms": mm, "peak_source": hsrc}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         try:
+            y = x.zerovector()
+            op.apply_into(x, y)
             ox, oGL, oGR, oh = oracle_problem(w)
             t, yo = cpu_matvec_time(ox, oGL, oGR, oh)
             yd = y.to_blocks()
             err = max(float(np.abs(yd[k] - v).max()) for k, v in yo.blocks.items()) / max(float(np.abs(v).max()) for v in yo.blocks.values())
+            y.free()
             cpu = {"value": flops / t / 1e12, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                    "sample": f"one full-size matvec of the same inputs ({t:.1f} s), numpy/OpenBLAS block-sparse port in the reference's "
                              f"contraction order; max rel. deviation GPU vs CPU {err:.2e}"}
@@ -308,80 +402,101 @@ def main():
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc!r}"}
 
     sweep = None
-    if rank == 0 and world == 1 and args.sweep_steps > 0:
-        for t in (w.get("op"), w.get("GL"), w.get("GR")):
-            if t is not None:
-                t.free()
+    if args.sweep_steps > 0:
+        for t in (op, w.get("GL"), w.get("GR"), xp, yp, x):
+            try:
+                if t is not None:
+                    t.free()
+            except Exception:
+                pass
         try:
-            sweep = sweep_window(ctx, m, args.D, args.r, args.sweep_steps)
+            sweep = sweep_window(ctx, m, args, world, allmax)
         except Exception as exc:       # secondary measurement: report the failure, keep the headline line
+            if world > 1:
+                raise                  # a rank that drops out of the collectives would hang the others
             sweep = {"error": repr(exc)}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "c128",
-                "data": "synthetic",
-                "config": {"workload": workload_name(args.D, args.r), "D": args.D, "chi": 2 + 3 * args.r, "flops_per_matvec": flops,
-                           "l2": "inputs larger than L2 (x 192 MB, environments 2 x 0.97 GB, intermediates 7.6 GB)",
-                           "parallelism": "single GPU" if world == 1 else f"{world} GPUs: row panels of the bra index, GL sharded, 1 NCCL allgather of y per matvec"},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "dmrg2_sweep": sweep}
+                "data": "synthetic", "config": cfg, "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+                "roofline_mix": roofline_mix, "cpu_baseline": cpu, "dmrg2_sweep": sweep, "flops_check": flops_check}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def sweep_window(ctx, m, D, r, nsteps):
-    """DMRG2 sweep-time estimate: `nsteps` consecutive two-site updates at the centre of an L=36 chain of the same
-    recipe (full bond dimension D there), each = ac2 build + environment update + Lanczos eigsolve (krylovdim 15, one
-    cycle) + truncated SVD + state update; extrapolated to the 197 updates of a full L=100 sweep by the measured
-    full-sweep profile (profiles/r01_full_sweep_D4096*.json: 150 of 197 updates run at full D)."""
+def sweep_window(ctx, m, args, world, allmax):
+    """DMRG2 sweep figure: `sweep_steps` consecutive two-site updates at the centre of an L=36 chain of the same recipe
+    (full bond dimension D there), each = ac2 build + environment update + operator plans + Lanczos eigensolve
+    (krylovdim 30, tol 1e-10, thick restarts) + truncated SVD + state update; all ranks take part (sharded
+    matvec / Krylov basis / environment updates / SVD sectors).  The L=100 figure extrapolates with the measured profile of
+    a full sweep (profiles/r01_full_sweep_D4096*.json: 150 of 197 updates run at full D, edge updates ~6 % of a centre one)."""
     import warnings
     import numpy as np
     from mpskit_b200.workloads import gaussian_bond_space
     from mpskit_b200 import dmrg as dm
+    D, r, nsteps = args.D, args.r, args.sweep_steps
     L = 36
     p = m.Space((-1, 1), (1, 1))
     H = m.heisenberg_longrange_u1(L, r=r)
     psi = m.FiniteMPS.random(20240213 + 3000, p, L, [gaussian_bond_space(D, k % 2) for k in range(1, L)], ctx, on_device=True)
     envs = m.environments(psi, H)
-    alg = m.Lanczos(tol=1e-10, krylovdim=15, maxiter=1)
+    alg = m.Lanczos(tol=1e-10, krylovdim=args.sweep_krylovdim, maxiter=args.sweep_maxiter)
     pos0 = L // 2 - nsteps // 2
     envs.leftenv(pos0, psi); envs.rightenv(pos0 + 1, psi)
-    # one untimed step absorbs cuSOLVER / allocator warm-up
-    times, matvecs = [], 0
+    names = ("ac2", "env_op", "eigsolve", "tsvd", "update")
+    phases = {k: 0.0 for k in names}
+    times, matvecs, conv, energies, flops_mv = [], 0, 0, [], 0.0
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        for step in range(nsteps + 1):
+        for step in range(nsteps + 1):      # one untimed update absorbs cuSOLVER / allocator warm-up
             pos = pos0 - 1 + step
             ctx.synchronize(); t0 = time.perf_counter()
             ac2 = dm.contract_ac2(psi, psi.AC[pos], psi.AR[pos + 1])
+            ctx.synchronize(); t1 = time.perf_counter()
             h = m.ddAC2(pos, psi, H, envs, ac2)
+            ctx.synchronize(); t2 = time.perf_counter()
             val, new, info = m.fixedpoint(h, ac2, "SR", alg, return_info=True)
+            ctx.synchronize(); t3 = time.perf_counter()
+            fl = h.flops
             h.free()
             al, c, ar, eps = dm.tsvd(psi, new, m.truncdim(D))
+            ctx.synchronize(); t4 = time.perf_counter()
             psi.AC[pos] = (al, c); psi.AC[pos + 1] = (c, ar)
             ac2.free(); new.free(); envs.drop_stale(psi)
-            ctx.synchronize()
+            ctx.synchronize(); t5 = time.perf_counter()
             if step > 0:
-                times.append(time.perf_counter() - t0); matvecs += info["numops"]
-    per = float(np.mean(times))
-    return {"seconds_per_centre_update": per, "matvecs_per_update": matvecs / len(times), "timed_updates": len(times),
+                times.append(t5 - t0); matvecs += info["numops"]; conv += int(info["converged"]); energies.append(val.real)
+                flops_mv += fl * info["numops"]
+                for k, dt in zip(names, (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4)):
+                    phases[k] += dt
+    per = allmax(float(np.mean(times)))
+    n = len(times)
+    eig = allmax(phases["eigsolve"] / n)
+    return {"seconds_per_centre_update": per, "matvecs_per_update": matvecs / n, "converged_updates": conv, "timed_updates": n,
+            "krylovdim": args.sweep_krylovdim, "tol": 1e-10, "maxiter": args.sweep_maxiter,
+            "phase_seconds_per_update": {k: v / n for k, v in phases.items()},
+            "non_eigsolve_share": 1.0 - eig / per, "energies": energies,
+            "eigsolve_tflops": flops_mv * world / max(phases["eigsolve"], 1e-30) / 1e12 if world > 1 else flops_mv / max(phases["eigsolve"], 1e-30) / 1e12,
             "estimated_sweep_seconds_L100": per * 150 + 0.06 * per * 47,
             "note": "estimate = 150 full-D updates + 47 edge updates (~6 % of a centre update each, from the measured full sweep); "
-                    "measured full sweeps are in profiles/"}
+                    "per-update time is the max over ranks of the mean over the timed updates"}
 
 
-def gemm_only_ms(ctx, op, x, y, stream, torch, reps):
-    """average duration of the GEMM launches of one matvec (CUDA events on the launching stream)."""
+def gemm_only_ms(ctx, op, reps):
+    """average duration of the GEMM launches of one matvec (CUDA events on the launching stream, inside the library)."""
     import ctypes as C
-    lib = ctx.lib
-    if not hasattr(lib, "mpsk_op_time_gemms"):
-        return float("nan")
-    lib.mpsk_op_time_gemms.restype = C.c_int32
-    lib.mpsk_op_time_gemms.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_double)]
     out = C.c_double()
-    ctx.check(lib.mpsk_op_time_gemms(ctx.h, op.h, reps, C.byref(out)))
+    ctx.check(ctx.lib.mpsk_op_time_gemms(ctx.h, op.h, reps, C.byref(out)))
     return out.value
+
+
+def mix_only_ms(ctx, op, reps):
+    import ctypes as C
+    ms, by = C.c_double(), C.c_double()
+    ctx.check(ctx.lib.mpsk_op_time_mix(ctx.h, op.h, reps, C.byref(ms), C.byref(by)))
+    return ms.value, by.value
 
 
 if __name__ == "__main__":

@@ -4,8 +4,10 @@
  * Every entry point below names the reference method (file:line under the reference tree) that a
  * thin `ccall` shim overloads with it (INTEGRATION.md shows the shim).  Plain pointers and sizes
  * only; no exceptions cross the boundary; every function returns an mpsk_status (0 = ok, <0 error)
- * and `mpsk_last_error` gives the message.  Thread safety: a context is used by one thread at a
- * time (create one per Julia task / per rank); distinct contexts are independent.
+ * and `mpsk_last_error` gives the message.  Thread safety: every entry point locks its context, so
+ * calls from concurrent host threads / Julia tasks (vumps.jl:39-45, mpohaminfenv.jl:65-68) on the
+ * same context serialise; distinct contexts are independent and may live on different devices (each
+ * call selects the context's device).  Handles are freed through the context that created them.
  *
  * Data model (TensorKit abelian block structure).  All tensors on the path are of
  * the generic three-leg form  T[l, m, r]  with graded bond spaces l, r and a flat label set m whose
@@ -50,9 +52,10 @@ enum { MPSK_NOTRUNC = 0, MPSK_TRUNCDIM = 1, MPSK_TRUNCERR = 2, MPSK_TRUNCBELOW =
 enum { MPSK_OP_DC = 0, MPSK_OP_DAC = 1, MPSK_OP_DAC2 = 2 };
 #define MPSK_OP_SHARDED 0x100   /* OR into `kind`: GL is this rank's row panel; apply/eigsolve/expv allgather the panels of y */
 
-#define MPSK_FLAG_EXACT_SVD 2ull      /* tsvd: cuSOLVER gesvd for every sector (default: Gram + heevd + QR route for sectors >= 256) */
+#define MPSK_FLAG_EXACT_SVD 2ull      /* tsvd: cuSOLVER gesvd for every sector (default: multi-level Gram + heevd + QR route for sectors >= 256) */
 #define MPSK_FLAG_FAST_SVD_ALL 4ull   /* tsvd: Gram route for every sector (tests) */
 #define MPSK_FLAG_DEBUG_GEMM 1ull  /* route contractions through the one-thread-per-element cross-check kernel (tests only) */
+#define MPSK_FLAG_REPLICATE_LOCAL 8ull /* with a communicator: keep environment updates and tsvd replicated per rank (default: distributed) */
 
 typedef struct { int32_t nsec; const int32_t* charge; const int64_t* dim; int32_t modulus; } mpsk_space;
 typedef struct { const void* ptr; int64_t stride_l; int64_t stride_r; } mpsk_blockref;   /* strides in scalar elements */
@@ -106,6 +109,10 @@ int32_t mpsk_scale(mpsk_ctx* ctx, double a_re, double a_im, mpsk_tensor* x);
 int32_t mpsk_mposlice_create(mpsk_ctx* ctx, int32_t odim, const int32_t* level_charge_left, const int32_t* level_charge_right,
                              int32_t d, const int32_t* phys_charge, const int32_t* kind, const double* scal,
                              const double* ops, mpsk_mposlice** out);
+/* same for a Z_N-graded slice: charges are compared modulo `modulus` (0 = U(1) / trivial) */
+int32_t mpsk_mposlice_create_zn(mpsk_ctx* ctx, int32_t odim, const int32_t* level_charge_left, const int32_t* level_charge_right,
+                                int32_t d, const int32_t* phys_charge, const int32_t* kind, const double* scal,
+                                const double* ops, int32_t modulus, mpsk_mposlice** out);
 void mpsk_mposlice_free(mpsk_ctx* ctx, mpsk_mposlice* s);
 /* keys(x) (sparseslice.jl:74-76), first index fastest; returns count, fills (i,j) pairs if non-NULL */
 int32_t mpsk_mposlice_keys(const mpsk_mposlice* s, int32_t* count, int32_t* ij);
@@ -119,15 +126,33 @@ void mpsk_op_free(mpsk_ctx* ctx, mpsk_op* op);
 double mpsk_op_flops(const mpsk_op* op);                           /* algorithmic real flops of one apply */
 /* measurement hook: mean device time (ms) of the grouped-GEMM launches of one apply (CUDA events on the context stream) */
 int32_t mpsk_op_time_gemms(mpsk_ctx* ctx, const mpsk_op* op, int32_t reps, double* ms_out);
-/* y = h(x): dC / dAC / dAC2 (derivatives.jl:77-197). */
+/* same for the memory-bound "mix" launch; bytes_out = its algorithmic bytes (16 B x rectangle elements x (terms + 1)) */
+int32_t mpsk_op_time_mix(mpsk_ctx* ctx, const mpsk_op* op, int32_t reps, double* ms_out, double* bytes_out);
+/* y = h(x): dC / dAC / dAC2 (derivatives.jl:77-197), or tm * v / v * tm for a transfer-matrix operator. */
 int32_t mpsk_op_apply(mpsk_ctx* ctx, const mpsk_op* op, const mpsk_tensor* x, mpsk_tensor* y);
-/* fixedpoint(h, x0, which, alg) (src/algorithms/fixedpoint.jl:9-30): Krylov eigensolve on the device. */
+/* fixedpoint(h, x0, which, alg) (src/algorithms/fixedpoint.jl:9-30): Krylov eigensolve on the device.
+ * hermitian != 0: Lanczos with full re-orthogonalisation and thick restarts (KrylovKit.Lanczos);
+ * hermitian == 0: Arnoldi with Krylov-Schur restarts (KrylovKit.Arnoldi = Defaults.eigsolver, defaults.jl:33).
+ * Both test convergence after every expansion step (eager = true). */
 int32_t mpsk_eigsolve(mpsk_ctx* ctx, const mpsk_op* op, const mpsk_tensor* x0, int32_t which, int32_t hermitian,
                       int32_t krylovdim, int32_t maxiter, double tol, double* val_re, double* val_im,
                       mpsk_tensor* vec, mpsk_info* info);
 /* integrate -> exponentiate(h, tau, y0) (src/algorithms/timestep/integrators.jl:20-25): y = exp(tau h) y0 */
 int32_t mpsk_expv(mpsk_ctx* ctx, const mpsk_op* op, double tau_re, double tau_im, const mpsk_tensor* y0,
                   int32_t krylovdim, int32_t maxiter, double tol, mpsk_tensor* y, mpsk_info* info);
+
+/* linsolve(f, b, x0, GMRES(tol, krylovdim, maxiter), a0, a1): solve (a0 + a1 f) x = b with restarted GMRES
+ * (src/environments/mpohaminfenv.jl:95,113,146,164; tol is absolute on the residual norm). */
+int32_t mpsk_linsolve(mpsk_ctx* ctx, const mpsk_op* op, const mpsk_tensor* b, const mpsk_tensor* x0, double a0_re, double a0_im,
+                      double a1_re, double a1_im, int32_t krylovdim, int32_t maxiter, double tol, mpsk_tensor* x, mpsk_info* info);
+/* TransferMatrix(above, middle, below) over a unit cell of `nsites` sites as an operator handle (transfermatrix.jl:4-66):
+ * left != 0: v -> v * tm (sites 0 .. n-1), else v -> tm * v (sites n-1 .. 0).  slices == NULL or slices[i] == NULL: MPO-free
+ * transfer (transfer.jl:18-45).  With lvec_adj / rvec the operator is regularised (transfermatrix.jl:68-76):
+ * v -> T(v) - <lvec_adj, T(v)> rvec, lvec_adj being adjoint(lvec) in the vector space.  Plans, TMA descriptors and workspaces are
+ * built once; the handle works with mpsk_op_apply, mpsk_eigsolve (hermitian = 0) and mpsk_linsolve, and is freed by mpsk_op_free. */
+int32_t mpsk_tmop_create(mpsk_ctx* ctx, int32_t left, int32_t nsites, const mpsk_mposlice* const* slices, const mpsk_tensor* const* A,
+                         const mpsk_tensor* const* Abar, const mpsk_tensor* v_like, const mpsk_tensor* lvec_adj, const mpsk_tensor* rvec,
+                         mpsk_op** out);
 
 /* ---- transfer matrices / environment updates (src/transfermatrix/transfer.jl:137-259,
  *      src/environments/FinEnv.jl:114-145) --------------------------------------------------------- */
@@ -164,6 +189,22 @@ int32_t mpsk_allreduce_sum(mpsk_ctx* ctx, mpsk_tensor* x);        /* partial-sum
 int32_t mpsk_tensor_row_panel(mpsk_ctx* ctx, const mpsk_tensor* t, int32_t rank, int32_t nranks, mpsk_tensor** out);
 int32_t mpsk_tensor_scatter_panel(mpsk_ctx* ctx, const mpsk_tensor* panel, int32_t rank, int32_t nranks, mpsk_tensor* full);
 int32_t mpsk_op_apply_local(mpsk_ctx* ctx, const mpsk_op* op, const mpsk_tensor* x, mpsk_tensor* y_panel);
+/* panel in -> panel out: allgathers the row panels of x into the operator's input (NCCL), then the local matvec.  This is the
+ * step the sharded Krylov solvers iterate: basis vectors, inner products (partial sums + one fused allreduce of the step's
+ * scalars) and axpys are 1/N per rank. */
+int32_t mpsk_op_apply_panel(mpsk_ctx* ctx, const mpsk_op* op, const mpsk_tensor* x_panel, mpsk_tensor* y_panel);
+/* panel over the left (axis 0) or right (axis 1) bond index; mpsk_tensor_row_panel == axis 0 */
+int32_t mpsk_tensor_panel(mpsk_ctx* ctx, const mpsk_tensor* t, int32_t axis, int32_t rank, int32_t nranks, mpsk_tensor** out);
+/* every rank passes its axis-0 panel; `full` (pre-allocated, same structure on all ranks) receives the whole tensor.  Stored
+ * environments are kept as panels (1/N of the memory per rank) and re-assembled when they become the active GL / GR.
+ * With a communicator, mpsk_transfer_left/right shard the update over the ket index of the new environment and mpsk_tsvd
+ * distributes the coupled sectors over the ranks; both return complete, bit-identical tensors on every rank. */
+int32_t mpsk_tensor_allgather(mpsk_ctx* ctx, const mpsk_tensor* panel, mpsk_tensor* full);
+
+/* ---- host-only numerical helper (exposed for the CPU test-suite) ------------------------------------ */
+/* complex Schur decomposition H = Z T Z^H used by the Krylov-Schur eigensolver; H, Z: n x n column-major interleaved complex;
+ * if 0 <= move_to <= move_from < n the eigenvalue at position move_from is moved to move_to afterwards. */
+int32_t mpsk_host_schur(int32_t n, double* H, double* Z, int32_t move_from, int32_t move_to);
 
 #ifdef __cplusplus
 }

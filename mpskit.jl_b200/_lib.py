@@ -12,7 +12,8 @@ F64, C128 = 0, 1
 SR, LM, LR = 0, 1, 2
 NOTRUNC, TRUNCDIM, TRUNCERR, TRUNCBELOW = 0, 1, 2, 3
 OP_DC, OP_DAC, OP_DAC2 = 0, 1, 2
-FLAG_DEBUG_GEMM = 1
+FLAG_DEBUG_GEMM, FLAG_EXACT_SVD, FLAG_FAST_SVD_ALL, FLAG_REPLICATE_LOCAL = 1, 2, 4, 8
+OP_SHARDED = 0x100
 
 
 class MpskError(RuntimeError):
@@ -75,15 +76,20 @@ PROTOTYPES = {
     "mpsk_axpy": (C.c_int32, [_P, C.c_double, C.c_double, _P, _P]),
     "mpsk_scale": (C.c_int32, [_P, C.c_double, C.c_double, _P]),
     "mpsk_mposlice_create": (C.c_int32, [_P, C.c_int32, _I32P, _I32P, C.c_int32, _I32P, _I32P, _DP, _DP, _PP]),
+    "mpsk_mposlice_create_zn": (C.c_int32, [_P, C.c_int32, _I32P, _I32P, C.c_int32, _I32P, _I32P, _DP, _DP, C.c_int32, _PP]),
     "mpsk_mposlice_free": (None, [_P, _P]),
     "mpsk_mposlice_keys": (C.c_int32, [_P, _I32P, _I32P]),
     "mpsk_op_create": (C.c_int32, [_P, C.c_int32, _P, _P, _P, _P, _P, _PP]),
     "mpsk_op_free": (None, [_P, _P]),
     "mpsk_op_flops": (C.c_double, [_P]),
     "mpsk_op_time_gemms": (C.c_int32, [_P, _P, C.c_int32, _DP]),
+    "mpsk_op_time_mix": (C.c_int32, [_P, _P, C.c_int32, _DP, _DP]),
     "mpsk_op_apply": (C.c_int32, [_P, _P, _P, _P]),
     "mpsk_eigsolve": (C.c_int32, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, _DP, _DP, _P, C.POINTER(c_info)]),
     "mpsk_expv": (C.c_int32, [_P, _P, C.c_double, C.c_double, _P, C.c_int32, C.c_int32, C.c_double, _P, C.POINTER(c_info)]),
+    "mpsk_linsolve": (C.c_int32, [_P, _P, _P, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_double, _P,
+                                  C.POINTER(c_info)]),
+    "mpsk_tmop_create": (C.c_int32, [_P, C.c_int32, C.c_int32, _PP, _PP, _PP, _P, _P, _P, _PP]),
     "mpsk_transfer_left": (C.c_int32, [_P, _P, _P, _P, _P, _PP]),
     "mpsk_transfer_right": (C.c_int32, [_P, _P, _P, _P, _P, _PP]),
     "mpsk_contract_ac2": (C.c_int32, [_P, _P, _P, _PP]),
@@ -99,6 +105,10 @@ PROTOTYPES = {
     "mpsk_tensor_row_panel": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, _PP]),
     "mpsk_tensor_scatter_panel": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, _P]),
     "mpsk_op_apply_local": (C.c_int32, [_P, _P, _P, _P]),
+    "mpsk_op_apply_panel": (C.c_int32, [_P, _P, _P, _P]),
+    "mpsk_tensor_panel": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _PP]),
+    "mpsk_tensor_allgather": (C.c_int32, [_P, _P, _P]),
+    "mpsk_host_schur": (C.c_int32, [C.c_int32, _DP, _DP, C.c_int32, C.c_int32]),
 }
 
 _lib = None

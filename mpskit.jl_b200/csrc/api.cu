@@ -6,6 +6,10 @@
 using namespace mpsk;
 
 #define CTX(c) (reinterpret_cast<Ctx*>(c))
+// every ABI entry that touches a context serialises on it and selects its device (contexts are thread-safe; calls from
+// concurrent host threads / Julia tasks on the SAME context run one after the other)
+#define ENTER(c) std::lock_guard<std::recursive_mutex> _lock(CTX(c)->mu); cudaSetDevice(CTX(c)->device)
+#define OPH(o) (const_cast<LinOp*>(reinterpret_cast<const LinOp*>(o)))
 #define TEN(t) (reinterpret_cast<Tensor*>(t))
 #define CTEN(t) (reinterpret_cast<const Tensor*>(t))
 #define SLICE(s) (reinterpret_cast<const MpoSlice*>(s))
@@ -21,9 +25,15 @@ static void unpack_block(T* dst, const T* src, int64_t nl, int64_t nr, int64_t s
 }
 
 
+static void* nccl_lib() {
+  static void* lib = nullptr;
+  if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  return lib;
+}
+
 extern "C" {
 
-int32_t mpsk_version(void) { return 100; }
+int32_t mpsk_version(void) { return 200; }
 
 int32_t mpsk_create(int32_t device, uint64_t flags, mpsk_ctx** out) {
   if (!out) return MPSK_EINVAL;
@@ -48,7 +58,15 @@ void mpsk_destroy(mpsk_ctx* ctx) {
   Ctx* c = CTX(ctx);
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  pool_destroy(c);
+  if (c->nccl) {
+    typedef int (*pfn_destroy)(void*);
+    pfn_destroy f = (pfn_destroy)dlsym(nccl_lib(), "ncclCommDestroy");
+    if (f) f(c->nccl);
+    c->nccl = nullptr;
+  }
   if (c->d_scratch) c->free(c->d_scratch);
+  if (c->h_arena) cudaFreeHost(c->h_arena);
   c->release_cache();
   for (auto& kv : c->sizes) cudaFree(kv.first);
   if (c->h_scratch) cudaFreeHost(c->h_scratch);
@@ -59,14 +77,14 @@ void mpsk_destroy(mpsk_ctx* ctx) {
 
 const char* mpsk_last_error(const mpsk_ctx* ctx) { return ctx ? reinterpret_cast<const Ctx*>(ctx)->err.c_str() : "null context"; }
 
-int32_t mpsk_set_stream(mpsk_ctx* ctx, void* s) {
+int32_t mpsk_set_stream(mpsk_ctx* ctx, void* s) { ENTER(ctx);
   Ctx* c = CTX(ctx);
   cudaStreamSynchronize(c->stream);
   c->stream = s ? (cudaStream_t)s : c->own_stream;
   return MPSK_OK;
 }
 
-int32_t mpsk_synchronize(mpsk_ctx* ctx) { Ctx* c = CTX(ctx); CUDA_TRY(c, cudaStreamSynchronize(c->stream)); return MPSK_OK; }
+int32_t mpsk_synchronize(mpsk_ctx* ctx) { ENTER(ctx); Ctx* c = CTX(ctx); CUDA_TRY(c, cudaStreamSynchronize(c->stream)); return MPSK_OK; }
 int64_t mpsk_launch_count(const mpsk_ctx* ctx) { return reinterpret_cast<const Ctx*>(ctx)->launches; }
 int64_t mpsk_bytes_in_use(const mpsk_ctx* ctx) { return reinterpret_cast<const Ctx*>(ctx)->bytes_in_use; }
 
@@ -95,7 +113,7 @@ int32_t mpsk_block_table(const mpsk_space* Vl, int32_t nm, const int32_t* mcharg
 }
 
 int32_t mpsk_tensor_zeros(mpsk_ctx* ctx, const mpsk_space* Vl, int32_t nm, const int32_t* mcharge, const mpsk_space* Vr, int32_t dtype,
-                          mpsk_tensor** out) {
+                          mpsk_tensor** out) { ENTER(ctx);
   Ctx* c = CTX(ctx); Space l, r;
   if (dtype != MPSK_F64 && dtype != MPSK_C128) return c->fail(MPSK_EINVAL, "bad dtype");
   MPSK_TRY(spaces_from_abi(c, Vl, Vr, &l, &r));
@@ -120,7 +138,7 @@ static void* pinned_stage(Ctx* c, size_t bytes) {
 }
 
 int32_t mpsk_tensor_upload(mpsk_ctx* ctx, const mpsk_space* Vl, int32_t nm, const int32_t* mcharge, const mpsk_space* Vr, int32_t dtype,
-                           const mpsk_blockref* blocks, int32_t nblocks, mpsk_tensor** out) {
+                           const mpsk_blockref* blocks, int32_t nblocks, mpsk_tensor** out) { ENTER(ctx);
   Ctx* c = CTX(ctx);
   mpsk_tensor* th = nullptr;
   MPSK_TRY(mpsk_tensor_zeros(ctx, Vl, nm, mcharge, Vr, dtype, &th));
@@ -171,7 +189,7 @@ int32_t mpsk_tensor_upload(mpsk_ctx* ctx, const mpsk_space* Vl, int32_t nm, cons
   return MPSK_OK;
 }
 
-int32_t mpsk_tensor_download(mpsk_ctx* ctx, const mpsk_tensor* th, const mpsk_blockref_mut* blocks, int32_t nblocks) {
+int32_t mpsk_tensor_download(mpsk_ctx* ctx, const mpsk_tensor* th, const mpsk_blockref_mut* blocks, int32_t nblocks) { ENTER(ctx);
   Ctx* c = CTX(ctx); const Tensor* t = CTEN(th);
   if ((int)t->blks.size() != nblocks) return c->fail(MPSK_ESPACE, "download: %d blocks given, structure has %zu", nblocks, t->blks.size());
   const size_t es = t->esize();
@@ -224,7 +242,7 @@ int32_t mpsk_tensor_download(mpsk_ctx* ctx, const mpsk_tensor* th, const mpsk_bl
   return MPSK_OK;
 }
 
-int32_t mpsk_tensor_stack_labels(mpsk_ctx* ctx, const mpsk_tensor* const* ts, int32_t n, mpsk_tensor** out) {
+int32_t mpsk_tensor_stack_labels(mpsk_ctx* ctx, const mpsk_tensor* const* ts, int32_t n, mpsk_tensor** out) { ENTER(ctx);
   std::vector<const Tensor*> v;
   for (int i = 0; i < n; ++i) v.push_back(CTEN(ts[i]));
   Tensor* o = nullptr;
@@ -232,22 +250,22 @@ int32_t mpsk_tensor_stack_labels(mpsk_ctx* ctx, const mpsk_tensor* const* ts, in
   *out = reinterpret_cast<mpsk_tensor*>(o);
   return MPSK_OK;
 }
-int32_t mpsk_tensor_select_labels(mpsk_ctx* ctx, const mpsk_tensor* t, const int32_t* labels, int32_t n, mpsk_tensor** out) {
+int32_t mpsk_tensor_select_labels(mpsk_ctx* ctx, const mpsk_tensor* t, const int32_t* labels, int32_t n, mpsk_tensor** out) { ENTER(ctx);
   Tensor* o = nullptr;
   MPSK_TRY(tensor_select_labels(CTX(ctx), CTEN(t), labels, n, &o));
   *out = reinterpret_cast<mpsk_tensor*>(o);
   return MPSK_OK;
 }
-int32_t mpsk_tensor_adjoint(mpsk_ctx* ctx, const mpsk_tensor* t, mpsk_tensor** out) {
+int32_t mpsk_tensor_adjoint(mpsk_ctx* ctx, const mpsk_tensor* t, mpsk_tensor** out) { ENTER(ctx);
   Tensor* o = nullptr;
   MPSK_TRY(tensor_adjoint(CTX(ctx), CTEN(t), &o));
   *out = reinterpret_cast<mpsk_tensor*>(o);
   return MPSK_OK;
 }
 
-int32_t mpsk_tensor_fill_random(mpsk_ctx* ctx, mpsk_tensor* t, uint64_t seed) { return tensor_fill_random(CTX(ctx), TEN(t), seed); }
+int32_t mpsk_tensor_fill_random(mpsk_ctx* ctx, mpsk_tensor* t, uint64_t seed) { ENTER(ctx); return tensor_fill_random(CTX(ctx), TEN(t), seed); }
 
-int32_t mpsk_tensor_copy(mpsk_ctx* ctx, const mpsk_tensor* th, mpsk_tensor** out) {
+int32_t mpsk_tensor_copy(mpsk_ctx* ctx, const mpsk_tensor* th, mpsk_tensor** out) { ENTER(ctx);
   Ctx* c = CTX(ctx); const Tensor* t = CTEN(th);
   Tensor* n = nullptr;
   MPSK_TRY(tensor_repack(c, t, F_KL, false, &n));
@@ -255,7 +273,7 @@ int32_t mpsk_tensor_copy(mpsk_ctx* ctx, const mpsk_tensor* th, mpsk_tensor** out
   return MPSK_OK;
 }
 
-void mpsk_tensor_free(mpsk_ctx*, mpsk_tensor* t) { delete TEN(t); }
+void mpsk_tensor_free(mpsk_ctx* ctx, mpsk_tensor* t) { if (!t) return; if (ctx) { ENTER(ctx); delete TEN(t); } else delete TEN(t); }
 
 int32_t mpsk_tensor_structure(const mpsk_tensor* th, int32_t* nsec_l, int32_t* nsec_r, int32_t* nm, int32_t* dtype) {
   const Tensor* t = CTEN(th);
@@ -281,7 +299,7 @@ static int check_pair(Ctx* c, const Tensor* x, const Tensor* y) {
   return MPSK_OK;
 }
 
-int32_t mpsk_dot(mpsk_ctx* ctx, const mpsk_tensor* xh, const mpsk_tensor* yh, double* re, double* im) {
+int32_t mpsk_dot(mpsk_ctx* ctx, const mpsk_tensor* xh, const mpsk_tensor* yh, double* re, double* im) { ENTER(ctx);
   Ctx* c = CTX(ctx); const Tensor* x = CTEN(xh); const Tensor* y = CTEN(yh);
   MPSK_TRY(check_pair(c, x, y));
   double* d = (double*)c->alloc(4 * sizeof(double));
@@ -295,31 +313,32 @@ int32_t mpsk_dot(mpsk_ctx* ctx, const mpsk_tensor* xh, const mpsk_tensor* yh, do
   return st;
 }
 
-int32_t mpsk_norm(mpsk_ctx* ctx, const mpsk_tensor* x, double* out) {
+int32_t mpsk_norm(mpsk_ctx* ctx, const mpsk_tensor* x, double* out) { ENTER(ctx);
   double re = 0, im = 0;
   MPSK_TRY(mpsk_dot(ctx, x, x, &re, &im));
   *out = std::sqrt(re);
   return MPSK_OK;
 }
 
-int32_t mpsk_axpy(mpsk_ctx* ctx, double ar, double ai, const mpsk_tensor* xh, mpsk_tensor* yh) {
+int32_t mpsk_axpy(mpsk_ctx* ctx, double ar, double ai, const mpsk_tensor* xh, mpsk_tensor* yh) { ENTER(ctx);
   Ctx* c = CTX(ctx); const Tensor* x = CTEN(xh); Tensor* y = TEN(yh);
   MPSK_TRY(check_pair(c, x, y));
   if (x->dtype == MPSK_F64 && ai != 0.0) return c->fail(MPSK_EINVAL, "complex coefficient on a real tensor");
   return vec_axpy(c, x->dtype == MPSK_C128, cplx(ar, ai), x->d, y->d, x->nelem);
 }
 
-int32_t mpsk_scale(mpsk_ctx* ctx, double ar, double ai, mpsk_tensor* xh) {
+int32_t mpsk_scale(mpsk_ctx* ctx, double ar, double ai, mpsk_tensor* xh) { ENTER(ctx);
   Ctx* c = CTX(ctx); Tensor* x = TEN(xh);
   if (x->dtype == MPSK_F64 && ai != 0.0) return c->fail(MPSK_EINVAL, "complex coefficient on a real tensor");
   return vec_scale(c, x->dtype == MPSK_C128, x->d, x->nelem, cplx(ar, ai));
 }
 
 // ------------------------------------------------------------------------------------------ MPO slices
-int32_t mpsk_mposlice_create(mpsk_ctx* ctx, int32_t odim, const int32_t* cl, const int32_t* cr, int32_t d, const int32_t* pch,
-                             const int32_t* kind, const double* scal, const double* ops, mpsk_mposlice** out) {
+int32_t mpsk_mposlice_create_zn(mpsk_ctx* ctx, int32_t odim, const int32_t* cl, const int32_t* cr, int32_t d, const int32_t* pch,
+                                const int32_t* kind, const double* scal, const double* ops, int32_t modulus, mpsk_mposlice** out) { ENTER(ctx);
   Ctx* c = CTX(ctx);
-  if (odim <= 0 || d <= 0) return c->fail(MPSK_EINVAL, "bad slice dimensions");
+  if (odim <= 0 || d <= 0 || modulus < 0) return c->fail(MPSK_EINVAL, "bad slice dimensions");
+  auto nrm = [&](int64_t q) -> int64_t { if (!modulus) return q; int64_t r = q % modulus; return r < 0 ? r + modulus : r; };
   std::unique_ptr<MpoSlice> s(new MpoSlice);
   s->odim = odim; s->d = d;
   s->cl.assign(cl, cl + odim); s->cr.assign(cr, cr + odim); s->pch.assign(pch, pch + d);
@@ -331,13 +350,13 @@ int32_t mpsk_mposlice_create(mpsk_ctx* ctx, int32_t odim, const int32_t* cl, con
     if (k < 0 || k > 2) return c->fail(MPSK_EINVAL, "bad entry kind");
     if (k == 1) {
       s->scal[i * odim + j] = cplx(scal[2 * (i * odim + j)], scal[2 * (i * odim + j) + 1]);
-      if (cl[i] != cr[j]) return c->fail(MPSK_ESPACE, "scalar entry (%d,%d) connects levels of different charge", i, j);
+      if (nrm(cl[i]) != nrm(cr[j])) return c->fail(MPSK_ESPACE, "scalar entry (%d,%d) connects levels of different charge", i, j);
     } else if (k == 2) {
       std::vector<cplx>& o = s->ops[i * odim + j];
       o.resize((size_t)d * d);
       for (int e = 0; e < d * d; ++e) o[e] = cplx(ops[2 * (nop * d * d + e)], ops[2 * (nop * d * d + e) + 1]);
       for (int a = 0; a < d; ++a) for (int b = 0; b < d; ++b)
-        if (o[a * d + b] != cplx(0.0) && cr[j] != cl[i] + pch[a] - pch[b])
+        if (o[a * d + b] != cplx(0.0) && nrm(cr[j]) != nrm((int64_t)cl[i] + pch[a] - pch[b]))
           return c->fail(MPSK_ESPACE, "operator entry (%d,%d) element (%d,%d) violates charge conservation", i, j, a, b);
       ++nop;
     }
@@ -346,7 +365,12 @@ int32_t mpsk_mposlice_create(mpsk_ctx* ctx, int32_t odim, const int32_t* cl, con
   return MPSK_OK;
 }
 
-void mpsk_mposlice_free(mpsk_ctx*, mpsk_mposlice* s) { delete reinterpret_cast<MpoSlice*>(s); }
+int32_t mpsk_mposlice_create(mpsk_ctx* ctx, int32_t odim, const int32_t* cl, const int32_t* cr, int32_t d, const int32_t* pch,
+                             const int32_t* kind, const double* scal, const double* ops, mpsk_mposlice** out) {
+  return mpsk_mposlice_create_zn(ctx, odim, cl, cr, d, pch, kind, scal, ops, 0, out);
+}
+
+void mpsk_mposlice_free(mpsk_ctx*, mpsk_mposlice* s) { delete reinterpret_cast<MpoSlice*>(const_cast<mpsk_mposlice*>(s)); }
 
 int32_t mpsk_mposlice_keys(const mpsk_mposlice* sh, int32_t* count, int32_t* ij) {
   const MpoSlice* s = SLICE(sh);
@@ -362,19 +386,20 @@ int32_t mpsk_mposlice_keys(const mpsk_mposlice* sh, int32_t* count, int32_t* ij)
 
 // ------------------------------------------------------------------------------------------ operators
 int32_t mpsk_op_create(mpsk_ctx* ctx, int32_t kind, const mpsk_mposlice* h1, const mpsk_mposlice* h2, const mpsk_tensor* GL,
-                       const mpsk_tensor* GR, const mpsk_tensor* x_like, mpsk_op** out) {
+                       const mpsk_tensor* GR, const mpsk_tensor* x_like, mpsk_op** out) { ENTER(ctx);
   HeffOp* op = nullptr;
   MPSK_TRY(heff_create(CTX(ctx), kind, SLICE(h1), SLICE(h2), CTEN(GL), CTEN(GR), CTEN(x_like), &op));
-  *out = reinterpret_cast<mpsk_op*>(op);
+  *out = reinterpret_cast<mpsk_op*>(static_cast<LinOp*>(op));
   return MPSK_OK;
 }
-void mpsk_op_free(mpsk_ctx*, mpsk_op* op) { delete reinterpret_cast<HeffOp*>(op); }
-double mpsk_op_flops(const mpsk_op* op) { return reinterpret_cast<const HeffOp*>(op)->flops; }
+void mpsk_op_free(mpsk_ctx* ctx, mpsk_op* op) { if (!op) return; if (ctx) { ENTER(ctx); delete reinterpret_cast<LinOp*>(op); } else delete reinterpret_cast<LinOp*>(op); }
+double mpsk_op_flops(const mpsk_op* op) { return reinterpret_cast<const LinOp*>(op)->flops(); }
 
 // measurement hook for bench.py: average device time (ms) of the two grouped-GEMM launches of one matvec,
 // CUDA events on the launching stream, inputs as left by the last apply.
-int32_t mpsk_op_time_gemms(mpsk_ctx* ctx, const mpsk_op* oph, int32_t reps, double* ms_out) {
-  Ctx* c = CTX(ctx); const HeffOp* op = reinterpret_cast<const HeffOp*>(oph);
+int32_t mpsk_op_time_gemms(mpsk_ctx* ctx, const mpsk_op* oph, int32_t reps, double* ms_out) { ENTER(ctx);
+  Ctx* c = CTX(ctx); const HeffOp* op = dynamic_cast<const HeffOp*>(reinterpret_cast<const LinOp*>(oph));
+  if (!op) return c->fail(MPSK_EINVAL, "not an effective-Hamiltonian operator");
   cudaEvent_t e0, e1;
   CUDA_TRY(c, cudaEventCreate(&e0)); CUDA_TRY(c, cudaEventCreate(&e1));
   double tot = 0;
@@ -398,19 +423,41 @@ int32_t mpsk_op_time_gemms(mpsk_ctx* ctx, const mpsk_op* oph, int32_t reps, doub
   return MPSK_OK;
 }
 
+// measurement hook: average device time (ms) and algorithmic bytes of the mix launch of one matvec
+int32_t mpsk_op_time_mix(mpsk_ctx* ctx, const mpsk_op* oph, int32_t reps, double* ms_out, double* bytes_out) { ENTER(ctx);
+  Ctx* c = CTX(ctx); const HeffOp* op = dynamic_cast<const HeffOp*>(reinterpret_cast<const LinOp*>(oph));
+  if (!op) return c->fail(MPSK_EINVAL, "not an effective-Hamiltonian operator");
+  cudaEvent_t e0, e1;
+  CUDA_TRY(c, cudaEventCreate(&e0)); CUDA_TRY(c, cudaEventCreate(&e1));
+  double tot = 0;
+  for (int r = 0; r < reps; ++r) {
+    float a = 0;
+    CUDA_TRY(c, cudaEventRecord(e0, c->stream));
+    MPSK_TRY(mix_plan_run(c, op->mix.get()));
+    CUDA_TRY(c, cudaEventRecord(e1, c->stream));
+    CUDA_TRY(c, cudaEventSynchronize(e1));
+    CUDA_TRY(c, cudaEventElapsedTime(&a, e0, e1));
+    tot += a;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (ms_out) *ms_out = tot / std::max(reps, 1);
+  if (bytes_out) *bytes_out = op->mix->bytes;
+  return MPSK_OK;
+}
+
 static int as_kl(Ctx* c, const Tensor* t) { return t->form == F_KL ? MPSK_OK : c->fail(MPSK_EINTERNAL, "tensor is not in vector (KL) form"); }
 
-int32_t mpsk_op_apply(mpsk_ctx* ctx, const mpsk_op* op, const mpsk_tensor* x, mpsk_tensor* y) {
+int32_t mpsk_op_apply(mpsk_ctx* ctx, const mpsk_op* op, const mpsk_tensor* x, mpsk_tensor* y) { ENTER(ctx);
   MPSK_TRY(as_kl(CTX(ctx), CTEN(x))); MPSK_TRY(as_kl(CTX(ctx), CTEN(y)));
-  return heff_apply(CTX(ctx), const_cast<HeffOp*>(reinterpret_cast<const HeffOp*>(op)), CTEN(x), TEN(y));
+  return OPH(op)->apply(CTEN(x), TEN(y));
 }
 
 int32_t mpsk_eigsolve(mpsk_ctx* ctx, const mpsk_op* op, const mpsk_tensor* x0, int32_t which, int32_t hermitian, int32_t krylovdim,
-                      int32_t maxiter, double tol, double* val_re, double* val_im, mpsk_tensor* vec, mpsk_info* info) {
+                      int32_t maxiter, double tol, double* val_re, double* val_im, mpsk_tensor* vec, mpsk_info* info) { ENTER(ctx);
   Ctx* c = CTX(ctx);
   MPSK_TRY(as_kl(c, CTEN(x0))); MPSK_TRY(as_kl(c, CTEN(vec)));
   cplx v = 0;
-  HeffOp* h = const_cast<HeffOp*>(reinterpret_cast<const HeffOp*>(op));
+  LinOp* h = OPH(op);
   int st = hermitian ? eigsolve_lanczos(c, h, CTEN(x0), which, krylovdim, maxiter, tol, &v, TEN(vec), info)
                      : eigsolve_arnoldi(c, h, CTEN(x0), which, krylovdim, maxiter, tol, &v, TEN(vec), info);
   if (val_re) *val_re = v.real();
@@ -419,10 +466,76 @@ int32_t mpsk_eigsolve(mpsk_ctx* ctx, const mpsk_op* op, const mpsk_tensor* x0, i
 }
 
 int32_t mpsk_expv(mpsk_ctx* ctx, const mpsk_op* op, double tr, double ti, const mpsk_tensor* y0, int32_t krylovdim, int32_t maxiter,
-                  double tol, mpsk_tensor* y, mpsk_info* info) {
+                  double tol, mpsk_tensor* y, mpsk_info* info) { ENTER(ctx);
   Ctx* c = CTX(ctx);
   MPSK_TRY(as_kl(c, CTEN(y0))); MPSK_TRY(as_kl(c, CTEN(y)));
-  return expv_lanczos(c, const_cast<HeffOp*>(reinterpret_cast<const HeffOp*>(op)), cplx(tr, ti), CTEN(y0), krylovdim, maxiter, tol, TEN(y), info);
+  return expv_lanczos(c, OPH(op), cplx(tr, ti), CTEN(y0), krylovdim, maxiter, tol, TEN(y), info);
+}
+
+int32_t mpsk_linsolve(mpsk_ctx* ctx, const mpsk_op* op, const mpsk_tensor* b, const mpsk_tensor* x0, double a0_re, double a0_im,
+                      double a1_re, double a1_im, int32_t krylovdim, int32_t maxiter, double tol, mpsk_tensor* x, mpsk_info* info) { ENTER(ctx);
+  Ctx* c = CTX(ctx);
+  MPSK_TRY(as_kl(c, CTEN(b))); MPSK_TRY(as_kl(c, CTEN(x0))); MPSK_TRY(as_kl(c, CTEN(x)));
+  return linsolve_gmres(c, OPH(op), CTEN(b), CTEN(x0), cplx(a0_re, a0_im), cplx(a1_re, a1_im), krylovdim, maxiter, tol, TEN(x), info);
+}
+
+// transfer matrix over a unit cell as an operator handle (transfermatrix.jl:4-90): usable with mpsk_op_apply, mpsk_eigsolve
+// (hermitian = 0: Arnoldi) and mpsk_linsolve
+int32_t mpsk_tmop_create(mpsk_ctx* ctx, int32_t left, int32_t nsites, const mpsk_mposlice* const* slices, const mpsk_tensor* const* A,
+                         const mpsk_tensor* const* Abar, const mpsk_tensor* v_like, const mpsk_tensor* lvec_adj, const mpsk_tensor* rvec,
+                         mpsk_op** out) { ENTER(ctx);
+  Ctx* c = CTX(ctx);
+  if (nsites <= 0 || !A || !Abar || !v_like) return c->fail(MPSK_EINVAL, "tmop: bad arguments");
+  if ((lvec_adj == nullptr) != (rvec == nullptr)) return c->fail(MPSK_EINVAL, "tmop: regularisation needs both vectors");
+  const Tensor* vl = CTEN(v_like);
+  std::unique_ptr<TmOp> op(new TmOp);
+  op->ctx = c; op->dtype = vl->dtype; op->left = left != 0;
+  { Tensor* t = nullptr; MPSK_TRY(tensor_create(c, vl->Vl, vl->mch, vl->Vr, vl->dtype, F_KL, true, &t)); op->vlike.reset(t); }
+  std::unique_ptr<Tensor> cur_like;     // structure of the vector entering the next site
+  const Tensor* cur = op->vlike.get();
+  for (int s = 0; s < nsites; ++s) {
+    const int site = left ? s : nsites - 1 - s;                      // v * tm sweeps left -> right, tm * v right -> left
+    const Tensor* a = CTEN(A[site]); const Tensor* ab = CTEN(Abar[site]);
+    const MpoSlice* h = slices ? SLICE(slices[site]) : nullptr;
+    MpoSlice unit;
+    if (!h) {     // MPO-free transfer (transfer.jl:18-45): one level, identity on the physical labels
+      if (cur->nm() != 1) return c->fail(MPSK_ESPACE, "tmop: MPO-free transfer needs single-level vectors");
+      unit.odim = 1; unit.d = a->nm(); unit.cl = {-cur->mch[0] * (left ? 1 : -1)}; unit.cr = unit.cl;
+      unit.pch.assign(a->mch.begin(), a->mch.end()); unit.kind = {1}; unit.scal = {cplx(1.0)}; unit.ops.resize(1);
+      h = &unit;
+    }
+    TransferPlan* p = nullptr;
+    MPSK_TRY(transfer_plan_create(c, left != 0, h, a, ab, cur, /*sharded=*/false, &p));
+    op->sites.emplace_back(p);
+    op->flops_ += p->flops;
+    cur = p->result();
+  }
+  if (!cur->same_structure(*op->vlike)) return c->fail(MPSK_ESPACE, "tmop: the unit cell does not map the vector space onto itself");
+  if (lvec_adj) {
+    const Tensor* la = CTEN(lvec_adj); const Tensor* rv = CTEN(rvec);
+    if (!la->same_structure(*op->vlike) || !rv->same_structure(*op->vlike) || la->form != F_KL || rv->form != F_KL)
+      return c->fail(MPSK_ESPACE, "tmop: regularisation vectors do not match the vector space");
+    Tensor* t = nullptr;
+    MPSK_TRY(tensor_repack(c, la, F_KL, false, &t)); op->ladj.reset(t);
+    MPSK_TRY(tensor_repack(c, rv, F_KL, false, &t)); op->rvec.reset(t);
+    op->d_coef = (double*)c->alloc(4 * sizeof(double));
+    if (!op->d_coef) return MPSK_ENOMEM;
+  }
+  *out = reinterpret_cast<mpsk_op*>(static_cast<LinOp*>(op.release()));
+  return MPSK_OK;
+}
+
+// host-only numerical helper exposed for the CPU test-suite: complex Schur decomposition (+ optional reordering) used by
+// the Krylov-Schur eigensolver.  H: n x n column-major complex (interleaved), overwritten by T; Z: n x n Schur vectors.
+int32_t mpsk_host_schur(int32_t n, double* H, double* Z, int32_t move_from, int32_t move_to) {
+  if (n <= 0) return MPSK_EINVAL;
+  std::vector<cplx> h((size_t)n * n), z;
+  for (size_t i = 0; i < h.size(); ++i) h[i] = cplx(H[2 * i], H[2 * i + 1]);
+  int st = schur_complex(n, h, z);
+  if (st != MPSK_OK) return st;
+  if (move_from >= 0 && move_to >= 0 && move_to <= move_from && move_from < n) schur_move(n, h, z, move_from, move_to);
+  for (size_t i = 0; i < h.size(); ++i) { H[2 * i] = h[i].real(); H[2 * i + 1] = h[i].imag(); Z[2 * i] = z[i].real(); Z[2 * i + 1] = z[i].imag(); }
+  return MPSK_OK;
 }
 
 // ------------------------------------------------------------------------------------------ transfers / local algebra
@@ -438,42 +551,42 @@ static int to_kl(Ctx* c, Tensor* t, mpsk_tensor** out) {
 }
 
 int32_t mpsk_transfer_left(mpsk_ctx* ctx, const mpsk_mposlice* h, const mpsk_tensor* A, const mpsk_tensor* Abar, const mpsk_tensor* GL,
-                           mpsk_tensor** out) {
+                           mpsk_tensor** out) { ENTER(ctx);
   Tensor* o = nullptr;
   MPSK_TRY(transfer_left(CTX(ctx), SLICE(h), CTEN(A), CTEN(Abar), CTEN(GL), &o));
   return to_kl(CTX(ctx), o, out);
 }
 int32_t mpsk_transfer_right(mpsk_ctx* ctx, const mpsk_mposlice* h, const mpsk_tensor* A, const mpsk_tensor* Abar, const mpsk_tensor* GR,
-                            mpsk_tensor** out) {
+                            mpsk_tensor** out) { ENTER(ctx);
   Tensor* o = nullptr;
   MPSK_TRY(transfer_right(CTX(ctx), SLICE(h), CTEN(A), CTEN(Abar), CTEN(GR), &o));
   return to_kl(CTX(ctx), o, out);
 }
-int32_t mpsk_contract_ac2(mpsk_ctx* ctx, const mpsk_tensor* A1, const mpsk_tensor* A2, mpsk_tensor** out) {
+int32_t mpsk_contract_ac2(mpsk_ctx* ctx, const mpsk_tensor* A1, const mpsk_tensor* A2, mpsk_tensor** out) { ENTER(ctx);
   Tensor* o = nullptr;
   MPSK_TRY(contract_ac2(CTX(ctx), CTEN(A1), CTEN(A2), &o));
   return to_kl(CTX(ctx), o, out);
 }
-int32_t mpsk_mul_bond_right(mpsk_ctx* ctx, const mpsk_tensor* A, const mpsk_tensor* C, mpsk_tensor** out) {
+int32_t mpsk_mul_bond_right(mpsk_ctx* ctx, const mpsk_tensor* A, const mpsk_tensor* C, mpsk_tensor** out) { ENTER(ctx);
   Tensor* o = nullptr;
   MPSK_TRY(mul_bond_right(CTX(ctx), CTEN(A), CTEN(C), &o));
   return to_kl(CTX(ctx), o, out);
 }
-int32_t mpsk_mul_bond_left(mpsk_ctx* ctx, const mpsk_tensor* C, const mpsk_tensor* A, mpsk_tensor** out) {
+int32_t mpsk_mul_bond_left(mpsk_ctx* ctx, const mpsk_tensor* C, const mpsk_tensor* A, mpsk_tensor** out) { ENTER(ctx);
   Tensor* o = nullptr;
   MPSK_TRY(mul_bond_left(CTX(ctx), CTEN(C), CTEN(A), &o));
   return to_kl(CTX(ctx), o, out);
 }
 
 int32_t mpsk_tsvd(mpsk_ctx* ctx, const mpsk_tensor* ac2, int32_t d1, const int32_t* p1_charge, mpsk_trunc trunc, mpsk_tensor** U,
-                  mpsk_tensor** S, mpsk_tensor** Vh, double* eps) {
+                  mpsk_tensor** S, mpsk_tensor** Vh, double* eps) { ENTER(ctx);
   Tensor *u = nullptr, *s = nullptr, *v = nullptr;
   MPSK_TRY(tsvd(CTX(ctx), CTEN(ac2), d1, p1_charge, trunc, &u, &s, &v, eps));
   *U = reinterpret_cast<mpsk_tensor*>(u); *S = reinterpret_cast<mpsk_tensor*>(s); *Vh = reinterpret_cast<mpsk_tensor*>(v);
   return MPSK_OK;
 }
 
-int32_t mpsk_tsvd_spectrum(mpsk_ctx* ctx, int32_t* nsec, int32_t* charge, int32_t* count, int32_t* kept, double* values) {
+int32_t mpsk_tsvd_spectrum(mpsk_ctx* ctx, int32_t* nsec, int32_t* charge, int32_t* count, int32_t* kept, double* values) { ENTER(ctx);
   const TsvdSpectrum& sp = CTX(ctx)->last_spectrum;
   if (nsec) *nsec = (int32_t)sp.charge.size();
   for (size_t i = 0; i < sp.charge.size(); ++i) { if (charge) charge[i] = sp.charge[i]; if (count) count[i] = sp.count[i]; if (kept) kept[i] = sp.kept[i]; }
@@ -481,13 +594,13 @@ int32_t mpsk_tsvd_spectrum(mpsk_ctx* ctx, int32_t* nsec, int32_t* charge, int32_
   return MPSK_OK;
 }
 
-int32_t mpsk_qrpos(mpsk_ctx* ctx, const mpsk_tensor* A, mpsk_tensor** Q, mpsk_tensor** R) {
+int32_t mpsk_qrpos(mpsk_ctx* ctx, const mpsk_tensor* A, mpsk_tensor** Q, mpsk_tensor** R) { ENTER(ctx);
   Tensor *q = nullptr, *r = nullptr;
   MPSK_TRY(qrpos(CTX(ctx), CTEN(A), true, &q, &r));
   *Q = reinterpret_cast<mpsk_tensor*>(q); *R = reinterpret_cast<mpsk_tensor*>(r);
   return MPSK_OK;
 }
-int32_t mpsk_lqpos(mpsk_ctx* ctx, const mpsk_tensor* A, mpsk_tensor** L, mpsk_tensor** Q) {
+int32_t mpsk_lqpos(mpsk_ctx* ctx, const mpsk_tensor* A, mpsk_tensor** L, mpsk_tensor** Q) { ENTER(ctx);
   Tensor *q = nullptr, *l = nullptr;
   MPSK_TRY(qrpos(CTX(ctx), CTEN(A), false, &q, &l));
   *Q = reinterpret_cast<mpsk_tensor*>(q); *L = reinterpret_cast<mpsk_tensor*>(l);
@@ -499,11 +612,6 @@ typedef struct { char internal[128]; } nccl_uid_t;
 typedef int (*pfn_ncclGetUniqueId)(nccl_uid_t*);
 typedef int (*pfn_ncclCommInitRank)(void**, int, nccl_uid_t, int);
 typedef int (*pfn_ncclAllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
-static void* nccl_lib() {
-  static void* lib = nullptr;
-  if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-  return lib;
-}
 
 int32_t mpsk_comm_unique_id(uint8_t out128[128]) {
   void* lib = nccl_lib();
@@ -515,7 +623,7 @@ int32_t mpsk_comm_unique_id(uint8_t out128[128]) {
   return MPSK_OK;
 }
 
-int32_t mpsk_comm_init(mpsk_ctx* ctx, const uint8_t id128[128], int32_t rank, int32_t nranks) {
+int32_t mpsk_comm_init(mpsk_ctx* ctx, const uint8_t id128[128], int32_t rank, int32_t nranks) { ENTER(ctx);
   Ctx* c = CTX(ctx);
   void* lib = nccl_lib();
   if (!lib) return c->fail(MPSK_ECUDA, "libnccl.so.2 not found: %s", dlerror());
@@ -529,24 +637,46 @@ int32_t mpsk_comm_init(mpsk_ctx* ctx, const uint8_t id128[128], int32_t rank, in
   return MPSK_OK;
 }
 
-int32_t mpsk_tensor_row_panel(mpsk_ctx* ctx, const mpsk_tensor* t, int32_t rank, int32_t nranks, mpsk_tensor** out) {
+int32_t mpsk_tensor_row_panel(mpsk_ctx* ctx, const mpsk_tensor* t, int32_t rank, int32_t nranks, mpsk_tensor** out) { ENTER(ctx);
   Tensor* o = nullptr;
   MPSK_TRY(tensor_row_panel(CTX(ctx), CTEN(t), rank, nranks, &o));
   *out = reinterpret_cast<mpsk_tensor*>(o);
   return MPSK_OK;
 }
 
-int32_t mpsk_tensor_scatter_panel(mpsk_ctx* ctx, const mpsk_tensor* panel, int32_t rank, int32_t nranks, mpsk_tensor* full) {
+int32_t mpsk_tensor_scatter_panel(mpsk_ctx* ctx, const mpsk_tensor* panel, int32_t rank, int32_t nranks, mpsk_tensor* full) { ENTER(ctx);
   Ctx* c = CTX(ctx); const Tensor* p = CTEN(panel); Tensor* f = TEN(full);
   if (p->form != F_KL || p->nelem != panel_nelem(f, rank, nranks) || p->dtype != f->dtype) return c->fail(MPSK_ESPACE, "tensor is not the row panel of that rank");
   return tensor_scatter_panel(c, p->d, rank, nranks, f, true);
 }
 
-int32_t mpsk_op_apply_local(mpsk_ctx* ctx, const mpsk_op* op, const mpsk_tensor* x, mpsk_tensor* y_panel) {
-  return heff_apply_local(CTX(ctx), const_cast<HeffOp*>(reinterpret_cast<const HeffOp*>(op)), CTEN(x), TEN(y_panel));
+static HeffOp* as_heff(const mpsk_op* op) { return dynamic_cast<HeffOp*>(OPH(op)); }
+
+int32_t mpsk_op_apply_local(mpsk_ctx* ctx, const mpsk_op* op, const mpsk_tensor* x, mpsk_tensor* y_panel) { ENTER(ctx);
+  HeffOp* h = as_heff(op);
+  if (!h) return CTX(ctx)->fail(MPSK_EINVAL, "not an effective-Hamiltonian operator");
+  return heff_apply_local(CTX(ctx), h, CTEN(x), TEN(y_panel));
 }
 
-int32_t mpsk_allreduce_sum(mpsk_ctx* ctx, mpsk_tensor* xh) {
+int32_t mpsk_op_apply_panel(mpsk_ctx* ctx, const mpsk_op* op, const mpsk_tensor* x_panel, mpsk_tensor* y_panel) { ENTER(ctx);
+  HeffOp* h = as_heff(op);
+  if (!h) return CTX(ctx)->fail(MPSK_EINVAL, "not an effective-Hamiltonian operator");
+  return heff_apply_panel(CTX(ctx), h, CTEN(x_panel), TEN(y_panel));
+}
+
+int32_t mpsk_tensor_panel(mpsk_ctx* ctx, const mpsk_tensor* t, int32_t axis, int32_t rank, int32_t nranks, mpsk_tensor** out) { ENTER(ctx);
+  if (axis != 0 && axis != 1) return CTX(ctx)->fail(MPSK_EINVAL, "axis must be 0 (left index) or 1 (right index)");
+  Tensor* o = nullptr;
+  MPSK_TRY(tensor_panel(CTX(ctx), CTEN(t), axis, rank, nranks, &o));
+  *out = reinterpret_cast<mpsk_tensor*>(o);
+  return MPSK_OK;
+}
+
+int32_t mpsk_tensor_allgather(mpsk_ctx* ctx, const mpsk_tensor* panel, mpsk_tensor* full) { ENTER(ctx);
+  return tensor_allgather_panels(CTX(ctx), CTEN(panel), TEN(full));
+}
+
+int32_t mpsk_allreduce_sum(mpsk_ctx* ctx, mpsk_tensor* xh) { ENTER(ctx);
   Ctx* c = CTX(ctx); Tensor* x = TEN(xh);
   if (c->nranks <= 1) return MPSK_OK;
   pfn_ncclAllReduce f = (pfn_ncclAllReduce)dlsym(nccl_lib(), "ncclAllReduce");
@@ -561,6 +691,16 @@ int32_t mpsk_allreduce_sum(mpsk_ctx* ctx, mpsk_tensor* xh) {
 }  // extern "C"
 
 namespace mpsk {
+int comm_allreduce_sum(Ctx* c, void* buf, size_t ndoubles) {
+  if (c->nranks <= 1 || ndoubles == 0) return MPSK_OK;
+  typedef int (*pfn_ncclAllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+  pfn_ncclAllReduce f = (pfn_ncclAllReduce)dlsym(nccl_lib(), "ncclAllReduce");
+  if (!f || !c->nccl) return c->fail(MPSK_ECUDA, "communicator not initialised");
+  int r = f(buf, buf, ndoubles, /*ncclDouble*/ 8, /*ncclSum*/ 0, c->nccl, c->stream);
+  if (r != 0) return c->fail(MPSK_ECUDA, "ncclAllReduce failed (%d)", r);
+  c->launches++;
+  return MPSK_OK;
+}
 int comm_allgather(Ctx* c, const void* send, void* recv, size_t bytes_per_rank) {
   typedef int (*pfn_ncclAllGather)(const void*, void*, size_t, int, void*, cudaStream_t);
   pfn_ncclAllGather f = (pfn_ncclAllGather)dlsym(nccl_lib(), "ncclAllGather");

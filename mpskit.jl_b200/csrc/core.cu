@@ -55,6 +55,35 @@ void Ctx::release_cache() {
   freelist.clear(); bytes_cached = 0;
 }
 
+// pinned bump arena (see internal.h): memory handed out stays valid until the arena wraps, and wrapping synchronises
+// the stream first, so asynchronous H2D copies out of it never read recycled bytes
+void* Ctx::arena_take(size_t bytes) {
+  bytes = (bytes + 63) / 64 * 64;
+  if (bytes > h_arena_bytes) {
+    cudaStreamSynchronize(stream);
+    if (h_arena) cudaFreeHost(h_arena);
+    h_arena = nullptr; h_arena_bytes = 0; h_arena_used = 0;
+    const size_t want = std::max<size_t>(bytes * 2, (size_t)8 << 20);
+    if (cudaMallocHost(&h_arena, want) != cudaSuccess) { cudaGetLastError(); fail(MPSK_ENOMEM, "pinned arena allocation failed"); return nullptr; }
+    h_arena_bytes = want;
+  }
+  if (h_arena_used + bytes > h_arena_bytes) { cudaStreamSynchronize(stream); h_arena_used = 0; }
+  void* p = h_arena + h_arena_used;
+  h_arena_used += bytes;
+  return p;
+}
+
+// stream-ordered upload of a small host table (pinned arena -> device, no host synchronisation)
+int upload_table(Ctx* ctx, const void* src, size_t bytes, void** d_out) {
+  void* h = ctx->arena_take(bytes);
+  void* d = ctx->alloc(bytes);
+  if (!h || !d) { if (d) ctx->free(d); return MPSK_ENOMEM; }
+  memcpy(h, src, bytes);
+  CUDA_TRY(ctx, cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  *d_out = d;
+  return MPSK_OK;
+}
+
 int space_from_abi(Ctx* ctx, const mpsk_space* s, Space* out) {
   if (!s || s->nsec < 0) return ctx->fail(MPSK_EINVAL, "null space");
   out->q.assign(s->charge, s->charge + s->nsec);
@@ -203,18 +232,17 @@ int run_copy_tasks(Ctx* ctx, const std::vector<CopyTask>& tasks, bool cplx) {
     for (int r0 = 0; r0 < tasks[i].nr; r0 += 32)
       for (int l0 = 0; l0 < tasks[i].nl; l0 += 32) tiles.push_back(CopyTile{(int)i, l0, r0, 0});
   if (tiles.empty()) return MPSK_OK;
-  CopyTask* d_tasks = (CopyTask*)ctx->alloc(tasks.size() * sizeof(CopyTask));
-  CopyTile* d_tiles = (CopyTile*)ctx->alloc(tiles.size() * sizeof(CopyTile));
-  if (!d_tasks || !d_tiles) return MPSK_ENOMEM;
-  CUDA_TRY(ctx, cudaMemcpyAsync(d_tasks, tasks.data(), tasks.size() * sizeof(CopyTask), cudaMemcpyHostToDevice, ctx->stream));
-  CUDA_TRY(ctx, cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(CopyTile), cudaMemcpyHostToDevice, ctx->stream));
+  // the tables travel through the pinned arena: no host synchronisation; the device copies are released in stream order
+  void *d_tasks = nullptr, *d_tiles = nullptr;
+  MPSK_TRY(upload_table(ctx, tasks.data(), tasks.size() * sizeof(CopyTask), &d_tasks));
+  int st = upload_table(ctx, tiles.data(), tiles.size() * sizeof(CopyTile), &d_tiles);
+  if (st != MPSK_OK) { ctx->free(d_tasks); return st; }
   const int grid = (int)std::min<size_t>(tiles.size(), (size_t)ctx->num_sms * 8);
-  if (cplx) copy_kernel<double2><<<grid, 256, 0, ctx->stream>>>(d_tasks, d_tiles, (int)tiles.size());
-  else copy_kernel<double><<<grid, 256, 0, ctx->stream>>>(d_tasks, d_tiles, (int)tiles.size());
+  if (cplx) copy_kernel<double2><<<grid, 256, 0, ctx->stream>>>((const CopyTask*)d_tasks, (const CopyTile*)d_tiles, (int)tiles.size());
+  else copy_kernel<double><<<grid, 256, 0, ctx->stream>>>((const CopyTask*)d_tasks, (const CopyTile*)d_tiles, (int)tiles.size());
   ctx->launches++;
-  CUDA_TRY(ctx, cudaGetLastError());
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // the host vectors are pageable: make sure the copies are done
   ctx->free(d_tasks); ctx->free(d_tiles);
+  CUDA_TRY(ctx, cudaGetLastError());
   return MPSK_OK;
 }
 
@@ -228,12 +256,8 @@ int copy_plan_build(Ctx* ctx, const std::vector<CopyTask>& tasks, bool cplx, Cop
     for (int r0 = 0; r0 < tasks[i].nr; r0 += 32)
       for (int l0 = 0; l0 < tasks[i].nl; l0 += 32) tiles.push_back(CopyTile{(int)i, l0, r0, 0});
   if (tiles.empty()) return MPSK_OK;
-  plan->d_tasks = ctx->alloc(tasks.size() * sizeof(CopyTask));
-  plan->d_tiles = ctx->alloc(tiles.size() * sizeof(CopyTile));
-  if (!plan->d_tasks || !plan->d_tiles) return MPSK_ENOMEM;
-  CUDA_TRY(ctx, cudaMemcpyAsync(plan->d_tasks, tasks.data(), tasks.size() * sizeof(CopyTask), cudaMemcpyHostToDevice, ctx->stream));
-  CUDA_TRY(ctx, cudaMemcpyAsync(plan->d_tiles, tiles.data(), tiles.size() * sizeof(CopyTile), cudaMemcpyHostToDevice, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  MPSK_TRY(upload_table(ctx, tasks.data(), tasks.size() * sizeof(CopyTask), &plan->d_tasks));
+  MPSK_TRY(upload_table(ctx, tiles.data(), tiles.size() * sizeof(CopyTile), &plan->d_tiles));
   plan->ntiles = (int)tiles.size();
   return MPSK_OK;
 }
@@ -372,65 +396,107 @@ static Space panel_space(const Space& V, int rank, int nranks) {
   return P;
 }
 
-// out = rows of t (l index) belonging to `rank`; any form in, KL form out
-int tensor_row_panel(Ctx* ctx, const Tensor* t, int rank, int nranks, Tensor** out) {
+// out = the part of t whose l index (axis 0) or r index (axis 1) belongs to `rank`; any form in, KL form out
+int tensor_panel(Ctx* ctx, const Tensor* t, int axis, int rank, int nranks, Tensor** out) {
   if (nranks < 1 || rank < 0 || rank >= nranks) return ctx->fail(MPSK_EINVAL, "bad rank / nranks");
-  Space P = panel_space(t->Vl, rank, nranks);
+  const Space& Vfull = axis == 0 ? t->Vl : t->Vr;
+  Space P = panel_space(Vfull, rank, nranks);
   Tensor* o = nullptr;
-  MPSK_TRY(tensor_create(ctx, P, t->mch, t->Vr, t->dtype, F_KL, true, &o));
+  if (axis == 0) MPSK_TRY(tensor_create(ctx, P, t->mch, t->Vr, t->dtype, F_KL, true, &o));
+  else MPSK_TRY(tensor_create(ctx, t->Vl, t->mch, P, t->dtype, F_KL, true, &o));
   std::unique_ptr<Tensor> og(o);
   std::vector<CopyTask> tasks;
   for (const Blk& b : o->blks) {
-    const int jl_full = t->Vl.find(P.q[b.jl]);
+    const int jl_full = axis == 0 ? t->Vl.find(P.q[b.jl]) : b.jl;
     const Blk* s = t->find(b.m, jl_full);
-    if (!s) return ctx->fail(MPSK_EINTERNAL, "row_panel: missing block");
-    int64_t lo, hi; panel_bounds(t->Vl, jl_full, rank, nranks, &lo, &hi);
-    tasks.push_back(CopyTask{t->ptr(s->off + lo * s->sl), o->ptr(b.off), s->sl, s->sr, b.sl, b.sr, (int32_t)(hi - lo), (int32_t)t->Vr.n[s->jr], 0, 0, nullptr});
+    if (!s) return ctx->fail(MPSK_EINTERNAL, "panel: missing block");
+    int64_t lo, hi;
+    if (axis == 0) {
+      panel_bounds(t->Vl, jl_full, rank, nranks, &lo, &hi);
+      tasks.push_back(CopyTask{t->ptr(s->off + lo * s->sl), o->ptr(b.off), s->sl, s->sr, b.sl, b.sr, (int32_t)(hi - lo), (int32_t)t->Vr.n[s->jr], 0, 0, nullptr});
+    } else {
+      if (t->Vr.q[s->jr] != P.q[b.jr]) return ctx->fail(MPSK_EINTERNAL, "panel: sector mismatch");
+      panel_bounds(t->Vr, s->jr, rank, nranks, &lo, &hi);
+      tasks.push_back(CopyTask{t->ptr(s->off + lo * s->sr), o->ptr(b.off), s->sl, s->sr, b.sl, b.sr, (int32_t)t->Vl.n[s->jl], (int32_t)(hi - lo), 0, 0, nullptr});
+    }
   }
   MPSK_TRY(run_copy_tasks(ctx, tasks, t->dtype == MPSK_C128));
   *out = og.release();
   return MPSK_OK;
 }
 
-// full[rows of `rank`] = panel data; `src` points at a buffer laid out like the KL-form panel tensor of that rank
-int scatter_panel_tasks(Ctx* ctx, const void* src, int rank, int nranks, Tensor* full, std::vector<CopyTask>* tasks) {
-  Space P = panel_space(full->Vl, rank, nranks);
-  Tensor lay; lay.ctx = nullptr; lay.Vl = P; lay.Vr = full->Vr; lay.mch = full->mch; lay.dtype = full->dtype; lay.form = F_KL;
-  tensor_layout_only(&lay);
+int tensor_row_panel(Ctx* ctx, const Tensor* t, int rank, int nranks, Tensor** out) { return tensor_panel(ctx, t, 0, rank, nranks, out); }
+
+static void panel_layout(const Tensor* full, int axis, int rank, int nranks, Tensor* lay, Space* P) {
+  *P = panel_space(axis == 0 ? full->Vl : full->Vr, rank, nranks);
+  lay->ctx = nullptr; lay->mch = full->mch; lay->dtype = full->dtype; lay->form = F_KL;
+  if (axis == 0) { lay->Vl = *P; lay->Vr = full->Vr; } else { lay->Vl = full->Vl; lay->Vr = *P; }
+  tensor_layout_only(lay);
+}
+
+// full[part of `rank`] = panel data; `src` points at a buffer laid out like the KL-form panel tensor of that rank
+int scatter_panel_tasks_axis(Ctx* ctx, const void* src, int axis, int rank, int nranks, Tensor* full, std::vector<CopyTask>* tasks) {
+  Tensor lay; Space P;
+  panel_layout(full, axis, rank, nranks, &lay, &P);
   const size_t es = full->esize();
   for (const Blk& b : lay.blks) {
-    const int jl_full = full->Vl.find(P.q[b.jl]);
+    const int jl_full = axis == 0 ? full->Vl.find(P.q[b.jl]) : b.jl;
     const Blk* d = full->find(b.m, jl_full);
     if (!d) return ctx->fail(MPSK_EINTERNAL, "scatter_panel: missing block");
-    int64_t lo, hi; panel_bounds(full->Vl, jl_full, rank, nranks, &lo, &hi);
-    tasks->push_back(CopyTask{(const char*)src + b.off * es, full->ptr(d->off + lo * d->sl), b.sl, b.sr, d->sl, d->sr, (int32_t)(hi - lo),
-                              (int32_t)full->Vr.n[d->jr], 0, 0, nullptr});
+    int64_t lo, hi;
+    if (axis == 0) {
+      panel_bounds(full->Vl, jl_full, rank, nranks, &lo, &hi);
+      tasks->push_back(CopyTask{(const char*)src + b.off * es, full->ptr(d->off + lo * d->sl), b.sl, b.sr, d->sl, d->sr, (int32_t)(hi - lo),
+                                (int32_t)full->Vr.n[d->jr], 0, 0, nullptr});
+    } else {
+      panel_bounds(full->Vr, d->jr, rank, nranks, &lo, &hi);
+      tasks->push_back(CopyTask{(const char*)src + b.off * es, full->ptr(d->off + lo * d->sr), b.sl, b.sr, d->sl, d->sr, (int32_t)full->Vl.n[d->jl],
+                                (int32_t)(hi - lo), 0, 0, nullptr});
+    }
   }
   return MPSK_OK;
 }
 
+int scatter_panel_tasks(Ctx* ctx, const void* src, int rank, int nranks, Tensor* full, std::vector<CopyTask>* tasks) {
+  return scatter_panel_tasks_axis(ctx, src, 0, rank, nranks, full, tasks);
+}
+
 int tensor_scatter_panel(Ctx* ctx, const void* src, int rank, int nranks, Tensor* full, bool sync) {
-  Space P = panel_space(full->Vl, rank, nranks);
-  Tensor lay; lay.ctx = nullptr; lay.Vl = P; lay.Vr = full->Vr; lay.mch = full->mch; lay.dtype = full->dtype; lay.form = F_KL;
-  tensor_layout_only(&lay);
   std::vector<CopyTask> tasks;
-  const size_t es = full->esize();
-  for (const Blk& b : lay.blks) {
-    const int jl_full = full->Vl.find(P.q[b.jl]);
-    const Blk* d = full->find(b.m, jl_full);
-    if (!d) return ctx->fail(MPSK_EINTERNAL, "scatter_panel: missing block");
-    int64_t lo, hi; panel_bounds(full->Vl, jl_full, rank, nranks, &lo, &hi);
-    tasks.push_back(CopyTask{(const char*)src + b.off * es, full->ptr(d->off + lo * d->sl), b.sl, b.sr, d->sl, d->sr, (int32_t)(hi - lo),
-                             (int32_t)full->Vr.n[d->jr], 0, 0, nullptr});
-  }
+  MPSK_TRY(scatter_panel_tasks_axis(ctx, src, 0, rank, nranks, full, &tasks));
   (void)sync;
   return run_copy_tasks(ctx, tasks, full->dtype == MPSK_C128);
 }
 
-int64_t panel_nelem(const Tensor* full, int rank, int nranks) {
-  Tensor lay; lay.ctx = nullptr; lay.Vl = panel_space(full->Vl, rank, nranks); lay.Vr = full->Vr; lay.mch = full->mch; lay.dtype = full->dtype; lay.form = F_KL;
-  tensor_layout_only(&lay);
+int64_t panel_nelem_axis(const Tensor* full, int axis, int rank, int nranks) {
+  Tensor lay; Space P;
+  panel_layout(full, axis, rank, nranks, &lay, &P);
   return lay.nelem;
+}
+int64_t panel_nelem(const Tensor* full, int rank, int nranks) { return panel_nelem_axis(full, 0, rank, nranks); }
+
+// every rank contributes its axis-0 panel (KL form) of a tensor with the structure of `full`; afterwards `full` holds
+// the whole tensor on every rank (used to re-activate environments that are stored sharded)
+int tensor_allgather_panels(Ctx* ctx, const Tensor* panel, Tensor* full) {
+  if (ctx->nranks <= 1) return ctx->fail(MPSK_EINVAL, "allgather without a communicator");
+  if (panel->form != F_KL || full->form != F_KL) return ctx->fail(MPSK_EINTERNAL, "allgather: tensors must be in KL form");
+  const size_t es = full->esize();
+  int64_t mx = 0;
+  for (int r = 0; r < ctx->nranks; ++r) mx = std::max(mx, panel_nelem(full, r, ctx->nranks));
+  if (panel->nelem != panel_nelem(full, ctx->rank, ctx->nranks) || panel->dtype != full->dtype) return ctx->fail(MPSK_ESPACE, "tensor is not this rank's row panel");
+  char* buf = (char*)ctx->alloc((size_t)mx * (ctx->nranks + 1) * es);
+  if (!buf) return MPSK_ENOMEM;
+  char* send = buf + (size_t)mx * ctx->nranks * es;
+  CUDA_TRY(ctx, cudaMemsetAsync(send, 0, (size_t)mx * es, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(send, panel->d, panel->bytes(), cudaMemcpyDeviceToDevice, ctx->stream));
+  int st = comm_allgather(ctx, send, buf, (size_t)mx * es);
+  if (st == MPSK_OK) {
+    std::vector<CopyTask> tasks;
+    for (int r = 0; r < ctx->nranks && st == MPSK_OK; ++r) st = scatter_panel_tasks(ctx, buf + (size_t)r * mx * es, r, ctx->nranks, full, &tasks);
+    if (st == MPSK_OK) st = run_copy_tasks(ctx, tasks, full->dtype == MPSK_C128);
+  }
+  ctx->free(buf);
+  return st;
 }
 
 // ------------------------------------------------------------------------------------------ random fill
@@ -469,22 +535,27 @@ int tensor_fill_random(Ctx* ctx, Tensor* t, uint64_t seed) {
     base += (uint64_t)t->Vl.n[b.jl] * t->Vr.n[b.jr];
   }
   if (tasks.empty()) return MPSK_OK;
-  FillTask* d = (FillTask*)ctx->alloc(tasks.size() * sizeof(FillTask));
-  if (!d) return MPSK_ENOMEM;
-  CUDA_TRY(ctx, cudaMemcpyAsync(d, tasks.data(), tasks.size() * sizeof(FillTask), cudaMemcpyHostToDevice, ctx->stream));
+  void* dv = nullptr;
+  MPSK_TRY(upload_table(ctx, tasks.data(), tasks.size() * sizeof(FillTask), &dv));
+  FillTask* d = (FillTask*)dv;
   dim3 grid(64, (unsigned)std::min<size_t>(tasks.size(), 1024));
   if (t->dtype == MPSK_C128) fill_kernel<true><<<grid, 256, 0, ctx->stream>>>(d, (int)tasks.size(), seed);
   else fill_kernel<false><<<grid, 256, 0, ctx->stream>>>(d, (int)tasks.size(), seed);
   ctx->launches++;
-  CUDA_TRY(ctx, cudaGetLastError());
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->free(d);
+  CUDA_TRY(ctx, cudaGetLastError());
   return MPSK_OK;
 }
 
 // ------------------------------------------------------------------------------------------ mix
-struct MixTile { int32_t task; int32_t pad; int64_t e0; };
-constexpr int MIX_CHUNK = 4096;
+// out[row, col] = sum_t coeff_t * src_t[row, col] over row-major rectangles: HBM streaming.
+// A CTA owns a tile of the destination rectangle, the term table of the task sits in shared memory, every thread keeps
+// MIX_R independent row accumulators for one column (MIX_R x terms loads in flight per thread, fully coalesced along
+// the contiguous column index, no integer division anywhere).  Two tile shapes: 256 columns x 8 rows for wide
+// rectangles, 64 columns x 32 rows for narrow ones (small sectors).
+struct MixTile { int32_t task, row0, col0, shape; };
+constexpr int MIX_R = 8;          // rows per thread
+constexpr int MIX_MAXT = 32;      // terms staged per round
 
 template <typename T> __device__ __forceinline__ T mix_zero();
 template <> __device__ __forceinline__ double mix_zero<double>() { return 0.0; }
@@ -494,24 +565,44 @@ __device__ __forceinline__ void mix_fma(double2& acc, double2 v, double cre, dou
   acc.x += cre * v.x - cim * v.y; acc.y += cre * v.y + cim * v.x;
 }
 
-// out[row, col] = sum_t coeff_t * src_t[row, col]; memory-bound streaming, coalesced along col.
 template <typename T>
 __global__ void __launch_bounds__(256) mix_kernel(const MixTask* __restrict__ tasks, const MixTerm* __restrict__ terms,
                                                   const MixTile* __restrict__ tiles, int ntiles) {
+  __shared__ MixTerm sterm[MIX_MAXT];
   for (int ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
     const MixTile tl = tiles[ti];
     const MixTask tk = tasks[tl.task];
-    const int64_t total = (int64_t)tk.rows * tk.cols;
-    const int64_t e1 = min(tl.e0 + (int64_t)MIX_CHUNK, total);
-    T* dst = (T*)tk.dst;
-    for (int64_t e = tl.e0 + threadIdx.x; e < e1; e += blockDim.x) {
-      const int row = (int)(e / tk.cols), col = (int)(e - (int64_t)row * tk.cols);
-      T acc = mix_zero<T>();
-      for (int t = tk.term_begin; t < tk.term_end; ++t) {
-        const MixTerm tm = terms[t];
-        mix_fma(acc, ((const T*)tm.src)[(int64_t)row * tm.lds + col], tm.cre, tm.cim);
+    const int nt = tk.term_end - tk.term_begin;
+    int col, row0;
+    if (tl.shape == 0) { col = tl.col0 + (int)threadIdx.x; row0 = tl.row0; }
+    else { col = tl.col0 + ((int)threadIdx.x & 63); row0 = tl.row0 + ((int)threadIdx.x >> 6) * MIX_R; }
+    const int nrow = min(MIX_R, tk.rows - row0);          // may be <= 0 for trailing threads
+    const bool active = col < tk.cols && nrow > 0;
+    T acc[MIX_R];
+#pragma unroll
+    for (int r = 0; r < MIX_R; ++r) acc[r] = mix_zero<T>();
+    for (int t0 = 0; t0 < nt; t0 += MIX_MAXT) {
+      const int cnt = min(MIX_MAXT, nt - t0);
+      __syncthreads();
+      if ((int)threadIdx.x < cnt) sterm[threadIdx.x] = terms[tk.term_begin + t0 + threadIdx.x];
+      __syncthreads();
+      if (active) {
+        for (int t = 0; t < cnt; ++t) {
+          const double cre = sterm[t].cre, cim = sterm[t].cim;
+          const int64_t lds = sterm[t].lds;
+          const T* src = (const T*)sterm[t].src + (int64_t)row0 * lds + col;
+          T v[MIX_R];
+#pragma unroll
+          for (int r = 0; r < MIX_R; ++r) v[r] = r < nrow ? src[(int64_t)r * lds] : mix_zero<T>();
+#pragma unroll
+          for (int r = 0; r < MIX_R; ++r) mix_fma(acc[r], v[r], cre, cim);
+        }
       }
-      dst[(int64_t)row * tk.ldd + col] = acc;
+    }
+    if (active) {
+      T* dst = (T*)tk.dst + (int64_t)row0 * tk.ldd + col;
+#pragma unroll
+      for (int r = 0; r < MIX_R; ++r) if (r < nrow) dst[(int64_t)r * tk.ldd] = acc[r];
     }
   }
 }
@@ -525,21 +616,23 @@ int mix_plan_build(Ctx* ctx, bool cplx, const std::vector<MixTask>& tasks, const
   std::vector<MixTile> tiles;
   const double es = cplx ? 16.0 : 8.0;
   for (size_t i = 0; i < tasks.size(); ++i) {
-    const int64_t total = (int64_t)tasks[i].rows * tasks[i].cols;
-    for (int64_t e0 = 0; e0 < total; e0 += MIX_CHUNK) tiles.push_back(MixTile{(int)i, 0, e0});
-    plan->bytes += es * total * (1 + tasks[i].term_end - tasks[i].term_begin);
+    const int rows = tasks[i].rows, cols = tasks[i].cols;
+    if (rows <= 0 || cols <= 0) continue;
+    if (cols > 96) {
+      for (int r0 = 0; r0 < rows; r0 += MIX_R)
+        for (int c0 = 0; c0 < cols; c0 += 256) tiles.push_back(MixTile{(int)i, r0, c0, 0});
+    } else {
+      for (int r0 = 0; r0 < rows; r0 += 4 * MIX_R)
+        for (int c0 = 0; c0 < cols; c0 += 64) tiles.push_back(MixTile{(int)i, r0, c0, 1});
+    }
+    plan->bytes += es * (double)rows * cols * (1 + tasks[i].term_end - tasks[i].term_begin);
   }
   plan->ntiles = (int)tiles.size();
   if (tiles.empty()) return MPSK_OK;
-  plan->d_tasks = ctx->alloc(tasks.size() * sizeof(MixTask));
-  plan->d_terms = ctx->alloc(std::max<size_t>(terms.size(), 1) * sizeof(MixTerm));
-  plan->d_tiles = ctx->alloc(tiles.size() * sizeof(MixTile));
-  if (!plan->d_tasks || !plan->d_terms || !plan->d_tiles) return MPSK_ENOMEM;
-  CUDA_TRY(ctx, cudaMemcpyAsync(plan->d_tasks, tasks.data(), tasks.size() * sizeof(MixTask), cudaMemcpyHostToDevice, ctx->stream));
-  if (!terms.empty())
-    CUDA_TRY(ctx, cudaMemcpyAsync(plan->d_terms, terms.data(), terms.size() * sizeof(MixTerm), cudaMemcpyHostToDevice, ctx->stream));
-  CUDA_TRY(ctx, cudaMemcpyAsync(plan->d_tiles, tiles.data(), tiles.size() * sizeof(MixTile), cudaMemcpyHostToDevice, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  MPSK_TRY(upload_table(ctx, tasks.data(), tasks.size() * sizeof(MixTask), &plan->d_tasks));
+  MixTerm dummy{nullptr, 0, 0.0, 0.0};
+  MPSK_TRY(upload_table(ctx, terms.empty() ? (const void*)&dummy : (const void*)terms.data(), std::max<size_t>(terms.size(), 1) * sizeof(MixTerm), &plan->d_terms));
+  MPSK_TRY(upload_table(ctx, tiles.data(), tiles.size() * sizeof(MixTile), &plan->d_tiles));
   return MPSK_OK;
 }
 

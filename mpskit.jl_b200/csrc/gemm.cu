@@ -390,20 +390,23 @@ int gemm_plan_build(Ctx* ctx, bool cplx, const std::vector<GemmProblemHost>& pro
     }
     const int pi = (int)dev.size();
     dev.push_back(d);
-    // raster: n-panels outer, m inner, so concurrently running CTAs share the B panel and stream A
-    for (int n0 = 0; n0 < h.N; n0 += BN)
-      for (int m0 = 0; m0 < h.M; m0 += BM) tiles.push_back(GemmTile{pi, m0, n0, 0});
+    // L2-aware raster: m-tiles are grouped into super-rows whose A panel (G x BM rows x K) stays L2-resident (~24 MB);
+    // inside a super-row the n-panels are the outer loop, so the ~148 concurrently running CTAs share one or a few B
+    // panels while the A super-row is re-used from L2 by every following n-panel instead of being streamed from DRAM
+    // once per n-panel (round 1: 42.9 GB of DRAM reads for 1.2 GB of stage-A operands).
+    const int64_t mt = (h.M + BM - 1) / BM;
+    int64_t G = ((int64_t)24 << 20) / std::max<int64_t>((int64_t)BM * h.K * (int64_t)esz, 1);
+    G = std::max<int64_t>(1, std::min<int64_t>(G, mt));
+    for (int64_t ms = 0; ms < mt; ms += G)
+      for (int n0 = 0; n0 < h.N; n0 += BN)
+        for (int64_t mi = ms; mi < std::min(ms + G, mt); ++mi) tiles.push_back(GemmTile{pi, (int32_t)(mi * BM), n0, 0});
   }
   plan->nprob = (int)dev.size();
   plan->ntiles = (int)tiles.size();
   plan->splitk = S;
   if (plan->nprob == 0) return MPSK_OK;
-  plan->d_probs = (GemmProblemDev*)ctx->alloc(dev.size() * sizeof(GemmProblemDev));
-  plan->d_tiles = (GemmTile*)ctx->alloc(tiles.size() * sizeof(GemmTile));
-  if (!plan->d_probs || !plan->d_tiles) return ctx->fail(MPSK_ENOMEM, "gemm plan alloc");
-  CUDA_TRY(ctx, cudaMemcpyAsync(plan->d_probs, dev.data(), dev.size() * sizeof(GemmProblemDev), cudaMemcpyHostToDevice, ctx->stream));
-  CUDA_TRY(ctx, cudaMemcpyAsync(plan->d_tiles, tiles.data(), tiles.size() * sizeof(GemmTile), cudaMemcpyHostToDevice, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+  { void* d = nullptr; MPSK_TRY(upload_table(ctx, dev.data(), dev.size() * sizeof(GemmProblemDev), &d)); plan->d_probs = (GemmProblemDev*)d; }
+  { void* d = nullptr; MPSK_TRY(upload_table(ctx, tiles.data(), tiles.size() * sizeof(GemmTile), &d)); plan->d_tiles = (GemmTile*)d; }
   if (!rtasks.empty()) {
     plan->reduce = new MixPlan;
     MPSK_TRY(mix_plan_build(ctx, cplx, rtasks, rterms, plan->reduce));
@@ -418,7 +421,7 @@ int gemm_plan_run(Ctx* ctx, const GemmPlan* plan) {
     if (plan->cplx) gemm_debug_kernel<true><<<grid, 256, 0, ctx->stream>>>(plan->d_probs, plan->nprob);
     else gemm_debug_kernel<false><<<grid, 256, 0, ctx->stream>>>(plan->d_probs, plan->nprob);
   } else {
-    static bool attr_set[3] = {false, false, false};
+    bool* attr_set = ctx->gemm_attr_set;
     if (plan->cplx && plan->narrow) {
       using Cfg = GemmCfg<true, GEMM_NARROW_N_CPLX>;
       const int grid = std::min(plan->ntiles, ctx->num_sms * Cfg::CTAS_PER_SM);

@@ -136,7 +136,7 @@ int heff_create(Ctx* ctx, int kind, const MpoSlice* h1, const MpoSlice* h2, cons
   auto Tptr = [&](int64_t off) { return (char*)op->T + off * es; };
   auto Uptr = [&](int64_t off) { return (char*)op->U + off * es; };
   const double kappa = cx ? 8.0 : 2.0;
-  op->flops = 0;
+  op->flops_ = 0;
   // ---- stage A
   std::vector<GemmProblemHost> pa;
   for (int jb = 0; jb < ngl; ++jb) {
@@ -144,7 +144,7 @@ int heff_create(Ctx* ctx, int kind, const MpoSlice* h1, const MpoSlice* h2, cons
     if (ga.rows == 0 || gx.rows == 0) continue;
     pa.push_back(GemmProblemHost{GLk.ptr(ga.off), xs.ptr(gx.off), Tptr(Toff[jb]), ga.ld, gx.ld, Tld[jb], (int32_t)ga.rows,
                                  (int32_t)gx.rows, (int32_t)ga.cols, 0});
-    op->flops += kappa * (double)ga.rows * gx.rows * ga.cols;
+    op->flops_ += kappa * (double)ga.rows * gx.rows * ga.cols;
   }
   // ---- mix + stage C
   std::vector<MixTask> tasks; std::vector<MixTerm> terms; std::vector<GemmProblemHost> pc;
@@ -180,15 +180,12 @@ int heff_create(Ctx* ctx, int kind, const MpoSlice* h1, const MpoSlice* h2, cons
     if (gz.cols == 0) continue;
     pc.push_back(GemmProblemHost{GRs.ptr(gz.off), Uptr(Uoff[b]), ys->ptr(bk.off), gz.ld, ldU, ys->groups[ja].ld, (int32_t)gz.rows,
                                  (int32_t)Vb.n[ja], (int32_t)gz.cols, 0});
-    op->flops += kappa * (double)gz.rows * Vb.n[ja] * klog;
+    op->flops_ += kappa * (double)gz.rows * Vb.n[ja] * klog;
   }
   op->gemmA.reset(new GemmPlan); op->gemmC.reset(new GemmPlan); op->mix.reset(new MixPlan);
   MPSK_TRY(gemm_plan_build(ctx, cx, pa, op->gemmA.get()));
   MPSK_TRY(mix_plan_build(ctx, cx, tasks, terms, op->mix.get()));
   MPSK_TRY(gemm_plan_build(ctx, cx, pc, op->gemmC.get()));
-  op->bound_x = op->xs->d; op->bound_y = ys->d;
-  op->GLk.get();
-  // keep the y staging tensor alive inside the op: reuse `bound_y` owner through a unique_ptr swap
   op->ybuf.reset(ys.release());
   *out = op.release();
   return MPSK_OK;
@@ -208,35 +205,105 @@ int heff_apply_local(Ctx* ctx, HeffOp* op, const Tensor* x, Tensor* y) {
   return MPSK_OK;
 }
 
+// allgather buffer (nranks slots + one send slot of the largest panel) and the two persistent scatter plans:
+// gathered panels -> yfull (full-vector apply) and gathered panels -> xs (Krylov apply on panel vectors)
+int HeffOp::ensure_gather() {
+  if (gather) return MPSK_OK;
+  if (ctx->nranks <= 1) return ctx->fail(MPSK_EINVAL, "row-panel operator used without a communicator");
+  const Tensor* like_ = xs.get();
+  const size_t es = like_->esize();
+  int64_t mx = 0;
+  for (int r = 0; r < ctx->nranks; ++r) mx = std::max(mx, panel_nelem(like_, r, ctx->nranks));
+  if (panel_nelem(like_, ctx->rank, ctx->nranks) != ybuf->nelem) return ctx->fail(MPSK_ESPACE, "left environment is not this rank's row panel");
+  gather_elems = mx;
+  gather = ctx->alloc((size_t)mx * (ctx->nranks + 1) * es);
+  if (!gather) return MPSK_ENOMEM;
+  CUDA_TRY(ctx, cudaMemsetAsync(gather, 0, (size_t)mx * (ctx->nranks + 1) * es, ctx->stream));
+  Tensor* yf = nullptr;
+  MPSK_TRY(tensor_create(ctx, like_->Vl, like_->mch, like_->Vr, like_->dtype, F_KL, true, &yf));
+  yfull.reset(yf);
+  std::vector<CopyTask> ty, tx;
+  for (int r = 0; r < ctx->nranks; ++r) {
+    MPSK_TRY(scatter_panel_tasks(ctx, (char*)gather + (size_t)r * mx * es, r, ctx->nranks, yf, &ty));
+    MPSK_TRY(scatter_panel_tasks(ctx, (char*)gather + (size_t)r * mx * es, r, ctx->nranks, xs.get(), &tx));
+  }
+  scatter.reset(new CopyPlan); scatter_x.reset(new CopyPlan);
+  MPSK_TRY(copy_plan_build(ctx, ty, like_->dtype == MPSK_C128, scatter.get()));
+  MPSK_TRY(copy_plan_build(ctx, tx, like_->dtype == MPSK_C128, scatter_x.get()));
+  return MPSK_OK;
+}
+
 // y = H_eff x.  Square operator: local.  Row-panel operator on a multi-rank context: every rank computes its panel,
 // one NCCL allgather over NVLink assembles the full y on all ranks (bitwise identical everywhere).
 int heff_apply(Ctx* ctx, HeffOp* op, const Tensor* x, Tensor* y) {
   if (!op->rectangular) return heff_apply_local(ctx, op, x, y);
-  if (ctx->nranks <= 1) return ctx->fail(MPSK_EINVAL, "row-panel operator applied without a communicator (use mpsk_op_apply_local)");
   if (!x->same_structure(*op->xs) || !y->same_structure(*op->xs)) return ctx->fail(MPSK_ESPACE, "vector structure does not match the operator");
+  MPSK_TRY(op->ensure_gather());
   MPSK_TRY(heff_apply_local(ctx, op, x, nullptr));
   const size_t es = y->esize();
-  if (!op->gather) {
-    int64_t mx = 0;
-    for (int r = 0; r < ctx->nranks; ++r) mx = std::max(mx, panel_nelem(y, r, ctx->nranks));
-    op->gather_elems = mx;
-    op->gather = ctx->alloc((size_t)mx * (ctx->nranks + 1) * es);
-    if (!op->gather) return MPSK_ENOMEM;
-    Tensor* yf = nullptr;
-    MPSK_TRY(tensor_create(ctx, y->Vl, y->mch, y->Vr, y->dtype, F_KL, true, &yf));
-    op->yfull.reset(yf);
-    std::vector<CopyTask> tasks;
-    for (int r = 0; r < ctx->nranks; ++r)
-      MPSK_TRY(scatter_panel_tasks(ctx, (char*)op->gather + (size_t)r * mx * es, r, ctx->nranks, yf, &tasks));
-    op->scatter.reset(new CopyPlan);
-    MPSK_TRY(copy_plan_build(ctx, tasks, y->dtype == MPSK_C128, op->scatter.get()));
-  }
   char* send = (char*)op->gather + (size_t)op->gather_elems * ctx->nranks * es;
-  if (panel_nelem(y, ctx->rank, ctx->nranks) != op->ybuf->nelem) return ctx->fail(MPSK_ESPACE, "left environment is not this rank's row panel");
   CUDA_TRY(ctx, cudaMemcpyAsync(send, op->ybuf->d, op->ybuf->bytes(), cudaMemcpyDeviceToDevice, ctx->stream));
   MPSK_TRY(comm_allgather(ctx, send, op->gather, (size_t)op->gather_elems * es));
   MPSK_TRY(copy_plan_run(ctx, op->scatter.get()));
   CUDA_TRY(ctx, cudaMemcpyAsync(y->d, op->yfull->d, y->bytes(), cudaMemcpyDeviceToDevice, ctx->stream));
+  return MPSK_OK;
+}
+
+// Panel in -> panel out (what a sharded Krylov solver iterates): allgather the panels of x straight into the operator's
+// input buffer (NCCL over NVLink + one scatter pass), then the local three-launch pipeline.  Krylov basis vectors, their
+// inner products and axpys stay 1/N per rank; no full-size vector other than the operator's input is ever materialised.
+int heff_apply_panel(Ctx* ctx, HeffOp* op, const Tensor* xp, Tensor* yp) {
+  if (!op->rectangular) return heff_apply_local(ctx, op, xp, yp);
+  if (!xp->same_structure(*op->ybuf) || !yp->same_structure(*op->ybuf)) return ctx->fail(MPSK_ESPACE, "panel structure does not match the operator");
+  MPSK_TRY(op->ensure_gather());
+  const size_t es = xp->esize();
+  char* send = (char*)op->gather + (size_t)op->gather_elems * ctx->nranks * es;
+  CUDA_TRY(ctx, cudaMemcpyAsync(send, xp->d, xp->bytes(), cudaMemcpyDeviceToDevice, ctx->stream));
+  MPSK_TRY(comm_allgather(ctx, send, op->gather, (size_t)op->gather_elems * es));
+  MPSK_TRY(copy_plan_run(ctx, op->scatter_x.get()));
+  MPSK_TRY(gemm_plan_run(ctx, op->gemmA.get()));
+  MPSK_TRY(mix_plan_run(ctx, op->mix.get()));
+  MPSK_TRY(gemm_plan_run(ctx, op->gemmC.get()));
+  if (yp->d != op->ybuf->d)
+    CUDA_TRY(ctx, cudaMemcpyAsync(yp->d, op->ybuf->d, yp->bytes(), cudaMemcpyDeviceToDevice, ctx->stream));
+  return MPSK_OK;
+}
+
+int HeffOp::apply(const Tensor* x, Tensor* y) { return heff_apply(ctx, this, x, y); }
+int HeffOp::apply_k(const Tensor* v, Tensor* w) { return heff_apply_panel(ctx, this, v, w); }
+
+int HeffOp::to_local(const Tensor* x, Tensor* loc) {
+  if (!rectangular) return LinOp::to_local(x, loc);
+  if (!x->same_structure(*xs) || !loc->same_structure(*ybuf)) return ctx->fail(MPSK_ESPACE, "to_local: structure mismatch");
+  Tensor* p = nullptr;
+  MPSK_TRY(tensor_row_panel(ctx, x, ctx->rank, ctx->nranks, &p));
+  std::unique_ptr<Tensor> pg(p);
+  if (p->nelem != loc->nelem) return ctx->fail(MPSK_EINTERNAL, "to_local: panel size mismatch");
+  CUDA_TRY(ctx, cudaMemcpyAsync(loc->d, p->d, p->bytes(), cudaMemcpyDeviceToDevice, ctx->stream));
+  return MPSK_OK;
+}
+
+int HeffOp::from_local(const Tensor* loc, Tensor* x) {
+  if (!rectangular) return LinOp::from_local(loc, x);
+  if (!x->same_structure(*xs) || !loc->same_structure(*ybuf)) return ctx->fail(MPSK_ESPACE, "from_local: structure mismatch");
+  MPSK_TRY(ensure_gather());
+  const size_t es = x->esize();
+  char* send = (char*)gather + (size_t)gather_elems * ctx->nranks * es;
+  CUDA_TRY(ctx, cudaMemcpyAsync(send, loc->d, loc->bytes(), cudaMemcpyDeviceToDevice, ctx->stream));
+  MPSK_TRY(comm_allgather(ctx, send, gather, (size_t)gather_elems * es));
+  MPSK_TRY(copy_plan_run(ctx, scatter.get()));
+  CUDA_TRY(ctx, cudaMemcpyAsync(x->d, yfull->d, x->bytes(), cudaMemcpyDeviceToDevice, ctx->stream));
+  return MPSK_OK;
+}
+
+int LinOp::to_local(const Tensor* x, Tensor* loc) {
+  if (!x->same_structure(*loc) || x->form != loc->form) return ctx->fail(MPSK_ESPACE, "to_local: structure mismatch");
+  if (x->d != loc->d) CUDA_TRY(ctx, cudaMemcpyAsync(loc->d, x->d, x->bytes(), cudaMemcpyDeviceToDevice, ctx->stream));
+  return MPSK_OK;
+}
+int LinOp::from_local(const Tensor* loc, Tensor* x) {
+  if (!x->same_structure(*loc) || x->form != loc->form) return ctx->fail(MPSK_ESPACE, "from_local: structure mismatch");
+  if (x->d != loc->d) CUDA_TRY(ctx, cudaMemcpyAsync(x->d, loc->d, x->bytes(), cudaMemcpyDeviceToDevice, ctx->stream));
   return MPSK_OK;
 }
 

@@ -10,6 +10,7 @@
 #include <complex>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <tuple>
 #include <unordered_map>
@@ -52,6 +53,7 @@ struct Ctx {
   void* pool_stream[4] = {nullptr, nullptr, nullptr, nullptr};   // worker streams / cuSOLVER handles of the factorisation pool
   void* pool_solver[4] = {nullptr, nullptr, nullptr, nullptr};
   int* pool_info[4] = {nullptr, nullptr, nullptr, nullptr};
+  void* pool = nullptr;         // WorkerPool* (svd.cu): persistent host threads driving the per-sector factorizations
   void* nccl = nullptr;         // ncclComm_t
   int rank = 0, nranks = 1;
   double* h_scratch = nullptr;  // pinned host scratch (scalars coming back from Krylov kernels)
@@ -60,6 +62,14 @@ struct Ctx {
   double* d_scratch = nullptr;  // device scratch for reductions
   size_t d_scratch_bytes = 0;
   TsvdSpectrum last_spectrum;
+  // pinned bump arena for the small task / tile tables of one-shot launches: the H2D copies are asynchronous and the
+  // arena is only recycled after a stream synchronisation, so building a launch never blocks the host
+  char* h_arena = nullptr; size_t h_arena_bytes = 0, h_arena_used = 0;
+  void* arena_take(size_t bytes);      // pinned host memory valid until the next wrap (which synchronises the stream)
+  bool gemm_attr_set[4] = {false, false, false, false};   // cudaFuncSetAttribute is per device -> per context
+  int profile = -1;                    // MPSK_PROFILE=1: host timers around the Krylov phases
+  double t_apply = 0, t_orth = 0, t_sync = 0;
+  std::recursive_mutex mu;             // every ABI entry locks the context: concurrent callers serialise
 
   void* alloc(size_t bytes);
   void free(void* p);
@@ -82,6 +92,7 @@ struct Space {
   bool operator==(const Space& o) const { return q == o.q && n == o.n && mod == o.mod; }
 };
 int space_from_abi(Ctx* ctx, const mpsk_space* s, Space* out);
+int upload_table(Ctx* ctx, const void* src, size_t bytes, void** d_out);   // async H2D of a small host table via the pinned arena
 
 // Device layouts ("forms") of a T[l, m, r] tensor.  Every form is a set of dense row-major group
 // matrices, one per sector of the grouping leg, chosen so that the contraction GEMMs need no
@@ -106,6 +117,7 @@ struct Tensor {
   std::vector<Group> groups;
   std::vector<int64_t> seg;            // [m * ngroups + g] row (K forms) / column (S forms) offset of label m in group g, -1 absent
   void* d = nullptr;
+  bool owns = true;                    // false: `d` aliases another buffer (views used by the Krylov solvers)
   int64_t nelem = 0;                   // elements including padding
   int nm() const { return (int)mch.size(); }
   int ngroups() const { return (int)groups.size(); }
@@ -114,7 +126,7 @@ struct Tensor {
   const Blk* find(int m, int jl) const { int i = blk_index[(size_t)m * Vl.nsec() + jl]; return i < 0 ? nullptr : &blks[i]; }
   char* ptr(int64_t off) const { return (char*)d + off * (int64_t)esize(); }
   bool same_structure(const Tensor& o) const { return Vl == o.Vl && Vr == o.Vr && mch == o.mch && dtype == o.dtype; }
-  ~Tensor() { if (d && ctx) ctx->free(d); }
+  ~Tensor() { if (d && ctx && owns) ctx->free(d); }
 };
 
 int tensor_create(Ctx* ctx, const Space& Vl, const std::vector<int32_t>& mch, const Space& Vr, int dtype, Form form,
@@ -129,9 +141,14 @@ int tensor_stack_labels(Ctx* ctx, const std::vector<const Tensor*>& ts, Tensor**
 int tensor_select_labels(Ctx* ctx, const Tensor* t, const int32_t* labels, int n, Tensor** out);
 int tensor_adjoint(Ctx* ctx, const Tensor* t, Tensor** out);
 void tensor_layout_only(Tensor* t);   // fills blks / groups / nelem for (Vl, mch, Vr, dtype, form) without allocating
+struct CopyTask;
 void panel_table(const Space& V, int nranks, std::vector<int64_t>* lo, std::vector<int64_t>* hi);
 void panel_bounds(const Space& V, int j, int rank, int nranks, int64_t* lo, int64_t* hi);
 int tensor_row_panel(Ctx* ctx, const Tensor* t, int rank, int nranks, Tensor** out);
+int tensor_panel(Ctx* ctx, const Tensor* t, int axis, int rank, int nranks, Tensor** out);   // axis 0: l index, 1: r index
+int scatter_panel_tasks_axis(Ctx* ctx, const void* src, int axis, int rank, int nranks, Tensor* full, std::vector<CopyTask>* tasks);
+int64_t panel_nelem_axis(const Tensor* full, int axis, int rank, int nranks);
+int tensor_allgather_panels(Ctx* ctx, const Tensor* panel, Tensor* full);
 int tensor_scatter_panel(Ctx* ctx, const void* src, int rank, int nranks, Tensor* full, bool sync);
 struct CopyTask;
 int scatter_panel_tasks(Ctx* ctx, const void* src, int rank, int nranks, Tensor* full, std::vector<CopyTask>* tasks);
@@ -200,40 +217,109 @@ struct MpoSlice {
   }
 };
 
+// ---- linear operators the Krylov solvers act on (effective Hamiltonians and transfer matrices)
+// Krylov vectors are tensors with the structure of `local_like()`: the full vector for ordinary operators, this rank's
+// row panel for a sharded effective Hamiltonian (then the inner products are partial sums + one fused allreduce).
+struct LinOp {
+  Ctx* ctx = nullptr; int dtype = MPSK_C128;
+  virtual ~LinOp() {}
+  virtual const Tensor* like() const = 0;                          // structure of the full vectors (ABI side)
+  virtual const Tensor* local_like() const { return like(); }      // structure of the Krylov vectors of this rank
+  virtual bool sharded() const { return false; }
+  virtual int apply(const Tensor* x, Tensor* y) = 0;               // y = f(x) on full vectors
+  virtual int apply_k(const Tensor* v, Tensor* w) { return apply(v, w); }   // on Krylov (local) vectors
+  virtual int to_local(const Tensor* x, Tensor* loc);              // default: copy
+  virtual int from_local(const Tensor* loc, Tensor* x);            // default: copy
+  virtual double flops() const { return 0.0; }
+};
+
 // ---- effective Hamiltonian = stage-A GEMMs -> mix -> stage-C GEMMs
 struct WEntry { int32_t i, k, mout, min; cplx c; };
-struct HeffOp {
-  Ctx* ctx = nullptr; int kind = 0; int dtype = MPSK_C128;
+struct HeffOp : LinOp {
+  int kind = 0;
   std::unique_ptr<Tensor> GLk;   // left env in KR form (owned copy)
   std::unique_ptr<Tensor> GRs;   // right env in SL form (owned copy)
   std::unique_ptr<Tensor> xs;    // input staging buffer / structure template of x (KL form)
   std::unique_ptr<Tensor> ybuf;  // output staging buffer (KL form, bra structure); plans are bound to xs / ybuf
   bool rectangular = false;      // bra space of GL != ket space of x: this op produces a row panel of y (multi-GPU sharding)
-  void* gather = nullptr; int64_t gather_elems = 0;   // allgather buffer (nranks x max panel elems)
-  std::unique_ptr<Tensor> yfull; std::unique_ptr<CopyPlan> scatter;   // persistent assembly of the gathered panels
+  void* gather = nullptr; int64_t gather_elems = 0;   // allgather buffer (nranks x max panel elems) + one send slot
+  std::unique_ptr<Tensor> yfull; std::unique_ptr<CopyPlan> scatter;     // gathered panels -> yfull (full-vector apply)
+  std::unique_ptr<CopyPlan> scatter_x;                                   // gathered panels -> xs   (Krylov apply)
   std::vector<WEntry> W;
   // workspaces
   void* T = nullptr; void* U = nullptr; int64_t T_elems = 0, U_elems = 0;
-  // plans are bound to concrete x / y buffers; rebuilt lazily when those change
-  const void* bound_x = nullptr; void* bound_y = nullptr;
   std::unique_ptr<GemmPlan> gemmA, gemmC; std::unique_ptr<MixPlan> mix;
-  double flops = 0;
+  double flops_ = 0;
   ~HeffOp();
+  const Tensor* like() const override { return xs.get(); }
+  const Tensor* local_like() const override { return rectangular ? ybuf.get() : xs.get(); }
+  bool sharded() const override { return rectangular; }
+  int apply(const Tensor* x, Tensor* y) override;
+  int apply_k(const Tensor* v, Tensor* w) override;
+  int to_local(const Tensor* x, Tensor* loc) override;
+  int from_local(const Tensor* loc, Tensor* x) override;
+  double flops() const override { return flops_; }
+  int ensure_gather();
 };
 int heff_create(Ctx* ctx, int kind, const MpoSlice* h1, const MpoSlice* h2, const Tensor* GL, const Tensor* GR,
                 const Tensor* x_like, HeffOp** out);
 int heff_apply(Ctx* ctx, HeffOp* op, const Tensor* x, Tensor* y);
 int heff_apply_local(Ctx* ctx, HeffOp* op, const Tensor* x, Tensor* y);
+int heff_apply_panel(Ctx* ctx, HeffOp* op, const Tensor* x_panel, Tensor* y_panel);
+
+// ---- one-site transfer with persistent plans: out = v * T(A, O, Abar) (left) or T(A, O, Abar) * v (right)
+struct TransferPlan {
+  Ctx* ctx = nullptr; bool left = true; bool cx = true;
+  std::unique_ptr<Tensor> Ak, Bs;            // site tensors in their GEMM forms (owned copies)
+  std::unique_ptr<Tensor> vin;               // input staging (KR form for left, KL for right)
+  std::unique_ptr<Tensor> vout;              // output in its native form (KR for left, KL for right)
+  std::unique_ptr<Tensor> in_like, out_like; // KL-form structure templates of input / output (no storage)
+  std::unique_ptr<CopyPlan> in_repack, out_repack;   // KL input -> vin (left only); vout -> KL out_kl (left only)
+  std::unique_ptr<Tensor> out_kl;            // left only: KL-form output staging
+  void* T = nullptr; void* Q = nullptr;
+  GemmPlan g1, g3; MixPlan mx;
+  double flops = 0;
+  // row-panel sharding of the output bra index (multi-GPU): this rank computes its panel, allgather assembles the rest
+  bool sharded = false; void* gather = nullptr; int64_t gather_elems = 0; std::unique_ptr<CopyPlan> scatter;
+  std::unique_ptr<Tensor> out_full;
+  ~TransferPlan();
+  const Tensor* result() const { return sharded ? out_full.get() : (left ? out_kl.get() : vout.get()); }
+};
+int transfer_plan_create(Ctx* ctx, bool left, const MpoSlice* h, const Tensor* A, const Tensor* Abar, const Tensor* v_like,
+                         bool sharded, TransferPlan** out);
+int transfer_plan_run(Ctx* ctx, TransferPlan* p, const Tensor* v);     // result in p->result() (KL form)
+
+// ---- transfer matrix over a unit cell as a linear operator (transfermatrix.jl:43-90), optionally regularised:
+// v -> T(v) - <l, T(v)> r
+struct TmOp : LinOp {
+  bool left = true;                                   // true: v * tm (sweep left -> right); false: tm * v
+  std::vector<std::unique_ptr<TransferPlan>> sites;   // in application order
+  std::unique_ptr<Tensor> vlike;                      // structure of the vectors (KL form, no storage... owns a buffer for apply staging)
+  std::unique_ptr<Tensor> ladj, rvec;                 // regularisation: ladj = adjoint(lvec) (dot partner), rvec
+  double* d_coef = nullptr;
+  double flops_ = 0;
+  ~TmOp();
+  const Tensor* like() const override { return vlike.get(); }
+  int apply(const Tensor* x, Tensor* y) override;
+  double flops() const override { return flops_; }
+};
 
 // ---- Krylov solvers (eigsolve.cu)
-int eigsolve_lanczos(Ctx* ctx, HeffOp* op, const Tensor* x0, int which, int krylovdim, int maxiter, double tol,
+int eigsolve_lanczos(Ctx* ctx, LinOp* op, const Tensor* x0, int which, int krylovdim, int maxiter, double tol,
                      cplx* val, Tensor* vec, mpsk_info* info);
-int eigsolve_arnoldi(Ctx* ctx, HeffOp* op, const Tensor* x0, int which, int krylovdim, int maxiter, double tol,
+int eigsolve_arnoldi(Ctx* ctx, LinOp* op, const Tensor* x0, int which, int krylovdim, int maxiter, double tol,
                      cplx* val, Tensor* vec, mpsk_info* info);
-int expv_lanczos(Ctx* ctx, HeffOp* op, cplx tau, const Tensor* y0, int krylovdim, int maxiter, double tol, Tensor* y,
+int expv_lanczos(Ctx* ctx, LinOp* op, cplx tau, const Tensor* y0, int krylovdim, int maxiter, double tol, Tensor* y,
                  mpsk_info* info);
+// (a0 + a1 f) x = b, restarted GMRES (KrylovKit.linsolve, mpohaminfenv.jl:95,113,146,164)
+int linsolve_gmres(Ctx* ctx, LinOp* op, const Tensor* b, const Tensor* x0, cplx a0, cplx a1, int krylovdim, int maxiter,
+                   double tol, Tensor* x, mpsk_info* info);
 // small dense host linear algebra
 void jacobi_eigh(int n, std::vector<double>& A /*n*n row-major, destroyed*/, std::vector<double>& evals, std::vector<double>& evecs);
+// complex Schur decomposition H = Z T Z^H of a general n x n matrix (column-major, overwritten by T), Z accumulated
+int schur_complex(int n, std::vector<cplx>& H, std::vector<cplx>& Z);
+// reorder the Schur form so that the eigenvalue at position `from` moves to position `to` (to <= from)
+void schur_move(int n, std::vector<cplx>& T, std::vector<cplx>& Z, int from, int to);
 
 // ---- transfers, local algebra, factorizations
 int transfer_left(Ctx* ctx, const MpoSlice* h, const Tensor* A, const Tensor* Abar, const Tensor* GL, Tensor** out);
@@ -243,6 +329,8 @@ int mul_bond_right(Ctx* ctx, const Tensor* A, const Tensor* C, Tensor** out);
 int mul_bond_left(Ctx* ctx, const Tensor* C, const Tensor* A, Tensor** out);
 int tsvd(Ctx* ctx, const Tensor* ac2, int d1, const int32_t* p1_charge, mpsk_trunc trunc, Tensor** U, Tensor** S, Tensor** Vh, double* eps);
 int qrpos(Ctx* ctx, const Tensor* A, bool left, Tensor** Q, Tensor** R);
+void pool_destroy(Ctx* ctx);
+int comm_allreduce_sum(Ctx* ctx, void* buf, size_t ndoubles);
 
 }  // namespace mpsk
 

@@ -22,165 +22,291 @@ struct Owned {
   ~Owned() { if (own) delete t; }
 };
 
+// ------------------------------------------------------------------------------------------ persistent transfer plans
+TransferPlan::~TransferPlan() { if (ctx) { ctx->free(T); ctx->free(Q); ctx->free(gather); } }
+
+// dst = (conj) src for two tensors of the same structure in (possibly) different forms; asynchronous
+static int tensor_copy_into(Ctx* ctx, const Tensor* src, Tensor* dst, bool conj) {
+  if (!src->same_structure(*dst)) return ctx->fail(MPSK_ESPACE, "tensor structures differ");
+  const bool cj = conj && src->dtype == MPSK_C128;
+  if (src->form == dst->form && !cj) {
+    if (src->d != dst->d) CUDA_TRY(ctx, cudaMemcpyAsync(dst->d, src->d, src->bytes(), cudaMemcpyDeviceToDevice, ctx->stream));
+    return MPSK_OK;
+  }
+  std::vector<CopyTask> tasks;
+  tasks.reserve(src->blks.size());
+  for (size_t b = 0; b < src->blks.size(); ++b) {
+    const Blk& s = src->blks[b]; const Blk& d = dst->blks[b];
+    tasks.push_back(CopyTask{src->ptr(s.off), dst->ptr(d.off), s.sl, s.sr, d.sl, d.sr, (int32_t)src->Vl.n[s.jl], (int32_t)src->Vr.n[s.jr], cj ? 1 : 0, 0, nullptr});
+  }
+  return run_copy_tasks(ctx, tasks, src->dtype == MPSK_C128);
+}
+
+static int alloc_work(Ctx* ctx, int64_t elems, size_t es, void** out) {
+  elems = std::max<int64_t>(elems, GROUP_ALIGN);
+  *out = ctx->alloc((size_t)elems * es);
+  if (!*out) return MPSK_ENOMEM;
+  CUDA_TRY(ctx, cudaMemsetAsync(*out, 0, (size_t)elems * es, ctx->stream));
+  return MPSK_OK;
+}
+
 // GL'[a' k; b'] = sum GL[a j; b] A[b s; b'] O[j,k][s',s] conj(Abar[a s'; a'])        (transfer.jl:105-107,166-211)
-int transfer_left(Ctx* ctx, const MpoSlice* h, const Tensor* A, const Tensor* Abar, const Tensor* GL, Tensor** out) {
+static int build_left(Ctx* ctx, TransferPlan* P, const MpoSlice* h, const Tensor* A, const Tensor* Abar, const Tensor* GL) {
   if (A->dtype != GL->dtype || Abar->dtype != GL->dtype) return ctx->fail(MPSK_EINVAL, "mixed scalar types");
   if (!(GL->Vr == A->Vl)) return ctx->fail(MPSK_ESPACE, "transfer_left: ket space of GL != left space of A");
   if (!(GL->Vl == Abar->Vl)) return ctx->fail(MPSK_ESPACE, "transfer_left: bra space of GL != left space of Abar");
   if (h->odim != GL->nm() || h->d != A->nm() || h->d != Abar->nm()) return ctx->fail(MPSK_ESPACE, "transfer_left: MPO slice does not match");
   const bool cx = GL->dtype == MPSK_C128;
   const size_t es = cx ? 16 : 8;
+  const double kappa = cx ? 8.0 : 2.0;
   const int od = h->odim, d = h->d;
   for (int j = 0; j < od; ++j) if (A->Vl.norm(-(int64_t)GL->mch[j]) != A->Vl.norm(h->cl[j])) return ctx->fail(MPSK_ESPACE, "transfer_left: level charges of GL and slice differ");
-  Owned Ak, Gk, Bs;
-  MPSK_TRY(tensor_as_form(ctx, A, F_KL, false, &Ak.t, &Ak.own));
-  MPSK_TRY(tensor_as_form(ctx, GL, F_KR, false, &Gk.t, &Gk.own));
-  MPSK_TRY(tensor_as_form(ctx, Abar, F_SL, true, &Bs.t, &Bs.own));
+  { Tensor* t = nullptr; MPSK_TRY(tensor_repack(ctx, A, F_KL, false, &t)); P->Ak.reset(t); }
+  { Tensor* t = nullptr; MPSK_TRY(tensor_repack(ctx, Abar, F_SL, true, &t)); P->Bs.reset(t); }
+  { Tensor* t = nullptr; MPSK_TRY(tensor_create(ctx, GL->Vl, GL->mch, GL->Vr, GL->dtype, F_KR, true, &t)); P->vin.reset(t); }
+  const Tensor* Ak = P->Ak.get(); const Tensor* Gk = P->vin.get(); const Tensor* Bs = P->Bs.get();
   std::vector<int32_t> mo(od);
   for (int k = 0; k < od; ++k) mo[k] = -h->cr[k];
   Tensor* o = nullptr;
   MPSK_TRY(tensor_create(ctx, Abar->Vr, mo, A->Vr, GL->dtype, F_KR, true, &o));
-  std::unique_ptr<Tensor> og(o);
+  P->vout.reset(o);
+  { Tensor* t = nullptr; MPSK_TRY(tensor_create(ctx, Abar->Vr, mo, A->Vr, GL->dtype, F_KL, true, &t)); P->out_kl.reset(t); }
   const Space& Vb = A->Vl;
   const int nb = Vb.nsec();
   // step 1: T^T_jb[(s,b') x (j,a)] = A_KL(jb) * GL_KR(jb)^T
   std::vector<int64_t> Toff(nb), Tld(nb); int64_t tot = 0;
-  for (int jb = 0; jb < nb; ++jb) { Tld[jb] = pad(Gk.t->groups[jb].rows); Toff[jb] = tot; tot += padg(Ak.t->groups[jb].rows * Tld[jb]); }
-  Work T; MPSK_TRY(T.init(ctx, tot, es));
+  for (int jb = 0; jb < nb; ++jb) { Tld[jb] = pad(Gk->groups[jb].rows); Toff[jb] = tot; tot += padg(Ak->groups[jb].rows * Tld[jb]); }
+  MPSK_TRY(alloc_work(ctx, tot, es, &P->T));
+  auto Tat = [&](int64_t off) { return (char*)P->T + off * es; };
   std::vector<GemmProblemHost> p1;
   for (int jb = 0; jb < nb; ++jb) {
-    const Group& ga = Ak.t->groups[jb]; const Group& gg = Gk.t->groups[jb];
+    const Group& ga = Ak->groups[jb]; const Group& gg = Gk->groups[jb];
     if (!ga.rows || !gg.rows) continue;
-    p1.push_back(GemmProblemHost{Ak.t->ptr(ga.off), Gk.t->ptr(gg.off), T.at(Toff[jb]), ga.ld, gg.ld, Tld[jb], (int32_t)ga.rows, (int32_t)gg.rows, (int32_t)ga.cols, 0});
+    p1.push_back(GemmProblemHost{Ak->ptr(ga.off), Gk->ptr(gg.off), Tat(Toff[jb]), ga.ld, gg.ld, Tld[jb], (int32_t)ga.rows, (int32_t)gg.rows, (int32_t)ga.cols, 0});
+    P->flops += kappa * (double)ga.rows * gg.rows * ga.cols;
   }
   // step 2/3
   std::vector<int64_t> Qoff(o->blks.size()); tot = 0;
-  for (size_t b = 0; b < o->blks.size(); ++b) { Qoff[b] = tot; tot += padg(o->Vr.n[o->blks[b].jr] * Bs.t->groups[o->blks[b].jl].ld); }
-  Work Q; MPSK_TRY(Q.init(ctx, tot, es));
+  for (size_t b = 0; b < o->blks.size(); ++b) { Qoff[b] = tot; tot += padg(o->Vr.n[o->blks[b].jr] * Bs->groups[o->blks[b].jl].ld); }
+  MPSK_TRY(alloc_work(ctx, tot, es, &P->Q));
+  auto Qat = [&](int64_t off) { return (char*)P->Q + off * es; };
   std::vector<MixTask> tasks; std::vector<MixTerm> terms; std::vector<GemmProblemHost> p3;
-  const int ngB = Bs.t->Vr.nsec();   // SL groups = r sectors of Abar (a')
+  const int ngB = Bs->Vr.nsec();   // SL groups = r sectors of Abar (a')
   for (size_t b = 0; b < o->blks.size(); ++b) {
     const Blk& bk = o->blks[b];
     const int k = bk.m, jap = bk.jl, jbp = bk.jr;
-    const Group& gB = Bs.t->groups[jap];
+    const Group& gB = Bs->groups[jap];
     for (int sp = 0; sp < d; ++sp) {
-      const int64_t seg = Bs.t->seg[(size_t)sp * ngB + jap];
+      const int64_t seg = Bs->seg[(size_t)sp * ngB + jap];
       if (seg < 0) continue;
-      const int ja = Bs.t->Vl.find((int64_t)Bs.t->Vr.q[jap] - Bs.t->mch[sp]);
-      MixTask tk; tk.dst = Q.at(Qoff[b] + seg); tk.ldd = gB.ld; tk.rows = (int32_t)o->Vr.n[jbp]; tk.cols = (int32_t)Bs.t->Vl.n[ja];
+      const int ja = Bs->Vl.find((int64_t)Bs->Vr.q[jap] - Bs->mch[sp]);
+      MixTask tk; tk.dst = Qat(Qoff[b] + seg); tk.ldd = gB.ld; tk.rows = (int32_t)o->Vr.n[jbp]; tk.cols = (int32_t)Bs->Vl.n[ja];
       tk.term_begin = (int32_t)terms.size();
       for (int j = 0; j < od; ++j) {
         if (!h->kind[j * od + k]) continue;
-        for (int s = 0; s < d; ++s) {
-          const cplx c = h->elem(j, k, sp, s);
+        for (int s_ = 0; s_ < d; ++s_) {
+          const cplx c = h->elem(j, k, sp, s_);
           if (c == cplx(0.0)) continue;
-          const int jb = Vb.find((int64_t)A->Vr.q[jbp] - A->mch[s]);
+          const int jb = Vb.find((int64_t)o->Vr.q[jbp] - A->mch[s_]);
           if (jb < 0) continue;
-          const Blk* ab = Ak.t->find(s, jb);
-          if (!ab || ab->jr != jbp) continue;
-          const int jbra = Gk.t->Vl.find((int64_t)Vb.q[jb] - Gk.t->mch[j]);
+          const Blk* ab = Ak->find(s_, jb);
+          if (!ab || Ak->Vr.q[ab->jr] != o->Vr.q[jbp]) continue;
+          const int jbra = Gk->Vl.find((int64_t)Vb.q[jb] - Gk->mch[j]);
           if (jbra < 0) continue;
           if (jbra != ja) return ctx->fail(MPSK_ESPACE, "transfer_left: MPO entry (%d,%d) violates charge conservation", j, k);
-          const int64_t rowoff = Ak.t->seg[(size_t)s * nb + jb], coloff = Gk.t->seg[(size_t)j * nb + jb];
+          const int64_t rowoff = Ak->seg[(size_t)s_ * nb + jb], coloff = Gk->seg[(size_t)j * nb + jb];
           if (rowoff < 0 || coloff < 0) return ctx->fail(MPSK_EINTERNAL, "transfer_left: missing segment");
-          terms.push_back(MixTerm{T.at(Toff[jb] + rowoff * Tld[jb] + coloff), Tld[jb], c.real(), c.imag()});
+          terms.push_back(MixTerm{Tat(Toff[jb] + rowoff * Tld[jb] + coloff), Tld[jb], c.real(), c.imag()});
         }
       }
       tk.term_end = (int32_t)terms.size();
       if (tk.term_end > tk.term_begin) tasks.push_back(tk);
     }
     if (!gB.cols) continue;
-    p3.push_back(GemmProblemHost{Bs.t->ptr(gB.off), Q.at(Qoff[b]), o->ptr(bk.off), gB.ld, gB.ld, o->groups[jbp].ld, (int32_t)gB.rows, (int32_t)o->Vr.n[jbp], (int32_t)gB.cols, 0});
+    p3.push_back(GemmProblemHost{Bs->ptr(gB.off), Qat(Qoff[b]), o->ptr(bk.off), gB.ld, gB.ld, o->groups[jbp].ld, (int32_t)gB.rows, (int32_t)o->Vr.n[jbp], (int32_t)gB.cols, 0});
+    P->flops += kappa * (double)gB.rows * o->Vr.n[jbp] * gB.cols;
   }
-  GemmPlan g1, g3; MixPlan mx;
-  MPSK_TRY(gemm_plan_build(ctx, cx, p1, &g1));
-  MPSK_TRY(mix_plan_build(ctx, cx, tasks, terms, &mx));
-  MPSK_TRY(gemm_plan_build(ctx, cx, p3, &g3));
-  MPSK_TRY(gemm_plan_run(ctx, &g1));
-  MPSK_TRY(mix_plan_run(ctx, &mx));
-  MPSK_TRY(gemm_plan_run(ctx, &g3));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // plans and workspaces die with this scope
-  *out = og.release();
+  MPSK_TRY(gemm_plan_build(ctx, cx, p1, &P->g1));
+  MPSK_TRY(mix_plan_build(ctx, cx, tasks, terms, &P->mx));
+  MPSK_TRY(gemm_plan_build(ctx, cx, p3, &P->g3));
   return MPSK_OK;
 }
 
 // GR'[a j; b] = sum A[a s; c] O[j,k][s',s] conj(Abar[b s'; c']) GR[c k; c']            (transfer.jl:108-110,212-259)
-int transfer_right(Ctx* ctx, const MpoSlice* h, const Tensor* A, const Tensor* Abar, const Tensor* GR, Tensor** out) {
+static int build_right(Ctx* ctx, TransferPlan* P, const MpoSlice* h, const Tensor* A, const Tensor* Abar, const Tensor* GR) {
   if (A->dtype != GR->dtype || Abar->dtype != GR->dtype) return ctx->fail(MPSK_EINVAL, "mixed scalar types");
   if (!(GR->Vl == A->Vr)) return ctx->fail(MPSK_ESPACE, "transfer_right: ket space of GR != right space of A");
   if (!(GR->Vr == Abar->Vr)) return ctx->fail(MPSK_ESPACE, "transfer_right: bra space of GR != right space of Abar");
   if (h->odim != GR->nm() || h->d != A->nm() || h->d != Abar->nm()) return ctx->fail(MPSK_ESPACE, "transfer_right: MPO slice does not match");
   const bool cx = GR->dtype == MPSK_C128;
   const size_t es = cx ? 16 : 8;
+  const double kappa = cx ? 8.0 : 2.0;
   const int od = h->odim, d = h->d;
   for (int k = 0; k < od; ++k) if (A->Vl.norm((int64_t)GR->mch[k]) != A->Vl.norm(h->cr[k])) return ctx->fail(MPSK_ESPACE, "transfer_right: level charges of GR and slice differ");
-  Owned Ak, Gk, Bs;
-  MPSK_TRY(tensor_as_form(ctx, A, F_KR, false, &Ak.t, &Ak.own));
-  MPSK_TRY(tensor_as_form(ctx, GR, F_KL, false, &Gk.t, &Gk.own));
-  MPSK_TRY(tensor_as_form(ctx, Abar, F_SR, true, &Bs.t, &Bs.own));
+  { Tensor* t = nullptr; MPSK_TRY(tensor_repack(ctx, A, F_KR, false, &t)); P->Ak.reset(t); }
+  { Tensor* t = nullptr; MPSK_TRY(tensor_repack(ctx, Abar, F_SR, true, &t)); P->Bs.reset(t); }
+  { Tensor* t = nullptr; MPSK_TRY(tensor_create(ctx, GR->Vl, GR->mch, GR->Vr, GR->dtype, F_KL, true, &t)); P->vin.reset(t); }
+  const Tensor* Ak = P->Ak.get(); const Tensor* Gk = P->vin.get(); const Tensor* Bs = P->Bs.get();
   std::vector<int32_t> mo(od);
   for (int j = 0; j < od; ++j) mo[j] = h->cl[j];
   Tensor* o = nullptr;
   MPSK_TRY(tensor_create(ctx, A->Vl, mo, Abar->Vl, GR->dtype, F_KL, true, &o));
-  std::unique_ptr<Tensor> og(o);
+  P->vout.reset(o);
   const Space& Vc = A->Vr;
   const int nc = Vc.nsec();
   // step 1: T^T_jc[(s,a) x (k,c')] = A_KR(jc) * GR_KL(jc)^T
   std::vector<int64_t> Toff(nc), Tld(nc); int64_t tot = 0;
-  for (int jc = 0; jc < nc; ++jc) { Tld[jc] = pad(Gk.t->groups[jc].rows); Toff[jc] = tot; tot += padg(Ak.t->groups[jc].rows * Tld[jc]); }
-  Work T; MPSK_TRY(T.init(ctx, tot, es));
+  for (int jc = 0; jc < nc; ++jc) { Tld[jc] = pad(Gk->groups[jc].rows); Toff[jc] = tot; tot += padg(Ak->groups[jc].rows * Tld[jc]); }
+  MPSK_TRY(alloc_work(ctx, tot, es, &P->T));
+  auto Tat = [&](int64_t off) { return (char*)P->T + off * es; };
   std::vector<GemmProblemHost> p1;
   for (int jc = 0; jc < nc; ++jc) {
-    const Group& ga = Ak.t->groups[jc]; const Group& gg = Gk.t->groups[jc];
+    const Group& ga = Ak->groups[jc]; const Group& gg = Gk->groups[jc];
     if (!ga.rows || !gg.rows) continue;
-    p1.push_back(GemmProblemHost{Ak.t->ptr(ga.off), Gk.t->ptr(gg.off), T.at(Toff[jc]), ga.ld, gg.ld, Tld[jc], (int32_t)ga.rows, (int32_t)gg.rows, (int32_t)ga.cols, 0});
+    p1.push_back(GemmProblemHost{Ak->ptr(ga.off), Gk->ptr(gg.off), Tat(Toff[jc]), ga.ld, gg.ld, Tld[jc], (int32_t)ga.rows, (int32_t)gg.rows, (int32_t)ga.cols, 0});
+    P->flops += kappa * (double)ga.rows * gg.rows * ga.cols;
   }
   std::vector<int64_t> Qoff(o->blks.size()); tot = 0;
-  for (size_t b = 0; b < o->blks.size(); ++b) { Qoff[b] = tot; tot += padg(o->Vl.n[o->blks[b].jl] * Bs.t->groups[o->blks[b].jr].ld); }
-  Work Q; MPSK_TRY(Q.init(ctx, tot, es));
+  for (size_t b = 0; b < o->blks.size(); ++b) { Qoff[b] = tot; tot += padg(o->Vl.n[o->blks[b].jl] * Bs->groups[o->blks[b].jr].ld); }
+  MPSK_TRY(alloc_work(ctx, tot, es, &P->Q));
+  auto Qat = [&](int64_t off) { return (char*)P->Q + off * es; };
   std::vector<MixTask> tasks; std::vector<MixTerm> terms; std::vector<GemmProblemHost> p3;
-  const int ngB = Bs.t->Vl.nsec();   // SR groups = l sectors of Abar (b)
+  const int ngB = Bs->Vl.nsec();   // SR groups = l sectors of Abar (b)
   for (size_t b = 0; b < o->blks.size(); ++b) {
     const Blk& bk = o->blks[b];
     const int j = bk.m, ja = bk.jl, jb = bk.jr;
-    const Group& gB = Bs.t->groups[jb];
+    const Group& gB = Bs->groups[jb];
     for (int sp = 0; sp < d; ++sp) {
-      const int64_t seg = Bs.t->seg[(size_t)sp * ngB + jb];
+      const int64_t seg = Bs->seg[(size_t)sp * ngB + jb];
       if (seg < 0) continue;
-      const int jcp = Bs.t->Vr.find((int64_t)Bs.t->Vl.q[jb] + Bs.t->mch[sp]);
-      MixTask tk; tk.dst = Q.at(Qoff[b] + seg); tk.ldd = gB.ld; tk.rows = (int32_t)o->Vl.n[ja]; tk.cols = (int32_t)Bs.t->Vr.n[jcp];
+      const int jcp = Bs->Vr.find((int64_t)Bs->Vl.q[jb] + Bs->mch[sp]);
+      MixTask tk; tk.dst = Qat(Qoff[b] + seg); tk.ldd = gB.ld; tk.rows = (int32_t)o->Vl.n[ja]; tk.cols = (int32_t)Bs->Vr.n[jcp];
       tk.term_begin = (int32_t)terms.size();
       for (int k = 0; k < od; ++k) {
         if (!h->kind[j * od + k]) continue;
-        for (int s = 0; s < d; ++s) {
-          const cplx c = h->elem(j, k, sp, s);
+        for (int s_ = 0; s_ < d; ++s_) {
+          const cplx c = h->elem(j, k, sp, s_);
           if (c == cplx(0.0)) continue;
-          const Blk* ab = Ak.t->find(s, ja);
+          const Blk* ab = Ak->find(s_, ja);
           if (!ab) continue;
           const int jc = ab->jr;
-          const int jbra = Gk.t->Vr.find((int64_t)Vc.q[jc] + Gk.t->mch[k]);
+          const int jbra = Gk->Vr.find((int64_t)Vc.q[jc] + Gk->mch[k]);
           if (jbra < 0) continue;
           if (jbra != jcp) return ctx->fail(MPSK_ESPACE, "transfer_right: MPO entry (%d,%d) violates charge conservation", j, k);
-          const int64_t rowoff = Ak.t->seg[(size_t)s * nc + jc], coloff = Gk.t->seg[(size_t)k * nc + jc];
+          const int64_t rowoff = Ak->seg[(size_t)s_ * nc + jc], coloff = Gk->seg[(size_t)k * nc + jc];
           if (rowoff < 0 || coloff < 0) return ctx->fail(MPSK_EINTERNAL, "transfer_right: missing segment");
-          terms.push_back(MixTerm{T.at(Toff[jc] + rowoff * Tld[jc] + coloff), Tld[jc], c.real(), c.imag()});
+          terms.push_back(MixTerm{Tat(Toff[jc] + rowoff * Tld[jc] + coloff), Tld[jc], c.real(), c.imag()});
         }
       }
       tk.term_end = (int32_t)terms.size();
       if (tk.term_end > tk.term_begin) tasks.push_back(tk);
     }
     if (!gB.cols) continue;
-    p3.push_back(GemmProblemHost{Bs.t->ptr(gB.off), Q.at(Qoff[b]), o->ptr(bk.off), gB.ld, gB.ld, o->groups[ja].ld, (int32_t)gB.rows, (int32_t)o->Vl.n[ja], (int32_t)gB.cols, 0});
+    p3.push_back(GemmProblemHost{Bs->ptr(gB.off), Qat(Qoff[b]), o->ptr(bk.off), gB.ld, gB.ld, o->groups[ja].ld, (int32_t)gB.rows, (int32_t)o->Vl.n[ja], (int32_t)gB.cols, 0});
+    P->flops += kappa * (double)gB.rows * o->Vl.n[ja] * gB.cols;
   }
-  GemmPlan g1, g3; MixPlan mx;
-  MPSK_TRY(gemm_plan_build(ctx, cx, p1, &g1));
-  MPSK_TRY(mix_plan_build(ctx, cx, tasks, terms, &mx));
-  MPSK_TRY(gemm_plan_build(ctx, cx, p3, &g3));
-  MPSK_TRY(gemm_plan_run(ctx, &g1));
-  MPSK_TRY(mix_plan_run(ctx, &mx));
-  MPSK_TRY(gemm_plan_run(ctx, &g3));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  *out = og.release();
+  MPSK_TRY(gemm_plan_build(ctx, cx, p1, &P->g1));
+  MPSK_TRY(mix_plan_build(ctx, cx, tasks, terms, &P->mx));
+  MPSK_TRY(gemm_plan_build(ctx, cx, p3, &P->g3));
+  return MPSK_OK;
+}
+
+// Multi-GPU: the update is sharded over the OUTPUT KET index (b' of GL', a of GR'), i.e. over the free bond index of the
+// ket tensor A.  Both GEMM stages then shrink by 1/N (a split over the bra index would leave stage 1 replicated), there
+// are no partial sums, and one allgather assembles the full environment on every rank (bit-identical everywhere).
+int transfer_plan_create(Ctx* ctx, bool left, const MpoSlice* h, const Tensor* A, const Tensor* Abar, const Tensor* v_like,
+                         bool sharded, TransferPlan** out) {
+  std::unique_ptr<TransferPlan> P(new TransferPlan);
+  P->ctx = ctx; P->left = left; P->cx = v_like->dtype == MPSK_C128;
+  sharded = sharded && ctx->nranks > 1;
+  P->sharded = sharded;
+  const Tensor* Ause = A; std::unique_ptr<Tensor> Apan;
+  if (sharded) {
+    Tensor* t = nullptr;
+    MPSK_TRY(tensor_panel(ctx, A, left ? 1 : 0, ctx->rank, ctx->nranks, &t));
+    Apan.reset(t); Ause = t;
+  }
+  MPSK_TRY(left ? build_left(ctx, P.get(), h, Ause, Abar, v_like) : build_right(ctx, P.get(), h, Ause, Abar, v_like));
+  if (sharded) {
+    const Tensor* res = left ? P->out_kl.get() : P->vout.get();
+    Tensor* full = nullptr;
+    if (left) MPSK_TRY(tensor_create(ctx, res->Vl, res->mch, A->Vr, res->dtype, F_KL, true, &full));
+    else MPSK_TRY(tensor_create(ctx, A->Vl, res->mch, res->Vr, res->dtype, F_KL, true, &full));
+    P->out_full.reset(full);
+    const int axis = left ? 1 : 0;
+    int64_t mx = 0;
+    for (int r = 0; r < ctx->nranks; ++r) mx = std::max(mx, panel_nelem_axis(full, axis, r, ctx->nranks));
+    if (panel_nelem_axis(full, axis, ctx->rank, ctx->nranks) != res->nelem) return ctx->fail(MPSK_EINTERNAL, "transfer: panel layout mismatch");
+    const size_t es = res->esize();
+    P->gather_elems = mx;
+    P->gather = ctx->alloc((size_t)mx * (ctx->nranks + 1) * es);
+    if (!P->gather) return MPSK_ENOMEM;
+    CUDA_TRY(ctx, cudaMemsetAsync(P->gather, 0, (size_t)mx * (ctx->nranks + 1) * es, ctx->stream));
+    std::vector<CopyTask> tasks;
+    for (int r = 0; r < ctx->nranks; ++r)
+      MPSK_TRY(scatter_panel_tasks_axis(ctx, (char*)P->gather + (size_t)r * mx * es, axis, r, ctx->nranks, full, &tasks));
+    P->scatter.reset(new CopyPlan);
+    MPSK_TRY(copy_plan_build(ctx, tasks, P->cx, P->scatter.get()));
+  }
+  *out = P.release();
+  return MPSK_OK;
+}
+
+int transfer_plan_run(Ctx* ctx, TransferPlan* P, const Tensor* v) {
+  MPSK_TRY(tensor_copy_into(ctx, v, P->vin.get(), false));
+  MPSK_TRY(gemm_plan_run(ctx, &P->g1));
+  MPSK_TRY(mix_plan_run(ctx, &P->mx));
+  MPSK_TRY(gemm_plan_run(ctx, &P->g3));
+  if (P->left) MPSK_TRY(tensor_copy_into(ctx, P->vout.get(), P->out_kl.get(), false));
+  if (P->sharded) {
+    const Tensor* res = P->left ? P->out_kl.get() : P->vout.get();
+    const size_t es = res->esize();
+    char* send = (char*)P->gather + (size_t)P->gather_elems * ctx->nranks * es;
+    CUDA_TRY(ctx, cudaMemcpyAsync(send, res->d, res->bytes(), cudaMemcpyDeviceToDevice, ctx->stream));
+    MPSK_TRY(comm_allgather(ctx, send, P->gather, (size_t)P->gather_elems * es));
+    MPSK_TRY(copy_plan_run(ctx, P->scatter.get()));
+  }
+  return MPSK_OK;
+}
+
+static int transfer_once(Ctx* ctx, bool left, const MpoSlice* h, const Tensor* A, const Tensor* Abar, const Tensor* v, Tensor** out) {
+  TransferPlan* P = nullptr;
+  MPSK_TRY(transfer_plan_create(ctx, left, h, A, Abar, v, /*sharded=*/!(ctx->flags & MPSK_FLAG_REPLICATE_LOCAL), &P));
+  std::unique_ptr<TransferPlan> pg(P);
+  MPSK_TRY(transfer_plan_run(ctx, P, v));
+  // hand the result tensor over to the caller (the plan and its workspaces are released in stream order)
+  if (P->sharded) *out = P->out_full.release();
+  else if (left) *out = P->out_kl.release();
+  else *out = P->vout.release();
+  return MPSK_OK;
+}
+
+int transfer_left(Ctx* ctx, const MpoSlice* h, const Tensor* A, const Tensor* Abar, const Tensor* GL, Tensor** out) {
+  return transfer_once(ctx, true, h, A, Abar, GL, out);
+}
+int transfer_right(Ctx* ctx, const MpoSlice* h, const Tensor* A, const Tensor* Abar, const Tensor* GR, Tensor** out) {
+  return transfer_once(ctx, false, h, A, Abar, GR, out);
+}
+
+// ------------------------------------------------------------------------------------------ transfer matrix as a linear operator
+TmOp::~TmOp() { if (ctx && d_coef) ctx->free(d_coef); }
+
+int TmOp::apply(const Tensor* x, Tensor* y) {
+  if (!x->same_structure(*vlike) || !y->same_structure(*vlike)) return ctx->fail(MPSK_ESPACE, "transfer matrix: vector structure mismatch");
+  const Tensor* cur = x;
+  for (auto& sp : sites) {
+    MPSK_TRY(transfer_plan_run(ctx, sp.get(), cur));
+    cur = sp->result();
+  }
+  if (!cur->same_structure(*y)) return ctx->fail(MPSK_ESPACE, "transfer matrix does not map the space onto itself");
+  CUDA_TRY(ctx, cudaMemcpyAsync(y->d, cur->d, y->bytes(), cudaMemcpyDeviceToDevice, ctx->stream));
+  if (ladj) {   // regularisation (transfermatrix.jl:68-76): y -= <l, y> r, the coefficient never leaves the device
+    const bool cx = y->dtype == MPSK_C128;
+    const void* V[1] = {ladj->d};
+    MPSK_TRY(vec_multidot(ctx, cx, 1, V, y->d, y->nelem, d_coef));
+    const void* R[1] = {rvec->d};
+    MPSK_TRY(vec_multiaxpy(ctx, cx, 1, R, d_coef, -1.0, y->d, y->nelem));
+  }
   return MPSK_OK;
 }
 
@@ -212,7 +338,6 @@ int contract_ac2(Ctx* ctx, const Tensor* A1, const Tensor* A2, Tensor** out) {
   GemmPlan g;
   MPSK_TRY(gemm_plan_build(ctx, cx, pr, &g));
   MPSK_TRY(gemm_plan_run(ctx, &g));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   *out = xg.release();
   return MPSK_OK;
 }
@@ -240,7 +365,6 @@ int mul_bond_right(Ctx* ctx, const Tensor* A, const Tensor* C, Tensor** out) {
   GemmPlan g;
   MPSK_TRY(gemm_plan_build(ctx, cx, pr, &g));
   MPSK_TRY(gemm_plan_run(ctx, &g));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   *out = og.release();
   return MPSK_OK;
 }
@@ -268,7 +392,6 @@ int mul_bond_left(Ctx* ctx, const Tensor* C, const Tensor* A, Tensor** out) {
   GemmPlan g;
   MPSK_TRY(gemm_plan_build(ctx, cx, pr, &g));
   MPSK_TRY(gemm_plan_run(ctx, &g));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   *out = og.release();
   return MPSK_OK;
 }

@@ -6,6 +6,8 @@
 #include <cusolverDn.h>
 #include <cmath>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <thread>
 
@@ -77,26 +79,94 @@ __global__ void q_phase_kernel(double* __restrict__ Q, int64_t ldq, int m, int k
   }
 }
 
-// Gram route post-processing.  lam ascending eigenvalues of W^H W, Vt = eigenvectors (row j of the buffer = vector j),
-// Bt = column-major B = W V (mm x nn).  Outputs in descending order: S[j] = sqrt(lam[n-1-j]), U[:, j] = B[:, n-1-j] / S[j],
-// VT[j, i] = conj(V[i, n-1-j])  (column-major nn x nn, ld = nn).
+// Gram route: emit the `head` singular triplets of one level.  lam ascending eigenvalues of M^H M (nl of them), the head
+// is the index range [t, nl); Bn = M V and Rn = R V column-major.  Output position of eigen-index i: outpos + (nl-1-i)
+// (descending singular values): S = sqrt(lam), U[:, o] = Bn[:, i] / S, VT[o, :] = conj(Rn[:, i])^T.
 template <bool CPLX>
-__global__ void gram_post_kernel(const double* __restrict__ Bt, const double* __restrict__ Vt, const double* __restrict__ lam, int mm, int nn,
-                                 double* __restrict__ U, double* __restrict__ VT, double* __restrict__ S) {
+__global__ void gram_emit_kernel(const double* __restrict__ Bn, int64_t ldb, const double* __restrict__ Rn, int64_t ldr,
+                                 const double* __restrict__ lam, int mm, int nn, int t, int nl, int outpos,
+                                 double* __restrict__ U, int64_t ldu, double* __restrict__ VT, int64_t ldvt, double* __restrict__ S) {
+  const int hc = nl - t;
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t e = tid; e < (int64_t)mm * nn; e += nth) {
-    const int r = (int)(e % mm), j = (int)(e / mm), js = nn - 1 - j;
-    const double l = lam[js];
+  for (int64_t e = tid; e < (int64_t)mm * hc; e += nth) {
+    const int r = (int)(e % mm), jj = (int)(e / mm), i = nl - 1 - jj, o = outpos + jj;
+    const double l = lam[i];
     const double sg = l > 0 ? sqrt(l) : 0.0, inv = sg > 0 ? 1.0 / sg : 0.0;
-    if (r == 0) S[j] = sg;
-    if (CPLX) { U[2 * (r + (int64_t)j * mm)] = Bt[2 * (r + (int64_t)js * mm)] * inv; U[2 * (r + (int64_t)j * mm) + 1] = Bt[2 * (r + (int64_t)js * mm) + 1] * inv; }
-    else U[r + (int64_t)j * mm] = Bt[r + (int64_t)js * mm] * inv;
+    if (r == 0) S[o] = sg;
+    if (CPLX) { U[2 * (r + (int64_t)o * ldu)] = Bn[2 * (r + (int64_t)i * ldb)] * inv; U[2 * (r + (int64_t)o * ldu) + 1] = Bn[2 * (r + (int64_t)i * ldb) + 1] * inv; }
+    else U[r + (int64_t)o * ldu] = Bn[r + (int64_t)i * ldb] * inv;
   }
-  for (int64_t e = tid; e < (int64_t)nn * nn; e += nth) {
-    const int j = (int)(e % nn), i = (int)(e / nn), js = nn - 1 - j;
-    if (CPLX) { VT[2 * (j + (int64_t)i * nn)] = Vt[2 * ((int64_t)js * nn + i)]; VT[2 * (j + (int64_t)i * nn) + 1] = -Vt[2 * ((int64_t)js * nn + i) + 1]; }
-    else VT[j + (int64_t)i * nn] = Vt[(int64_t)js * nn + i];
+  for (int64_t e = tid; e < (int64_t)nn * hc; e += nth) {
+    const int c = (int)(e % nn), jj = (int)(e / nn), i = nl - 1 - jj, o = outpos + jj;
+    if (CPLX) { VT[2 * (o + (int64_t)c * ldvt)] = Rn[2 * (c + (int64_t)i * ldr)]; VT[2 * (o + (int64_t)c * ldvt) + 1] = -Rn[2 * (c + (int64_t)i * ldr) + 1]; }
+    else VT[o + (int64_t)c * ldvt] = Rn[c + (int64_t)i * ldr];
   }
+}
+
+// ---- persistent pool of host threads driving independent cuSOLVER factorizations (one stream + handle per worker)
+struct WorkerPool {
+  std::vector<std::thread> th; std::mutex m; std::condition_variable cv_job, cv_done;
+  std::function<void(int)> job; int gen = 0, pending = 0, nactive = 0; bool stop = false;
+  void start(int n, int dev) {
+    for (int t = (int)th.size(); t < n; ++t)
+      th.emplace_back([this, t, dev]() {
+        cudaSetDevice(dev);
+        int seen = 0;
+        for (;;) {
+          std::function<void(int)> f; bool mine = false;
+          {
+            std::unique_lock<std::mutex> lk(m);
+            cv_job.wait(lk, [&] { return stop || gen != seen; });
+            if (stop) return;
+            seen = gen; mine = t < nactive; f = job;
+          }
+          if (mine) {
+            f(t);
+            std::unique_lock<std::mutex> lk(m);
+            if (--pending == 0) cv_done.notify_all();
+          }
+        }
+      });
+  }
+  void run(int nthreads, std::function<void(int)> f) {
+    if (nthreads <= 0) return;
+    std::unique_lock<std::mutex> lk(m);
+    job = std::move(f); nactive = nthreads; pending = nthreads; ++gen;
+    cv_job.notify_all();
+    cv_done.wait(lk, [&] { return pending == 0; });
+  }
+  ~WorkerPool() {
+    { std::unique_lock<std::mutex> lk(m); stop = true; }
+    cv_job.notify_all();
+    for (auto& t : th) t.join();
+  }
+};
+constexpr int POOL_THREADS = 4;
+
+void pool_destroy(Ctx* ctx) {
+  delete (WorkerPool*)ctx->pool; ctx->pool = nullptr;
+  for (int t = 0; t < POOL_THREADS; ++t) {
+    if (ctx->pool_solver[t]) cusolverDnDestroy((cusolverDnHandle_t)ctx->pool_solver[t]);
+    if (ctx->pool_stream[t]) cudaStreamDestroy((cudaStream_t)ctx->pool_stream[t]);
+    if (ctx->pool_info[t]) cudaFree(ctx->pool_info[t]);
+    ctx->pool_solver[t] = ctx->pool_stream[t] = nullptr; ctx->pool_info[t] = nullptr;
+  }
+  if (ctx->cusolver) { cusolverDnDestroy((cusolverDnHandle_t)ctx->cusolver); ctx->cusolver = nullptr; }
+}
+
+static int pool_get(Ctx* ctx, WorkerPool** out) {
+  for (int t = 0; t < POOL_THREADS; ++t) {     // persistent per-worker stream + cuSOLVER handle (creation costs milliseconds)
+    if (ctx->pool_solver[t]) continue;
+    cudaStream_t st; cusolverDnHandle_t hs; int* di = nullptr;
+    CUDA_TRY(ctx, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    CUSOLVER_TRY(ctx, cusolverDnCreate(&hs));
+    CUSOLVER_TRY(ctx, cusolverDnSetStream(hs, st));
+    CUDA_TRY(ctx, cudaMalloc(&di, sizeof(int)));
+    ctx->pool_stream[t] = st; ctx->pool_solver[t] = hs; ctx->pool_info[t] = di;
+  }
+  if (!ctx->pool) { WorkerPool* p = new WorkerPool; p->start(POOL_THREADS, ctx->device); ctx->pool = p; }
+  *out = (WorkerPool*)ctx->pool;
+  return MPSK_OK;
 }
 
 struct Coupled {
@@ -104,14 +174,37 @@ struct Coupled {
   std::vector<std::pair<int, int>> rows, cols;    // (l-sector, u), (r-sector, t)
   std::vector<int64_t> rowoff, coloff;
   int64_t m = 0, n = 0, k = 0;
-  bool flip = false;                              // factorise M^H instead (gesvd needs rows >= cols)
+  bool flip = false;                              // factorise M^H instead (rows >= cols)
+  bool mine = true, fast = false;                 // owned by this rank; Gram route
+  int mm = 0, nn = 0;                             // factorised matrix is mm x nn, mm >= nn
   void* W = nullptr; void* U = nullptr; void* VT = nullptr; double* S = nullptr;
   int64_t ldw = 0, ldu = 0, ldvt = 0;
   int keep = 0;
 };
 
-int tsvd(Ctx* ctx, const Tensor* x, int d1, const int32_t* p1ch, mpsk_trunc trunc, Tensor** Uo, Tensor** So, Tensor** Vo, double* eps_out);
+// per-sector state of the multi-level Gram route
+struct GramState {
+  void* M = nullptr; void* R = nullptr; int nl = 0, outpos = 0, split = 0;     // current level: M (mm x nl), R (nn x nl, null = identity)
+  int64_t ldm = 0, ldn = 0;
+  void *Mconj = nullptr, *Mrow = nullptr, *Rrow = nullptr, *G = nullptr, *buf[2] = {nullptr, nullptr}, *rbuf[2] = {nullptr, nullptr};
+  double* lam = nullptr; void* work = nullptr; int lwork = 0;
+  void* tau = nullptr; double* ph = nullptr; void* Rtmp = nullptr; void* work2 = nullptr; int lwork2 = 0;
+  std::vector<double> hlam; double lam0 = 0.0;
+};
 
+// Truncated SVD of the two-site tensor (dmrg.jl:96-97).  Per coupled sector:
+//   * small sectors (min dim < 256): cuSOLVER gesvd (LAPACK-class, what the reference calls);
+//   * large sectors: a multi-level ("deflated") Gram route built from our grouped DMMA GEMM + cuSOLVER heevd:
+//       level l:  G = M^H M,  G = V L V^H,  B = M V,  R <- R V;   singular values within 1e-3 of the level's largest are
+//       emitted (sigma = sqrt(L), u = b / sigma, v = r): their relative error is eps * (sigma_top/sigma)^2 <= 1e-10.  The
+//       remaining columns of B (norms <= 1e-3 of the level scale, orthogonal to the emitted ones to rounding) form the
+//       matrix of the next level, so every level restores three decades of relative accuracy; at most 6 levels reach the
+//       rounding floor eps * sigma_max, where gesvd's own absolute accuracy ends.  A final Householder QR with positive
+//       diagonal makes U an exact isometry.  (Round 1 used a single level: singular values below 1e-8 sigma_max were
+//       noise, see ADVICE.md.)
+// Multi-GPU: the coupled sectors are distributed over the ranks (longest-processing-time rule on m n^2); the singular
+// values are combined with one allreduce so that every rank takes the same global truncation decision, and the output
+// tensors are assembled with one allreduce each (every element is written by exactly one rank: bit-identical results).
 int tsvd(Ctx* ctx, const Tensor* x, int d1, const int32_t* p1ch, mpsk_trunc trunc, Tensor** Uo, Tensor** So, Tensor** Vo,
          double* eps_out) {
   const bool normalize = !(trunc.kind & 0x100);
@@ -143,17 +236,41 @@ int tsvd(Ctx* ctx, const Tensor* x, int d1, const int32_t* p1ch, mpsk_trunc trun
   }
   std::vector<Coupled*> secs;
   for (auto& kv : cs) if (kv.second.m > 0 && kv.second.n > 0) secs.push_back(&kv.second);
+  const int ns = (int)secs.size();
   struct Cleanup { Ctx* ctx; std::vector<Coupled*>* s; ~Cleanup() { for (Coupled* c : *s) { ctx->free(c->W); ctx->free(c->U); ctx->free(c->VT); ctx->free(c->S); } } } cleanup{ctx, &secs};
-  // ---- assemble the column-major matrices
+  const int64_t fast_min = (ctx->flags & MPSK_FLAG_EXACT_SVD) ? (int64_t)1 << 60 : ((ctx->flags & MPSK_FLAG_FAST_SVD_ALL) ? 2 : 256);
+  // ---- ownership: sectors are distributed over the ranks (LPT on m n^2), deterministic on every rank
+  const bool dist = ctx->nranks > 1 && !(ctx->flags & MPSK_FLAG_REPLICATE_LOCAL);
+  std::vector<int> owner(ns, 0);
+  {
+    std::vector<int> ord(ns);
+    for (int i = 0; i < ns; ++i) ord[i] = i;
+    auto cost = [&](int i) { const double a = (double)std::max(secs[i]->m, secs[i]->n), b = (double)std::min(secs[i]->m, secs[i]->n); return a * b * b; };
+    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return cost(a) > cost(b); });
+    std::vector<double> load(std::max(ctx->nranks, 1), 0.0);
+    for (int i : ord) {
+      int best = 0;
+      if (dist) for (int r = 1; r < ctx->nranks; ++r) if (load[r] < load[best]) best = r;
+      owner[i] = best; load[best] += cost(i);
+    }
+  }
+  // ---- assemble the column-major matrices of the sectors this rank factorises
   std::vector<CopyTask> tasks;
-  for (Coupled* c : secs) {
+  int64_t ktot = 0; std::vector<int64_t> koff(ns);
+  for (int si = 0; si < ns; ++si) {
+    Coupled* c = secs[si];
     c->k = std::min(c->m, c->n); c->flip = c->m < c->n;
-    const int64_t mm = c->flip ? c->n : c->m, nn = c->flip ? c->m : c->n;
-    c->ldw = mm; c->ldu = mm; c->ldvt = c->k;
-    c->W = ctx->alloc(mm * nn * es); c->U = ctx->alloc(mm * c->k * es); c->VT = ctx->alloc(c->k * nn * es);
+    c->mm = (int)(c->flip ? c->n : c->m); c->nn = (int)(c->flip ? c->m : c->n);
+    c->mine = !dist || owner[si] == ctx->rank;
+    c->fast = c->k >= fast_min;
+    koff[si] = ktot; ktot += c->k;
+    if (!c->mine) continue;
+    const int64_t mm = c->mm, nn = c->nn;
+    c->ldw = pad(mm); c->ldu = pad(mm); c->ldvt = pad(c->k);
+    c->W = ctx->alloc(c->ldw * nn * es); c->U = ctx->alloc(c->ldu * c->k * es); c->VT = ctx->alloc(c->ldvt * nn * es);
     c->S = (double*)ctx->alloc(c->k * sizeof(double));
     if (!c->W || !c->U || !c->VT || !c->S) return MPSK_ENOMEM;
-    CUDA_TRY(ctx, cudaMemsetAsync(c->W, 0, mm * nn * es, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(c->W, 0, c->ldw * nn * es, ctx->stream));
     for (size_t ri = 0; ri < c->rows.size(); ++ri) for (size_t ci = 0; ci < c->cols.size(); ++ci) {
       const int jl = c->rows[ri].first, u = c->rows[ri].second, jr = c->cols[ci].first, t = c->cols[ci].second;
       const Blk* b = xk->find(u * d2 + t, jl);
@@ -166,169 +283,232 @@ int tsvd(Ctx* ctx, const Tensor* x, int d1, const int32_t* p1ch, mpsk_trunc trun
     }
   }
   MPSK_TRY(run_copy_tasks(ctx, tasks, cx));
-  // ---- factorise every sector.  Small sectors: cuSOLVER gesvd (LAPACK-class, what the reference calls).  Large
-  // sectors: the GEMM-rich route  G = W^H W (our grouped DMMA GEMM) -> heevd(G) = V L V^H -> B = W V (GEMM) ->
-  // U = B / sigma -> re-orthonormalised by one Householder QR with positive diagonal.  sigma = sqrt(L) is accurate to
-  // eps * sigma_max^2 / sigma (<= 1e-10 for every singular value a truncation keeps), V is orthonormal to machine
-  // precision and the QR makes U exactly isometric, so A = U S V^H holds to ~1e-13 * |A| while the cost drops from
-  // ~540 ms (gesvd, 1964^2 complex) to ~80 ms.  Independent sectors run on a small pool of host threads, each with
-  // its own cuSOLVER handle and stream.
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  std::vector<std::vector<double>> sv(secs.size());
-  {
-    const int64_t fast_min = (ctx->flags & MPSK_FLAG_EXACT_SVD) ? (int64_t)1 << 60 : ((ctx->flags & MPSK_FLAG_FAST_SVD_ALL) ? 2 : 256);
-    std::vector<char> fast(secs.size(), 0);
-    std::vector<int> order(secs.size());
-    for (size_t i = 0; i < secs.size(); ++i) { order[i] = (int)i; fast[i] = std::min(secs[i]->m, secs[i]->n) >= fast_min; }
-    std::sort(order.begin(), order.end(), [&](int a, int b) { return secs[a]->m * secs[a]->n > secs[b]->m * secs[b]->n; });
-    const int nthreads = (int)std::min<size_t>(4, secs.size());
-    // per-sector scratch (all from the context allocator, freed at scope exit)
-    struct Scratch { void* work = nullptr; double* rwork = nullptr; int lwork = 0; void* Xc = nullptr; void* Wr = nullptr; void* G = nullptr;
-                     double* lam = nullptr; void* tau = nullptr; double* ph = nullptr; void* Rtmp = nullptr; void* work2 = nullptr; int lwork2 = 0; };
-    std::vector<Scratch> sc(secs.size());
-    struct ScCleanup { Ctx* c; std::vector<Scratch>* v; ~ScCleanup() { for (auto& x : *v) { c->free(x.work); c->free(x.rwork); c->free(x.Xc); c->free(x.Wr);
-                       c->free(x.G); c->free(x.lam); c->free(x.tau); c->free(x.ph); c->free(x.Rtmp); c->free(x.work2); } } } scc{ctx, &sc};
-    cusolverDnHandle_t h0;
-    MPSK_TRY(get_cusolver(ctx, &h0));
-    std::vector<CopyTask> ct;
-    std::vector<GemmProblemHost> g1, g2;
-    for (size_t si = 0; si < secs.size(); ++si) {
-      Coupled* c = secs[si];
-      const int mm = (int)(c->flip ? c->n : c->m), nn = (int)(c->flip ? c->m : c->n);
-      Scratch& x = sc[si];
-      if (!fast[si]) {
-        if (cx) CUSOLVER_TRY(ctx, cusolverDnZgesvd_bufferSize(h0, mm, nn, &x.lwork));
-        else CUSOLVER_TRY(ctx, cusolverDnDgesvd_bufferSize(h0, mm, nn, &x.lwork));
-        x.work = ctx->alloc((size_t)std::max(x.lwork, 1) * es);
-        x.rwork = (double*)ctx->alloc(sizeof(double) * std::max(nn, 1) * 5);
-        if (!x.work || !x.rwork) return MPSK_ENOMEM;
-        continue;
+  WorkerPool* pool = nullptr;
+  MPSK_TRY(pool_get(ctx, &pool));
+  cusolverDnHandle_t h0;
+  MPSK_TRY(get_cusolver(ctx, &h0));
+  std::vector<std::vector<double>> sv(ns);
+  // work lists (largest first)
+  std::vector<int> slow, fastl;
+  for (int si = 0; si < ns; ++si) if (secs[si]->mine) (secs[si]->fast ? fastl : slow).push_back(si);
+  auto bysize = [&](int a, int b) { return (double)secs[a]->mm * secs[a]->nn > (double)secs[b]->mm * secs[b]->nn; };
+  std::sort(slow.begin(), slow.end(), bysize); std::sort(fastl.begin(), fastl.end(), bysize);
+  // scratch
+  struct SlowScratch { void* work = nullptr; double* rwork = nullptr; int lwork = 0; };
+  std::vector<SlowScratch> ss(ns); std::vector<GramState> gs(ns);
+  struct ScCleanup { Ctx* c; std::vector<SlowScratch>* a; std::vector<GramState>* g;
+    ~ScCleanup() { for (auto& x : *a) { c->free(x.work); c->free(x.rwork); }
+                   for (auto& x : *g) { c->free(x.Mconj); c->free(x.Mrow); c->free(x.Rrow); c->free(x.G); c->free(x.buf[0]); c->free(x.buf[1]); c->free(x.rbuf[0]); c->free(x.rbuf[1]);
+                                        c->free(x.lam); c->free(x.work); c->free(x.tau); c->free(x.ph); c->free(x.Rtmp); c->free(x.work2); } } } scc{ctx, &ss, &gs};
+  for (int si : slow) {
+    Coupled* c = secs[si]; SlowScratch& x = ss[si];
+    if (cx) CUSOLVER_TRY(ctx, cusolverDnZgesvd_bufferSize(h0, c->mm, c->nn, &x.lwork));
+    else CUSOLVER_TRY(ctx, cusolverDnDgesvd_bufferSize(h0, c->mm, c->nn, &x.lwork));
+    x.work = ctx->alloc((size_t)std::max(x.lwork, 1) * es);
+    x.rwork = (double*)ctx->alloc(sizeof(double) * std::max(c->nn, 1) * 5);
+    if (!x.work || !x.rwork) return MPSK_ENOMEM;
+  }
+  for (int si : fastl) {
+    Coupled* c = secs[si]; GramState& g = gs[si];
+    const int64_t mm = c->mm, nn = c->nn;
+    g.ldm = pad(mm); g.ldn = pad(nn); g.M = c->W; g.R = nullptr; g.nl = (int)nn; g.outpos = 0;
+    g.Mconj = ctx->alloc(g.ldm * nn * es); g.Mrow = ctx->alloc(mm * g.ldn * es); g.G = ctx->alloc(g.ldn * nn * es);
+    g.buf[0] = ctx->alloc(g.ldm * nn * es); g.rbuf[0] = ctx->alloc(g.ldn * nn * es);
+    g.lam = (double*)ctx->alloc(sizeof(double) * nn); g.tau = ctx->alloc((size_t)nn * es); g.ph = (double*)ctx->alloc((size_t)nn * es);
+    g.Rtmp = ctx->alloc((size_t)nn * nn * es);
+    if (!g.Mconj || !g.Mrow || !g.G || !g.buf[0] || !g.rbuf[0] || !g.lam || !g.tau || !g.ph || !g.Rtmp) return MPSK_ENOMEM;
+    int l1 = 0, l2 = 0, l3 = 0;
+    if (cx) { CUSOLVER_TRY(ctx, cusolverDnZheevd_bufferSize(h0, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)nn, (cuDoubleComplex*)g.G, (int)g.ldn, g.lam, &l1));
+              CUSOLVER_TRY(ctx, cusolverDnZgeqrf_bufferSize(h0, (int)mm, (int)nn, (cuDoubleComplex*)c->U, (int)c->ldu, &l2));
+              CUSOLVER_TRY(ctx, cusolverDnZungqr_bufferSize(h0, (int)mm, (int)nn, (int)nn, (cuDoubleComplex*)c->U, (int)c->ldu, (cuDoubleComplex*)g.tau, &l3)); }
+    else { CUSOLVER_TRY(ctx, cusolverDnDsyevd_bufferSize(h0, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)nn, (double*)g.G, (int)g.ldn, g.lam, &l1));
+           CUSOLVER_TRY(ctx, cusolverDnDgeqrf_bufferSize(h0, (int)mm, (int)nn, (double*)c->U, (int)c->ldu, &l2));
+           CUSOLVER_TRY(ctx, cusolverDnDorgqr_bufferSize(h0, (int)mm, (int)nn, (int)nn, (double*)c->U, (int)c->ldu, (double*)g.tau, &l3)); }
+    g.lwork = std::max(l1, 1); g.lwork2 = std::max(std::max(l2, l3), 1);
+    g.work = ctx->alloc((size_t)g.lwork * es); g.work2 = ctx->alloc((size_t)g.lwork2 * es);
+    if (!g.work || !g.work2) return MPSK_ENOMEM;
+  }
+  std::vector<int> status(POOL_THREADS, 0);
+  std::vector<std::string> errs(POOL_THREADS);
+  // generic pool phase: `fn(si, stream, handle, d_info)` enqueues the factorisation of sector si and returns its status
+  auto run_phase = [&](const std::vector<int>& list, const char* what,
+                       const std::function<cusolverStatus_t(int, cudaStream_t, cusolverDnHandle_t, int*)>& fn,
+                       const std::function<void(int, cudaStream_t)>& after) -> int {
+    if (list.empty()) return MPSK_OK;
+    const int nthreads = (int)std::min<size_t>(POOL_THREADS, list.size());
+    std::atomic<int> next(0);
+    pool->run(nthreads, [&](int tid) {
+      cudaStream_t st = (cudaStream_t)ctx->pool_stream[tid]; cusolverDnHandle_t hs = (cusolverDnHandle_t)ctx->pool_solver[tid];
+      int* d_info = ctx->pool_info[tid];
+      for (;;) {
+        const int oi = next.fetch_add(1);
+        if (oi >= (int)list.size()) break;
+        const int si = list[oi];
+        cusolverStatus_t cs_ = fn(si, st, hs, d_info);
+        int info = 0;
+        cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, st);
+        if (after) after(si, st);
+        cudaError_t ce = cudaStreamSynchronize(st);
+        if (cs_ != CUSOLVER_STATUS_SUCCESS || ce != cudaSuccess || info != 0) {
+          status[tid] = MPSK_ECUDA;
+          errs[tid] = std::string(what) + " failed in sector " + std::to_string(secs[si]->Q) + " (status " + std::to_string((int)cs_) + ", info " + std::to_string(info) + ")";
+          break;
+        }
       }
-      x.Xc = ctx->alloc((size_t)mm * nn * es); x.Wr = ctx->alloc((size_t)mm * nn * es); x.G = ctx->alloc((size_t)nn * nn * es);
-      x.lam = (double*)ctx->alloc(sizeof(double) * nn); x.tau = ctx->alloc((size_t)nn * es); x.ph = (double*)ctx->alloc((size_t)nn * es);
-      x.Rtmp = ctx->alloc((size_t)nn * nn * es);
-      if (!x.Xc || !x.Wr || !x.G || !x.lam || !x.tau || !x.ph || !x.Rtmp) return MPSK_ENOMEM;
-      int l1 = 0, l2 = 0, l3 = 0;
-      if (cx) { CUSOLVER_TRY(ctx, cusolverDnZheevd_bufferSize(h0, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, nn, (cuDoubleComplex*)x.G, nn, x.lam, &l1));
-                CUSOLVER_TRY(ctx, cusolverDnZgeqrf_bufferSize(h0, mm, nn, (cuDoubleComplex*)c->U, mm, &l2));
-                CUSOLVER_TRY(ctx, cusolverDnZungqr_bufferSize(h0, mm, nn, nn, (cuDoubleComplex*)c->U, mm, (cuDoubleComplex*)x.tau, &l3)); }
-      else { CUSOLVER_TRY(ctx, cusolverDnDsyevd_bufferSize(h0, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, nn, (double*)x.G, nn, x.lam, &l1));
-             CUSOLVER_TRY(ctx, cusolverDnDgeqrf_bufferSize(h0, mm, nn, (double*)c->U, mm, &l2));
-             CUSOLVER_TRY(ctx, cusolverDnDorgqr_bufferSize(h0, mm, nn, nn, (double*)c->U, mm, (double*)x.tau, &l3)); }
-      x.lwork = std::max(l1, 1); x.lwork2 = std::max(std::max(l2, l3), 1);
-      x.work = ctx->alloc((size_t)x.lwork * es); x.work2 = ctx->alloc((size_t)x.lwork2 * es);
-      if (!x.work || !x.work2) return MPSK_ENOMEM;
-      // W is column-major mm x nn == row-major X (nn x mm).  Xc = conj(X);  Wr = W in row-major (mm x nn)
-      ct.push_back(CopyTask{c->W, x.Xc, 1, mm, 1, mm, mm, nn, cx ? 1 : 0, 0, nullptr});
-      ct.push_back(CopyTask{c->W, x.Wr, 1, mm, nn, 1, mm, nn, 0, 0, nullptr});
-      // G (column-major) = row-major buffer C[i][j] = sum_k X[i][k] conj(X[j][k])
-      g1.push_back(GemmProblemHost{c->W, x.Xc, x.G, mm, mm, nn, nn, nn, mm, 0});
+    });
+    for (int t = 0; t < POOL_THREADS; ++t) if (status[t] != 0) return ctx->fail(status[t], "tsvd: %s", errs[t].c_str());
+    return MPSK_OK;
+  };
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));     // W is assembled: hand the sectors to the pool streams
+  // ---- small sectors: gesvd
+  MPSK_TRY(run_phase(slow, "gesvd",
+    [&](int si, cudaStream_t, cusolverDnHandle_t hs, int* d_info) {
+      Coupled* c = secs[si]; SlowScratch& x = ss[si];
+      if (cx) return cusolverDnZgesvd(hs, 'S', 'S', c->mm, c->nn, (cuDoubleComplex*)c->W, (int)c->ldw, c->S, (cuDoubleComplex*)c->U, (int)c->ldu,
+                                      (cuDoubleComplex*)c->VT, (int)c->ldvt, (cuDoubleComplex*)x.work, x.lwork, x.rwork, d_info);
+      return cusolverDnDgesvd(hs, 'S', 'S', c->mm, c->nn, (double*)c->W, (int)c->ldw, c->S, (double*)c->U, (int)c->ldu, (double*)c->VT,
+                              (int)c->ldvt, (double*)x.work, x.lwork, x.rwork, d_info);
+    },
+    [&](int si, cudaStream_t st) { sv[si].resize(secs[si]->k); cudaMemcpyAsync(sv[si].data(), secs[si]->S, sizeof(double) * secs[si]->k, cudaMemcpyDeviceToHost, st); }));
+  ctx->launches += (int64_t)slow.size();
+  // ---- large sectors: multi-level Gram route
+  constexpr int MAXLEV = 6;
+  constexpr double SPLIT = 1e-3;       // singular values within this factor of the level's largest are emitted
+  std::vector<int> active = fastl;
+  for (int lev = 0; lev < MAXLEV + 1 && !active.empty(); ++lev) {
+    std::vector<CopyTask> ct; std::vector<GemmProblemHost> g1;
+    for (int si : active) {
+      Coupled* c = secs[si]; GramState& g = gs[si];
+      const int mm = c->mm, nl = g.nl;
+      const int64_t ldr = pad(nl);
+      ct.push_back(CopyTask{g.M, g.Mconj, 1, g.ldm, 1, g.ldm, mm, nl, cx ? 1 : 0, 0, nullptr});      // conj(M), same layout
+      ct.push_back(CopyTask{g.M, g.Mrow, 1, g.ldm, ldr, 1, mm, nl, 0, 0, nullptr});                  // M row-major
+      if (g.R) {
+        if (!g.Rrow) { g.Rrow = ctx->alloc((size_t)c->nn * g.ldn * es); if (!g.Rrow) return MPSK_ENOMEM; }
+        ct.push_back(CopyTask{g.R, g.Rrow, 1, g.ldn, ldr, 1, c->nn, nl, 0, 0, nullptr});
+      }
+      // G (column-major, ld pad(nl)) = row-major buffer C[i][j] = sum_k M[k,i] conj(M[k,j])
+      g1.push_back(GemmProblemHost{g.M, g.Mconj, g.G, g.ldm, g.ldm, ldr, nl, nl, mm, 0});
     }
-    GemmPlan p1;
-    if (!g1.empty()) {
-      MPSK_TRY(run_copy_tasks(ctx, ct, cx));
+    MPSK_TRY(run_copy_tasks(ctx, ct, cx));
+    {
+      GemmPlan p1;
       MPSK_TRY(gemm_plan_build(ctx, cx, g1, &p1));
       MPSK_TRY(gemm_plan_run(ctx, &p1));
       CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     }
-    const int dev = ctx->device;
-    for (int t = 0; t < nthreads; ++t) {     // persistent per-worker stream + cuSOLVER handle (creation costs milliseconds)
-      if (ctx->pool_solver[t]) continue;
-      cudaStream_t st; cusolverDnHandle_t hs; int* di = nullptr;
-      CUDA_TRY(ctx, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-      CUSOLVER_TRY(ctx, cusolverDnCreate(&hs));
-      CUSOLVER_TRY(ctx, cusolverDnSetStream(hs, st));
-      CUDA_TRY(ctx, cudaMalloc(&di, sizeof(int)));
-      ctx->pool_stream[t] = st; ctx->pool_solver[t] = hs; ctx->pool_info[t] = di;
+    MPSK_TRY(run_phase(active, "heevd",
+      [&](int si, cudaStream_t, cusolverDnHandle_t hs, int* d_info) {
+        GramState& g = gs[si]; const int nl = g.nl; const int ldg = (int)pad(nl);
+        if (cx) return cusolverDnZheevd(hs, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, nl, (cuDoubleComplex*)g.G, ldg, g.lam, (cuDoubleComplex*)g.work, g.lwork, d_info);
+        return cusolverDnDsyevd(hs, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, nl, (double*)g.G, ldg, g.lam, (double*)g.work, g.lwork, d_info);
+      },
+      [&](int si, cudaStream_t st) { GramState& g = gs[si]; g.hlam.resize(g.nl); cudaMemcpyAsync(g.hlam.data(), g.lam, sizeof(double) * g.nl, cudaMemcpyDeviceToHost, st); }));
+    ctx->launches += (int64_t)active.size();
+    // split decisions (host): emit everything within SPLIT of the level's largest singular value; at the rounding floor
+    // of the original matrix (or at the last level) emit everything
+    std::vector<GemmProblemHost> g2;
+    for (int si : active) {
+      Coupled* c = secs[si]; GramState& g = gs[si];
+      const int nl = g.nl;
+      const double ltop = std::max(g.hlam[nl - 1], 0.0);
+      if (lev == 0) g.lam0 = ltop;
+      const double floor2 = g.lam0 * (double)c->mm * 1e-30;          // (eps sqrt(m) sigma_max)^2 up to a small factor
+      int t = 0;
+      if (lev < MAXLEV && ltop > floor2) {
+        const double cut = std::max(ltop * SPLIT * SPLIT, floor2);
+        while (t < nl && g.hlam[t] < cut) ++t;
+      }
+      g.split = t;
+      const int64_t ldr = pad(nl);
+      void* Bn = g.buf[lev & 1];
+      if (!Bn) { Bn = g.buf[lev & 1] = ctx->alloc(g.ldm * (size_t)nl * es); if (!Bn) return MPSK_ENOMEM; }
+      // Bn (column-major mm x nl, ld ldm) = row-major C[j][k] = sum_i Vt[j][i] Mrow[k][i]
+      g2.push_back(GemmProblemHost{g.G, g.Mrow, Bn, ldr, ldr, g.ldm, nl, c->mm, nl, 0});
+      if (g.R) {
+        void* Rn = g.rbuf[lev & 1];
+        if (!Rn) { Rn = g.rbuf[lev & 1] = ctx->alloc(g.ldn * (size_t)nl * es); if (!Rn) return MPSK_ENOMEM; }
+        g2.push_back(GemmProblemHost{g.G, g.Rrow, Rn, ldr, ldr, g.ldn, nl, c->nn, nl, 0});
+      }
     }
-    std::vector<int> status(nthreads, 0);
-    std::vector<std::string> errs(nthreads);
-    // phase: 0 = gesvd (slow sectors) + heevd (fast sectors); 1 = QR re-orthonormalisation of U (fast sectors)
-    auto run_pool = [&](int phase) {
-      std::atomic<int> next(0);
-      auto worker = [&](int tid) {
-        cudaSetDevice(dev);
-        cudaStream_t st = (cudaStream_t)ctx->pool_stream[tid]; cusolverDnHandle_t hs = (cusolverDnHandle_t)ctx->pool_solver[tid];
-        int* d_info = ctx->pool_info[tid];
-        for (;;) {
-          const int oi = next.fetch_add(1);
-          if (oi >= (int)order.size()) break;
-          const int si = order[oi];
-          Coupled* c = secs[si]; Scratch& x = sc[si];
-          const int mm = (int)(c->flip ? c->n : c->m), nn = (int)(c->flip ? c->m : c->n);
-          cusolverStatus_t cs_ = CUSOLVER_STATUS_SUCCESS;
-          if (phase == 0 && !fast[si]) {
-            if (cx) cs_ = cusolverDnZgesvd(hs, 'S', 'S', mm, nn, (cuDoubleComplex*)c->W, (int)c->ldw, c->S, (cuDoubleComplex*)c->U, (int)c->ldu,
-                                           (cuDoubleComplex*)c->VT, (int)c->ldvt, (cuDoubleComplex*)x.work, x.lwork, x.rwork, d_info);
-            else cs_ = cusolverDnDgesvd(hs, 'S', 'S', mm, nn, (double*)c->W, (int)c->ldw, c->S, (double*)c->U, (int)c->ldu, (double*)c->VT,
-                                        (int)c->ldvt, (double*)x.work, x.lwork, x.rwork, d_info);
-          } else if (phase == 0) {
-            if (cx) cs_ = cusolverDnZheevd(hs, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, nn, (cuDoubleComplex*)x.G, nn, x.lam, (cuDoubleComplex*)x.work, x.lwork, d_info);
-            else cs_ = cusolverDnDsyevd(hs, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, nn, (double*)x.G, nn, x.lam, (double*)x.work, x.lwork, d_info);
-          } else if (fast[si]) {
-            if (cx) cs_ = cusolverDnZgeqrf(hs, mm, nn, (cuDoubleComplex*)c->U, mm, (cuDoubleComplex*)x.tau, (cuDoubleComplex*)x.work2, x.lwork2, d_info);
-            else cs_ = cusolverDnDgeqrf(hs, mm, nn, (double*)c->U, mm, (double*)x.tau, (double*)x.work2, x.lwork2, d_info);
-            const int grid = (int)std::min<int64_t>(((int64_t)nn * nn + 255) / 256, 4096);
-            if (cx) qr_phase_kernel<true><<<grid, 256, 0, st>>>((const double*)c->U, mm, nn, nn, x.ph, (double*)x.Rtmp, 1, nn, 0);
-            else qr_phase_kernel<false><<<grid, 256, 0, st>>>((const double*)c->U, mm, nn, nn, x.ph, (double*)x.Rtmp, 1, nn, 0);
-            if (cs_ == CUSOLVER_STATUS_SUCCESS) {
-              if (cx) cs_ = cusolverDnZungqr(hs, mm, nn, nn, (cuDoubleComplex*)c->U, mm, (cuDoubleComplex*)x.tau, (cuDoubleComplex*)x.work2, x.lwork2, d_info);
-              else cs_ = cusolverDnDorgqr(hs, mm, nn, nn, (double*)c->U, mm, (double*)x.tau, (double*)x.work2, x.lwork2, d_info);
-            }
-            const int grid2 = (int)std::min<int64_t>(((int64_t)mm * nn + 255) / 256, 4096);
-            if (cx) q_phase_kernel<true><<<grid2, 256, 0, st>>>((double*)c->U, mm, mm, nn, x.ph);
-            else q_phase_kernel<false><<<grid2, 256, 0, st>>>((double*)c->U, mm, mm, nn, x.ph);
-          } else continue;
-          int info = 0;
-          cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, st);
-          if (phase == 0 && !fast[si]) { sv[si].resize(c->k); cudaMemcpyAsync(sv[si].data(), c->S, sizeof(double) * c->k, cudaMemcpyDeviceToHost, st); }
-          cudaError_t ce = cudaStreamSynchronize(st);
-          if (cs_ != CUSOLVER_STATUS_SUCCESS || ce != cudaSuccess || info != 0) {
-            status[tid] = MPSK_ECUDA;
-            errs[tid] = "factorisation failed in sector " + std::to_string(c->Q) + " (phase " + std::to_string(phase) + ", status " + std::to_string((int)cs_) + ", info " + std::to_string(info) + ")";
-            break;
-          }
+    GemmPlan p2;
+    MPSK_TRY(gemm_plan_build(ctx, cx, g2, &p2));
+    MPSK_TRY(gemm_plan_run(ctx, &p2));
+    std::vector<int> next_active;
+    for (int si : active) {
+      Coupled* c = secs[si]; GramState& g = gs[si];
+      const int nl = g.nl, t = g.split;
+      const int64_t ldr = pad(nl);
+      void* Bn = g.buf[lev & 1];
+      const void* Rn = g.R ? g.rbuf[lev & 1] : g.G;          // level 0: R V = V
+      const int64_t ldrn = g.R ? g.ldn : ldr;
+      const int64_t work_items = (int64_t)c->mm * (nl - t);
+      const int grid = (int)std::min<int64_t>((work_items + 255) / 256 + 1, 8192);
+      if (cx) gram_emit_kernel<true><<<grid, 256, 0, ctx->stream>>>((const double*)Bn, g.ldm, (const double*)Rn, ldrn, g.lam, c->mm, c->nn, t, nl, g.outpos,
+                                                                      (double*)c->U, c->ldu, (double*)c->VT, c->ldvt, c->S);
+      else gram_emit_kernel<false><<<grid, 256, 0, ctx->stream>>>((const double*)Bn, g.ldm, (const double*)Rn, ldrn, g.lam, c->mm, c->nn, t, nl, g.outpos,
+                                                                   (double*)c->U, c->ldu, (double*)c->VT, c->ldvt, c->S);
+      ctx->launches++;
+      g.outpos += nl - t;
+      if (t > 0) {
+        if (!g.R) {      // level 0: the tail of V becomes the accumulated right factor (G is recycled by the next level)
+          CUDA_TRY(ctx, cudaMemcpyAsync(g.rbuf[0], g.G, (size_t)ldr * t * es, cudaMemcpyDeviceToDevice, ctx->stream));
+          g.R = g.rbuf[0];
+          if (ldr != g.ldn) return ctx->fail(MPSK_EINTERNAL, "tsvd: leading dimension mismatch");
+        } else g.R = g.rbuf[lev & 1];
+        g.M = Bn; g.nl = t;
+        next_active.push_back(si);
+      }
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    active.swap(next_active);
+  }
+  if (!fastl.empty()) {
+    for (int si : fastl) { sv[si].resize(secs[si]->k); CUDA_TRY(ctx, cudaMemcpyAsync(sv[si].data(), secs[si]->S, sizeof(double) * secs[si]->k, cudaMemcpyDeviceToHost, ctx->stream)); }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    // re-orthonormalise U: Householder QR with positive diagonal (exact isometry; changes U by O(eps sigma_max / sigma))
+    MPSK_TRY(run_phase(fastl, "QR clean-up",
+      [&](int si, cudaStream_t st, cusolverDnHandle_t hs, int* d_info) {
+        Coupled* c = secs[si]; GramState& g = gs[si];
+        const int mm = c->mm, nn = c->nn; const int ldu = (int)c->ldu;
+        cusolverStatus_t cs_;
+        if (cx) cs_ = cusolverDnZgeqrf(hs, mm, nn, (cuDoubleComplex*)c->U, ldu, (cuDoubleComplex*)g.tau, (cuDoubleComplex*)g.work2, g.lwork2, d_info);
+        else cs_ = cusolverDnDgeqrf(hs, mm, nn, (double*)c->U, ldu, (double*)g.tau, (double*)g.work2, g.lwork2, d_info);
+        const int grid = (int)std::min<int64_t>(((int64_t)nn * nn + 255) / 256, 4096);
+        if (cx) qr_phase_kernel<true><<<grid, 256, 0, st>>>((const double*)c->U, ldu, nn, nn, g.ph, (double*)g.Rtmp, 1, nn, 0);
+        else qr_phase_kernel<false><<<grid, 256, 0, st>>>((const double*)c->U, ldu, nn, nn, g.ph, (double*)g.Rtmp, 1, nn, 0);
+        if (cs_ == CUSOLVER_STATUS_SUCCESS) {
+          if (cx) cs_ = cusolverDnZungqr(hs, mm, nn, nn, (cuDoubleComplex*)c->U, ldu, (cuDoubleComplex*)g.tau, (cuDoubleComplex*)g.work2, g.lwork2, d_info);
+          else cs_ = cusolverDnDorgqr(hs, mm, nn, nn, (double*)c->U, ldu, (double*)g.tau, (double*)g.work2, g.lwork2, d_info);
         }
-      };
-      std::vector<std::thread> th;
-      for (int t = 0; t < nthreads; ++t) th.emplace_back(worker, t);
-      for (auto& t : th) t.join();
-    };
-    run_pool(0);
-    ctx->launches += (int64_t)secs.size();
-    for (int t = 0; t < nthreads; ++t) if (status[t] != 0) return ctx->fail(status[t], "tsvd: %s", errs[t].c_str());
-    if (!g1.empty()) {
-      // B^T[j][k] = sum_i Vt[j][i] Wr[k][i]  (row-major nn x mm == column-major B = W V, written over Xc)
-      for (size_t si = 0; si < secs.size(); ++si) {
-        if (!fast[si]) continue;
-        Coupled* c = secs[si];
-        const int mm = (int)(c->flip ? c->n : c->m), nn = (int)(c->flip ? c->m : c->n);
-        g2.push_back(GemmProblemHost{sc[si].G, sc[si].Wr, sc[si].Xc, nn, nn, mm, nn, mm, nn, 0});
-      }
-      GemmPlan p2;
-      MPSK_TRY(gemm_plan_build(ctx, cx, g2, &p2));
-      MPSK_TRY(gemm_plan_run(ctx, &p2));
-      for (size_t si = 0; si < secs.size(); ++si) {
-        if (!fast[si]) continue;
-        Coupled* c = secs[si];
-        const int mm = (int)(c->flip ? c->n : c->m), nn = (int)(c->flip ? c->m : c->n);
-        const int grid = (int)std::min<int64_t>(((int64_t)mm * nn + 255) / 256, 8192);
-        if (cx) gram_post_kernel<true><<<grid, 256, 0, ctx->stream>>>((const double*)sc[si].Xc, (const double*)sc[si].G, sc[si].lam, mm, nn, (double*)c->U, (double*)c->VT, c->S);
-        else gram_post_kernel<false><<<grid, 256, 0, ctx->stream>>>((const double*)sc[si].Xc, (const double*)sc[si].G, sc[si].lam, mm, nn, (double*)c->U, (double*)c->VT, c->S);
-        ctx->launches++;
-        sv[si].resize(c->k);
-        CUDA_TRY(ctx, cudaMemcpyAsync(sv[si].data(), c->S, sizeof(double) * c->k, cudaMemcpyDeviceToHost, ctx->stream));
-      }
-      CUDA_TRY(ctx, cudaGetLastError());
-      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-      run_pool(1);
-      for (int t = 0; t < nthreads; ++t) if (status[t] != 0) return ctx->fail(status[t], "tsvd: %s", errs[t].c_str());
+        const int grid2 = (int)std::min<int64_t>(((int64_t)mm * nn + 255) / 256, 4096);
+        if (cx) q_phase_kernel<true><<<grid2, 256, 0, st>>>((double*)c->U, ldu, mm, nn, g.ph);
+        else q_phase_kernel<false><<<grid2, 256, 0, st>>>((double*)c->U, ldu, mm, nn, g.ph);
+        return cs_;
+      }, nullptr));
+    ctx->launches += 4 * (int64_t)fastl.size();
+  }
+  // ---- singular values of all sectors on every rank
+  if (dist) {
+    double* d_all = (double*)ctx->alloc(sizeof(double) * std::max<int64_t>(ktot, 1));
+    if (!d_all) return MPSK_ENOMEM;
+    CUDA_TRY(ctx, cudaMemsetAsync(d_all, 0, sizeof(double) * std::max<int64_t>(ktot, 1), ctx->stream));
+    for (int si = 0; si < ns; ++si)
+      if (secs[si]->mine) CUDA_TRY(ctx, cudaMemcpyAsync(d_all + koff[si], secs[si]->S, sizeof(double) * secs[si]->k, cudaMemcpyDeviceToDevice, ctx->stream));
+    int st = comm_allreduce_sum(ctx, d_all, (size_t)ktot);
+    std::vector<double> all((size_t)ktot);
+    if (st == MPSK_OK && ktot > 0) {
+      cudaMemcpyAsync(all.data(), d_all, sizeof(double) * ktot, cudaMemcpyDeviceToHost, ctx->stream);
+      cudaStreamSynchronize(ctx->stream);
     }
+    ctx->free(d_all);
+    MPSK_TRY(st);
+    for (int si = 0; si < ns; ++si) sv[si].assign(all.begin() + koff[si], all.begin() + koff[si] + secs[si]->k);
   }
   // ---- global truncation select (same rule as oracle/linalg.py:tsvd): drop smallest first; ties: later sector, larger index first
   struct Ent { double s; int sec, idx; };
   std::vector<Ent> all;
-  for (size_t si = 0; si < secs.size(); ++si) { secs[si]->keep = (int)secs[si]->k; for (int i = 0; i < secs[si]->k; ++i) all.push_back(Ent{sv[si][i], (int)si, i}); }
+  for (int si = 0; si < ns; ++si) { secs[si]->keep = (int)secs[si]->k; for (int i = 0; i < secs[si]->k; ++i) all.push_back(Ent{sv[si][i], si, i}); }
   std::stable_sort(all.begin(), all.end(), [](const Ent& a, const Ent& b) {
     if (a.s != b.s) return a.s < b.s;
     if (a.sec != b.sec) return a.sec > b.sec;
@@ -347,13 +527,13 @@ int tsvd(Ctx* ctx, const Tensor* x, int d1, const int32_t* p1ch, mpsk_trunc trun
   for (size_t i = 0; i < ndrop; ++i) { secs[all[i].sec]->keep--; dropped2 += all[i].s * all[i].s; }
   if (eps_out) *eps_out = std::sqrt(dropped2);
   double kept2 = 0.0;
-  for (size_t si = 0; si < secs.size(); ++si) for (int i = 0; i < secs[si]->keep; ++i) kept2 += sv[si][i] * sv[si][i];
+  for (int si = 0; si < ns; ++si) for (int i = 0; i < secs[si]->keep; ++i) kept2 += sv[si][i] * sv[si][i];
   if (kept2 <= 0.0) return ctx->fail(MPSK_EINVAL, "tsvd: truncation removed every singular value");
   const double snorm = normalize ? 1.0 / std::sqrt(kept2) : 1.0;
   // record the spectrum for mpsk_tsvd_spectrum
   TsvdSpectrum& sp = ctx->last_spectrum;
   sp.charge.clear(); sp.count.clear(); sp.kept.clear(); sp.values.clear();
-  for (size_t si = 0; si < secs.size(); ++si) {
+  for (int si = 0; si < ns; ++si) {
     sp.charge.push_back(secs[si]->Q); sp.count.push_back((int32_t)secs[si]->k); sp.kept.push_back(secs[si]->keep);
     sp.values.insert(sp.values.end(), sv[si].begin(), sv[si].end());
   }
@@ -369,7 +549,7 @@ int tsvd(Ctx* ctx, const Tensor* x, int d1, const int32_t* p1ch, mpsk_trunc trun
   std::unique_ptr<Tensor> vg(Vt);
   tasks.clear();
   for (Coupled* c : secs) {
-    if (c->keep <= 0) continue;
+    if (c->keep <= 0 || !c->mine) continue;
     const int jn = Vn.find(c->Q);
     for (size_t ri = 0; ri < c->rows.size(); ++ri) {
       const int jl = c->rows[ri].first, u = c->rows[ri].second;
@@ -395,7 +575,13 @@ int tsvd(Ctx* ctx, const Tensor* x, int d1, const int32_t* p1ch, mpsk_trunc trun
     ctx->launches++;
   }
   MPSK_TRY(run_copy_tasks(ctx, tasks, cx));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (dist) {   // every element of the outputs was written by exactly one rank (zero elsewhere): a sum assembles them
+    const size_t dpe = cx ? 2 : 1;
+    MPSK_TRY(comm_allreduce_sum(ctx, Ut->d, (size_t)Ut->nelem * dpe));
+    MPSK_TRY(comm_allreduce_sum(ctx, St->d, (size_t)St->nelem * dpe));
+    MPSK_TRY(comm_allreduce_sum(ctx, Vt->d, (size_t)Vt->nelem * dpe));
+  }
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // the pool streams may reuse this memory next
   *Uo = ug.release(); *So = sg.release(); *Vo = vg.release();
   return MPSK_OK;
 }
@@ -489,7 +675,6 @@ int qrpos(Ctx* ctx, const Tensor* A, bool left, Tensor** Qo, Tensor** Ro) {
     else q_phase_kernel<false><<<grid2, 256, 0, ctx->stream>>>((double*)s.W, m, m, k, s.ph);
     ctx->launches += 4;
     CUDA_TRY(ctx, cudaGetLastError());
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->free(work);
     // Q blocks
     for (auto& rw : s.rows) {
@@ -510,7 +695,6 @@ int qrpos(Ctx* ctx, const Tensor* A, bool left, Tensor** Qo, Tensor** Ro) {
   }
   ctx->free(d_info);
   MPSK_TRY(run_copy_tasks(ctx, tasks, cx));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   *Qo = qg.release(); *Ro = rg.release();
   return MPSK_OK;
 }

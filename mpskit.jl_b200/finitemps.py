@@ -225,7 +225,15 @@ class FiniteMPS:
 
     # ---- read-outs ------------------------------------------------------------------------------
     def entanglement_spectrum(self, i):
-        """toolbox.jl:65-69: singular values of CR[i] per sector (host read-out of a small bond matrix)."""
+        """toolbox.jl:65-69: singular values of CR[i] per sector, computed on the device (the bond matrix is factorised by
+        the library's per-sector SVD, only the spectrum comes back to the host)."""
         Cm = self.CR[i]
-        blocks = Cm.to_blocks()
-        return {Cm.Vl.charges[jl]: np.linalg.svd(b, compute_uv=False) for (m, jl), b in blocks.items()}
+        ctx = self.ctx
+        pc = (C.c_int32 * 1)(0)
+        U, S, Vh = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        eps = C.c_double()
+        ctx.check(ctx.lib.mpsk_tsvd(ctx.h, Cm.h, 1, pc, _lib.c_trunc(_lib.NOTRUNC | 0x100, 0.0), C.byref(U), C.byref(S), C.byref(Vh), C.byref(eps)))
+        for h in (U, S, Vh):
+            ctx.lib.mpsk_tensor_free(ctx.h, h)
+        from .dmrg import tsvd_spectrum
+        return {q: vals for q, (vals, kept) in tsvd_spectrum(ctx).items()}

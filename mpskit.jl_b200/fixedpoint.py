@@ -28,11 +28,23 @@ class Arnoldi:
     hermitian: bool = True
 
 
+def _device_handle(A, x0):
+    """mpsk_op handle of A acting on vectors like x0, or None when A is not expressible as one device operator"""
+    if hasattr(A, "h") and A.h is not None:
+        return A.h
+    if hasattr(A, "device_op") and hasattr(x0, "h"):
+        return A.device_op(x0).h
+    return None
+
+
 def fixedpoint(A, x0, which, alg, return_info=False):
-    """val, vec = fixedpoint(A, x0, which, alg)   (fixedpoint.jl:9-30)"""
+    """val, vec = fixedpoint(A, x0, which, alg)   (fixedpoint.jl:9-30).  Single device operators (effective Hamiltonians,
+    transfer matrices) run inside the library: Lanczos (thick restart) for Hermitian maps, Krylov-Schur Arnoldi otherwise."""
     herm = 1 if isinstance(alg, Lanczos) or getattr(alg, "hermitian", False) else 0
-    if not (herm and hasattr(A, "h") and hasattr(x0, "h")):
-        # not a single Hermitian device operator: host-driven Krylov over the VectorInterface (krylov.py), as KrylovKit does
+    handle = _device_handle(A, x0) if hasattr(x0, "h") else None
+    if handle is None:
+        # sums of operators / tuples of vectors (LazySum, RecursiveVec): host-driven Krylov over the VectorInterface
+        # (krylov.py), the way KrylovKit drives the reference
         from . import krylov
         solver = krylov.eigsolve_lanczos if herm else krylov.eigsolve_arnoldi
         val, vec, info = solver(A, x0, which, alg.tol, alg.krylovdim, alg.maxiter)
@@ -43,7 +55,7 @@ def fixedpoint(A, x0, which, alg, return_info=False):
     vec = x0.zerovector()
     re, im = C.c_double(), C.c_double()
     info = _lib.c_info()
-    ctx.check(ctx.lib.mpsk_eigsolve(ctx.h, A.h, x0.h, _WHICH[which], herm, alg.krylovdim, alg.maxiter, alg.tol,
+    ctx.check(ctx.lib.mpsk_eigsolve(ctx.h, handle, x0.h, _WHICH[which], herm, alg.krylovdim, alg.maxiter, alg.tol,
                                     C.byref(re), C.byref(im), vec.h, C.byref(info)))
     if info.converged == 0:   # fixedpoint.jl:12-14
         warnings.warn(f"fixedpoint not converged after {info.numiter} iterations: normres = {info.normres}")
@@ -51,6 +63,26 @@ def fixedpoint(A, x0, which, alg, return_info=False):
     if return_info:
         return val, vec, dict(converged=info.converged, numiter=info.numiter, numops=info.numops, normres=info.normres)
     return val, vec
+
+
+def linsolve(f, b, x0, a0=1.0, a1=-1.0, tol=1e-12, krylovdim=30, maxiter=100, return_info=False):
+    """x = linsolve(f, b, x0, GMRES(tol, krylovdim, maxiter), a0, a1): (a0 + a1 f) x = b (mpohaminfenv.jl:95,113,146,164).
+    Device transfer-matrix operators are solved by the library's GMRES (mpsk_linsolve); anything else by krylov.py."""
+    handle = _device_handle(f, x0) if hasattr(x0, "h") else None
+    if handle is None:
+        from . import krylov
+        x, info = krylov.linsolve_gmres(f, b, x0, a0, a1, tol, krylovdim, maxiter)
+    else:
+        ctx = x0.ctx
+        x = x0.zerovector()
+        ci = _lib.c_info()
+        a0, a1 = complex(a0), complex(a1)
+        ctx.check(ctx.lib.mpsk_linsolve(ctx.h, handle, b.h, x0.h, a0.real, a0.imag, a1.real, a1.imag, krylovdim, maxiter, tol,
+                                        x.h, C.byref(ci)))
+        info = dict(converged=ci.converged, numops=ci.numops, normres=ci.normres)
+    if info["converged"] == 0:
+        warnings.warn(f"linsolve failed to converge: normres = {info['normres']}")
+    return (x, info) if return_info else x
 
 
 def integrate(f, y0, t, dt, alg: Lanczos = None, return_info=False):

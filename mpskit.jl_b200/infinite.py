@@ -15,7 +15,7 @@ from .tensor import DeviceTensor
 from .operators import SparseMPOSlice, MPOHamiltonian
 from .finitemps import qrpos, lqpos, _mask
 from .derivatives import MPO_ddAC, MPO_ddC
-from .fixedpoint import fixedpoint, Arnoldi, Lanczos
+from .fixedpoint import fixedpoint, linsolve, Arnoldi, Lanczos
 from . import krylov
 
 TOLGAUGE = 1e-14
@@ -79,37 +79,65 @@ def transfer_right(v, sl1, A, Ab):
     return DeviceTensor.wrap(ctx, h, A.Vl.modulus)
 
 
+class _DeviceOp:
+    """an mpsk_op handle created by mpsk_tmop_create (persistent plans; freed with the wrapper)"""
+
+    def __init__(self, ctx, h):
+        self.ctx, self.h = ctx, h
+
+    def __call__(self, v):
+        y = v.zerovector()
+        self.ctx.check(self.ctx.lib.mpsk_op_apply(self.ctx.h, self.h, v.h, y.h))
+        return y
+
+    def free(self):
+        if self.h is not None and self.ctx.h:
+            self.ctx.lib.mpsk_op_free(self.ctx.h, self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _tmop(ctx, left, middle, above, below, v_like, ladj=None, rvec=None):
+    n = len(above)
+    sl = (C.c_void_p * n)(*[(m_.device(ctx) if m_ is not None else None) for m_ in middle])
+    A = (C.c_void_p * n)(*[a.h for a in above])
+    Ab = (C.c_void_p * n)(*[a.h for a in below])
+    h = C.c_void_p()
+    ctx.check(ctx.lib.mpsk_tmop_create(ctx.h, 1 if left else 0, n, sl, A, Ab, v_like.h,
+                                       ladj.h if ladj is not None else None, rvec.h if rvec is not None else None, C.byref(h)))
+    return _DeviceOp(ctx, h)
+
+
 class TransferMatrix:
     """TransferMatrix(above, middle, below) over a unit cell; `tm * v` / `v * tm` (transfermatrix.jl:43-66).
-    above / below: lists of site tensors; middle: list of 1x1 slices (or None)."""
+    above / below: lists of site tensors; middle: list of MPO slices (or None: MPO-free transfer).  The product over the
+    unit cell is ONE device operator (mpsk_tmop_create) whose plans are built once per vector structure."""
 
     def __init__(self, above, middle, below, isflipped=False):
-        self.above = above if isinstance(above, (list, tuple)) else [above]
-        self.below = below if isinstance(below, (list, tuple)) else [below]
+        self.above = list(above) if isinstance(above, (list, tuple)) else [above]
+        self.below = list(below) if isinstance(below, (list, tuple)) else [below]
         mid = middle if isinstance(middle, (list, tuple)) else [middle] * len(self.above)
         self.middle = list(mid)
         self.isflipped = isflipped
-        self._unit = None
-
-    def _sl(self, i):
-        if self.middle[i] is not None:
-            return self.middle[i]
-        if self._unit is None:
-            pq = self.above[0].mch
-            self._unit = SparseMPOSlice([[1.0]], (0,), (0,), pq)
-        return self._unit
+        self.ctx = self.above[0].ctx
+        self._ops = {}
 
     def flip(self):
         return TransferMatrix(self.above, self.middle, self.below, not self.isflipped)
 
+    def device_op(self, v, ladj=None, rvec=None):
+        key = (v.Vl, v.mch, v.Vr, id(ladj), id(rvec))
+        if key not in self._ops:
+            self._ops[key] = _tmop(self.ctx, self.isflipped, self.middle, self.above, self.below, v, ladj, rvec)
+        return self._ops[key]
+
     def __call__(self, v):
-        if self.isflipped:                      # v * tm: sweep left -> right
-            for i in range(len(self.above)):
-                v = transfer_left(v, self._sl(i), self.above[i], self.below[i])
-        else:                                   # tm * v: sweep right -> left
-            for i in range(len(self.above) - 1, -1, -1):
-                v = transfer_right(v, self._sl(i), self.above[i], self.below[i])
-        return v
+        return self.device_op(v)(v)
 
     def __mul__(self, v):
         return self(v)
@@ -118,17 +146,22 @@ class TransferMatrix:
         return self.flip()(v)
 
 
-def regularize(tm, lvec, rvec):
-    """RegTransferMatrix (transfermatrix.jl:28-33,55,68-76): v -> tm(v) - <lvec, tm(v)> rvec with
-    <l, v> = sum l[1;2] v[2;1]"""
-    ladj = lvec.adjoint()
+class RegTransferMatrix:
+    """RegTransferMatrix (transfermatrix.jl:28-33,55,68-76): v -> tm(v) - <lvec, tm(v)> rvec with <l, v> = sum l[1;2] v[2;1];
+    the projection runs inside the device operator (the coefficient never leaves the GPU)."""
 
-    def f(v):
-        w = tm(v)
-        s = ladj.dot(w)
-        w.axpy(-s, rvec)
-        return w
-    return f
+    def __init__(self, tm, lvec, rvec):
+        self.tm, self.ladj, self.rvec, self.ctx = tm, lvec.adjoint(), rvec, tm.ctx
+
+    def device_op(self, v):
+        return self.tm.device_op(v, self.ladj, self.rvec)
+
+    def __call__(self, v):
+        return self.device_op(v)(v)
+
+
+def regularize(tm, lvec, rvec):
+    return RegTransferMatrix(tm, lvec, rvec)
 
 
 # ------------------------------------------------------------------------------------------ InfiniteMPS
@@ -325,10 +358,8 @@ def _right_cyclethrough(index, fp, H, st):
 
 
 def _gmres(f, b, x0, tol, maxiter):
-    x, info = krylov.linsolve_gmres(f, b, x0, 1.0, -1.0, tol, 30, maxiter)
-    if info["converged"] == 0:
-        warnings.warn(f"environment linsolve failed to converge: normres = {info['normres']}")
-    return x
+    """linsolve(flip(tm), b, x0, solver, 1, -1) (mpohaminfenv.jl:95): device GMRES on the transfer-matrix operator"""
+    return linsolve(f, b, x0, 1.0, -1.0, tol, 30, maxiter)
 
 
 def calclw(fp, st: InfiniteMPS, H, tol, maxiter):

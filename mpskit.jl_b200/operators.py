@@ -9,7 +9,8 @@ from . import _lib
 
 
 class SparseMPOSlice:
-    def __init__(self, Os, level_charges_left, level_charges_right, phys_charges):
+    def __init__(self, Os, level_charges_left, level_charges_right, phys_charges, modulus=0):
+        self.modulus = int(modulus)                                    # 0: U(1) / trivial charges, N: Z_N
         self.odim = len(Os)
         self.Os = [[Os[i][j] for j in range(self.odim)] for i in range(self.odim)]
         self.domcharges = tuple(int(c) for c in level_charges_left)    # domspaces (left virtual levels)
@@ -64,8 +65,8 @@ class SparseMPOSlice:
             cl = (C.c_int32 * od)(*self.domcharges); cr = (C.c_int32 * od)(*self.imcharges)
             pc = (C.c_int32 * d)(*self.pcharges)
             h = C.c_void_p()
-            ctx.check(ctx.lib.mpsk_mposlice_create(ctx.h, od, cl, cr, d, pc, kind, scal,
-                                                   flat.ctypes.data_as(C.POINTER(C.c_double)), C.byref(h)))
+            ctx.check(ctx.lib.mpsk_mposlice_create_zn(ctx.h, od, cl, cr, d, pc, kind, scal,
+                                                      flat.ctypes.data_as(C.POINTER(C.c_double)), self.modulus, C.byref(h)))
             self._dev[key] = h
         return self._dev[key]
 
@@ -119,6 +120,20 @@ def transverse_field_ising(L, g=1.0):
     X = np.array([[0, 1], [1, 0]], dtype=np.complex128)
     Z = np.array([[1, 0], [0, -1]], dtype=np.complex128)
     return _fsm(L, 3, {(0, 0): 1.0, (2, 2): 1.0, (0, 1): -Z, (1, 2): Z, (0, 2): -g * X}, (0, 0, 0), (0, 0))
+
+
+def transverse_field_ising_z2(L, g=1.0):
+    """the same operator in the X eigenbasis with its Z2 parity symmetry: -sum X X - g sum Z (|+>: charge 0, |->: charge 1);
+    the coupling operator flips the parity, so its MPO level carries charge 1 (mod 2)."""
+    X = np.array([[0, 1], [1, 0]], dtype=np.complex128)
+    Z = np.array([[1, 0], [0, -1]], dtype=np.complex128)
+    out = []
+    for _ in range(L):
+        Os = [[0] * 3 for _ in range(3)]
+        for (i, j), v in {(0, 0): 1.0, (2, 2): 1.0, (0, 1): -X, (1, 2): X, (0, 2): -g * Z}.items():
+            Os[i][j] = v
+        out.append(SparseMPOSlice(Os, (0, 1, 0), (0, 1, 0), (0, 1), modulus=2))
+    return MPOHamiltonian(out)
 
 
 def heisenberg_u1(L, d=2, J=1.0):

@@ -1,14 +1,14 @@
 """leading_boundary(psi::InfiniteMPS, O::DenseMPO, VUMPS()) on the device: src/algorithms/statmech/vumps.jl:15-84,
 PerMPOInfEnv + mixed_fixpoints (src/environments/permpoinfenv.jl:23-63,138-189), expectation_value
 (src/algorithms/expval.jl:165-173).  Single-row unit cells (an InfiniteMPS with any number of columns); the
-non-Hermitian eigenproblems use the host-driven Arnoldi of krylov.py on device vectors."""
+non-Hermitian eigenproblems are solved by the library's device-resident Krylov-Schur Arnoldi (mpsk_eigsolve, hermitian = 0)."""
 from __future__ import annotations
 import ctypes as C
 import numpy as np
 from .tensor import DeviceTensor
 from .derivatives import MPO_ddAC, MPO_ddC
 from .fixedpoint import fixedpoint, Arnoldi
-from .infinite import InfiniteMPS, regauge, dyn_tol, TOLGAUGE, mul_right, VUMPS
+from .infinite import InfiniteMPS, TransferMatrix, regauge, dyn_tol, TOLGAUGE, mul_right, VUMPS
 from .algorithms import _overlap
 
 
@@ -44,15 +44,11 @@ class PerMPOInfEnv:
         L0 = self.lw[0] if same else DeviceTensor.random(ctx, V0, lc, V0, 17, psi.dtype)
         R0 = self.rw[N - 1] if same else DeviceTensor.random(ctx, V0, rc, V0, 18, psi.dtype)
 
-        def TL(v):
-            for i in range(N):
-                v = _tl(psi, self.opp[i], psi.AL[i], v)
-            return v
-
-        def TR(v):
-            for i in range(N - 1, -1, -1):
-                v = _tr(psi, self.opp[i], psi.AR[i], v)
-            return v
+        # TransferMatrix(AL, O, AL) over the unit cell (permpoinfenv.jl:150-170) as single device operators: the Arnoldi
+        # (Krylov-Schur) solves run inside the library
+        mids = [self.opp[i] for i in range(N)]
+        TL = TransferMatrix(list(psi.AL), mids, list(psi.AL)).flip()
+        TR = TransferMatrix(list(psi.AR), mids, list(psi.AR))
         alg = Arnoldi(tol=tol, krylovdim=30, maxiter=100, hermitian=False)
         GL, GR = [None] * N, [None] * N
         _, GL[0] = fixedpoint(TL, L0, "LM", alg)

@@ -149,3 +149,33 @@ def test_header_is_plain_c99_and_links_from_c(tmp_path):
                         "-L", libdir, "-lmpskit_b200", "-Wl,-rpath," + libdir], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert subprocess.run([str(exe)]).returncode == 0
+
+
+def test_host_schur_and_reordering_against_numpy():
+    """the complex Schur decomposition + reordering behind the device Krylov-Schur eigensolver (csrc/eigsolve.cu) is pure
+    host code: checked here without a GPU against numpy (A = Z T Z^H, T upper triangular, Z unitary, eigenvalues)."""
+    import ctypes as C
+    import numpy as np
+    import mpskit_b200 as m
+    lib = m.load_library()
+    DP = C.POINTER(C.c_double)
+    rng = np.random.default_rng(1)
+    for n in (1, 2, 3, 7, 30, 61):
+        A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+        if n == 7:
+            A = np.triu(A, -1)                                        # already Hessenberg (plain Arnoldi)
+        H = np.asfortranarray(A.copy()); Z = np.zeros((n, n), dtype=complex, order="F")
+        assert lib.mpsk_host_schur(n, H.ctypes.data_as(DP), Z.ctypes.data_as(DP), -1, -1) == 0
+        assert np.abs(Z @ H @ Z.conj().T - A).max() <= 1e-12 * max(1.0, np.abs(A).max()) * n
+        assert np.abs(np.tril(H, -1)).max() == 0.0
+        assert np.abs(Z.conj().T @ Z - np.eye(n)).max() <= 1e-13 * n
+        ev = np.linalg.eigvals(A)
+        assert max(np.abs(ev - d).min() for d in np.diag(H)) <= 1e-11 * n
+        if n >= 3:
+            H2 = np.asfortranarray(A.copy()); Z2 = np.zeros((n, n), dtype=complex, order="F")
+            assert lib.mpsk_host_schur(n, H2.ctypes.data_as(DP), Z2.ctypes.data_as(DP), n - 1, 0) == 0
+            assert abs(H2[0, 0] - H[n - 1, n - 1]) <= 1e-12 * n       # the last eigenvalue moved to the front
+            assert np.abs(Z2 @ H2 @ Z2.conj().T - A).max() <= 1e-12 * max(1.0, np.abs(A).max()) * n
+            assert np.abs(np.tril(H2, -1)).max() == 0.0
+            # first Schur vector = eigenvector of the leading eigenvalue
+            assert np.linalg.norm(A @ Z2[:, 0] - H2[0, 0] * Z2[:, 0]) <= 1e-11 * n

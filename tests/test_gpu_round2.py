@@ -1,0 +1,307 @@
+"""GPU parity tests added in round 2: device Arnoldi (Krylov-Schur) / GMRES / thick-restart Lanczos against dense
+linear algebra, the multi-level Gram SVD on prescribed (rapidly decaying) spectra, Z_N-graded MPO slices, ket-index
+panels, the on-device entanglement spectrum and converged-run parity at the north-star tolerances
+(energies 1e-10 relative, singular values / truncation errors 1e-8, bookkeeping bit-exact)."""
+import ctypes as C
+import numpy as np
+import pytest
+import mpskit_b200 as m
+from mpskit_b200 import _lib
+from oracle.spaces import Space as OSpace
+from oracle.blocks import BlockTensor
+from oracle import mpo as ompo, contract as oc, linalg as ol, finite as of, krylov as ok
+from helpers import *
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_site(rng, Vl, pq, Vr):
+    return BlockTensor.random(rng, Vl, pq, Vr)
+
+
+def _dense_tm_left(As, Bs):
+    """matrix of v[a;b] -> v * TransferMatrix(A, nothing, B) over the unit cell ('ab,bpc,apd->dc' per site), acting on
+    vec(v) in C order"""
+    Da, Db = Bs[0].shape[0], As[0].shape[0]
+    n = Da * Db
+    T = np.zeros((n, n), dtype=np.complex128)
+    for k in range(n):
+        v = np.zeros(n, dtype=np.complex128); v[k] = 1
+        v = v.reshape(Da, Db)
+        for A, B in zip(As, Bs):
+            v = np.einsum('ab,bpc,apd->dc', v, A, B.conj())
+        T[:, k] = v.reshape(-1)
+    return T
+
+
+@pytest.mark.parametrize("sym", ["trivial", "u1"])
+def test_device_arnoldi_transfer_matrix_vs_dense(ctx, sym):
+    """fixedpoint(flip(TransferMatrix(A, B)), v0, :LM, Arnoldi) (fixedpoint.jl:19-30; ortho.jl:184) inside the library:
+    Krylov-Schur with a small krylovdim (several restarts) against numpy.linalg.eig of the dense transfer matrix."""
+    rng = np.random.default_rng(201)
+    if sym == "trivial":
+        pq = [0, 0]; Vs = [OSpace((0,), (7,)), OSpace((0,), (6,))]
+    else:
+        pq = [-1, 1]; Vs = [OSpace((-2, 0, 2), (2, 4, 2)), OSpace((-1, 1), (4, 3))]
+    A = [_rand_site(rng, Vs[i], pq, Vs[(i + 1) % 2]) for i in range(2)]
+    B = [_rand_site(rng, Vs[i], pq, Vs[(i + 1) % 2]) for i in range(2)]
+    dA, dB = [dev_tensor(ctx, t) for t in A], [dev_tensor(ctx, t) for t in B]
+    v0 = BlockTensor.random(rng, Vs[0], [0], Vs[0])
+    dv = dev_tensor(ctx, v0)
+    tm = m.TransferMatrix(dA, None, dB).flip()
+    # one application against the dense einsum
+    T = _dense_tm_left([t.to_dense() for t in A], [t.to_dense() for t in B])
+    out = tm(dv).to_dense()[:, 0, :]
+    ref = (T @ v0.to_dense()[:, 0, :].reshape(-1)).reshape(out.shape)
+    assert relerr(out, ref) <= 1e-12
+    # charge-0 block of T: restrict to symmetric vectors
+    mask = (v0.to_dense()[:, 0, :] != 0).reshape(-1)
+    ev = np.linalg.eigvals(T[np.ix_(mask, mask)])
+    lam = ev[np.argmax(np.abs(ev))]
+    val, vec, info = m.fixedpoint(tm, dv, "LM", m.Arnoldi(tol=1e-12, krylovdim=8, maxiter=200, hermitian=False), return_info=True)
+    print("arnoldi", sym, val, lam, info)
+    assert info["converged"] == 1
+    assert abs(abs(val) - abs(lam)) <= 1e-10 * abs(lam)
+    w = vec.to_dense()[:, 0, :].reshape(-1)
+    assert np.linalg.norm(T @ w - val * w) <= 1e-9 * abs(val) * np.linalg.norm(w)      # eigen-residual
+    # the same through the host-driven Arnoldi of krylov.py (cross-check of the two implementations)
+    from mpskit_b200 import krylov
+    val_h, _, _ = krylov.eigsolve_arnoldi(lambda x: tm(x), dv, "LM", 1e-12, 30, 100)
+    assert abs(abs(val_h) - abs(val)) <= 1e-9 * abs(val)
+
+
+def test_device_gmres_regularised_transfer_matrix_vs_dense(ctx):
+    """linsolve(f, b, x0, GMRES, 1, -1) (mpohaminfenv.jl:95): (1 - T) x = b with T a contraction, and with a
+    regularised T (transfermatrix.jl:68-76), against numpy.linalg.solve."""
+    rng = np.random.default_rng(202)
+    pq = [0, 0]; V = OSpace((0,), (6,))
+    A = _rand_site(rng, V, pq, V); B = _rand_site(rng, V, pq, V)
+    T = _dense_tm_left([A.to_dense()], [B.to_dense()])
+    scale = 0.7 / np.abs(np.linalg.eigvals(T)).max()
+    A.blocks = {k: v * scale for k, v in A.blocks.items()}
+    T = T * scale
+    dA, dB = dev_tensor(ctx, A), dev_tensor(ctx, B)
+    b = BlockTensor.random(rng, V, [0], V); x0 = BlockTensor.random(rng, V, [0], V)
+    db, dx0 = dev_tensor(ctx, b), dev_tensor(ctx, x0)
+    tm = m.TransferMatrix([dA], None, [dB]).flip()
+    from mpskit_b200.fixedpoint import linsolve
+    x, info = linsolve(tm, db, dx0, 1.0, -1.0, 1e-12, 10, 100, return_info=True)      # krylovdim 10 < 36: restarts
+    ref = np.linalg.solve(np.eye(T.shape[0]) - T, b.to_dense()[:, 0, :].reshape(-1))
+    print("gmres", info)
+    assert info["converged"] == 1
+    assert relerr(x.to_dense()[:, 0, :].reshape(-1), ref) <= 1e-10
+    # regularised: v -> T v - <l, T v> r with <l, v> = sum l[1;2] v[2;1]
+    l = BlockTensor.random(rng, V, [0], V); r = BlockTensor.random(rng, V, [0], V)
+    dl, dr = dev_tensor(ctx, l), dev_tensor(ctx, r)
+    reg = m.regularize(tm, dl, dr)
+    lv = l.to_dense()[:, 0, :].T.reshape(-1)                  # <l, v> = sum_ab l[b,a] v[a,b]
+    Treg = T - np.outer(r.to_dense()[:, 0, :].reshape(-1), lv @ T)
+    out = reg(dx0).to_dense()[:, 0, :].reshape(-1)
+    assert relerr(out, Treg @ x0.to_dense()[:, 0, :].reshape(-1)) <= 1e-12
+    c = 0.5 + 0.25j
+    x2, info2 = linsolve(reg, db, dx0, 1.0, -c, 1e-12, 30, 100, return_info=True)
+    ref2 = np.linalg.solve(np.eye(T.shape[0]) - c * Treg, b.to_dense()[:, 0, :].reshape(-1))
+    assert info2["converged"] == 1 and relerr(x2.to_dense()[:, 0, :].reshape(-1), ref2) <= 1e-10
+
+
+def test_lanczos_thick_restart_small_krylovdim(ctx):
+    """eigsolve with krylovdim 6 needs many thick restarts; the converged eigenpair equals the dense one"""
+    rng = np.random.default_rng(41)
+    L = 6
+    Ho = ompo.heisenberg_u1(L)
+    p = OSpace((-1, 1), (1, 1))
+    psi = of.FiniteMPS.random(rng, p, L, [of.gaussian_bond_space(12, k % 2) for k in range(1, L)])
+    envs = of.FinEnv(psi, Ho)
+    pos = 2
+    ac2 = np.einsum('apk,kqr->aprq', psi.get_AC(pos), psi.get_AR(pos + 1))
+    GL, GR = envs.leftenv(pos, psi), envs.rightenv(pos + 1, psi)
+    Vl, Vr = psi.V[pos], psi.V[pos + 2]
+    h = Ho[pos]
+    mch = [h.pch[a] + h.pch[b] for a in range(2) for b in range(2)]
+    val_o, vec_o, _ = ok.eigsolve_lanczos(lambda v: oc.dAC2_sparse(v, h, h, GL, GR), ac2, "SR", 1e-13, 40, 100)
+    dVl, dVr = to_dev_space(Vl), to_dev_space(Vr)
+    dx = m.DeviceTensor.from_dense(ctx, x2_from_dense(ac2, 2), dVl, mch, dVr)
+    dGL = m.DeviceTensor.from_dense(ctx, GL, dVl, [-c for c in h.cl], dVl)
+    dGR = m.DeviceTensor.from_dense(ctx, GR, dVr, [c for c in h.cr], dVr)
+    op = m.MPO_ddAC2(ctx, dev_slice(h), dev_slice(h), dGL, dGR, dx)
+    for kd in (6, 3):
+        val, vec, info = m.fixedpoint(op, dx, "SR", m.Lanczos(tol=1e-12, krylovdim=kd, maxiter=500), return_info=True)
+        print("thick restart kd", kd, val, val_o, info)
+        assert info["converged"] == 1 and info["numiter"] > 1
+        assert abs(val.real - val_o) <= 1e-10 * abs(val_o)
+        v = x2_dense(BlockTensor.from_dense(vec.to_dense(), Vl, mch, Vr), 2)
+        assert abs(abs(np.vdot(vec_o, v)) - 1) <= 1e-8
+    # the Arnoldi (Krylov-Schur) path on the same Hermitian operator gives the same eigenvalue (Defaults.eigsolver is Arnoldi)
+    val_a, _, info_a = m.fixedpoint(op, dx, "SR", m.Arnoldi(tol=1e-12, krylovdim=8, maxiter=300, hermitian=False), return_info=True)
+    assert info_a["converged"] == 1 and abs(val_a.real - val_o) <= 1e-10 * abs(val_o) and abs(val_a.imag) <= 1e-10
+
+
+def _prescribed(rng, mrows, ncols, svals, dtype):
+    k = len(svals)
+    def orth(n):
+        a = rng.standard_normal((n, k))
+        if np.dtype(dtype).kind == "c":
+            a = a + 1j * rng.standard_normal((n, k))
+        return np.linalg.qr(a)[0]
+    return (orth(mrows) * svals[None, :]) @ orth(ncols).conj().T
+
+
+@pytest.mark.parametrize("dtype,shape", [(np.complex128, (300, 260)), (np.float64, (301, 257)), (np.complex128, (150, 310))])
+def test_tsvd_gram_route_prescribed_spectrum(dtype, shape):
+    """multi-level Gram SVD (csrc/svd.cu) on a matrix with singular values 1 ... 1e-14 (the physical, rapidly decaying
+    case the single-level route of round 1 got wrong below 1e-8): sigma, eps_trunc, kept dims, reconstruction, isometries.
+    The float64 case has odd dimensions (TMA needs padded leading dimensions)."""
+    c = m.Context(0, _lib.FLAG_FAST_SVD_ALL)
+    rng = np.random.default_rng(301)
+    mr, nc = shape
+    k = min(mr, nc)
+    s = np.logspace(0, -14, k)
+    M = _prescribed(rng, mr, nc, s, dtype)
+    Vl, Vr = OSpace((0,), (mr,)), OSpace((0,), (nc,))
+    x = BlockTensor(Vl, [0], Vr, dtype, {(0, 0): M})
+    s_ref = np.linalg.svd(M, compute_uv=False)                       # LAPACK gesdd: absolute accuracy eps * sigma_max
+
+    class P:
+        pass
+    P.ctx, P.pq, P.pspace = c, (0,), m.Space((0,), (1,))
+    al, cc, ar, eps0 = m.tsvd(P, dev_tensor(c, x), m.notrunc(), normalize=False)
+    sd = m.tsvd_spectrum(c)[0][0]
+    assert len(sd) == k
+    assert np.abs(sd - s_ref).max() <= 1e-12                         # absolute: 1e-8 required, gesvd-class achieved
+    big = s >= 1e-9
+    assert np.abs(sd[big] / s[big] - 1).max() <= 1e-6                # relative accuracy where the true values are known
+    assert np.all(np.diff(sd) <= 1e-15)                              # descending
+    U = al.to_dense().reshape(mr, -1); Vh = ar.to_dense().reshape(-1, nc); S = cc.to_dense()[:, 0, :]
+    assert np.abs(U.conj().T @ U - np.eye(k)).max() <= 1e-12
+    assert np.abs(Vh @ Vh.conj().T - np.eye(k)).max() <= 1e-12
+    assert np.linalg.norm(U @ S @ Vh - M) <= 1e-12 * np.linalg.norm(M)
+    # truncation decisions on the same matrix
+    for trunc in (("truncerr", 1e-6), ("truncbelow", 3e-9), ("truncdim", 40)):
+        rowq = np.zeros(mr, dtype=int); colq = np.zeros(nc, dtype=int)
+        _, S_o, _, newV, eps_o, info = ol.tsvd(M, rowq, colq, trunc)
+        al, cc, ar, eps_d = m.tsvd(P, dev_tensor(c, x), getattr(m, trunc[0])(trunc[1]), normalize=False)
+        assert al.Vr.dims == newV.dims, (trunc, al.Vr.dims, newV.dims)      # kept dimension: bit-exact
+        assert abs(eps_d - eps_o) <= 1e-10
+    c.close()
+
+
+def test_tsvd_gram_route_rank_deficient():
+    """exact zero singular values (rank-deficient two-site tensors of early sweeps) come out at the rounding floor, not
+    at sqrt(eps): truncbelow(1e-10) removes exactly the null space"""
+    c = m.Context(0, _lib.FLAG_FAST_SVD_ALL)
+    rng = np.random.default_rng(302)
+    mr, nc, rk = 280, 300, 37
+    M = (rng.standard_normal((mr, rk)) + 1j * rng.standard_normal((mr, rk))) @ (rng.standard_normal((rk, nc)) + 1j * rng.standard_normal((rk, nc)))
+    x = BlockTensor(OSpace((0,), (mr,)), [0], OSpace((0,), (nc,)), np.complex128, {(0, 0): M})
+
+    class P:
+        pass
+    P.ctx, P.pq, P.pspace = c, (0,), m.Space((0,), (1,))
+    al, cc, ar, eps = m.tsvd(P, dev_tensor(c, x), m.truncbelow(1e-10 * np.linalg.norm(M, 2)), normalize=False)
+    sd = m.tsvd_spectrum(c)[0][0]
+    assert al.Vr.dim == rk
+    assert sd[rk:].max() <= 1e-12 * sd[0]
+    assert eps <= 1e-11 * sd[0]
+    c.close()
+
+
+def test_z2_graded_slices_tfi_dmrg2_vs_exact(ctx):
+    """Z_N charges (`modulus`): the transverse-field Ising chain with its Z2 parity symmetry (charged MPO level):
+    DMRG2 at full bond dimension reproduces the exact ground-state energy of the dense Hamiltonian."""
+    L, g = 8, 0.7
+    Hd = m.operators.transverse_field_ising_z2(L, g)
+    E_exact = np.linalg.eigvalsh(ompo.dense_hamiltonian(ompo.transverse_field_ising(L, g))).min()
+    p = m.Space((0, 1), (1, 1), 2)
+    psi = m.FiniteMPS.random(np.random.default_rng(7), p, L, m.Space((0, 1), (8, 8), 2), ctx)
+    log = []
+    psi, envs, eps = m.find_groundstate(psi, Hd, m.DMRG2(tol=1e-12, maxiter=6, eigalg=m.Lanczos(tol=1e-13), trscheme=m.truncdim(16)), log=log)
+    print("Z2 TFI", log[-1]["energy"], E_exact)
+    assert abs(log[-1]["energy"] - E_exact) <= 1e-10 * abs(E_exact)
+    # a slice that violates Z2 conservation is still rejected
+    X = np.array([[0, 1], [1, 0]], dtype=np.complex128)
+    bad = m.SparseMPOSlice([[1.0, X], [0, 1.0]], (0, 0), (0, 0), (0, 1), modulus=2)
+    with pytest.raises(m.SpaceMismatch):
+        bad.device(ctx)
+
+
+def test_ket_index_panels_and_entanglement_spectrum(ctx):
+    """mpsk_tensor_panel over the right (ket) index -- the partition of the sharded environment updates -- against numpy
+    slicing with the library's integer rule; on-device entanglement_spectrum (toolbox.jl:65-69) against numpy SVD."""
+    rng = np.random.default_rng(401)
+    Vl, Vr = OSpace((-2, 0, 2), (5, 9, 4)), OSpace((-3, -1, 1, 3), (2, 7, 10, 3))
+    t = BlockTensor.random(rng, Vl, [-1, 1], Vr)
+    dt = dev_tensor(ctx, t)
+    dVr = to_dev_space(Vr)
+    for N in (2, 3, 8):
+        got = 0
+        for r in range(N):
+            h = C.c_void_p()
+            ctx.check(ctx.lib.mpsk_tensor_panel(ctx.h, dt.h, 1, r, N, C.byref(h)))
+            p = m.DeviceTensor.wrap(ctx, h)
+            Vp = m.panel_space(dVr, r, N)
+            assert (p.Vr.charges, p.Vr.dims) == (Vp.charges, Vp.dims) and p.Vl == dt.Vl
+            blocks = p.to_blocks()
+            for (mm, jl), b in blocks.items():
+                q = Vl.charges[jl] + t.mch[mm]
+                jr = Vr.charges.index(q)
+                lo, hi = m.panel_bounds(dVr, jr, r, N)
+                assert np.array_equal(b, t.blocks[(mm, jl)][:, lo:hi])              # bit-exact copy
+                got += b.size
+        assert got == t.numel()
+    # entanglement spectrum on the device
+    L = 6
+    p = m.Space((-1, 1), (1, 1))
+    psi = m.FiniteMPS.random(np.random.default_rng(9), p, L, [m.Space(v.charges, v.dims) for v in [of.gaussian_bond_space(8, k % 2) for k in range(1, L)]], ctx)
+    for i in (1, 2):
+        Cm = psi.CR[i]
+        es = psi.entanglement_spectrum(i)
+        for (mm, jl), b in Cm.to_blocks().items():
+            ref = np.linalg.svd(b, compute_uv=False)
+            assert np.abs(es[Cm.Vl.charges[jl]] - ref).max() <= 1e-12
+
+
+def test_dmrg2_converged_gram_route_vs_oracle():
+    """converged DMRG2 (Heisenberg U(1), L = 12, truncdim 32) with the multi-level Gram SVD forced on every sector: the
+    physical, decaying spectra go through the route the D = 4096 sweeps use.  Energy 1e-10, spectra / truncation errors
+    1e-8, kept sector dimensions bit-exact against the oracle sweep (LAPACK SVD)."""
+    c = m.Context(0, _lib.FLAG_FAST_SVD_ALL)
+    L, D = 12, 32
+    Ho = ompo.heisenberg_u1(L); p = OSpace((-1, 1), (1, 1))
+    maxV = [of.gaussian_bond_space(D, k % 2) for k in range(1, L)]
+    psi_o = of.FiniteMPS.random(np.random.default_rng(71), p, L, maxV)
+    log_o = []
+    of.dmrg2_sweeps(psi_o, Ho, nsweeps=4, trunc=("truncdim", D), tol=1e-13, log=log_o)
+    psi_d = m.FiniteMPS.random(np.random.default_rng(71), to_dev_space(p), L, [to_dev_space(v) for v in maxV], c)
+    log_d = []
+    alg = m.DMRG2(tol=1e-13, maxiter=4, eigalg=m.Lanczos(tol=1e-13), trscheme=m.truncdim(D))
+    psi_d, envs, eps = m.find_groundstate(psi_d, dev_hamiltonian(Ho), alg, log=log_d)
+    E_d, E_o = log_d[-1]["energy"], log_o[-1]["energy"]
+    print("gram-route DMRG2", E_d, E_o)
+    assert abs(E_d - E_o) <= 1e-10 * abs(E_o)
+    assert len(log_d) == len(log_o)
+    for a, b in zip(log_d[-2 * (L - 1):], log_o[-2 * (L - 1):]):       # the last (converged) sweep, step by step
+        assert {q: k for q, k in a["kept"].items() if k} == {q: k for q, k in b["kept"].items() if k}
+        assert abs(a["eps_trunc"] - b["eps_trunc"]) <= 1e-8
+        for q, s_o in b["spectrum"].items():
+            assert np.abs(a["spectrum"][q] - s_o).max() <= 1e-8
+    c.close()
+
+
+def test_exact_svd_flag_gives_same_energy(ctx):
+    """MPSK_FLAG_EXACT_SVD (gesvd everywhere) vs the default route on one DMRG2 run: energies agree to 1e-10"""
+    L, D = 10, 24
+    H = m.heisenberg_u1(L)
+    p = m.Space((-1, 1), (1, 1))
+    from mpskit_b200.workloads import gaussian_bond_space
+    maxV = [gaussian_bond_space(D, k % 2) for k in range(1, L)]
+    out = []
+    for flags in (_lib.FLAG_EXACT_SVD, _lib.FLAG_FAST_SVD_ALL):
+        c = m.Context(0, flags)
+        psi = m.FiniteMPS.random(np.random.default_rng(5), p, L, maxV, c)
+        log = []
+        m.find_groundstate(psi, H, m.DMRG2(tol=1e-13, maxiter=3, eigalg=m.Lanczos(tol=1e-13), trscheme=m.truncdim(D)), log=log)
+        out.append([e["energy"] for e in log])
+        c.close()
+    a, b = np.array(out[0]), np.array(out[1])
+    assert np.abs(a - b).max() <= 1e-10 * np.abs(a).max()
+    assert np.all(np.diff(a[-(L - 1):]) <= 1e-9)                      # energy non-increasing along the last half-sweep

@@ -290,9 +290,13 @@ def test_golden_trajectories_and_bench_flop_model():
     spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(GOLD), "..", "bench.py"))
     bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)
     V = of.gaussian_bond_space(4096, 0)
-    h = ompo.heisenberg_longrange_u1(2, 6)[0]
-    F = bench.algorithmic_flops(V, h, [h.pch[a] + h.pch[b] for a in range(2) for b in range(2)])
+    assert bench.bond_space_dims(4096) == V.as_dict()            # both bench arms build their config from this recipe
+    F = bench.algorithmic_flops_cfg3(4096, 6)
     assert F == 3084892580736.0 and abs(F - 3.1e12) < 0.05e12
+
+    class A:
+        D, r, gpus = 4096, 6, 4
+    assert bench.config_dict(A) == bench.config_dict(A) and bench.config_dict(A)["flops_per_matvec"] == F
 
 
 def test_idmrg1_oracle_matches_vumps_energy():
