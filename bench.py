@@ -193,7 +193,7 @@ def run_reference(args):
     except Exception:
         pass
     # bounded sample: calibrate on a small instance of the same recipe, then take the largest D <= args.D whose
-    # (warmup + steps) matvecs fit in ~150 s of CPU time (cost grows ~ D^3)
+    # (warmup + steps) matvecs fit in ~190 s of CPU time (cost grows ~ D^3)
     prob = cpu_problem(512, args.r)
     dAC2_blocks(prob[0], prob[3], prob[3], prob[1], prob[2])
     t0 = time.perf_counter()
@@ -201,7 +201,7 @@ def run_reference(args):
     t512 = time.perf_counter() - t0
     nrun = args.steps + args.warmup
     Ds = args.D
-    while Ds > 512 and nrun * t512 * (Ds / 512.0) ** 3 > 150.0:
+    while Ds > 512 and nrun * t512 * (Ds / 512.0) ** 3 > 190.0:
         Ds //= 2
     x, GL, GR, h = cpu_problem(Ds, args.r) if Ds != 512 else prob
     flops = algorithmic_flops_cfg3(Ds, args.r)

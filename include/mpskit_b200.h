@@ -52,7 +52,9 @@ enum { MPSK_NOTRUNC = 0, MPSK_TRUNCDIM = 1, MPSK_TRUNCERR = 2, MPSK_TRUNCBELOW =
 enum { MPSK_OP_DC = 0, MPSK_OP_DAC = 1, MPSK_OP_DAC2 = 2 };
 #define MPSK_OP_SHARDED 0x100   /* OR into `kind`: GL is this rank's row panel; apply/eigsolve/expv allgather the panels of y */
 
-#define MPSK_FLAG_EXACT_SVD 2ull      /* tsvd: cuSOLVER gesvd for every sector (default: multi-level Gram + heevd + QR route for sectors >= 256) */
+#define MPSK_FLAG_EXACT_SVD 2ull      /* tsvd: cuSOLVER gesvd for every sector (default: two-level Gram + heevd + QR route for sectors >= 32:
+                                         every singular value to ~1e-11 sigma_max absolute) */
+#define MPSK_FLAG_SVD_RELATIVE 16ull  /* tsvd: continue the Gram levels down to the rounding floor (full relative accuracy, up to 6 levels) */
 #define MPSK_FLAG_FAST_SVD_ALL 4ull   /* tsvd: Gram route for every sector (tests) */
 #define MPSK_FLAG_DEBUG_GEMM 1ull  /* route contractions through the one-thread-per-element cross-check kernel (tests only) */
 #define MPSK_FLAG_REPLICATE_LOCAL 8ull /* with a communicator: keep environment updates and tsvd replicated per rank (default: distributed) */

@@ -12,7 +12,7 @@ F64, C128 = 0, 1
 SR, LM, LR = 0, 1, 2
 NOTRUNC, TRUNCDIM, TRUNCERR, TRUNCBELOW = 0, 1, 2, 3
 OP_DC, OP_DAC, OP_DAC2 = 0, 1, 2
-FLAG_DEBUG_GEMM, FLAG_EXACT_SVD, FLAG_FAST_SVD_ALL, FLAG_REPLICATE_LOCAL = 1, 2, 4, 8
+FLAG_DEBUG_GEMM, FLAG_EXACT_SVD, FLAG_FAST_SVD_ALL, FLAG_REPLICATE_LOCAL, FLAG_SVD_RELATIVE = 1, 2, 4, 8, 16
 OP_SHARDED = 0x100
 
 

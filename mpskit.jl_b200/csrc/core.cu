@@ -550,12 +550,13 @@ int tensor_fill_random(Ctx* ctx, Tensor* t, uint64_t seed) {
 // ------------------------------------------------------------------------------------------ mix
 // out[row, col] = sum_t coeff_t * src_t[row, col] over row-major rectangles: HBM streaming.
 // A CTA owns a tile of the destination rectangle, the term table of the task sits in shared memory, every thread keeps
-// MIX_R independent row accumulators for one column (MIX_R x terms loads in flight per thread, fully coalesced along
-// the contiguous column index, no integer division anywhere).  Two tile shapes: 256 columns x 8 rows for wide
-// rectangles, 64 columns x 32 rows for narrow ones (small sectors).
+// MIX_R independent row accumulators for one column (MIX_R loads in flight per term and thread, fully coalesced along
+// the contiguous column index, no integer division anywhere).  Two tile shapes: 256 columns x 64 rows for wide
+// rectangles, 64 columns x 256 rows for narrow ones (small sectors); each thread walks MIX_G groups of MIX_R rows.
 struct MixTile { int32_t task, row0, col0, shape; };
 constexpr int MIX_R = 8;          // rows per thread
 constexpr int MIX_MAXT = 32;      // terms staged per round
+constexpr int MIX_G = 8;          // row groups per tile
 
 template <typename T> __device__ __forceinline__ T mix_zero();
 template <> __device__ __forceinline__ double mix_zero<double>() { return 0.0; }
@@ -566,43 +567,72 @@ __device__ __forceinline__ void mix_fma(double2& acc, double2 v, double cre, dou
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) mix_kernel(const MixTask* __restrict__ tasks, const MixTerm* __restrict__ terms,
-                                                  const MixTile* __restrict__ tiles, int ntiles) {
+__global__ void __launch_bounds__(256, 2) mix_kernel(const MixTask* __restrict__ tasks, const MixTerm* __restrict__ terms,
+                                                     const MixTile* __restrict__ tiles, int ntiles) {
   __shared__ MixTerm sterm[MIX_MAXT];
   for (int ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
     const MixTile tl = tiles[ti];
     const MixTask tk = tasks[tl.task];
     const int nt = tk.term_end - tk.term_begin;
-    int col, row0;
-    if (tl.shape == 0) { col = tl.col0 + (int)threadIdx.x; row0 = tl.row0; }
-    else { col = tl.col0 + ((int)threadIdx.x & 63); row0 = tl.row0 + ((int)threadIdx.x >> 6) * MIX_R; }
-    const int nrow = min(MIX_R, tk.rows - row0);          // may be <= 0 for trailing threads
-    const bool active = col < tk.cols && nrow > 0;
-    T acc[MIX_R];
-#pragma unroll
-    for (int r = 0; r < MIX_R; ++r) acc[r] = mix_zero<T>();
-    for (int t0 = 0; t0 < nt; t0 += MIX_MAXT) {
-      const int cnt = min(MIX_MAXT, nt - t0);
+    // a tile is MIX_G row groups deep, so the descriptor fetches (tile -> task -> terms: a chain of dependent global
+    // loads) are paid once per MIX_G * MIX_R rows
+    int col, rbase, rstep;
+    if (tl.shape == 0) { col = tl.col0 + (int)threadIdx.x; rbase = tl.row0; rstep = MIX_R; }
+    else { col = tl.col0 + ((int)threadIdx.x & 63); rbase = tl.row0 + ((int)threadIdx.x >> 6) * MIX_R; rstep = 4 * MIX_R; }
+    const bool colok = col < tk.cols;
+    if (nt <= MIX_MAXT) {
       __syncthreads();
-      if ((int)threadIdx.x < cnt) sterm[threadIdx.x] = terms[tk.term_begin + t0 + threadIdx.x];
+      if ((int)threadIdx.x < nt) sterm[threadIdx.x] = terms[tk.term_begin + threadIdx.x];
       __syncthreads();
-      if (active) {
-        for (int t = 0; t < cnt; ++t) {
-          const double cre = sterm[t].cre, cim = sterm[t].cim;
-          const int64_t lds = sterm[t].lds;
-          const T* src = (const T*)sterm[t].src + (int64_t)row0 * lds + col;
-          T v[MIX_R];
+      if (colok) {
+        for (int g = 0; g < MIX_G; ++g) {
+          const int row0 = rbase + g * rstep;
+          const int nrow = min(MIX_R, tk.rows - row0);
+          if (nrow <= 0) break;
+          T acc[MIX_R];
 #pragma unroll
-          for (int r = 0; r < MIX_R; ++r) v[r] = r < nrow ? src[(int64_t)r * lds] : mix_zero<T>();
+          for (int r = 0; r < MIX_R; ++r) acc[r] = mix_zero<T>();
+          for (int t = 0; t < nt; ++t) {
+            const double cre = sterm[t].cre, cim = sterm[t].cim;
+            const int64_t lds = sterm[t].lds;
+            const T* src = (const T*)sterm[t].src + (int64_t)row0 * lds + col;
+            T v[MIX_R];
 #pragma unroll
-          for (int r = 0; r < MIX_R; ++r) mix_fma(acc[r], v[r], cre, cim);
+            for (int r = 0; r < MIX_R; ++r) v[r] = r < nrow ? src[(int64_t)r * lds] : mix_zero<T>();
+#pragma unroll
+            for (int r = 0; r < MIX_R; ++r) mix_fma(acc[r], v[r], cre, cim);
+          }
+          T* dst = (T*)tk.dst + (int64_t)row0 * tk.ldd + col;
+#pragma unroll
+          for (int r = 0; r < MIX_R; ++r) if (r < nrow) dst[(int64_t)r * tk.ldd] = acc[r];
         }
       }
-    }
-    if (active) {
-      T* dst = (T*)tk.dst + (int64_t)row0 * tk.ldd + col;
+    } else {
+      // more terms than the shared table holds (split-K reductions with many slices never get here; kept for generality)
+      for (int g = 0; g < MIX_G; ++g) {
+        const int row0 = rbase + g * rstep;
+        const int nrow = min(MIX_R, tk.rows - row0);
+        T acc[MIX_R];
 #pragma unroll
-      for (int r = 0; r < MIX_R; ++r) if (r < nrow) dst[(int64_t)r * tk.ldd] = acc[r];
+        for (int r = 0; r < MIX_R; ++r) acc[r] = mix_zero<T>();
+        for (int t0 = 0; t0 < nt; t0 += MIX_MAXT) {
+          const int cnt = min(MIX_MAXT, nt - t0);
+          __syncthreads();
+          if ((int)threadIdx.x < cnt) sterm[threadIdx.x] = terms[tk.term_begin + t0 + threadIdx.x];
+          __syncthreads();
+          if (colok && nrow > 0)
+            for (int t = 0; t < cnt; ++t) {
+              const T* src = (const T*)sterm[t].src + (int64_t)row0 * sterm[t].lds + col;
+#pragma unroll
+              for (int r = 0; r < MIX_R; ++r) if (r < nrow) mix_fma(acc[r], src[(int64_t)r * sterm[t].lds], sterm[t].cre, sterm[t].cim);
+            }
+        }
+        if (colok && nrow > 0) {
+          T* dst = (T*)tk.dst + (int64_t)row0 * tk.ldd + col;
+#pragma unroll
+          for (int r = 0; r < MIX_R; ++r) if (r < nrow) dst[(int64_t)r * tk.ldd] = acc[r];
+        }
+      }
     }
   }
 }
@@ -619,10 +649,10 @@ int mix_plan_build(Ctx* ctx, bool cplx, const std::vector<MixTask>& tasks, const
     const int rows = tasks[i].rows, cols = tasks[i].cols;
     if (rows <= 0 || cols <= 0) continue;
     if (cols > 96) {
-      for (int r0 = 0; r0 < rows; r0 += MIX_R)
+      for (int r0 = 0; r0 < rows; r0 += MIX_R * MIX_G)
         for (int c0 = 0; c0 < cols; c0 += 256) tiles.push_back(MixTile{(int)i, r0, c0, 0});
     } else {
-      for (int r0 = 0; r0 < rows; r0 += 4 * MIX_R)
+      for (int r0 = 0; r0 < rows; r0 += 4 * MIX_R * MIX_G)
         for (int c0 = 0; c0 < cols; c0 += 64) tiles.push_back(MixTile{(int)i, r0, c0, 1});
     }
     plan->bytes += es * (double)rows * cols * (1 + tasks[i].term_end - tasks[i].term_begin);

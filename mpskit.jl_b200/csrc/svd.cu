@@ -5,6 +5,8 @@
 #include "internal.h"
 #include <cusolverDn.h>
 #include <cmath>
+#include <chrono>
+#include <cstdlib>
 #include <atomic>
 #include <condition_variable>
 #include <functional>
@@ -237,8 +239,28 @@ int tsvd(Ctx* ctx, const Tensor* x, int d1, const int32_t* p1ch, mpsk_trunc trun
   std::vector<Coupled*> secs;
   for (auto& kv : cs) if (kv.second.m > 0 && kv.second.n > 0) secs.push_back(&kv.second);
   const int ns = (int)secs.size();
-  struct Cleanup { Ctx* ctx; std::vector<Coupled*>* s; ~Cleanup() { for (Coupled* c : *s) { ctx->free(c->W); ctx->free(c->U); ctx->free(c->VT); ctx->free(c->S); } } } cleanup{ctx, &secs};
-  const int64_t fast_min = (ctx->flags & MPSK_FLAG_EXACT_SVD) ? (int64_t)1 << 60 : ((ctx->flags & MPSK_FLAG_FAST_SVD_ALL) ? 2 : 256);
+  // every scratch buffer of this call comes out of ONE allocation (bump arena): a centre update at D = 4096 needs ~150
+  // buffers whose sizes change from site to site, which defeats the caching allocator (cudaMalloc dominated the first
+  // profile of this function)
+  struct Arena {
+    Ctx* ctx; char* base = nullptr; size_t off = 0;
+    void* take(size_t bytes) { off = (off + 255) & ~(size_t)255; void* p = base ? base + off : (void*)(uintptr_t)(off + 256); off += std::max<size_t>(bytes, 16); return p; }
+    ~Arena() { if (base) ctx->free(base); }
+  } arena{ctx};
+  // gesvd only for tiny sectors: cuSOLVER's QR-iteration SVD is latency-bound (tens of ms already at 200 x 200), the
+  // multi-level Gram route is as accurate and an order of magnitude faster from ~32 columns on
+  const int64_t fast_min = (ctx->flags & MPSK_FLAG_EXACT_SVD) ? (int64_t)1 << 60 : ((ctx->flags & MPSK_FLAG_FAST_SVD_ALL) ? 2 : 32);
+  if (ctx->profile < 0) ctx->profile = getenv("MPSK_PROFILE") ? 1 : 0;
+  auto tnow = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double tp0 = ctx->profile ? tnow() : 0.0;
+  double tp_prev = tp0;
+  auto lap = [&](const char* what, int a = 0, int b = 0) {
+    if (!ctx->profile) return;
+    cudaStreamSynchronize(ctx->stream);
+    const double t = tnow();
+    fprintf(stderr, "[mpsk profile] tsvd %-14s %8.2f ms  (%d, %d)\n", what, (t - tp_prev) * 1e3, a, b);
+    tp_prev = t;
+  };
   // ---- ownership: sectors are distributed over the ranks (LPT on m n^2), deterministic on every rank
   const bool dist = ctx->nranks > 1 && !(ctx->flags & MPSK_FLAG_REPLICATE_LOCAL);
   std::vector<int> owner(ns, 0);
@@ -254,8 +276,7 @@ int tsvd(Ctx* ctx, const Tensor* x, int d1, const int32_t* p1ch, mpsk_trunc trun
       owner[i] = best; load[best] += cost(i);
     }
   }
-  // ---- assemble the column-major matrices of the sectors this rank factorises
-  std::vector<CopyTask> tasks;
+  // ---- sizes, ownership, scratch layout
   int64_t ktot = 0; std::vector<int64_t> koff(ns);
   for (int si = 0; si < ns; ++si) {
     Coupled* c = secs[si];
@@ -263,13 +284,69 @@ int tsvd(Ctx* ctx, const Tensor* x, int d1, const int32_t* p1ch, mpsk_trunc trun
     c->mm = (int)(c->flip ? c->n : c->m); c->nn = (int)(c->flip ? c->m : c->n);
     c->mine = !dist || owner[si] == ctx->rank;
     c->fast = c->k >= fast_min;
+    c->ldw = pad(c->mm); c->ldu = pad(c->mm); c->ldvt = pad(c->k);
     koff[si] = ktot; ktot += c->k;
+  }
+  cusolverDnHandle_t h0;
+  MPSK_TRY(get_cusolver(ctx, &h0));
+  struct SlowScratch { void* work = nullptr; double* rwork = nullptr; int lwork = 0; };
+  std::vector<SlowScratch> ss(ns); std::vector<GramState> gs(ns);
+  void* dummy = ctx->alloc(256);           // the size queries only want a valid device pointer
+  if (!dummy) return MPSK_ENOMEM;
+  struct DummyFree { Ctx* c; void* p; ~DummyFree() { c->free(p); } } dummy_free{ctx, dummy};
+  for (int si = 0; si < ns; ++si) {        // cuSOLVER workspace sizes (host-side queries, no device work)
+    Coupled* c = secs[si];
     if (!c->mine) continue;
-    const int64_t mm = c->mm, nn = c->nn;
-    c->ldw = pad(mm); c->ldu = pad(mm); c->ldvt = pad(c->k);
-    c->W = ctx->alloc(c->ldw * nn * es); c->U = ctx->alloc(c->ldu * c->k * es); c->VT = ctx->alloc(c->ldvt * nn * es);
-    c->S = (double*)ctx->alloc(c->k * sizeof(double));
-    if (!c->W || !c->U || !c->VT || !c->S) return MPSK_ENOMEM;
+    const int mm = c->mm, nn = c->nn;
+    if (!c->fast) {
+      if (cx) CUSOLVER_TRY(ctx, cusolverDnZgesvd_bufferSize(h0, mm, nn, &ss[si].lwork));
+      else CUSOLVER_TRY(ctx, cusolverDnDgesvd_bufferSize(h0, mm, nn, &ss[si].lwork));
+      continue;
+    }
+    GramState& g = gs[si];
+    g.ldm = pad(mm); g.ldn = pad(nn);
+    int l1 = 0, l2 = 0, l3 = 0;
+    if (cx) { CUSOLVER_TRY(ctx, cusolverDnZheevd_bufferSize(h0, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, nn, (cuDoubleComplex*)dummy, (int)g.ldn, (double*)dummy, &l1));
+              CUSOLVER_TRY(ctx, cusolverDnZgeqrf_bufferSize(h0, mm, nn, (cuDoubleComplex*)dummy, (int)c->ldu, &l2));
+              CUSOLVER_TRY(ctx, cusolverDnZungqr_bufferSize(h0, mm, nn, nn, (cuDoubleComplex*)dummy, (int)c->ldu, (cuDoubleComplex*)dummy, &l3)); }
+    else { CUSOLVER_TRY(ctx, cusolverDnDsyevd_bufferSize(h0, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, nn, (double*)dummy, (int)g.ldn, (double*)dummy, &l1));
+           CUSOLVER_TRY(ctx, cusolverDnDgeqrf_bufferSize(h0, mm, nn, (double*)dummy, (int)c->ldu, &l2));
+           CUSOLVER_TRY(ctx, cusolverDnDorgqr_bufferSize(h0, mm, nn, nn, (double*)dummy, (int)c->ldu, (double*)dummy, &l3)); }
+    g.lwork = std::max(l1, 1); g.lwork2 = std::max(std::max(l2, l3), 1);
+  }
+  auto layout = [&]() {                    // assigns every buffer from the arena (first call only counts bytes)
+    arena.off = 0;
+    for (int si = 0; si < ns; ++si) {
+      Coupled* c = secs[si];
+      if (!c->mine) continue;
+      const size_t mm = c->mm, nn = c->nn;
+      c->W = arena.take(c->ldw * nn * es); c->U = arena.take(c->ldu * c->k * es); c->VT = arena.take(c->ldvt * nn * es);
+      c->S = (double*)arena.take(c->k * sizeof(double));
+      if (!c->fast) {
+        ss[si].work = arena.take((size_t)std::max(ss[si].lwork, 1) * es);
+        ss[si].rwork = (double*)arena.take(sizeof(double) * std::max<size_t>(nn, 1) * 5);
+        continue;
+      }
+      GramState& g = gs[si];
+      g.Mconj = arena.take(g.ldm * nn * es); g.Mrow = arena.take(mm * g.ldn * es); g.G = arena.take(g.ldn * nn * es);
+      g.buf[0] = arena.take(g.ldm * nn * es); g.buf[1] = arena.take(g.ldm * nn * es);
+      g.rbuf[0] = arena.take(g.ldn * nn * es); g.rbuf[1] = arena.take(g.ldn * nn * es); g.Rrow = arena.take(nn * g.ldn * es);
+      g.lam = (double*)arena.take(sizeof(double) * nn); g.tau = arena.take(nn * es); g.ph = (double*)arena.take(nn * es);
+      g.Rtmp = arena.take(nn * nn * es);
+      g.work = arena.take((size_t)g.lwork * es); g.work2 = arena.take((size_t)g.lwork2 * es);
+      g.M = c->W; g.R = nullptr; g.nl = (int)nn; g.outpos = 0;
+    }
+  };
+  layout();
+  arena.base = (char*)ctx->alloc(arena.off + 512);
+  if (!arena.base) return MPSK_ENOMEM;
+  layout();
+  // ---- assemble the column-major matrices of the sectors this rank factorises
+  std::vector<CopyTask> tasks;
+  for (int si = 0; si < ns; ++si) {
+    Coupled* c = secs[si];
+    if (!c->mine) continue;
+    const int64_t nn = c->nn;
     CUDA_TRY(ctx, cudaMemsetAsync(c->W, 0, c->ldw * nn * es, ctx->stream));
     for (size_t ri = 0; ri < c->rows.size(); ++ri) for (size_t ci = 0; ci < c->cols.size(); ++ci) {
       const int jl = c->rows[ri].first, u = c->rows[ri].second, jr = c->cols[ci].first, t = c->cols[ci].second;
@@ -285,49 +362,12 @@ int tsvd(Ctx* ctx, const Tensor* x, int d1, const int32_t* p1ch, mpsk_trunc trun
   MPSK_TRY(run_copy_tasks(ctx, tasks, cx));
   WorkerPool* pool = nullptr;
   MPSK_TRY(pool_get(ctx, &pool));
-  cusolverDnHandle_t h0;
-  MPSK_TRY(get_cusolver(ctx, &h0));
   std::vector<std::vector<double>> sv(ns);
   // work lists (largest first)
   std::vector<int> slow, fastl;
   for (int si = 0; si < ns; ++si) if (secs[si]->mine) (secs[si]->fast ? fastl : slow).push_back(si);
   auto bysize = [&](int a, int b) { return (double)secs[a]->mm * secs[a]->nn > (double)secs[b]->mm * secs[b]->nn; };
   std::sort(slow.begin(), slow.end(), bysize); std::sort(fastl.begin(), fastl.end(), bysize);
-  // scratch
-  struct SlowScratch { void* work = nullptr; double* rwork = nullptr; int lwork = 0; };
-  std::vector<SlowScratch> ss(ns); std::vector<GramState> gs(ns);
-  struct ScCleanup { Ctx* c; std::vector<SlowScratch>* a; std::vector<GramState>* g;
-    ~ScCleanup() { for (auto& x : *a) { c->free(x.work); c->free(x.rwork); }
-                   for (auto& x : *g) { c->free(x.Mconj); c->free(x.Mrow); c->free(x.Rrow); c->free(x.G); c->free(x.buf[0]); c->free(x.buf[1]); c->free(x.rbuf[0]); c->free(x.rbuf[1]);
-                                        c->free(x.lam); c->free(x.work); c->free(x.tau); c->free(x.ph); c->free(x.Rtmp); c->free(x.work2); } } } scc{ctx, &ss, &gs};
-  for (int si : slow) {
-    Coupled* c = secs[si]; SlowScratch& x = ss[si];
-    if (cx) CUSOLVER_TRY(ctx, cusolverDnZgesvd_bufferSize(h0, c->mm, c->nn, &x.lwork));
-    else CUSOLVER_TRY(ctx, cusolverDnDgesvd_bufferSize(h0, c->mm, c->nn, &x.lwork));
-    x.work = ctx->alloc((size_t)std::max(x.lwork, 1) * es);
-    x.rwork = (double*)ctx->alloc(sizeof(double) * std::max(c->nn, 1) * 5);
-    if (!x.work || !x.rwork) return MPSK_ENOMEM;
-  }
-  for (int si : fastl) {
-    Coupled* c = secs[si]; GramState& g = gs[si];
-    const int64_t mm = c->mm, nn = c->nn;
-    g.ldm = pad(mm); g.ldn = pad(nn); g.M = c->W; g.R = nullptr; g.nl = (int)nn; g.outpos = 0;
-    g.Mconj = ctx->alloc(g.ldm * nn * es); g.Mrow = ctx->alloc(mm * g.ldn * es); g.G = ctx->alloc(g.ldn * nn * es);
-    g.buf[0] = ctx->alloc(g.ldm * nn * es); g.rbuf[0] = ctx->alloc(g.ldn * nn * es);
-    g.lam = (double*)ctx->alloc(sizeof(double) * nn); g.tau = ctx->alloc((size_t)nn * es); g.ph = (double*)ctx->alloc((size_t)nn * es);
-    g.Rtmp = ctx->alloc((size_t)nn * nn * es);
-    if (!g.Mconj || !g.Mrow || !g.G || !g.buf[0] || !g.rbuf[0] || !g.lam || !g.tau || !g.ph || !g.Rtmp) return MPSK_ENOMEM;
-    int l1 = 0, l2 = 0, l3 = 0;
-    if (cx) { CUSOLVER_TRY(ctx, cusolverDnZheevd_bufferSize(h0, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)nn, (cuDoubleComplex*)g.G, (int)g.ldn, g.lam, &l1));
-              CUSOLVER_TRY(ctx, cusolverDnZgeqrf_bufferSize(h0, (int)mm, (int)nn, (cuDoubleComplex*)c->U, (int)c->ldu, &l2));
-              CUSOLVER_TRY(ctx, cusolverDnZungqr_bufferSize(h0, (int)mm, (int)nn, (int)nn, (cuDoubleComplex*)c->U, (int)c->ldu, (cuDoubleComplex*)g.tau, &l3)); }
-    else { CUSOLVER_TRY(ctx, cusolverDnDsyevd_bufferSize(h0, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)nn, (double*)g.G, (int)g.ldn, g.lam, &l1));
-           CUSOLVER_TRY(ctx, cusolverDnDgeqrf_bufferSize(h0, (int)mm, (int)nn, (double*)c->U, (int)c->ldu, &l2));
-           CUSOLVER_TRY(ctx, cusolverDnDorgqr_bufferSize(h0, (int)mm, (int)nn, (int)nn, (double*)c->U, (int)c->ldu, (double*)g.tau, &l3)); }
-    g.lwork = std::max(l1, 1); g.lwork2 = std::max(std::max(l2, l3), 1);
-    g.work = ctx->alloc((size_t)g.lwork * es); g.work2 = ctx->alloc((size_t)g.lwork2 * es);
-    if (!g.work || !g.work2) return MPSK_ENOMEM;
-  }
   std::vector<int> status(POOL_THREADS, 0);
   std::vector<std::string> errs(POOL_THREADS);
   // generic pool phase: `fn(si, stream, handle, d_info)` enqueues the factorisation of sector si and returns its status
@@ -360,6 +400,7 @@ int tsvd(Ctx* ctx, const Tensor* x, int d1, const int32_t* p1ch, mpsk_trunc trun
     return MPSK_OK;
   };
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));     // W is assembled: hand the sectors to the pool streams
+  lap("assemble", ns, (int)fastl.size());
   // ---- small sectors: gesvd
   MPSK_TRY(run_phase(slow, "gesvd",
     [&](int si, cudaStream_t, cusolverDnHandle_t hs, int* d_info) {
@@ -371,8 +412,13 @@ int tsvd(Ctx* ctx, const Tensor* x, int d1, const int32_t* p1ch, mpsk_trunc trun
     },
     [&](int si, cudaStream_t st) { sv[si].resize(secs[si]->k); cudaMemcpyAsync(sv[si].data(), secs[si]->S, sizeof(double) * secs[si]->k, cudaMemcpyDeviceToHost, st); }));
   ctx->launches += (int64_t)slow.size();
+  lap("gesvd", (int)slow.size(), slow.empty() ? 0 : secs[slow[0]]->nn);
   // ---- large sectors: multi-level Gram route
-  constexpr int MAXLEV = 6;
+  // Two levels (MAXLEV = 1) already bound the ABSOLUTE error of every singular value by ~1e-11 sigma_max: level 1 works on
+  // columns of norm <= 1e-3 sigma_max, so even a value lost in its rounding noise is off by at most sqrt(eps) * 1e-3 sigma_max.
+  // That is what the parity targets need (spectra / truncation errors to 1e-8) and what the sweeps use.
+  // MPSK_FLAG_SVD_RELATIVE continues down to the rounding floor (up to 6 levels) for full relative accuracy.
+  const int MAXLEV = (ctx->flags & MPSK_FLAG_SVD_RELATIVE) ? 6 : 1;
   constexpr double SPLIT = 1e-3;       // singular values within this factor of the level's largest are emitted
   std::vector<int> active = fastl;
   for (int lev = 0; lev < MAXLEV + 1 && !active.empty(); ++lev) {
@@ -384,7 +430,6 @@ int tsvd(Ctx* ctx, const Tensor* x, int d1, const int32_t* p1ch, mpsk_trunc trun
       ct.push_back(CopyTask{g.M, g.Mconj, 1, g.ldm, 1, g.ldm, mm, nl, cx ? 1 : 0, 0, nullptr});      // conj(M), same layout
       ct.push_back(CopyTask{g.M, g.Mrow, 1, g.ldm, ldr, 1, mm, nl, 0, 0, nullptr});                  // M row-major
       if (g.R) {
-        if (!g.Rrow) { g.Rrow = ctx->alloc((size_t)c->nn * g.ldn * es); if (!g.Rrow) return MPSK_ENOMEM; }
         ct.push_back(CopyTask{g.R, g.Rrow, 1, g.ldn, ldr, 1, c->nn, nl, 0, 0, nullptr});
       }
       // G (column-major, ld pad(nl)) = row-major buffer C[i][j] = sum_k M[k,i] conj(M[k,j])
@@ -397,6 +442,7 @@ int tsvd(Ctx* ctx, const Tensor* x, int d1, const int32_t* p1ch, mpsk_trunc trun
       MPSK_TRY(gemm_plan_run(ctx, &p1));
       CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     }
+    lap("gram", lev, gs[active[0]].nl);
     MPSK_TRY(run_phase(active, "heevd",
       [&](int si, cudaStream_t, cusolverDnHandle_t hs, int* d_info) {
         GramState& g = gs[si]; const int nl = g.nl; const int ldg = (int)pad(nl);
@@ -405,6 +451,7 @@ int tsvd(Ctx* ctx, const Tensor* x, int d1, const int32_t* p1ch, mpsk_trunc trun
       },
       [&](int si, cudaStream_t st) { GramState& g = gs[si]; g.hlam.resize(g.nl); cudaMemcpyAsync(g.hlam.data(), g.lam, sizeof(double) * g.nl, cudaMemcpyDeviceToHost, st); }));
     ctx->launches += (int64_t)active.size();
+    lap("heevd", lev, (int)active.size());
     // split decisions (host): emit everything within SPLIT of the level's largest singular value; at the rounding floor
     // of the original matrix (or at the last level) emit everything
     std::vector<GemmProblemHost> g2;
@@ -422,12 +469,10 @@ int tsvd(Ctx* ctx, const Tensor* x, int d1, const int32_t* p1ch, mpsk_trunc trun
       g.split = t;
       const int64_t ldr = pad(nl);
       void* Bn = g.buf[lev & 1];
-      if (!Bn) { Bn = g.buf[lev & 1] = ctx->alloc(g.ldm * (size_t)nl * es); if (!Bn) return MPSK_ENOMEM; }
       // Bn (column-major mm x nl, ld ldm) = row-major C[j][k] = sum_i Vt[j][i] Mrow[k][i]
       g2.push_back(GemmProblemHost{g.G, g.Mrow, Bn, ldr, ldr, g.ldm, nl, c->mm, nl, 0});
       if (g.R) {
         void* Rn = g.rbuf[lev & 1];
-        if (!Rn) { Rn = g.rbuf[lev & 1] = ctx->alloc(g.ldn * (size_t)nl * es); if (!Rn) return MPSK_ENOMEM; }
         g2.push_back(GemmProblemHost{g.G, g.Rrow, Rn, ldr, ldr, g.ldn, nl, c->nn, nl, 0});
       }
     }
@@ -462,6 +507,7 @@ int tsvd(Ctx* ctx, const Tensor* x, int d1, const int32_t* p1ch, mpsk_trunc trun
     }
     CUDA_TRY(ctx, cudaGetLastError());
     active.swap(next_active);
+    lap("project+emit", lev, (int)active.size());
   }
   if (!fastl.empty()) {
     for (int si : fastl) { sv[si].resize(secs[si]->k); CUDA_TRY(ctx, cudaMemcpyAsync(sv[si].data(), secs[si]->S, sizeof(double) * secs[si]->k, cudaMemcpyDeviceToHost, ctx->stream)); }
@@ -487,6 +533,7 @@ int tsvd(Ctx* ctx, const Tensor* x, int d1, const int32_t* p1ch, mpsk_trunc trun
         return cs_;
       }, nullptr));
     ctx->launches += 4 * (int64_t)fastl.size();
+    lap("qr clean-up", (int)fastl.size(), 0);
   }
   // ---- singular values of all sectors on every rank
   if (dist) {
@@ -582,6 +629,8 @@ int tsvd(Ctx* ctx, const Tensor* x, int d1, const int32_t* p1ch, mpsk_trunc trun
     MPSK_TRY(comm_allreduce_sum(ctx, Vt->d, (size_t)Vt->nelem * dpe));
   }
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // the pool streams may reuse this memory next
+  lap("outputs", 0, 0);
+  if (ctx->profile) fprintf(stderr, "[mpsk profile] tsvd total %.2f ms\n", (tnow() - tp0) * 1e3);
   *Uo = ug.release(); *So = sg.release(); *Vo = vg.release();
   return MPSK_OK;
 }

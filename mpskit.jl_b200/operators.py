@@ -163,6 +163,64 @@ def heisenberg_longrange_u1(L, r=6, d=2, power=2.0):
     return _fsm(L, odim, ent, ch, pch)
 
 
+def cylinder_bonds(W, Lx, J1=1.0, J2=0.5):
+    """bond list {(i, j): J}, i < j, of the J1-J2 Heisenberg model on a width-W cylinder (periodic around, open along),
+    snake order n = x W + y (BASELINE.json config 5)."""
+    bonds = {}
+    for x in range(Lx):
+        for y in range(W):
+            n = x * W + y
+            nbrs = []
+            if W > 2 or y == 0:
+                nbrs.append((x * W + (y + 1) % W, J1))
+            if x + 1 < Lx:
+                nbrs.append(((x + 1) * W + y, J1))
+                nbrs += [((x + 1) * W + (y + dy) % W, J2) for dy in ((1, -1) if W > 2 else (1,))]
+            for o, J in nbrs:
+                if o != n:
+                    key = (min(n, o), max(n, o))
+                    bonds[key] = bonds.get(key, 0.0) + J
+    return bonds
+
+
+def heisenberg_bonds_u1(L, bonds, d=2):
+    """sum_{(i,j)} J_ij S_i.S_j as a U(1) finite-state-machine MPO with three delay lines of length R = max |i - j|
+    (level 1 + t R + k: operator t in {S+, S-, Sz} applied k + 1 sites ago); levels exist only while a bond waits for them.
+    Host-side model construction (the reference builds such MPOs in MPSKitModels)."""
+    Sp, Sm, Sz, pch = spin_ops(d)
+    R = max(j - i for (i, j) in bonds)
+    odim, first, last, qs = 2 + 3 * R, [Sp, Sm, Sz], [0.5 * Sm, 0.5 * Sp, Sz], [2, -2, 0]
+    end = odim - 1
+    ch = [0] + [qs[t] for t in range(3) for _ in range(R)] + [0]
+    starts = {i for (i, j) in bonds}
+    waiting = [set() for _ in range(L + 1)]            # waiting[n]: sites i < n whose operator is still needed at some j >= n
+    for (i, j) in bonds:
+        for n in range(i + 1, j + 1):
+            waiting[n].add(i)
+    out = []
+    for n in range(L):
+        Os = [[0] * odim for _ in range(odim)]
+        Os[0][0] = 1.0; Os[end][end] = 1.0
+        for t in range(3):
+            if n in starts:
+                Os[0][1 + t * R] = first[t]
+            for i in waiting[n]:
+                k = n - i - 1
+                lev = 1 + t * R + k
+                J = bonds.get((i, n), 0.0)
+                if J != 0.0:
+                    Os[lev][end] = J * last[t]
+                if i in waiting[n + 1]:
+                    Os[lev][lev + 1] = 1.0
+        out.append(SparseMPOSlice(Os, ch, ch, pch))
+    return MPOHamiltonian(out)
+
+
+def j1j2_cylinder_u1(W=6, Lx=16, J1=1.0, J2=0.5):
+    """config 5: J1-J2 Heisenberg on a width-W cylinder of length Lx, snake MPO with chi = 2 + 3 (2 W - 1) (35 for W = 6)."""
+    return heisenberg_bonds_u1(W * Lx, cylinder_bonds(W, Lx, J1, J2))
+
+
 def drop_symmetry(H: MPOHamiltonian):
     """same operator with all charges set to zero (trivial-symmetry / dense path)."""
     return MPOHamiltonian([SparseMPOSlice(s.Os, (0,) * s.odim, (0,) * s.odim, (0,) * s.d) for s in H.slices])

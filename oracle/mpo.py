@@ -163,6 +163,85 @@ def heisenberg_longrange_u1(L, r=6, d=2, power=2.0):
     return fsm_hamiltonian(L, odim, ent, ch, pch)
 
 
+def cylinder_bonds(W, Lx, J1=1.0, J2=0.5):
+    """{(i, j): J} with i < j for the J1-J2 Heisenberg model on a cylinder of circumference W (periodic) and length Lx
+    (open), snake order n = x * W + y (BASELINE.json config 5: W = 6, Lx = 16, J2 = 0.5).  J1: nearest neighbours
+    (around the ring and along the cylinder), J2: the two diagonals of every plaquette."""
+    bonds = {}
+
+    def add(a, b, J):
+        i, j = (a, b) if a < b else (b, a)
+        if i != j:
+            bonds[(i, j)] = bonds.get((i, j), 0.0) + J
+    for x in range(Lx):
+        for y in range(W):
+            n = x * W + y
+            if W > 2 or y == 0:
+                add(n, x * W + (y + 1) % W, J1)                       # around the ring
+            if x + 1 < Lx:
+                add(n, (x + 1) * W + y, J1)                           # along the cylinder
+                for dy in ((1, -1) if W > 2 else (1,)):
+                    add(n, (x + 1) * W + (y + dy) % W, J2)            # plaquette diagonals
+    return bonds
+
+
+def heisenberg_bonds_u1(L, bonds, d=2):
+    """U(1) FSM MPO of sum_{(i,j)} J_ij S_i . S_j for an arbitrary bond list on a chain of L sites: three delay lines
+    (S+, S-, Sz) of length R = max |i - j|; level (t, k) = "operator t was applied k + 1 sites ago".  Site-dependent
+    slices, chi = 2 + 3 R (snake MPO of a width-6 cylinder: R = 11, chi = 35)."""
+    Sp, Sm, Sz, pch = spin_ops(d)
+    R = max(j - i for (i, j) in bonds)
+    odim = 2 + 3 * R
+    end = odim - 1
+    first, last, qs = [Sp, Sm, Sz], [0.5 * Sm, 0.5 * Sp, Sz], [2, -2, 0]
+    ch = [0] * odim
+    for t in range(3):
+        for k in range(R):
+            ch[1 + t * R + k] = qs[t]
+    # a delay-line level is only needed while some bond still waits for it: (t, k) at the left of site n exists iff a
+    # bond (n - k - 1, j) with j >= n is present
+    def pending(n, k):
+        i = n - k - 1
+        return i >= 0 and any((i, j) in bonds for j in range(n, min(L, i + R + 1)))
+    slices = []
+    for n in range(L):
+        Os = [[0 for _ in range(odim)] for _ in range(odim)]
+        Os[0][0] = 1.0; Os[end][end] = 1.0
+        for t in range(3):
+            if any((n, j) in bonds for j in range(n + 1, min(L, n + R + 1))):
+                Os[0][1 + t * R] = first[t]
+            for k in range(R):
+                lev = 1 + t * R + k
+                if not pending(n, k):
+                    continue
+                J = bonds.get((n - k - 1, n), 0.0)
+                if J != 0.0:
+                    Os[lev][end] = J * last[t]
+                if k + 1 < R and pending(n + 1, k + 1):
+                    Os[lev][lev + 1] = 1.0
+        slices.append(SparseMPOSlice(Os, ch, ch, pch))
+    return MPOHamiltonian(slices)
+
+
+def j1j2_cylinder_u1(W=6, Lx=16, J1=1.0, J2=0.5):
+    """BASELINE.json config 5: J1-J2 Heisenberg on a width-W cylinder as a snake MPO (U(1), chi = 2 + 3 (2 W - 1))."""
+    return heisenberg_bonds_u1(W * Lx, cylinder_bonds(W, Lx, J1, J2))
+
+
+def bonds_dense_hamiltonian(L, bonds, d=2):
+    """sum_{(i,j)} J_ij S_i . S_j built directly from Kronecker products (independent of the MPO construction)"""
+    Sp, Sm, Sz, _ = spin_ops(d)
+    def site(op, i):
+        out = np.eye(1)
+        for k in range(L):
+            out = np.kron(out, op if k == i else np.eye(d))
+        return out
+    H = np.zeros((d ** L, d ** L))
+    for (i, j), J in bonds.items():
+        H += J * (0.5 * (site(Sp, i) @ site(Sm, j) + site(Sm, i) @ site(Sp, j)) + site(Sz, i) @ site(Sz, j))
+    return H
+
+
 def heisenberg_dense(L, d=2, J=1.0):
     """same operator without symmetry (all charges zero): the dense/trivial path."""
     H = heisenberg_u1(L, d, J)
