@@ -9,7 +9,7 @@ from .tensor import DeviceTensor, block_table  # noqa: F401
 from .operators import (SparseMPOSlice, MPOHamiltonian, transverse_field_ising, heisenberg_u1,  # noqa: F401
                         heisenberg_longrange_u1, drop_symmetry, DenseMPO, dense_mpo_slice, classical_ising,
                         periodic_boundary_conditions, transverse_field_ising_z2, cylinder_bonds, heisenberg_bonds_u1,
-                        j1j2_cylinder_u1)
+                        j1j2_cylinder_u1, mpo_product)
 from . import operators  # noqa: F401
 from .derivatives import (MPO_ddC, MPO_ddAC, MPO_ddAC2, ddC, ddAC, ddAC2, LazySumOp, MultipliedOp,  # noqa: F401
                           LinearCombinationOp)
@@ -18,7 +18,7 @@ from .fixedpoint import fixedpoint, integrate, linsolve, Lanczos, Arnoldi  # noq
 from .finitemps import FiniteMPS, virtual_spaces, qrpos, lqpos  # noqa: F401
 from .environments import FinEnv, environments  # noqa: F401
 from .dmrg import (DMRG2, find_groundstate_inplace, expectation_value, tsvd, contract_ac2,  # noqa: F401
-                   truncdim, truncerr, truncbelow, notrunc, tsvd_spectrum)
+                   truncdim, truncerr, truncbelow, notrunc, tsvd_spectrum, variance)
 from .algorithms import (DMRG, TDVP, TDVP2, find_groundstate, find_groundstate_dmrg_inplace, calc_galerkin,  # noqa: F401
                          timestep, timestep_inplace)
 from .sharding import panel_bounds, panel_table, panel_space, row_panel, scatter_panel, apply_local, init_communicator  # noqa: F401

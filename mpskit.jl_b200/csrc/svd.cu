@@ -83,18 +83,34 @@ __global__ void q_phase_kernel(double* __restrict__ Q, int64_t ldq, int m, int k
 
 // Gram route: emit the `head` singular triplets of one level.  lam ascending eigenvalues of M^H M (nl of them), the head
 // is the index range [t, nl); Bn = M V and Rn = R V column-major.  Output position of eigen-index i: outpos + (nl-1-i)
-// (descending singular values): S = sqrt(lam), U[:, o] = Bn[:, i] / S, VT[o, :] = conj(Rn[:, i])^T.
+// (descending).  The singular value is the NORM OF THE COLUMN b_i = M v_i (gram_colnorm_kernel), i.e. the Rayleigh
+// quotient of the exact Gram matrix: its error is second order in the eigenvector error, whereas sqrt(lam_i) carries the
+// first-order rounding error eps * lam_top of the explicitly formed Gram matrix.  U[:, o] = b_i / |b_i|,
+// VT[o, :] = conj(Rn[:, i])^T, so U S V^H reproduces M to rounding before the final re-orthonormalisation.
+template <bool CPLX>
+__global__ void __launch_bounds__(256) gram_colnorm_kernel(const double* __restrict__ Bn, int64_t ldb, int mm, int t, int nl, int outpos,
+                                                            double* __restrict__ S) {
+  const int jj = blockIdx.x, i = nl - 1 - jj;
+  if (i < t) return;
+  const double* col = Bn + (CPLX ? 2 : 1) * (int64_t)i * ldb;
+  double acc = 0.0;
+  for (int r = threadIdx.x; r < (CPLX ? 2 : 1) * mm; r += blockDim.x) { const double v = col[r]; acc += v * v; }
+  __shared__ double sm[256];
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o]; __syncthreads(); }
+  if (threadIdx.x == 0) S[outpos + jj] = sqrt(sm[0]);
+}
+
 template <bool CPLX>
 __global__ void gram_emit_kernel(const double* __restrict__ Bn, int64_t ldb, const double* __restrict__ Rn, int64_t ldr,
-                                 const double* __restrict__ lam, int mm, int nn, int t, int nl, int outpos,
-                                 double* __restrict__ U, int64_t ldu, double* __restrict__ VT, int64_t ldvt, double* __restrict__ S) {
+                                 int mm, int nn, int t, int nl, int outpos,
+                                 double* __restrict__ U, int64_t ldu, double* __restrict__ VT, int64_t ldvt, const double* __restrict__ S) {
   const int hc = nl - t;
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = tid; e < (int64_t)mm * hc; e += nth) {
     const int r = (int)(e % mm), jj = (int)(e / mm), i = nl - 1 - jj, o = outpos + jj;
-    const double l = lam[i];
-    const double sg = l > 0 ? sqrt(l) : 0.0, inv = sg > 0 ? 1.0 / sg : 0.0;
-    if (r == 0) S[o] = sg;
+    const double sg = S[o], inv = sg > 0 ? 1.0 / sg : 0.0;
     if (CPLX) { U[2 * (r + (int64_t)o * ldu)] = Bn[2 * (r + (int64_t)i * ldb)] * inv; U[2 * (r + (int64_t)o * ldu) + 1] = Bn[2 * (r + (int64_t)i * ldb) + 1] * inv; }
     else U[r + (int64_t)o * ldu] = Bn[r + (int64_t)i * ldb] * inv;
   }
@@ -198,7 +214,7 @@ struct GramState {
 //   * small sectors (min dim < 256): cuSOLVER gesvd (LAPACK-class, what the reference calls);
 //   * large sectors: a multi-level ("deflated") Gram route built from our grouped DMMA GEMM + cuSOLVER heevd:
 //       level l:  G = M^H M,  G = V L V^H,  B = M V,  R <- R V;   singular values within 1e-3 of the level's largest are
-//       emitted (sigma = sqrt(L), u = b / sigma, v = r): their relative error is eps * (sigma_top/sigma)^2 <= 1e-10.  The
+//       emitted (sigma = |b| = norm of the column of B, u = b / sigma, v = r): relative error <= eps * (sigma_top/sigma)^2 <= 1e-10.  The
 //       remaining columns of B (norms <= 1e-3 of the level scale, orthogonal to the emitted ones to rounding) form the
 //       matrix of the next level, so every level restores three decades of relative accuracy; at most 6 levels reach the
 //       rounding floor eps * sigma_max, where gesvd's own absolute accuracy ends.  A final Householder QR with positive
@@ -489,10 +505,15 @@ int tsvd(Ctx* ctx, const Tensor* x, int d1, const int32_t* p1ch, mpsk_trunc trun
       const int64_t ldrn = g.R ? g.ldn : ldr;
       const int64_t work_items = (int64_t)c->mm * (nl - t);
       const int grid = (int)std::min<int64_t>((work_items + 255) / 256 + 1, 8192);
-      if (cx) gram_emit_kernel<true><<<grid, 256, 0, ctx->stream>>>((const double*)Bn, g.ldm, (const double*)Rn, ldrn, g.lam, c->mm, c->nn, t, nl, g.outpos,
-                                                                      (double*)c->U, c->ldu, (double*)c->VT, c->ldvt, c->S);
-      else gram_emit_kernel<false><<<grid, 256, 0, ctx->stream>>>((const double*)Bn, g.ldm, (const double*)Rn, ldrn, g.lam, c->mm, c->nn, t, nl, g.outpos,
-                                                                   (double*)c->U, c->ldu, (double*)c->VT, c->ldvt, c->S);
+      if (nl - t > 0) {
+        if (cx) gram_colnorm_kernel<true><<<nl - t, 256, 0, ctx->stream>>>((const double*)Bn, g.ldm, c->mm, t, nl, g.outpos, c->S);
+        else gram_colnorm_kernel<false><<<nl - t, 256, 0, ctx->stream>>>((const double*)Bn, g.ldm, c->mm, t, nl, g.outpos, c->S);
+        if (cx) gram_emit_kernel<true><<<grid, 256, 0, ctx->stream>>>((const double*)Bn, g.ldm, (const double*)Rn, ldrn, c->mm, c->nn, t, nl, g.outpos,
+                                                                        (double*)c->U, c->ldu, (double*)c->VT, c->ldvt, c->S);
+        else gram_emit_kernel<false><<<grid, 256, 0, ctx->stream>>>((const double*)Bn, g.ldm, (const double*)Rn, ldrn, c->mm, c->nn, t, nl, g.outpos,
+                                                                     (double*)c->U, c->ldu, (double*)c->VT, c->ldvt, c->S);
+        ctx->launches++;
+      }
       ctx->launches++;
       g.outpos += nl - t;
       if (t > 0) {

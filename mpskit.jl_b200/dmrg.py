@@ -141,3 +141,14 @@ def expectation_value(psi, H, envs):
     e = ac.dot(y) / ac.dot(ac)
     h.free(); y.free()
     return e.real if isinstance(e, complex) else e
+
+
+def variance(psi, H, envs=None):
+    """variance(state::FiniteMPS, H, envs) (src/algorithms/toolbox.jl:141-145): Re(<H * H> - <H>^2) with H * H the product MPO
+    (sparsempo.jl:232-264) and its own finite environments; everything but the host-side operator product runs on the device."""
+    from .operators import mpo_product
+    envs = envs if envs is not None else environments(psi, H)
+    H2 = mpo_product(H, H)
+    e2 = expectation_value(psi, H2, environments(psi, H2))
+    e1 = expectation_value(psi, H, envs)
+    return float(e2 - e1 * e1)

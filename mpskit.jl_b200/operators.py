@@ -221,6 +221,32 @@ def j1j2_cylinder_u1(W=6, Lx=16, J1=1.0, J2=0.5):
     return heisenberg_bonds_u1(W * Lx, cylinder_bonds(W, Lx, J1, J2))
 
 
+def mpo_product(B, A):
+    """B * A for two sparse MPOs with width-1 levels (src/operators/sparsempo/sparsempo.jl:232-264): new level
+    (i, k) -> i + k * odim_A (first index fastest, as LinearIndices), entry [(i,k),(j,l)] = A[i,j] then B[k,l]
+    (operator product B[k,l] @ A[i,j]; two scalars multiply), level charges add.  Used by `variance` (H * H)."""
+    out = []
+    for sa, sb in zip(A.slices, B.slices):
+        oa, ob = sa.odim, sb.odim
+        n = oa * ob
+        Os = [[0 for _ in range(n)] for _ in range(n)]
+        for (i, j) in sa.keys():
+            for (k, l) in sb.keys():
+                if sa.isscal(i, j) and sb.isscal(k, l):
+                    v = sa.Os[i][j] * sb.Os[k][l]
+                else:
+                    ea = sa.Os[i][j] * np.eye(sa.d) if sa.isscal(i, j) else np.asarray(sa.Os[i][j], dtype=np.complex128)
+                    eb = sb.Os[k][l] * np.eye(sb.d) if sb.isscal(k, l) else np.asarray(sb.Os[k][l], dtype=np.complex128)
+                    v = eb @ ea
+                    if np.abs(v).max() == 0:
+                        continue
+                Os[i + k * oa][j + l * oa] = v
+        cl = [sa.domcharges[i] + sb.domcharges[k] for k in range(ob) for i in range(oa)]
+        cr = [sa.imcharges[i] + sb.imcharges[k] for k in range(ob) for i in range(oa)]
+        out.append(SparseMPOSlice(Os, cl, cr, sa.pcharges, sa.modulus))
+    return MPOHamiltonian(out)
+
+
 def drop_symmetry(H: MPOHamiltonian):
     """same operator with all charges set to zero (trivial-symmetry / dense path)."""
     return MPOHamiltonian([SparseMPOSlice(s.Os, (0,) * s.odim, (0,) * s.odim, (0,) * s.d) for s in H.slices])

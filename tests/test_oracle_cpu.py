@@ -307,3 +307,27 @@ def test_idmrg1_oracle_matches_vumps_energy():
     st, envs, eps = oi.idmrg1(psi, H, tol=1e-10, maxiter=200)
     assert eps < 1e-10
     assert abs(oi.expectation_value(st, H, envs).sum().real - (-1.063544409973)) < 1e-10
+
+
+def test_cylinder_snake_mpo_and_mpo_product():
+    """config 5 operator: the J1-J2 cylinder snake MPO (oracle and package build it independently) equals the lattice
+    Hamiltonian assembled from Kronecker products; H * H (sparsempo.jl:232-264, used by `variance`) equals the matrix square."""
+    import mpskit_b200 as m
+    for (W, Lx) in ((3, 3), (2, 4), (4, 2)):
+        L = W * Lx
+        b = ompo.cylinder_bonds(W, Lx)
+        assert b == m.cylinder_bonds(W, Lx)
+        H = ompo.heisenberg_bonds_u1(L, b)
+        assert np.abs(ompo.dense_hamiltonian(H) - ompo.bonds_dense_hamiltonian(L, b)).max() <= 1e-13
+        Hm = m.heisenberg_bonds_u1(L, b)
+        for so, sm in zip(H.slices, Hm.slices):
+            assert so.kinds() == sm.kinds() and tuple(so.cl) == tuple(sm.domcharges)          # bit-exact bookkeeping
+            for (i, j) in so.keys():
+                assert np.array_equal(np.asarray(so.Os[i][j]), np.asarray(sm.Os[i][j]))
+    H6 = ompo.j1j2_cylinder_u1(6, 16)
+    assert H6.odim == 35 and len(H6) == 96 and len(ompo.cylinder_bonds(6, 16)) == 366
+    H = ompo.heisenberg_longrange_u1(5, r=2)
+    d = ompo.dense_hamiltonian(H)
+    assert np.abs(ompo.dense_hamiltonian(ompo.mpo_product(H, H)) - d @ d).max() <= 1e-12
+    Hm = m.heisenberg_longrange_u1(5, r=2)
+    assert all(a.kinds() == b.kinds() for a, b in zip(ompo.mpo_product(H, H).slices, m.mpo_product(Hm, Hm).slices))
