@@ -156,6 +156,12 @@ int32_t mpsk_tmop_create(mpsk_ctx* ctx, int32_t left, int32_t nsites, const mpsk
                          const mpsk_tensor* const* Abar, const mpsk_tensor* v_like, const mpsk_tensor* lvec_adj, const mpsk_tensor* rvec,
                          mpsk_op** out);
 
+/* Multi-row (MPSMultiline) derivatives: (dAC, dAC2, dC)(x::RecursiveVec, ...) = RecursiveVec(circshift(map(...), 1))
+ * (derivatives.jl:107-110,163-166,195-197).  The composite operator acts on ONE tensor whose labels are the rows' labels
+ * stacked (mpsk_tensor_stack_labels / mpsk_tensor_select_labels convert to and from the RecursiveVec): y[(r + shift) mod n] =
+ * ops[r](x[r]).  All rows must share their bond spaces.  `ops` must outlive the handle; freed by mpsk_op_free. */
+int32_t mpsk_multiop_create(mpsk_ctx* ctx, int32_t n, const mpsk_op* const* ops, int32_t shift, mpsk_op** out);
+
 /* ---- transfer matrices / environment updates (src/transfermatrix/transfer.jl:137-259,
  *      src/environments/FinEnv.jl:114-145) --------------------------------------------------------- */
 int32_t mpsk_transfer_left(mpsk_ctx* ctx, const mpsk_mposlice* h, const mpsk_tensor* A, const mpsk_tensor* Abar,

@@ -25,5 +25,6 @@ from .sharding import panel_bounds, panel_table, panel_space, row_panel, scatter
 from .infinite import (InfiniteMPS, TransferMatrix, regularize, MPOHamInfEnv, VUMPS, find_groundstate_vumps,  # noqa: F401
                        uniform_leftorth, uniform_rightorth, regauge, IDMRG1, IDMRGEnv, find_groundstate_idmrg1)
 from . import infinite  # noqa: F401
-from .statmech import PerMPOInfEnv, leading_boundary  # noqa: F401
+from .statmech import (PerMPOInfEnv, leading_boundary, MultilineOp, MultilineEnv, leading_boundary_multiline,  # noqa: F401
+                       expectation_value_multiline, fixedpoint_multiline)
 from . import statmech  # noqa: F401

@@ -90,6 +90,7 @@ PROTOTYPES = {
     "mpsk_linsolve": (C.c_int32, [_P, _P, _P, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_double, _P,
                                   C.POINTER(c_info)]),
     "mpsk_tmop_create": (C.c_int32, [_P, C.c_int32, C.c_int32, _PP, _PP, _PP, _P, _P, _P, _PP]),
+    "mpsk_multiop_create": (C.c_int32, [_P, C.c_int32, _PP, C.c_int32, _PP]),
     "mpsk_transfer_left": (C.c_int32, [_P, _P, _P, _P, _P, _PP]),
     "mpsk_transfer_right": (C.c_int32, [_P, _P, _P, _P, _P, _PP]),
     "mpsk_contract_ac2": (C.c_int32, [_P, _P, _P, _PP]),

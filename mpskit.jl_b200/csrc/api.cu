@@ -49,6 +49,13 @@ int32_t mpsk_create(int32_t device, uint64_t flags, mpsk_ctx** out) {
   c->device = device; c->flags = flags; c->num_sms = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return MPSK_ECUDA; }
   c->stream = c->own_stream;
+  {   // keep freed device memory in the stream-ordered pool (see Ctx::alloc)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t thr = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+  }
   *out = reinterpret_cast<mpsk_ctx*>(c);
   return MPSK_OK;
 }
@@ -67,8 +74,9 @@ void mpsk_destroy(mpsk_ctx* ctx) {
   }
   if (c->d_scratch) c->free(c->d_scratch);
   if (c->h_arena) cudaFreeHost(c->h_arena);
+  for (auto& kv : c->sizes) cudaFreeAsync(kv.first, c->stream);
+  c->sizes.clear();
   c->release_cache();
-  for (auto& kv : c->sizes) cudaFree(kv.first);
   if (c->h_scratch) cudaFreeHost(c->h_scratch);
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -522,6 +530,16 @@ int32_t mpsk_tmop_create(mpsk_ctx* ctx, int32_t left, int32_t nsites, const mpsk
     if (!op->d_coef) return MPSK_ENOMEM;
   }
   *out = reinterpret_cast<mpsk_op*>(static_cast<LinOp*>(op.release()));
+  return MPSK_OK;
+}
+
+// direct sum of operators with a cyclic shift (multi-row derivatives of the statmech VUMPS, derivatives.jl:107-110,163-166,195-197)
+int32_t mpsk_multiop_create(mpsk_ctx* ctx, int32_t n, const mpsk_op* const* ops, int32_t shift, mpsk_op** out) { ENTER(ctx);
+  std::vector<LinOp*> v;
+  for (int i = 0; i < n; ++i) v.push_back(OPH(ops[i]));
+  MultiOp* m = nullptr;
+  MPSK_TRY(multiop_create(CTX(ctx), v, shift, &m));
+  *out = reinterpret_cast<mpsk_op*>(static_cast<LinOp*>(m));
   return MPSK_OK;
 }
 

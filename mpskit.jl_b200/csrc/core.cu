@@ -13,26 +13,24 @@ int Ctx::fail(int code, const char* fmt, ...) {
 
 static size_t round_size(size_t b) {
   if (b < 512) return 512;
-  if (b < (1u << 20)) return (b + 511) / 512 * 512;
-  return (b + (1u << 20) - 1) / (1u << 20) * (1u << 20);
+  return (b + 511) / 512 * 512;
 }
 
+// Device memory comes from CUDA's stream-ordered pool (cudaMallocAsync on the context stream, release threshold = never):
+// the pool splits and coalesces blocks, so the multi-GB workspaces of a sweep (GEMM intermediates, Krylov bases, SVD
+// arenas, environments -- all with sizes that drift from site to site) are recycled without ever going back to
+// cudaMalloc / cudaFree.  (Round 1's exact-size free list missed on drifting sizes, grew, and was trimmed with
+// device-wide cudaFree storms: 0.15 s per centre update.)  Memory is used on the context stream, or on the factorisation
+// pool's streams strictly between synchronisations of the context stream.
 void* Ctx::alloc(size_t bytes) {
-  size_t sz = round_size(bytes);
-  auto it = freelist.lower_bound(sz);
-  if (it != freelist.end() && it->first <= sz + sz / 4 + (1u << 20)) {
-    void* p = it->second; size_t got = it->first;
-    freelist.erase(it);
-    bytes_cached -= got; bytes_in_use += got; sizes[p] = got;
-    return p;
-  }
+  const size_t sz = round_size(bytes);
   void* p = nullptr;
-  cudaError_t e = cudaMalloc(&p, sz);
+  cudaError_t e = cudaMallocAsync(&p, sz, stream);
   if (e != cudaSuccess) {
     cudaGetLastError();
     release_cache();
-    e = cudaMalloc(&p, sz);
-    if (e != cudaSuccess) { cudaGetLastError(); fail(MPSK_ENOMEM, "cudaMalloc(%zu) failed", sz); return nullptr; }
+    e = cudaMallocAsync(&p, sz, stream);
+    if (e != cudaSuccess) { cudaGetLastError(); fail(MPSK_ENOMEM, "cudaMallocAsync(%zu) failed", sz); return nullptr; }
   }
   sizes[p] = sz; bytes_in_use += sz;
   return p;
@@ -42,17 +40,15 @@ void Ctx::free(void* p) {
   if (!p) return;
   auto it = sizes.find(p);
   if (it == sizes.end()) return;
-  size_t sz = it->second;
+  bytes_in_use -= it->second;
   sizes.erase(it);
-  bytes_in_use -= sz; bytes_cached += sz;
-  freelist.emplace(sz, p);
-  if (bytes_cached > (int64_t)48 << 30) release_cache();
+  cudaFreeAsync(p, stream);
 }
 
 void Ctx::release_cache() {
   cudaStreamSynchronize(stream);
-  for (auto& kv : freelist) cudaFree(kv.second);
-  freelist.clear(); bytes_cached = 0;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
 }
 
 // pinned bump arena (see internal.h): memory handed out stays valid until the arena wraps, and wrapping synchronises

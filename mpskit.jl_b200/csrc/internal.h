@@ -45,10 +45,9 @@ struct Ctx {
   int num_sms = 148;
   std::string err;
   int64_t launches = 0;
-  // stream-ordered caching allocator (all work of a context is on one stream)
-  std::multimap<size_t, void*> freelist;
+  // stream-ordered allocator: CUDA's memory pool (cudaMallocAsync / cudaFreeAsync on the context stream)
   std::unordered_map<void*, size_t> sizes;
-  int64_t bytes_in_use = 0, bytes_cached = 0;
+  int64_t bytes_in_use = 0;
   void* cusolver = nullptr;     // cusolverDnHandle_t, created lazily
   void* pool_stream[4] = {nullptr, nullptr, nullptr, nullptr};   // worker streams / cuSOLVER handles of the factorisation pool
   void* pool_solver[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -303,6 +302,21 @@ struct TmOp : LinOp {
   int apply(const Tensor* x, Tensor* y) override;
   double flops() const override { return flops_; }
 };
+
+// ---- direct sum of operators with a cyclic shift: y[(r + shift) mod n] = ops[r](x[r]) -- the multi-row (MPSMultiline)
+// derivatives of the statmech VUMPS (derivatives.jl:107-110,163-166,195-197: RecursiveVec + circshift).  The composite
+// vector is ONE tensor whose labels are the rows' labels stacked (mpsk_tensor_stack_labels), so the Krylov BLAS-1 and
+// every solver work on it unchanged; all rows must share their bond spaces.
+struct MultiOp : LinOp {
+  std::vector<LinOp*> ops;                            // not owned
+  int shift = 1;
+  std::unique_ptr<Tensor> vlike;                      // stacked structure (storage unused)
+  std::vector<std::unique_ptr<Tensor>> xin, yout;     // per-row staging vectors
+  const Tensor* like() const override { return vlike.get(); }
+  int apply(const Tensor* x, Tensor* y) override;
+  double flops() const override { double f = 0; for (auto* o : ops) f += o->flops(); return f; }
+};
+int multiop_create(Ctx* ctx, const std::vector<LinOp*>& ops, int shift, MultiOp** out);
 
 // ---- Krylov solvers (eigsolve.cu)
 int eigsolve_lanczos(Ctx* ctx, LinOp* op, const Tensor* x0, int which, int krylovdim, int maxiter, double tol,

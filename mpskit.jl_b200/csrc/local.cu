@@ -310,6 +310,57 @@ int TmOp::apply(const Tensor* x, Tensor* y) {
   return MPSK_OK;
 }
 
+// ------------------------------------------------------------------------------------------ multi-row operators
+// copy `n` consecutive labels (all their blocks) between two tensors with the same bond spaces; asynchronous
+static int copy_labels(Ctx* ctx, const Tensor* src, int s0, Tensor* dst, int d0, int n) {
+  if (!(src->Vl == dst->Vl) || !(src->Vr == dst->Vr) || src->dtype != dst->dtype) return ctx->fail(MPSK_ESPACE, "copy_labels: bond spaces differ");
+  std::vector<CopyTask> tasks;
+  for (int m = 0; m < n; ++m) {
+    if (src->mch[s0 + m] != dst->mch[d0 + m]) return ctx->fail(MPSK_ESPACE, "copy_labels: label charges differ");
+    for (int jl = 0; jl < src->Vl.nsec(); ++jl) {
+      const Blk* a = src->find(s0 + m, jl); const Blk* b = dst->find(d0 + m, jl);
+      if (!a || !b) continue;
+      tasks.push_back(CopyTask{src->ptr(a->off), dst->ptr(b->off), a->sl, a->sr, b->sl, b->sr, (int32_t)src->Vl.n[a->jl], (int32_t)src->Vr.n[a->jr], 0, 0, nullptr});
+    }
+  }
+  return run_copy_tasks(ctx, tasks, src->dtype == MPSK_C128);
+}
+
+int multiop_create(Ctx* ctx, const std::vector<LinOp*>& ops, int shift, MultiOp** out) {
+  if (ops.empty()) return ctx->fail(MPSK_EINVAL, "multiop: no operators");
+  std::unique_ptr<MultiOp> M(new MultiOp);
+  M->ctx = ctx; M->ops = ops; M->shift = shift; M->dtype = ops[0]->dtype;
+  const Tensor* l0 = ops[0]->like();
+  std::vector<int32_t> mch;
+  for (LinOp* o : ops) {
+    const Tensor* l = o->like();
+    if (o->sharded()) return ctx->fail(MPSK_EINVAL, "multiop: row-panel operators are not supported");
+    if (!(l->Vl == l0->Vl) || !(l->Vr == l0->Vr) || l->dtype != l0->dtype || l->mch != l0->mch)
+      return ctx->fail(MPSK_ESPACE, "multiop: all rows must act on vectors of the same structure");
+    mch.insert(mch.end(), l->mch.begin(), l->mch.end());
+    Tensor* a = nullptr; Tensor* b = nullptr;
+    MPSK_TRY(tensor_create(ctx, l->Vl, l->mch, l->Vr, l->dtype, F_KL, true, &a)); M->xin.emplace_back(a);
+    MPSK_TRY(tensor_create(ctx, l->Vl, l->mch, l->Vr, l->dtype, F_KL, true, &b)); M->yout.emplace_back(b);
+  }
+  Tensor* v = nullptr;
+  MPSK_TRY(tensor_create(ctx, l0->Vl, mch, l0->Vr, l0->dtype, F_KL, true, &v));
+  M->vlike.reset(v);
+  *out = M.release();
+  return MPSK_OK;
+}
+
+int MultiOp::apply(const Tensor* x, Tensor* y) {
+  if (!x->same_structure(*vlike) || !y->same_structure(*vlike)) return ctx->fail(MPSK_ESPACE, "multiop: vector structure mismatch");
+  const int n = (int)ops.size(), nm = ops[0]->like()->nm();
+  for (int r = 0; r < n; ++r) {
+    MPSK_TRY(copy_labels(ctx, x, r * nm, xin[r].get(), 0, nm));
+    MPSK_TRY(ops[r]->apply(xin[r].get(), yout[r].get()));
+    const int tr = ((r + shift) % n + n) % n;
+    MPSK_TRY(copy_labels(ctx, yout[r].get(), 0, y, tr * nm, nm));
+  }
+  return MPSK_OK;
+}
+
 // ac2[l (p1 p2) r] = sum_k A1[l p1 k] A2[k p2 r]     (dmrg.jl:92,108)
 int contract_ac2(Ctx* ctx, const Tensor* A1, const Tensor* A2, Tensor** out) {
   if (A1->dtype != A2->dtype) return ctx->fail(MPSK_EINVAL, "mixed scalar types");

@@ -1,6 +1,7 @@
 """leading_boundary(psi::InfiniteMPS, O::DenseMPO, VUMPS()) on the device: src/algorithms/statmech/vumps.jl:15-84,
 PerMPOInfEnv + mixed_fixpoints (src/environments/permpoinfenv.jl:23-63,138-189), expectation_value
-(src/algorithms/expval.jl:165-173).  Single-row unit cells (an InfiniteMPS with any number of columns); the
+(src/algorithms/expval.jl:165-173).  Single-row unit cells (an InfiniteMPS with any number of columns) and multi-row
+unit cells (MPSMultiline = list of InfiniteMPS rows: the *_multiline functions, RecursiveVec + circshift on the device); the
 non-Hermitian eigenproblems are solved by the library's device-resident Krylov-Schur Arnoldi (mpsk_eigsolve, hermitian = 0)."""
 from __future__ import annotations
 import ctypes as C
@@ -8,6 +9,7 @@ import numpy as np
 from .tensor import DeviceTensor
 from .derivatives import MPO_ddAC, MPO_ddC
 from .fixedpoint import fixedpoint, Arnoldi
+from .krylov import RecursiveVec
 from .infinite import InfiniteMPS, TransferMatrix, regauge, dyn_tol, TOLGAUGE, mul_right, VUMPS
 from .algorithms import _overlap
 
@@ -131,3 +133,158 @@ def leading_boundary(psi: InfiniteMPS, opp, alg: VUMPS = None, envs=None, log=No
         if eps <= alg.tol:
             break
     return psi, envs, eps
+
+
+# ------------------------------------------------------------------------------------------ multi-row unit cells (MPSMultiline)
+class MultilineOp:
+    """MPO_ddAC / MPO_ddC of an MPSMultiline column (derivatives.jl:107-110,195-197): acts on the RecursiveVec of all
+    rows, y[r + 1] = h_r(x[r]).  One device operator (mpsk_multiop_create) on the rows' vectors stacked along the label
+    axis, so the Arnoldi eigensolve runs inside the library."""
+
+    def __init__(self, ops, shift=1):
+        self.ops, self.ctx, self.shift = list(ops), ops[0].ctx, shift
+        arr = (C.c_void_p * len(ops))(*[o.h for o in ops])
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.mpsk_multiop_create(self.ctx.h, len(ops), arr, shift, C.byref(h)))
+        self.h = h
+
+    def __call__(self, x):
+        y = self.stack(x).zerovector()
+        self.ctx.check(self.ctx.lib.mpsk_op_apply(self.ctx.h, self.h, self.stack(x).h, y.h))
+        return self.split(y, x)
+
+    @staticmethod
+    def stack(rv):
+        return DeviceTensor.stack(rv.vecs)
+
+    @staticmethod
+    def split(t, like):
+        nm = len(like.vecs[0].mch)
+        return RecursiveVec([t.select(list(range(r * nm, (r + 1) * nm))) for r in range(len(like.vecs))])
+
+    def free(self):
+        if self.h is not None and self.ctx.h:
+            self.ctx.lib.mpsk_op_free(self.ctx.h, self.h)
+        self.h = None
+        for o in self.ops:
+            o.free()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def fixedpoint_multiline(op: MultilineOp, x0: RecursiveVec, which, alg):
+    """fixedpoint(H::MPO_ddAC over all rows, RecursiveVec(...), which, alg) (statmech/vumps.jl:33-36) on the device"""
+    xs = MultilineOp.stack(x0)
+    val, vec = fixedpoint(op, xs, which, alg)
+    out = MultilineOp.split(vec, x0)
+    for v in out.vecs:
+        v._is_bond = getattr(x0.vecs[0], "_is_bond", False)
+    return val, out
+
+
+class MultilineEnv:
+    """PerMPOInfEnv of an MPSMultiline (permpoinfenv.jl:4-63,138-189): lw[r][c] / rw[r][c] between row r (ket) and row
+    r + 1 (bra); opp[r][c] is the MPO slice of row r, column c.  All rows share their bond spaces."""
+
+    def __init__(self, rows, opp, tol=1e-12):
+        self.opp, self.tol = opp, tol
+        self.lw = self.rw = None
+        self.dependency = None
+        self.recalculate(rows)
+
+    def recalculate(self, rows, tol=None):
+        tol = self.tol if tol is None else tol
+        R, N, ctx = len(rows), rows[0].N, rows[0].ctx
+        alg = Arnoldi(tol=tol, krylovdim=30, maxiter=100, hermitian=False)
+        GLs = [[None] * N for _ in range(R)]
+        GRs = [[None] * N for _ in range(R)]
+        for r in range(R):
+            top, bot = rows[r], rows[(r + 1) % R]
+            Os = [self.opp[r][c] for c in range(N)]
+            lc = [-c for c in Os[0].domcharges]
+            rc = [c for c in Os[N - 1].imcharges]
+            V0 = top.V[0]
+            same = self.lw is not None and self.lw[r][0].Vl == V0
+            L0 = self.lw[r][0] if same else DeviceTensor.random(ctx, V0, lc, V0, 17 + r, top.dtype)
+            R0 = self.rw[r][N - 1] if same else DeviceTensor.random(ctx, V0, rc, V0, 18 + r, top.dtype)
+            TL = TransferMatrix(list(top.AL), Os, list(bot.AL)).flip()
+            TR = TransferMatrix(list(top.AR), Os, list(bot.AR))
+            _, GLs[r][0] = fixedpoint(TL, L0, "LM", alg)
+            for c in range(1, N):
+                GLs[r][c] = TransferMatrix([top.AL[c - 1]], [Os[c - 1]], [bot.AL[c - 1]]).flip()(GLs[r][c - 1])
+            _, GRs[r][N - 1] = fixedpoint(TR, R0, "LM", alg)
+            for c in range(N - 2, -1, -1):
+                GRs[r][c] = TransferMatrix([top.AR[c + 1]], [Os[c + 1]], [bot.AR[c + 1]])(GRs[r][c + 1])
+            for c in range(N):                              # permpoinfenv.jl:180-185 (+ removal of the arbitrary Arnoldi phase)
+                h = MPO_ddC(ctx, GLs[r][(c + 1) % N], GRs[r][c], top.CR[c])
+                lam = complex(bot.CR[c].dot(h(top.CR[c]))); h.free()
+                GLs[r][(c + 1) % N].scale(np.conj(lam) / abs(lam) / np.sqrt(abs(lam)))
+                GRs[r][c].scale(1.0 / np.sqrt(abs(lam)))
+        self.lw, self.rw, self.dependency = GLs, GRs, rows
+        return self
+
+
+def expectation_value_multiline(rows, envs):
+    """expval.jl:165-173: <AC[r + 1, c]| O[r, c] |AC[r, c]> per (row, column)"""
+    R, N = len(rows), rows[0].N
+    out = np.zeros((R, N), dtype=np.complex128)
+    for r in range(R):
+        for c in range(N):
+            h = MPO_ddAC(rows[r].ctx, envs.opp[r][c], envs.lw[r][c], envs.rw[r][c], rows[r].AC[c])
+            y = h(rows[r].AC[c]); h.free()
+            out[r, c] = complex(rows[(r + 1) % R].AC[c].dot(y))
+            y.free()
+    return out
+
+
+def calc_galerkin_multiline(rows, envs):
+    """toolbox.jl:26-38"""
+    R, N = len(rows), rows[0].N
+    eps = 0.0
+    for r in range(R):
+        for c in range(N):
+            h = MPO_ddAC(rows[r].ctx, envs.opp[r][c], envs.lw[r][c], envs.rw[r][c], rows[r].AC[c])
+            ac = h(rows[r].AC[c]); h.free()
+            ac.scale(1.0 / ac.norm())
+            AL = rows[(r + 1) % R].AL[c]
+            ov = _overlap(rows[r], ac, AL)
+            proj = mul_right(AL, ov)
+            ac.axpy(-1.0, proj)
+            eps = max(eps, ac.norm())
+    return eps
+
+
+def leading_boundary_multiline(rows, opp, alg: VUMPS = None, envs=None, log=None):
+    """leading_boundary(psi::MPSMultiline, H::MPOMultiline, alg::VUMPS, envs) (statmech/vumps.jl:20-84).  rows: list of
+    InfiniteMPS (one per row, same bond spaces); opp[r][c]: MPO slices.  Every column update is ONE Arnoldi eigensolve on
+    the RecursiveVec of all rows inside the library."""
+    alg = alg or VUMPS(tol=1e-10)
+    envs = envs or MultilineEnv(rows, opp)
+    R, N, ctx = len(rows), rows[0].N, rows[0].ctx
+    eps = calc_galerkin_multiline(rows, envs)
+    for it in range(1, alg.maxiter + 1):
+        etol = dyn_tol(eps, it, 1e-12, 1e-5, 1e-5)
+        eig = Arnoldi(tol=etol, krylovdim=30, maxiter=100, hermitian=False)
+        newAL = [[None] * N for _ in range(R)]
+        for col in range(N):
+            hac = MultilineOp([MPO_ddAC(ctx, opp[r][col], envs.lw[r][col], envs.rw[r][col], rows[r].AC[col]) for r in range(R)])
+            _, ac = fixedpoint_multiline(hac, RecursiveVec([rows[r].AC[col] for r in range(R)]), "LM", eig); hac.free()
+            hc = MultilineOp([MPO_ddC(ctx, envs.lw[r][(col + 1) % N], envs.rw[r][col], rows[r].CR[col]) for r in range(R)])
+            _, c = fixedpoint_multiline(hc, RecursiveVec([rows[r].CR[col] for r in range(R)]), "LM", eig); hc.free()
+            for r in range(R):
+                newAL[r][col] = regauge(ac.vecs[r], c.vecs[r])
+        gtol = dyn_tol(eps, it, TOLGAUGE, 1e-5, 1e-8)
+        rows = [InfiniteMPS.from_AL(newAL[r], rows[r].CR[N - 1], rows[r].V, rows[r].pspace, ctx, gtol, 100) for r in range(R)]
+        envs.recalculate(rows, dyn_tol(eps, it, 1e-12, 1e-5, 1e-5))
+        if alg.finalize is not None:
+            rows, envs = alg.finalize(it, rows, opp, envs)
+        eps = calc_galerkin_multiline(rows, envs)
+        if log is not None:
+            log.append(dict(iter=it, eps=eps, value=expectation_value_multiline(rows, envs)))
+        if eps <= alg.tol:
+            break
+    return rows, envs, eps

@@ -1,7 +1,8 @@
 """Statistical-mechanics VUMPS for a single-row unit cell (leading_boundary of an InfiniteMPS with a DenseMPO):
 src/algorithms/statmech/vumps.jl:15-84, src/environments/permpoinfenv.jl:23-63,138-189 (mixed_fixpoints),
 src/algorithms/expval.jl:165-173.  Dense restatement; the MPO is given as a list of flattened slices (oracle/mpo.py
-dense_mpo_slice).  Multi-row unit cells (MPSMultiline with more than one row) are not covered."""
+dense_mpo_slice).  Multi-row unit cells (MPSMultiline: RecursiveVec + circshift, derivatives.jl:107-110,195-197;
+mixed_fixpoints row by row, permpoinfenv.jl:138-189) are restated in the *_multiline functions at the end."""
 from __future__ import annotations
 import numpy as np
 from .infinite import InfiniteMPS, regauge, dyn_tol, TOLGAUGE
@@ -101,3 +102,106 @@ def leading_boundary(psi: InfiniteMPS, slices, tol=1e-10, maxiter=100, log=None)
         if eps <= tol:
             break
     return psi, envs, eps
+
+
+# ------------------------------------------------------------------------------------------ multi-row unit cells
+class MultilineEnv:
+    """PerMPOInfEnv for an MPSMultiline (permpoinfenv.jl:4-63,138-189): lw[r][c] / rw[r][c] between row r (top, ket)
+    and row r + 1 (bottom, bra); slices[r][c] is the MPO tensor of row r, column c."""
+
+    def __init__(self, rows, slices, tol=1e-12):
+        self.opp, self.tol = slices, tol
+        self.lw = self.rw = None
+        self.dependency = None
+        self.recalculate(rows)
+
+    def recalculate(self, rows, tol=None):
+        tol = self.tol if tol is None else tol
+        R, N = len(rows), rows[0].N
+        GLs = [[None] * N for _ in range(R)]
+        GRs = [[None] * N for _ in range(R)]
+        rng = np.random.default_rng(0)
+        for r in range(R):
+            top, bot = rows[r], rows[(r + 1) % R]
+            Os = self.opp[r]
+            chi = Os[0].odim
+            D0 = top.AL[0].shape[0]
+            same = self.lw is not None and self.lw[r][0].shape[0] == D0
+            L0 = self.lw[r][0] if same else rng.standard_normal((D0, chi, D0)) + 0j
+            R0 = self.rw[r][N - 1] if same else rng.standard_normal((D0, chi, D0)) + 0j
+
+            def TL(v):
+                for i in range(N):
+                    v = transfer_left_sparse(v, Os[i], top.AL[i], bot.AL[i])
+                return v
+
+            def TR(v):
+                for i in range(N - 1, -1, -1):
+                    v = transfer_right_sparse(v, Os[i], top.AR[i], bot.AR[i])
+                return v
+            _, GLs[r][0], _ = eigsolve_arnoldi(TL, L0, "LM", tol, 30, 100)
+            for c in range(1, N):
+                GLs[r][c] = transfer_left_sparse(GLs[r][c - 1], Os[c - 1], top.AL[c - 1], bot.AL[c - 1])
+            _, GRs[r][N - 1], _ = eigsolve_arnoldi(TR, R0, "LM", tol, 30, 100)
+            for c in range(N - 2, -1, -1):
+                GRs[r][c] = transfer_right_sparse(GRs[r][c + 1], Os[c + 1], top.AR[c + 1], bot.AR[c + 1])
+            for c in range(N):                      # permpoinfenv.jl:180-185 (+ removal of the arbitrary Arnoldi phase)
+                lam = np.vdot(bot.CR[c], dC_dense(top.CR[c], GLs[r][(c + 1) % N], GRs[r][c]))
+                GLs[r][(c + 1) % N] = GLs[r][(c + 1) % N] * (np.conj(lam) / abs(lam)) / np.sqrt(abs(lam))
+                GRs[r][c] = GRs[r][c] / np.sqrt(abs(lam))
+        self.lw, self.rw, self.dependency = GLs, GRs, rows
+        return self
+
+
+def expectation_value_multiline(rows, envs):
+    """expval.jl:165-173: <AC[r+1, c]| O[r, c] |AC[r, c]> with the environments, per (row, column)"""
+    R, N = len(rows), rows[0].N
+    out = np.zeros((R, N), dtype=np.complex128)
+    for r in range(R):
+        for c in range(N):
+            y = dAC_sparse(rows[r].AC[c], envs.opp[r][c], envs.lw[r][c], envs.rw[r][c])
+            out[r, c] = np.vdot(rows[(r + 1) % R].AC[c], y)
+    return out
+
+
+def calc_galerkin_multiline(rows, envs):
+    """toolbox.jl:26-38"""
+    R, N = len(rows), rows[0].N
+    eps = 0.0
+    for r in range(R):
+        for c in range(N):
+            y = dAC_sparse(rows[r].AC[c], envs.opp[r][c], envs.lw[r][c], envs.rw[r][c])
+            y = y / np.linalg.norm(y)
+            AL = rows[(r + 1) % R].AL[c]
+            eps = max(eps, float(np.linalg.norm(y - np.einsum('apb,cqb,cqd->apd', AL, np.conj(AL), y, optimize=True))))
+    return eps
+
+
+def leading_boundary_multiline(rows, slices, tol=1e-10, maxiter=100, log=None):
+    """leading_boundary(psi::MPSMultiline, H::MPOMultiline, VUMPS()) (statmech/vumps.jl:20-84): every column update is ONE
+    eigenproblem on the RecursiveVec of all rows, (dAC x)[r + 1] = dAC(x[r], O[r, col], GL[r, col], GR[r, col])."""
+    envs = MultilineEnv(rows, slices)
+    R, N = len(rows), rows[0].N
+    eps = calc_galerkin_multiline(rows, envs)
+    for it in range(1, maxiter + 1):
+        etol = dyn_tol(eps, it, 1e-12, 1e-5, 1e-5)
+        newAL = [[None] * N for _ in range(R)]
+        for col in range(N):
+            def HAC(x):
+                return np.stack([dAC_sparse(x[(r - 1) % R], slices[(r - 1) % R][col], envs.lw[(r - 1) % R][col], envs.rw[(r - 1) % R][col]) for r in range(R)])
+
+            def HC(x):
+                return np.stack([dC_dense(x[(r - 1) % R], envs.lw[(r - 1) % R][(col + 1) % N], envs.rw[(r - 1) % R][col]) for r in range(R)])
+            _, ac, _ = eigsolve_arnoldi(HAC, np.stack([rows[r].AC[col] for r in range(R)]), "LM", etol, 30, 100)
+            _, c, _ = eigsolve_arnoldi(HC, np.stack([rows[r].CR[col] for r in range(R)]), "LM", etol, 30, 100)
+            for r in range(R):
+                newAL[r][col] = regauge(ac[r], c[r], rows[r].V[col], rows[r].V[(col + 1) % N], rows[r].pq, rows[r].modulus)
+        gtol = dyn_tol(eps, it, TOLGAUGE, 1e-5, 1e-8)
+        rows = [InfiniteMPS.from_AL(newAL[r], rows[r].CR[N - 1], rows[r].V, rows[r].pq, gtol, 100, rows[r].modulus) for r in range(R)]
+        envs.recalculate(rows, dyn_tol(eps, it, 1e-12, 1e-5, 1e-5))
+        eps = calc_galerkin_multiline(rows, envs)
+        if log is not None:
+            log.append(dict(iter=it, eps=eps, value=expectation_value_multiline(rows, envs)))
+        if eps <= tol:
+            break
+    return rows, envs, eps
