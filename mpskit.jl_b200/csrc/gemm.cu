@@ -1,5 +1,6 @@
 #include "gemm.cuh"
 #include "internal.h"
+#include <cstdlib>
 
 namespace mpsk {
 
@@ -58,15 +59,15 @@ struct LoadCursor {
   }
 };
 
-template <bool CPLX, int WARPS_N>
-__global__ void __launch_bounds__(GemmCfg<CPLX, WARPS_N>::NTHREADS, GemmCfg<CPLX, WARPS_N>::CTAS_PER_SM)
+template <bool CPLX, int WARPS_N, int WN_ = 32>
+__global__ void __launch_bounds__(GemmCfg<CPLX, WARPS_N, WN_>::NTHREADS, GemmCfg<CPLX, WARPS_N, WN_>::CTAS_PER_SM)
 gemm_dmma_kernel(const GemmProblemDev* __restrict__ probs, const GemmTile* __restrict__ tiles, int ntiles) {
-  using Cfg = GemmCfg<CPLX, WARPS_N>;
+  using Cfg = GemmCfg<CPLX, WARPS_N, WN_>;
   constexpr int BM = Cfg::BM, BN = Cfg::BN, KSUB = Cfg::KSUB, NSUB = Cfg::NSUB, STAGES = Cfg::STAGES;
   constexpr int KSTAGE = KSUB * NSUB;                       // elements of K per stage
   constexpr int A_SUB_BYTES = BM * 64, B_SUB_BYTES = BN * 64;
   constexpr int STAGE_BYTES = NSUB * (A_SUB_BYTES + B_SUB_BYTES);
-  constexpr int WM = CPLX ? 32 : 64, WN = 32;               // warp tile
+  constexpr int WM = CPLX ? 32 : 64, WN = Cfg::WN;          // warp tile
   constexpr int MI = WM / 8, NI = WN / 8;
   constexpr int WARPS_M = Cfg::WARPS_M;                     // 4 (cplx) / 2 (real)
   constexpr int NWARPS = Cfg::WARPS_M * Cfg::WARPS_N;
@@ -279,8 +280,8 @@ static bool encode_map(CUtensorMap* tm, const void* base, int64_t rows, int64_t 
   return r == CUDA_SUCCESS;
 }
 
-template <bool CPLX, int WN> static int smem_bytes() {
-  using Cfg = GemmCfg<CPLX, WN>;
+template <bool CPLX, int WARPS_N, int WN = 32> static int smem_bytes() {
+  using Cfg = GemmCfg<CPLX, WARPS_N, WN>;
   return Cfg::STAGES * Cfg::NSUB * (Cfg::BM + Cfg::BN) * 64 + 2 * Cfg::STAGES * 8 + 128;
 }
 
@@ -303,15 +304,17 @@ int gemm_plan_build(Ctx* ctx, bool cplx, const std::vector<GemmProblemHost>& pro
   const size_t esz = cplx ? 16 : 8;
   // ---- tile configuration: narrow (128 x 32, complex only) when it cuts the quantised tile work by > 7 %
   int BN = cplx ? 32 * GEMM_WIDE_N_CPLX : 32 * GEMM_WIDE_N_REAL;
-  plan->narrow = false;
+  plan->narrow = false; plan->narrow16 = false;
   if (cplx && !(ctx->flags & MPSK_FLAG_DEBUG_GEMM)) {
-    double wide = 0, nar = 0;
+    double wide = 0, nar = 0, nar16 = 0;
     for (const GemmProblemHost& h : probs_in) {
       if (h.M <= 0 || h.N <= 0) continue;
       const double mt = (double)((h.M + BM - 1) / BM) * BM * h.K;
-      wide += mt * ((h.N + 63) / 64) * 64; nar += mt * ((h.N + 31) / 32) * 32;
+      wide += mt * ((h.N + 63) / 64) * 64; nar += mt * ((h.N + 31) / 32) * 32; nar16 += mt * ((h.N + 15) / 16) * 16;
     }
     if (nar < 0.93 * wide) { plan->narrow = true; BN = 32 * GEMM_NARROW_N_CPLX; }
+    // 16-wide tiles cost ~1.5x the shared-memory operand traffic per DMMA: only when they remove > 6 % of the padded work
+    if (plan->narrow && nar16 < 0.94 * nar && !getenv("MPSK_NO_NARROW16")) { plan->narrow16 = true; BN = 16; }
   }
   // ---- split-K decision
   int64_t base_tiles = 0; int64_t maxK = 0;
@@ -321,7 +324,7 @@ int gemm_plan_build(Ctx* ctx, bool cplx, const std::vector<GemmProblemHost>& pro
     maxK = std::max<int64_t>(maxK, h.K);
     plan->flops += (cplx ? 8.0 : 2.0) * (double)h.M * h.N * h.K;
   }
-  const int64_t want_tiles = 4LL * ctx->num_sms * (plan->narrow ? 2 : 1);
+  const int64_t want_tiles = 4LL * ctx->num_sms * (plan->narrow16 ? 3 : (plan->narrow ? 2 : 1));
   int S = 1;
   if (base_tiles > 0 && base_tiles < want_tiles && maxK >= 512 && !(ctx->flags & MPSK_FLAG_DEBUG_GEMM))
     S = (int)std::min<int64_t>(8, (want_tiles + base_tiles - 1) / base_tiles);
@@ -422,7 +425,12 @@ int gemm_plan_run(Ctx* ctx, const GemmPlan* plan) {
     else gemm_debug_kernel<false><<<grid, 256, 0, ctx->stream>>>(plan->d_probs, plan->nprob);
   } else {
     bool* attr_set = ctx->gemm_attr_set;
-    if (plan->cplx && plan->narrow) {
+    if (plan->cplx && plan->narrow16) {
+      using Cfg = GemmCfg<true, 1, 16>;
+      const int grid = std::min(plan->ntiles, ctx->num_sms * Cfg::CTAS_PER_SM);
+      if (!attr_set[3]) { CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_dmma_kernel<true, 1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<true, 1, 16>())); attr_set[3] = true; }
+      gemm_dmma_kernel<true, 1, 16><<<grid, Cfg::NTHREADS, smem_bytes<true, 1, 16>(), ctx->stream>>>(plan->d_probs, plan->d_tiles, plan->ntiles);
+    } else if (plan->cplx && plan->narrow) {
       using Cfg = GemmCfg<true, GEMM_NARROW_N_CPLX>;
       const int grid = std::min(plan->ntiles, ctx->num_sms * Cfg::CTAS_PER_SM);
       if (!attr_set[2]) { CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_dmma_kernel<true, GEMM_NARROW_N_CPLX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<true, GEMM_NARROW_N_CPLX>())); attr_set[2] = true; }

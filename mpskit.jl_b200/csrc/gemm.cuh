@@ -30,18 +30,21 @@ struct GemmProblemHost {
   int64_t lda, ldb, ldc; int32_t M, N, K; int32_t accumulate;
 };
 
-// Tile configurations.  Warp tile: 32 x 32 (complex) / 64 x 32 (real); CTA tile = BM x (32 * WARPS_N).
-//   wide   : 8 warps, 128 x 64 complex / 128 x 128 real, 1 CTA per SM, 4 / 3 pipeline stages
-//   narrow : 4 warps, 128 x 32 complex, 2 CTAs per SM, 2 stages -- for plans dominated by narrow-N problems (the row
-//            panels of a sharded matvec), where 64-wide tiles would waste up to 40 % of the DMMA work
-template <bool CPLX, int WARPS_N_> struct GemmCfg {
+// Tile configurations.  Warp tile: 32 x WN (complex) / 64 x WN (real); CTA tile = BM x (WN * WARPS_N).
+//   wide     : 8 warps, 128 x 64 complex / 128 x 128 real, 1 CTA per SM, 4 / 3 pipeline stages
+//   narrow   : 4 warps, 128 x 32 complex, 2 CTAs per SM, 2 stages -- for plans dominated by narrow-N problems (the row
+//              panels of a sharded matvec), where 64-wide tiles would waste up to 40 % of the DMMA work
+//   narrow16 : 4 warps, 128 x 16 complex (warp tile 32 x 16), 3 CTAs per SM -- row panels whose width is far from a
+//              multiple of 32 (136 rows per sector at 8 GPUs: 144 instead of 160 padded columns)
+template <bool CPLX, int WARPS_N_, int WN_ = 32> struct GemmCfg {
   static constexpr int WARPS_M = CPLX ? 4 : 2;
   static constexpr int WARPS_N = WARPS_N_;
-  static constexpr int BM = 128, BN = 32 * WARPS_N_;
+  static constexpr int WN = WN_;
+  static constexpr int BM = 128, BN = WN_ * WARPS_N_;
   static constexpr int KSUB = CPLX ? 4 : 8, NSUB = 4;
   static constexpr int NTHREADS = 32 * WARPS_M * WARPS_N;
-  static constexpr int CTAS_PER_SM = NTHREADS <= 128 ? 2 : 1;
-  static constexpr int STAGES = CTAS_PER_SM == 2 ? 2 : (CPLX ? 4 : 3);
+  static constexpr int CTAS_PER_SM = NTHREADS <= 128 ? (WN_ <= 16 ? 3 : 2) : 1;
+  static constexpr int STAGES = CTAS_PER_SM >= 2 ? 2 : (CPLX ? 4 : 3);
 };
 constexpr int GEMM_WIDE_N_CPLX = 2, GEMM_NARROW_N_CPLX = 1, GEMM_WIDE_N_REAL = 4;
 

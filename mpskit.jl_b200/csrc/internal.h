@@ -186,6 +186,7 @@ struct GemmPlan {
   GemmProblemDev* d_probs = nullptr; GemmTile* d_tiles = nullptr;
   int nprob = 0, ntiles = 0; double flops = 0;
   bool narrow = false;      // 128 x 32 tile configuration (complex, narrow-N plans)
+  bool narrow16 = false;    // 128 x 16 tile configuration (row panels far from a multiple of 32)
   int splitk = 1; void* partials = nullptr; MixPlan* reduce = nullptr;    // split-K partial products + their reduction pass
   ~GemmPlan();
 };

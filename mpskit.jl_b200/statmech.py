@@ -149,8 +149,9 @@ class MultilineOp:
         self.h = h
 
     def __call__(self, x):
-        y = self.stack(x).zerovector()
-        self.ctx.check(self.ctx.lib.mpsk_op_apply(self.ctx.h, self.h, self.stack(x).h, y.h))
+        xs = self.stack(x)                # keep the stacked tensor alive across the call
+        y = xs.zerovector()
+        self.ctx.check(self.ctx.lib.mpsk_op_apply(self.ctx.h, self.h, xs.h, y.h))
         return self.split(y, x)
 
     @staticmethod
