@@ -448,6 +448,7 @@ def sweep_window(ctx, m, args, world, allmax):
     names = ("ac2", "env_op", "eigsolve", "tsvd", "update")
     phases = {k: 0.0 for k in names}
     times, matvecs, conv, energies, flops_mv = [], 0, 0, [], 0.0
+    sub = {}
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         for step in range(nsteps + 1):      # one untimed update absorbs cuSOLVER / allocator warm-up
@@ -455,7 +456,11 @@ def sweep_window(ctx, m, args, world, allmax):
             ctx.synchronize(); t0 = time.perf_counter()
             ac2 = dm.contract_ac2(psi, psi.AC[pos], psi.AR[pos + 1])
             ctx.synchronize(); t1 = time.perf_counter()
-            h = m.ddAC2(pos, psi, H, envs, ac2)
+            gl = envs.leftenv(pos, psi)                      # environment update (sharded transfer + allgather)
+            ctx.synchronize(); t1a = time.perf_counter()
+            gr = envs.rightenv(pos + 1, psi)                 # stored right environment: panels -> full (allgather)
+            ctx.synchronize(); t1b = time.perf_counter()
+            h = m.MPO_ddAC2(ctx, envs.opp[pos], envs.opp[pos + 1], gl, gr, ac2)      # = ddAC2(pos, psi, H, envs) (derivatives.jl:55-58)
             ctx.synchronize(); t2 = time.perf_counter()
             val, new, info = m.fixedpoint(h, ac2, "SR", alg, return_info=True)
             ctx.synchronize(); t3 = time.perf_counter()
@@ -471,12 +476,15 @@ def sweep_window(ctx, m, args, world, allmax):
                 flops_mv += fl * info["numops"]
                 for k, dt in zip(names, (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4)):
                     phases[k] += dt
+                for k, dt in zip(("leftenv_update", "rightenv_activate", "operator_create"), (t1a - t1, t1b - t1a, t2 - t1b)):
+                    sub[k] = sub.get(k, 0.0) + dt
     per = allmax(float(np.mean(times)))
     n = len(times)
     eig = allmax(phases["eigsolve"] / n)
     return {"seconds_per_centre_update": per, "matvecs_per_update": matvecs / n, "converged_updates": conv, "timed_updates": n,
             "krylovdim": args.sweep_krylovdim, "tol": 1e-10, "maxiter": args.sweep_maxiter,
             "phase_seconds_per_update": {k: v / n for k, v in phases.items()},
+            "env_op_breakdown": {k: v / n for k, v in sub.items()}, "normres_last": info["normres"],
             "non_eigsolve_share": 1.0 - eig / per, "energies": energies,
             "eigsolve_tflops": flops_mv * world / max(phases["eigsolve"], 1e-30) / 1e12 if world > 1 else flops_mv / max(phases["eigsolve"], 1e-30) / 1e12,
             "estimated_sweep_seconds_L100": per * 150 + 0.06 * per * 47,

@@ -6,6 +6,8 @@
 // which is the optimal-order contraction whose flop count SURVEY.md 8d defines as the algorithmic work.
 // The reference evaluates the same sum entry by entry (derivatives.jl:125-151); results agree to rounding.
 #include "internal.h"
+#include <chrono>
+#include <cstdlib>
 
 namespace mpsk {
 
@@ -73,6 +75,10 @@ static int build_W(Ctx* ctx, int kind, const MpoSlice* h1, const MpoSlice* h2, c
 int heff_create(Ctx* ctx, int kind, const MpoSlice* h1, const MpoSlice* h2, const Tensor* GL, const Tensor* GR,
                 const Tensor* x_like, HeffOp** out) {
   if (!GL || !GR || !x_like) return ctx->fail(MPSK_EINVAL, "null argument");
+  if (ctx->profile < 0) ctx->profile = getenv("MPSK_PROFILE") ? 1 : 0;
+  auto wall = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double tp0 = 0, tp1 = 0, tp2 = 0;
+  if (ctx->profile) { cudaStreamSynchronize(ctx->stream); tp0 = wall(); }
   if (GL->dtype != x_like->dtype || GR->dtype != x_like->dtype) return ctx->fail(MPSK_EINVAL, "mixed scalar types");
   if (!(GL->Vr == x_like->Vl)) return ctx->fail(MPSK_ESPACE, "left environment does not match the left bond of x");
   for (int j = 0; j < GL->Vl.nsec(); ++j) {     // bra space: the left bond of x or a row panel of it (multi-GPU sharding)
@@ -104,6 +110,7 @@ int heff_create(Ctx* ctx, int kind, const MpoSlice* h1, const MpoSlice* h2, cons
   { Tensor* t = nullptr; MPSK_TRY(tensor_repack(ctx, GL, F_KR, false, &t)); op->GLk.reset(t); }
   { Tensor* t = nullptr; MPSK_TRY(tensor_repack(ctx, GR, F_SL, false, &t)); op->GRs.reset(t); }
   { Tensor* t = nullptr; MPSK_TRY(tensor_create(ctx, x_like->Vl, x_like->mch, x_like->Vr, x_like->dtype, F_KL, true, &t)); op->xs.reset(t); }
+  if (ctx->profile) { cudaStreamSynchronize(ctx->stream); tp1 = wall(); }
   const Tensor& xs = *op->xs; const Tensor& GLk = *op->GLk; const Tensor& GRs = *op->GRs;
   Tensor* ybuf = nullptr;
   MPSK_TRY(tensor_create(ctx, Vb, x_like->mch, x_like->Vr, x_like->dtype, F_KL, true, &ybuf));
@@ -182,11 +189,13 @@ int heff_create(Ctx* ctx, int kind, const MpoSlice* h1, const MpoSlice* h2, cons
                                  (int32_t)Vb.n[ja], (int32_t)gz.cols, 0});
     op->flops_ += kappa * (double)gz.rows * Vb.n[ja] * klog;
   }
+  if (ctx->profile) { cudaStreamSynchronize(ctx->stream); tp2 = wall(); }
   op->gemmA.reset(new GemmPlan); op->gemmC.reset(new GemmPlan); op->mix.reset(new MixPlan);
   MPSK_TRY(gemm_plan_build(ctx, cx, pa, op->gemmA.get()));
   MPSK_TRY(mix_plan_build(ctx, cx, tasks, terms, op->mix.get()));
   MPSK_TRY(gemm_plan_build(ctx, cx, pc, op->gemmC.get()));
   op->ybuf.reset(ys.release());
+  if (ctx->profile) { cudaStreamSynchronize(ctx->stream); fprintf(stderr, "[mpsk profile] heff_create: repack %.2f ms, workspaces+problem lists %.2f ms, plans %.2f ms\n", (tp1 - tp0) * 1e3, (tp2 - tp1) * 1e3, (wall() - tp2) * 1e3); }
   *out = op.release();
   return MPSK_OK;
 }

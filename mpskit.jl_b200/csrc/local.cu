@@ -1,6 +1,8 @@
 // Environment updates (transfer.jl:137-259 through FinEnv.jl:114-145) and the local tensor algebra of the
 // sweep bodies (dmrg.jl:92,108; orthoview.jl:95-106), all expressed as grouped NT GEMMs + one mix pass.
 #include "internal.h"
+#include <chrono>
+#include <cstdlib>
 
 namespace mpsk {
 
@@ -269,11 +271,18 @@ int transfer_plan_run(Ctx* ctx, TransferPlan* P, const Tensor* v) {
   return MPSK_OK;
 }
 
+static double wall_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 static int transfer_once(Ctx* ctx, bool left, const MpoSlice* h, const Tensor* A, const Tensor* Abar, const Tensor* v, Tensor** out) {
+  if (ctx->profile < 0) ctx->profile = getenv("MPSK_PROFILE") ? 1 : 0;
+  double t0 = 0, t1 = 0;
+  if (ctx->profile) { cudaStreamSynchronize(ctx->stream); t0 = wall_s(); }
   TransferPlan* P = nullptr;
   MPSK_TRY(transfer_plan_create(ctx, left, h, A, Abar, v, /*sharded=*/!(ctx->flags & MPSK_FLAG_REPLICATE_LOCAL), &P));
   std::unique_ptr<TransferPlan> pg(P);
+  if (ctx->profile) { cudaStreamSynchronize(ctx->stream); t1 = wall_s(); }
   MPSK_TRY(transfer_plan_run(ctx, P, v));
+  if (ctx->profile) { cudaStreamSynchronize(ctx->stream); fprintf(stderr, "[mpsk profile] transfer_%s: plan %.2f ms, run %.2f ms (sharded %d)\n", left ? "left" : "right", (t1 - t0) * 1e3, (wall_s() - t1) * 1e3, (int)P->sharded); }
   // hand the result tensor over to the caller (the plan and its workspaces are released in stream order)
   if (P->sharded) *out = P->out_full.release();
   else if (left) *out = P->out_kl.release();
