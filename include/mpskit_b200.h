@@ -183,6 +183,8 @@ int32_t mpsk_tsvd(mpsk_ctx* ctx, const mpsk_tensor* ac2, int32_t d1, const int32
                   mpsk_tensor** S, mpsk_tensor** Vh, double* eps_trunc);
 /* singular values of the last mpsk_tsvd, per coupled sector, before truncation: two-phase query */
 int32_t mpsk_tsvd_spectrum(mpsk_ctx* ctx, int32_t* nsec, int32_t* charge, int32_t* count, int32_t* kept, double* values);
+/* inv(C) of a bond tensor, sector by sector (the edge updates of IDMRG2, idmrg.jl:130-134,172-173) */
+int32_t mpsk_bond_inverse(mpsk_ctx* ctx, const mpsk_tensor* C, mpsk_tensor** out);
 /* leftorth!(A; alg=QRpos()) / rightorth!(A; alg=LQpos()) (orthoview.jl:49-60) */
 int32_t mpsk_qrpos(mpsk_ctx* ctx, const mpsk_tensor* A, mpsk_tensor** Q, mpsk_tensor** R);
 int32_t mpsk_lqpos(mpsk_ctx* ctx, const mpsk_tensor* A, mpsk_tensor** L, mpsk_tensor** Q);

@@ -23,8 +23,10 @@ from .algorithms import (DMRG, TDVP, TDVP2, find_groundstate, find_groundstate_d
                          timestep, timestep_inplace)
 from .sharding import panel_bounds, panel_table, panel_space, row_panel, scatter_panel, apply_local, init_communicator  # noqa: F401
 from .infinite import (InfiniteMPS, TransferMatrix, regularize, MPOHamInfEnv, VUMPS, find_groundstate_vumps,  # noqa: F401
-                       uniform_leftorth, uniform_rightorth, regauge, IDMRG1, IDMRGEnv, find_groundstate_idmrg1)
+                       uniform_leftorth, uniform_rightorth, regauge, IDMRG1, IDMRGEnv, find_groundstate_idmrg1, IDMRG2,
+                       find_groundstate_idmrg2, bond_inverse)
 from . import infinite  # noqa: F401
 from .statmech import (PerMPOInfEnv, leading_boundary, MultilineOp, MultilineEnv, leading_boundary_multiline,  # noqa: F401
                        expectation_value_multiline, fixedpoint_multiline)
 from . import statmech  # noqa: F401
+from .approximate import approximate, approximate_inplace, ac_proj, ac2_proj  # noqa: F401

@@ -98,6 +98,7 @@ PROTOTYPES = {
     "mpsk_mul_bond_left": (C.c_int32, [_P, _P, _P, _PP]),
     "mpsk_tsvd": (C.c_int32, [_P, _P, C.c_int32, _I32P, c_trunc, _PP, _PP, _PP, _DP]),
     "mpsk_tsvd_spectrum": (C.c_int32, [_P, _I32P, _I32P, _I32P, _I32P, _DP]),
+    "mpsk_bond_inverse": (C.c_int32, [_P, _P, _PP]),
     "mpsk_qrpos": (C.c_int32, [_P, _P, _PP, _PP]),
     "mpsk_lqpos": (C.c_int32, [_P, _P, _PP, _PP]),
     "mpsk_comm_unique_id": (C.c_int32, [C.POINTER(C.c_uint8)]),

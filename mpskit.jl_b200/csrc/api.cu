@@ -612,6 +612,13 @@ int32_t mpsk_tsvd_spectrum(mpsk_ctx* ctx, int32_t* nsec, int32_t* charge, int32_
   return MPSK_OK;
 }
 
+int32_t mpsk_bond_inverse(mpsk_ctx* ctx, const mpsk_tensor* C, mpsk_tensor** out) { ENTER(ctx);
+  Tensor* o = nullptr;
+  MPSK_TRY(bond_inverse(CTX(ctx), CTEN(C), &o));
+  *out = reinterpret_cast<mpsk_tensor*>(o);
+  return MPSK_OK;
+}
+
 int32_t mpsk_qrpos(mpsk_ctx* ctx, const mpsk_tensor* A, mpsk_tensor** Q, mpsk_tensor** R) { ENTER(ctx);
   Tensor *q = nullptr, *r = nullptr;
   MPSK_TRY(qrpos(CTX(ctx), CTEN(A), true, &q, &r));

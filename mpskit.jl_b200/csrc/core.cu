@@ -45,6 +45,27 @@ void Ctx::free(void* p) {
   cudaFreeAsync(p, stream);
 }
 
+void* Ctx::lease(int slot, size_t bytes, bool* leased) {
+  Scratch& sc = scratch[slot];
+  if (sc.busy) { *leased = false; return alloc(bytes); }
+  if (sc.cap < bytes) {
+    if (sc.p) free(sc.p);
+    sc.p = nullptr; sc.cap = 0;
+    const size_t want = bytes + bytes / 8 + ((size_t)1 << 20);
+    sc.p = alloc(want);
+    if (!sc.p) { sc.p = alloc(bytes); if (!sc.p) { *leased = false; return nullptr; } sc.cap = bytes; }
+    else sc.cap = want;
+  }
+  sc.busy = true; *leased = true;
+  return sc.p;
+}
+
+void Ctx::unlease(int slot, void* p, bool leased) {
+  if (!p) return;
+  if (leased) scratch[slot].busy = false;
+  else free(p);
+}
+
 void Ctx::release_cache() {
   cudaStreamSynchronize(stream);
   cudaMemPool_t pool;

@@ -188,10 +188,25 @@ static double now_s() { return std::chrono::duration<double>(std::chrono::steady
 
 struct KSpace {
   Ctx* ctx = nullptr; LinOp* op = nullptr; bool cx = true; int kd = 0; int64_t n = 0;
-  std::vector<Tensor*> V;       // kd + 1 basis vectors (structure of op->local_like())
-  std::vector<Tensor*> spare;   // targets of basis rotations (thick restarts), allocated on first use
+  std::vector<Tensor*> V;       // kd + 1 basis vectors (structure of op->local_like()): views into one leased slab
+  std::vector<Tensor*> spare;   // targets of basis rotations (thick restarts), allocated on first use (second slab)
   double* d_s = nullptr;
-  ~KSpace() { for (Tensor* t : V) delete t; for (Tensor* t : spare) delete t; if (d_s) ctx->free(d_s); }
+  void* slab = nullptr; bool slab_leased = false; void* slab2 = nullptr; bool slab2_leased = false; int nspare_cap = 0;
+  ~KSpace() {
+    for (Tensor* t : V) delete t;
+    for (Tensor* t : spare) delete t;
+    if (d_s) ctx->free(d_s);
+    if (ctx) { ctx->unlease(Ctx::S_KRYLOV, slab, slab_leased); ctx->unlease(Ctx::S_KRYLOV_SPARE, slab2, slab2_leased); }
+  }
+  // a vector with the structure of `like` whose storage is `data` (not owned)
+  Tensor* view(void* data) {
+    const Tensor* like = op->local_like();
+    Tensor* t = new Tensor;
+    t->ctx = ctx; t->Vl = like->Vl; t->Vr = like->Vr; t->mch = like->mch; t->dtype = like->dtype; t->form = F_KL;
+    tensor_layout_only(t);
+    t->d = data; t->owns = false;
+    return t;
+  }
 
   double* d_h1() const { return d_s; }
   double* d_h2() const { return d_s + 2 * (kd + 1); }
@@ -204,7 +219,10 @@ struct KSpace {
   }
   int init(Ctx* c, LinOp* o, int kd_) {
     ctx = c; op = o; kd = kd_; cx = o->local_like()->dtype == MPSK_C128; n = o->local_like()->nelem;
-    for (int i = 0; i <= kd; ++i) { Tensor* t = nullptr; MPSK_TRY(newvec(&t)); V.push_back(t); }
+    const size_t vb = o->local_like()->bytes();
+    slab = ctx->lease(Ctx::S_KRYLOV, vb * (size_t)(kd + 1), &slab_leased);
+    if (!slab) return MPSK_ENOMEM;
+    for (int i = 0; i <= kd; ++i) V.push_back(view((char*)slab + (size_t)i * vb));
     d_s = (double*)ctx->alloc(sizeof(double) * (4 * (kd + 1) + 4 + 2 * (kd + 2)));
     if (!d_s) return MPSK_ENOMEM;
     if (!ctx->h_scratch) CUDA_TRY(ctx, cudaMallocHost(&ctx->h_scratch, sizeof(double) * 2048));
@@ -287,7 +305,14 @@ struct KSpace {
   // basis rotation of a restart: V[j] <- sum_{i<m} V[i] Y(i, j) for j < keep (Y column-major m x *, leading dim m),
   // V[keep] <- V[m].  New vectors are written to spare buffers and swapped in (no copies of basis vectors).
   int rotate(int m, int keep, const cplx* Y) {
-    while ((int)spare.size() < keep) { Tensor* t = nullptr; MPSK_TRY(newvec(&t)); spare.push_back(t); }
+    if (!slab2) {      // spare vectors for every possible restart of this solve (keep <= kd)
+      const size_t vb = op->local_like()->bytes();
+      nspare_cap = (3 * kd) / 5 + 1;          // restarts keep at most 3/5 of the Ritz / Schur vectors
+      slab2 = ctx->lease(Ctx::S_KRYLOV_SPARE, vb * (size_t)nspare_cap, &slab2_leased);
+      if (!slab2) return MPSK_ENOMEM;
+    }
+    if (keep > nspare_cap) return ctx->fail(MPSK_EINTERNAL, "krylov: restart keeps more vectors than reserved");
+    while ((int)spare.size() < keep) spare.push_back(view((char*)slab2 + spare.size() * op->local_like()->bytes()));
     for (int j = 0; j < keep; ++j) MPSK_TRY(combine(m, Y + (size_t)j * m, spare[j]));
     for (int j = 0; j < keep; ++j) std::swap(V[j], spare[j]);
     std::swap(V[keep], V[m]);

@@ -12,7 +12,7 @@
 namespace mpsk {
 
 HeffOp::~HeffOp() {
-  if (ctx) { ctx->free(T); ctx->free(U); ctx->free(gather); }
+  if (ctx) { ctx->unlease(Ctx::S_HEFF_T, T, T_leased); ctx->unlease(Ctx::S_HEFF_U, U, U_leased); ctx->free(gather); }
 }
 
 static int build_W(Ctx* ctx, int kind, const MpoSlice* h1, const MpoSlice* h2, const Tensor* x_like, int nlev,
@@ -80,12 +80,13 @@ int heff_create(Ctx* ctx, int kind, const MpoSlice* h1, const MpoSlice* h2, cons
   double tp0 = 0, tp1 = 0, tp2 = 0;
   if (ctx->profile) { cudaStreamSynchronize(ctx->stream); tp0 = wall(); }
   if (GL->dtype != x_like->dtype || GR->dtype != x_like->dtype) return ctx->fail(MPSK_EINVAL, "mixed scalar types");
+  // ket legs of the environments must match x; the bra legs (GL->Vl, GR->Vr) fix the structure of y.  Square operators
+  // (bra = ket) are what the eigensolvers iterate; a row panel of the bra-left space is the multi-GPU shard; general
+  // rectangular operators project a vector of one state onto the tangent space of another (ac_proj / ac2_proj of
+  // `approximate`, derivatives.jl:209-232).
   if (!(GL->Vr == x_like->Vl)) return ctx->fail(MPSK_ESPACE, "left environment does not match the left bond of x");
-  for (int j = 0; j < GL->Vl.nsec(); ++j) {     // bra space: the left bond of x or a row panel of it (multi-GPU sharding)
-    const int jf = x_like->Vl.find(GL->Vl.q[j]);
-    if (jf < 0 || GL->Vl.n[j] > x_like->Vl.n[jf]) return ctx->fail(MPSK_ESPACE, "bra space of the left environment is not contained in the left bond of x");
-  }
-  if (!(GR->Vl == x_like->Vr) || !(GR->Vr == x_like->Vr)) return ctx->fail(MPSK_ESPACE, "right environment does not match the right bond of x");
+  if (!(GR->Vl == x_like->Vr)) return ctx->fail(MPSK_ESPACE, "right environment does not match the right bond of x");
+  if (GL->Vl.mod != x_like->Vl.mod || GR->Vr.mod != x_like->Vr.mod) return ctx->fail(MPSK_ESPACE, "environments and vector belong to different groups");
   if (GL->nm() != GR->nm()) return ctx->fail(MPSK_ESPACE, "environments have different numbers of MPO levels");
   const int nlev = GL->nm();
   if (h1 && h1->odim != nlev) return ctx->fail(MPSK_ESPACE, "MPO slice odim %d != environment levels %d", h1->odim, nlev);
@@ -113,7 +114,7 @@ int heff_create(Ctx* ctx, int kind, const MpoSlice* h1, const MpoSlice* h2, cons
   if (ctx->profile) { cudaStreamSynchronize(ctx->stream); tp1 = wall(); }
   const Tensor& xs = *op->xs; const Tensor& GLk = *op->GLk; const Tensor& GRs = *op->GRs;
   Tensor* ybuf = nullptr;
-  MPSK_TRY(tensor_create(ctx, Vb, x_like->mch, x_like->Vr, x_like->dtype, F_KL, true, &ybuf));
+  MPSK_TRY(tensor_create(ctx, Vb, x_like->mch, GR->Vr, x_like->dtype, F_KL, true, &ybuf));
   std::unique_ptr<Tensor> ys(ybuf);
   const int ngl = Vl.nsec();
   // ---- T workspace: per l-sector jb a (M_A x N_A) matrix
@@ -135,8 +136,8 @@ int heff_create(Ctx* ctx, int kind, const MpoSlice* h1, const MpoSlice* h2, cons
   }
   op->U_elems = std::max<int64_t>(tot, GROUP_ALIGN);
   const size_t es = cx ? 16 : 8;
-  op->T = ctx->alloc(op->T_elems * es);
-  op->U = ctx->alloc(op->U_elems * es);
+  op->T = ctx->lease(Ctx::S_HEFF_T, op->T_elems * es, &op->T_leased);
+  op->U = ctx->lease(Ctx::S_HEFF_U, op->U_elems * es, &op->U_leased);
   if (!op->T || !op->U) return MPSK_ENOMEM;
   CUDA_TRY(ctx, cudaMemsetAsync(op->T, 0, op->T_elems * es, ctx->stream));
   CUDA_TRY(ctx, cudaMemsetAsync(op->U, 0, op->U_elems * es, ctx->stream));
@@ -155,7 +156,7 @@ int heff_create(Ctx* ctx, int kind, const MpoSlice* h1, const MpoSlice* h2, cons
   }
   // ---- mix + stage C
   std::vector<MixTask> tasks; std::vector<MixTerm> terms; std::vector<GemmProblemHost> pc;
-  const int ngr = x_like->Vr.nsec();
+  const int ngr = GRs.Vr.nsec();
   for (size_t b = 0; b < ys->blks.size(); ++b) {
     const Blk& bk = ys->blks[b];
     const int ja = bk.jl, jz = bk.jr;

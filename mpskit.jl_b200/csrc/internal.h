@@ -69,6 +69,16 @@ struct Ctx {
   int profile = -1;                    // MPSK_PROFILE=1: host timers around the Krylov phases
   double t_apply = 0, t_orth = 0, t_sync = 0;
   std::recursive_mutex mu;             // every ABI entry locks the context: concurrent callers serialise
+  // Leased scratch slots: the multi-GB transient workspaces of an update (GEMM intermediates of the effective Hamiltonian
+  // and of the environment update, the Krylov basis, the SVD arena) live in persistent per-context buffers that only ever
+  // grow.  A slot that is busy (e.g. two operators alive at once) falls back to the allocator.  Without this the
+  // workspaces -- ~25 GB allocated and released per centre update at D = 4096, with sizes drifting from site to site --
+  // go through the memory pool, which degrades badly once > 100 GB of environments are resident (full sweeps on 1 GPU).
+  enum { S_HEFF_T = 0, S_HEFF_U, S_TR_T, S_TR_Q, S_TSVD, S_KRYLOV, S_KRYLOV_SPARE, S_NSLOT };
+  struct Scratch { void* p = nullptr; size_t cap = 0; bool busy = false; };
+  Scratch scratch[S_NSLOT];
+  void* lease(int slot, size_t bytes, bool* leased);
+  void unlease(int slot, void* p, bool leased);
 
   void* alloc(size_t bytes);
   void free(void* p);
@@ -246,8 +256,8 @@ struct HeffOp : LinOp {
   std::unique_ptr<Tensor> yfull; std::unique_ptr<CopyPlan> scatter;     // gathered panels -> yfull (full-vector apply)
   std::unique_ptr<CopyPlan> scatter_x;                                   // gathered panels -> xs   (Krylov apply)
   std::vector<WEntry> W;
-  // workspaces
-  void* T = nullptr; void* U = nullptr; int64_t T_elems = 0, U_elems = 0;
+  // workspaces (leased context slots when free)
+  void* T = nullptr; void* U = nullptr; int64_t T_elems = 0, U_elems = 0; bool T_leased = false, U_leased = false;
   std::unique_ptr<GemmPlan> gemmA, gemmC; std::unique_ptr<MixPlan> mix;
   double flops_ = 0;
   ~HeffOp();
@@ -276,7 +286,7 @@ struct TransferPlan {
   std::unique_ptr<Tensor> in_like, out_like; // KL-form structure templates of input / output (no storage)
   std::unique_ptr<CopyPlan> in_repack, out_repack;   // KL input -> vin (left only); vout -> KL out_kl (left only)
   std::unique_ptr<Tensor> out_kl;            // left only: KL-form output staging
-  void* T = nullptr; void* Q = nullptr;
+  void* T = nullptr; void* Q = nullptr; bool T_leased = false, Q_leased = false;
   GemmPlan g1, g3; MixPlan mx;
   double flops = 0;
   // row-panel sharding of the output bra index (multi-GPU): this rank computes its panel, allgather assembles the rest
@@ -345,6 +355,7 @@ int mul_bond_left(Ctx* ctx, const Tensor* C, const Tensor* A, Tensor** out);
 int tsvd(Ctx* ctx, const Tensor* ac2, int d1, const int32_t* p1_charge, mpsk_trunc trunc, Tensor** U, Tensor** S, Tensor** Vh, double* eps);
 int qrpos(Ctx* ctx, const Tensor* A, bool left, Tensor** Q, Tensor** R);
 void pool_destroy(Ctx* ctx);
+int bond_inverse(Ctx* ctx, const Tensor* C, Tensor** out);
 int comm_allreduce_sum(Ctx* ctx, void* buf, size_t ndoubles);
 
 }  // namespace mpsk

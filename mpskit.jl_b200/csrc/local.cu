@@ -25,7 +25,7 @@ struct Owned {
 };
 
 // ------------------------------------------------------------------------------------------ persistent transfer plans
-TransferPlan::~TransferPlan() { if (ctx) { ctx->free(T); ctx->free(Q); ctx->free(gather); } }
+TransferPlan::~TransferPlan() { if (ctx) { ctx->unlease(Ctx::S_TR_T, T, T_leased); ctx->unlease(Ctx::S_TR_Q, Q, Q_leased); ctx->free(gather); } }
 
 // dst = (conj) src for two tensors of the same structure in (possibly) different forms; asynchronous
 static int tensor_copy_into(Ctx* ctx, const Tensor* src, Tensor* dst, bool conj) {
@@ -44,9 +44,9 @@ static int tensor_copy_into(Ctx* ctx, const Tensor* src, Tensor* dst, bool conj)
   return run_copy_tasks(ctx, tasks, src->dtype == MPSK_C128);
 }
 
-static int alloc_work(Ctx* ctx, int64_t elems, size_t es, void** out) {
+static int alloc_work(Ctx* ctx, int slot, int64_t elems, size_t es, void** out, bool* leased) {
   elems = std::max<int64_t>(elems, GROUP_ALIGN);
-  *out = ctx->alloc((size_t)elems * es);
+  *out = ctx->lease(slot, (size_t)elems * es, leased);
   if (!*out) return MPSK_ENOMEM;
   CUDA_TRY(ctx, cudaMemsetAsync(*out, 0, (size_t)elems * es, ctx->stream));
   return MPSK_OK;
@@ -78,7 +78,7 @@ static int build_left(Ctx* ctx, TransferPlan* P, const MpoSlice* h, const Tensor
   // step 1: T^T_jb[(s,b') x (j,a)] = A_KL(jb) * GL_KR(jb)^T
   std::vector<int64_t> Toff(nb), Tld(nb); int64_t tot = 0;
   for (int jb = 0; jb < nb; ++jb) { Tld[jb] = pad(Gk->groups[jb].rows); Toff[jb] = tot; tot += padg(Ak->groups[jb].rows * Tld[jb]); }
-  MPSK_TRY(alloc_work(ctx, tot, es, &P->T));
+  MPSK_TRY(alloc_work(ctx, Ctx::S_TR_T, tot, es, &P->T, &P->T_leased));
   auto Tat = [&](int64_t off) { return (char*)P->T + off * es; };
   std::vector<GemmProblemHost> p1;
   for (int jb = 0; jb < nb; ++jb) {
@@ -90,7 +90,7 @@ static int build_left(Ctx* ctx, TransferPlan* P, const MpoSlice* h, const Tensor
   // step 2/3
   std::vector<int64_t> Qoff(o->blks.size()); tot = 0;
   for (size_t b = 0; b < o->blks.size(); ++b) { Qoff[b] = tot; tot += padg(o->Vr.n[o->blks[b].jr] * Bs->groups[o->blks[b].jl].ld); }
-  MPSK_TRY(alloc_work(ctx, tot, es, &P->Q));
+  MPSK_TRY(alloc_work(ctx, Ctx::S_TR_Q, tot, es, &P->Q, &P->Q_leased));
   auto Qat = [&](int64_t off) { return (char*)P->Q + off * es; };
   std::vector<MixTask> tasks; std::vector<MixTerm> terms; std::vector<GemmProblemHost> p3;
   const int ngB = Bs->Vr.nsec();   // SL groups = r sectors of Abar (a')
@@ -159,7 +159,7 @@ static int build_right(Ctx* ctx, TransferPlan* P, const MpoSlice* h, const Tenso
   // step 1: T^T_jc[(s,a) x (k,c')] = A_KR(jc) * GR_KL(jc)^T
   std::vector<int64_t> Toff(nc), Tld(nc); int64_t tot = 0;
   for (int jc = 0; jc < nc; ++jc) { Tld[jc] = pad(Gk->groups[jc].rows); Toff[jc] = tot; tot += padg(Ak->groups[jc].rows * Tld[jc]); }
-  MPSK_TRY(alloc_work(ctx, tot, es, &P->T));
+  MPSK_TRY(alloc_work(ctx, Ctx::S_TR_T, tot, es, &P->T, &P->T_leased));
   auto Tat = [&](int64_t off) { return (char*)P->T + off * es; };
   std::vector<GemmProblemHost> p1;
   for (int jc = 0; jc < nc; ++jc) {
@@ -170,7 +170,7 @@ static int build_right(Ctx* ctx, TransferPlan* P, const MpoSlice* h, const Tenso
   }
   std::vector<int64_t> Qoff(o->blks.size()); tot = 0;
   for (size_t b = 0; b < o->blks.size(); ++b) { Qoff[b] = tot; tot += padg(o->Vl.n[o->blks[b].jl] * Bs->groups[o->blks[b].jr].ld); }
-  MPSK_TRY(alloc_work(ctx, tot, es, &P->Q));
+  MPSK_TRY(alloc_work(ctx, Ctx::S_TR_Q, tot, es, &P->Q, &P->Q_leased));
   auto Qat = [&](int64_t off) { return (char*)P->Q + off * es; };
   std::vector<MixTask> tasks; std::vector<MixTerm> terms; std::vector<GemmProblemHost> p3;
   const int ngB = Bs->Vl.nsec();   // SR groups = l sectors of Abar (b)

@@ -259,9 +259,9 @@ int tsvd(Ctx* ctx, const Tensor* x, int d1, const int32_t* p1ch, mpsk_trunc trun
   // buffers whose sizes change from site to site, which defeats the caching allocator (cudaMalloc dominated the first
   // profile of this function)
   struct Arena {
-    Ctx* ctx; char* base = nullptr; size_t off = 0;
+    Ctx* ctx; char* base = nullptr; size_t off = 0; bool leased = false;
     void* take(size_t bytes) { off = (off + 255) & ~(size_t)255; void* p = base ? base + off : (void*)(uintptr_t)(off + 256); off += std::max<size_t>(bytes, 16); return p; }
-    ~Arena() { if (base) ctx->free(base); }
+    ~Arena() { if (base) ctx->unlease(Ctx::S_TSVD, base, leased); }
   } arena{ctx};
   // gesvd only for tiny sectors: cuSOLVER's QR-iteration SVD is latency-bound (tens of ms already at 200 x 200), the
   // multi-level Gram route is as accurate and an order of magnitude faster from ~32 columns on
@@ -354,7 +354,7 @@ int tsvd(Ctx* ctx, const Tensor* x, int d1, const int32_t* p1ch, mpsk_trunc trun
     }
   };
   layout();
-  arena.base = (char*)ctx->alloc(arena.off + 512);
+  arena.base = (char*)ctx->lease(Ctx::S_TSVD, arena.off + 512, &arena.leased);
   if (!arena.base) return MPSK_ENOMEM;
   layout();
   // ---- assemble the column-major matrices of the sectors this rank factorises
@@ -653,6 +653,60 @@ int tsvd(Ctx* ctx, const Tensor* x, int d1, const int32_t* p1ch, mpsk_trunc trun
   lap("outputs", 0, 0);
   if (ctx->profile) fprintf(stderr, "[mpsk profile] tsvd total %.2f ms\n", (tnow() - tp0) * 1e3);
   *Uo = ug.release(); *So = sg.release(); *Vo = vg.release();
+  return MPSK_OK;
+}
+
+// ------------------------------------------------------------------------------------------ inverse of a bond matrix
+// inv(C) per sector (idmrg.jl:130-134,172-173: the edge updates of IDMRG2 divide by the bond matrix): LU with partial
+// pivoting (cuSOLVER getrf / getrs on an identity right-hand side; LAPACK-class library call as in the reference).
+__global__ void eye_kernel(double* dst, int64_t ld, int n, int cplx) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < (int64_t)n * n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e % n), j = (int)(e / n);
+    const double v = i == j ? 1.0 : 0.0;
+    if (cplx) { dst[2 * (i + j * ld)] = v; dst[2 * (i + j * ld) + 1] = 0.0; } else dst[i + j * ld] = v;
+  }
+}
+
+int bond_inverse(Ctx* ctx, const Tensor* C, Tensor** out) {
+  if (C->nm() != 1 || C->mch[0] != 0) return ctx->fail(MPSK_ESPACE, "bond_inverse: not a bond tensor");
+  const bool cx = C->dtype == MPSK_C128;
+  const size_t es = cx ? 16 : 8;
+  Tensor* o = nullptr;
+  MPSK_TRY(tensor_create(ctx, C->Vr, std::vector<int32_t>{0}, C->Vl, C->dtype, F_KL, true, &o));
+  std::unique_ptr<Tensor> og(o);
+  cusolverDnHandle_t hs;
+  MPSK_TRY(get_cusolver(ctx, &hs));
+  int* d_info = (int*)ctx->alloc(sizeof(int));
+  if (!d_info) return MPSK_ENOMEM;
+  struct Tmp { Ctx* c; std::vector<void*> p; ~Tmp() { for (void* q : p) c->free(q); } } tmp{ctx, {d_info}};
+  for (const Blk& b : C->blks) {
+    const int n = (int)C->Vl.n[b.jl];
+    if ((int)C->Vr.n[b.jr] != n) return ctx->fail(MPSK_ESPACE, "bond_inverse: sector %d is not square", (int)C->Vl.q[b.jl]);
+    const Blk* ob = o->find(0, b.jr);
+    if (!ob || ob->jr != b.jl) return ctx->fail(MPSK_EINTERNAL, "bond_inverse: block mismatch");
+    const int64_t ld = pad(n);
+    void* W = ctx->alloc((size_t)ld * n * es); void* B = ctx->alloc((size_t)ld * n * es); int* piv = (int*)ctx->alloc(sizeof(int) * n);
+    if (!W || !B || !piv) return MPSK_ENOMEM;
+    tmp.p.push_back(W); tmp.p.push_back(B); tmp.p.push_back(piv);
+    std::vector<CopyTask> in{CopyTask{C->ptr(b.off), W, b.sl, b.sr, 1, ld, n, n, 0, 0, nullptr}};      // W(l, r) column-major
+    MPSK_TRY(run_copy_tasks(ctx, in, cx));
+    eye_kernel<<<std::min((n * n + 255) / 256, 1024), 256, 0, ctx->stream>>>((double*)B, ld, n, cx ? 1 : 0);
+    int lw = 0;
+    if (cx) CUSOLVER_TRY(ctx, cusolverDnZgetrf_bufferSize(hs, n, n, (cuDoubleComplex*)W, (int)ld, &lw));
+    else CUSOLVER_TRY(ctx, cusolverDnDgetrf_bufferSize(hs, n, n, (double*)W, (int)ld, &lw));
+    void* work = ctx->alloc((size_t)std::max(lw, 1) * es);
+    if (!work) return MPSK_ENOMEM;
+    tmp.p.push_back(work);
+    if (cx) { CUSOLVER_TRY(ctx, cusolverDnZgetrf(hs, n, n, (cuDoubleComplex*)W, (int)ld, (cuDoubleComplex*)work, piv, d_info));
+              CUSOLVER_TRY(ctx, cusolverDnZgetrs(hs, CUBLAS_OP_N, n, n, (const cuDoubleComplex*)W, (int)ld, piv, (cuDoubleComplex*)B, (int)ld, d_info)); }
+    else { CUSOLVER_TRY(ctx, cusolverDnDgetrf(hs, n, n, (double*)W, (int)ld, (double*)work, piv, d_info));
+           CUSOLVER_TRY(ctx, cusolverDnDgetrs(hs, CUBLAS_OP_N, n, n, (const double*)W, (int)ld, piv, (double*)B, (int)ld, d_info)); }
+    std::vector<CopyTask> outt{CopyTask{B, o->ptr(ob->off), 1, ld, ob->sl, ob->sr, n, n, 0, 0, nullptr}};
+    MPSK_TRY(run_copy_tasks(ctx, outt, cx));
+    ctx->launches += 3;
+  }
+  CUDA_TRY(ctx, cudaGetLastError());
+  *out = og.release();
   return MPSK_OK;
 }
 

@@ -15,6 +15,7 @@ class DerivativeOperator:
     def __init__(self, ctx, h1, h2, leftenv, rightenv, x_like):
         self.ctx = ctx
         self.o1, self.o2 = h1, h2
+        self._bra_l, self._bra_r = leftenv.Vl, rightenv.Vr          # structure of the output: y[bra_l, m, bra_r]
         kind = self.kind
         if getattr(ctx, "nranks", 1) > 1 and leftenv.Vl == x_like.Vl:
             kind |= 0x100                      # MPSK_OP_SHARDED
@@ -32,8 +33,13 @@ class DerivativeOperator:
         self.h = op
 
     def __call__(self, x, *_t):
-        """y = h(x); the optional second argument is the (ignored) time of derivatives.jl:31."""
-        y = x.zerovector()
+        """y = h(x); the optional second argument is the (ignored) time of derivatives.jl:31.  Rectangular operators
+        (bra spaces of the environments != bond spaces of x: ac_proj / ac2_proj of `approximate`) return a vector in the
+        bra spaces."""
+        if self._bra_l == x.Vl and self._bra_r == x.Vr:
+            y = x.zerovector()
+        else:
+            y = DeviceTensor.zeros(self.ctx, self._bra_l, x.mch, self._bra_r, x.dtype)
         self.ctx.check(self.ctx.lib.mpsk_op_apply(self.ctx.h, self.h, x.h, y.h))
         return y
 

@@ -566,3 +566,106 @@ def find_groundstate_idmrg1(ost: InfiniteMPS, H, alg: IDMRG1 = None, oenvs=None,
     nst = InfiniteMPS.from_tensors(AR, ost.V, ost.pspace, ctx, tol=alg.tol_gauge)     # idmrg.jl:72
     nenvs = environments(nst, H)
     return nst, nenvs, eps
+
+
+# ------------------------------------------------------------------------------------------ IDMRG2
+def bond_inverse(Cm):
+    """inv(C) of a bond tensor on the device (idmrg.jl:130-134,172-173)"""
+    h = C.c_void_p()
+    Cm.ctx.check(Cm.ctx.lib.mpsk_bond_inverse(Cm.ctx.h, Cm.h, C.byref(h)))
+    out = DeviceTensor.wrap(Cm.ctx, h, Cm.Vl.modulus)
+    out._is_bond = True
+    return out
+
+
+@dataclass
+class IDMRG2:
+    """idmrg.jl:84-91"""
+    tol: float = 1e-12
+    tol_gauge: float = TOLGAUGE
+    eigalg: object = field(default_factory=lambda: Lanczos(tol=1e-12))
+    maxiter: int = 100
+    verbosity: int = 0
+    trscheme: tuple = None
+
+
+def find_groundstate_idmrg2(ost: InfiniteMPS, H, alg: IDMRG2 = None, oenvs=None, log=None):
+    """find_groundstate(ost::InfiniteMPS, H, alg::IDMRG2, oenvs) (idmrg.jl:92-204): two-site updates through the unit cell
+    and across its edge, every tensor operation on the device (two-site matvec + Lanczos, truncated SVD, bond-matrix inverse,
+    manual environment updates)."""
+    from .dmrg import tsvd, contract_ac2, truncerr
+    from .derivatives import MPO_ddAC2
+    alg = alg or IDMRG2()
+    trscheme = alg.trscheme if alg.trscheme is not None else truncerr(1e-6)
+    N = ost.N
+    if N < 2:
+        raise ValueError("unit cell should be >= 2")
+    oenvs = oenvs or environments(ost, H)
+    ctx = ost.ctx
+    AL, AR, AC, CR = list(ost.AL), list(ost.AR), list(ost.AC), list(ost.CR)
+    envs = IDMRGEnv(ost, oenvs)
+    lw, rw = envs.lw, envs.rw
+
+    def update(pos, ac2):
+        """eigensolve + tsvd of the two-site tensor on sites pos, pos + 1 (periodic)"""
+        h = MPO_ddAC2(ctx, H[pos], H[pos + 1], lw[pos % N], rw[(pos + 1) % N], ac2)
+        val, new = fixedpoint(h, ac2, "SR", alg.eigalg); h.free()
+        al, c, ar, _ = tsvd(ost, new, trscheme)                     # normalize!(c) inside
+        new.free()
+        return al, c, ar, val
+
+    def tl(i):      # update_leftenv!(envs, psi, H, i + 1)
+        lw[(i + 1) % N] = transfer_left(lw[i % N], H[i], AL[i % N], AL[i % N])
+
+    def tr(i):      # update_rightenv!(envs, psi, H, i - 1)
+        rw[(i - 1) % N] = transfer_right(rw[i % N], H[i], AR[i % N], AR[i % N])
+    eps, val = np.inf, 0.0
+    for it in range(1, alg.maxiter + 1):
+        for pos in range(N - 1):                                                    # idmrg.jl:111-126
+            ac2 = contract_ac2(ost, AC[pos], AR[pos + 1])
+            al, c, ar, val = update(pos, ac2); ac2.free()
+            AL[pos], CR[pos], AR[pos + 1] = al, c, ar
+            AC[pos + 1] = mul_left(c, ar)
+            tl(pos); tr(pos + 1)
+        # edge: sites N-1 and 0 (idmrg.jl:129-148)
+        left = mul_right(AC[N - 1], bond_inverse(CR[N - 1]))
+        ac2 = contract_ac2(ost, left, mul_right(AL[0], CR[0]))
+        al, c, ar, val = update(N - 1, ac2); ac2.free()
+        AC[N - 1] = mul_right(al, c); AL[N - 1] = al; CR[N - 1] = c; AR[0] = ar
+        AC[0] = mul_left(c, ar)
+        AL[0] = mul_right(AC[0], bond_inverse(CR[0]))
+        Ccur = c
+        tl(N - 1); tr(0)
+        for pos in range(N - 2, -1, -1):                                            # idmrg.jl:151-167
+            ac2 = contract_ac2(ost, AL[pos], AC[pos + 1])
+            al, c, ar, val = update(pos, ac2); ac2.free()
+            AL[pos], CR[pos], AR[pos + 1] = al, c, ar
+            AC[pos] = mul_right(al, c)
+            AC[pos + 1] = mul_left(c, ar)
+            tl(pos); tr(pos + 1)
+        # edge (idmrg.jl:170-186)
+        left = mul_left(CR[N - 2], AR[N - 1])
+        ac2 = contract_ac2(ost, mul_right(left, bond_inverse(CR[N - 1])), AC[0])
+        al, c, ar, val = update(N - 1, ac2); ac2.free()
+        AR[N - 1] = mul_left(bond_inverse(CR[N - 2]), mul_right(al, c))
+        AL[N - 1] = al; CR[N - 1] = c; AR[0] = ar
+        AC[0] = mul_left(c, ar)
+        tl(N - 1); tr(0)
+        # error on the smallest common space (idmrg.jl:189-192); the bond matrices are small: host read-out
+        ba, bb = Ccur.to_blocks(), c.to_blocks()
+        acc = 0.0
+        for jl_a, q in enumerate(Ccur.Vl.charges):
+            if q not in c.Vl.charges:
+                continue
+            x, y = ba[(0, jl_a)], bb[(0, c.Vl.charges.index(q))]
+            k = min(x.shape[0], y.shape[0])
+            acc += float(np.linalg.norm(y[:k, :k] - x[:k, :k]) ** 2)
+        eps = float(np.sqrt(acc))
+        if log is not None:
+            log.append(dict(iter=it, eps=eps, energy=val.real, D=c.Vl.dim))
+        if eps < alg.tol:
+            break
+    V = [AR[i].Vl for i in range(N)]
+    nst = InfiniteMPS.from_tensors(AR, V, ost.pspace, ctx, tol=alg.tol_gauge)       # idmrg.jl:201
+    nenvs = environments(nst, H)
+    return nst, nenvs, eps

@@ -83,7 +83,7 @@ def transfer_right_sparse(vec, ham: SparseMPOSlice, A, Ab):
 def dAC_sparse(x, H: SparseMPOSlice, GL, GR):
     """derivatives.jl:77-93 (serial branch) with the per-entry contraction order of 95-104:
     x*GR_j (label 1), then the operator (2,3), then GL_i (4,5)."""
-    y = np.zeros_like(x, dtype=np.result_type(x, GL, np.complex128))
+    y = np.zeros((GL.shape[0], x.shape[1], GR.shape[2]), dtype=np.result_type(x, GL, np.complex128))   # bra spaces (rectangular for ac_proj)
     for (i, j) in H.keys():
         t = np.einsum('dbx,xz->dbz', x, GR[:, j, :])
         if H.isscal(i, j):

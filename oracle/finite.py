@@ -191,8 +191,9 @@ class FiniteMPS:
 class FinEnv:
     """FinEnv.jl:9-145 with identity-based staleness (`===`)."""
 
-    def __init__(self, psi: FiniteMPS, H: MPOHamiltonian):
+    def __init__(self, psi: FiniteMPS, H: MPOHamiltonian, above: FiniteMPS = None):
         self.opp = H
+        self.above = above           # FinEnv.jl:72-106: environments between `above` (ket) and psi (bra) -- approximate
         L = psi.L
         odim = H.odim
         # FinEnv.jl:41-70: l_LL (x) 1 on level 1, r_RR (x) 1 on level odim (MPOHamiltonian)
@@ -214,7 +215,8 @@ class FinEnv:
         if a is not None:
             for j in range(a, ind, -1):
                 AR = psi.get_AR(j)
-                self.rightenvs[j] = transfer_right_sparse(self.rightenvs[j + 1], self.opp[j], AR, AR)
+                ket = AR if self.above is None else self.above.get_AR(j)
+                self.rightenvs[j] = transfer_right_sparse(self.rightenvs[j + 1], self.opp[j], ket, AR)
                 self.rdep[j] = AR
         return self.rightenvs[ind + 1]
 
@@ -228,7 +230,8 @@ class FinEnv:
         if a is not None:
             for j in range(a, ind):
                 AL = psi.get_AL(j)
-                self.leftenvs[j + 1] = transfer_left_sparse(self.leftenvs[j], self.opp[j], AL, AL)
+                ket = AL if self.above is None else self.above.get_AL(j)
+                self.leftenvs[j + 1] = transfer_left_sparse(self.leftenvs[j], self.opp[j], ket, AL)
                 self.ldep[j] = AL
         return self.leftenvs[ind]
 
@@ -417,3 +420,38 @@ def tdvp2_step(psi: FiniteMPS, H, dt, envs=None, trunc=("truncerr", 1e-3), tol=1
         if i != 1:
             one_site_back(i - 1, dt / 2)
     return psi, envs
+
+
+def approximate(psi: FiniteMPS, O, above: FiniteMPS, nsweeps=1, trunc=("truncerr", 1e-6), two_site=True, tol=1e-12, log=None):
+    """approximate!(psi, (O, above), DMRG2 / DMRG) (src/algorithms/approximate/fvomps.jl:11-114) with ac2_proj / ac_proj
+    (src/algorithms/derivatives.jl:209-232): psi <- the best MPS approximation of O |above> in psi's manifold."""
+    envs = FinEnv(psi, O, above)
+    L = psi.L
+    eps = 0.0
+    for it in range(nsweeps):
+        eps = 0.0
+        if two_site:
+            for pos in list(range(0, L - 1)) + list(range(L - 3, -1, -1)):
+                x = np.einsum('apk,kqr->aprq', above.get_AC(pos), above.get_AR(pos + 1))
+                new = dAC2_sparse(x, O[pos], O[pos + 1], envs.leftenv(pos, psi), envs.rightenv(pos + 1, psi))
+                Dl, d1, Dr, d2 = new.shape
+                rowq, colq = ac2_space_charges(psi, pos)
+                U, S, Vh, newV, eps_tr, sinfo = tsvd(new.reshape(Dl * d1, Dr * d2), rowq, colq, trunc, psi.p.modulus)
+                old = np.einsum('apk,kqr->aprq', psi.get_AC(pos), psi.get_AR(pos + 1))
+                rec = (U * S[None, :]) @ Vh
+                eps = max(eps, float(np.linalg.norm(rec.reshape(old.shape) - old) / np.linalg.norm(old)))
+                al = U.reshape(Dl, d1, newV.dim)
+                ar = Vh.reshape(newV.dim, Dr, d2).transpose(0, 2, 1)
+                c = np.diag(S).astype(np.complex128)
+                psi.set_AC_alc(pos, al, c, newV)
+                psi.set_AC_car(pos + 1, c, ar, newV)
+        else:
+            for pos in list(range(0, L - 1)) + list(range(L - 1, 0, -1)):
+                new = dAC_sparse(above.get_AC(pos), O[pos], envs.leftenv(pos, psi), envs.rightenv(pos, psi))
+                eps = max(eps, float(np.linalg.norm(new - psi.get_AC(pos)) / np.linalg.norm(new)))
+                psi.set_AC(pos, new)
+        if log is not None:
+            log.append(dict(iter=it, eps=eps))
+        if eps < tol:
+            break
+    return psi, envs, eps

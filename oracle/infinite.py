@@ -370,3 +370,82 @@ def idmrg1(st: InfiniteMPS, H, tol=1e-12, maxiter=100, envs=None, log=None):
     nst = InfiniteMPS.from_tensors(AR, st.V, st.pq, mod=st.modulus)
     nenvs = MPOHamInfEnv(nst, H)
     return nst, nenvs, eps
+
+
+def idmrg2(st: InfiniteMPS, H, trunc=("truncerr", 1e-6), tol=1e-12, maxiter=100, envs=None, log=None):
+    """find_groundstate(psi::InfiniteMPS, H, IDMRG2()) (src/algorithms/groundstate/idmrg.jl:92-204): two-site updates
+    through the unit cell and across its edge (with inv(CR) re-gauging), truncated SVD after every update, manually
+    updated IDMRGEnv.  Unit cell >= 2.  Bond spaces change with the truncation (tracked in V)."""
+    from .contract import transfer_left_sparse, transfer_right_sparse, dAC2_sparse
+    from .linalg import tsvd
+    from .spaces import Space
+    N = st.N
+    assert N >= 2, "unit cell should be >= 2"
+    envs0 = envs or MPOHamInfEnv(st, H)
+    lw = [envs0.leftenv(i, st).copy() for i in range(N)]
+    rw = [envs0.rightenv(i, st).copy() for i in range(N)]
+    AL, AR, AC, CR, V = list(st.AL), list(st.AR), list(st.AC), list(st.CR), list(st.V)
+    pq, mod = np.asarray(st.pq), st.modulus
+    state = {"E": 0.0}
+
+    def update(GL, GR, h1, h2, ac2, Vl, Vr, etol):
+        val, new, _ = eigsolve_lanczos(lambda x: dAC2_sparse(x, h1, h2, GL, GR), ac2, "SR", etol, 30, 100)
+        state["E"] = float(np.real(val))
+        Dl, d1, Dr, d2 = new.shape
+        rowq = (Vl.index_charges()[:, None] + pq[None, :]).reshape(-1)
+        colq = (Vr.index_charges()[:, None] - pq[None, :]).reshape(-1)
+        U, S, Vh, newV, _, _ = tsvd(new.reshape(Dl * d1, Dr * d2), rowq, colq, trunc, mod)
+        S = S / np.linalg.norm(S)                                                 # normalize!(c)
+        return U.reshape(Dl, d1, newV.dim), np.diag(S).astype(np.complex128), Vh.reshape(newV.dim, Dr, d2).transpose(0, 2, 1), newV
+
+    def tl(i):      # update_leftenv!(envs, psi, H, i + 1) (idmrgenv.jl:68-72)
+        lw[(i + 1) % N] = transfer_left_sparse(lw[i], H[i], AL[i], AL[i])
+
+    def tr(i):      # update_rightenv!(envs, psi, H, i - 1) (idmrgenv.jl:63-66)
+        rw[(i - 1) % N] = transfer_right_sparse(rw[i], H[i], AR[i], AR[i])
+    eps = np.inf
+    for it in range(1, maxiter + 1):
+        etol = max(tol / 10, 1e-14)
+        for pos in range(N - 1):                                                  # idmrg.jl:111-126
+            ac2 = np.einsum('apk,kqr->aprq', AC[pos], AR[pos + 1])
+            al, c, ar, nV = update(lw[pos], rw[pos + 1], H[pos], H[pos + 1], ac2, V[pos], V[(pos + 2) % N], etol)
+            AL[pos], CR[pos], AR[pos + 1], V[pos + 1] = al, c, ar, nV
+            AC[pos + 1] = np.einsum('ab,bpc->apc', c, ar)
+            tl(pos); tr(pos + 1)
+        # edge (idmrg.jl:129-148): sites N-1 and 0
+        ac2 = np.einsum('apk,kl,lqm,mr->aprq', AC[N - 1], np.linalg.inv(CR[N - 1]), AL[0], CR[0])
+        al, c, ar, nV = update(lw[N - 1], rw[0], H[N - 1], H[0], ac2, V[N - 1], V[1 % N], etol)
+        AC[N - 1] = np.einsum('apb,bc->apc', al, c); AL[N - 1] = al; CR[N - 1] = c; AR[0] = ar; V[0] = nV
+        AC[0] = np.einsum('ab,bpc->apc', c, ar)
+        AL[0] = np.einsum('apb,bc->apc', AC[0], np.linalg.inv(CR[0]))
+        Ccur, Vcur = c, nV
+        tl(N - 1); tr(0)
+        for pos in range(N - 2, -1, -1):                                          # idmrg.jl:151-167
+            ac2 = np.einsum('apk,kqr->aprq', AL[pos], AC[pos + 1])
+            al, c, ar, nV = update(lw[pos], rw[pos + 1], H[pos], H[pos + 1], ac2, V[pos], V[(pos + 2) % N], etol)
+            AL[pos], CR[pos], AR[pos + 1], V[pos + 1] = al, c, ar, nV
+            AC[pos] = np.einsum('apb,bc->apc', al, c)
+            AC[pos + 1] = np.einsum('ab,bpc->apc', c, ar)
+            tl(pos); tr(pos + 1)
+        # edge (idmrg.jl:170-186)
+        ac2 = np.einsum('ab,bpc,cd,dqe->apeq', CR[N - 2], AR[N - 1], np.linalg.inv(CR[N - 1]), AC[0])
+        al, c, ar, nV = update(lw[N - 1], rw[0], H[N - 1], H[0], ac2, V[N - 1], V[1 % N], etol)
+        AR[N - 1] = np.einsum('ab,bpc->apc', np.linalg.inv(CR[N - 2]), np.einsum('apb,bc->apc', al, c))
+        AL[N - 1] = al; CR[N - 1] = c; AR[0] = ar; V[0] = nV
+        AC[0] = np.einsum('ab,bpc->apc', c, ar)
+        tl(N - 1); tr(0)
+        # error (idmrg.jl:189-192): compare on the smallest common space
+        qa, qb = Vcur.index_charges(), nV.index_charges()
+        ia, ib = [], []
+        for q in sorted(set(qa.tolist()) & set(qb.tolist())):
+            xa, xb = np.nonzero(qa == q)[0], np.nonzero(qb == q)[0]
+            k = min(len(xa), len(xb))
+            ia += list(xa[:k]); ib += list(xb[:k])
+        eps = float(np.linalg.norm(c[np.ix_(ib, ib)] - Ccur[np.ix_(ia, ia)]))
+        if log is not None:
+            log.append(dict(iter=it, eps=eps, energy=state["E"], D=nV.dim))
+        if eps < tol:
+            break
+    nst = InfiniteMPS.from_tensors(AR, V, st.pq, mod=mod)                          # idmrg.jl:201
+    nenvs = MPOHamInfEnv(nst, H)
+    return nst, nenvs, eps

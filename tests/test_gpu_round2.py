@@ -15,6 +15,20 @@ from helpers import *
 pytestmark = pytest.mark.gpu
 
 
+def _full_state(psi):
+    T = psi.AC[0].to_dense()
+    for i in range(1, len(psi)):
+        T = np.tensordot(T, psi.AR[i].to_dense(), axes=([-1], [0]))
+    return T.reshape(-1)
+
+
+def _full_state_o(psi):
+    T = psi.get_AC(0)
+    for i in range(1, psi.L):
+        T = np.tensordot(T, psi.get_AR(i), axes=([-1], [0]))
+    return T.reshape(-1)
+
+
 def _rand_site(rng, Vl, pq, Vr):
     return BlockTensor.random(rng, Vl, pq, Vr)
 
@@ -371,3 +385,35 @@ def test_multiline_statmech_two_rows(ctx):
     log_f = []
     osm.leading_boundary(psi, [ompo.dense_mpo_slice(F)], tol=1e-11, maxiter=80, log=log_f)
     assert abs(v_d - log_f[-1]["value"][0]) <= 1e-7 * abs(v_d)     # different variational manifolds at D = 8
+
+
+@pytest.mark.parametrize("two_site", [True, False])
+def test_approximate_mpo_times_state(ctx, two_site):
+    """approximate(psi, (H, above), DMRG2 / DMRG) (approximate/fvomps.jl:11-114): rectangular effective Hamiltonians
+    (ac2_proj / ac_proj, derivatives.jl:209-232) between `above` (D = 4) and the approximating state (D = 16).  With enough
+    bond dimension the result equals H|above> exactly; device vs oracle sweep and vs the dense state."""
+    L = 6
+    Ho = ompo.heisenberg_u1(L)
+    po = OSpace((-1, 1), (1, 1))
+    Va = [of.gaussian_bond_space(4, k % 2) for k in range(1, L)]
+    Vb = [of.gaussian_bond_space(16, k % 2) for k in range(1, L)]
+    above_o = of.FiniteMPS.random(np.random.default_rng(1), po, L, Va)
+    psi_o = of.FiniteMPS.random(np.random.default_rng(2), po, L, Vb)
+    log_o = []
+    of.approximate(psi_o, Ho, above_o, nsweeps=4, trunc=("truncdim", 16), two_site=two_site, log=log_o)
+    p = to_dev_space(po)
+    above_d = m.FiniteMPS.random(np.random.default_rng(1), p, L, [to_dev_space(v) for v in Va], ctx)
+    psi_d = m.FiniteMPS.random(np.random.default_rng(2), p, L, [to_dev_space(v) for v in Vb], ctx)
+    Hd = dev_hamiltonian(Ho)
+    alg = m.DMRG2(tol=1e-12, maxiter=4, trscheme=m.truncdim(16)) if two_site else m.DMRG(tol=1e-12, maxiter=4)
+    log_d = []
+    psi_d, envs, eps = m.approximate(psi_d, (Hd, above_d), alg, log=log_d)
+    print("approximate", two_site, log_d, log_o)
+    assert eps <= 1e-12 and len(log_d) == len(log_o)
+    va = _full_state(above_d)
+    target = ompo.dense_hamiltonian(Ho) @ va
+    vp = _full_state(psi_d)
+    assert abs(abs(np.vdot(target, vp)) / np.linalg.norm(target) / np.linalg.norm(vp) - 1) <= 1e-12
+    assert abs(np.linalg.norm(vp) - np.linalg.norm(target)) <= 1e-10 * np.linalg.norm(target)     # the norm is carried too
+    vo = _full_state_o(psi_o)
+    assert abs(abs(np.vdot(vo, vp)) / np.linalg.norm(vo) / np.linalg.norm(vp) - 1) <= 1e-12
