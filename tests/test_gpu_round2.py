@@ -417,3 +417,30 @@ def test_approximate_mpo_times_state(ctx, two_site):
     assert abs(np.linalg.norm(vp) - np.linalg.norm(target)) <= 1e-10 * np.linalg.norm(target)     # the norm is carried too
     vo = _full_state_o(psi_o)
     assert abs(abs(np.vdot(vo, vp)) / np.linalg.norm(vo) / np.linalg.norm(vp) - 1) <= 1e-12
+
+
+def test_idmrg2_device(ctx):
+    """find_groundstate(psi, H, IDMRG2(trscheme = truncdim(10))) (idmrg.jl:92-204) on a 2-site unit cell: two-site updates
+    through the cell and across its edge (bond-matrix inverse on the device), vs the oracle IDMRG2 and the energy density the
+    reference logged for this model at D = 10 (docs/src/examples/quantum1d/3.ising-dqpt/index.md:112-118)."""
+    from oracle import infinite as oi
+    from mpskit_b200 import infinite as di
+    Ho = ompo.transverse_field_ising(2, 0.5)
+    Vo = [OSpace((0,), (6,)), OSpace((0,), (6,))]
+    psi_o = oi.InfiniteMPS.random(np.random.default_rng(3), OSpace((0,), (2,)), Vo)
+    log_o = []
+    st_o, envs_o, eps_o = oi.idmrg2(psi_o, Ho, trunc=("truncdim", 10), tol=1e-10, maxiter=100, log=log_o)
+    E_o = oi.expectation_value(st_o, Ho, envs_o).real
+    psi_d = m.InfiniteMPS.random(np.random.default_rng(3), m.Space((0,), (2,)), [to_dev_space(v) for v in Vo], ctx)
+    Hd = dev_hamiltonian(Ho)
+    log_d = []
+    st_d, envs_d, eps_d = m.find_groundstate_idmrg2(psi_d, Hd, m.IDMRG2(tol=1e-10, maxiter=100, trscheme=m.truncdim(10)), log=log_d)
+    E_d = di.expectation_value(st_d, Hd, envs_d).real
+    print("IDMRG2", E_d, E_o, eps_d, eps_o, len(log_d), len(log_o), log_d[-1]["D"])
+    assert eps_d < 1e-10 and log_d[-1]["D"] == 10
+    assert np.abs(E_d - E_o).max() <= 1e-9
+    assert np.abs(E_d - (-1.063544409973)).max() <= 1e-9
+    # bond inverse on its own
+    Cm = st_d.CR[0]
+    prod = di.mul_right(Cm, di.bond_inverse(Cm)).to_dense()[:, 0, :]
+    assert np.abs(prod - np.eye(prod.shape[0])).max() <= 1e-10
