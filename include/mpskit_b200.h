@@ -183,6 +183,14 @@ int32_t mpsk_tsvd(mpsk_ctx* ctx, const mpsk_tensor* ac2, int32_t d1, const int32
                   mpsk_tensor** S, mpsk_tensor** Vh, double* eps_trunc);
 /* singular values of the last mpsk_tsvd, per coupled sector, before truncation: two-phase query */
 int32_t mpsk_tsvd_spectrum(mpsk_ctx* ctx, int32_t* nsec, int32_t* charge, int32_t* count, int32_t* kept, double* values);
+/* leftnull(A): isometry N[l p; k'] onto the orthogonal complement of the range of A[l p; r]; rightnull(A): N[k' p; r] with
+ * orthonormal rows spanning the complement of the row space of A[l; p r] (changebonds/optimalexpand.jl:28-29,95-96) */
+int32_t mpsk_leftnull(mpsk_ctx* ctx, const mpsk_tensor* A, mpsk_tensor** out);
+int32_t mpsk_rightnull(mpsk_ctx* ctx, const mpsk_tensor* A, mpsk_tensor** out);
+/* B[k' p2; r] = sum_{l,p1} conj(N[l p1; k']) x2[l (p1 p2); r]  (adjoint(VL) * AC2, optimalexpand.jl:30,98) */
+int32_t mpsk_contract_adjoint_left(mpsk_ctx* ctx, const mpsk_tensor* N, const mpsk_tensor* x2, mpsk_tensor** out);
+/* direct sum along the left (axis 0: catcodomain) or right (axis 1: catdomain) bond (optimalexpand.jl:103-104) */
+int32_t mpsk_tensor_cat(mpsk_ctx* ctx, const mpsk_tensor* A, const mpsk_tensor* B, int32_t axis, mpsk_tensor** out);
 /* inv(C) of a bond tensor, sector by sector (the edge updates of IDMRG2, idmrg.jl:130-134,172-173) */
 int32_t mpsk_bond_inverse(mpsk_ctx* ctx, const mpsk_tensor* C, mpsk_tensor** out);
 /* leftorth!(A; alg=QRpos()) / rightorth!(A; alg=LQpos()) (orthoview.jl:49-60) */
@@ -215,6 +223,8 @@ int32_t mpsk_tensor_allgather(mpsk_ctx* ctx, const mpsk_tensor* panel, mpsk_tens
 /* complex Schur decomposition H = Z T Z^H used by the Krylov-Schur eigensolver; H, Z: n x n column-major interleaved complex;
  * if 0 <= move_to <= move_from < n the eigenvalue at position move_from is moved to move_to afterwards. */
 int32_t mpsk_host_schur(int32_t n, double* H, double* Z, int32_t move_from, int32_t move_to);
+/* randomised self-test of the device allocator's free-list logic (split / coalesce / trim) with malloc as the backend; 0 = ok */
+int32_t mpsk_host_alloc_selftest(uint64_t seed, int32_t nops);
 
 #ifdef __cplusplus
 }

@@ -99,6 +99,10 @@ PROTOTYPES = {
     "mpsk_tsvd": (C.c_int32, [_P, _P, C.c_int32, _I32P, c_trunc, _PP, _PP, _PP, _DP]),
     "mpsk_tsvd_spectrum": (C.c_int32, [_P, _I32P, _I32P, _I32P, _I32P, _DP]),
     "mpsk_bond_inverse": (C.c_int32, [_P, _P, _PP]),
+    "mpsk_leftnull": (C.c_int32, [_P, _P, _PP]),
+    "mpsk_rightnull": (C.c_int32, [_P, _P, _PP]),
+    "mpsk_contract_adjoint_left": (C.c_int32, [_P, _P, _P, _PP]),
+    "mpsk_tensor_cat": (C.c_int32, [_P, _P, _P, C.c_int32, _PP]),
     "mpsk_qrpos": (C.c_int32, [_P, _P, _PP, _PP]),
     "mpsk_lqpos": (C.c_int32, [_P, _P, _PP, _PP]),
     "mpsk_comm_unique_id": (C.c_int32, [C.POINTER(C.c_uint8)]),
@@ -111,6 +115,7 @@ PROTOTYPES = {
     "mpsk_tensor_panel": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _PP]),
     "mpsk_tensor_allgather": (C.c_int32, [_P, _P, _P]),
     "mpsk_host_schur": (C.c_int32, [C.c_int32, _DP, _DP, C.c_int32, C.c_int32]),
+    "mpsk_host_alloc_selftest": (C.c_int32, [C.c_uint64, C.c_int32]),
 }
 
 _lib = None

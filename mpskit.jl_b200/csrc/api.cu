@@ -49,13 +49,7 @@ int32_t mpsk_create(int32_t device, uint64_t flags, mpsk_ctx** out) {
   c->device = device; c->flags = flags; c->num_sms = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return MPSK_ECUDA; }
   c->stream = c->own_stream;
-  {   // keep freed device memory in the stream-ordered pool (see Ctx::alloc)
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-      uint64_t thr = UINT64_MAX;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-    }
-  }
+
   *out = reinterpret_cast<mpsk_ctx*>(c);
   return MPSK_OK;
 }
@@ -74,9 +68,12 @@ void mpsk_destroy(mpsk_ctx* ctx) {
   }
   if (c->d_scratch) c->free(c->d_scratch);
   if (c->h_arena) cudaFreeHost(c->h_arena);
-  for (auto& kv : c->sizes) cudaFreeAsync(kv.first, c->stream);
-  c->sizes.clear();
-  c->release_cache();
+  {   // everything still live belongs to handles the caller leaked: release the chunks regardless
+    std::vector<void*> live;
+    for (auto& kv : c->dev.live) live.push_back(kv.first);
+    for (void* q : live) c->dev.free(q);
+    c->release_cache();
+  }
   if (c->h_scratch) cudaFreeHost(c->h_scratch);
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -543,6 +540,39 @@ int32_t mpsk_multiop_create(mpsk_ctx* ctx, int32_t n, const mpsk_op* const* ops,
   return MPSK_OK;
 }
 
+// host-only self-test of the device allocator's free-list logic (devalloc.h) with malloc as the backend: random
+// allocate / release traffic, invariants checked after every operation; returns 0 on success
+static void* host_chunk_alloc(size_t b) { return malloc(b); }
+static void host_chunk_free(void* p) { free(p); }
+int32_t mpsk_host_alloc_selftest(uint64_t seed, int32_t nops) {
+  BlockAllocator a;
+  a.chunk_alloc = host_chunk_alloc; a.chunk_free = host_chunk_free; a.chunk_bytes = (size_t)1 << 20;
+  std::vector<std::pair<char*, size_t>> livev;
+  uint64_t x = seed * 2862933555777941757ull + 3037000493ull;
+  auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+  for (int i = 0; i < nops; ++i) {
+    const bool do_alloc = livev.empty() || (rnd() % 100) < 55;
+    if (do_alloc) {
+      size_t sz = (size_t)(rnd() % (((rnd() % 8) == 0) ? (3u << 20) : (64u << 10))) + 1;
+      char* p = (char*)a.alloc(sz);
+      if (!p) return -10;
+      for (auto& lv : livev) if (p < lv.first + lv.second && lv.first < p + sz) return -11;      // overlap with a live block
+      memset(p, (int)(i & 0xff), sz);
+      livev.push_back({p, sz});
+    } else {
+      const size_t k = rnd() % livev.size();
+      a.free(livev[k].first);
+      livev[k] = livev.back(); livev.pop_back();
+    }
+    if (!a.check()) return -12;
+  }
+  for (auto& lv : livev) a.free(lv.first);
+  if (!a.check() || a.bytes_live != 0) return -13;
+  if (a.free_by_addr.size() != a.chunks.size()) return -14;                                      // everything coalesced back
+  a.trim();
+  return a.chunks.empty() && a.bytes_reserved == 0 ? 0 : -15;
+}
+
 // host-only numerical helper exposed for the CPU test-suite: complex Schur decomposition (+ optional reordering) used by
 // the Krylov-Schur eigensolver.  H: n x n column-major complex (interleaved), overwritten by T; Z: n x n Schur vectors.
 int32_t mpsk_host_schur(int32_t n, double* H, double* Z, int32_t move_from, int32_t move_to) {
@@ -609,6 +639,32 @@ int32_t mpsk_tsvd_spectrum(mpsk_ctx* ctx, int32_t* nsec, int32_t* charge, int32_
   if (nsec) *nsec = (int32_t)sp.charge.size();
   for (size_t i = 0; i < sp.charge.size(); ++i) { if (charge) charge[i] = sp.charge[i]; if (count) count[i] = sp.count[i]; if (kept) kept[i] = sp.kept[i]; }
   if (values) std::copy(sp.values.begin(), sp.values.end(), values);
+  return MPSK_OK;
+}
+
+int32_t mpsk_leftnull(mpsk_ctx* ctx, const mpsk_tensor* A, mpsk_tensor** out) { ENTER(ctx);
+  Tensor* o = nullptr;
+  MPSK_TRY(nullspace(CTX(ctx), CTEN(A), true, &o));
+  *out = reinterpret_cast<mpsk_tensor*>(o);
+  return MPSK_OK;
+}
+int32_t mpsk_rightnull(mpsk_ctx* ctx, const mpsk_tensor* A, mpsk_tensor** out) { ENTER(ctx);
+  Tensor* o = nullptr;
+  MPSK_TRY(nullspace(CTX(ctx), CTEN(A), false, &o));
+  *out = reinterpret_cast<mpsk_tensor*>(o);
+  return MPSK_OK;
+}
+int32_t mpsk_contract_adjoint_left(mpsk_ctx* ctx, const mpsk_tensor* N, const mpsk_tensor* x2, mpsk_tensor** out) { ENTER(ctx);
+  Tensor* o = nullptr;
+  MPSK_TRY(contract_adjoint_left(CTX(ctx), CTEN(N), CTEN(x2), &o));
+  *out = reinterpret_cast<mpsk_tensor*>(o);
+  return MPSK_OK;
+}
+int32_t mpsk_tensor_cat(mpsk_ctx* ctx, const mpsk_tensor* A, const mpsk_tensor* B, int32_t axis, mpsk_tensor** out) { ENTER(ctx);
+  if (axis != 0 && axis != 1) return CTX(ctx)->fail(MPSK_EINVAL, "axis must be 0 or 1");
+  Tensor* o = nullptr;
+  MPSK_TRY(tensor_cat(CTX(ctx), CTEN(A), CTEN(B), axis, &o));
+  *out = reinterpret_cast<mpsk_tensor*>(o);
   return MPSK_OK;
 }
 

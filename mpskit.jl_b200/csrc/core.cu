@@ -11,38 +11,37 @@ int Ctx::fail(int code, const char* fmt, ...) {
   return code;
 }
 
-static size_t round_size(size_t b) {
-  if (b < 512) return 512;
-  return (b + 511) / 512 * 512;
-}
-
-// Device memory comes from CUDA's stream-ordered pool (cudaMallocAsync on the context stream, release threshold = never):
-// the pool splits and coalesces blocks, so the multi-GB workspaces of a sweep (GEMM intermediates, Krylov bases, SVD
-// arenas, environments -- all with sizes that drift from site to site) are recycled without ever going back to
-// cudaMalloc / cudaFree.  (Round 1's exact-size free list missed on drifting sizes, grew, and was trimmed with
-// device-wide cudaFree storms: 0.15 s per centre update.)  Memory is used on the context stream, or on the factorisation
-// pool's streams strictly between synchronisations of the context stream.
-void* Ctx::alloc(size_t bytes) {
-  const size_t sz = round_size(bytes);
+static void* cuda_chunk_alloc(size_t bytes) {
   void* p = nullptr;
-  cudaError_t e = cudaMallocAsync(&p, sz, stream);
-  if (e != cudaSuccess) {
-    cudaGetLastError();
-    release_cache();
-    e = cudaMallocAsync(&p, sz, stream);
-    if (e != cudaSuccess) { cudaGetLastError(); fail(MPSK_ENOMEM, "cudaMallocAsync(%zu) failed", sz); return nullptr; }
+  if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+static void cuda_chunk_free(void* p) { cudaFree(p); }
+
+// Device memory of a context: see devalloc.h.  Chunks of 8 GB (or the request, if larger) come from cudaMalloc; in steady
+// state no driver call is made.
+void* Ctx::alloc(size_t bytes) {
+  if (!dev.chunk_alloc) { dev.chunk_alloc = cuda_chunk_alloc; dev.chunk_free = cuda_chunk_free; }
+  void* p = dev.alloc(bytes);
+  if (!p) {
+    cudaStreamSynchronize(stream);
+    dev.trim();
+    p = dev.alloc(bytes);
+    if (!p) { fail(MPSK_ENOMEM, "device allocation of %zu bytes failed (%zu live, %zu reserved)", bytes, dev.bytes_live, dev.bytes_reserved); return nullptr; }
   }
-  sizes[p] = sz; bytes_in_use += sz;
+  bytes_in_use = (int64_t)dev.bytes_live;
   return p;
 }
 
 void Ctx::free(void* p) {
   if (!p) return;
-  auto it = sizes.find(p);
-  if (it == sizes.end()) return;
-  bytes_in_use -= it->second;
-  sizes.erase(it);
-  cudaFreeAsync(p, stream);
+  dev.free(p);
+  bytes_in_use = (int64_t)dev.bytes_live;
+}
+
+void Ctx::release_cache() {
+  cudaStreamSynchronize(stream);
+  dev.trim();
 }
 
 void* Ctx::lease(int slot, size_t bytes, bool* leased) {
@@ -66,11 +65,6 @@ void Ctx::unlease(int slot, void* p, bool leased) {
   else free(p);
 }
 
-void Ctx::release_cache() {
-  cudaStreamSynchronize(stream);
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
-}
 
 // pinned bump arena (see internal.h): memory handed out stays valid until the arena wraps, and wrapping synchronises
 // the stream first, so asynchronous H2D copies out of it never read recycled bytes

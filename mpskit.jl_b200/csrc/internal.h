@@ -17,6 +17,7 @@
 #include <vector>
 #include "../../include/mpskit_b200.h"
 #include "gemm.cuh"
+#include "devalloc.h"
 
 namespace mpsk {
 
@@ -45,8 +46,8 @@ struct Ctx {
   int num_sms = 148;
   std::string err;
   int64_t launches = 0;
-  // stream-ordered allocator: CUDA's memory pool (cudaMallocAsync / cudaFreeAsync on the context stream)
-  std::unordered_map<void*, size_t> sizes;
+  // device memory: chunked best-fit allocator with coalescing (devalloc.h); stream-ordered use on the context stream
+  BlockAllocator dev;
   int64_t bytes_in_use = 0;
   void* cusolver = nullptr;     // cusolverDnHandle_t, created lazily
   void* pool_stream[4] = {nullptr, nullptr, nullptr, nullptr};   // worker streams / cuSOLVER handles of the factorisation pool
@@ -356,6 +357,9 @@ int tsvd(Ctx* ctx, const Tensor* ac2, int d1, const int32_t* p1_charge, mpsk_tru
 int qrpos(Ctx* ctx, const Tensor* A, bool left, Tensor** Q, Tensor** R);
 void pool_destroy(Ctx* ctx);
 int bond_inverse(Ctx* ctx, const Tensor* C, Tensor** out);
+int nullspace(Ctx* ctx, const Tensor* A, bool left, Tensor** out);
+int contract_adjoint_left(Ctx* ctx, const Tensor* N, const Tensor* x2, Tensor** out);
+int tensor_cat(Ctx* ctx, const Tensor* A, const Tensor* B, int axis, Tensor** out);
 int comm_allreduce_sum(Ctx* ctx, void* buf, size_t ndoubles);
 
 }  // namespace mpsk

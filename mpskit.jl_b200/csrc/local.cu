@@ -402,6 +402,89 @@ int contract_ac2(Ctx* ctx, const Tensor* A1, const Tensor* A2, Tensor** out) {
   return MPSK_OK;
 }
 
+// B[k' p2; r] = sum_{l, p1} conj(N[l p1; k']) x2[l (p1 p2); r]: the adjoint of contract_ac2 in its first factor
+// (adjoint(VL) * AC2 of changebonds/optimalexpand.jl:30,98).  One K-stacked GEMM per output block: N (conjugated) and the
+// p2-slice of x2 in SL form share the K layout (segments (p1, l-sector)).
+int contract_adjoint_left(Ctx* ctx, const Tensor* N, const Tensor* x2, Tensor** out) {
+  if (N->dtype != x2->dtype) return ctx->fail(MPSK_EINVAL, "mixed scalar types");
+  if (!(N->Vl == x2->Vl)) return ctx->fail(MPSK_ESPACE, "contract_adjoint_left: left bonds differ");
+  const int d1 = N->nm();
+  if (d1 <= 0 || x2->nm() % d1) return ctx->fail(MPSK_ESPACE, "contract_adjoint_left: label counts do not match");
+  const int d2 = x2->nm() / d1;
+  const bool cx = N->dtype == MPSK_C128;
+  std::vector<int32_t> s2(d2);
+  for (int t = 0; t < d2; ++t) s2[t] = x2->mch[t] - N->mch[0];
+  for (int u = 0; u < d1; ++u) for (int t = 0; t < d2; ++t)
+    if (x2->mch[u * d2 + t] != N->mch[u] + s2[t]) return ctx->fail(MPSK_ESPACE, "contract_adjoint_left: label charges do not factorise");
+  Tensor* o = nullptr;
+  MPSK_TRY(tensor_create(ctx, N->Vr, s2, x2->Vr, N->dtype, F_KL, true, &o));
+  std::unique_ptr<Tensor> og(o);
+  Tensor* Ns = nullptr;
+  MPSK_TRY(tensor_repack(ctx, N, F_SL, true, &Ns));
+  std::unique_ptr<Tensor> nsg(Ns);
+  std::vector<std::unique_ptr<Tensor>> keep;
+  std::vector<GemmProblemHost> pr;
+  for (int t = 0; t < d2; ++t) {
+    std::vector<int32_t> lab(d1);
+    for (int u = 0; u < d1; ++u) lab[u] = u * d2 + t;
+    Tensor* Xp = nullptr; Tensor* Xs = nullptr;
+    MPSK_TRY(tensor_select_labels(ctx, x2, lab.data(), d1, &Xp));
+    std::unique_ptr<Tensor> xpg(Xp);
+    MPSK_TRY(tensor_repack(ctx, Xp, F_SL, false, &Xs));
+    keep.emplace_back(Xs);
+    for (int jk = 0; jk < o->Vl.nsec(); ++jk) {
+      const Blk* b = o->find(t, jk);
+      if (!b) continue;
+      const Group& gN = Ns->groups[jk]; const Group& gX = Xs->groups[b->jr];
+      if (gN.cols == 0 || gX.cols == 0) continue;
+      if (gN.cols != gX.cols) return ctx->fail(MPSK_EINTERNAL, "contract_adjoint_left: K layouts differ");
+      pr.push_back(GemmProblemHost{Xs->ptr(gX.off), Ns->ptr(gN.off), o->ptr(b->off), gX.ld, gN.ld, o->groups[jk].ld,
+                                   (int32_t)gX.rows, (int32_t)gN.rows, (int32_t)gN.cols, 0});
+    }
+  }
+  GemmPlan g;
+  MPSK_TRY(gemm_plan_build(ctx, cx, pr, &g));
+  MPSK_TRY(gemm_plan_run(ctx, &g));
+  *out = og.release();
+  return MPSK_OK;
+}
+
+// direct sum along the left (axis 0) or right (axis 1) bond: catcodomain / catdomain of TensorKit
+// (changebonds/optimalexpand.jl:103-104, changebonds.jl:17-32).  B may be NULL with `extra` giving a space to pad with zeros.
+int tensor_cat(Ctx* ctx, const Tensor* A, const Tensor* B, int axis, Tensor** out) {
+  if (A->dtype != B->dtype || A->mch != B->mch) return ctx->fail(MPSK_ESPACE, "cat: labels / scalar types differ");
+  if (axis == 0 ? !(A->Vr == B->Vr) : !(A->Vl == B->Vl)) return ctx->fail(MPSK_ESPACE, "cat: the other bond differs");
+  const Space& Sa = axis == 0 ? A->Vl : A->Vr; const Space& Sb = axis == 0 ? B->Vl : B->Vr;
+  if (Sa.mod != Sb.mod) return ctx->fail(MPSK_ESPACE, "cat: different groups");
+  std::map<int32_t, int64_t> dims;
+  for (int j = 0; j < Sa.nsec(); ++j) dims[Sa.q[j]] += Sa.n[j];
+  for (int j = 0; j < Sb.nsec(); ++j) dims[Sb.q[j]] += Sb.n[j];
+  Space Sn; Sn.mod = Sa.mod;
+  for (auto& kv : dims) { Sn.q.push_back(kv.first); Sn.n.push_back(kv.second); }
+  Tensor* o = nullptr;
+  if (axis == 0) MPSK_TRY(tensor_create(ctx, Sn, A->mch, A->Vr, A->dtype, F_KL, true, &o));
+  else MPSK_TRY(tensor_create(ctx, A->Vl, A->mch, Sn, A->dtype, F_KL, true, &o));
+  std::unique_ptr<Tensor> og(o);
+  std::vector<CopyTask> tasks;
+  for (int which = 0; which < 2; ++which) {
+    const Tensor* T = which ? B : A;
+    const Space& St = axis == 0 ? T->Vl : T->Vr;
+    for (const Blk& b : T->blks) {
+      const int js = axis == 0 ? b.jl : b.jr;
+      const int jn = Sn.find(St.q[js]);
+      int64_t shift = 0;
+      if (which) { const int ja = Sa.find(St.q[js]); shift = ja >= 0 ? Sa.n[ja] : 0; }
+      const Blk* d = axis == 0 ? o->find(b.m, jn) : o->find(b.m, b.jl);
+      if (!d || (axis == 1 && d->jr != jn)) return ctx->fail(MPSK_EINTERNAL, "cat: output block mismatch");
+      char* dst = o->ptr(d->off + shift * (axis == 0 ? d->sl : d->sr));
+      tasks.push_back(CopyTask{T->ptr(b.off), dst, b.sl, b.sr, d->sl, d->sr, (int32_t)T->Vl.n[b.jl], (int32_t)T->Vr.n[b.jr], 0, 0, nullptr});
+    }
+  }
+  MPSK_TRY(run_copy_tasks(ctx, tasks, A->dtype == MPSK_C128));
+  *out = og.release();
+  return MPSK_OK;
+}
+
 // A'[l p r'] = sum_r A[l p r] C[r r']
 int mul_bond_right(Ctx* ctx, const Tensor* A, const Tensor* C, Tensor** out) {
   if (A->dtype != C->dtype) return ctx->fail(MPSK_EINVAL, "mixed scalar types");

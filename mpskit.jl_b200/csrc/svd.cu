@@ -710,6 +710,100 @@ int bond_inverse(Ctx* ctx, const Tensor* C, Tensor** out) {
   return MPSK_OK;
 }
 
+// ------------------------------------------------------------------------------------------ leftnull / rightnull
+// leftnull(A) (left = true): isometry N[l m; k'] spanning the orthogonal complement of the range of A[l m; r];
+// rightnull(A) (left = false): N[k' m; r] with orthonormal rows spanning the complement of the row space of A[l; m r]
+// (changebonds/optimalexpand.jl:28-29,95-96).  Per coupled sector a full Householder QR (cuSOLVER geqrf + ungqr generating
+// all M columns); coupled sectors of the fused (bond x label) space that are absent from the other bond are null entirely.
+int nullspace(Ctx* ctx, const Tensor* A, bool left, Tensor** out) {
+  const bool cx = A->dtype == MPSK_C128;
+  const size_t es = cx ? 16 : 8;
+  const Space& Vg = left ? A->Vr : A->Vl;       // the bond the factorisation removes (columns)
+  const Space& Vo = left ? A->Vl : A->Vr;       // the bond that stays (fused with the labels into the rows)
+  struct Row { int m, jo; int64_t off; };
+  struct Sec { int64_t Q = 0; std::vector<Row> rows; int64_t M = 0, n = 0, k = 0; int jg = -1; void* W = nullptr; void* tau = nullptr; };
+  std::map<int64_t, Sec> smap;
+  for (int mm = 0; mm < A->nm(); ++mm)
+    for (int jo = 0; jo < Vo.nsec(); ++jo) {
+      const int64_t Q = Vo.norm(left ? (int64_t)Vo.q[jo] + A->mch[mm] : (int64_t)Vo.q[jo] - A->mch[mm]);
+      Sec& sc = smap[Q]; sc.Q = Q;
+      sc.rows.push_back(Row{mm, jo, sc.M}); sc.M += Vo.n[jo];
+    }
+  Space Vn; Vn.mod = Vg.mod;
+  std::vector<Sec*> secs;
+  for (auto& kv : smap) {
+    Sec& sc = kv.second;
+    sc.jg = Vg.find(sc.Q); sc.n = sc.jg >= 0 ? Vg.n[sc.jg] : 0; sc.k = std::min(sc.M, sc.n);
+    if (sc.M - sc.k > 0) { Vn.q.push_back((int32_t)sc.Q); Vn.n.push_back(sc.M - sc.k); secs.push_back(&sc); }
+  }
+  Tensor* N = nullptr;
+  if (left) MPSK_TRY(tensor_create(ctx, A->Vl, A->mch, Vn, A->dtype, F_KL, true, &N));
+  else MPSK_TRY(tensor_create(ctx, Vn, A->mch, A->Vr, A->dtype, F_KL, true, &N));
+  std::unique_ptr<Tensor> ng(N);
+  struct Cleanup { Ctx* c; std::vector<Sec*>* v; ~Cleanup() { for (Sec* sc : *v) { c->free(sc->W); c->free(sc->tau); } } } cl{ctx, &secs};
+  cusolverDnHandle_t hs;
+  MPSK_TRY(get_cusolver(ctx, &hs));
+  int* d_info = (int*)ctx->alloc(sizeof(int));
+  if (!d_info) return MPSK_ENOMEM;
+  struct InfoFree { Ctx* c; void* p; ~InfoFree() { c->free(p); } } inf{ctx, d_info};
+  std::vector<CopyTask> outt;
+  for (Sec* sp : secs) {
+    Sec& sc = *sp;
+    const int M = (int)sc.M, n = (int)sc.n, k = (int)sc.k;
+    sc.W = ctx->alloc((size_t)M * M * es); sc.tau = ctx->alloc((size_t)std::max(k, 1) * es);
+    if (!sc.W || !sc.tau) return MPSK_ENOMEM;
+    if (n == 0) {
+      eye_kernel<<<std::min((int)(((int64_t)M * M + 255) / 256), 4096), 256, 0, ctx->stream>>>((double*)sc.W, M, M, cx ? 1 : 0);
+    } else {
+      CUDA_TRY(ctx, cudaMemsetAsync(sc.W, 0, (size_t)M * M * es, ctx->stream));
+      std::vector<CopyTask> in;
+      for (const Row& rw : sc.rows) {
+        const Blk* b = left ? A->find(rw.m, rw.jo) : A->find(rw.m, sc.jg);
+        if (!b) return ctx->fail(MPSK_EINTERNAL, "nullspace: missing block");
+        CopyTask tk; tk.src = A->ptr(b->off); tk.ssl = b->sl; tk.ssr = b->sr; tk.nl = (int32_t)A->Vl.n[b->jl]; tk.nr = (int32_t)A->Vr.n[b->jr];
+        tk.scale_axis = 0; tk.scale = nullptr; tk.dst = (char*)sc.W + rw.off * es;
+        if (left) { tk.dsl = 1; tk.dsr = M; tk.conj = 0; } else { tk.dsl = M; tk.dsr = 1; tk.conj = cx ? 1 : 0; }
+        in.push_back(tk);
+      }
+      MPSK_TRY(run_copy_tasks(ctx, in, cx));
+      int lw1 = 0, lw2 = 0;
+      if (cx) { CUSOLVER_TRY(ctx, cusolverDnZgeqrf_bufferSize(hs, M, n, (cuDoubleComplex*)sc.W, M, &lw1));
+                CUSOLVER_TRY(ctx, cusolverDnZungqr_bufferSize(hs, M, M, k, (cuDoubleComplex*)sc.W, M, (cuDoubleComplex*)sc.tau, &lw2)); }
+      else { CUSOLVER_TRY(ctx, cusolverDnDgeqrf_bufferSize(hs, M, n, (double*)sc.W, M, &lw1));
+             CUSOLVER_TRY(ctx, cusolverDnDorgqr_bufferSize(hs, M, M, k, (double*)sc.W, M, (double*)sc.tau, &lw2)); }
+      const int lw = std::max(std::max(lw1, lw2), 1);
+      void* work = ctx->alloc((size_t)lw * es);
+      if (!work) return MPSK_ENOMEM;
+      if (cx) { CUSOLVER_TRY(ctx, cusolverDnZgeqrf(hs, M, n, (cuDoubleComplex*)sc.W, M, (cuDoubleComplex*)sc.tau, (cuDoubleComplex*)work, lw, d_info));
+                CUSOLVER_TRY(ctx, cusolverDnZungqr(hs, M, M, k, (cuDoubleComplex*)sc.W, M, (cuDoubleComplex*)sc.tau, (cuDoubleComplex*)work, lw, d_info)); }
+      else { CUSOLVER_TRY(ctx, cusolverDnDgeqrf(hs, M, n, (double*)sc.W, M, (double*)sc.tau, (double*)work, lw, d_info));
+             CUSOLVER_TRY(ctx, cusolverDnDorgqr(hs, M, M, k, (double*)sc.W, M, (double*)sc.tau, (double*)work, lw, d_info)); }
+      ctx->free(work);
+      ctx->launches += 2;
+    }
+    const int jn = Vn.find(sc.Q);
+    const int nd = M - k;
+    for (const Row& rw : sc.rows) {
+      CopyTask tk; tk.scale_axis = 0; tk.scale = nullptr;
+      tk.src = (char*)sc.W + (rw.off + (int64_t)k * M) * es;          // W(rw.off + i, k + c)
+      if (left) {
+        const Blk* b = N->find(rw.m, rw.jo);
+        if (!b || b->jr != jn) return ctx->fail(MPSK_EINTERNAL, "leftnull: output block mismatch");
+        tk.dst = N->ptr(b->off); tk.dsl = b->sl; tk.dsr = b->sr; tk.nl = (int32_t)Vo.n[rw.jo]; tk.nr = nd; tk.ssl = 1; tk.ssr = M; tk.conj = 0;
+      } else {
+        const Blk* b = N->find(rw.m, jn);
+        if (!b || b->jr != rw.jo) return ctx->fail(MPSK_EINTERNAL, "rightnull: output block mismatch");
+        tk.dst = N->ptr(b->off); tk.dsl = b->sl; tk.dsr = b->sr; tk.nl = nd; tk.nr = (int32_t)Vo.n[rw.jo]; tk.ssl = M; tk.ssr = 1; tk.conj = cx ? 1 : 0;
+      }
+      outt.push_back(tk);
+    }
+  }
+  MPSK_TRY(run_copy_tasks(ctx, outt, cx));
+  CUDA_TRY(ctx, cudaGetLastError());
+  *out = ng.release();
+  return MPSK_OK;
+}
+
 // ------------------------------------------------------------------------------------------ QRpos / LQpos
 // leftorth!(A; alg=QRpos()) and rightorth!(A; alg=LQpos()) (orthoview.jl:49-60, ortho.jl:127-138, finitemps.jl:150):
 // per coupled sector one Householder QR (cuSOLVER geqrf/ungqr: LAPACK-class library call as in the reference), then

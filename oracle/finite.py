@@ -455,3 +455,63 @@ def approximate(psi: FiniteMPS, O, above: FiniteMPS, nsweeps=1, trunc=("truncerr
         if eps < tol:
             break
     return psi, envs, eps
+
+
+def _null_blocks(M, rowq, colq):
+    """orthonormal basis N (rows x nnull, with a charge per column) of the orthogonal complement of range(M), sector by sector"""
+    cols, charges = [], []
+    for q in sorted(set(rowq.tolist())):
+        ri = np.nonzero(rowq == q)[0]
+        ci = np.nonzero(colq == q)[0]
+        if len(ci) == 0:
+            basis = np.eye(len(ri), dtype=np.complex128)
+        else:
+            Qf = np.linalg.qr(M[np.ix_(ri, ci)], mode="complete")[0]
+            basis = Qf[:, min(len(ri), len(ci)):]
+        for k in range(basis.shape[1]):
+            v = np.zeros(M.shape[0], dtype=np.complex128); v[ri] = basis[:, k]
+            cols.append(v); charges.append(q)
+    N = np.stack(cols, axis=1) if cols else np.zeros((M.shape[0], 0), dtype=np.complex128)
+    return N, np.asarray(charges, dtype=np.int64)
+
+
+def optimal_expand(psi: FiniteMPS, H, trunc=("truncdim", 1), envs=None, log=None):
+    """changebonds!(psi::FiniteMPS, H, OptimalExpand(trscheme)) (src/algorithms/changebonds/optimalexpand.jl:84-110)"""
+    from .spaces import Space
+    envs = envs or FinEnv(psi, H)
+    L, pq, mod = psi.L, psi.pq, psi.p.modulus
+    d = len(pq)
+    for i in range(L - 1):
+        AC, AR = psi.get_AC(i), psi.get_AR(i + 1)
+        Vl, Vk, Vr = psi.V[i], psi.V[i + 1], psi.V[i + 2]
+        Dl, Dk, Dr = Vl.dim, Vk.dim, Vr.dim
+        rowq = (Vl.index_charges()[:, None] + pq[None, :]).reshape(-1)             # (l, p1)
+        colq = (pq[:, None] * -1 + Vr.index_charges()[None, :]).reshape(-1)        # (p2, r): charge of the k index q_r - s_p2
+        NL, nlq = _null_blocks(AC.reshape(Dl * d, Dk), rowq, Vk.index_charges())
+        NRh, nrq = _null_blocks(AR.reshape(Dk, d * Dr).conj().T, colq, Vk.index_charges())     # columns of NR^H
+        if NL.shape[1] == 0 or NRh.shape[1] == 0:
+            continue
+        ac2 = np.einsum('apk,kqr->aprq', AC, AR)
+        AC2 = dAC2_sparse(ac2, H[i], H[i + 1], envs.leftenv(i, psi), envs.rightenv(i + 1, psi))
+        Mat = AC2.transpose(0, 1, 3, 2).reshape(Dl * d, d * Dr)                    # (l p1) x (p2 r)
+        inter = NL.conj().T @ Mat @ NRh                                           # adjoint(NL) * AC2 * adjoint(NR)
+        U, S, Vh, newV, eps, info = tsvd(inter, nlq, nrq, trunc, mod)
+        if log is not None:
+            log.append(dict(pos=i, added=newV.as_dict(), spectrum={q: s.copy() for q, s in info["spectrum"].items()}))
+        ar_re = (Vh @ NRh.conj().T).reshape(newV.dim, d, Dr)                       # V * NR: [n p; r]
+        # direct sums, sector by sector (old indices first inside every sector)
+        both = Space.from_dict({q: Vk.as_dict().get(q, 0) + newV.as_dict().get(q, 0) for q in set(Vk.charges) | set(newV.charges)}, mod)
+        idx_old, idx_new = [], []
+        off = 0
+        for q, n in zip(both.charges, both.dims):
+            no = Vk.as_dict().get(q, 0)
+            idx_old += list(range(off, off + no)); idx_new += list(range(off + no, off + n)); off += n
+        ACp = np.zeros((Dl, d, both.dim), dtype=np.complex128); ACp[:, :, idx_old] = AC
+        ARp = np.zeros((both.dim, d, Dr), dtype=np.complex128); ARp[idx_old] = AR; ARp[idx_new] = ar_re
+        Q, R, nV = qrpos(ACp.reshape(Dl * d, both.dim), rowq, both.index_charges(), mod)
+        nal = Q.reshape(Dl, d, nV.dim)
+        # new bond space of the QR can be smaller than `both` only if a sector is rank deficient; keep R rectangular then
+        assert nV.dim == both.dim, "rank-deficient expansion"
+        psi.set_AC_alc(i, nal, R, nV)
+        psi.set_AC_car(i + 1, R, ARp, nV)
+    return psi, envs

@@ -179,3 +179,12 @@ def test_host_schur_and_reordering_against_numpy():
             assert np.abs(np.tril(H2, -1)).max() == 0.0
             # first Schur vector = eigenvector of the leading eigenvalue
             assert np.linalg.norm(A @ Z2[:, 0] - H2[0, 0] * Z2[:, 0]) <= 1e-11 * n
+
+
+def test_device_allocator_free_list_logic_on_host():
+    """devalloc.h (split / coalesce / trim) under random traffic with malloc as the backend: no overlap of live blocks,
+    free blocks disjoint and merged, live + free == reserved after every operation, everything returned at the end."""
+    import mpskit_b200 as m
+    lib = m.load_library()
+    for seed in (1, 2, 3, 4):
+        assert lib.mpsk_host_alloc_selftest(seed, 15000) == 0

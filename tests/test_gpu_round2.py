@@ -444,3 +444,48 @@ def test_idmrg2_device(ctx):
     Cm = st_d.CR[0]
     prod = di.mul_right(Cm, di.bond_inverse(Cm)).to_dense()[:, 0, :]
     assert np.abs(prod - np.eye(prod.shape[0])).max() <= 1e-10
+
+
+def test_optimal_expand_finite(ctx):
+    """changebonds(psi, H, OptimalExpand(truncdim(2))) (changebonds/optimalexpand.jl:84-110): device leftnull / rightnull,
+    adjoint contractions, tsvd of the projected two-site tensor, direct sums and QRpos.  The state is unchanged, the bond
+    spaces grow exactly as in the oracle, the (gauge-invariant) singular values of the projected tensor agree, and a
+    subsequent single-site DMRG reaches the same lower energy as in the oracle."""
+    L = 8
+    Ho = ompo.heisenberg_u1(L)
+    po = OSpace((-1, 1), (1, 1))
+    maxV = [of.gaussian_bond_space(4, k % 2) for k in range(1, L)]
+    psi_o = of.FiniteMPS.random(np.random.default_rng(1), po, L, maxV)
+    of.dmrg_sweeps(psi_o, Ho, nsweeps=2, tol=1e-13)
+    log_o = []
+    psi_o, envs_o = of.optimal_expand(psi_o, Ho, ("truncdim", 2), log=log_o)
+    lo = []
+    of.dmrg_sweeps(psi_o, Ho, nsweeps=2, tol=1e-13, log=lo)
+    Hd = dev_hamiltonian(Ho)
+    psi_d = m.FiniteMPS.random(np.random.default_rng(1), to_dev_space(po), L, [to_dev_space(v) for v in maxV], ctx)
+    psi_d, envs, _ = m.find_groundstate(psi_d, Hd, m.DMRG(tol=1e-13, maxiter=2, eigalg=m.Lanczos(tol=1e-13)))
+    v0 = _full_state(psi_d)
+    # null spaces on their own: isometries orthogonal to the tensor
+    AC = psi_d.AC[3]
+    NL = m.leftnull(AC)
+    A = AC.to_dense().reshape(-1, AC.Vr.dim); N = NL.to_dense().reshape(-1, NL.Vr.dim)
+    assert N.shape[1] == A.shape[0] - A.shape[1] - 0 or N.shape[1] > 0
+    assert np.abs(N.conj().T @ N - np.eye(N.shape[1])).max() <= 1e-12 and np.abs(N.conj().T @ A).max() <= 1e-12
+    AR = psi_d.AR[4]
+    NR = m.rightnull(AR)
+    B = AR.to_dense().reshape(AR.Vl.dim, -1); Nr = NR.to_dense().reshape(NR.Vl.dim, -1)
+    assert np.abs(Nr @ Nr.conj().T - np.eye(Nr.shape[0])).max() <= 1e-12 and np.abs(B @ Nr.conj().T).max() <= 1e-12
+    log_d = []
+    psi_d, envs = m.changebonds(psi_d, Hd, m.OptimalExpand(trscheme=m.truncdim(2)), envs, log=log_d)
+    v1 = _full_state(psi_d)
+    assert abs(abs(np.vdot(v0, v1)) / np.linalg.norm(v0) / np.linalg.norm(v1) - 1) <= 1e-12       # the state is unchanged
+    assert [psi_d.V[i].as_dict() for i in range(L + 1)] == [psi_o.V[i].as_dict() for i in range(L + 1)]     # bit-exact bond spaces
+    assert len(log_d) == len(log_o)
+    for a, b in zip(log_d, log_o):
+        assert a["pos"] == b["pos"] and a["added"] == b["added"]
+        for q, s_o in b["spectrum"].items():
+            assert np.abs(a["spectrum"][q] - s_o).max() <= 1e-9
+    ld = []
+    psi_d, envs, _ = m.find_groundstate(psi_d, Hd, m.DMRG(tol=1e-13, maxiter=2, eigalg=m.Lanczos(tol=1e-13)), log=ld)
+    print("optimal expand", ld[-1]["energy"], lo[-1]["energy"], [psi_d.V[i].dim for i in range(L + 1)])
+    assert abs(ld[-1]["energy"] - lo[-1]["energy"]) <= 1e-9 * abs(lo[-1]["energy"])
