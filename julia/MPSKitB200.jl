@@ -324,6 +324,33 @@ function device_tsvd(ac2::MPOTensor, trunc)
     return al, c, ar, eps[]
 end
 
+# Handle-level wrappers of the entries the bond-changing algorithms use (changebonds/optimalexpand.jl:26-28,84-95 and the
+# edge updates of IDMRG2, idmrg.jl:126,139,168,174): unary / binary device operations returning a new handle.
+function unary(sym::Symbol, a::Handle)
+    out = Ref{Ptr{Cvoid}}()
+    check(ccall((sym, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), CTX[], a.p, out))
+    return Handle(out[])
+end
+device_leftnull(a::Handle) = unary(:mpsk_leftnull, a)                      # leftnull(AL)
+device_rightnull(a::Handle) = unary(:mpsk_rightnull, a)                    # rightnull!(_transpose_tail(AR))
+device_inv(c::Handle) = unary(:mpsk_bond_inverse, c)                       # inv(ψ.CR[i])
+device_adjoint(a::Handle) = unary(:mpsk_tensor_adjoint, a)
+function device_adjoint_left(n::Handle, x2::Handle)                        # adjoint(VL) * AC2
+    out = Ref{Ptr{Cvoid}}()
+    check(ccall((:mpsk_contract_adjoint_left, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), CTX[], n.p, x2.p, out))
+    return Handle(out[])
+end
+function device_cat(a::Handle, b::Handle, axis::Integer)                   # catcodomain (axis 0) / catdomain (axis 1)
+    out = Ref{Ptr{Cvoid}}()
+    check(ccall((:mpsk_tensor_cat, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ref{Ptr{Cvoid}}), CTX[], a.p, b.p, axis, out))
+    return Handle(out[])
+end
+function TensorKit.leftnull(A::MPSTensor{<:GradedSpace{U1Irrep}})
+    h = device_leftnull(resident(A))
+    N = TensorMap(undef, scalartype(A), codomain(A), device_space(h, :right))
+    return download!(N, h)
+end
+
 # Whole sweeps can stay on the device (state, environments and Krylov basis resident between calls): the sweep body of
 # dmrg.jl:80-137 with the calls above on handles is exactly mpskit.jl_b200/dmrg.py (find_groundstate_inplace); a Julia
 # `find_groundstate!(ψ::FiniteMPS, H::MPOHamiltonian, alg::DMRG2, envs)` method built from `device_op`, `device_eigsolve`,
