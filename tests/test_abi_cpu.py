@@ -188,3 +188,27 @@ def test_device_allocator_free_list_logic_on_host():
     lib = m.load_library()
     for seed in (1, 2, 3, 4):
         assert lib.mpsk_host_alloc_selftest(seed, 15000) == 0
+
+
+def test_state_file_pack_unpack_roundtrip(tmp_path):
+    """serialize.py host halves: a block tensor written in ABI block order and read back through np.savez is bit-identical,
+    and a truncated data vector is rejected."""
+    import mpskit_b200 as m
+    rng = np.random.default_rng(5)
+    Vl, Vr = m.Space((-2, 0, 2), (3, 5, 2)), m.Space((-3, -1, 1, 3), (2, 4, 4, 1))
+    mch = [-1, 1]
+    table = m.block_table(Vl, mch, Vr)
+    blocks = {(mm, jl): rng.standard_normal((Vl.dims[jl], Vr.dims[jr])) + 1j * rng.standard_normal((Vl.dims[jl], Vr.dims[jr]))
+              for (mm, jl, jr) in table}
+    store = {}
+    m.pack_tensor("AL/0", Vl, mch, Vr, np.complex128, blocks, table, store)
+    np.savez(tmp_path / "t.npz", **store)
+    with np.load(tmp_path / "t.npz") as st:
+        Vl2, mch2, Vr2, dt, b2 = m.unpack_tensor("AL/0", st, m.block_table)
+        assert (Vl2.charges, Vl2.dims, Vr2.charges, Vr2.dims, mch2) == (Vl.charges, Vl.dims, Vr.charges, Vr.dims, mch)
+        assert dt == np.complex128 and set(b2) == set(blocks)
+        assert all(np.array_equal(b2[k], blocks[k]) for k in blocks)
+        bad = {k: st[k] for k in st.files}
+    bad["AL/0/data"] = bad["AL/0/data"][:-1]
+    with pytest.raises(ValueError):
+        m.unpack_tensor("AL/0", bad, m.block_table)
