@@ -34,6 +34,7 @@ typedef struct mpsk_ctx mpsk_ctx;
 typedef struct mpsk_tensor mpsk_tensor;
 typedef struct mpsk_mposlice mpsk_mposlice;
 typedef struct mpsk_op mpsk_op;
+typedef struct mpsk_matvec_stream mpsk_matvec_stream;
 
 typedef enum {
   MPSK_OK = 0,
@@ -218,6 +219,21 @@ int32_t mpsk_tensor_panel(mpsk_ctx* ctx, const mpsk_tensor* t, int32_t axis, int
  * With a communicator, mpsk_transfer_left/right shard the update over the ket index of the new environment and mpsk_tsvd
  * distributes the coupled sectors over the ranks; both return complete, bit-identical tensors on every rank. */
 int32_t mpsk_tensor_allgather(mpsk_ctx* ctx, const mpsk_tensor* panel, mpsk_tensor* full);
+
+/* Streamed matvecs on HOST buffers: y_i = op(x_i) for a sequence of independent vectors whose blocks live in (pinned) host
+ * memory -- the host-buffer form of `(h::MPO_∂∂AC2)(x)` (derivatives.jl:26-31,119-154) for callers that keep their vectors on
+ * the host (block Krylov methods, `map(h, xs)`).  The H2D copy of x_{i+1}, the matvec of x_i and the D2H copy of y_{i-1} overlap
+ * (two copy streams + the context stream, `depth` device slots).  x_like / y_like give the block structures (row panels with a
+ * communicator: the semantics of mpsk_op_apply_panel).  Blocks must be contiguous, all row-major (host_layout 0, numpy) or all
+ * column-major (host_layout 1, TensorKit).  submit returns as soon as the work is enqueued and blocks only while `depth`
+ * submissions are in flight; a y buffer may be read after the `depth`-th following submit or after wait; an x buffer may be
+ * overwritten under the same rule. */
+int32_t mpsk_matvec_stream_create(mpsk_ctx* ctx, const mpsk_op* op, const mpsk_tensor* x_like, const mpsk_tensor* y_like, int32_t depth,
+                                  int32_t host_layout, mpsk_matvec_stream** out);
+int32_t mpsk_matvec_stream_submit(mpsk_ctx* ctx, mpsk_matvec_stream* s, const mpsk_blockref* xblocks, int32_t nx,
+                                  const mpsk_blockref_mut* yblocks, int32_t ny);
+int32_t mpsk_matvec_stream_wait(mpsk_ctx* ctx, mpsk_matvec_stream* s);
+void mpsk_matvec_stream_free(mpsk_ctx* ctx, mpsk_matvec_stream* s);
 
 /* ---- host-only numerical helper (exposed for the CPU test-suite) ------------------------------------ */
 /* complex Schur decomposition H = Z T Z^H used by the Krylov-Schur eigensolver; H, Z: n x n column-major interleaved complex;

@@ -116,6 +116,10 @@ PROTOTYPES = {
     "mpsk_tensor_allgather": (C.c_int32, [_P, _P, _P]),
     "mpsk_host_schur": (C.c_int32, [C.c_int32, _DP, _DP, C.c_int32, C.c_int32]),
     "mpsk_host_alloc_selftest": (C.c_int32, [C.c_uint64, C.c_int32]),
+    "mpsk_matvec_stream_create": (C.c_int32, [_P, _P, _P, _P, C.c_int32, C.c_int32, _PP]),
+    "mpsk_matvec_stream_submit": (C.c_int32, [_P, _P, C.POINTER(c_blockref), C.c_int32, C.POINTER(c_blockref), C.c_int32]),
+    "mpsk_matvec_stream_wait": (C.c_int32, [_P, _P]),
+    "mpsk_matvec_stream_free": (None, [_P, _P]),
 }
 
 _lib = None

@@ -745,6 +745,138 @@ int32_t mpsk_op_apply_panel(mpsk_ctx* ctx, const mpsk_op* op, const mpsk_tensor*
   return heff_apply_panel(CTX(ctx), h, CTEN(x_panel), TEN(y_panel));
 }
 
+// ---- streamed matvecs on host buffers: H2D copy, matvec and D2H copy of successive independent vectors overlap -------------
+// (copy engines on two side streams, events between them and the context stream; `depth` slots of device buffers)
+namespace {
+struct MatvecStream {
+  Ctx* ctx = nullptr; HeffOp* op = nullptr; int depth = 2; int layout = 0; int64_t submitted = 0;
+  struct Slot {
+    Tensor* x = nullptr; Tensor* y = nullptr; void* sx = nullptr; void* sy = nullptr;
+    CopyPlan in, out; cudaEvent_t up = nullptr, done = nullptr, down = nullptr; bool busy = false;
+  };
+  std::vector<Slot> slots;
+  cudaStream_t h2d = nullptr, d2h = nullptr;
+  void drain() { for (auto& k : slots) if (k.busy) { cudaEventSynchronize(k.down); k.busy = false; } }
+  ~MatvecStream() {
+    drain();
+    if (ctx) cudaStreamSynchronize(ctx->stream);
+    for (auto& k : slots) {
+      delete k.x; delete k.y;
+      if (ctx) { ctx->free(k.sx); ctx->free(k.sy); }
+      if (k.up) cudaEventDestroy(k.up);
+      if (k.done) cudaEventDestroy(k.done);
+      if (k.down) cudaEventDestroy(k.down);
+    }
+    if (h2d) cudaStreamDestroy(h2d);
+    if (d2h) cudaStreamDestroy(d2h);
+  }
+};
+// contiguous staging image of a tensor's blocks (ABI order), row-major (layout 0) or column-major (layout 1) per block
+static void staging_tasks(const Tensor* t, void* stage, int layout, bool to_tensor, std::vector<CopyTask>* tasks) {
+  const size_t es = t->esize(); int64_t off = 0;
+  for (const Blk& b : t->blks) {
+    const int64_t nl = t->Vl.n[b.jl], nr = t->Vr.n[b.jr];
+    char* sp = (char*)stage + off * es;
+    const int64_t ssl = layout ? 1 : nr, ssr = layout ? nl : 1;
+    if (to_tensor) tasks->push_back(CopyTask{sp, t->ptr(b.off), ssl, ssr, b.sl, b.sr, (int32_t)nl, (int32_t)nr, 0, 0, nullptr});
+    else tasks->push_back(CopyTask{t->ptr(b.off), sp, b.sl, b.sr, ssl, ssr, (int32_t)nl, (int32_t)nr, 0, 0, nullptr});
+    off += nl * nr;
+  }
+}
+static int64_t dense_elems(const Tensor* t) { int64_t n = 0; for (const Blk& b : t->blks) n += t->Vl.n[b.jl] * t->Vr.n[b.jr]; return n; }
+}  // namespace
+
+int32_t mpsk_matvec_stream_create(mpsk_ctx* ctx, const mpsk_op* oph, const mpsk_tensor* x_like, const mpsk_tensor* y_like, int32_t depth,
+                                  int32_t host_layout, mpsk_matvec_stream** out) { ENTER(ctx);
+  Ctx* c = CTX(ctx);
+  HeffOp* h = as_heff(oph);
+  if (!h) return c->fail(MPSK_EINVAL, "not an effective-Hamiltonian operator");
+  if (depth < 1 || depth > 8) return c->fail(MPSK_EINVAL, "depth must be 1..8");
+  if (host_layout != 0 && host_layout != 1) return c->fail(MPSK_EINVAL, "host_layout: 0 row-major blocks, 1 column-major blocks");
+  const Tensor* xl = CTEN(x_like); const Tensor* yl = CTEN(y_like);
+  std::unique_ptr<MatvecStream> s(new MatvecStream);
+  s->ctx = c; s->op = h; s->depth = depth; s->layout = host_layout;
+  CUDA_TRY(c, cudaStreamCreateWithFlags(&s->h2d, cudaStreamNonBlocking));
+  CUDA_TRY(c, cudaStreamCreateWithFlags(&s->d2h, cudaStreamNonBlocking));
+  s->slots.resize(depth);
+  for (auto& k : s->slots) {
+    MPSK_TRY(tensor_create(c, xl->Vl, xl->mch, xl->Vr, xl->dtype, F_KL, true, &k.x));
+    MPSK_TRY(tensor_create(c, yl->Vl, yl->mch, yl->Vr, yl->dtype, F_KL, true, &k.y));
+    k.sx = c->alloc(std::max<int64_t>(dense_elems(k.x), 1) * k.x->esize());
+    k.sy = c->alloc(std::max<int64_t>(dense_elems(k.y), 1) * k.y->esize());
+    if (!k.sx || !k.sy) return MPSK_ENOMEM;
+    std::vector<CopyTask> tin, tout;
+    staging_tasks(k.x, k.sx, host_layout, true, &tin);
+    staging_tasks(k.y, k.sy, host_layout, false, &tout);
+    MPSK_TRY(copy_plan_build(c, tin, k.x->dtype == MPSK_C128, &k.in));
+    MPSK_TRY(copy_plan_build(c, tout, k.y->dtype == MPSK_C128, &k.out));
+    CUDA_TRY(c, cudaEventCreateWithFlags(&k.up, cudaEventDisableTiming));
+    CUDA_TRY(c, cudaEventCreateWithFlags(&k.done, cudaEventDisableTiming));
+    CUDA_TRY(c, cudaEventCreateWithFlags(&k.down, cudaEventDisableTiming));
+  }
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  *out = reinterpret_cast<mpsk_matvec_stream*>(s.release());
+  return MPSK_OK;
+}
+
+int32_t mpsk_matvec_stream_submit(mpsk_ctx* ctx, mpsk_matvec_stream* sh, const mpsk_blockref* xblocks, int32_t nx,
+                                  const mpsk_blockref_mut* yblocks, int32_t ny) { ENTER(ctx);
+  Ctx* c = CTX(ctx); MatvecStream* s = reinterpret_cast<MatvecStream*>(sh);
+  MatvecStream::Slot& k = s->slots[s->submitted % s->depth];
+  if ((int)k.x->blks.size() != nx || (int)k.y->blks.size() != ny)
+    return c->fail(MPSK_ESPACE, "stream submit: %d / %d blocks given, structures have %zu / %zu", nx, ny, k.x->blks.size(), k.y->blks.size());
+  auto layout_ok = [&](int64_t nl, int64_t nr, int64_t sl, int64_t sr) { return s->layout ? contiguous_cm(nl, nr, sl, sr) : contiguous_rm(nl, nr, sl, sr); };
+  for (int i = 0; i < nx; ++i) {
+    const Blk& b = k.x->blks[i];
+    if (!xblocks[i].ptr || !layout_ok(k.x->Vl.n[b.jl], k.x->Vr.n[b.jr], xblocks[i].stride_l, xblocks[i].stride_r))
+      return c->fail(MPSK_EINVAL, "stream submit: x block %d is not a contiguous %s block", i, s->layout ? "column-major" : "row-major");
+  }
+  for (int i = 0; i < ny; ++i) {
+    const Blk& b = k.y->blks[i];
+    if (!yblocks[i].ptr || !layout_ok(k.y->Vl.n[b.jl], k.y->Vr.n[b.jr], yblocks[i].stride_l, yblocks[i].stride_r))
+      return c->fail(MPSK_EINVAL, "stream submit: y block %d is not a contiguous %s block", i, s->layout ? "column-major" : "row-major");
+  }
+  if (k.busy) { CUDA_TRY(c, cudaEventSynchronize(k.down)); k.busy = false; }     // the slot's previous result has landed
+  const size_t es = k.x->esize();
+  int64_t off = 0;
+  for (int i = 0; i < nx; ++i) {
+    const Blk& b = k.x->blks[i];
+    const int64_t n = k.x->Vl.n[b.jl] * k.x->Vr.n[b.jr];
+    CUDA_TRY(c, cudaMemcpyAsync((char*)k.sx + off * es, xblocks[i].ptr, n * es, cudaMemcpyHostToDevice, s->h2d));
+    off += n;
+  }
+  CUDA_TRY(c, cudaEventRecord(k.up, s->h2d));
+  CUDA_TRY(c, cudaStreamWaitEvent(c->stream, k.up, 0));
+  MPSK_TRY(copy_plan_run(c, &k.in));
+  MPSK_TRY(heff_apply_panel(c, s->op, k.x, k.y));
+  MPSK_TRY(copy_plan_run(c, &k.out));
+  CUDA_TRY(c, cudaEventRecord(k.done, c->stream));
+  CUDA_TRY(c, cudaStreamWaitEvent(s->d2h, k.done, 0));
+  off = 0;
+  for (int i = 0; i < ny; ++i) {
+    const Blk& b = k.y->blks[i];
+    const int64_t n = k.y->Vl.n[b.jl] * k.y->Vr.n[b.jr];
+    CUDA_TRY(c, cudaMemcpyAsync(yblocks[i].ptr, (const char*)k.sy + off * es, n * es, cudaMemcpyDeviceToHost, s->d2h));
+    off += n;
+  }
+  CUDA_TRY(c, cudaEventRecord(k.down, s->d2h));
+  k.busy = true;
+  s->submitted++;
+  return MPSK_OK;
+}
+
+int32_t mpsk_matvec_stream_wait(mpsk_ctx* ctx, mpsk_matvec_stream* sh) { ENTER(ctx);
+  Ctx* c = CTX(ctx); MatvecStream* s = reinterpret_cast<MatvecStream*>(sh);
+  for (auto& k : s->slots) if (k.busy) { CUDA_TRY(c, cudaEventSynchronize(k.down)); k.busy = false; }
+  return MPSK_OK;
+}
+
+void mpsk_matvec_stream_free(mpsk_ctx* ctx, mpsk_matvec_stream* sh) {
+  if (!sh) return;
+  ENTER(ctx);
+  delete reinterpret_cast<MatvecStream*>(sh);
+}
+
 int32_t mpsk_tensor_panel(mpsk_ctx* ctx, const mpsk_tensor* t, int32_t axis, int32_t rank, int32_t nranks, mpsk_tensor** out) { ENTER(ctx);
   if (axis != 0 && axis != 1) return CTX(ctx)->fail(MPSK_EINVAL, "axis must be 0 (left index) or 1 (right index)");
   Tensor* o = nullptr;
