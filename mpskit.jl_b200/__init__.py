@@ -32,4 +32,4 @@ from . import statmech  # noqa: F401
 from .approximate import approximate, approximate_inplace, ac_proj, ac2_proj  # noqa: F401
 from .streaming import MatvecStream  # noqa: F401
 from .serialize import save_mps, load_mps, pack_tensor, unpack_tensor  # noqa: F401
-from .changebonds import OptimalExpand, changebonds, changebonds_inplace, leftnull, rightnull, contract_adjoint_left, cat  # noqa: F401
+from .changebonds import SvdCut, svdcut_inplace, OptimalExpand, changebonds, changebonds_inplace, leftnull, rightnull, contract_adjoint_left, cat  # noqa: F401

@@ -1,4 +1,5 @@
-"""changebonds(psi, H, OptimalExpand(trscheme)) for finite MPS: mirror of src/algorithms/changebonds/optimalexpand.jl:80-110.
+"""changebonds for finite MPS.  `SvdCut` (changebonds/svdcut.jl:14-24): truncated SVD of every bond matrix.
+`changebonds(psi, H, OptimalExpand(trscheme))`: mirror of src/algorithms/changebonds/optimalexpand.jl:80-110.
 Every tensor operation runs on the device: two-site matvec, leftnull / rightnull (full Householder QR per coupled sector),
 the projections onto the null spaces, the truncated SVD of the projected two-site tensor, direct sums along the bonds, QRpos."""
 from __future__ import annotations
@@ -8,7 +9,7 @@ import numpy as np
 from .tensor import DeviceTensor
 from .derivatives import ddAC2
 from .environments import environments
-from .dmrg import contract_ac2, truncdim, tsvd
+from .dmrg import contract_ac2, truncdim, notrunc, tsvd, _mul_right
 from .finitemps import qrpos
 from .operators import SparseMPOSlice
 
@@ -105,6 +106,49 @@ def changebonds_inplace(psi, H, alg: OptimalExpand, envs=None, log=None):
     return psi, envs
 
 
-def changebonds(psi, H, alg: OptimalExpand, envs=None, log=None):
-    """changebonds(psi, H, alg) = changebonds!(copy(psi), H, alg, envs) (optimalexpand.jl:80-82)"""
+def changebonds(psi, H=None, alg=None, envs=None, log=None):
+    """changebonds(psi, H, alg::OptimalExpand, envs) = changebonds!(copy(psi), ...) (optimalexpand.jl:80-82);
+    changebonds(psi, alg::SvdCut) = changebonds!(copy(psi), alg) (svdcut.jl:13)"""
+    if isinstance(H, SvdCut) and alg is None:
+        H, alg = None, H
+    if isinstance(alg, SvdCut):
+        return svdcut_inplace(psi.copy(), alg, log)
     return changebonds_inplace(psi.copy(), H, alg, envs, log)
+
+
+@dataclass
+class SvdCut:
+    """svdcut.jl:9-11"""
+    trscheme: tuple = field(default_factory=notrunc)
+
+
+class _BondLeg:
+    """what `tsvd` needs to know to factorise a bond tensor: one trivial label on the left"""
+    def __init__(self, psi):
+        self.ctx, self.pq, self.pspace = psi.ctx, (0,), psi.pspace
+
+
+def svdcut_inplace(psi, alg: SvdCut, log=None):
+    """changebonds!(psi::AbstractFiniteMPS, alg::SvdCut) (svdcut.jl:14-24): for i = L-1 ... 1: U, S, V = tsvd(CR[i]; trunc);
+    AC[i] = (AL[i] * U, S); AC[i+1] = (S, V * AR[i+1]); normalize!(psi).  The SVD of the bond matrix, the two bond
+    multiplications and the final scaling all run on the device."""
+    ctx = psi.ctx
+    P = _BondLeg(psi)
+    for i in range(len(psi) - 2, -1, -1):
+        Cm = psi.CR[i]
+        AL, AR = psi.AL[i], psi.AR[i + 1]
+        U, S, V, eps = tsvd(P, Cm, alg.trscheme, normalize=False)
+        if log is not None:
+            from .dmrg import tsvd_spectrum
+            log.append(dict(pos=i, kept=S.Vl.as_dict(), eps_trunc=eps, spectrum={q: s for q, (s, k) in tsvd_spectrum(ctx).items()}))
+        al = _mul_right(psi, AL, U)                                           # AL[i] * U
+        h = C.c_void_p()
+        ctx.check(ctx.lib.mpsk_mul_bond_left(ctx.h, V.h, AR.h, C.byref(h)))     # V * AR[i+1]
+        ar = DeviceTensor.wrap(ctx, h, psi.pspace.modulus)
+        psi.AC[i] = (al, S)
+        psi.AC[i + 1] = (S, ar)
+        U.free(); V.free()
+    c = psi.CR[0]
+    c.scale(1.0 / c.norm())                                                   # normalize!(psi)
+    psi.ACs = [None] * psi.L
+    return psi

@@ -8,9 +8,13 @@ from .tensor import block_table
 
 
 class MatvecStream:
-    def __init__(self, op, x_like, y_like=None, depth=2):
+    def __init__(self, op, x_like, y_like=None, depth=2, order="C"):
         """op: an effective-Hamiltonian operator handle holder (`.h`), x_like / y_like: DeviceTensors giving the block
-        structures of the inputs and outputs (row panels when the context has a communicator)."""
+        structures of the inputs and outputs (row panels when the context has a communicator); order: "C" for row-major host
+        blocks (numpy default), "F" for column-major ones (TensorKit's layout)."""
+        if order not in ("C", "F"):
+            raise ValueError("order must be 'C' or 'F'")
+        self.order = order
         y_like = x_like if y_like is None else y_like
         self.ctx = x_like.ctx
         self._tx = block_table(x_like.Vl, x_like.mch, x_like.Vr)
@@ -19,16 +23,17 @@ class MatvecStream:
         self._shape_y = [(y_like.Vl.dims[jl], y_like.Vr.dims[jr]) for (_, jl, jr) in self._ty]
         self.dtype = x_like.dtype
         self.h = C.c_void_p()
-        self.ctx.check(self.ctx.lib.mpsk_matvec_stream_create(self.ctx.h, op.h, x_like.h, y_like.h, int(depth), 0, C.byref(self.h)))
+        self.ctx.check(self.ctx.lib.mpsk_matvec_stream_create(self.ctx.h, op.h, x_like.h, y_like.h, int(depth), 0 if order == "C" else 1, C.byref(self.h)))
         self._keep = []
 
     def _refs(self, blocks, table, shapes):
         refs = (_lib.c_blockref * max(len(table), 1))()
         for i, (m, jl, jr) in enumerate(table):
             b = blocks[(m, jl)]
-            if b.dtype != self.dtype or b.shape != shapes[i] or not b.flags.c_contiguous:
-                raise _lib.SpaceMismatch(_lib.ESPACE, f"block {(m, jl)}: need a C-contiguous {self.dtype} array of shape {shapes[i]}")
-            refs[i] = _lib.c_blockref(b.ctypes.data, shapes[i][1], 1)
+            ok = b.flags.c_contiguous if self.order == "C" else b.flags.f_contiguous
+            if b.dtype != self.dtype or b.shape != shapes[i] or not ok:
+                raise _lib.SpaceMismatch(_lib.ESPACE, f"block {(m, jl)}: need a {self.order}-contiguous {self.dtype} array of shape {shapes[i]}")
+            refs[i] = _lib.c_blockref(b.ctypes.data, shapes[i][1], 1) if self.order == "C" else _lib.c_blockref(b.ctypes.data, 1, shapes[i][0])
         return refs
 
     def submit(self, xblocks, yblocks):

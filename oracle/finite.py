@@ -515,3 +515,26 @@ def optimal_expand(psi: FiniteMPS, H, trunc=("truncdim", 1), envs=None, log=None
         psi.set_AC_alc(i, nal, R, nV)
         psi.set_AC_car(i + 1, R, ARp, nV)
     return psi, envs
+
+
+def svdcut(psi: FiniteMPS, trunc=("notrunc",), log=None):
+    """changebonds!(psi::AbstractFiniteMPS, alg::SvdCut) (src/algorithms/changebonds/svdcut.jl:14-24): right-to-left sweep,
+    truncated SVD of every bond matrix CR[i], absorbed into AL[i] / AR[i+1]; normalize!(psi) at the end."""
+    mod = psi.p.modulus
+    for i in range(psi.L - 2, -1, -1):
+        AL = psi.get_AL(i)
+        # CR[i] through the getter's own route (orthoview.jl:49-60): LQpos of AC[i+1]; after a truncation of the bond to the
+        # right the L factor is rectangular (V[i+1] x V'), which the square-matrix getter of this port does not track
+        Cm, AR, Vp = psi._rightorth(psi.get_AC(i + 1), psi.V[i + 1], psi.V[i + 2])
+        U, S, Vh, newV, eps, info = tsvd(Cm, psi.V[i + 1].index_charges(), Vp.index_charges(), trunc, mod)
+        if log is not None:
+            log.append(dict(pos=i, kept=newV.as_dict(), eps_trunc=eps, spectrum={c: s.copy() for c, s in info["spectrum"].items()}))
+        al = np.einsum('apk,kn->apn', AL, U)
+        ar = np.einsum('nk,kpr->npr', Vh, AR)
+        c = np.diag(S).astype(np.complex128)
+        psi.set_AC_alc(i, al, c, newV)
+        psi.set_AC_car(i + 1, c, ar, newV)
+    c = psi.get_CR(0)
+    psi.CL[1] = c / np.linalg.norm(c)
+    psi.AC = [None] * psi.L
+    return psi

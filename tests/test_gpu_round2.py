@@ -549,8 +549,44 @@ def test_streamed_matvecs_from_host_buffers(ctx):
         assert all(np.array_equal(o[k], r[k]) for k in r)
     yo = oc.dAC2_blocks(xs[3], ho, Ho.slices[3], GLo, GRo)
     assert max(np.abs(outs[3][k] - yo.blocks[k]).max() for k in yo.blocks) < 1e-11
+    # column-major host blocks (TensorKit's layout, host_layout = 1)
+    stf = m.MatvecStream(h, x0, depth=1, order="F")
+    of_ = {k: np.empty(v.shape, dtype=v.dtype, order="F") for k, v in ref[0].items()}
+    stf.submit({k: np.asfortranarray(v) for k, v in xs[1].blocks.items()}, of_)
+    stf.wait()
+    assert all(np.array_equal(of_[k], ref[1][k]) for k in ref[1])
+    stf.free()
     # a non-contiguous block is rejected, not silently copied
     bad = {k: np.asfortranarray(v) if v.shape[0] > 1 and v.shape[1] > 1 else v for k, v in outs[0].items()}
     with pytest.raises((m.MpskError, m.SpaceMismatch)):
         st.submit({k: np.ascontiguousarray(v) for k, v in xs[0].blocks.items()}, bad)
     st.free()
+
+
+@pytest.mark.gpu
+def test_svdcut_finite(ctx):
+    """changebonds(psi, SvdCut(trscheme)) (changebonds/svdcut.jl:14-24) on the device against the oracle restatement: kept sector
+    dimensions bit-exact, truncation errors and spectra of every bond to 1e-10, the truncated states agree as vectors; with
+    notrunc the state is unchanged.  Bonds next to a truncated one go through rectangular LQ factors."""
+    L = 8
+    po = OSpace((-1, 1), (1, 1))
+    maxV = [of.gaussian_bond_space(12, k % 2) for k in range(1, L)]
+    psi_o = of.FiniteMPS.random(np.random.default_rng(1), po, L, maxV)
+    psi_d = m.FiniteMPS.random(np.random.default_rng(1), to_dev_space(po), L, [to_dev_space(v) for v in maxV], ctx)
+    v0 = _full_state(psi_d)
+    same = m.changebonds(psi_d, m.SvdCut())
+    v1 = _full_state(same)
+    assert abs(abs(np.vdot(v0, v1)) / np.linalg.norm(v0) / np.linalg.norm(v1) - 1) <= 1e-12
+    log_o, log_d = [], []
+    psi_o = of.svdcut(psi_o, ("truncdim", 5), log=log_o)
+    cut = m.changebonds(psi_d, m.SvdCut(trscheme=m.truncdim(5)), log=log_d)
+    assert [cut.V[i].as_dict() for i in range(L + 1)] == [psi_o.V[i].as_dict() for i in range(L + 1)]
+    assert len(log_o) == len(log_d)
+    for a, b in zip(log_d, log_o):
+        assert a["pos"] == b["pos"] and a["kept"] == b["kept"] and abs(a["eps_trunc"] - b["eps_trunc"]) <= 1e-10
+        for q, s_o in b["spectrum"].items():
+            assert np.abs(a["spectrum"][q] - s_o).max() <= 1e-10
+    vd, vo = _full_state(cut), _full_state_o(psi_o)
+    assert abs(np.linalg.norm(vd) - 1) <= 1e-12 and abs(np.linalg.norm(vo) - 1) <= 1e-12
+    assert abs(abs(np.vdot(vd, vo)) - 1) <= 1e-10
+    print("svdcut", [cut.V[i].dim for i in range(L + 1)], abs(np.vdot(v0, vd)) / np.linalg.norm(v0))
