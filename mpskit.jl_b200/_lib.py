@@ -12,7 +12,7 @@ F64, C128 = 0, 1
 SR, LM, LR = 0, 1, 2
 NOTRUNC, TRUNCDIM, TRUNCERR, TRUNCBELOW = 0, 1, 2, 3
 OP_DC, OP_DAC, OP_DAC2 = 0, 1, 2
-FLAG_DEBUG_GEMM, FLAG_EXACT_SVD, FLAG_FAST_SVD_ALL, FLAG_REPLICATE_LOCAL, FLAG_SVD_RELATIVE = 1, 2, 4, 8, 16
+FLAG_DEBUG_GEMM, FLAG_EXACT_SVD, FLAG_FAST_SVD_ALL, FLAG_REPLICATE_LOCAL, FLAG_SVD_RELATIVE, FLAG_GEMM_4M = 1, 2, 4, 8, 16, 32
 OP_SHARDED = 0x100
 
 
@@ -187,5 +187,7 @@ def default_context():
     if _default_ctx is None:
         dev = int(os.environ.get("LOCAL_RANK", "0"))
         flags = FLAG_DEBUG_GEMM if os.environ.get("MPSK_DEBUG_GEMM") == "1" else 0
+        if os.environ.get("MPSK_GEMM_4M") == "1":
+            flags |= FLAG_GEMM_4M
         _default_ctx = Context(dev, flags)
     return _default_ctx

@@ -31,6 +31,13 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// explicit shared-space 128-bit load: the ring base is re-aligned at run time, which makes the compiler lose the address
+// space and emit generic LD.E.128 with 64-bit addresses; ld.shared gives LDS.128 on a 32-bit address
+__device__ __forceinline__ double2 lds128(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1},{%2},{%3},{%0,%1};"
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
@@ -59,10 +66,10 @@ struct LoadCursor {
   }
 };
 
-template <bool CPLX, int WARPS_N, int WN_ = 32>
-__global__ void __launch_bounds__(GemmCfg<CPLX, WARPS_N, WN_>::NTHREADS, GemmCfg<CPLX, WARPS_N, WN_>::CTAS_PER_SM)
+template <bool CPLX, int WARPS_N, int WN_ = 32, bool M3 = false>
+__global__ void __launch_bounds__(GemmCfg<CPLX, WARPS_N, WN_, M3>::NTHREADS, GemmCfg<CPLX, WARPS_N, WN_, M3>::CTAS_PER_SM)
 gemm_dmma_kernel(const GemmProblemDev* __restrict__ probs, const GemmTile* __restrict__ tiles, int ntiles) {
-  using Cfg = GemmCfg<CPLX, WARPS_N, WN_>;
+  using Cfg = GemmCfg<CPLX, WARPS_N, WN_, M3>;
   constexpr int BM = Cfg::BM, BN = Cfg::BN, KSUB = Cfg::KSUB, NSUB = Cfg::NSUB, STAGES = Cfg::STAGES;
   constexpr int KSTAGE = KSUB * NSUB;                       // elements of K per stage
   constexpr int A_SUB_BYTES = BM * 64, B_SUB_BYTES = BN * 64;
@@ -77,6 +84,7 @@ gemm_dmma_kernel(const GemmProblemDev* __restrict__ probs, const GemmTile* __res
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
   uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
+  const uint32_t smem_base = smem_u32(smem);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -116,6 +124,8 @@ gemm_dmma_kernel(const GemmProblemDev* __restrict__ probs, const GemmTile* __res
   const int g = lane >> 2, t4 = lane & 3;
   const int wm = warp % WARPS_M, wn = warp / WARPS_M;
   int stage = 0; uint32_t phase = 0;
+  const uint32_t frag_a = smem_base + (wm * WM + g) * 64 + t4 * 16;
+  const uint32_t frag_b = smem_base + NSUB * A_SUB_BYTES + (wn * WN + g) * 64 + t4 * 16;
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const GemmTile t = tiles[tile];
@@ -124,12 +134,14 @@ gemm_dmma_kernel(const GemmProblemDev* __restrict__ probs, const GemmTile* __res
 
     double acc_re[MI][NI][2];
     double acc_im[CPLX ? MI : 1][CPLX ? NI : 1][2];
+    double acc_p3[M3 ? MI : 1][M3 ? NI : 1][2];
 #pragma unroll
     for (int i = 0; i < MI; ++i)
 #pragma unroll
       for (int j = 0; j < NI; ++j) {
         acc_re[i][j][0] = 0.0; acc_re[i][j][1] = 0.0;
         if (CPLX) { acc_im[i][j][0] = 0.0; acc_im[i][j][1] = 0.0; }
+        if (M3) { acc_p3[i][j][0] = 0.0; acc_p3[i][j][1] = 0.0; }
       }
 
 #pragma unroll 1
@@ -137,16 +149,39 @@ gemm_dmma_kernel(const GemmProblemDev* __restrict__ probs, const GemmTile* __res
       if (producer) issue_one();
       __syncwarp();
       mbar_wait(&full_bar[stage], phase);
-      const unsigned char* sa = smem + stage * STAGE_BYTES + (wm * WM + g) * 64 + t4 * 16;
-      const unsigned char* sb = smem + stage * STAGE_BYTES + NSUB * A_SUB_BYTES + (wn * WN + g) * 64 + t4 * 16;
-#pragma unroll 2
+      const uint32_t sa = frag_a + stage * STAGE_BYTES, sb = frag_b + stage * STAGE_BYTES;
+      // wide 3M: 192 accumulator registers leave no room to hold two k-steps of fragments (the second warp of the
+      // scheduler covers the LDS latency); every other configuration double-buffers through the unrolled loop
+#pragma unroll ((M3 && WN_ == 32) ? 1 : 2)
       for (int s = 0; s < NSUB; ++s) {
         double2 a[MI], b[NI];
 #pragma unroll
-        for (int i = 0; i < MI; ++i) a[i] = *(const double2*)(sa + s * A_SUB_BYTES + i * 8 * 64);
+        for (int i = 0; i < MI; ++i) a[i] = lds128(sa + s * A_SUB_BYTES + i * 8 * 64);
 #pragma unroll
-        for (int j = 0; j < NI; ++j) b[j] = *(const double2*)(sb + s * B_SUB_BYTES + j * 8 * 64);
-        if (CPLX) {
+        for (int j = 0; j < NI; ++j) b[j] = lds128(sb + s * B_SUB_BYTES + j * 8 * 64);
+        if (M3) {
+          // 3M complex product (three real DMMAs instead of four, 25 % less tensor-pipe work):
+          //   P1 += ar br ; P2 += ai bi ; P3 += (ar + ai)(br + bi)   ->   re = P1 - P2 ; im = P3 - P1 - P2  (epilogue)
+          // The 8 operand sums per k-step share the FP64 pipe with the 48 DMMAs (tools/dmma_dadd_mix.cu: 5 % of the pipe);
+          // the compiler overwrites the real parts with them once P1 has consumed those, so they cost no registers.
+          double as[MI], bs[NI];
+#pragma unroll
+          for (int i = 0; i < MI; ++i) as[i] = a[i].x + a[i].y;
+#pragma unroll
+          for (int j = 0; j < NI; ++j) bs[j] = b[j].x + b[j].y;
+#pragma unroll
+          for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NI; ++j) dmma884(acc_re[i][j][0], acc_re[i][j][1], a[i].x, b[j].x);
+#pragma unroll
+          for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NI; ++j) dmma884(acc_im[i][j][0], acc_im[i][j][1], a[i].y, b[j].y);
+#pragma unroll
+          for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NI; ++j) dmma884(acc_p3[i][j][0], acc_p3[i][j][1], as[i], bs[j]);
+        } else if (CPLX) {
           // (ar + i ai)(br + i bi): re += ar br - ai bi ; im += ar bi + ai br
 #pragma unroll
           for (int i = 0; i < MI; ++i)
@@ -187,6 +222,18 @@ gemm_dmma_kernel(const GemmProblemDev* __restrict__ probs, const GemmTile* __res
     double* C = (double*)p->C;
     const int64_t ldc = p->ldc;
     const bool accum = p->accumulate != 0;
+    if (M3) {
+#pragma unroll
+      for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NI; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const double p1 = acc_re[i][j][e], p2 = acc_im[i][j][e];
+            acc_re[i][j][e] = p1 - p2;
+            acc_im[i][j][e] = acc_p3[i][j][e] - (p1 + p2);
+          }
+    }
 #pragma unroll
     for (int i = 0; i < MI; ++i) {
       const int row = t.m0 + wm * WM + i * 8 + g;
@@ -280,9 +327,17 @@ static bool encode_map(CUtensorMap* tm, const void* base, int64_t rows, int64_t 
   return r == CUDA_SUCCESS;
 }
 
-template <bool CPLX, int WARPS_N, int WN = 32> static int smem_bytes() {
-  using Cfg = GemmCfg<CPLX, WARPS_N, WN>;
-  return Cfg::STAGES * Cfg::NSUB * (Cfg::BM + Cfg::BN) * 64 + 2 * Cfg::STAGES * 8 + 128;
+template <bool CPLX, int WARPS_N, int WN, bool M3> static int launch_cfg(Ctx* ctx, const GemmPlan* plan, int slot) {
+  using Cfg = GemmCfg<CPLX, WARPS_N, WN, M3>;
+  constexpr int smem = Cfg::STAGES * Cfg::NSUB * (Cfg::BM + Cfg::BN) * 64 + 2 * Cfg::STAGES * 8 + 128;
+  auto kern = gemm_dmma_kernel<CPLX, WARPS_N, WN, M3>;
+  const int grid = std::min(plan->ntiles, ctx->num_sms * Cfg::CTAS_PER_SM);
+  if (!ctx->gemm_attr_set[slot]) {
+    CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ctx->gemm_attr_set[slot] = true;
+  }
+  kern<<<grid, Cfg::NTHREADS, smem, ctx->stream>>>(plan->d_probs, plan->d_tiles, plan->ntiles);
+  return MPSK_OK;
 }
 
 GemmPlan::~GemmPlan() {
@@ -305,6 +360,7 @@ int gemm_plan_build(Ctx* ctx, bool cplx, const std::vector<GemmProblemHost>& pro
   // ---- tile configuration: narrow (128 x 32, complex only) when it cuts the quantised tile work by > 7 %
   int BN = cplx ? 32 * GEMM_WIDE_N_CPLX : 32 * GEMM_WIDE_N_REAL;
   plan->narrow = false; plan->narrow16 = false;
+  plan->m3 = cplx && !(ctx->flags & MPSK_FLAG_GEMM_4M);
   if (cplx && !(ctx->flags & MPSK_FLAG_DEBUG_GEMM)) {
     double wide = 0, nar = 0, nar16 = 0;
     for (const GemmProblemHost& h : probs_in) {
@@ -424,27 +480,15 @@ int gemm_plan_run(Ctx* ctx, const GemmPlan* plan) {
     if (plan->cplx) gemm_debug_kernel<true><<<grid, 256, 0, ctx->stream>>>(plan->d_probs, plan->nprob);
     else gemm_debug_kernel<false><<<grid, 256, 0, ctx->stream>>>(plan->d_probs, plan->nprob);
   } else {
-    bool* attr_set = ctx->gemm_attr_set;
-    if (plan->cplx && plan->narrow16) {
-      using Cfg = GemmCfg<true, 1, 16>;
-      const int grid = std::min(plan->ntiles, ctx->num_sms * Cfg::CTAS_PER_SM);
-      if (!attr_set[3]) { CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_dmma_kernel<true, 1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<true, 1, 16>())); attr_set[3] = true; }
-      gemm_dmma_kernel<true, 1, 16><<<grid, Cfg::NTHREADS, smem_bytes<true, 1, 16>(), ctx->stream>>>(plan->d_probs, plan->d_tiles, plan->ntiles);
-    } else if (plan->cplx && plan->narrow) {
-      using Cfg = GemmCfg<true, GEMM_NARROW_N_CPLX>;
-      const int grid = std::min(plan->ntiles, ctx->num_sms * Cfg::CTAS_PER_SM);
-      if (!attr_set[2]) { CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_dmma_kernel<true, GEMM_NARROW_N_CPLX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<true, GEMM_NARROW_N_CPLX>())); attr_set[2] = true; }
-      gemm_dmma_kernel<true, GEMM_NARROW_N_CPLX><<<grid, Cfg::NTHREADS, smem_bytes<true, GEMM_NARROW_N_CPLX>(), ctx->stream>>>(plan->d_probs, plan->d_tiles, plan->ntiles);
-    } else if (plan->cplx) {
-      using Cfg = GemmCfg<true, GEMM_WIDE_N_CPLX>;
-      const int grid = std::min(plan->ntiles, ctx->num_sms);
-      if (!attr_set[1]) { CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_dmma_kernel<true, GEMM_WIDE_N_CPLX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<true, GEMM_WIDE_N_CPLX>())); attr_set[1] = true; }
-      gemm_dmma_kernel<true, GEMM_WIDE_N_CPLX><<<grid, Cfg::NTHREADS, smem_bytes<true, GEMM_WIDE_N_CPLX>(), ctx->stream>>>(plan->d_probs, plan->d_tiles, plan->ntiles);
+    if (!plan->cplx) MPSK_TRY((launch_cfg<false, GEMM_WIDE_N_REAL, 32, false>(ctx, plan, TC_REAL)));
+    else if (plan->m3) {
+      if (plan->narrow16) MPSK_TRY((launch_cfg<true, 1, 16, true>(ctx, plan, TC_3M + TC_NARROW16)));
+      else if (plan->narrow) MPSK_TRY((launch_cfg<true, GEMM_NARROW_N_CPLX, 32, true>(ctx, plan, TC_3M + TC_NARROW)));
+      else MPSK_TRY((launch_cfg<true, GEMM_WIDE_N_CPLX, 32, true>(ctx, plan, TC_3M + TC_WIDE)));
     } else {
-      using Cfg = GemmCfg<false, GEMM_WIDE_N_REAL>;
-      const int grid = std::min(plan->ntiles, ctx->num_sms);
-      if (!attr_set[0]) { CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_dmma_kernel<false, GEMM_WIDE_N_REAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<false, GEMM_WIDE_N_REAL>())); attr_set[0] = true; }
-      gemm_dmma_kernel<false, GEMM_WIDE_N_REAL><<<grid, Cfg::NTHREADS, smem_bytes<false, GEMM_WIDE_N_REAL>(), ctx->stream>>>(plan->d_probs, plan->d_tiles, plan->ntiles);
+      if (plan->narrow16) MPSK_TRY((launch_cfg<true, 1, 16, false>(ctx, plan, TC_NARROW16)));
+      else if (plan->narrow) MPSK_TRY((launch_cfg<true, GEMM_NARROW_N_CPLX, 32, false>(ctx, plan, TC_NARROW)));
+      else MPSK_TRY((launch_cfg<true, GEMM_WIDE_N_CPLX, 32, false>(ctx, plan, TC_WIDE)));
     }
   }
   ctx->launches++;

@@ -36,7 +36,13 @@ struct GemmProblemHost {
 //              panels of a sharded matvec), where 64-wide tiles would waste up to 40 % of the DMMA work
 //   narrow16 : 4 warps, 128 x 16 complex (warp tile 32 x 16), 3 CTAs per SM -- row panels whose width is far from a
 //              multiple of 32 (136 rows per sector at 8 GPUs: 144 instead of 160 padded columns)
-template <bool CPLX, int WARPS_N_, int WN_ = 32> struct GemmCfg {
+//   3M (M3_) : the same three complex tile shapes with the 3-multiplication complex product (Karatsuba / "zgemm3m"):
+//              P1 = Ar Br^T, P2 = Ai Bi^T, P3 = (Ar + Ai)(Br + Bi)^T accumulate in three register sets (192 accumulator
+//              registers for the 32 x 32 warp tile) and are combined in the epilogue -- 3 DMMAs per complex k4 step instead
+//              of 4, i.e. 25 % less work on the pipe that bounds the kernel.  Default for ComplexF64; MPSK_FLAG_GEMM_4M
+//              selects the conventional product.
+template <bool CPLX, int WARPS_N_, int WN_ = 32, bool M3_ = false> struct GemmCfg {
+  static constexpr bool M3 = CPLX && M3_;
   static constexpr int WARPS_M = CPLX ? 4 : 2;
   static constexpr int WARPS_N = WARPS_N_;
   static constexpr int WN = WN_;
@@ -47,5 +53,7 @@ template <bool CPLX, int WARPS_N_, int WN_ = 32> struct GemmCfg {
   static constexpr int STAGES = CTAS_PER_SM >= 2 ? 2 : (CPLX ? 4 : 3);
 };
 constexpr int GEMM_WIDE_N_CPLX = 2, GEMM_NARROW_N_CPLX = 1, GEMM_WIDE_N_REAL = 4;
+// tile configuration ids of a plan (GemmPlan::cfg); +4 = the 3M variant of a complex configuration
+enum { TC_REAL = 0, TC_WIDE = 1, TC_NARROW = 2, TC_NARROW16 = 3, TC_3M = 4, TC_NCFG = 8 };
 
 }  // namespace mpsk

@@ -66,7 +66,7 @@ struct Ctx {
   // arena is only recycled after a stream synchronisation, so building a launch never blocks the host
   char* h_arena = nullptr; size_t h_arena_bytes = 0, h_arena_used = 0;
   void* arena_take(size_t bytes);      // pinned host memory valid until the next wrap (which synchronises the stream)
-  bool gemm_attr_set[4] = {false, false, false, false};   // cudaFuncSetAttribute is per device -> per context
+  bool gemm_attr_set[8] = {false, false, false, false, false, false, false, false};   // cudaFuncSetAttribute is per device -> per context
   int profile = -1;                    // MPSK_PROFILE=1: host timers around the Krylov phases
   double t_apply = 0, t_orth = 0, t_sync = 0;
   std::recursive_mutex mu;             // every ABI entry locks the context: concurrent callers serialise
@@ -198,6 +198,7 @@ struct GemmPlan {
   int nprob = 0, ntiles = 0; double flops = 0;
   bool narrow = false;      // 128 x 32 tile configuration (complex, narrow-N plans)
   bool narrow16 = false;    // 128 x 16 tile configuration (row panels far from a multiple of 32)
+  bool m3 = false;          // 3-multiplication complex product (gemm.cuh)
   int splitk = 1; void* partials = nullptr; MixPlan* reduce = nullptr;    // split-K partial products + their reduction pass
   ~GemmPlan();
 };

@@ -590,3 +590,32 @@ def test_svdcut_finite(ctx):
     assert abs(np.linalg.norm(vd) - 1) <= 1e-12 and abs(np.linalg.norm(vo) - 1) <= 1e-12
     assert abs(abs(np.vdot(vd, vo)) - 1) <= 1e-10
     print("svdcut", [cut.V[i].dim for i in range(L + 1)], abs(np.vdot(v0, vd)) / np.linalg.norm(v0))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("Dl", [256, 224, 200, 40, 7])
+def test_complex_gemm_3m_and_4m_tile_configurations(Dl):
+    """The ComplexF64 grouped GEMM in its three tile configurations (128 x 64 / 128 x 32 / 128 x 16: chosen from the
+    quantised work, here steered by the left bond dimension = N of the GEMM) with the default 3-multiplication complex
+    product and with MPSK_FLAG_GEMM_4M, against numpy: 1e-13 of the largest element (K = 300: rounding only)."""
+    from mpskit_b200.infinite import mul_right
+    rng = np.random.default_rng(4400 + Dl)
+    d, Dr, Dr2 = 3, 300, 333
+    A = rng.standard_normal((Dl, d, Dr)) + 1j * rng.standard_normal((Dl, d, Dr))
+    Cm = rng.standard_normal((Dr, 1, Dr2)) + 1j * rng.standard_normal((Dr, 1, Dr2))
+    ref = np.einsum('lpr,rs->lps', A, Cm[:, 0, :])
+    triv = lambda n: OSpace((0,), (n,))
+    outs = {}
+    for name, flags in (("3m", 0), ("4m", _lib.FLAG_GEMM_4M)):
+        c = m.Context(0, flags)
+        dA = dev_tensor(c, BlockTensor.from_dense(A, triv(Dl), [0] * d, triv(Dr)))
+        dC = dev_tensor(c, BlockTensor.from_dense(Cm, triv(Dr), [0], triv(Dr2)))
+        outs[name] = mul_right(dA, dC).to_dense()
+        assert relerr(outs[name], ref) < 1e-13, (name, Dl, relerr(outs[name], ref))
+    # real-valued data in complex storage: the 3M imaginary part P3 - P1 - P2 cancels exactly (P3 == P1 bit for bit, P2 == 0)
+    c = m.Context(0, 0)
+    dA = dev_tensor(c, BlockTensor.from_dense(A.real.astype(np.complex128), triv(Dl), [0] * d, triv(Dr)))
+    dC = dev_tensor(c, BlockTensor.from_dense(Cm.real.astype(np.complex128), triv(Dr), [0], triv(Dr2)))
+    out = mul_right(dA, dC).to_dense()
+    assert np.all(out.imag == 0.0)
+    assert relerr(out.real, np.einsum('lpr,rs->lps', A.real, Cm.real[:, 0, :])) < 1e-13
