@@ -389,15 +389,24 @@ def main():
             s0.record(); (a @ b); s1.record(); torch.cuda.synchronize()
             best = min(best, s0.elapsed_time(s1))
         peak = 8.0 * n ** 3 / (best * 1e-3) / 1e12
+        peak3m = cublas_zgemm3m_tflops(torch, a, b)
         del a, b
         reps = max(3, min(args.steps, 10))
         gm = gemm_only_ms(ctx, op, reps)
         traffic, tsrc = ncu_traffic(args.D, args.r)
-        roofline = {"bound": "tensor", "kernel": "gemm_dmma_kernel<complex> (stage A + stage C of one matvec)",
-                    "achieved": flops / (gm * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
-                    "frac": flops / (gm * 1e-3) / 1e12 / peak, "traffic": traffic, "traffic_source": tsrc,
-                    "peak_source": "builder-measured: live torch.matmul complex128 4096^3 (cuBLAS zgemm) on this GPU in this run; DMMA "
-                                   "issue microbenchmark profiles/r01_peak_fp64_microbench.json gives 36.99; MEASURED_PEAKS.json has no FP64 entry",
+        ach = flops / (gm * 1e-3) / 1e12
+        lib_peak = max(peak, peak3m or 0.0)
+        roofline = {"bound": "tensor", "kernel": "gemm_dmma_kernel<complex, 3M> (stage A + stage C of one matvec)",
+                    "achieved": ach, "peak": lib_peak, "unit": "TFLOP/s", "frac": ach / lib_peak, "traffic": traffic, "traffic_source": tsrc,
+                    "peak_source": "builder-measured, live on this GPU in this run (MEASURED_PEAKS.json has no FP64 entry): the faster of "
+                                   "cuBLAS zgemm (torch.matmul complex128 4096^3, conventional complex product) and cublasZgemm3m (the "
+                                   "library's 3-multiplication complex GEMM), both in algorithmic flops 8 n^3; the DMMA issue "
+                                   "microbenchmark profiles/r01_peak_fp64_microbench.json gives 36.99 executed TFLOP/s",
+                    "note": "achieved counts ALGORITHMIC flops (8 per complex multiply-add, SURVEY.md 8d: independent of any 3M trick); "
+                            "the kernel uses the 3-multiplication complex product and executes 0.75 x that many DMMA flops",
+                    "cublas_zgemm_tflops": peak, "frac_of_cublas_zgemm": ach / peak,
+                    "cublas_zgemm3m_tflops": peak3m, "frac_of_cublas_zgemm3m": (ach / peak3m) if peak3m else None,
+                    "executed_tflops": 0.75 * ach, "dmma_pipe_frac": 0.75 * ach / 36.99,
                     "gemm_ms_per_matvec": gm, "share_of_step": gm / ms}
         mm, mb = mix_only_ms(ctx, op, reps)
         hp, hsrc = hbm_peak()
@@ -509,6 +518,47 @@ def sweep_window(ctx, m, args, world, allmax):
             "estimated_sweep_seconds_L100": per * 150 + 0.06 * per * 47,
             "note": "estimate = 150 full-D updates + 47 edge updates (~6 % of a centre update each, from the measured full sweep); "
                     "per-update time is the max over ranks of the mean over the timed updates"}
+
+
+def cublas_zgemm3m_tflops(torch, a, b):
+    """live cublasZgemm3m (the library's own 3-multiplication complex GEMM) on the same 4096^3 problem, in algorithmic
+    TFLOP/s (8 n^3): the like-for-like library number for the 3M kernel.  None if the entry point cannot be bound."""
+    import ctypes as C
+    try:
+        lib = None
+        for name in ("libcublas.so.12", "libcublas.so"):
+            try:
+                lib = C.CDLL(name)
+                break
+            except OSError:
+                continue
+        if lib is None:
+            return None
+        fn = lib.cublasZgemm3m
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                       C.c_void_p, C.c_void_p, C.c_int]
+        n = a.shape[0]
+        c = torch.empty_like(a)
+        handle = torch.cuda.current_blas_handle()
+        alpha = (C.c_double * 2)(1.0, 0.0); beta = (C.c_double * 2)(0.0, 0.0)
+
+        def run():
+            st = fn(handle, 0, 0, n, n, n, alpha, a.data_ptr(), n, b.data_ptr(), n, beta, c.data_ptr(), n)
+            if st != 0:
+                raise RuntimeError(f"cublasZgemm3m status {st}")
+        run(); torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(3):
+            s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
+            s0.record(); run(); s1.record(); torch.cuda.synchronize()
+            best = min(best, s0.elapsed_time(s1))
+        ref = a.T @ b.T          # column-major C = A B on row-major storage: C^T = B^T A^T -> c (as row-major) = (a^T b^T)^T
+        if not torch.allclose(c.T, ref, rtol=1e-9, atol=1e-9 * float(ref.abs().max())):
+            return None
+        return 8.0 * n ** 3 / (best * 1e-3) / 1e12
+    except Exception:
+        return None
 
 
 def gemm_only_ms(ctx, op, reps):
