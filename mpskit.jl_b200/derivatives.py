@@ -88,17 +88,24 @@ class MPO_ddAC2(DerivativeOperator):
 
 
 def ddC(pos, psi, H, envs):
-    """derivatives.jl:34-36: MPO_ddC(leftenv(envs, pos+1), rightenv(envs, pos))"""
+    """derivatives.jl:34-36: MPO_ddC(leftenv(envs, pos+1), rightenv(envs, pos)); LinearCombination / ProjectionOperator
+    dispatch (derivatives.jl:234-247, 275-281) lives with those operator types (excitations.py)"""
+    if hasattr(H, "_ddC"):
+        return H._ddC(pos, psi, envs)
     return MPO_ddC(psi.ctx, envs.leftenv(pos + 1, psi), envs.rightenv(pos, psi), psi.CR[pos])
 
 
 def ddAC(pos, psi, H, envs):
     """derivatives.jl:44-46"""
+    if hasattr(H, "_ddAC"):
+        return H._ddAC(pos, psi, envs)
     return MPO_ddAC(psi.ctx, envs.opp[pos], envs.leftenv(pos, psi), envs.rightenv(pos, psi), psi.AC[pos])
 
 
 def ddAC2(pos, psi, H, envs, x_like):
     """derivatives.jl:55-58: (opp[pos], opp[pos+1], leftenv(pos), rightenv(pos+1))"""
+    if hasattr(H, "_ddAC2"):
+        return H._ddAC2(pos, psi, envs, x_like)
     return MPO_ddAC2(psi.ctx, envs.opp[pos], envs.opp[pos + 1], envs.leftenv(pos, psi), envs.rightenv(pos + 1, psi), x_like)
 
 
@@ -112,6 +119,10 @@ class MultipliedOp:
     def __call__(self, x, t=None):
         c = self.f(t) if callable(self.f) else self.f
         return self.op(x).scale(c)
+
+    def free(self):
+        if hasattr(self.op, "free"):
+            self.op.free()
 
 
 class LazySumOp:
@@ -127,6 +138,13 @@ class LazySumOp:
             y.axpy(1.0, z)
             z.free()
         return y
+
+    __mul__ = __call__
+
+    def free(self):
+        for o in self.ops:
+            if hasattr(o, "free"):
+                o.free()
 
 
 class LinearCombinationOp(LazySumOp):

@@ -128,7 +128,10 @@ class FinEnv:
 
 
 def environments(below, O, above=None):
-    """FinEnv.jl:41-70: start vectors l_LL (x) 1 on level 1 and r_RR (x) 1 on level odim (MPOHamiltonian)."""
+    """FinEnv.jl:41-70: start vectors l_LL (x) 1 on level 1 and r_RR (x) 1 on level odim (MPOHamiltonian).
+    LinearCombination -> LazyLincoCache (lazylincocache.jl:6-8), ProjectionOperator -> overlap environments (FinEnv.jl:101-105)."""
+    if hasattr(O, "_environments"):
+        return O._environments(below)
     ctx = below.ctx
     L = len(below)
     odim = O.odim

@@ -17,7 +17,7 @@ from .blocks import mask3
 from .contract import (transfer_left_sparse, transfer_right_sparse, dAC_sparse, dAC2_sparse, dC_dense)
 from .krylov import eigsolve_lanczos, exponentiate_lanczos
 from .linalg import tsvd, qrpos, lqpos
-from .mpo import MPOHamiltonian
+from .mpo import MPOHamiltonian, SparseMPOSlice
 
 
 def virtual_spaces(pspace: Space, L: int, maxV, left: Space = None, right: Space = None):
@@ -538,3 +538,54 @@ def svdcut(psi: FiniteMPS, trunc=("notrunc",), log=None):
     psi.CL[1] = c / np.linalg.norm(c)
     psi.AC = [None] * psi.L
     return psi
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# ProjectionOperator / AC_EffProj / LinearCombination / FiniteExcited
+def unit_mpo(psi: FiniteMPS):
+    """one-level identity MPO: environments of a ProjectionOperator are plain overlap environments between the state (bra)
+    and opp.ket (ket) -- FinEnv.jl:101-105 builds them with opp = fill(nothing) and the trivial start vectors l_LL (x) l_LL"""
+    return MPOHamiltonian([SparseMPOSlice([[1.0]], (0,), (0,), psi.pq)])
+
+
+def proj_vector(pos, psi, ket: FiniteMPS, penv: "FinEnv"):
+    """|p> = le * ket.AC[pos] * re in the bond spaces of psi: the vector AC_EffProj projects on (derivatives.jl:249-265:
+    y = conj(v) * (le a1 re), v = <x | le a1 re>, i.e. y = |p><p|x>)"""
+    return dAC_sparse(ket.get_AC(pos), penv.opp[pos], penv.leftenv(pos, psi), penv.rightenv(pos, psi))
+
+
+def finite_excited(H, states, init: FiniteMPS, weight=10.0, nsweeps=1, tol=1e-12, krylovdim=30, maxiter=100, log=None):
+    """excitations(H, FiniteExcited(gsalg = DMRG(), weight), states; init) for ONE new state
+    (src/algorithms/excitation/dmrgexcitation.jl:16-36): single-site DMRG (dmrg.jl:22-55) on
+    LinearCombination((H, ProjectionOperator.(states)...), (1.0, weight, ...)), whose local operator is
+    dAC(H) + weight * sum_k |p_k><p_k| (derivatives.jl:234-247, 249-281) with the environments of a LazyLincoCache
+    (lazylincocache.jl:1-8).  Returns (energy of the new state under H, new state)."""
+    psi = init
+    envH = FinEnv(psi, H)
+    unit = unit_mpo(psi)
+    penvs = [FinEnv(psi, unit, ket) for ket in states]
+    L = psi.L
+
+    def local_op(pos):
+        GL, GR = envH.leftenv(pos, psi), envH.rightenv(pos, psi)
+        ps = [proj_vector(pos, psi, ket, pe) for ket, pe in zip(states, penvs)]
+        return lambda x: dAC_sparse(x, H[pos], GL, GR) + weight * sum(p * np.vdot(p, x) for p in ps)
+
+    def galerkin(pos):
+        y = local_op(pos)(psi.get_AC(pos))
+        y = y / np.linalg.norm(y)
+        AL = psi.get_AL(pos)
+        return float(np.linalg.norm(y - np.einsum('apb,cqb,cqd->apd', AL, np.conj(AL), y, optimize=True)))
+    eps = 0.0
+    for it in range(nsweeps):
+        eps_s = np.zeros(L)
+        for pos in list(range(0, L - 1)) + list(range(L - 1, 0, -1)):
+            val, vec, info = eigsolve_lanczos(local_op(pos), psi.get_AC(pos), "SR", tol, krylovdim, maxiter)
+            eps_s[pos] = max(eps_s[pos], galerkin(pos))
+            psi.set_AC(pos, vec)
+            if log is not None:
+                log.append(dict(sweep=it, pos=pos, energy=float(np.real(val)), numops=info["numops"]))
+        eps = eps_s.max()
+        if eps <= tol:
+            break
+    return float(np.real(sum(expectation_value(psi, H, FinEnv(psi, H))))), psi

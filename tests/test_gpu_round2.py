@@ -619,3 +619,70 @@ def test_complex_gemm_3m_and_4m_tile_configurations(Dl):
     out = mul_right(dA, dC).to_dense()
     assert np.all(out.imag == 0.0)
     assert relerr(out.real, np.einsum('lpr,rs->lps', A.real, Cm.real[:, 0, :])) < 1e-13
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sym", ["trivial", "u1"])
+def test_projection_operator_and_finite_excited(ctx, sym):
+    """AC_EffProj / AC2_EffProj (derivatives.jl:249-281), the environments of a ProjectionOperator (FinEnv.jl:101-105),
+    LinearCombination + LazyLincoCache (derivatives.jl:234-247, lazylincocache.jl) and FiniteExcited
+    (dmrgexcitation.jl:16-40) on the device: projector applications against the oracle restatement (1e-12), excited-state
+    energies against exact diagonalisation and the oracle run (1e-10)."""
+    L = 8
+    if sym == "trivial":
+        H = ompo.transverse_field_ising(L, 1.3)
+        p = OSpace((0,), (2,)); maxV = OSpace((0,), (16,))
+        ev = np.linalg.eigvalsh(ompo.dense_hamiltonian(H))
+        mk = lambda seed: of.FiniteMPS.random(np.random.default_rng(seed), p, L, maxV)
+    else:
+        H = ompo.heisenberg_u1(L)
+        p = OSpace((-1, 1), (1, 1))
+        Hd = ompo.dense_hamiltonian(H)
+        sz = np.array([sum(1 if (k >> b) & 1 else -1 for b in range(L)) for k in range(2 ** L)])
+        ev = np.linalg.eigvalsh(Hd[np.ix_(sz == 0, sz == 0)])          # the U(1) MPS lives in the S_z = 0 sector
+        mk = lambda seed: of.FiniteMPS.random(np.random.default_rng(seed), p, L, [of.gaussian_bond_space(64, k % 2) for k in range(1, L)])  # = the full fused spaces at L = 8
+    dH = dev_hamiltonian(H)
+    o_gs = mk(3)
+    o_gs, o_envs, _ = of.dmrg_sweeps(o_gs, H, nsweeps=4)
+    assert abs(sum(of.expectation_value(o_gs, H, o_envs)).real - ev[0]) < 1e-11
+
+    def to_dev(o):
+        As = [o.get_AL(i) for i in range(L - 1)] + [o.get_AC(L - 1)]
+        return m.FiniteMPS(As, [to_dev_space(v) for v in o.V], to_dev_space(o.p), ctx)
+    gs = to_dev(o_gs)
+    o_init = mk(4)
+    init = to_dev(o_init)
+    # ---- the projector itself, at a bulk site, against the oracle restatement (gauge-invariant read-outs:
+    #      <x|P x> = |<p|x>|^2 and |P x| = |p| |<p|x>|)
+    P = m.ProjectionOperator(gs)
+    penv = m.environments(init, P)
+    openv = of.FinEnv(o_init, of.unit_mpo(o_init), o_gs)
+    pos = 3
+    op = m.ddAC(pos, init, P, penv)
+    x = init.AC[pos]
+    y = op(x)
+    pv = of.proj_vector(pos, o_init, o_gs, openv)
+    xo = o_init.get_AC(pos)
+    yo = pv * np.vdot(pv, xo)
+    assert abs(x.dot(y) - np.vdot(xo, yo)) < 1e-12 and abs(y.norm() - np.linalg.norm(yo)) < 1e-12
+    op2 = m.ddAC2(pos, init, P, penv, None)
+    x2 = m.contract_ac2(init, init.AC[pos], init.AR[pos + 1])
+    y2 = op2(x2)
+    from oracle.contract import dAC2_sparse
+    u = of.unit_mpo(o_init)
+    ko = np.einsum('apk,kqr->aprq', o_gs.get_AC(pos), o_gs.get_AR(pos + 1))
+    pv2 = dAC2_sparse(ko, u[pos], u[pos + 1], openv.leftenv(pos, o_init), openv.rightenv(pos + 1, o_init))
+    x2o = np.einsum('apk,kqr->aprq', o_init.get_AC(pos), o_init.get_AR(pos + 1))
+    y2o = pv2 * np.vdot(pv2, x2o)
+    assert abs(x2.dot(y2) - np.vdot(x2o, y2o)) < 1e-12 and abs(y2.norm() - np.linalg.norm(y2o)) < 1e-12
+    # <psi|P|psi> per site = |<gs|psi>|^2 (expval.jl:200-212)
+    ov = abs(np.vdot(_full_state_o(o_gs), _full_state_o(o_init))) ** 2
+    ens = m.expectation_value(init, P)
+    assert np.abs(ens - ov).max() < 1e-12
+    # ---- FiniteExcited: two states above the ground state
+    alg = m.FiniteExcited(gsalg=m.DMRG(tol=1e-11, maxiter=6), weight=10.0)
+    ens, sts = m.excitations(dH, alg, gs, init=init, num=1)
+    assert abs(ens[0] - ev[1]) < 1e-10 * abs(ev[1])
+    e1o, _ = of.finite_excited(H, [o_gs], mk(4), nsweeps=6)
+    assert abs(ens[0] - e1o) < 1e-10 * abs(e1o)
+    assert abs(np.vdot(_full_state(gs), _full_state(sts[0]))) < 1e-6          # orthogonal to the ground state

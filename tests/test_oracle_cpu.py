@@ -258,6 +258,20 @@ def test_periodic_boundary_conditions_and_dmrg_vs_ed():
         assert Hd[i].kinds() == Hh[i].kinds() and Hd[i].domcharges == Hh[i].cl and Hd[i].keys() == Hh[i].keys()
 
 
+def test_reference_logged_energy_critical_tfi_ring_L20_D64():
+    """docs/src/examples/quantum1d/1.ising-cft/index.md:254-296: `find_groundstate(FiniteMPS(20, C^2, C^64),
+    periodic_boundary_conditions(transverse_field_ising(), 20), DMRG())` logs obj = -2.549098968636e+01 from its first
+    sweep on (a number the reference itself produced, through toolbox.jl:186-306 and the single-site DMRG path);
+    the free-fermion value of the critical ring is -2 / sin(pi / 2L)."""
+    L = 20
+    Hp = ompo.periodic_boundary_conditions(ompo.transverse_field_ising(1, 1.0), L)
+    psi = of.FiniteMPS.random(np.random.default_rng(5), Space((0,), (2,)), L, Space((0,), (64,)))
+    log = []
+    of.dmrg_sweeps(psi, Hp, nsweeps=2, log=log)
+    assert abs(log[-1]["energy"] - (-25.49098968636)) < 2e-11
+    assert abs(log[-1]["energy"] - (-2.0 / np.sin(np.pi / (2 * L)))) < 2e-11
+
+
 def test_transfer_matrix_fixed_points_and_tdvp_energy_conservation():
     """test/states.jl:62-70 (l * T(AL, AL) = l, T(AR, AR) * r = r) and test/algorithms.jl:96-128 (energy conserved
     under TDVP to 1e-2; here 1e-8 over three steps at full bond dimension)."""
@@ -331,3 +345,20 @@ def test_cylinder_snake_mpo_and_mpo_product():
     assert np.abs(ompo.dense_hamiltonian(ompo.mpo_product(H, H)) - d @ d).max() <= 1e-12
     Hm = m.heisenberg_longrange_u1(5, r=2)
     assert all(a.kinds() == b.kinds() for a, b in zip(ompo.mpo_product(H, H).slices, m.mpo_product(Hm, Hm).slices))
+
+
+def test_finite_excited_oracle_equals_exact_diagonalisation():
+    """dmrgexcitation.jl:16-40 with AC_EffProj (derivatives.jl:249-281): the ground states of H + w sum |psi_k><psi_k| are the
+    next eigenstates of H -- TFI L=8 against exact diagonalisation (the reference's own test, test/algorithms.jl:238-242, holds
+    the first excitation to 1e-4 against the quasiparticle ansatz)."""
+    L = 8
+    H = ompo.transverse_field_ising(L, 1.3)
+    ev = np.linalg.eigvalsh(ompo.dense_hamiltonian(H))
+    triv = lambda n: Space((0,), (n,))
+    psi = of.FiniteMPS.random(np.random.default_rng(3), triv(2), L, triv(16))
+    psi, envs, _ = of.dmrg_sweeps(psi, H, nsweeps=4)
+    assert abs(sum(of.expectation_value(psi, H, envs)).real - ev[0]) < 1e-12
+    e1, st1 = of.finite_excited(H, [psi], of.FiniteMPS.random(np.random.default_rng(4), triv(2), L, triv(16)), nsweeps=4)
+    assert abs(e1 - ev[1]) < 1e-11
+    e2, _ = of.finite_excited(H, [psi, st1], of.FiniteMPS.random(np.random.default_rng(5), triv(2), L, triv(16)), nsweeps=4)
+    assert abs(e2 - ev[2]) < 1e-11
