@@ -328,6 +328,28 @@ def test_exact_svd_flag_gives_same_energy(ctx):
     assert np.all(np.diff(a[-(L - 1):]) <= 1e-9)                      # energy non-increasing along the last half-sweep
 
 
+def test_gemm_3m_and_4m_give_the_same_dmrg2_run():
+    """the default 3-multiplication complex product vs MPSK_FLAG_GEMM_4M on one DMRG2 run with a long-range MPO: energies of
+    every update agree to 1e-12, kept sector dimensions are identical, truncation errors agree to 1e-12"""
+    L, D = 10, 32
+    H = m.heisenberg_longrange_u1(L, r=3)
+    p = m.Space((-1, 1), (1, 1))
+    from mpskit_b200.workloads import gaussian_bond_space
+    maxV = [gaussian_bond_space(D, k % 2) for k in range(1, L)]
+    out = []
+    for flags in (0, _lib.FLAG_GEMM_4M):
+        c = m.Context(0, flags)
+        psi = m.FiniteMPS.random(np.random.default_rng(6), p, L, maxV, c)
+        log = []
+        m.find_groundstate(psi, H, m.DMRG2(tol=1e-13, maxiter=2, eigalg=m.Lanczos(tol=1e-13), trscheme=m.truncdim(D)), log=log)
+        out.append(log)
+        c.close()
+    ea, eb = np.array([e["energy"] for e in out[0]]), np.array([e["energy"] for e in out[1]])
+    assert np.abs(ea - eb).max() <= 1e-12 * np.abs(ea).max()
+    assert all(x["kept"] == y["kept"] for x, y in zip(out[0], out[1]))
+    assert max(abs(x["eps_trunc"] - y["eps_trunc"]) for x, y in zip(out[0], out[1])) <= 1e-12
+
+
 def test_variance_finite_mps(ctx):
     """variance(psi, H) = <H*H> - <H>^2 (toolbox.jl:141-145) through the product MPO (sparsempo.jl:232-264) and its own
     device environments, against the dense state vector; a converged DMRG2 state has (numerically) zero variance."""
