@@ -36,3 +36,4 @@ from .changebonds import SvdCut, svdcut_inplace, OptimalExpand, changebonds, cha
 from .excitations import (ProjectionOperator, AC_EffProj, AC2_EffProj, LinearCombination, LazyLincoCache, FiniteExcited,  # noqa: F401
                           excitations, unit_mpo)
 from .excitations import expectation_value  # noqa: F401,F811  (general form: MPOHamiltonian / LinearCombination / ProjectionOperator)
+from .lazyops import MultipliedOperator, TimedOperator, UntimedOperator, LazySum, MultipleEnvironments  # noqa: F401

@@ -115,6 +115,13 @@ def expectation_value(psi, O, envs=None):
     (every entry equals |<ket|psi>|^2 / <psi|psi>); MPOHamiltonian -> total energy (dmrg.expectation_value)."""
     from .dmrg import expectation_value as _ev
     envs = envs if envs is not None else _environments(psi, O)
+    from .lazyops import LazySum, MultipliedOperator
+    if isinstance(O, LazySum):                      # expval.jl:186-192
+        return sum(np.sum(expectation_value(psi, o, e)) for o, e in zip(O.ops, envs.envs))
+    if isinstance(O, MultipliedOperator):           # expval.jl:182-184 (UntimedOperator)
+        if O.istimed:
+            raise ValueError("expectation value of a time-dependent operator: evaluate it at a time first, H(t)")
+        return O.f * np.sum(expectation_value(psi, O.op, envs))
     if isinstance(O, LinearCombination):
         return sum(c * np.sum(expectation_value(psi, o, e)) for c, o, e in zip(O.coeffs, O.opps, envs.envs))
     if isinstance(O, ProjectionOperator):

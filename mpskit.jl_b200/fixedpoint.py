@@ -89,9 +89,21 @@ def integrate(f, y0, t, dt, alg: Lanczos = None, return_info=False):
     """y = exponentiate(f(t + dt/2), -im*dt, y0, alg)   (integrators.jl:20-25); f is a DerivativeOperator."""
     alg = alg or Lanczos(tol=1e-12)
     ctx = f.ctx
+    tau = -1j * dt
+    if not hasattr(f, "h") or f.h is None:
+        from .derivatives import MultipliedOp
+        if isinstance(f, MultipliedOp) and getattr(f.op, "h", None) is not None:
+            # f(t) * h with h a device operator: the coefficient at t + dt/2 scales the exponent (derivatives.jl:284-285)
+            c = f.f(t + dt / 2) if callable(f.f) else f.f
+            return integrate(f.op, y0, t, dt * c, alg, return_info)
+        # LazySum of derivatives: host-driven exponentiate of x -> f(x, t + dt/2)
+        from . import krylov
+        y, info = krylov.exponentiate_lanczos(lambda x: f(x, t + dt / 2), tau, y0, alg.tol, alg.krylovdim, alg.maxiter)
+        if info["converged"] == 0:
+            warnings.warn("integrate not converged")
+        return (y, info) if return_info else y
     y = y0.zerovector()
     info = _lib.c_info()
-    tau = -1j * dt
     ctx.check(ctx.lib.mpsk_expv(ctx.h, f.h, tau.real, tau.imag, y0.h, alg.krylovdim, alg.maxiter, alg.tol, y.h, C.byref(info)))
     if info.converged == 0:   # integrators.jl:22-23
         warnings.warn("integrate not converged")

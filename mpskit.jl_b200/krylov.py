@@ -171,3 +171,57 @@ def linsolve_gmres(f, b, x0, a0=1.0, a1=-1.0, tol=1e-12, krylovdim=30, maxiter=1
             x.axpy(c, v)
     r = op(x); r.scale(-1.0); r.axpy(1.0, b)
     return x, dict(converged=0, numops=numops, normres=r.norm())
+
+
+def exponentiate_lanczos(f, tau, y0, tol=1e-12, krylovdim=30, maxiter=100):
+    """y = exp(tau f) y0 for a Hermitian map f that is not a single device operator (KrylovKit.exponentiate with Lanczos,
+    called by integrate, integrators.jl:20-25): Krylov projections of dimension <= krylovdim on the device vectors, the small
+    exponential on the host; if the a-posteriori error estimate |beta_m [exp(dtau T)]_{m,1}| of a full-dimension projection
+    exceeds the tolerance the step is halved and the remaining interval is continued from the intermediate vector."""
+    y = y0.copy()
+    done, numops = 0.0, 0
+    step = 1.0
+    converged = 1
+    it = 0
+    while done < 1.0 - 1e-15:
+        it += 1
+        if it > maxiter:
+            converged = 0
+            break
+        beta0 = y.norm()
+        if beta0 == 0.0:
+            break
+        V = [y.copy().scale(1.0 / beta0)]
+        alphas, betas = [], []
+        w = None
+        happy = False
+        for k in range(krylovdim):
+            w = f(V[k]); numops += 1
+            w, h = _orth(w, V)
+            alphas.append(h[k].real)
+            b = w.norm()
+            betas.append(b)
+            if b < 1e-14 * max(1.0, abs(alphas[-1])):
+                happy = True
+                break
+            if k + 1 < krylovdim:
+                V.append(w.scale(1.0 / b))
+        m = len(alphas)
+        T = np.diag(alphas) + np.diag(betas[:m - 1], 1) + np.diag(betas[:m - 1], -1)
+        ev, U = np.linalg.eigh(T)
+        while True:
+            dt_ = min(step, 1.0 - done)
+            c = U @ (np.exp(tau * dt_ * ev) * U[0, :].conj())
+            err = 0.0 if happy else abs(betas[m - 1] * c[m - 1]) * beta0
+            if err <= tol * dt_ or dt_ < 1e-6:
+                if err > tol * dt_:
+                    converged = 0
+                break
+            step *= 0.5
+        ynew = _combine(c * beta0, V[:m])
+        for v in V:
+            v.free() if hasattr(v, "free") else None
+        y.free() if hasattr(y, "free") else None
+        y = ynew
+        done += dt_
+    return y, dict(converged=converged, numops=numops)

@@ -708,3 +708,55 @@ def test_projection_operator_and_finite_excited(ctx, sym):
     e1o, _ = of.finite_excited(H, [o_gs], mk(4), nsweeps=6)
     assert abs(ens[0] - e1o) < 1e-10 * abs(e1o)
     assert abs(np.vdot(_full_state(gs), _full_state(sts[0]))) < 1e-6          # orthogonal to the ground state
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("two_site", [False, True])
+def test_time_dependent_lazysum_tdvp(ctx, two_site):
+    """test/algorithms.jl:110-128: timestep with LazySum([3H, 1.55H, -0.1H]) and with the time-dependent
+    Ht = MultipliedOperator(H, t -> 4) + MultipliedOperator(H, 1.45): timestep(psi, Ht, 1.0, dt) equals timestep(psi, Ht(1.0),
+    0.0, dt) (reference: atol 1e-8) -- and both equal the oracle's TDVP step of (3 + 1.55 - 0.1) H resp. 5.45 H, i.e. of H with a
+    rescaled time step (state overlap 1e-9); the time-dependent coefficients are evaluated at the sub-step midpoints.  Operator-level LazySum / MultipliedOperator, MultipleEnvironments
+    (multipleenv.jl:1-15), the derivative constructors of derivatives.jl:298-323 and integrate at t + dt/2 (integrators.jl:20-25)."""
+    L = 6
+    Ho = ompo.heisenberg_u1(L)
+    po = OSpace((-1, 1), (1, 1))
+    maxV = [of.gaussian_bond_space(8, k % 2) for k in range(1, L)]
+    dt = 0.05
+    Hd = dev_hamiltonian(Ho)
+    alg = m.TDVP2(trscheme=m.truncdim(8)) if two_site else m.TDVP()
+    mk = lambda: m.FiniteMPS.random(np.random.default_rng(91), to_dev_space(po), L, [to_dev_space(v) for v in maxV], ctx)
+
+    def oracle(scale):
+        psi_o = of.FiniteMPS.random(np.random.default_rng(91), po, L, maxV)
+        if two_site:
+            psi_o, _ = of.tdvp2_step(psi_o, Ho, scale * dt, trunc=("truncdim", 8))
+        else:
+            psi_o, _ = of.tdvp_step(psi_o, Ho, scale * dt)
+        return _full_state_o(psi_o)
+    # time-independent sum
+    Hlazy = m.LazySum([3 * m.UntimedOperator(Hd), 1.55 * m.UntimedOperator(Hd), -0.1 * m.UntimedOperator(Hd)])
+    psi, envs = m.timestep(mk(), Hlazy, 0.0, dt, alg)
+    assert abs(abs(np.vdot(_full_state(psi), oracle(3 + 1.55 - 0.1))) - 1) <= 1e-9
+    E = m.expectation_value(psi, Hlazy, envs)
+    E1 = m.expectation_value(psi, Hd)
+    assert abs(E - 4.45 * E1) <= 1e-10 * abs(E)
+    # time-dependent sum (the reference's test: a constant function of time)
+    seen = []
+    Ht = m.MultipliedOperator(Hd, lambda t: (seen.append(t), 4.0)[1]) + m.MultipliedOperator(Hd, 1.45)
+    t0 = 1.0
+    psi_a, envs_a = m.timestep(mk(), Ht(t0), 0.0, dt, alg)
+    seen.clear()
+    psi_t, envs_t = m.timestep(mk(), Ht, t0, dt, alg)
+    # every sub-step evaluates the operator in the middle of its interval (integrators.jl:20-25): forward half steps from t and
+    # t + dt/2 at t + dt/4 and t + 3dt/4, the backward steps (-dt/2: tdvp.jl:71-72, 85-86, 131, 147) at t - dt/4 and t + dt/4
+    times = set(float(np.round(x, 12)) for x in seen)
+    assert times <= {round(t0 - dt / 4, 12), round(t0 + dt / 4, 12), round(t0 + 3 * dt / 4, 12)}
+    assert {round(t0 + dt / 4, 12), round(t0 + 3 * dt / 4, 12)} <= times
+    Ea = m.expectation_value(psi_a, Ht(t0), envs_a)
+    Et = m.expectation_value(psi_t, Ht(t0), envs_t)
+    assert abs(Ea - Et) <= 1e-8
+    assert abs(abs(np.vdot(_full_state(psi_t), _full_state(psi_a))) - 1) <= 1e-9
+    assert abs(abs(np.vdot(_full_state(psi_t), oracle(5.45))) - 1) <= 1e-8
+    with pytest.raises(ValueError):
+        Ht()                                           # lazysum.jl:37-39: a time-dependent sum needs a time
