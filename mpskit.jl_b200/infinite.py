@@ -499,6 +499,29 @@ def find_groundstate_vumps(st: InfiniteMPS, H, alg: VUMPS = None, envs=None, log
     return st, envs, eps
 
 
+def timestep_infinite(st: InfiniteMPS, H, t, dt, alg=None, envs=None):
+    """timestep(psi::InfiniteMPS, H, t, dt, alg::TDVP, envs; leftorthflag = true) (src/algorithms/timestep/tdvp.jl:21-59):
+    AC and CR of every site of the unit cell are evolved on the device (mpsk_expv through `integrate`), regauged
+    (ortho.jl:127-131), the uniform gauge is restored and the environments are recalculated."""
+    from .fixedpoint import integrate
+    from .algorithms import TDVP
+    alg = alg or TDVP()
+    envs = envs or environments(st, H)
+    N = st.N
+    newAL = []
+    for loc in range(N):
+        hac = MPO_ddAC(st.ctx, H[loc], envs.leftenv(loc, st), envs.rightenv(loc, st), st.AC[loc])
+        ac = integrate(hac, st.AC[loc], t, dt, alg.integrator); hac.free()
+        hc = MPO_ddC(st.ctx, envs.leftenv(loc + 1, st), envs.rightenv(loc, st), st.CR[loc])
+        c = integrate(hc, st.CR[loc], t, dt, alg.integrator); hc.free()
+        newAL.append(regauge(ac, c))
+    st = InfiniteMPS.from_AL(newAL, st.CR[N - 1], st.V, st.pspace, st.ctx, alg.tolgauge, alg.gaugemaxiter)
+    envs.recalculate(st)
+    if alg.finalize is not None:
+        st, envs = alg.finalize(t, st, H, envs)
+    return st, envs
+
+
 # ------------------------------------------------------------------------------------------ IDMRG1
 @dataclass
 class IDMRG1:

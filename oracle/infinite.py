@@ -338,6 +338,25 @@ def vumps(st: InfiniteMPS, H, tol=1e-12, maxiter=100, envs=None, log=None):
     return st, envs, eps
 
 
+def tdvp_step(st: InfiniteMPS, H, dt, envs=None, tol=1e-12, krylovdim=30, tolgauge=TOLGAUGE, gaugemaxiter=100):
+    """timestep(psi::InfiniteMPS, H, t, dt, TDVP(), envs) with leftorthflag = true (src/algorithms/timestep/tdvp.jl:21-59):
+    every AC and CR of the unit cell is evolved with its own effective Hamiltonian (integrators.jl:20-25), the pairs are
+    regauged to left-orthonormal tensors (ortho.jl:127-131) and the environments are recalculated."""
+    from .krylov import exponentiate_lanczos
+    envs = envs or MPOHamInfEnv(st, H)
+    N = st.N
+    newAL = []
+    for loc in range(N):
+        GL, GR = envs.leftenv(loc, st), envs.rightenv(loc, st)
+        ac, _ = exponentiate_lanczos(lambda x: dAC_sparse(x, H[loc], GL, GR), -1j * dt, st.AC[loc], tol, krylovdim)
+        GLc, GRc = envs.leftenv(loc + 1, st), envs.rightenv(loc, st)
+        c, _ = exponentiate_lanczos(lambda x: dC_dense(x, GLc, GRc), -1j * dt, st.CR[loc], tol, krylovdim)
+        newAL.append(regauge(ac, c, st.V[loc], st.V[(loc + 1) % N], st.pq, st.modulus))
+    st = InfiniteMPS.from_AL(newAL, st.CR[N - 1], st.V, st.pq, tolgauge, gaugemaxiter, st.modulus)
+    envs.recalculate(st)
+    return st, envs
+
+
 # ------------------------------------------------------------------------------------------ IDMRG1 (next-row preparation)
 def idmrg1(st: InfiniteMPS, H, tol=1e-12, maxiter=100, envs=None, log=None):
     """find_groundstate(psi::InfiniteMPS, H, IDMRG1()) (src/algorithms/groundstate/idmrg.jl:21-75) with the manually

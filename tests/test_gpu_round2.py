@@ -760,3 +760,40 @@ def test_time_dependent_lazysum_tdvp(ctx, two_site):
     assert abs(abs(np.vdot(_full_state(psi_t), oracle(5.45))) - 1) <= 1e-8
     with pytest.raises(ValueError):
         Ht()                                           # lazysum.jl:37-39: a time-dependent sum needs a time
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sym", ["trivial", "u1"])
+def test_infinite_tdvp_step(ctx, sym):
+    """timestep(psi::InfiniteMPS, H, t, dt, TDVP()) (tdvp.jl:21-59; reference test: energy conserved to 1e-2,
+    test/algorithms.jl:130-138): two steps on the device against the oracle restatement (energies 1e-9) and energy
+    conservation; a converged VUMPS ground state is stationary (energy unchanged to 1e-10)."""
+    from oracle import infinite as oi
+    from mpskit_b200.infinite import timestep_infinite, expectation_value as ev_inf, environments as env_inf
+    if sym == "trivial":
+        Ho = ompo.transverse_field_ising(1, 0.5)
+        po, Vo = OSpace((0,), (2,)), [OSpace((0,), (10,))]
+    else:
+        Ho = ompo.heisenberg_u1(2)
+        po, Vo = OSpace((-1, 1), (1, 1)), [OSpace((-2, 0, 2), (3, 6, 3)), OSpace((-3, -1, 1, 3), (1, 5, 5, 1))]
+    dt = 0.1
+    psi_o = oi.InfiniteMPS.random(np.random.default_rng(5), po, Vo)
+    envs_o = oi.MPOHamInfEnv(psi_o, Ho)
+    E0 = np.sum(oi.expectation_value(psi_o, Ho, envs_o)).real
+    Hd = dev_hamiltonian(Ho)
+    psi_d = m.InfiniteMPS.random(np.random.default_rng(5), to_dev_space(po), [to_dev_space(v) for v in Vo], ctx)
+    envs_d = env_inf(psi_d, Hd)
+    assert abs(np.sum(ev_inf(psi_d, Hd, envs_d)).real - E0) <= 1e-10 * max(1.0, abs(E0))
+    for step in range(2):
+        psi_o, envs_o = oi.tdvp_step(psi_o, Ho, dt, envs_o)
+        psi_d, envs_d = timestep_infinite(psi_d, Hd, step * dt, dt, m.TDVP(), envs_d)
+        Eo = np.sum(oi.expectation_value(psi_o, Ho, envs_o)).real
+        Ed = np.sum(ev_inf(psi_d, Hd, envs_d)).real
+        assert abs(Ed - Eo) <= 1e-9 * max(1.0, abs(Eo)), (step, Ed, Eo)
+        assert abs(Ed - E0) <= 1e-2
+    if sym == "trivial":
+        gs, genv, eps = m.find_groundstate_vumps(m.InfiniteMPS.random(np.random.default_rng(3), to_dev_space(po), [to_dev_space(v) for v in Vo], ctx),
+                                                 Hd, m.VUMPS(tol=1e-12, maxiter=30))
+        Eg = np.sum(ev_inf(gs, Hd, genv)).real
+        gs2, genv = timestep_infinite(gs, Hd, 0.0, dt, m.TDVP(), genv)
+        assert abs(np.sum(ev_inf(gs2, Hd, genv)).real - Eg) <= 1e-10

@@ -362,3 +362,22 @@ def test_finite_excited_oracle_equals_exact_diagonalisation():
     assert abs(e1 - ev[1]) < 1e-11
     e2, _ = of.finite_excited(H, [psi, st1], of.FiniteMPS.random(np.random.default_rng(5), triv(2), L, triv(16)), nsweeps=4)
     assert abs(e2 - ev[2]) < 1e-11
+
+
+def test_infinite_tdvp_oracle_energy_conservation():
+    """test/algorithms.jl:130-138: timestep(psi::InfiniteMPS, H, 0, dt, TDVP()) conserves the energy (atol 1e-2 there); and a
+    VUMPS ground state is stationary under the step (tdvp.jl:21-59)."""
+    from oracle import infinite as oi
+    H = ompo.transverse_field_ising(1, 0.5)
+    st = oi.InfiniteMPS.random(np.random.default_rng(5), Space((0,), (2,)), [Space((0,), (10,))])
+    envs = oi.MPOHamInfEnv(st, H)
+    E0 = np.sum(oi.expectation_value(st, H, envs)).real
+    for _ in range(2):
+        st, envs = oi.tdvp_step(st, H, 0.1, envs)
+    assert abs(np.sum(oi.expectation_value(st, H, envs)).real - E0) < 1e-2
+    gs = oi.InfiniteMPS.random(np.random.default_rng(3), Space((0,), (2,)), [Space((0,), (10,))])
+    gs, genv, _ = oi.vumps(gs, H, tol=1e-12, maxiter=30)
+    Eg = np.sum(oi.expectation_value(gs, H, genv)).real
+    gs2, genv = oi.tdvp_step(gs, H, 0.1, genv)
+    assert abs(np.sum(oi.expectation_value(gs2, H, genv)).real - Eg) < 1e-10
+    assert abs(Eg - (-1.063544409973)) < 2e-11
