@@ -26,7 +26,8 @@ from .infinite import (InfiniteMPS, TransferMatrix, regularize, MPOHamInfEnv, VU
                        uniform_leftorth, uniform_rightorth, regauge, IDMRG1, IDMRGEnv, find_groundstate_idmrg1, IDMRG2,
                        find_groundstate_idmrg2, bond_inverse)
 from . import infinite  # noqa: F401
-from .infinite import timestep_infinite  # noqa: F401
+from .infinite import timestep_infinite, expectation_value_lazy  # noqa: F401
+from .algorithms import time_evolve  # noqa: F401
 from .statmech import (PerMPOInfEnv, leading_boundary, MultilineOp, MultilineEnv, leading_boundary_multiline,  # noqa: F401
                        expectation_value_multiline, fixedpoint_multiline)
 from . import statmech  # noqa: F401

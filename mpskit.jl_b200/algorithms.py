@@ -160,3 +160,23 @@ def timestep_inplace(psi, H, t, dt, alg, envs=None):
 def timestep(psi, H, t, dt, alg, envs=None):
     """timestep(psi, H, t, dt, alg, envs) = timestep!(copy(psi), ...) (tdvp.jl:93-96, 153-157)"""
     return timestep_inplace(psi.copy(), H, t, dt, alg, envs)
+
+
+def time_evolve(psi, H, t_span, alg=None, envs=None):
+    """time_evolve(psi, H, t_span, alg, envs) (src/algorithms/timestep/time_evolve.jl:17-40): step through the time points
+    of t_span with timestep (finite or infinite state), calling alg.finalize(t, psi, H, envs) after every step."""
+    from .infinite import InfiniteMPS, timestep_infinite
+    alg = alg or TDVP()
+    infinite = isinstance(psi, InfiniteMPS)
+    if not infinite:
+        psi = psi.copy()
+        envs = envs if envs is not None else environments(psi, H)
+    for k in range(len(t_span) - 1):
+        t, dt = t_span[k], t_span[k + 1] - t_span[k]
+        if infinite:
+            psi, envs = timestep_infinite(psi, H, t, dt, alg, envs)      # applies alg.finalize itself
+        else:
+            psi, envs = timestep_inplace(psi, H, t, dt, alg, envs)
+            if alg.finalize is not None:
+                psi, envs = alg.finalize(t, psi, H, envs)
+    return psi, envs

@@ -499,6 +499,40 @@ def find_groundstate_vumps(st: InfiniteMPS, H, alg: VUMPS = None, envs=None, log
     return st, envs, eps
 
 
+def _inf_ddAC(loc, st, H, envs):
+    """ddAC(loc, psi::InfiniteMPS, H, envs) (derivatives.jl:44-46) with the lazy-operator dispatch of derivatives.jl:298-323"""
+    from .lazyops import LazySum, MultipliedOperator
+    from .derivatives import LazySumOp, MultipliedOp
+    if isinstance(H, LazySum):
+        return LazySumOp([_inf_ddAC(loc, st, o, e) for o, e in zip(H.ops, envs.envs)])
+    if isinstance(H, MultipliedOperator):
+        return MultipliedOp(_inf_ddAC(loc, st, H.op, envs), H.f)
+    return MPO_ddAC(st.ctx, H[loc], envs.leftenv(loc, st), envs.rightenv(loc, st), st.AC[loc])
+
+
+def _inf_ddC(loc, st, H, envs):
+    """ddC(loc, psi::InfiniteMPS, H, envs) (derivatives.jl:34-36, 298-323)"""
+    from .lazyops import LazySum, MultipliedOperator
+    from .derivatives import LazySumOp, MultipliedOp
+    if isinstance(H, LazySum):
+        return LazySumOp([_inf_ddC(loc, st, o, e) for o, e in zip(H.ops, envs.envs)])
+    if isinstance(H, MultipliedOperator):
+        return MultipliedOp(_inf_ddC(loc, st, H.op, envs), H.f)
+    return MPO_ddC(st.ctx, envs.leftenv(loc + 1, st), envs.rightenv(loc, st), st.CR[loc])
+
+
+def expectation_value_lazy(st: InfiniteMPS, H, envs):
+    """expval.jl:182-192 for InfiniteMPS: LazySum -> sum of the parts, UntimedOperator -> f * <op>"""
+    from .lazyops import LazySum, MultipliedOperator
+    if isinstance(H, LazySum):
+        return sum(expectation_value_lazy(st, o, e) for o, e in zip(H.ops, envs.envs))
+    if isinstance(H, MultipliedOperator):
+        if H.istimed:
+            raise ValueError("expectation value of a time-dependent operator: evaluate it at a time first, H(t)")
+        return H.f * expectation_value_lazy(st, H.op, envs)
+    return expectation_value(st, H, envs)
+
+
 def timestep_infinite(st: InfiniteMPS, H, t, dt, alg=None, envs=None):
     """timestep(psi::InfiniteMPS, H, t, dt, alg::TDVP, envs; leftorthflag = true) (src/algorithms/timestep/tdvp.jl:21-59):
     AC and CR of every site of the unit cell are evolved on the device (mpsk_expv through `integrate`), regauged
@@ -506,13 +540,15 @@ def timestep_infinite(st: InfiniteMPS, H, t, dt, alg=None, envs=None):
     from .fixedpoint import integrate
     from .algorithms import TDVP
     alg = alg or TDVP()
-    envs = envs or environments(st, H)
+    if envs is None:
+        from .lazyops import _environments as _lazy_environments
+        envs = _lazy_environments(st, H)
     N = st.N
     newAL = []
     for loc in range(N):
-        hac = MPO_ddAC(st.ctx, H[loc], envs.leftenv(loc, st), envs.rightenv(loc, st), st.AC[loc])
+        hac = _inf_ddAC(loc, st, H, envs)
         ac = integrate(hac, st.AC[loc], t, dt, alg.integrator); hac.free()
-        hc = MPO_ddC(st.ctx, envs.leftenv(loc + 1, st), envs.rightenv(loc, st), st.CR[loc])
+        hc = _inf_ddC(loc, st, H, envs)
         c = integrate(hc, st.CR[loc], t, dt, alg.integrator); hc.free()
         newAL.append(regauge(ac, c))
     st = InfiniteMPS.from_AL(newAL, st.CR[N - 1], st.V, st.pspace, st.ctx, alg.tolgauge, alg.gaugemaxiter)

@@ -6,7 +6,17 @@ evaluated at `t + dt/2` by `integrate` (integrators.jl:20-25) and iterated by th
 from __future__ import annotations
 import numpy as np
 from .derivatives import MultipliedOp, LazySumOp, ddAC as _ddAC, ddAC2 as _ddAC2, ddC as _ddC
-from .environments import environments as _environments
+from .environments import environments as _finite_environments
+
+
+def _environments(state, op):
+    """environments(st, op): FinEnv for a FiniteMPS, MPOHamInfEnv for an InfiniteMPS (multipleenv.jl:13-26)"""
+    if hasattr(op, "_environments"):
+        return op._environments(state)
+    from .infinite import InfiniteMPS, environments as _infinite_environments
+    if isinstance(state, InfiniteMPS):
+        return _infinite_environments(state, op)
+    return _finite_environments(state, op)
 
 
 class MultipliedOperator:
@@ -133,3 +143,8 @@ class MultipleEnvironments:
     def drop_stale(self, state):
         for e in self.envs:
             e.drop_stale(state)
+
+    def recalculate(self, state, *args):            # multipleenv.jl:52-57
+        for e in self.envs:
+            e.recalculate(state, *args)
+        return self

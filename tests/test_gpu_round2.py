@@ -797,3 +797,48 @@ def test_infinite_tdvp_step(ctx, sym):
         Eg = np.sum(ev_inf(gs, Hd, genv)).real
         gs2, genv = timestep_infinite(gs, Hd, 0.0, dt, m.TDVP(), genv)
         assert abs(np.sum(ev_inf(gs2, Hd, genv)).real - Eg) <= 1e-10
+
+
+@pytest.mark.gpu
+def test_infinite_lazysum_tdvp_and_time_evolve(ctx):
+    """test/algorithms.jl:141-158 ("Infinite LazySum TDVP", "Infinite TimeDependent LazySum"): a step with
+    LazySum([3H, 1.55H, -0.1H]) equals the oracle's step of H over 4.45 dt (energy 1e-9); the time-dependent
+    Ht = MultipliedOperator(H, t -> 4) + MultipliedOperator(H, 1.45) stepped at t = 1 equals Ht(1.0) stepped at t = 0 (reference:
+    atol 1e-8); time_evolve over a time grid (time_evolve.jl:17-40) equals the chain of single steps, finite and infinite."""
+    from oracle import infinite as oi
+    from mpskit_b200.infinite import timestep_infinite, expectation_value_lazy, environments as env_inf
+    from mpskit_b200.lazyops import _environments as lazy_env
+    Ho = ompo.transverse_field_ising(1, 0.5)
+    po, Vo = OSpace((0,), (2,)), [OSpace((0,), (10,))]
+    dt = 0.05
+    Hd = dev_hamiltonian(Ho)
+    mk = lambda: m.InfiniteMPS.random(np.random.default_rng(5), to_dev_space(po), [to_dev_space(v) for v in Vo], ctx)
+    psi_o = oi.InfiniteMPS.random(np.random.default_rng(5), po, Vo)
+    psi_o, envs_o = oi.tdvp_step(psi_o, Ho, 4.45 * dt)
+    Eo = np.sum(oi.expectation_value(psi_o, Ho, envs_o)).real
+    Hlazy = m.LazySum([3 * m.UntimedOperator(Hd), 1.55 * m.UntimedOperator(Hd), -0.1 * m.UntimedOperator(Hd)])
+    psi, envs = timestep_infinite(mk(), Hlazy, 0.0, dt, m.TDVP())
+    E = np.sum(expectation_value_lazy(psi, Hlazy, envs)).real
+    assert abs(E - 4.45 * Eo) <= 1e-9 * abs(E)
+    Ht = m.MultipliedOperator(Hd, lambda t: 4.0) + m.MultipliedOperator(Hd, 1.45)
+    psi_a, envs_a = timestep_infinite(mk(), Ht(1.0), 0.0, dt, m.TDVP())
+    psi_t, envs_t = timestep_infinite(mk(), Ht, 1.0, dt, m.TDVP())
+    Ea = np.sum(expectation_value_lazy(psi_a, Ht(1.0), envs_a)).real
+    Et = np.sum(expectation_value_lazy(psi_t, Ht(1.0), envs_t)).real
+    assert abs(Ea - Et) <= 1e-8
+    # time_evolve == chained steps (infinite)
+    ts = [0.0, 0.05, 0.15]
+    p1, e1 = m.time_evolve(mk(), Hd, ts, m.TDVP())
+    p2, e2 = timestep_infinite(mk(), Hd, 0.0, 0.05, m.TDVP())
+    p2, e2 = timestep_infinite(p2, Hd, 0.05, 0.10, m.TDVP(), e2)
+    from mpskit_b200.infinite import expectation_value as ev_inf
+    assert abs(np.sum(ev_inf(p1, Hd, e1)).real - np.sum(ev_inf(p2, Hd, e2)).real) <= 1e-12
+    # time_evolve == chained steps (finite)
+    L = 6
+    Hf = dev_hamiltonian(ompo.heisenberg_u1(L))
+    pf = OSpace((-1, 1), (1, 1)); maxV = [of.gaussian_bond_space(8, k % 2) for k in range(1, L)]
+    mkf = lambda: m.FiniteMPS.random(np.random.default_rng(91), to_dev_space(pf), L, [to_dev_space(v) for v in maxV], ctx)
+    f1, _ = m.time_evolve(mkf(), Hf, ts, m.TDVP())
+    f2, ef = m.timestep(mkf(), Hf, 0.0, 0.05, m.TDVP())
+    f2, ef = m.timestep(f2, Hf, 0.05, 0.10, m.TDVP(), ef)
+    assert abs(abs(np.vdot(_full_state(f1), _full_state(f2))) - 1) <= 1e-12
