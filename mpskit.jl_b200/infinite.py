@@ -445,13 +445,13 @@ def expectation_value(st: InfiniteMPS, H, envs: MPOHamInfEnv):
 
 
 def calc_galerkin(st: InfiniteMPS, loc, envs):
-    """toolbox.jl:17-22"""
+    """toolbox.jl:17-22 (envs.opp may be a lazy sum: the derivative constructor dispatches, derivatives.jl:298-323)"""
     from .algorithms import _overlap
 
     class _P:       # what _overlap needs
         pass
     P = _P(); P.ctx, P.pq, P.pspace, P.dtype = st.ctx, st.pq, st.pspace, st.dtype
-    h = MPO_ddAC(st.ctx, envs.opp[loc], envs.leftenv(loc, st), envs.rightenv(loc, st), st.AC[loc])
+    h = _inf_ddAC(loc, st, envs.opp, envs)
     ac = h(st.AC[loc]); h.free()
     ac.scale(1.0 / ac.norm())
     AL = st.AL[loc]
@@ -473,7 +473,9 @@ class VUMPS:
 def find_groundstate_vumps(st: InfiniteMPS, H, alg: VUMPS = None, envs=None, log=None):
     """find_groundstate(psi::InfiniteMPS, H, alg::VUMPS, envs) (vumps.jl:29-92)"""
     alg = alg or VUMPS()
-    envs = envs or environments(st, H)
+    if envs is None:
+        from .lazyops import _environments as _lazy_environments
+        envs = _lazy_environments(st, H)                             # MPOHamInfEnv, or MultipleEnvironments for a LazySum
     N = st.N
     eps = max(calc_galerkin(st, i, envs) for i in range(N))
     for it in range(1, alg.maxiter + 1):
@@ -481,9 +483,9 @@ def find_groundstate_vumps(st: InfiniteMPS, H, alg: VUMPS = None, envs=None, log
         eig = Lanczos(tol=etol, krylovdim=30, maxiter=100)
         newAL = []
         for loc in range(N):                                       # _vumps_localupdate (vumps.jl:77-92)
-            hac = MPO_ddAC(st.ctx, H[loc], envs.leftenv(loc, st), envs.rightenv(loc, st), st.AC[loc])
+            hac = _inf_ddAC(loc, st, H, envs)
             _, ac = fixedpoint(hac, st.AC[loc], "SR", eig); hac.free()
-            hc = MPO_ddC(st.ctx, envs.leftenv(loc + 1, st), envs.rightenv(loc, st), st.CR[loc])
+            hc = _inf_ddC(loc, st, H, envs)
             _, c = fixedpoint(hc, st.CR[loc], "SR", eig); hc.free()
             newAL.append(regauge(ac, c))
         gtol = dyn_tol(eps, it, TOLGAUGE, 1e-5, 1e-8)

@@ -842,3 +842,32 @@ def test_infinite_lazysum_tdvp_and_time_evolve(ctx):
     f2, ef = m.timestep(mkf(), Hf, 0.0, 0.05, m.TDVP())
     f2, ef = m.timestep(f2, Hf, 0.05, 0.10, m.TDVP(), ef)
     assert abs(abs(np.vdot(_full_state(f1), _full_state(f2))) - 1) <= 1e-12
+
+
+@pytest.mark.gpu
+def test_find_groundstate_with_lazysum(ctx):
+    """test/algorithms.jl:42-92 ("LazySum Infinite", "LazySum Finite"): find_groundstate on LazySum([3H, -1H, 5.557H]) resp.
+    LazySum([3H, H, 5.557H]) (TFI g = 4, D = 6) gives the ground state of the summed operator: energies equal the scaled
+    energies of the plain run (reference: atol 1e-6; here 1e-9 relative), for VUMPS, DMRG and DMRG2."""
+    from mpskit_b200.infinite import expectation_value as ev_inf
+    Ho1 = ompo.transverse_field_ising(1, 4.0)
+    H1 = dev_hamiltonian(Ho1)
+    mk = lambda: m.InfiniteMPS.random(np.random.default_rng(7), m.Space((0,), (2,)), [m.Space((0,), (6,))], ctx)
+    st, envs, eps = m.find_groundstate_vumps(mk(), H1, m.VUMPS(tol=1e-10, maxiter=40))
+    e_plain = np.sum(ev_inf(st, H1, envs)).real
+    Hl = m.LazySum([3 * m.UntimedOperator(H1), -1 * m.UntimedOperator(H1), 5.557 * m.UntimedOperator(H1)])
+    stl, envl, epsl = m.find_groundstate_vumps(mk(), Hl, m.VUMPS(tol=1e-10, maxiter=40))
+    e_lazy = np.sum(m.expectation_value_lazy(stl, Hl, envl)).real
+    assert eps < 1e-9 and epsl < 1e-8
+    assert abs(e_lazy - 7.557 * e_plain) <= 1e-9 * abs(e_lazy)
+    # finite
+    L = 10
+    Hf = dev_hamiltonian(ompo.transverse_field_ising(L, 4.0))
+    Hfl = m.LazySum([3 * m.UntimedOperator(Hf), m.UntimedOperator(Hf), 5.557 * m.UntimedOperator(Hf)])
+    mkf = lambda: m.FiniteMPS.random(np.random.default_rng(8), m.Space((0,), (2,)), L, m.Space((0,), (6,)), ctx)
+    for alg in (m.DMRG(tol=1e-10, maxiter=10), m.DMRG2(tol=1e-10, maxiter=5, trscheme=m.truncdim(6), eigalg=m.Lanczos(tol=1e-12))):
+        p0, e0, _ = m.find_groundstate(mkf(), Hf, alg)
+        pl, el, _ = m.find_groundstate(mkf(), Hfl, alg)
+        E0 = m.expectation_value(p0, Hf, e0)
+        El = m.expectation_value(pl, Hfl, el)
+        assert abs(El - 9.557 * E0) <= 1e-9 * abs(El), (type(alg).__name__, El, E0)
