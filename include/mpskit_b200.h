@@ -142,6 +142,13 @@ int32_t mpsk_op_apply(mpsk_ctx* ctx, const mpsk_op* op, const mpsk_tensor* x, mp
 int32_t mpsk_eigsolve(mpsk_ctx* ctx, const mpsk_op* op, const mpsk_tensor* x0, int32_t which, int32_t hermitian,
                       int32_t krylovdim, int32_t maxiter, double tol, double* val_re, double* val_im,
                       mpsk_tensor* vec, mpsk_info* info);
+/* eigsolve(f, x0, howmany, which; tol) with Arnoldi / Krylov-Schur for the `howmany` most wanted eigenvalues (values only):
+ * transfer_spectrum (src/algorithms/toolbox.jl:42-58: eigsolve(flip(TransferMatrix(above.AL, below.AL)), init, num_vals, :LM)).
+ * vals: 2 * howmany doubles (re, im interleaved), most wanted first; *nvals (<= howmany) how many were produced (fewer only
+ * if the Krylov space closed early), *nconverged how many leading ones have residuals below tol.  howmany <= 3/5 krylovdim. */
+int32_t mpsk_eigsolve_values(mpsk_ctx* ctx, const mpsk_op* op, const mpsk_tensor* x0, int32_t which, int32_t howmany,
+                             int32_t krylovdim, int32_t maxiter, double tol, double* vals, int32_t* nvals, int32_t* nconverged,
+                             mpsk_info* info);
 /* integrate -> exponentiate(h, tau, y0) (src/algorithms/timestep/integrators.jl:20-25): y = exp(tau h) y0 */
 int32_t mpsk_expv(mpsk_ctx* ctx, const mpsk_op* op, double tau_re, double tau_im, const mpsk_tensor* y0,
                   int32_t krylovdim, int32_t maxiter, double tol, mpsk_tensor* y, mpsk_info* info);

@@ -39,3 +39,6 @@ from .excitations import (ProjectionOperator, AC_EffProj, AC2_EffProj, LinearCom
                           excitations, unit_mpo)
 from .excitations import expectation_value  # noqa: F401,F811  (general form: MPOHamiltonian / LinearCombination / ProjectionOperator)
 from .lazyops import MultipliedOperator, TimedOperator, UntimedOperator, LazySum, MultipleEnvironments  # noqa: F401
+from . import toolbox  # noqa: F401
+from .toolbox import (transfer_spectrum, marek_gap, correlation_length, entropy, entanglement_spectrum,  # noqa: F401
+                      expectation_value_local, correlator, decompose_localmpo)

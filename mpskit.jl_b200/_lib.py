@@ -86,6 +86,8 @@ PROTOTYPES = {
     "mpsk_op_time_mix": (C.c_int32, [_P, _P, C.c_int32, _DP, _DP]),
     "mpsk_op_apply": (C.c_int32, [_P, _P, _P, _P]),
     "mpsk_eigsolve": (C.c_int32, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, _DP, _DP, _P, C.POINTER(c_info)]),
+    "mpsk_eigsolve_values": (C.c_int32, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, _DP, _I32P, _I32P,
+                                         C.POINTER(c_info)]),
     "mpsk_expv": (C.c_int32, [_P, _P, C.c_double, C.c_double, _P, C.c_int32, C.c_int32, C.c_double, _P, C.POINTER(c_info)]),
     "mpsk_linsolve": (C.c_int32, [_P, _P, _P, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_double, _P,
                                   C.POINTER(c_info)]),

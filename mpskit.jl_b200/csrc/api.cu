@@ -470,6 +470,22 @@ int32_t mpsk_eigsolve(mpsk_ctx* ctx, const mpsk_op* op, const mpsk_tensor* x0, i
   return st;
 }
 
+int32_t mpsk_eigsolve_values(mpsk_ctx* ctx, const mpsk_op* op, const mpsk_tensor* x0, int32_t which, int32_t howmany, int32_t krylovdim,
+                             int32_t maxiter, double tol, double* vals, int32_t* nvals, int32_t* nconverged, mpsk_info* info) { ENTER(ctx);
+  Ctx* c = CTX(ctx);
+  if (!vals || howmany < 1) return c->fail(MPSK_EINVAL, "eigsolve_values: bad arguments");
+  MPSK_TRY(as_kl(c, CTEN(x0)));
+  std::vector<cplx> v((size_t)howmany, cplx(0.0));
+  int nc = 0, got = 0;
+  mpsk_info li; li.converged = 0; li.numiter = 0; li.numops = 0; li.normres = 0;
+  MPSK_TRY(eigsolve_arnoldi(c, OPH(op), CTEN(x0), which, krylovdim, maxiter, tol, nullptr, nullptr, &li, howmany, v.data(), &got, &nc));
+  for (int j = 0; j < howmany; ++j) { vals[2 * j] = j < got ? v[j].real() : 0.0; vals[2 * j + 1] = j < got ? v[j].imag() : 0.0; }
+  if (nvals) *nvals = got;
+  if (nconverged) *nconverged = nc;
+  if (info) *info = li;
+  return MPSK_OK;
+}
+
 int32_t mpsk_expv(mpsk_ctx* ctx, const mpsk_op* op, double tr, double ti, const mpsk_tensor* y0, int32_t krylovdim, int32_t maxiter,
                   double tol, mpsk_tensor* y, mpsk_info* info) { ENTER(ctx);
   Ctx* c = CTX(ctx);

@@ -392,10 +392,16 @@ int eigsolve_lanczos(Ctx* ctx, LinOp* op, const Tensor* x0, int which, int krylo
 }
 
 // ------------------------------------------------------------------------------------------ Arnoldi / Krylov-Schur
+// howmany > 1 (KrylovKit eigsolve(f, x0, howmany, which): transfer_spectrum, toolbox.jl:42-58): the leading `howmany`
+// positions of the Schur form hold the most wanted Ritz values in order of wantedness; the solve has converged when the
+// residuals |b^H z_j| of all of them are below tol.  `vals` receives *nvals = min(howmany, m) values, `nconv` how many leading ones
+// have converged; `vec` (first Schur vector = eigenvector of the most wanted value) may be NULL.
 int eigsolve_arnoldi(Ctx* ctx, LinOp* op, const Tensor* x0, int which, int krylovdim, int maxiter, double tol,
-                     cplx* val, Tensor* vec, mpsk_info* info) {
-  MPSK_TRY(check_vectors(ctx, op, x0, vec, krylovdim));
+                     cplx* val, Tensor* vec, mpsk_info* info, int howmany, cplx* vals, int* nvals, int* nconv) {
+  MPSK_TRY(check_vectors(ctx, op, x0, vec ? vec : x0, krylovdim));
   const int kd = krylovdim;
+  if (howmany < 1 || howmany > std::max(1, (3 * kd) / 5) || (howmany > 1 && howmany > kd - 1))
+    return ctx->fail(MPSK_EINVAL, "eigsolve: howmany must be between 1 and 3/5 of krylovdim (the restart keeps that many Schur vectors)");
   KSpace K;
   MPSK_TRY(K.init(ctx, op, kd));
   MPSK_TRY(op->to_local(x0, K.V[0]));
@@ -405,7 +411,7 @@ int eigsolve_arnoldi(Ctx* ctx, LinOp* op, const Tensor* x0, int which, int krylo
   const int ld = kd + 1;
   std::vector<cplx> B((size_t)ld * ld, cplx(0.0));      // Krylov decomposition A V_m = V_m B_m + v_{m+1} b^H, column-major
   auto b = [&](int i, int j) -> cplx& { return B[(size_t)i + (size_t)j * ld]; };
-  int numops = 0, m0 = 0, it = 0, m = 0; double res = 0; bool conv = false; cplx theta = 0;
+  int numops = 0, m0 = 0, it = 0, m = 0, want = 1, nc = 0; double res = 0; bool conv = false; cplx theta = 0;
   std::vector<cplx> S, Z, h;
   for (it = 1; it <= std::max(maxiter, 1); ++it) {
     double beta = 0;
@@ -417,19 +423,27 @@ int eigsolve_arnoldi(Ctx* ctx, LinOp* op, const Tensor* x0, int which, int krylo
       S.assign((size_t)m * m, cplx(0.0));
       for (int j = 0; j < m; ++j) for (int i = 0; i < m; ++i) S[(size_t)i + (size_t)j * m] = b(i, j);
       if (schur_complex(m, S, Z) != MPSK_OK) return ctx->fail(MPSK_EINTERNAL, "Schur decomposition of the projected matrix did not converge");
-      int p = 0;
-      for (int i = 1; i < m; ++i) if (more_wanted(S[(size_t)i + (size_t)i * m], S[(size_t)p + (size_t)p * m], which)) p = i;
-      schur_move(m, S, Z, p, 0);
+      want = std::min(howmany, m);
+      for (int j = 0; j < want; ++j) {                       // selection sort of the leading block by wantedness
+        int p = j;
+        for (int i = j + 1; i < m; ++i) if (more_wanted(S[(size_t)i + (size_t)i * m], S[(size_t)p + (size_t)p * m], which)) p = i;
+        schur_move(m, S, Z, p, j);
+      }
       theta = S[0];
-      res = std::abs(beta * Z[(size_t)(m - 1)]);             // |b^H z_0| with b = beta e_m
-      if (res < tol || beta < 1e-14) { conv = true; break; }
+      res = 0.0; nc = 0;
+      for (int j = 0; j < want; ++j) {                       // |b^H z_j| with b = beta e_m
+        const double rj = std::abs(beta * Z[(size_t)(m - 1) + (size_t)j * m]);
+        res = std::max(res, rj);
+        if (rj < tol && nc == j) ++nc;
+      }
+      if ((m >= howmany && nc >= howmany) || beta < 1e-14) { conv = true; if (beta < 1e-14) nc = want; break; }
       if (k + 1 < kd || it < maxiter) MPSK_TRY(K.scale_last(k + 1));
     }
     if (conv || it >= maxiter) break;
     // ---- Krylov-Schur restart: order the Schur form by wantedness, keep the leading block
     int keep = std::min(m - 1, std::max(1, (3 * kd) / 5));
     if (keep < 1) { m0 = 0; std::swap(K.V[0], K.V[m]); std::fill(B.begin(), B.end(), cplx(0.0)); continue; }
-    for (int j = 1; j < keep; ++j) {
+    for (int j = want; j < keep; ++j) {
       int p = j;
       for (int i = j + 1; i < m; ++i) if (more_wanted(S[(size_t)i + (size_t)i * m], S[(size_t)p + (size_t)p * m], which)) p = i;
       schur_move(m, S, Z, p, j);
@@ -442,14 +456,19 @@ int eigsolve_arnoldi(Ctx* ctx, LinOp* op, const Tensor* x0, int which, int krylo
     }
     m0 = keep;
   }
-  Tensor* xr = nullptr;
-  MPSK_TRY(K.newvec(&xr));
-  std::unique_ptr<Tensor> xr_guard(xr);
-  MPSK_TRY(K.combine(m, Z.data(), xr));                     // first Schur vector = eigenvector of the wanted Ritz value
-  MPSK_TRY(K.normalise_into(xr, xr, nullptr));
-  MPSK_TRY(op->from_local(xr, vec));
+  if (vec) {
+    Tensor* xr = nullptr;
+    MPSK_TRY(K.newvec(&xr));
+    std::unique_ptr<Tensor> xr_guard(xr);
+    MPSK_TRY(K.combine(m, Z.data(), xr));                   // first Schur vector = eigenvector of the wanted Ritz value
+    MPSK_TRY(K.normalise_into(xr, xr, nullptr));
+    MPSK_TRY(op->from_local(xr, vec));
+  }
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  *val = theta;
+  if (val) *val = theta;
+  if (vals) for (int j = 0; j < std::min(howmany, m); ++j) vals[j] = S[(size_t)j + (size_t)j * m];
+  if (nvals) *nvals = std::min(howmany, m);
+  if (nconv) *nconv = std::min(nc, std::min(howmany, m));
   if (info) { info->converged = conv ? 1 : 0; info->numiter = std::min(it, std::max(maxiter, 1)); info->numops = numops; info->normres = res; }
   return MPSK_OK;
 }

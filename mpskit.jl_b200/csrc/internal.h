@@ -335,7 +335,7 @@ int multiop_create(Ctx* ctx, const std::vector<LinOp*>& ops, int shift, MultiOp*
 int eigsolve_lanczos(Ctx* ctx, LinOp* op, const Tensor* x0, int which, int krylovdim, int maxiter, double tol,
                      cplx* val, Tensor* vec, mpsk_info* info);
 int eigsolve_arnoldi(Ctx* ctx, LinOp* op, const Tensor* x0, int which, int krylovdim, int maxiter, double tol,
-                     cplx* val, Tensor* vec, mpsk_info* info);
+                     cplx* val, Tensor* vec, mpsk_info* info, int howmany = 1, cplx* vals = nullptr, int* nvals = nullptr, int* nconv = nullptr);
 int expv_lanczos(Ctx* ctx, LinOp* op, cplx tau, const Tensor* y0, int krylovdim, int maxiter, double tol, Tensor* y,
                  mpsk_info* info);
 // (a0 + a1 f) x = b, restarted GMRES (KrylovKit.linsolve, mpohaminfenv.jl:95,113,146,164)

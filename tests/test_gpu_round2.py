@@ -871,3 +871,117 @@ def test_find_groundstate_with_lazysum(ctx):
         E0 = m.expectation_value(p0, Hf, e0)
         El = m.expectation_value(pl, Hfl, el)
         assert abs(El - 9.557 * E0) <= 1e-9 * abs(El), (type(alg).__name__, El, E0)
+
+
+@pytest.mark.parametrize("sym", ["trivial", "u1"])
+def test_transfer_spectrum_device(ctx, sym):
+    """transfer_spectrum(above; below, num_vals, sector) (toolbox.jl:42-58): several eigenvalues of the unit-cell transfer
+    matrix from ONE Krylov-Schur solve on the device (mpsk_eigsolve_values), against dense diagonalisation in the oracle:
+    neutral sector, a charged sector (U(1)) and above != below."""
+    from oracle import infinite as oi, toolbox as ot
+    from mpskit_b200 import toolbox as dt
+    if sym == "trivial":
+        p_o = OSpace((0,), (2,)); Vo = [OSpace((0,), (8,))]; sectors = [0]
+    else:
+        p_o = OSpace((-1, 1), (1, 1)); Vo = [OSpace((-2, 0, 2), (3, 5, 3)), OSpace((-1, 1), (5, 4))]; sectors = [0, 2]
+    st_o = oi.InfiniteMPS.random(np.random.default_rng(7), p_o, Vo)
+    st_d = m.InfiniteMPS.random(np.random.default_rng(7), to_dev_space(p_o), [to_dev_space(v) for v in Vo], ctx)
+    b_o = oi.InfiniteMPS.random(np.random.default_rng(8), p_o, Vo)
+    b_d = m.InfiniteMPS.random(np.random.default_rng(8), to_dev_space(p_o), [to_dev_space(v) for v in Vo], ctx)
+    for sec in sectors:
+        for (bo, bd) in ((None, None), (b_o, b_d)):
+            ref = ot.transfer_spectrum(st_o, below=bo, num_vals=40, sector=sec)
+            vals, info = dt.transfer_spectrum(st_d, below=bd, num_vals=6, sector=sec, tol=1e-11, return_info=True)
+            print("transfer spectrum", sym, sec, bo is not None, np.abs(vals), np.abs(ref[:6]), info)
+            assert len(vals) == 6 and info["converged"] >= 6
+            assert np.abs(np.abs(vals) - np.abs(ref[:6])).max() <= 1e-9
+            for v in vals:                                     # every value is an eigenvalue of the dense transfer matrix
+                assert np.abs(ref - v).min() <= 1e-9
+            if bo is None and sec == 0:
+                assert abs(vals[0] - 1.0) <= 1e-10
+    # a single value through the same entry reproduces fixedpoint(..., :LM, Arnoldi)
+    one = dt.transfer_spectrum(st_d, num_vals=1)
+    assert abs(one[0] - 1.0) <= 1e-10
+
+
+def test_toolbox_readouts_device(ctx):
+    """Local expectation values (expval.jl:22-65), correlators (correlators.jl:10-46), entropy and entanglement spectrum
+    (toolbox.jl:1-5,65-69) on the device: a finite U(1) state against its own dense state vector (charged virtual level in
+    the S+ S- correlator), and the reference's "correlation length / entropy" and "expectation value / correlator" test sets
+    (test/algorithms.jl:399-443) on VUMPS ground states against the oracle."""
+    from oracle import infinite as oi, toolbox as ot
+    from mpskit_b200 import toolbox as dt
+    from mpskit_b200.workloads import gaussian_bond_space
+    L = 6
+    p = m.Space((-1, 1), (1, 1))
+    psi = m.FiniteMPS.random(np.random.default_rng(11), p, L, [gaussian_bond_space(6, k % 2) for k in range(1, L)], ctx)
+    v = _full_state(psi)
+    nrm = np.vdot(v, v).real
+
+    def site_op(i, O):
+        out = np.eye(1)
+        for k in range(L):
+            out = np.kron(out, O if k == i else np.eye(2))
+        return out
+    Sp, Sm, Sz, _ = ompo.spin_ops(2)
+    ez = dt.expectation_value_local(psi, Sz)
+    for i in range(L):
+        assert abs(ez[i] - np.vdot(v, site_op(i, Sz) @ v) / nrm) <= 1e-12
+    SzSz = np.einsum('ac,bd->abcd', Sz, Sz); SpSm = np.einsum('ac,bd->abcd', Sp, Sm)
+    for at in (0, 2, 4):
+        ref = np.vdot(v, site_op(at, Sz) @ site_op(at + 1, Sz) @ v) / nrm
+        assert abs(dt.expectation_value_local(psi, SzSz, at) - ref) <= 1e-12
+        ref = np.vdot(v, site_op(at, Sp) @ site_op(at + 1, Sm) @ v) / nrm
+        assert abs(dt.expectation_value_local(psi, SpSm, at) - ref) <= 1e-12
+    G = dt.correlator(psi, SpSm, 1, range(2, 6))
+    for k, j in enumerate(range(2, 6)):
+        assert abs(G[k] - np.vdot(v, site_op(1, Sp) @ site_op(j, Sm) @ v) / nrm) <= 1e-12
+    szm = Sz.reshape(1, 2, 2, 1); idm = np.eye(2).reshape(1, 2, 2, 1)
+    assert abs(dt.expectation_value_local(psi, [szm, idm, szm], 0) - dt.correlator(psi, szm, szm, 0, 2)) <= 1e-12
+    # S.S: three virtual levels of charges -2, 0, 2 between the two MPO tensors (rectangular tensors in square slices)
+    SS = SzSz + 0.5 * (SpSm + np.einsum('ac,bd->abcd', Sm, Sp))
+
+    def ss_dense(i, j):
+        return site_op(i, Sz) @ site_op(j, Sz) + 0.5 * (site_op(i, Sp) @ site_op(j, Sm) + site_op(i, Sm) @ site_op(j, Sp))
+    assert abs(dt.expectation_value_local(psi, SS, 1) - np.vdot(v, ss_dense(1, 2) @ v) / nrm) <= 1e-12
+    Gss = dt.correlator(psi, SS, 0, range(1, 6, 2))
+    for k, j in enumerate(range(1, 6, 2)):
+        assert abs(Gss[k] - np.vdot(v, ss_dense(0, j) @ v) / nrm) <= 1e-12
+    s = np.linalg.svd(v.reshape(8, 8), compute_uv=False)
+    s = s[s > 1e-14] / np.sqrt(nrm)
+    spec = np.sort(np.concatenate([np.asarray(x) for x in dt.entanglement_spectrum(psi, 2).values()]))[::-1]
+    assert np.abs(spec[:len(s)] - s).max() <= 1e-10
+    assert abs(dt.entropy(psi, 2) - (-np.sum(s ** 2 * np.log(s ** 2)))) <= 1e-10
+    # ---- infinite: TFI g = 1 / g = 4, D = 10
+    res = {}
+    for g in (1.0, 4.0):
+        Ho = ompo.transverse_field_ising(1, g)
+        st_o = oi.InfiniteMPS.random(np.random.default_rng(3), OSpace((0,), (2,)), [OSpace((0,), (10,))])
+        st_o, _, _ = oi.vumps(st_o, Ho, tol=1e-10, maxiter=200)
+        st_d = m.InfiniteMPS.random(np.random.default_rng(3), m.Space((0,), (2,)), [m.Space((0,), (10,))], ctx)
+        st_d, _, eps = m.find_groundstate_vumps(st_d, dev_hamiltonian(Ho), m.VUMPS(tol=1e-10, maxiter=200))
+        xi_d = dt.correlation_length(st_d, num_vals=10)
+        xi_o = ot.correlation_length(st_o, num_vals=10)
+        S_d, S_o = dt.entropy(st_d)[0], ot.entropy(st_o)[0]
+        print("correlation length / entropy", g, xi_d, xi_o, S_d, S_o, eps)
+        tol = 1e-6 if g == 4.0 else 1e-3            # g = 1 is critical: the D = 10 state itself is only converged to 1e-10 in eps
+        assert abs(xi_d - xi_o) <= tol * xi_o and abs(S_d - S_o) <= tol
+        res[g] = (xi_d, S_d, st_d, st_o)
+    assert res[1.0][0] > res[4.0][0] and res[1.0][1] > res[4.0][1]          # test/algorithms.jl:411-412
+    st_d, st_o = res[4.0][2], res[4.0][3]
+    X = np.array([[0, 1], [1, 0]], dtype=float)
+    xm = X.reshape(1, 2, 2, 1)
+    XX = np.einsum('ac,bd->abcd', X, X)
+    ex = dt.expectation_value_local(st_d, X)[0]
+    exx = dt.expectation_value_local(st_d, XX, 0)
+    assert abs(ex - ot.expectation_value_site(st_o, X)[0]) <= 1e-8
+    assert abs(dt.expectation_value_local(st_d, [xm], 0) - ex) <= 1e-10
+    assert abs(dt.expectation_value_local(st_d, [xm, xm], 0) - exx) <= 1e-10
+    assert abs(dt.expectation_value_local(st_d, [xm, xm], 1) - exx) <= 1e-10
+    G = dt.correlator(st_d, xm, xm, 0, range(1, 5))
+    G2 = dt.correlator(st_d, XX, 0, range(2, 5, 2))
+    Go = ot.correlator(st_o, xm, xm, 0, range(1, 5))
+    assert np.abs(G - Go).max() <= 1e-8
+    assert abs(G[1] - G2[0]) <= 1e-10 and abs(G[3] - G2[1]) <= 1e-10 and abs(G[0] - exx) <= 1e-10
+    assert abs(G[1] - dt.expectation_value_local(st_d, [xm, idm, xm], 0)) <= 1e-10
+    assert abs(dt.correlator(st_d, xm, xm, 0, 1) - exx) <= 1e-10

@@ -381,3 +381,97 @@ def test_infinite_tdvp_oracle_energy_conservation():
     gs2, genv = oi.tdvp_step(gs, H, 0.1, genv)
     assert abs(np.sum(oi.expectation_value(gs2, H, genv)).real - Eg) < 1e-10
     assert abs(Eg - (-1.063544409973)) < 2e-11
+
+
+def _dense_state(psi):
+    T = psi.get_AC(0)
+    for i in range(1, psi.L):
+        T = np.tensordot(T, psi.get_AR(i), axes=([-1], [0]))
+    return T.reshape(-1)
+
+
+def _site_op(L, i, O, d=2):
+    out = np.eye(1)
+    for k in range(L):
+        out = np.kron(out, O if k == i else np.eye(d))
+    return out
+
+
+def test_toolbox_oracle_local_expectation_values_and_correlators_vs_dense_state():
+    """oracle/toolbox.py (expval.jl:22-65, correlators.jl:10-46) on a finite U(1) state against the dense state vector:
+    single-site <Sz_i>, a two-site operator through decompose_localmpo, an explicit local MPO, and <S+_i S-_j> correlators
+    whose MPO tensors carry a charged virtual level."""
+    from oracle import toolbox as ot
+    L = 6
+    p = Space((-1, 1), (1, 1))
+    psi = of.FiniteMPS.random(np.random.default_rng(11), p, L, [of.gaussian_bond_space(6, k % 2) for k in range(1, L)])
+    v = _dense_state(psi)
+    nrm = np.vdot(v, v).real
+    Sp, Sm, Sz, _ = ompo.spin_ops(2)
+    ez = ot.expectation_value_site(psi, Sz)
+    for i in range(L):
+        assert abs(ez[i] - np.vdot(v, _site_op(L, i, Sz) @ v) / nrm) < 1e-12
+    SzSz = np.einsum('ac,bd->abcd', Sz, Sz)
+    SpSm = np.einsum('ac,bd->abcd', Sp, Sm)
+    for at in (0, 2, 4):
+        ref = np.vdot(v, _site_op(L, at, Sz) @ _site_op(L, at + 1, Sz) @ v) / nrm
+        assert abs(ot.expectation_value_nsite(psi, SzSz, at) - ref) < 1e-12
+        ref = np.vdot(v, _site_op(L, at, Sp) @ _site_op(L, at + 1, Sm) @ v) / nrm
+        assert abs(ot.expectation_value_nsite(psi, SpSm, at) - ref) < 1e-12
+    O1, O2 = ot.decompose_localmpo(SpSm)
+    G = ot.correlator(psi, O1, O2, 1, range(2, 6))
+    for k, j in enumerate(range(2, 6)):
+        ref = np.vdot(v, _site_op(L, 1, Sp) @ _site_op(L, j, Sm) @ v) / nrm
+        assert abs(G[k] - ref) < 1e-12
+    # three-site local MPO with an identity in the middle == the correlator two sites apart (test/algorithms.jl:438)
+    idm = np.eye(2).reshape(1, 2, 2, 1)
+    szm = Sz.reshape(1, 2, 2, 1)
+    Gz = ot.correlator(psi, szm, szm, 0, [2])
+    # the local-MPO form transfers with AL from the left edge and closes with CR CR'
+    assert abs(ot.expectation_value_localmpo(psi, [szm, idm, szm], 0) - Gz[0]) < 1e-12
+    # entanglement spectrum / entropy against the Schmidt decomposition of the dense state
+    s = np.linalg.svd(v.reshape(2 ** 3, 2 ** 3), compute_uv=False)
+    s = s[s > 1e-14] / np.sqrt(nrm)
+    spec = np.sort(np.concatenate(list(ot.entanglement_spectrum(psi, 2).values())))[::-1]
+    assert np.allclose(spec[:len(s)], s, atol=1e-12)
+    assert abs(ot.entropy(psi, 2) - (-np.sum(s ** 2 * np.log(s ** 2)))) < 1e-12
+
+
+def test_toolbox_oracle_correlation_length_and_entropy_infinite():
+    """test/algorithms.jl:399-413 ("correlation length / entropy") and :415-443 ("expectation value / correlator") on the
+    oracle: VUMPS ground states of the TFI chain at g = 1 (critical) and g = 4 (gapped), D = 10.  The reference only asserts
+    orderings / 1e-2; here the identities hold to 1e-10 and the magnetisation matches the exact infinite-chain value."""
+    from oracle import infinite as oi, toolbox as ot
+    res = {}
+    for g in (1.0, 4.0):
+        H = ompo.transverse_field_ising(1, g)
+        st = oi.InfiniteMPS.random(np.random.default_rng(3), Space((0,), (2,)), [Space((0,), (10,))])
+        st, envs, eps = oi.vumps(st, H, tol=1e-10, maxiter=200)
+        spec = ot.transfer_spectrum(st, num_vals=10)
+        assert abs(spec[0] - 1.0) < 1e-10 and np.all(np.abs(spec[1:]) < 1 - 1e-6)
+        res[g] = (ot.correlation_length(spec), ot.entropy(st)[0], st)
+    assert res[1.0][0] > res[4.0][0] and res[1.0][1] > res[4.0][1]
+    st = res[4.0][2]
+    X = np.array([[0, 1], [1, 0]], dtype=float); Z = np.diag([1.0, -1.0])
+    xm = X.reshape(1, 2, 2, 1); idm = np.eye(2).reshape(1, 2, 2, 1)
+    XX = np.einsum('ac,bd->abcd', X, X)
+    ex = ot.expectation_value_site(st, X)[0]
+    assert abs(ot.expectation_value_localmpo(st, [xm], 0) - ex) < 1e-10
+    exx = ot.expectation_value_nsite(st, XX, 0)
+    assert abs(ot.expectation_value_localmpo(st, [xm, xm], 0) - exx) < 1e-10
+    G = ot.correlator(st, xm, xm, 0, range(1, 5))
+    G2 = ot.correlator(st, *ot.decompose_localmpo(XX), 0, range(2, 5, 2))
+    assert abs(G[1] - G2[0]) < 1e-10 and abs(G[3] - G2[1]) < 1e-10 and abs(G[0] - exx) < 1e-10
+    assert abs(G[1] - ot.expectation_value_localmpo(st, [xm, idm, xm], 0)) < 1e-10
+    # exact transverse magnetisation of H = -sum ZZ - g sum X:  <X> = (1/pi) int_0^pi (g + cos k) / sqrt(1 + g^2 + 2 g cos k) dk
+    import scipy.integrate as si
+    g = 4.0
+    mx = si.quad(lambda k: (g + np.cos(k)) / np.sqrt(1 + g * g + 2 * g * np.cos(k)), 0, np.pi)[0] / np.pi
+    assert abs(ex.real - mx) < 1e-8
+    # connected correlations decay with the correlation length of the transfer spectrum
+    conn = np.abs(np.array(ot.correlator(st, Z.reshape(1, 2, 2, 1), Z.reshape(1, 2, 2, 1), 0, range(1, 9))))
+    xi_fit = -1.0 / np.polyfit(np.arange(4, 9), np.log(conn[3:]), 1)[0]
+    assert abs(xi_fit - res[4.0][0]) < 0.1 * res[4.0][0]
+    # marek gap bookkeeping on a synthetic spectrum: theta = pi sector, two values there
+    eps_, delta, theta = ot.marek_gap(np.array([1.0, -0.5, 0.4, -0.25, -0.2]))
+    assert abs(eps_ - np.log(2)) < 1e-14 and abs(delta - (np.log(4) - np.log(2))) < 1e-14 and abs(theta - np.pi) < 1e-14
