@@ -1,4 +1,4 @@
-"""changebonds for finite MPS.  `SvdCut` (changebonds/svdcut.jl:14-24): truncated SVD of every bond matrix.
+"""changebonds for finite and infinite MPS.  `SvdCut` (changebonds/svdcut.jl:14-24): truncated SVD of every bond matrix.
 `changebonds(psi, H, OptimalExpand(trscheme))`: mirror of src/algorithms/changebonds/optimalexpand.jl:80-110.
 Every tensor operation runs on the device: two-site matvec, leftnull / rightnull (full Householder QR per coupled sector),
 the projections onto the null spaces, the truncated SVD of the projected two-site tensor, direct sums along the bonds, QRpos."""
@@ -10,6 +10,7 @@ from .tensor import DeviceTensor
 from .derivatives import ddAC2
 from .environments import environments
 from .dmrg import contract_ac2, truncdim, notrunc, tsvd, _mul_right
+from .spaces import infimum
 from .finitemps import qrpos
 from .operators import SparseMPOSlice
 
@@ -69,7 +70,9 @@ def changebonds_inplace(psi, H, alg: OptimalExpand, envs=None, log=None):
     """changebonds!(psi::FiniteMPS, H, alg::OptimalExpand, envs) (optimalexpand.jl:84-110): the state is unchanged, every bond
     gains the dominant directions of the two-site update orthogonal to the current tensors (zeros on site i, optimal
     vectors on site i + 1)."""
-    envs = envs if envs is not None else environments(psi, H)
+    rand = isinstance(alg, RandExpand)                # changebonds!(psi, alg::RandExpand) (randexpand.jl:41-63): random AC2
+    if not rand:
+        envs = envs if envs is not None else environments(psi, H)
     ctx = psi.ctx
     L = len(psi)
     for i in range(L - 1):
@@ -79,8 +82,11 @@ def changebonds_inplace(psi, H, alg: OptimalExpand, envs=None, log=None):
         if NL.Vr.dim == 0 or NR.Vl.dim == 0:          # the bond is already full rank on one side: nothing to add
             continue
         ac2 = contract_ac2(psi, ac, ar)
-        h = ddAC2(i, psi, H, envs, ac2)
-        AC2 = h(ac2); h.free(); ac2.free()
+        if rand:
+            AC2 = DeviceTensor.random(ctx, ac2.Vl, ac2.mch, ac2.Vr, alg.seed + i, psi.dtype); ac2.free()
+        else:
+            h = ddAC2(i, psi, H, envs, ac2)
+            AC2 = h(ac2); h.free(); ac2.free()
         B = contract_adjoint_left(NL, AC2)            # adjoint(NL) * AC2
         inter = _right_overlap(psi, B, NR)            # ... * adjoint(NR): bond tensor [k'; k'']
 
@@ -102,17 +108,29 @@ def changebonds_inplace(psi, H, alg: OptimalExpand, envs=None, log=None):
         psi.AC[i + 1] = (nc, nar)
         for t in (NL, NR, AC2, B, inter, U, S, ar_le):
             t.free()
-        envs.drop_stale(psi)
+        if envs is not None:
+            envs.drop_stale(psi)
+    if rand:
+        k = max(L - 2, 0)
+        c = psi.CR[k].copy()                          # normalize!(psi) (randexpand.jl:62); psi is a shallow copy: do not scale
+        c.scale(1.0 / c.norm())                       # a bond tensor it may share with the input state
+        c._is_bond = True
+        psi.CLs[k + 1] = c
+        psi.ACs = [None] * psi.L
+        return psi
     return psi, envs
 
 
 def changebonds(psi, H=None, alg=None, envs=None, log=None):
     """changebonds(psi, H, alg::OptimalExpand, envs) = changebonds!(copy(psi), ...) (optimalexpand.jl:80-82);
     changebonds(psi, alg::SvdCut) = changebonds!(copy(psi), alg) (svdcut.jl:13)"""
-    if isinstance(H, SvdCut) and alg is None:
+    if alg is None:                                   # changebonds(psi, alg)
         H, alg = None, H
+    if hasattr(psi, "N") and not hasattr(psi, "L"):   # InfiniteMPS
+        return changebonds_infinite(psi, H, alg, envs, log)
     if isinstance(alg, SvdCut):
-        return svdcut_inplace(psi.copy(), alg, log)
+        out = svdcut_inplace(psi.copy(), alg, log)
+        return (out, envs) if H is not None else out   # svdcut.jl:48-50
     return changebonds_inplace(psi.copy(), H, alg, envs, log)
 
 
@@ -152,3 +170,242 @@ def svdcut_inplace(psi, alg: SvdCut, log=None):
     c.scale(1.0 / c.norm())                                                   # normalize!(psi)
     psi.ACs = [None] * psi.L
     return psi
+
+
+# ------------------------------------------------------------------------------------------ InfiniteMPS
+@dataclass
+class RandExpand:
+    """randexpand.jl:11-13"""
+    trscheme: tuple = field(default_factory=lambda: truncdim(1))
+    seed: int = 0
+
+
+@dataclass
+class VUMPSSvdCut:
+    """vumpssvd.jl:12-17"""
+    tol_gauge: float = 1e-14
+    tol: float = 1e-12
+    tol_eigenval: float = 1e-12
+    trscheme: tuple = field(default_factory=notrunc)
+
+
+def _bond_leg(st):
+    class _P:
+        pass
+    P = _P(); P.ctx, P.pq, P.pspace = st.ctx, (0,), st.pspace
+    return P
+
+
+def _mul_left(Cm, A):
+    return _call(A.ctx, A.ctx.lib.mpsk_mul_bond_left, Cm.h, A.h, modulus=A.Vl.modulus)
+
+
+def _mul_right_t(A, Cm):
+    return _call(A.ctx, A.ctx.lib.mpsk_mul_bond_right, A.h, Cm.h, modulus=A.Vl.modulus)
+
+
+def _expansion_vectors(st, i, AC2, trscheme, log):
+    """VL = leftnull(AL[i]); VR = rightnull(AR[i+1]); U, _, V = tsvd(VL' * AC2 * VR'; trunc) -> (VL * U, V * VR)
+    (optimalexpand.jl:26-33, randexpand.jl:23-30), all on the device"""
+    N = st.N
+    VL = leftnull(st.AL[i % N])
+    VR = rightnull(st.AR[(i + 1) % N])
+    B = contract_adjoint_left(VL, AC2)
+    inter = _right_overlap(st, B, VR)
+    U, S, V, eps = tsvd(_bond_leg(st), inter, trscheme, normalize=False)
+    if log is not None:
+        from .dmrg import tsvd_spectrum
+        log.append(dict(pos=i, added=V.Vl.as_dict(), spectrum={q: s for q, (s, k) in tsvd_spectrum(st.ctx).items()}))
+    alp = _mul_right_t(VL, U)
+    arp = _mul_left(V, VR)
+    for t in (VL, VR, B, inter, U, S, V):
+        t.free()
+    return alp, arp
+
+
+def _expand(st, ALp, ARp):
+    """_expand!(psi, AL', AR') (changebonds.jl:13-38): AL -> [AL AL'; 0 0], AR -> [AR 0; AR' 0], CR -> [C 0; 0 0], AC = AL * CR,
+    normalize!(psi); direct sums along the bonds on the device (mpsk_tensor_cat).  ALp[i]: [l p; n_i] on the bond right of
+    site i; ARp[i]: [n_{i-1} p; r] on the bond left of site i."""
+    from .infinite import InfiniteMPS, mul_right
+    ctx, N, dt = st.ctx, st.N, st.dtype
+    AL, AR, CR, AC = [None] * N, [None] * N, [None] * N, [None] * N
+    for i in range(N):
+        nl = ARp[i].Vl                    # n_{i-1}: space added on the bond left of site i  (== _lastspace(AL'[i-1])')
+        nr = ALp[i].Vr                    # n_i
+        al = cat(st.AL[i], ALp[i], 1)
+        lz = DeviceTensor.zeros(ctx, nl, al.mch, al.Vr, dt)
+        AL[i] = cat(al, lz, 0)
+        ar = cat(st.AR[i], ARp[i], 0)
+        rz = DeviceTensor.zeros(ctx, ar.Vl, ar.mch, nr, dt)
+        AR[i] = cat(ar, rz, 1)
+        c = st.CR[i]
+        cz = DeviceTensor.zeros(ctx, c.Vl, c.mch, nr, dt)
+        c1 = cat(c, cz, 1)
+        cz2 = DeviceTensor.zeros(ctx, nr, c.mch, c1.Vr, dt)
+        CR[i] = cat(c1, cz2, 0)
+        CR[i]._is_bond = True
+        for t in (al, lz, ar, rz, cz, c1, cz2):
+            t.free()
+    for i in range(N):                    # normalize!(psi) (infinitemps.jl:252-256): CR and AC separately
+        CR[i].scale(1.0 / CR[i].norm())
+        AC[i] = mul_right(AL[i], CR[i])
+        AC[i].scale(1.0 / AC[i].norm())
+    V = [AL[i].Vl for i in range(N)]
+    return InfiniteMPS(AL, AR, CR, AC, V, st.pspace, ctx)
+
+
+def _inf_ddAC2(loc, st, H, envs, ac2):
+    """ddAC2(loc, psi::InfiniteMPS, H, envs) (derivatives.jl:55-58)"""
+    from .derivatives import MPO_ddAC2
+    return MPO_ddAC2(st.ctx, H[loc], H[loc + 1], envs.leftenv(loc, st), envs.rightenv(loc + 1, st), ac2)
+
+
+def changebonds_infinite(st, H=None, alg=None, envs=None, log=None):
+    """changebonds(psi::InfiniteMPS, [H,] alg[, envs]) for OptimalExpand (optimalexpand.jl:16-38), RandExpand
+    (randexpand.jl:15-35), SvdCut (svdcut.jl:36-46) and VUMPSSvdCut (vumpssvd.jl:19-86).  Returns (state, envs) when a
+    Hamiltonian is given, else the state."""
+    from . import infinite as di
+    if alg is None:
+        H, alg = None, H
+    N = st.N
+    if isinstance(alg, (OptimalExpand, RandExpand)):
+        if isinstance(alg, OptimalExpand):
+            envs = envs if envs is not None else di.environments(st, H)
+        ALp, ARp = [None] * N, [None] * N
+        for i in range(N):
+            ac2 = contract_ac2(st, st.AC[i], st.AR[(i + 1) % N])
+            if isinstance(alg, OptimalExpand):
+                h = _inf_ddAC2(i, st, H, envs, ac2)
+                AC2 = h(ac2); h.free(); ac2.free()
+            else:                                                # randomize!(AC2)
+                AC2 = DeviceTensor.random(st.ctx, ac2.Vl, ac2.mch, ac2.Vr, alg.seed + i, st.dtype); ac2.free()
+            ALp[i], ARp[(i + 1) % N] = _expansion_vectors(st, i, AC2, alg.trscheme, log)
+            AC2.free()
+        new = _expand(st, ALp, ARp)
+        return (new, envs) if H is not None else new
+    if isinstance(alg, SvdCut):
+        copied = list(st.AL)
+        ncr = st.CR[0]
+        P = _bond_leg(st)
+        for i in range(N):
+            U, S, V, eps = tsvd(P, st.CR[i], alg.trscheme, normalize=False)
+            if log is not None:
+                log.append(dict(pos=i, kept=S.Vl.as_dict(), eps_trunc=eps))
+            ncr = S
+            copied[i] = _mul_right_t(copied[i], U)
+            copied[(i + 1) % N] = _mul_left(U.adjoint(), copied[(i + 1) % N])
+            V.free()
+        Vs = [copied[i].Vl for i in range(N)]
+        new = di.InfiniteMPS.from_AL(copied, ncr, Vs, st.pspace, st.ctx)
+        for i in range(N):                                       # normalize!
+            new.CR[i].scale(1.0 / new.CR[i].norm()); new.AC[i].scale(1.0 / new.AC[i].norm())
+        return (new, envs) if H is not None else new
+    if isinstance(alg, VUMPSSvdCut):
+        return _vumps_svdcut(st, H, alg, envs, log)
+    raise TypeError(f"changebonds: unsupported algorithm {alg!r}")
+
+
+def _isometry(ctx, Vrow, Vcol, dtype):
+    """isometry(Vcol, Vrow)' as a bond tensor [Vrow; Vcol]: the identity on the leading min(n_row, n_col) indices of every
+    common sector (vumpssvd.jl:72)"""
+    M = np.zeros((Vrow.dim, 1, Vcol.dim), dtype=dtype)
+    ro, co = Vrow.offsets(), Vcol.offsets()
+    for jl, q in enumerate(Vrow.charges):
+        if q in Vcol.charges:
+            jr = Vcol.charges.index(q)
+            k = min(Vrow.dims[jl], Vcol.dims[jr])
+            M[ro[jl]:ro[jl] + k, 0, co[jr]:co[jr] + k] = np.eye(k)
+    t = DeviceTensor.from_dense(ctx, M, Vrow, (0,), Vcol, dtype)
+    t._is_bond = True
+    return t
+
+
+def _vumps_svdcut_n(st, H, alg, envs, log):
+    """changebonds_n (vumpssvd.jl:49-86)"""
+    from . import infinite as di
+    from .fixedpoint import fixedpoint, Arnoldi
+    from .finitemps import qrpos as _qrpos
+    ctx, mod = st.ctx, st.pspace.modulus
+    eig = Arnoldi(tol=alg.tol_eigenval, krylovdim=30, maxiter=100, hermitian=True)
+    for loc in range(st.N):
+        N = st.N
+        if envs is None or envs.dependency is not st:      # leftenv(envs, pos, state) recalculates for a new state
+            envs = di.environments(st, H)
+        ac2 = contract_ac2(st, st.AC[loc], st.AR[(loc + 1) % N])
+        h2 = _inf_ddAC2(loc, st, H, envs, ac2)
+        _, nac2 = fixedpoint(h2, ac2, "SR", eig); h2.free(); ac2.free()
+        hc = di._inf_ddC((loc + 1) % N, st, H, envs)
+        _, nc2 = fixedpoint(hc, st.CR[(loc + 1) % N], "SR", eig); hc.free()
+        AL1, S, Vt, eps = tsvd(st, nac2, alg.trscheme, normalize=False)
+        if log is not None:
+            log.append(dict(pos=loc, kept=S.Vl.as_dict(), eps_trunc=eps))
+        AC = _mul_left(S, Vt)                               # S * V: [n p; r]
+        QAC, r1 = _qrpos(ctx, AC, mod)
+        QC, r2 = _qrpos(ctx, nc2, mod)
+        if QAC.Vr == QC.Vr:
+            AL2 = _mul_right_t(QAC, QC.adjoint())
+        else:                                               # AL2 = QAC * dom_map' * QC'
+            E = _isometry(ctx, QAC.Vr, QC.Vr, st.dtype)
+            t = _mul_right_t(QAC, E)
+            AL2 = _mul_right_t(t, QC.adjoint())
+            E.free(); t.free()
+        copied = list(st.AL)
+        copied[loc] = AL1
+        copied[(loc + 1) % N] = AL2
+        Vs = [copied[i].Vl for i in range(N)]
+        for t in (nac2, nc2, S, Vt, AC, QAC, r1, QC, r2):
+            t.free()
+        st = di.InfiniteMPS.from_tensors(copied, Vs, st.pspace, ctx, tol=alg.tol_gauge)
+    return st, di.environments(st, H)
+
+
+def _truncspace_cut(st, target):
+    """changebonds(psi, SvdCut(trscheme = truncspace(target))) for InfiniteMPS (svdcut.jl:36-46 with TensorKit's truncspace):
+    per sector the leading min(n, target_n) singular vectors; the restriction is a rectangular identity applied on the device"""
+    from . import infinite as di
+    N = st.N
+    copied = list(st.AL)
+    ncr = st.CR[0]
+    P = _bond_leg(st)
+    for i in range(N):
+        U, S, V, eps = tsvd(P, st.CR[i], notrunc(), normalize=False)
+        keep = infimum(S.Vl, target)
+        E = _isometry(st.ctx, S.Vl, keep, st.dtype)        # [n; n']
+        Uc = _mul_right_t(U, E)
+        t = _mul_right_t(S, E)
+        ncr = _mul_left(E.adjoint(), t)
+        ncr._is_bond = True
+        copied[i] = _mul_right_t(copied[i], Uc)
+        copied[(i + 1) % N] = _mul_left(Uc.adjoint(), copied[(i + 1) % N])
+        for x in (U, S, V, E, t):
+            x.free()
+    Vs = [copied[i].Vl for i in range(N)]
+    new = di.InfiniteMPS.from_AL(copied, ncr, Vs, st.pspace, st.ctx)
+    for i in range(N):
+        new.CR[i].scale(1.0 / new.CR[i].norm()); new.AC[i].scale(1.0 / new.AC[i].norm())
+    return new
+
+
+def _vumps_svdcut(st, H, alg, envs, log):
+    """changebonds(state, H, alg::VUMPSSvdCut, envs) (vumpssvd.jl:81-86); unit cells of one site are doubled, expanded and
+    collapsed again (changebonds_1, vumpssvd.jl:19-47)"""
+    from . import infinite as di
+    if st.N > 1:
+        return _vumps_svdcut_n(st, H, alg, envs, log)
+    from .operators import MPOHamiltonian
+    two = di.InfiniteMPS.from_tensors([st.AL[0], st.AL[0]], [st.V[0], st.V[0]], st.pspace, st.ctx)
+    H2 = MPOHamiltonian([H[0], H[0]])
+    two, _ = _vumps_svdcut_n(two, H2, alg, None, log)
+    D1, D2 = two.AL[0].Vl, two.AL[1].Vl
+    if D1 != D2:
+        two = _truncspace_cut(two, infimum(D1, D2))
+    one = di.InfiniteMPS.from_AL([two.AL[0]], two.CR[0], [two.AL[0].Vl], st.pspace, st.ctx, alg.tol_gauge)
+    return one, di.environments(one, H)
+
+
+def dot_infinite(a, b, krylovdim=30, tol=1e-12):
+    """dot(psi1::InfiniteMPS, psi2::InfiniteMPS): dominant eigenvalue of the mixed transfer matrix of the AL tensors, by the
+    device Arnoldi on the unit-cell transfer operator"""
+    from .toolbox import transfer_spectrum
+    return transfer_spectrum(b, below=a, num_vals=1, tol=tol, krylovdim=krylovdim)[0]

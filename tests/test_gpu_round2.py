@@ -985,3 +985,94 @@ def test_toolbox_readouts_device(ctx):
     assert abs(G[1] - G2[0]) <= 1e-10 and abs(G[3] - G2[1]) <= 1e-10 and abs(G[0] - exx) <= 1e-10
     assert abs(G[1] - dt.expectation_value_local(st_d, [xm, idm, xm], 0)) <= 1e-10
     assert abs(dt.correlator(st_d, xm, xm, 0, 1) - exx) <= 1e-10
+
+
+@pytest.mark.parametrize("sym", ["trivial", "u1"])
+def test_changebonds_infinite_device(ctx, sym):
+    """changebonds for InfiniteMPS on the device (test/algorithms.jl:271-295): OptimalExpand (optimalexpand.jl:16-38), RandExpand
+    (randexpand.jl:15-35), SvdCut (svdcut.jl:36-46), VUMPSSvdCut (vumpssvd.jl:19-86) against the oracle restatement: added
+    sector dimensions bit-exact, singular values of the projected two-site tensor 1e-9, overlaps 1 (the reference asserts
+    1e-8), unchanged energies 1e-11, VUMPSSvdCut energies 1e-9."""
+    from oracle import infinite as oi, changebonds as ocb
+    from mpskit_b200 import infinite as di
+    import importlib
+    dcb = importlib.import_module(m.__name__ + ".changebonds")
+    if sym == "trivial":
+        Ho = ompo.transverse_field_ising(2, 0.7); p_o = OSpace((0,), (2,)); Vo = [OSpace((0,), (4,)), OSpace((0,), (4,))]
+    else:
+        Ho = ompo.heisenberg_u1(2); p_o = OSpace((-1, 1), (1, 1)); Vo = [OSpace((-2, 0, 2), (1, 2, 1)), OSpace((-1, 1), (2, 2))]
+    Hd = dev_hamiltonian(Ho)
+    st_o = oi.InfiniteMPS.random(np.random.default_rng(5), p_o, Vo)
+    st_d = m.InfiniteMPS.random(np.random.default_rng(5), to_dev_space(p_o), [to_dev_space(v) for v in Vo], ctx)
+    envs_o = oi.MPOHamInfEnv(st_o, Ho); envs_d = di.environments(st_d, Hd)
+    E0 = di.expectation_value(st_d, Hd, envs_d)
+    assert np.abs(E0 - oi.expectation_value(st_o, Ho, envs_o)).max() <= 1e-10
+    # ---- OptimalExpand
+    log_o, log_d = [], []
+    oe_o, _ = ocb.optimal_expand(st_o, Ho, ("truncdim", 2), envs_o, log_o)
+    oe_d, _ = m.changebonds(st_d, Hd, m.OptimalExpand(trscheme=m.truncdim(2)), envs_d, log=log_d)
+    for i in range(2):
+        assert oe_d.V[i].as_dict() == oe_o.V[i].as_dict()                      # bookkeeping bit-exact
+        assert log_d[i]["added"] == log_o[i]["added"]
+        for q, s in log_o[i]["spectrum"].items():
+            assert np.abs(np.asarray(log_d[i]["spectrum"][q]) - s).max() <= 1e-9
+    assert abs(abs(dcb.dot_infinite(st_d, oe_d)) - 1.0) <= 1e-10               # test/algorithms.jl:288
+    E1 = di.expectation_value(oe_d, Hd, di.environments(oe_d, Hd))
+    assert np.abs(E1 - E0).max() <= 1e-11
+    for i in range(2):                                                          # gauge relations of the expanded state
+        lhs = di.mul_right(oe_d.AL[i], oe_d.CR[i]).to_dense(); rhs = di.mul_left(oe_d.CR[i - 1], oe_d.AR[i]).to_dense()
+        assert np.abs(lhs - rhs).max() <= 1e-12
+    # ---- RandExpand
+    re_d = m.changebonds(st_d, dcb.RandExpand(trscheme=m.truncdim(3), seed=4))
+    assert all(re_d.V[i].dim == st_d.V[i].dim + 3 for i in range(2))
+    assert abs(abs(dcb.dot_infinite(st_d, re_d)) - 1.0) <= 1e-10               # test/algorithms.jl:279
+    # ---- SvdCut back to the original dimension
+    cut_d = m.changebonds(oe_d, m.SvdCut(trscheme=m.truncdim(st_d.V[0].dim)))
+    cut_o = ocb.svdcut(oe_o, ("truncdim", st_o.V[0].dim))
+    assert [cut_d.V[i].as_dict() for i in range(2)] == [cut_o.V[i].as_dict() for i in range(2)]
+    assert abs(abs(dcb.dot_infinite(st_d, cut_d)) - 1.0) <= 1e-10
+    # ---- VUMPSSvdCut: two-site expansion step
+    vs_o, venv_o = ocb.vumps_svdcut(st_o, Ho, ("notrunc",))
+    vs_d, venv_d = m.changebonds(st_d, Hd, dcb.VUMPSSvdCut())
+    assert [vs_d.V[i].as_dict() for i in range(2)] == [vs_o.V[i].as_dict() for i in range(2)]
+    Ev_d = di.expectation_value(vs_d, Hd, venv_d); Ev_o = oi.expectation_value(vs_o, Ho, venv_o)
+    print("VUMPSSvdCut", sym, [vs_d.V[i].as_dict() for i in range(2)], Ev_d.real.sum(), Ev_o.real.sum(), E0.real.sum())
+    assert abs(Ev_d.real.sum() - Ev_o.real.sum()) <= 1e-9 and Ev_d.real.sum() < E0.real.sum()
+    tr_d = m.changebonds(vs_d, m.SvdCut(trscheme=m.truncdim(4)))
+    assert tr_d.V[1].dim < vs_d.V[1].dim                                        # test/algorithms.jl:293-294
+    if sym == "trivial":
+        # unit cell of one site: doubled, expanded, collapsed (changebonds_1, vumpssvd.jl:19-47)
+        H1 = dev_hamiltonian(ompo.transverse_field_ising(1, 0.7))
+        s1 = m.InfiniteMPS.random(np.random.default_rng(6), m.Space((0,), (2,)), [m.Space((0,), (3,))], ctx)
+        e_before = di.expectation_value(s1, H1, di.environments(s1, H1)).real.sum()
+        s1n, env1 = m.changebonds(s1, H1, dcb.VUMPSSvdCut())
+        e_after = di.expectation_value(s1n, H1, env1).real.sum()
+        print("VUMPSSvdCut N=1", s1.V[0].dim, "->", s1n.V[0].dim, e_before, e_after)
+        assert s1n.N == 1 and s1n.V[0].dim > s1.V[0].dim and e_after < e_before
+
+
+def test_randexpand_finite_device(ctx):
+    """changebonds(psi::FiniteMPS, RandExpand) (randexpand.jl:40-63; test/algorithms.jl:302-304): the state is unchanged
+    (overlap 1), every bond that can grow does, and SvdCut brings the dimensions back."""
+    import importlib
+    dcb = importlib.import_module(m.__name__ + ".changebonds")
+    from mpskit_b200.workloads import gaussian_bond_space
+    L = 8
+    p = m.Space((-1, 1), (1, 1))
+    psi = m.FiniteMPS.random(np.random.default_rng(2), p, L, [gaussian_bond_space(4, k % 2) for k in range(1, L)], ctx)
+    def state_from_left(s):          # AL[0] ... AL[L-2] AC[L-1]: only tensors the left-to-right sweep leaves materialised
+        T = s.AL[0].to_dense()
+        for i in range(1, L - 1):
+            T = np.tensordot(T, s.AL[i].to_dense(), axes=([-1], [0]))
+        return np.tensordot(T, s.AC[L - 1].to_dense(), axes=([-1], [0])).reshape(-1)
+    v0 = state_from_left(psi)
+    new = m.changebonds(psi, dcb.RandExpand(trscheme=m.truncdim(2), seed=9))
+    v1 = state_from_left(new)
+    ov = np.vdot(v0, v1) / np.sqrt(np.vdot(v0, v0).real * np.vdot(v1, v1).real)
+    dims0 = [psi.AL[i].Vr.dim for i in range(L - 1)]; dims1 = [new.AL[i].Vr.dim for i in range(L - 1)]
+    print("RandExpand finite", dims0, dims1, abs(ov))
+    assert abs(abs(ov) - 1.0) <= 1e-12
+    assert all(b >= a for a, b in zip(dims0, dims1)) and sum(dims1) > sum(dims0)
+    back = m.changebonds(new, m.SvdCut(trscheme=m.truncdim(4)))
+    v2 = _full_state(back)
+    assert abs(abs(np.vdot(v0, v2)) / np.sqrt(np.vdot(v0, v0).real * np.vdot(v2, v2).real) - 1.0) <= 1e-10
