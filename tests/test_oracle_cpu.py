@@ -475,3 +475,35 @@ def test_toolbox_oracle_correlation_length_and_entropy_infinite():
     # marek gap bookkeeping on a synthetic spectrum: theta = pi sector, two values there
     eps_, delta, theta = ot.marek_gap(np.array([1.0, -0.5, 0.4, -0.25, -0.2]))
     assert abs(eps_ - np.log(2)) < 1e-14 and abs(delta - (np.log(4) - np.log(2))) < 1e-14 and abs(theta - np.pi) < 1e-14
+
+
+def test_changebonds_infinite_oracle_invariants():
+    """oracle/changebonds.py (changebonds.jl:13-38, optimalexpand.jl:16-38, randexpand.jl:15-35, svdcut.jl:36-46,
+    vumpssvd.jl:49-86) on trivial and U(1) two-site unit cells: expansions leave the state (overlap, energy per site, gauge
+    relations) unchanged -- test/algorithms.jl:279,288 assert the overlap to 1e-8 --, SvdCut restores the dimensions,
+    VUMPSSvdCut grows the bonds and lowers the energy."""
+    from oracle import infinite as oi, changebonds as ocb
+    for sym in ("trivial", "u1"):
+        if sym == "trivial":
+            H = ompo.transverse_field_ising(2, 0.7); p = Space((0,), (2,)); Vs = [Space((0,), (4,)), Space((0,), (4,))]
+        else:
+            H = ompo.heisenberg_u1(2); p = Space((-1, 1), (1, 1)); Vs = [Space((-2, 0, 2), (1, 2, 1)), Space((-1, 1), (2, 2))]
+        st = oi.InfiniteMPS.random(np.random.default_rng(5), p, Vs)
+        envs = oi.MPOHamInfEnv(st, H)
+        E0 = oi.expectation_value(st, H, envs)
+        log = []
+        oe, _ = ocb.optimal_expand(st, H, ("truncdim", 2), envs, log)
+        assert all(oe.V[i].dim == st.V[i].dim + 2 for i in range(2)) and len(log) == 2
+        assert abs(abs(ocb.dot(st, oe)) - 1) < 1e-12
+        assert np.abs(oi.expectation_value(oe, H, oi.MPOHamInfEnv(oe, H)) - E0).max() < 1e-11
+        for i in range(2):
+            a = oe.AL[i]; assert np.allclose(np.einsum('apb,apc->bc', a.conj(), a), np.eye(a.shape[2]), atol=1e-12)
+            b = oe.AR[i]; assert np.allclose(np.einsum('apb,cpb->ac', b, b.conj()), np.eye(b.shape[0]), atol=1e-12)
+            assert np.allclose(np.einsum('apb,bc->apc', oe.AL[i], oe.CR[i]), np.einsum('ab,bpc->apc', oe.CR[i - 1], oe.AR[i]), atol=1e-12)
+        re_ = ocb.rand_expand(st, ("truncdim", 3), np.random.default_rng(1))
+        assert all(re_.V[i].dim == st.V[i].dim + 3 for i in range(2)) and abs(abs(ocb.dot(st, re_)) - 1) < 1e-12
+        cut = ocb.svdcut(oe, ("truncdim", st.V[0].dim))
+        assert [v.as_dict() for v in cut.V] == [v.as_dict() for v in st.V] and abs(abs(ocb.dot(st, cut)) - 1) < 1e-10
+        vs, venv = ocb.vumps_svdcut(st, H, ("notrunc",))
+        assert vs.V[0].dim > st.V[0].dim and vs.V[1].dim > st.V[1].dim
+        assert oi.expectation_value(vs, H, venv).real.sum() < E0.real.sum() - 0.1
