@@ -43,3 +43,5 @@ from .lazyops import MultipliedOperator, TimedOperator, UntimedOperator, LazySum
 from . import toolbox  # noqa: F401
 from .toolbox import (transfer_spectrum, marek_gap, correlation_length, entropy, entanglement_spectrum,  # noqa: F401
                       expectation_value_local, correlator, decompose_localmpo)
+from .propagator import DynamicalDMRG, propagator  # noqa: F401
+from .statmech import VOMPS, MixedPerMPOInfEnv, approximate_vomps  # noqa: F401

@@ -73,5 +73,11 @@ def approximate_inplace(psi, toapprox, alg, envs=None, log=None):
 
 
 def approximate(psi, toapprox, alg, envs=None, log=None):
-    """approximate(psi, toapprox, alg) = approximate!(copy(psi), ...) (fvomps.jl:2-4)"""
+    """approximate(psi, toapprox, alg) = approximate!(copy(psi), ...) (fvomps.jl:2-4); InfiniteMPS with VOMPS:
+    src/algorithms/approximate/vomps.jl:1-11 (statmech.approximate_vomps)"""
+    if hasattr(psi, "N") and not hasattr(psi, "L"):
+        from .statmech import VOMPS, approximate_vomps
+        if not isinstance(alg, VOMPS):
+            raise TypeError("approximate on InfiniteMPS: alg must be VOMPS")
+        return approximate_vomps(psi, toapprox, alg, envs, log)
     return approximate_inplace(psi.copy(), toapprox, alg, envs, log)

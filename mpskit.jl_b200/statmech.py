@@ -108,6 +108,8 @@ def calc_galerkin(psi, loc, envs):
 
 def leading_boundary(psi: InfiniteMPS, opp, alg: VUMPS = None, envs=None, log=None):
     """leading_boundary(psi, opp, alg::VUMPS, envs) (statmech/vumps.jl:15-84)"""
+    if isinstance(alg, VOMPS):                      # leading_boundary(psi, O, alg::VOMPS) (statmech/vomps.jl:27-87): power method
+        return approximate_vomps(psi, (opp, None), alg, envs, log)
     alg = alg or VUMPS(tol=1e-10)
     envs = envs or environments(psi, opp)
     N = psi.N
@@ -289,3 +291,130 @@ def leading_boundary_multiline(rows, opp, alg: VUMPS = None, envs=None, log=None
         if eps <= alg.tol:
             break
     return rows, envs, eps
+
+
+# ------------------------------------------------------------------------------------------ VOMPS
+from dataclasses import dataclass as _dataclass
+
+
+@_dataclass
+class VOMPS:
+    """statmech/vomps.jl:17-25 (dynamic gauge / environment tolerances of defaults.jl:38-57)"""
+    tol: float = 1e-12
+    maxiter: int = 100
+    verbosity: int = 0
+    finalize: object = None
+
+
+class MixedPerMPOInfEnv:
+    """environments(below, (opp, above)) for one row (permpoinfenv.jl:29-63; mixed_fixpoints, permpoinfenv.jl:138-189):
+    dominant eigenvectors of TransferMatrix(above.AL, O, below.AL) and TransferMatrix(above.AR, O, below.AR) -- rectangular
+    device operators, Krylov-Schur Arnoldi inside the library -- normalised with lambda = <C_below| dC(GL, GR) |C_above>.
+    above = None: above is the state itself (leading_boundary with VOMPS)."""
+
+    def __init__(self, below: InfiniteMPS, opp, above: InfiniteMPS = None, tol=1e-12):
+        self.opp, self.above, self.tol = opp, above, tol
+        self.lw = self.rw = None
+        self.dependency = None
+        self.recalculate(below)
+
+    def recalculate(self, below, tol=None):
+        from .infinite import transfer_left, transfer_right
+        tol = self.tol if tol is None else tol
+        above = below if self.above is None else self.above
+        N, ctx = below.N, below.ctx
+        lc = [-c for c in self.opp[0].domcharges]
+        rc = [c for c in self.opp[N - 1].imcharges]
+        Vb, Va = below.V[0], above.V[0]
+        same = self.lw is not None and self.lw[0].Vl == Vb and self.lw[0].Vr == Va
+        L0 = self.lw[0] if same else DeviceTensor.random(ctx, Vb, lc, Va, 17, below.dtype)
+        R0 = self.rw[N - 1] if same else DeviceTensor.random(ctx, Va, rc, Vb, 18, below.dtype)
+        mids = [self.opp[i] for i in range(N)]
+        TL = TransferMatrix(list(above.AL), mids, list(below.AL)).flip()
+        TR = TransferMatrix(list(above.AR), mids, list(below.AR))
+        alg = Arnoldi(tol=tol, krylovdim=30, maxiter=100, hermitian=False)
+        GL, GR = [None] * N, [None] * N
+        _, GL[0] = fixedpoint(TL, L0, "LM", alg)
+        for c in range(1, N):
+            GL[c] = transfer_left(GL[c - 1], self.opp[c - 1], above.AL[c - 1], below.AL[c - 1])
+        _, GR[N - 1] = fixedpoint(TR, R0, "LM", alg)
+        for c in range(N - 2, -1, -1):
+            GR[c] = transfer_right(GR[c + 1], self.opp[c + 1], above.AR[c + 1], below.AR[c + 1])
+        for c in range(N):                                  # permpoinfenv.jl:180-185 (+ removal of the arbitrary Arnoldi phase)
+            h = MPO_ddC(ctx, GL[(c + 1) % N], GR[c], above.CR[c])
+            y = h(above.CR[c]); h.free()
+            lam = complex(below.CR[c].dot(y)); y.free()
+            GL[(c + 1) % N].scale(np.conj(lam) / abs(lam) / np.sqrt(abs(lam)))
+            GR[c].scale(1.0 / np.sqrt(abs(lam)))
+        self.lw, self.rw, self.dependency = GL, GR, below
+        return self
+
+    def leftenv(self, pos, psi):
+        if self.dependency is not psi:
+            self.recalculate(psi)
+        return self.lw[pos % psi.N]
+
+    def rightenv(self, pos, psi):
+        if self.dependency is not psi:
+            self.recalculate(psi)
+        return self.rw[pos % psi.N]
+
+
+def _ac_proj(col, psi, envs):
+    """ac_proj(row, col, below, envs) (derivatives.jl:216-219): dAC(above.AC, opp, leftenv, rightenv) in the spaces of below"""
+    top = psi if envs.above is None else envs.above
+    h = MPO_ddAC(psi.ctx, envs.opp[col], envs.leftenv(col, psi), envs.rightenv(col, psi), top.AC[col])
+    y = h(top.AC[col]); h.free()
+    return y
+
+
+def _c_proj(col, psi, envs):
+    """c_proj(row, col, below, envs) (derivatives.jl:204-207)"""
+    top = psi if envs.above is None else envs.above
+    h = MPO_ddC(psi.ctx, envs.leftenv(col + 1, psi), envs.rightenv(col, psi), top.CR[col])
+    y = h(top.CR[col]); h.free()
+    return y
+
+
+def calc_galerkin_mixed(psi, loc, envs):
+    """calc_galerkin(state::MPSMultiline, envs::PerMPOInfEnv) (toolbox.jl:26-38) for one row: AC' = normalize(dAC * above.AC)"""
+    ac = _ac_proj(loc, psi, envs)
+    ac.scale(1.0 / ac.norm())
+    AL = psi.AL[loc]
+    ov = _overlap(psi, ac, AL)
+    proj = mul_right(AL, ov)
+    ac.axpy(-1.0, proj)
+    out = ac.norm()
+    for t in (ac, ov, proj):
+        t.free()
+    return out
+
+
+def approximate_vomps(psi: InfiniteMPS, toapprox, alg: VOMPS = None, envs=None, log=None):
+    """approximate(psi::InfiniteMPS, (O, above), alg::VOMPS, envs) (src/algorithms/approximate/vomps.jl:1-80) for one row:
+    AL <- regauge(ac_proj, c_proj) on every site, uniform gauge restored (from_AL), environments recalculated, until the
+    Galerkin error of the projected tensor is below tol.  toapprox = (O, None) is the power method
+    leading_boundary(psi, O, VOMPS()) (src/algorithms/statmech/vomps.jl:27-87)."""
+    alg = alg or VOMPS()
+    opp, above = toapprox
+    envs = envs if envs is not None else MixedPerMPOInfEnv(psi, opp, above)
+    N = psi.N
+    eps = max(calc_galerkin_mixed(psi, i, envs) for i in range(N))
+    for it in range(1, alg.maxiter + 1):
+        newAL = []
+        for col in range(N):                                       # _vomps_localupdate (vomps.jl:62-80)
+            ac = _ac_proj(col, psi, envs)
+            c = _c_proj(col, psi, envs)
+            newAL.append(regauge(ac, c))
+            ac.free(); c.free()
+        gtol = dyn_tol(eps, it, TOLGAUGE, 1e-5, 1e-8)
+        psi = InfiniteMPS.from_AL(newAL, psi.CR[N - 1], psi.V, psi.pspace, psi.ctx, gtol, 100)
+        envs.recalculate(psi, dyn_tol(eps, it, 1e-12, 1e-5, 1e-5))
+        if alg.finalize is not None:
+            psi, envs = alg.finalize(it, psi, toapprox, envs)
+        eps = max(calc_galerkin_mixed(psi, i, envs) for i in range(N))
+        if log is not None:
+            log.append(dict(iter=it, eps=eps))
+        if eps <= alg.tol:
+            break
+    return psi, envs, eps

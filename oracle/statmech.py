@@ -205,3 +205,93 @@ def leading_boundary_multiline(rows, slices, tol=1e-10, maxiter=100, log=None):
         if eps <= tol:
             break
     return rows, envs, eps
+
+
+# ------------------------------------------------------------------------------------------ VOMPS (approximate / power method)
+class MixedPerMPOInfEnv:
+    """environments(below, (opp, above)) for one row (permpoinfenv.jl:29-63, mixed_fixpoints 138-189): fixed points of
+    TransferMatrix(above.AL, O, below.AL) / TransferMatrix(above.AR, O, below.AR), normalised with
+    lambda = <C_below| dC(GL, GR) |C_above>; above = None means above = the state itself (leading_boundary)."""
+
+    def __init__(self, below: InfiniteMPS, slices, above: InfiniteMPS = None, tol=1e-12):
+        self.opp, self.above, self.tol = slices, above, tol
+        self.lw = self.rw = None
+        self.dependency = None
+        self.recalculate(below)
+
+    def recalculate(self, below, tol=None):
+        tol = self.tol if tol is None else tol
+        above = below if self.above is None else self.above
+        N = below.N
+        chi = self.opp[0].odim
+        Db, Da = below.AL[0].shape[0], above.AL[0].shape[0]
+        rng = np.random.default_rng(0)
+        ok = self.lw is not None and self.lw[0].shape == (Db, chi, Da)
+        L0 = self.lw[0] if ok else rng.standard_normal((Db, chi, Da)) + 0j
+        R0 = self.rw[N - 1] if ok else rng.standard_normal((Da, chi, Db)) + 0j
+
+        def TL(v):
+            for i in range(N):
+                v = transfer_left_sparse(v, self.opp[i], above.AL[i], below.AL[i])
+            return v
+
+        def TR(v):
+            for i in range(N - 1, -1, -1):
+                v = transfer_right_sparse(v, self.opp[i], above.AR[i], below.AR[i])
+            return v
+        GL, GR = [None] * N, [None] * N
+        _, GL[0], _ = eigsolve_arnoldi(TL, L0, "LM", tol, 30, 100)
+        for c in range(1, N):
+            GL[c] = transfer_left_sparse(GL[c - 1], self.opp[c - 1], above.AL[c - 1], below.AL[c - 1])
+        _, GR[N - 1], _ = eigsolve_arnoldi(TR, R0, "LM", tol, 30, 100)
+        for c in range(N - 2, -1, -1):
+            GR[c] = transfer_right_sparse(GR[c + 1], self.opp[c + 1], above.AR[c + 1], below.AR[c + 1])
+        for c in range(N):                      # permpoinfenv.jl:180-185
+            lam = np.vdot(below.CR[c], dC_dense(above.CR[c], GL[(c + 1) % N], GR[c]))
+            GL[(c + 1) % N] = GL[(c + 1) % N] * (np.conj(lam) / abs(lam)) / np.sqrt(abs(lam))
+            GR[c] = GR[c] / np.sqrt(abs(lam))
+        self.lw, self.rw, self.dependency = GL, GR, below
+        return self
+
+    def leftenv(self, pos, psi):
+        if self.dependency is not psi:
+            self.recalculate(psi)
+        return self.lw[pos % psi.N]
+
+    def rightenv(self, pos, psi):
+        if self.dependency is not psi:
+            self.recalculate(psi)
+        return self.rw[pos % psi.N]
+
+
+def calc_galerkin_mixed(psi, loc, envs):
+    """toolbox.jl:26-38: AC' = normalize(dAC * above.AC); || AC' - AL AL' AC' ||"""
+    above = psi if envs.above is None else envs.above
+    y = dAC_sparse(above.AC[loc], envs.opp[loc], envs.leftenv(loc, psi), envs.rightenv(loc, psi))
+    y = y / np.linalg.norm(y)
+    AL = psi.AL[loc]
+    return float(np.linalg.norm(y - np.einsum('apb,cqb,cqd->apd', AL, np.conj(AL), y, optimize=True)))
+
+
+def vomps(psi: InfiniteMPS, slices, above: InfiniteMPS = None, tol=1e-12, maxiter=100, log=None):
+    """approximate(psi, (O, above), VOMPS()) (src/algorithms/approximate/vomps.jl:19-80) for one row; above = None:
+    leading_boundary(psi, O, VOMPS()) (src/algorithms/statmech/vomps.jl:27-87), the power method on the current state"""
+    envs = MixedPerMPOInfEnv(psi, slices, above)
+    N = psi.N
+    eps = max(calc_galerkin_mixed(psi, i, envs) for i in range(N))
+    for it in range(1, maxiter + 1):
+        top = psi if above is None else above
+        newAL = []
+        for col in range(N):
+            ac = dAC_sparse(top.AC[col], slices[col], envs.leftenv(col, psi), envs.rightenv(col, psi))        # ac_proj
+            c = dC_dense(top.CR[col], envs.leftenv(col + 1, psi), envs.rightenv(col, psi))                    # c_proj
+            newAL.append(regauge(ac, c, psi.V[col], psi.V[(col + 1) % N], psi.pq, psi.modulus))
+        gtol = dyn_tol(eps, it, TOLGAUGE, 1e-5, 1e-8)
+        psi = InfiniteMPS.from_AL(newAL, psi.CR[N - 1], psi.V, psi.pq, gtol, 100, psi.modulus)
+        envs.recalculate(psi, dyn_tol(eps, it, 1e-12, 1e-5, 1e-5))
+        eps = max(calc_galerkin_mixed(psi, i, envs) for i in range(N))
+        if log is not None:
+            log.append(dict(iter=it, eps=eps))
+        if eps <= tol:
+            break
+    return psi, envs, eps

@@ -1076,3 +1076,81 @@ def test_randexpand_finite_device(ctx):
     back = m.changebonds(new, m.SvdCut(trscheme=m.truncdim(4)))
     v2 = _full_state(back)
     assert abs(abs(np.vdot(v0, v2)) / np.sqrt(np.vdot(v0, v0).real * np.vdot(v2, v2).real) - 1.0) <= 1e-10
+
+
+@pytest.mark.parametrize("flavour", ["NaiveInvert", "Jeckelmann"])
+def test_dynamical_dmrg_propagator(ctx, flavour):
+    """propagator(psi0, z, H, DynamicalDMRG(flavour)) (corvector.jl:57-158; test/algorithms.jl:342-366 checks it to 1e-8 against
+    the pole of a window state): on a finite chain whose bond dimension holds the full Hilbert space the sweeps converge to
+    the exact resolvent <psi0| (z - H)^-1 |psi0> -- trivial TFI and U(1) Heisenberg chains against dense linear algebra, and
+    against the oracle restatement."""
+    from oracle import propagator as oprop
+    L = 6
+    for sym in ("trivial", "u1"):
+        if sym == "trivial":
+            Ho = ompo.transverse_field_ising(L, 1.3); p_o = OSpace((0,), (2,)); maxV = OSpace((0,), (8,))
+            psi_o = of.FiniteMPS.random(np.random.default_rng(4), p_o, L, maxV)
+            psi_d = m.FiniteMPS.random(np.random.default_rng(4), to_dev_space(p_o), L, to_dev_space(maxV), ctx)
+        else:
+            Ho = ompo.heisenberg_u1(L); p_o = OSpace((-1, 1), (1, 1))
+            maxVs = [of.gaussian_bond_space(20, k % 2) for k in range(1, L)]
+            psi_o = of.FiniteMPS.random(np.random.default_rng(4), p_o, L, maxVs)
+            psi_d = m.FiniteMPS.random(np.random.default_rng(4), to_dev_space(p_o), L, [to_dev_space(v) for v in maxVs], ctx)
+        Hd = dev_hamiltonian(Ho)
+        v = _full_state(psi_d)
+        Hm = ompo.dense_hamiltonian(Ho)
+        E = np.vdot(v, Hm @ v).real / np.vdot(v, v).real
+        for shift in (-0.5, 0.3):
+            z = E + shift + 0.3j
+            ref = np.vdot(v, np.linalg.solve(z * np.eye(len(v)) - Hm, v))
+            log = []
+            val, sol = m.propagator(psi_d, z, Hd, m.DynamicalDMRG(flavour=flavour, tol=1e-10, maxiter=30), log=log)
+            val_o, _ = oprop.propagator(psi_o, z, Ho, flavour, tol=1e-10, maxiter=30)
+            print("DDMRG", flavour, sym, shift, val, ref, abs(val - ref), abs(val - val_o), len(log))
+            assert abs(val - ref) <= 1e-9 * max(1.0, abs(ref)) and abs(val - val_o) <= 1e-9 * max(1.0, abs(ref))
+            assert log[-1]["eps"] <= 1e-10
+
+
+def test_vomps_approximate_and_power_method(ctx):
+    """approximate(psi, (W, psi), VOMPS()) (src/algorithms/approximate/vomps.jl:19-80; test/algorithms.jl:447-466): one
+    first-order time-evolution MPO W = 1 - i dt H (the W^I form of the TFI chain, bond dimension 2) applied to a two-site
+    InfiniteMPS is approximated in the same manifold and compared with a TDVP step (the reference asserts |dot| = 1 within dt;
+    here 1e-8) and with the oracle VOMPS through the gauge-invariant entanglement spectra (1e-8).  Then the power method
+    leading_boundary(psi, O, VOMPS()) (statmech/vomps.jl:27-87) against VUMPS on the classical Ising model."""
+    from oracle import infinite as oi, statmech as osm, toolbox as ot
+    from mpskit_b200 import statmech as dsm, toolbox as dt_
+    g, dt = 4.0, 1e-3
+    tau = -1j * dt
+    X = np.array([[0, 1], [1, 0]], dtype=complex); Z = np.diag([1.0, -1.0]).astype(complex); I2 = np.eye(2, dtype=complex)
+    W = np.zeros((2, 2, 2, 2), dtype=complex)
+    W[0, :, :, 0] = I2 + tau * (-g * X); W[0, :, :, 1] = np.sqrt(tau) * (-Z); W[1, :, :, 0] = np.sqrt(tau) * Z
+    sl_o = [ompo.dense_mpo_slice(W), ompo.dense_mpo_slice(W)]
+    sl_d = [dev_slice(s) for s in sl_o]
+    Ho = ompo.transverse_field_ising(2, g)
+    Vo = [OSpace((0,), (6,)), OSpace((0,), (6,))]
+    st_o = oi.InfiniteMPS.random(np.random.default_rng(9), OSpace((0,), (2,)), Vo)
+    st_d = m.InfiniteMPS.random(np.random.default_rng(9), m.Space((0,), (2,)), [to_dev_space(v) for v in Vo], ctx)
+    log_o, log_d = [], []
+    a_o, _, eps_o = osm.vomps(st_o, sl_o, st_o, tol=1e-12, maxiter=100, log=log_o)
+    a_d, _, eps_d = m.approximate(st_d, (sl_d, st_d), m.VOMPS(tol=1e-12, maxiter=100), log=log_d)
+    print("VOMPS", len(log_d), len(log_o), eps_d, eps_o)
+    assert eps_d <= 1e-11 and len(log_d) <= len(log_o) + 2
+    for i in range(2):
+        so = np.sort(np.concatenate(list(ot.entanglement_spectrum(a_o, i).values())))[::-1]
+        sd = np.sort(np.concatenate([np.asarray(x) for x in dt_.entanglement_spectrum(a_d, i).values()]))[::-1]
+        assert np.abs(so - sd).max() <= 1e-8
+    t_d, _ = m.timestep_infinite(st_d, dev_hamiltonian(Ho), 0.0, dt)
+    ov = abs(m.dot_infinite(a_d, t_d)); ov0 = abs(m.dot_infinite(st_d, t_d))
+    print("VOMPS vs TDVP", ov, ov0)
+    assert abs(ov - 1.0) <= 1e-8 and abs(ov0 - 1.0) > 1e-6          # test/algorithms.jl:461 (atol = dt there)
+    # ---- power method on the classical Ising model (beta = 0.35, away from criticality)
+    O_o = [ompo.dense_mpo_slice(ompo.classical_ising(0.35))]
+    O_d = [dev_slice(s) for s in O_o]
+    b_d = m.InfiniteMPS.random(np.random.default_rng(2), m.Space((0,), (2,)), [m.Space((0,), (6,))], ctx)
+    v_d, venv, veps = m.leading_boundary(b_d, O_d, m.VUMPS(tol=1e-10, maxiter=100))
+    p_d, penv, peps = m.leading_boundary(b_d, O_d, m.VOMPS(tol=1e-9, maxiter=300))
+    lam_v = dsm.expectation_value(v_d, venv)[0]
+    lam_p = dsm.expectation_value(p_d, dsm.environments(p_d, O_d))[0]
+    print("power method", peps, lam_p, lam_v)
+    assert peps <= 1e-9 and abs(lam_p - lam_v) <= 1e-8 * abs(lam_v)
+    assert abs(abs(m.dot_infinite(p_d, v_d)) - 1.0) <= 1e-7

@@ -507,3 +507,45 @@ def test_changebonds_infinite_oracle_invariants():
         vs, venv = ocb.vumps_svdcut(st, H, ("notrunc",))
         assert vs.V[0].dim > st.V[0].dim and vs.V[1].dim > st.V[1].dim
         assert oi.expectation_value(vs, H, venv).real.sum() < E0.real.sum() - 0.1
+
+
+def test_dynamical_dmrg_oracle_equals_exact_resolvent():
+    """oracle/propagator.py (corvector.jl:57-158): with a bond dimension that holds the full Hilbert space both flavours of
+    dynamical DMRG converge to <psi0| (z - H)^-1 |psi0> of exact linear algebra (trivial TFI and U(1) Heisenberg)."""
+    from oracle import propagator as oprop
+    L = 6
+    cases = [(ompo.transverse_field_ising(L, 1.3), Space((0,), (2,)), Space((0,), (8,))),
+             (ompo.heisenberg_u1(L), Space((-1, 1), (1, 1)), [of.gaussian_bond_space(20, k % 2) for k in range(1, L)])]
+    for H, p, maxV in cases:
+        A = of.FiniteMPS.random(np.random.default_rng(4), p, L, maxV)
+        v = _dense_state(A)
+        Hm = ompo.dense_hamiltonian(H)
+        E = np.vdot(v, Hm @ v).real / np.vdot(v, v).real
+        z = E + 0.3 + 0.3j
+        ref = np.vdot(v, np.linalg.solve(z * np.eye(len(v)) - Hm, v))
+        for fl in ("NaiveInvert", "Jeckelmann"):
+            val, _ = oprop.propagator(A, z, H, fl, tol=1e-10, maxiter=30)
+            assert abs(val - ref) < 1e-10
+
+
+def test_vomps_oracle_time_step_and_power_method():
+    """oracle/statmech.py vomps (approximate/vomps.jl:19-80, statmech/vomps.jl:27-87): W^I = 1 - i dt H applied to a state
+    and re-approximated in its manifold agrees with a TDVP step far better than dt (test/algorithms.jl:461); the power method
+    on the classical Ising model reaches the VUMPS fixed point."""
+    from oracle import infinite as oi, statmech as osm, changebonds as ocb
+    g, dt = 4.0, 1e-3
+    tau = -1j * dt
+    X = np.array([[0, 1], [1, 0]], dtype=complex); Z = np.diag([1.0, -1.0]).astype(complex); I2 = np.eye(2, dtype=complex)
+    W = np.zeros((2, 2, 2, 2), dtype=complex)
+    W[0, :, :, 0] = I2 + tau * (-g * X); W[0, :, :, 1] = np.sqrt(tau) * (-Z); W[1, :, :, 0] = np.sqrt(tau) * Z
+    sl = [ompo.dense_mpo_slice(W), ompo.dense_mpo_slice(W)]
+    st = oi.InfiniteMPS.random(np.random.default_rng(9), Space((0,), (2,)), [Space((0,), (6,)), Space((0,), (6,))])
+    st1, _, eps = osm.vomps(st, sl, st, tol=1e-12, maxiter=100)
+    st5, _ = oi.tdvp_step(st, ompo.transverse_field_ising(2, g), dt)
+    assert eps < 1e-11 and abs(abs(ocb.dot(st1, st5)) - 1) < 1e-9 and abs(abs(ocb.dot(st, st5)) - 1) > 1e-6
+    O = [ompo.dense_mpo_slice(ompo.classical_ising(0.35))]
+    b = oi.InfiniteMPS.random(np.random.default_rng(2), Space((0,), (2,)), [Space((0,), (6,))])
+    pv, ev, _ = osm.leading_boundary(b, O, tol=1e-10, maxiter=100)
+    pp, _, epsp = osm.vomps(b, O, None, tol=1e-9, maxiter=300)
+    lam_v = osm.expectation_value(pv, ev)[0]; lam_p = osm.expectation_value(pp, osm.PerMPOInfEnv(pp, O))[0]
+    assert epsp < 1e-9 and abs(lam_p - lam_v) < 1e-8 * abs(lam_v)
