@@ -100,6 +100,21 @@ function blockrefs(C::AbstractTensorMap{S,1,1}) where {S}
 end
 mcharges(::AbstractTensorMap{S,1,1}) where {S} = Int32[0]
 
+# transfer-matrix vectors v[l; e r] with a one-dimensional charged leg e in the domain (transfer_spectrum, toolbox.jl:44-46):
+# one label; conservation q_l = q_e + q_r with the domain sectors as they appear in the fusion tree f2, i.e. the ABI label
+# charge (q_r = q_l + m) is -charge2 of that sector
+function blockrefs(v::AbstractTensorMap{S,1,2}) where {S}
+    trees = collect(fusiontrees(v))
+    refs = BlockRef[]
+    for ql in secs(space(v, 1)), (f1, f2) in trees
+        f1.uncoupled == (ql,) || continue
+        sv = v[f1, f2]; st = strides(sv)                      # size (n_l, 1, n_r)
+        push!(refs, BlockRef(pointer(sv), st[1], st[3]))
+    end
+    return refs
+end
+mcharges(v::AbstractTensorMap{S,1,2}) where {S} = Int32[-charge2(first(fusiontrees(v))[2].uncoupled[1])]
+
 # two-site tensors x[l p1; r p2] (dmrg.jl:92): labels (p1, p2) with p2 fastest; the p2 leg sits in the domain, where its
 # sectors appear conjugated (P'), so its contribution to the label charge is -charge2 of the sector in f2.uncoupled[2]
 function blockrefs(x::AbstractTensorMap{S,2,2}) where {S}
@@ -126,6 +141,7 @@ left_space(t) = space(t, 1)
 right_space(t::AbstractTensorMap{S,2,1}) where {S} = space(t, 3)'      # domain leg: undo the dual of `space(t, i)`
 right_space(t::AbstractTensorMap{S,1,1}) where {S} = space(t, 2)'
 right_space(t::AbstractTensorMap{S,2,2}) where {S} = space(t, 3)'
+right_space(t::AbstractTensorMap{S,1,2}) where {S} = space(t, 3)'
 
 function upload(t::AbstractTensorMap)
     ql, nl = cspace(left_space(t)); qr, nr = cspace(right_space(t))
@@ -349,6 +365,36 @@ function TensorKit.leftnull(A::MPSTensor{<:GradedSpace{U1Irrep}})
     h = device_leftnull(resident(A))
     N = TensorMap(undef, scalartype(A), codomain(A), device_space(h, :right))
     return download!(N, h)
+end
+
+# transfer_spectrum(above; below, tol, num_vals, sector) -- src/algorithms/toolbox.jl:42-58: the reference calls
+# eigsolve(flip(TransferMatrix(above.AL, below.AL)), init, num_vals, :LM; tol); here the unit-cell transfer operator is one
+# device operator and the Krylov-Schur solve for all `num_vals` values runs inside the library.
+function device_transfer_spectrum(above::InfiniteMPS, below::InfiniteMPS, init::AbstractTensorMap, num_vals::Integer, tol::Real;
+                                  krylovdim::Integer=max(30, 2 * num_vals), maxiter::Integer=100)
+    n = length(above)
+    A = [resident(above.AL[i]).p for i in 1:n]; Ab = [resident(below.AL[i]).p for i in 1:n]
+    v = upload(init)
+    op = Ref{Ptr{Cvoid}}()
+    GC.@preserve A Ab check(ccall((:mpsk_tmop_create, LIB), Int32,
+                                  (Ptr{Cvoid}, Int32, Int32, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}),
+                                  CTX[], 1, n, C_NULL, A, Ab, v.p, C_NULL, C_NULL, op))       # left = 1: v -> v * tm (flip)
+    vals = zeros(Float64, 2 * num_vals); nvals = Ref{Int32}(0); nconv = Ref{Int32}(0); info = Ref(CInfo(0, 0, 0, 0.0))
+    check(ccall((:mpsk_eigsolve_values, LIB), Int32,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32, Int32, Int32, Float64, Ptr{Float64}, Ref{Int32}, Ref{Int32}, Ref{CInfo}),
+                CTX[], op[], v.p, which_code(:LM), num_vals, krylovdim, maxiter, tol, vals, nvals, nconv, info))
+    free_op(op[])
+    nconv[] < num_vals && @warn "correlation length failed to converge: normres = $(info[].normres)"      # toolbox.jl:54-55
+    return [complex(vals[2j - 1], vals[2j]) for j in 1:nvals[]]
+end
+function MPSKit.transfer_spectrum(above::InfiniteMPS{<:MPSTensor{<:GradedSpace{U1Irrep}}}; below=above, tol=MPSKit.Defaults.tol,
+                                  num_vals=20, sector=first(sectors(oneunit(left_virtualspace(above, 1)))))
+    init = randomize!(similar(above.AL[1], left_virtualspace(below, 0),
+                              ℂ[typeof(sector)](sector => 1)' * left_virtualspace(above, 0)))     # toolbox.jl:44-46
+    transferspace = fuse(left_virtualspace(above, 0) * left_virtualspace(below, 0)')
+    num_vals = min(dim(transferspace, sector), num_vals)                                          # toolbox.jl:48-49
+    # the one-dimensional sector leg becomes the label charge of the device vector (blockrefs of a 1 <- 2 tensor map)
+    return device_transfer_spectrum(above, below, init, num_vals, tol)
 end
 
 # Whole sweeps can stay on the device (state, environments and Krylov basis resident between calls): the sweep body of
