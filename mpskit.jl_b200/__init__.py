@@ -45,3 +45,4 @@ from .toolbox import (transfer_spectrum, marek_gap, correlation_length, entropy,
                       expectation_value_local, correlator, decompose_localmpo)
 from .propagator import DynamicalDMRG, propagator  # noqa: F401
 from .statmech import VOMPS, MixedPerMPOInfEnv, approximate_vomps  # noqa: F401
+from .statmech import approximate_idmrg1, approximate_idmrg2  # noqa: F401

@@ -76,8 +76,13 @@ def approximate(psi, toapprox, alg, envs=None, log=None):
     """approximate(psi, toapprox, alg) = approximate!(copy(psi), ...) (fvomps.jl:2-4); InfiniteMPS with VOMPS:
     src/algorithms/approximate/vomps.jl:1-11 (statmech.approximate_vomps)"""
     if hasattr(psi, "N") and not hasattr(psi, "L"):
-        from .statmech import VOMPS, approximate_vomps
-        if not isinstance(alg, VOMPS):
-            raise TypeError("approximate on InfiniteMPS: alg must be VOMPS")
-        return approximate_vomps(psi, toapprox, alg, envs, log)
+        from .statmech import VOMPS, approximate_vomps, approximate_idmrg1, approximate_idmrg2
+        from .infinite import IDMRG1, IDMRG2
+        if isinstance(alg, VOMPS):
+            return approximate_vomps(psi, toapprox, alg, envs, log)
+        if isinstance(alg, IDMRG1):                    # approximate/idmrg.jl:1-58
+            return approximate_idmrg1(psi, toapprox, alg, envs, log)
+        if isinstance(alg, IDMRG2):                    # approximate/idmrg.jl:60-145
+            return approximate_idmrg2(psi, toapprox, alg, envs, log)
+        raise TypeError("approximate on InfiniteMPS: alg must be VOMPS, IDMRG1 or IDMRG2")
     return approximate_inplace(psi.copy(), toapprox, alg, envs, log)

@@ -418,3 +418,100 @@ def approximate_vomps(psi: InfiniteMPS, toapprox, alg: VOMPS = None, envs=None, 
         if eps <= alg.tol:
             break
     return psi, envs, eps
+
+
+# ------------------------------------------------------------------------------------------ approximate with IDMRG1 / IDMRG2
+def _normalized(t):
+    t.scale(1.0 / t.norm())
+    return t
+
+
+def approximate_idmrg1(ost: InfiniteMPS, toapprox, alg=None, oenvs=None, log=None):
+    """approximate(ost, (mpo, above), alg::IDMRG1, oenvs) (src/algorithms/approximate/idmrg.jl:1-58) for one row: sweeps of
+    AC <- normalize(dAC * above.AC) with QRpos / LQpos and manual updates of the mixed environments
+    lw <- normalize(lw * TransferMatrix(above.AL, mpo, AL)); everything on the device."""
+    from .infinite import IDMRG1, transfer_left, transfer_right
+    from .finitemps import qrpos, lqpos
+    alg = alg or IDMRG1()
+    mpo, above = toapprox
+    oenvs = oenvs if oenvs is not None else MixedPerMPOInfEnv(ost, mpo, above)
+    ctx, mod, N = ost.ctx, ost.pspace.modulus, ost.N
+    lw = [oenvs.leftenv(i, ost).copy() for i in range(N)]
+    rw = [oenvs.rightenv(i, ost).copy() for i in range(N)]
+    AL, AR, AC, CR = list(ost.AL), list(ost.AR), list(ost.AC), list(ost.CR)
+    eps = 2 * alg.tol
+
+    def local(col):
+        h = MPO_ddAC(ctx, mpo[col], lw[col], rw[col], above.AC[col])
+        ac = h(above.AC[col]); h.free()
+        return _normalized(ac)
+    for it in range(1, alg.maxiter + 1):
+        Ccur = CR[N - 1]
+        for col in range(N):                                        # idmrg.jl:15-26
+            AC[col] = local(col)
+            AL[col], CR[col] = qrpos(ctx, AC[col], mod)
+            lw[(col + 1) % N] = _normalized(transfer_left(lw[col], mpo[col], above.AL[col], AL[col]))
+        for col in range(N - 1, -1, -1):                            # idmrg.jl:29-41
+            AC[col] = local(col)
+            CR[(col - 1) % N], AR[col] = lqpos(ctx, AC[col], mod)
+            rw[(col - 1) % N] = _normalized(transfer_right(rw[col], mpo[col], above.AR[col], AR[col]))
+        d = Ccur.copy(); d.axpy(-1.0, CR[N - 1]); eps = d.norm(); d.free()
+        if log is not None:
+            log.append(dict(iter=it, eps=eps))
+        if eps < alg.tol:
+            break
+    nst = InfiniteMPS.from_tensors(AR, ost.V, ost.pspace, ctx, tol=alg.tol_gauge)                     # idmrg.jl:55
+    return nst, MixedPerMPOInfEnv(nst, mpo, above), eps
+
+
+def approximate_idmrg2(ost: InfiniteMPS, toapprox, alg=None, oenvs=None, log=None):
+    """approximate(ost, (mpo, above), alg::IDMRG2, oenvs) (src/algorithms/approximate/idmrg.jl:60-145) for one row: two-site
+    projections dAC2 * (above.AC above.AR) truncated on the device, manual updates of both mixed environments."""
+    from .infinite import IDMRG2, transfer_left, transfer_right
+    from .dmrg import tsvd, contract_ac2, truncerr
+    from .derivatives import MPO_ddAC2
+    alg = alg or IDMRG2()
+    trscheme = alg.trscheme if alg.trscheme is not None else truncerr(1e-6)
+    if ost.N < 2:
+        raise ValueError("unit cell should be >= 2")
+    mpo, above = toapprox
+    oenvs = oenvs if oenvs is not None else MixedPerMPOInfEnv(ost, mpo, above)
+    ctx, N = ost.ctx, ost.N
+    lw = [oenvs.leftenv(i, ost).copy() for i in range(N)]
+    rw = [oenvs.rightenv(i, ost).copy() for i in range(N)]
+    AL, AR, CR = list(ost.AL), list(ost.AR), list(ost.CR)
+    eps = 2 * alg.tol
+
+    def step(col, a1, a2):
+        c0, c1 = col % N, (col + 1) % N
+        x2 = contract_ac2(above, a1, a2)
+        h = MPO_ddAC2(ctx, mpo[c0], mpo[c1], lw[c0], rw[c1], x2)
+        y = h(x2); h.free(); x2.free()
+        al, c, ar, _ = tsvd(ost, y, trscheme)                       # normalize!(c) inside (idmrg.jl:80-81)
+        y.free()
+        AL[c0], CR[c0], AR[c1] = al, c, ar
+        lw[c1] = _normalized(transfer_left(lw[c0], mpo[c0], above.AL[c0], al))
+        rw[c0] = _normalized(transfer_right(rw[c1], mpo[c1], above.AR[c1], ar))
+    for it in range(1, alg.maxiter + 1):
+        Ccur = CR[N - 1]
+        for col in range(N):                                        # idmrg.jl:74-97
+            step(col, above.AC[col], above.AR[(col + 1) % N])
+        for col in range(N - 2, -2, -1):                            # idmrg.jl:100-123
+            step(col, above.AL[col % N], above.AC[(col + 1) % N])
+        c = CR[N - 1]
+        ba, bb = Ccur.to_blocks(), c.to_blocks()                    # idmrg.jl:126-131 (small bond matrices: host read-out)
+        acc = 0.0
+        for jl_a, q in enumerate(Ccur.Vl.charges):
+            if q not in c.Vl.charges:
+                continue
+            x, y = ba[(0, jl_a)], bb[(0, c.Vl.charges.index(q))]
+            k = min(x.shape[0], y.shape[0])
+            acc += float(np.linalg.norm(y[:k, :k] - x[:k, :k]) ** 2)
+        eps = float(np.sqrt(acc))
+        if log is not None:
+            log.append(dict(iter=it, eps=eps, D=c.Vl.dim))
+        if eps < alg.tol:
+            break
+    V = [AR[i].Vl for i in range(N)]
+    nst = InfiniteMPS.from_tensors(AR, V, ost.pspace, ctx, tol=alg.tol_gauge)                          # idmrg.jl:142
+    return nst, MixedPerMPOInfEnv(nst, mpo, above), eps

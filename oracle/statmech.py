@@ -295,3 +295,91 @@ def vomps(psi: InfiniteMPS, slices, above: InfiniteMPS = None, tol=1e-12, maxite
         if eps <= tol:
             break
     return psi, envs, eps
+
+
+def approximate_idmrg1(ost: InfiniteMPS, slices, above: InfiniteMPS, tol=1e-12, tol_gauge=TOLGAUGE, maxiter=100, log=None):
+    """approximate(ost, (mpo, above), IDMRG1()) (src/algorithms/approximate/idmrg.jl:1-58) for one row"""
+    from .linalg import qrpos as _qr, lqpos as _lq
+    envs0 = MixedPerMPOInfEnv(ost, slices, above)
+    N, pq, mod = ost.N, ost.pq, ost.modulus
+    lw = [envs0.leftenv(i, ost).copy() for i in range(N)]
+    rw = [envs0.rightenv(i, ost).copy() for i in range(N)]
+    AL, AR, AC, CR = list(ost.AL), list(ost.AR), list(ost.AC), list(ost.CR)
+    eps = 2 * tol
+    for it in range(1, maxiter + 1):
+        Ccur = CR[N - 1]
+        for col in range(N):
+            ac = dAC_sparse(above.AC[col], slices[col], lw[col], rw[col])
+            ac = ac / np.linalg.norm(ac)
+            AC[col] = ac
+            AL[col], CR[col] = InfiniteMPS.leftorth(ac, ost.V[col], ost.V[(col + 1) % N], pq, mod)
+            nl = transfer_left_sparse(lw[col], slices[col], above.AL[col], AL[col])
+            lw[(col + 1) % N] = nl / np.linalg.norm(nl)
+        for col in range(N - 1, -1, -1):
+            ac = dAC_sparse(above.AC[col], slices[col], lw[col], rw[col])
+            ac = ac / np.linalg.norm(ac)
+            AC[col] = ac
+            CR[(col - 1) % N], AR[col] = InfiniteMPS.rightorth(ac, ost.V[col], ost.V[(col + 1) % N], pq, mod)
+            nr = transfer_right_sparse(rw[col], slices[col], above.AR[col], AR[col])
+            rw[(col - 1) % N] = nr / np.linalg.norm(nr)
+        eps = float(np.linalg.norm(Ccur - CR[N - 1]))
+        if log is not None:
+            log.append(dict(iter=it, eps=eps))
+        if eps < tol:
+            break
+    nst = InfiniteMPS.from_tensors(AR, ost.V, pq, tol=tol_gauge, mod=mod)
+    return nst, MixedPerMPOInfEnv(nst, slices, above), eps
+
+
+def approximate_idmrg2(ost: InfiniteMPS, slices, above: InfiniteMPS, trunc=("truncerr", 1e-6), tol=1e-12, tol_gauge=TOLGAUGE,
+                       maxiter=100, log=None):
+    """approximate(ost, (mpo, above), IDMRG2(trscheme)) (src/algorithms/approximate/idmrg.jl:60-145) for one row"""
+    from .linalg import tsvd as _tsvd
+    from .contract import dAC2_sparse
+    if ost.N < 2:
+        raise ValueError("unit cell should be >= 2")
+    envs0 = MixedPerMPOInfEnv(ost, slices, above)
+    N, pq, mod = ost.N, ost.pq, ost.modulus
+    d = len(pq)
+    lw = [envs0.leftenv(i, ost).copy() for i in range(N)]
+    rw = [envs0.rightenv(i, ost).copy() for i in range(N)]
+    AL, AR, CR, V = list(ost.AL), list(ost.AR), list(ost.CR), list(ost.V)
+    eps = 2 * tol
+
+    def step(col, x2):
+        c1 = (col + 1) % N
+        y = dAC2_sparse(x2, slices[col % N], slices[c1], lw[col % N], rw[c1])
+        Dl, _, Dr, _ = y.shape
+        Vl, Vr = V[col % N], V[(col + 2) % N]
+        rowq = (Vl.index_charges()[:, None] + pq[None, :]).reshape(-1)
+        colq = (-pq[:, None] + Vr.index_charges()[None, :]).reshape(-1)
+        U, S, Vh, newV, _, _ = _tsvd(y.transpose(0, 1, 3, 2).reshape(Dl * d, d * Dr), rowq, colq, trunc, mod)
+        S = S / np.linalg.norm(S)
+        AL[col % N] = U.reshape(Dl, d, newV.dim)
+        CR[col % N] = np.diag(S).astype(np.complex128)
+        AR[c1] = Vh.reshape(newV.dim, d, Dr)
+        V[c1] = newV
+        nl = transfer_left_sparse(lw[col % N], slices[col % N], above.AL[col % N], AL[col % N])
+        lw[c1] = nl / np.linalg.norm(nl)
+        nr = transfer_right_sparse(rw[c1], slices[c1], above.AR[c1], AR[c1])
+        rw[col % N] = nr / np.linalg.norm(nr)
+    for it in range(1, maxiter + 1):
+        Ccur, Vcur = CR[N - 1], V[0]
+        for col in range(N):
+            step(col, np.einsum('apk,kqr->aprq', above.AC[col], above.AR[(col + 1) % N]))
+        for col in range(N - 2, -2, -1):
+            step(col, np.einsum('apk,kqr->aprq', above.AL[col % N], above.AC[(col + 1) % N]))
+        c2, V2 = CR[N - 1], V[0]
+        acc = 0.0
+        q1, q2 = Vcur.index_charges(), V2.index_charges()
+        for q in set(Vcur.charges) & set(V2.charges):
+            x, y = Ccur[np.ix_(q1 == q, q1 == q)], c2[np.ix_(q2 == q, q2 == q)]
+            k = min(x.shape[0], y.shape[0])
+            acc += float(np.linalg.norm(y[:k, :k] - x[:k, :k]) ** 2)
+        eps = float(np.sqrt(acc))
+        if log is not None:
+            log.append(dict(iter=it, eps=eps, D=V[0].dim))
+        if eps < tol:
+            break
+    nst = InfiniteMPS.from_tensors(AR, V, pq, tol=tol_gauge, mod=mod)
+    return nst, MixedPerMPOInfEnv(nst, slices, above), eps

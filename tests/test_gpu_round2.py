@@ -1154,3 +1154,36 @@ def test_vomps_approximate_and_power_method(ctx):
     print("power method", peps, lam_p, lam_v)
     assert peps <= 1e-9 and abs(lam_p - lam_v) <= 1e-8 * abs(lam_v)
     assert abs(abs(m.dot_infinite(p_d, v_d)) - 1.0) <= 1e-7
+
+
+def test_approximate_idmrg_infinite(ctx):
+    """approximate(psi, (W, psi), IDMRG1()) / IDMRG2(trscheme = truncdim(6)) (src/algorithms/approximate/idmrg.jl:1-145;
+    test/algorithms.jl:456-464): the same W^I time-step MPO as in the VOMPS test; all three algorithms reach the same state
+    (the reference asserts |dot| = 1 within dt, here 1e-8) and the oracle restatements give the same entanglement spectra (1e-8)."""
+    from oracle import infinite as oi, statmech as osm, toolbox as ot
+    from mpskit_b200 import toolbox as dt_
+    g, dt = 4.0, 1e-3
+    tau = -1j * dt
+    X = np.array([[0, 1], [1, 0]], dtype=complex); Z = np.diag([1.0, -1.0]).astype(complex); I2 = np.eye(2, dtype=complex)
+    W = np.zeros((2, 2, 2, 2), dtype=complex)
+    W[0, :, :, 0] = I2 + tau * (-g * X); W[0, :, :, 1] = np.sqrt(tau) * (-Z); W[1, :, :, 0] = np.sqrt(tau) * Z
+    sl_o = [ompo.dense_mpo_slice(W), ompo.dense_mpo_slice(W)]
+    sl_d = [dev_slice(s) for s in sl_o]
+    Vo = [OSpace((0,), (6,)), OSpace((0,), (6,))]
+    st_o = oi.InfiniteMPS.random(np.random.default_rng(9), OSpace((0,), (2,)), Vo)
+    st_d = m.InfiniteMPS.random(np.random.default_rng(9), m.Space((0,), (2,)), [to_dev_space(v) for v in Vo], ctx)
+    v_d, _, _ = m.approximate(st_d, (sl_d, st_d), m.VOMPS(tol=1e-12, maxiter=100))
+    log1, log2 = [], []
+    a1_d, _, e1 = m.approximate(st_d, (sl_d, st_d), m.IDMRG1(tol=1e-12, maxiter=200), log=log1)
+    a2_d, _, e2 = m.approximate(st_d, (sl_d, st_d), m.IDMRG2(tol=1e-12, maxiter=200, trscheme=m.truncdim(6)), log=log2)
+    a1_o, _, _ = osm.approximate_idmrg1(st_o, sl_o, st_o, tol=1e-12, maxiter=200)
+    a2_o, _, _ = osm.approximate_idmrg2(st_o, sl_o, st_o, ("truncdim", 6), tol=1e-12, maxiter=200)
+    ov1, ov2 = abs(m.dot_infinite(v_d, a1_d)), abs(m.dot_infinite(v_d, a2_d))
+    print("approximate IDMRG1 / IDMRG2", len(log1), e1, ov1, len(log2), e2, ov2, log2[-1]["D"])
+    assert e1 < 1e-12 and e2 < 1e-12 and log2[-1]["D"] == 6
+    assert abs(ov1 - 1.0) <= 1e-8 and abs(ov2 - 1.0) <= 1e-8
+    for dev, orc in ((a1_d, a1_o), (a2_d, a2_o)):
+        for i in range(2):
+            so = np.sort(np.concatenate(list(ot.entanglement_spectrum(orc, i).values())))[::-1]
+            sd = np.sort(np.concatenate([np.asarray(x) for x in dt_.entanglement_spectrum(dev, i).values()]))[::-1]
+            assert np.abs(so - sd).max() <= 1e-8

@@ -549,3 +549,21 @@ def test_vomps_oracle_time_step_and_power_method():
     pp, _, epsp = osm.vomps(b, O, None, tol=1e-9, maxiter=300)
     lam_v = osm.expectation_value(pv, ev)[0]; lam_p = osm.expectation_value(pp, osm.PerMPOInfEnv(pp, O))[0]
     assert epsp < 1e-9 and abs(lam_p - lam_v) < 1e-8 * abs(lam_v)
+
+
+def test_approximate_idmrg_oracle_agrees_with_vomps():
+    """oracle approximate with IDMRG1 / IDMRG2 (approximate/idmrg.jl:1-145) reaches the VOMPS state (test/algorithms.jl:456-464
+    asserts the overlaps within dt; here 1e-10)."""
+    from oracle import infinite as oi, statmech as osm, changebonds as ocb
+    g, dt = 4.0, 1e-3
+    tau = -1j * dt
+    X = np.array([[0, 1], [1, 0]], dtype=complex); Z = np.diag([1.0, -1.0]).astype(complex); I2 = np.eye(2, dtype=complex)
+    W = np.zeros((2, 2, 2, 2), dtype=complex)
+    W[0, :, :, 0] = I2 + tau * (-g * X); W[0, :, :, 1] = np.sqrt(tau) * (-Z); W[1, :, :, 0] = np.sqrt(tau) * Z
+    sl = [ompo.dense_mpo_slice(W), ompo.dense_mpo_slice(W)]
+    st = oi.InfiniteMPS.random(np.random.default_rng(9), Space((0,), (2,)), [Space((0,), (6,)), Space((0,), (6,))])
+    v, _, _ = osm.vomps(st, sl, st, tol=1e-12, maxiter=100)
+    a1, _, e1 = osm.approximate_idmrg1(st, sl, st, tol=1e-12, maxiter=200)
+    a2, _, e2 = osm.approximate_idmrg2(st, sl, st, ("truncdim", 6), tol=1e-12, maxiter=200)
+    assert e1 < 1e-12 and e2 < 1e-12
+    assert abs(abs(ocb.dot(v, a1)) - 1) < 1e-10 and abs(abs(ocb.dot(v, a2)) - 1) < 1e-10
