@@ -464,6 +464,36 @@ def approximate_idmrg1(ost: InfiniteMPS, toapprox, alg=None, oenvs=None, log=Non
     return nst, MixedPerMPOInfEnv(nst, mpo, above), eps
 
 
+def _fix_svd_phases(al, ar):
+    """Deterministic phases for the singular vectors of one tsvd: every row of ar[n, (p r)] gets its largest-magnitude entry
+    real positive (al takes the opposite phase, c is diagonal and unchanged).  The reference's approximate(..., IDMRG2) builds
+    its result from AR tensors of DIFFERENT factorisations of the same two-site tensor (idmrg.jl:100-123,142) and is correct
+    only because LAPACK returns the same singular vectors for the same matrix; the library's SVD fixes no such convention
+    (with random phases the reference algorithm converges to the same bond matrices and a wrong state -- checked on the
+    oracle), so the convention is imposed here.  ar is read back once per step (n x d r numbers)."""
+    from .infinite import mul_left, mul_right
+    ctx = ar.ctx
+    blocks = ar.to_blocks()
+    Vn = ar.Vl
+    off = Vn.offsets()
+    P = np.zeros((Vn.dim, 1, Vn.dim), dtype=ar.dtype)
+    for jl in range(len(Vn.charges)):
+        rows = [blocks[(mm, jl)] for mm in range(len(ar.mch)) if (mm, jl) in blocks]
+        if not rows:
+            P[off[jl]:off[jl + 1], 0, off[jl]:off[jl + 1]] = np.eye(Vn.dims[jl])
+            continue
+        M = np.concatenate(rows, axis=1)
+        e = M[np.arange(M.shape[0]), np.argmax(np.abs(M), axis=1)]
+        ph = np.where(np.abs(e) > 0, np.conj(e) / np.maximum(np.abs(e), 1e-300), 1.0)
+        P[off[jl]:off[jl + 1], 0, off[jl]:off[jl + 1]] = np.diag(ph)
+    Ph = DeviceTensor.from_dense(ctx, P, Vn, (0,), Vn, ar.dtype)
+    Ph._is_bond = True
+    ar2 = mul_left(Ph, ar)
+    al2 = mul_right(al, Ph.adjoint())
+    Ph.free(); al.free(); ar.free()
+    return al2, ar2
+
+
 def approximate_idmrg2(ost: InfiniteMPS, toapprox, alg=None, oenvs=None, log=None):
     """approximate(ost, (mpo, above), alg::IDMRG2, oenvs) (src/algorithms/approximate/idmrg.jl:60-145) for one row: two-site
     projections dAC2 * (above.AC above.AR) truncated on the device, manual updates of both mixed environments."""
@@ -489,6 +519,7 @@ def approximate_idmrg2(ost: InfiniteMPS, toapprox, alg=None, oenvs=None, log=Non
         y = h(x2); h.free(); x2.free()
         al, c, ar, _ = tsvd(ost, y, trscheme)                       # normalize!(c) inside (idmrg.jl:80-81)
         y.free()
+        al, ar = _fix_svd_phases(al, ar)
         AL[c0], CR[c0], AR[c1] = al, c, ar
         lw[c1] = _normalized(transfer_left(lw[c0], mpo[c0], above.AL[c0], al))
         rw[c0] = _normalized(transfer_right(rw[c1], mpo[c1], above.AR[c1], ar))
