@@ -46,3 +46,4 @@ from .toolbox import (transfer_spectrum, marek_gap, correlation_length, entropy,
 from .propagator import DynamicalDMRG, propagator  # noqa: F401
 from .statmech import VOMPS, MixedPerMPOInfEnv, approximate_vomps  # noqa: F401
 from .statmech import approximate_idmrg1, approximate_idmrg2  # noqa: F401
+from .quasiparticle import QuasiparticleAnsatz, FiniteQP, excitations_qp  # noqa: F401

@@ -1187,3 +1187,41 @@ def test_approximate_idmrg_infinite(ctx):
             so = np.sort(np.concatenate(list(ot.entanglement_spectrum(orc, i).values())))[::-1]
             sd = np.sort(np.concatenate([np.asarray(x) for x in dt_.entanglement_spectrum(dev, i).values()]))[::-1]
             assert np.abs(so - sd).max() <= 1e-8
+
+
+def test_quasiparticle_excitations_finite(ctx):
+    """excitations(H, QuasiparticleAnsatz(), psi::FiniteMPS, envs; num = 2) (quasiparticleexcitation.jl:130-170, 234-362;
+    qpenv.jl:145-166; test/algorithms.jl:221-247 compares it with FiniteExcited at 1e-4): with a bond dimension that holds the
+    whole Hilbert space the tangent space is complete and the quasiparticle energies are the exact gaps (1e-8: TFI chain, and the
+    S_z = 0 sector of the U(1) Heisenberg chain); at a truncated bond dimension the device agrees with the oracle (1e-7)."""
+    from oracle import quasiparticle as oq
+    from mpskit_b200.workloads import gaussian_bond_space
+    L = 8
+    cases = [("tfi-full", ompo.transverse_field_ising(L, 1.5), OSpace((0,), (2,)), OSpace((0,), (16,)), 16, True),
+             ("tfi-D6", ompo.transverse_field_ising(L, 1.5), OSpace((0,), (2,)), OSpace((0,), (6,)), 6, False),
+             ("heisenberg-u1", ompo.heisenberg_u1(L), OSpace((-1, 1), (1, 1)), [of.gaussian_bond_space(40, k % 2) for k in range(1, L)], 40, True)]
+    for name, Ho, p_o, maxV, D, exact in cases:
+        Hd = dev_hamiltonian(Ho)
+        maxV_d = [to_dev_space(v) for v in maxV] if isinstance(maxV, list) else to_dev_space(maxV)
+        psi_d = m.FiniteMPS.random(np.random.default_rng(1), to_dev_space(p_o), L, maxV_d, ctx)
+        psi_d, envs_d, _ = m.find_groundstate(psi_d, Hd, m.DMRG2(tol=1e-13, maxiter=8, eigalg=m.Lanczos(tol=1e-13), trscheme=m.truncdim(D)))
+        psi_o = of.FiniteMPS.random(np.random.default_rng(1), p_o, L, maxV)
+        psi_o, envs_o, _ = of.dmrg2_sweeps(psi_o, Ho, nsweeps=8, trunc=("truncdim", D), tol=1e-13)
+        en_o, _, _ = oq.excitations(Ho, psi_o, envs_o, num=2, tol=1e-11)
+        log = []
+        en_d, Xs, qp = m.excitations_qp(Hd, m.QuasiparticleAnsatz(tol=1e-11), psi_d, envs_d, num=2, log=log)
+        print("quasiparticle", name, en_d, en_o, [l["numops"] for l in log])
+        assert np.abs(np.array(en_d) - np.array(en_o)).max() <= (1e-8 if exact else 1e-7)
+        if exact:
+            Hm = ompo.dense_hamiltonian(Ho)
+            if name.startswith("heisenberg"):
+                keep = [k for k in range(2 ** L) if bin(k).count("1") == L // 2]
+                Hm = Hm[np.ix_(keep, keep)]
+            ev = np.linalg.eigvalsh(Hm)
+            gaps = []
+            for e in ev[1:]:                    # distinct gaps above the ground state (degenerate multiplets count once)
+                if not gaps or abs(e - ev[0] - gaps[-1]) > 1e-8:
+                    gaps.append(e - ev[0])
+                if len(gaps) == 2:
+                    break
+            assert np.abs(np.array(en_d) - np.array(gaps)).max() <= 1e-8

@@ -567,3 +567,24 @@ def test_approximate_idmrg_oracle_agrees_with_vomps():
     a2, _, e2 = osm.approximate_idmrg2(st, sl, st, ("truncdim", 6), tol=1e-12, maxiter=200)
     assert e1 < 1e-12 and e2 < 1e-12
     assert abs(abs(ocb.dot(v, a1)) - 1) < 1e-10 and abs(abs(ocb.dot(v, a2)) - 1) < 1e-10
+
+
+def test_quasiparticle_oracle_equals_exact_gaps():
+    """oracle/quasiparticle.py (quasiparticleexcitation.jl:130-170,234-362; qpenv.jl:145-166): at full bond dimension the
+    finite quasiparticle ansatz spans the orthogonal complement of the ground state, so its lowest energies are the exact gaps."""
+    from oracle import quasiparticle as oq
+    L = 8
+    H = ompo.transverse_field_ising(L, 1.5)
+    psi = of.FiniteMPS.random(np.random.default_rng(1), Space((0,), (2,)), L, Space((0,), (16,)))
+    psi, envs, _ = of.dmrg2_sweeps(psi, H, nsweeps=8, trunc=("truncdim", 16), tol=1e-13)
+    ev = np.linalg.eigvalsh(ompo.dense_hamiltonian(H))
+    en, _, qp = oq.excitations(H, psi, envs, num=2, tol=1e-11)
+    assert sum(qp.sizes) == 2 ** L - 1
+    assert abs(en[0] - (ev[1] - ev[0])) < 1e-9 and abs(en[1] - (ev[2] - ev[0])) < 1e-9
+    Hh = ompo.heisenberg_u1(L)
+    psi = of.FiniteMPS.random(np.random.default_rng(1), Space((-1, 1), (1, 1)), L, [of.gaussian_bond_space(40, k % 2) for k in range(1, L)])
+    psi, envs, _ = of.dmrg2_sweeps(psi, Hh, nsweeps=8, trunc=("truncdim", 40), tol=1e-13)
+    keep = [k for k in range(2 ** L) if bin(k).count("1") == L // 2]
+    ev = np.linalg.eigvalsh(ompo.dense_hamiltonian(Hh)[np.ix_(keep, keep)])
+    en, _, _ = oq.excitations(Hh, psi, envs, num=1, tol=1e-11)
+    assert abs(en[0] - (ev[1] - ev[0])) < 1e-9
