@@ -212,3 +212,30 @@ def test_state_file_pack_unpack_roundtrip(tmp_path):
     bad["AL/0/data"] = bad["AL/0/data"][:-1]
     with pytest.raises(ValueError):
         m.unpack_tensor("AL/0", bad, m.block_table)
+
+
+def test_toolbox_host_logic_without_gpu():
+    """host-side pieces of mpskit_b200/toolbox.py (no device call): the per-charge decomposition of multi-site operators into
+    local MPO tensors (decompose_localmpo of expval.jl:41-44 with definite level charges), the square-slice embedding of
+    rectangular local MPO tensors, rationalize / approx_angles / marek_gap (toolbox.jl:74-117) against the oracle's."""
+    import numpy as np
+    from mpskit_b200 import toolbox as tb
+    from oracle import toolbox as ot, mpo as ompo
+    Sp, Sm, Sz, pq = ompo.spin_ops(2)
+    SS = np.einsum('ac,bd->abcd', Sz, Sz) + 0.5 * (np.einsum('ac,bd->abcd', Sp, Sm) + np.einsum('ac,bd->abcd', Sm, Sp))
+    Os, ch = tb.decompose_localmpo(SS, pq, return_charges=True)
+    assert [o.shape for o in Os] == [(1, 2, 2, 3), (3, 2, 2, 1)] and ch == [[0], [-2, 0, 2], [0]]
+    assert np.abs(np.einsum('apqb,brsc->prqs', Os[0], Os[1]) - SS).max() < 1e-14
+    assert tb._level_charges_from_ops(Os, pq) == ch
+    H3 = np.einsum('abcd,ef->abecdf', SS, np.eye(2)) + np.einsum('ef,abcd->eabfcd', np.eye(2), SS)
+    Os3, ch3 = tb.decompose_localmpo(H3, pq, return_charges=True)
+    assert np.abs(np.einsum('apqb,brsc,ctud->prtqsu', *Os3) - H3).max() < 1e-13 and ch3[0] == [0] and ch3[-1] == [0]
+    slices, od, lc = tb.local_mpo_slices(Os, pq, ch)
+    assert od == 3 and slices[0].kinds() == [[2, 2, 2], [0, 0, 0], [0, 0, 0]] and slices[1].kinds() == [[2, 0, 0], [2, 0, 0], [2, 0, 0]]
+    assert slices[0].imcharges == (-2, 0, 2) and slices[1].domcharges == (-2, 0, 2) and slices[1].imcharges == (0, 0, 0)
+    for x, tol in ((0.3333, 0.01), (-0.98, 0.1), (0.52, 0.1), (0.0, 0.1), (0.749, 0.01)):
+        assert tb.rationalize(x, tol) == ot.rationalize(x, tol)
+    spec = np.array([1.0, -0.5, 0.4, -0.25, -0.2, 0.1j])
+    assert np.allclose(tb.approx_angles(spec), ot.approx_angles(spec))
+    assert np.allclose(tb.marek_gap(spec), ot.marek_gap(spec))
+    assert abs(tb.correlation_length(spec) - 1 / np.log(2)) < 1e-14

@@ -588,3 +588,46 @@ def test_quasiparticle_oracle_equals_exact_gaps():
     ev = np.linalg.eigvalsh(ompo.dense_hamiltonian(Hh)[np.ix_(keep, keep)])
     en, _, _ = oq.excitations(Hh, psi, envs, num=1, tol=1e-11)
     assert abs(en[0] - (ev[1] - ev[0])) < 1e-9
+
+
+def test_reference_approximate_idmrg2_depends_on_svd_phase_convention():
+    """Finding recorded in DESIGN.md: approximate(psi, (O, above), IDMRG2) (approximate/idmrg.jl:60-145) builds its result from
+    AR tensors that come from DIFFERENT factorisations of the same two-site tensor, which is consistent only when the SVD returns
+    the same singular vectors for the same matrix (LAPACK does).  With arbitrary phases on the singular vectors the iteration
+    converges to the same bond matrices in the same number of steps and to a WRONG state; a deterministic phase convention
+    (largest entry of every right singular vector real positive -- what mpskit_b200.statmech._fix_svd_phases imposes on the
+    device) restores the result."""
+    from oracle import infinite as oi, statmech as osm, changebonds as ocb, linalg as ol
+    g, dt = 4.0, 1e-3
+    tau = -1j * dt
+    X = np.array([[0, 1], [1, 0]], dtype=complex); Z = np.diag([1.0, -1.0]).astype(complex); I2 = np.eye(2, dtype=complex)
+    W = np.zeros((2, 2, 2, 2), dtype=complex)
+    W[0, :, :, 0] = I2 + tau * (-g * X); W[0, :, :, 1] = np.sqrt(tau) * (-Z); W[1, :, :, 0] = np.sqrt(tau) * Z
+    sl = [ompo.dense_mpo_slice(W), ompo.dense_mpo_slice(W)]
+    st = oi.InfiniteMPS.random(np.random.default_rng(9), Space((0,), (2,)), [Space((0,), (6,)), Space((0,), (6,))])
+    v, _, _ = osm.vomps(st, sl, st, tol=1e-12, maxiter=100)
+    orig = ol.tsvd
+    rng = np.random.default_rng(0)
+
+    def randphase(M, rowq, colq, trunc=("notrunc",), modulus=0):
+        U, S, Vh, newV, eps, info = orig(M, rowq, colq, trunc, modulus)
+        ph = np.exp(2j * np.pi * rng.random(len(S)))
+        return U * ph[None, :], S, ph.conj()[:, None] * Vh, newV, eps, info
+
+    def fixed(M, rowq, colq, trunc=("notrunc",), modulus=0):
+        U, S, Vh, newV, eps, info = randphase(M, rowq, colq, trunc, modulus)
+        e = Vh[np.arange(Vh.shape[0]), np.argmax(np.abs(Vh), axis=1)]
+        ph = np.conj(e) / np.abs(e)
+        return U * ph.conj()[None, :], S, ph[:, None] * Vh, newV, eps, info
+    try:
+        ol.tsvd = randphase
+        log_r = []
+        bad, _, e_r = osm.approximate_idmrg2(st, sl, st, ("truncdim", 6), tol=1e-12, maxiter=200, log=log_r)
+        ol.tsvd = fixed
+        log_f = []
+        good, _, e_f = osm.approximate_idmrg2(st, sl, st, ("truncdim", 6), tol=1e-12, maxiter=200, log=log_f)
+    finally:
+        ol.tsvd = orig
+    assert e_r < 1e-12 and e_f < 1e-12 and len(log_r) == len(log_f)
+    assert abs(abs(ocb.dot(v, good)) - 1) < 1e-10
+    assert abs(abs(ocb.dot(v, bad)) - 1) > 1e-2
