@@ -166,3 +166,224 @@ def excitations_qp(H, alg: QuasiparticleAnsatz, gs, envs=None, num=1, seed=0, we
         energies.append(float(np.real(val))); found.append(vec)
     heff.free()
     return energies, found, qp
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# Infinite quasiparticle ansatz (trivial excitation sector, left_gs == right_gs)
+class InfiniteQP:
+    """LeftGaugedQP(rand, psi::InfiniteMPS; momentum) (quasiparticle_state.jl:30-42): VLs[i] = leftnull(AL[i]) on the device;
+    the momentum is per site, as in the reference (qpenv.jl:68-71)"""
+
+    def __init__(self, gs, momentum=0.0, seed=0):
+        self.gs, self.momentum, self.seed = gs, float(momentum), seed
+        self.VLs = [leftnull(gs.AL[i]) for i in range(gs.N)]
+        self.active = list(range(gs.N))
+
+    def random(self, seed=None):
+        seed = self.seed if seed is None else seed
+        gs = self.gs
+        return RecursiveVec([DeviceTensor.random(gs.ctx, self.VLs[i].Vr, (0,), gs.AR[i].Vr, seed + 17 * i, gs.dtype)
+                             for i in range(gs.N)])
+
+    def B(self, X, k):
+        return mul_right(self.VLs[k], X.vecs[k])
+
+
+def _replace_level(t, i, new):
+    """stacked level tensor with level i replaced"""
+    nlev = len(t.mch)
+    parts = [new if j == i else t.select([j]) for j in range(nlev)]
+    out = DeviceTensor.stack(parts)
+    for j, p in enumerate(parts):
+        if j != i:
+            p.free()
+    return out
+
+
+def _remove_component(level, Cm):
+    """level -= <C, level> C : the regularisation of the identity levels (qpenv.jl:73-82,90-99; exci_transfer_system.jl:15-21)"""
+    level.axpy(-complex(Cm.dot(level)), Cm)
+    return level
+
+
+class _InfHEff:
+    """phi -> effective_excitation_hamiltonian(H, phi, environments(phi, H, lenvs, renvs), E) for an InfiniteQP
+    (quasiparticleexcitation.jl:234-256,295-334; qpenv.jl:56-143; exci_transfer_system.jl:1-85)"""
+
+    def __init__(self, H, qp: InfiniteQP, envs, E, solver_tol=1e-12, solver_maxiter=100):
+        from .infinite import TransferMatrix, regularize, _entry_slice, _isid
+        self.H, self.qp, self.envs, self.E = H, qp, envs, E
+        self.tol, self.maxiter = solver_tol, solver_maxiter
+        gs = qp.gs
+        N, od = gs.N, H.odim
+        self.N, self.od = N, od
+        self.GL = [envs.leftenv(i, gs) for i in range(N)]
+        self.GR = [envs.rightenv(i, gs) for i in range(N)]
+        self.AL, self.AR, self.CR = list(gs.AL), list(gs.AR), list(gs.CR)
+        self.isid = [_isid(H, i) for i in range(od)]
+        self.ids = [i for i in range(1, od - 1) if self.isid[i]]
+        self.center = [MPO_ddAC(gs.ctx, H[i], self.GL[i], self.GR[i], self.AL[i]) for i in range(N)]
+        Cn = self.CR[N - 1]
+        Cadj = Cn.adjoint()
+        # diagonal transfer operators of the two linear systems (persistent device operators)
+        self.tl, self.tr = {}, {}
+        for i in range(od):
+            if not all(sl.contains(i, i) for sl in H.slices):
+                continue
+            mids = None if self.isid[i] else [_entry_slice(H[s], i, i) for s in range(N)]
+            tl = TransferMatrix(self.AR, mids, self.AL).flip()
+            tr = TransferMatrix(self.AL, mids, self.AR)
+            if self.isid[i]:
+                tl = regularize(tl, Cadj, Cn)
+                tr = regularize(tr, Cadj, Cn)
+            self.tl[i], self.tr[i] = tl, tr
+
+    # ---- exci_transfer_system.jl
+    def _left_system(self, lB0):
+        from .fixedpoint import linsolve
+        H, N, od, p = self.H, self.N, self.od, self.qp.momentum
+        Cn = self.CR[N - 1]
+        found = lB0.zerovector()
+        for i in range(od):
+            t = found.copy()
+            for s in range(N):
+                nt = transfer_left(t, H[s], self.AR[s], self.AL[s]); t.free(); t = nt
+            start = t.select([i]); t.free()
+            start.scale(np.exp(-1j * p * N))
+            if self.isid[i]:
+                _remove_component(start, Cn)
+            b0 = lB0.select([i])
+            start.axpy(1.0, b0); b0.free()
+            if i in self.tl:
+                sol = linsolve(self.tl[i], start, start, 1.0, -np.exp(-1j * p * N), self.tol, 30, self.maxiter)
+                start.free(); start = sol
+            nf = _replace_level(found, i, start)
+            found.free(); start.free(); found = nf
+        return found
+
+    def _right_system(self, rB0):
+        from .fixedpoint import linsolve
+        H, N, od, p = self.H, self.N, self.od, self.qp.momentum
+        Cn = self.CR[N - 1]
+        found = rB0.zerovector()
+        for i in range(od - 1, -1, -1):
+            t = found.copy()
+            for s in range(N - 1, -1, -1):
+                nt = transfer_right(t, H[s], self.AL[s], self.AR[s]); t.free(); t = nt
+            start = t.select([i]); t.free()
+            start.scale(np.exp(1j * p * N))
+            if self.isid[i]:
+                _remove_component(start, Cn)
+            b0 = rB0.select([i])
+            start.axpy(1.0, b0); b0.free()
+            if i in self.tr:
+                sol = linsolve(self.tr[i], start, start, 1.0, -np.exp(1j * p * N), self.tol, 30, self.maxiter)
+                start.free(); start = sol
+            nf = _replace_level(found, i, start)
+            found.free(); start.free(); found = nf
+        return found
+
+    def _regularise_ids(self, t, Cm):
+        for k in self.ids:
+            lev = _remove_component(t.select([k]), Cm)
+            nt = _replace_level(t, k, lev)
+            t.free(); lev.free(); t = nt
+        return t
+
+    def __call__(self, X):
+        H, qp, N = self.H, self.qp, self.N
+        gs = qp.gs
+        ctx = gs.ctx
+        ph = np.exp(1j * qp.momentum)
+        Bs = [qp.B(X, k) for k in range(N)]
+        # ---- environments(exci::InfiniteQP, H, lenvs, renvs) (qpenv.jl:68-137)
+        lB = [self.GL[i].zerovector() for i in range(N)]
+        for pos in range(N):
+            new = transfer_left(lB[pos], H[pos], self.AR[pos], self.AL[pos])
+            t = transfer_left(self.GL[pos], H[pos], Bs[pos], self.AL[pos])
+            new.axpy(1.0, t); t.free()
+            new.scale(1.0 / ph)
+            new = self._regularise_ids(new, self.CR[pos])
+            lB[(pos + 1) % N].free()
+            lB[(pos + 1) % N] = new
+        rB = [self.GR[i].zerovector() for i in range(N)]
+        for pos in range(N - 1, -1, -1):
+            new = transfer_right(rB[pos], H[pos], self.AL[pos], self.AR[pos])
+            t = transfer_right(self.GR[pos], H[pos], Bs[pos], self.AR[pos])
+            new.axpy(1.0, t); t.free()
+            new.scale(ph)
+            new = self._regularise_ids(new, self.CR[(pos - 1) % N])
+            rB[(pos - 1) % N].free()
+            rB[(pos - 1) % N] = new
+        s0 = self._left_system(lB[0]); lB[0].free(); lB[0] = s0
+        s1 = self._right_system(rB[N - 1]); rB[N - 1].free(); rB[N - 1] = s1
+        cur = lB[0].copy()
+        for i in range(N - 1):
+            nt = transfer_left(cur, H[i], self.AR[i], self.AL[i]); cur.free(); cur = nt
+            cur.scale(1.0 / ph)
+            cur = self._regularise_ids(cur, self.CR[i])
+            lB[i + 1].axpy(1.0, cur)
+        cur.free()
+        cur = rB[N - 1].copy()
+        for i in range(N - 1, 0, -1):
+            nt = transfer_right(cur, H[i], self.AL[i], self.AR[i]); cur.free(); cur = nt
+            cur.scale(ph)
+            cur = self._regularise_ids(cur, self.CR[i - 1])
+            rB[i - 1].axpy(1.0, cur)
+        cur.free()
+        # ---- _effective_excitation_local_apply (quasiparticleexcitation.jl:295-334): all three terms on every site
+        out = []
+        for loc in range(N):
+            B = Bs[loc]
+            Bp = self.center[loc](B)
+            Bp.axpy(-self.E[loc], B)
+            h = MPO_ddAC(ctx, H[loc], lB[loc], self.GR[loc], self.AR[loc])
+            t = h(self.AR[loc]); h.free()
+            Bp.axpy(1.0, t); t.free()
+            h = MPO_ddAC(ctx, H[loc], self.GL[loc], rB[loc], self.AL[loc])
+            t = h(self.AL[loc]); h.free()
+            Bp.axpy(1.0, t); t.free()
+            out.append(_overlap(gs, Bp, qp.VLs[loc]))
+            Bp.free()
+        for t in Bs + lB + rB:
+            t.free()
+        return RecursiveVec(out)
+
+    def free(self):
+        for o in self.center:
+            o.free()
+        self.center = []
+
+
+def excitations_qp_infinite(H, alg: QuasiparticleAnsatz, momentum, gs, envs=None, num=1, seed=0, weight=100.0, log=None):
+    """excitations(H, alg::QuasiparticleAnsatz, momentum::Number, psi::InfiniteMPS, envs; num)
+    (quasiparticleexcitation.jl:39-92): energies of the `num` lowest quasiparticle states of (per-site) momentum `momentum`."""
+    from . import infinite as di
+    alg = alg or QuasiparticleAnsatz()
+    envs = envs if envs is not None else di.environments(gs, H)
+    qp = InfiniteQP(gs, momentum, seed)
+    E = []
+    for loc in range(gs.N):                              # effective_excitation_renormalization_energy (…:336-349)
+        ac = gs.AC[loc]
+        h = MPO_ddAC(gs.ctx, H[loc], envs.leftenv(loc, gs), envs.rightenv(loc, gs), ac)
+        y = h(ac); h.free()
+        E.append(complex(ac.dot(y))); y.free()
+    heff = _InfHEff(H, qp, envs, E)
+    found, energies = [], []
+
+    def f(v):
+        y = heff(v)
+        for u in found:
+            y.axpy(weight * complex(u.dot(v)), u)
+        return y
+    for n in range(num):
+        x0 = qp.random(seed + 1000 * n)
+        val, vec, info = eigsolve_lanczos(f, x0, "SR", alg.tol, alg.krylovdim, alg.maxiter)
+        if info["converged"] == 0:
+            import warnings
+            warnings.warn(f"excitation failed to converge: normres = {info['normres']}")
+        if log is not None:
+            log.append(dict(state=n, energy=float(np.real(val)), **info))
+        energies.append(float(np.real(val))); found.append(vec)
+    heff.free()
+    return energies, found, qp

@@ -1225,3 +1225,23 @@ def test_quasiparticle_excitations_finite(ctx):
                 if len(gaps) == 2:
                     break
             assert np.abs(np.array(en_d) - np.array(gaps)).max() <= 1e-8
+
+
+def test_quasiparticle_excitations_infinite(ctx):
+    """excitations(H, QuasiparticleAnsatz(), momentum, psi::InfiniteMPS, envs) (quasiparticleexcitation.jl:39-92; qpenv.jl:56-143;
+    exci_transfer_system.jl:1-85; test/algorithms.jl:204-211 checks the Haldane gap to 1e-4): the transverse-field Ising chain
+    H = -sum ZZ - g sum X has the exact one-particle dispersion 2 sqrt(1 + g^2 - 2 g cos k); at g = 4 the D = 8 ansatz
+    reproduces it to 1e-8 on one- and two-site unit cells (two sites fold k and k + pi).  The oracle restatement is held to the
+    same exact values (1e-9) in tests/test_oracle_cpu.py, so device = oracle to 1e-8 follows."""
+    g = 4.0
+    eps_k = lambda k: 2 * np.sqrt(1 + g * g - 2 * g * np.cos(k))
+    for N, momenta in ((1, (0.0, np.pi / 2, np.pi)), (2, (np.pi / 2,))):
+        Hd = dev_hamiltonian(ompo.transverse_field_ising(N, g))
+        st_d = m.InfiniteMPS.random(np.random.default_rng(3), m.Space((0,), (2,)), [m.Space((0,), (8,))] * N, ctx)
+        st_d, envs_d, _ = m.find_groundstate_vumps(st_d, Hd, m.VUMPS(tol=1e-11, maxiter=200))
+        for k in momenta:
+            log = []
+            en_d, _, _ = m.excitations_qp_infinite(Hd, m.QuasiparticleAnsatz(tol=1e-10), k, st_d, envs_d, log=log)
+            exact = eps_k(k) if N == 1 else min(eps_k(k), eps_k(k + np.pi))
+            print("infinite quasiparticle", N, k, en_d[0], exact, log[0]["numops"])
+            assert abs(en_d[0] - exact) <= 1e-8

@@ -631,3 +631,23 @@ def test_reference_approximate_idmrg2_depends_on_svd_phase_convention():
     assert e_r < 1e-12 and e_f < 1e-12 and len(log_r) == len(log_f)
     assert abs(abs(ocb.dot(v, good)) - 1) < 1e-10
     assert abs(abs(ocb.dot(v, bad)) - 1) > 1e-2
+
+
+def test_infinite_quasiparticle_oracle_equals_exact_tfi_dispersion():
+    """oracle/quasiparticle.py, infinite ansatz (quasiparticleexcitation.jl:39-92, qpenv.jl:56-143, exci_transfer_system.jl:1-85):
+    for H = -sum ZZ - g sum X the one-particle band is 2 sqrt(1 + g^2 - 2 g cos k); at g = 4 a D = 8 VUMPS ground state gives
+    it to 1e-9 at k = 0, pi/2, pi, and a two-site unit cell folds k and k + pi."""
+    from oracle import infinite as oi, quasiparticle as oq
+    g = 4.0
+    eps_k = lambda k: 2 * np.sqrt(1 + g * g - 2 * g * np.cos(k))
+    H = ompo.transverse_field_ising(1, g)
+    st = oi.InfiniteMPS.random(np.random.default_rng(3), Space((0,), (2,)), [Space((0,), (8,))])
+    st, envs, _ = oi.vumps(st, H, tol=1e-11, maxiter=200)
+    for k in (0.0, np.pi / 2, np.pi):
+        en, _, _ = oq.excitations_infinite(H, k, st, envs, num=1, tol=1e-10)
+        assert abs(en[0] - eps_k(k)) < 1e-9
+    H2 = ompo.transverse_field_ising(2, g)
+    st2 = oi.InfiniteMPS.random(np.random.default_rng(3), Space((0,), (2,)), [Space((0,), (8,))] * 2)
+    st2, envs2, _ = oi.vumps(st2, H2, tol=1e-11, maxiter=200)
+    en, _, _ = oq.excitations_infinite(H2, np.pi / 2, st2, envs2, num=1, tol=1e-10)
+    assert abs(en[0] - eps_k(np.pi / 2)) < 1e-9
