@@ -1245,3 +1245,27 @@ def test_quasiparticle_excitations_infinite(ctx):
             exact = eps_k(k) if N == 1 else min(eps_k(k), eps_k(k + np.pi))
             print("infinite quasiparticle", N, k, en_d[0], exact, log[0]["numops"])
             assert abs(en_d[0] - exact) <= 1e-8
+
+
+@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: never run on a GPU; XPASS = verified")
+def test_haldane_gap_device(ctx):
+    """The reference's own quasiparticle assertion on the device (test/algorithms.jl:204-211: energies[1] ~ 0.41047925,
+    atol 1e-4, D = 48): spin-1 Heisenberg chain with U(1) blocks, device VUMPS + device infinite quasiparticle ansatz at
+    momentum pi, against the reference constant (1e-4) and the oracle's recorded run in the same bond space
+    (tests/golden/haldane_gap_oracle.json, 1e-6).  Every primitive on this path is verified by the tests above (U(1) VUMPS,
+    U(1) finite quasiparticles, the infinite ansatz on the TFI chain); this combination itself has not been executed on a GPU,
+    hence the non-strict xfail marker."""
+    import json
+    import os
+    rec = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "haldane_gap_oracle.json")))
+    d48 = [r for r in rec["runs"] if r["D"] == 48][0]
+    Ho = ompo.heisenberg_u1(1, d=3)
+    Hd = dev_hamiltonian(Ho)
+    V = m.Space.from_dict({int(k): v for k, v in d48["bond_space"].items()})
+    st = m.InfiniteMPS.random(np.random.default_rng(3), m.Space((-2, 0, 2), (1, 1, 1)), [V], ctx)
+    log = []
+    st, envs, eps = m.find_groundstate_vumps(st, Hd, m.VUMPS(tol=1e-10, maxiter=400), log=log)
+    en, _, _ = m.excitations_qp_infinite(Hd, m.QuasiparticleAnsatz(tol=1e-8), np.pi, st, envs)
+    print("Haldane gap on the device", en[0], d48["gap"], log[-1]["energy"], d48["energy_per_site"], eps)
+    assert abs(log[-1]["energy"] - d48["energy_per_site"]) <= 1e-9
+    assert abs(en[0] - 0.41047925) <= 1e-4 and abs(en[0] - d48["gap"]) <= 1e-6
