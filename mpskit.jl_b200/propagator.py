@@ -5,7 +5,6 @@ solves with the LinearCombination (-2w H_AC + (H^2)_AC) through the host-driven 
 right-hand sides are the overlap projections ac_proj (derivatives.jl:210-215) of the source state."""
 from __future__ import annotations
 from dataclasses import dataclass
-import numpy as np
 from .derivatives import ddAC, LinearCombinationOp
 from .environments import environments
 from .fixedpoint import linsolve

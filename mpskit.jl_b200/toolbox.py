@@ -292,9 +292,8 @@ def correlator(st, O1, O2, i, js=None, level_charges=None):
     """correlator(state, O1, O2, i, js) (correlators.jl:10-39): G[k] = <O1[i] O2[js[k]]> for MPO tensors O1[1, p_out, p_in, w],
     O2[w, p_out, p_in, 1]; correlator(state, O12, i, js) for a two-site operator O12[p1_out, p2_out, p1_in, p2_in]
     (correlators.jl:41-45).  `js` may be an int (returns a scalar) or an increasing range."""
-    if js is None:                                    # correlator(state, O12, i, js)
-        O12, js = np.asarray(O1), i
-        i = O2
+    if js is None:                                    # correlator(state, O12, i, js): the arguments shift by one
+        O12, i, js = np.asarray(O1), O2, i
         (O1, O2), lcs = decompose_localmpo(O12, st.pq, return_charges=True)
         level_charges = lcs[1]
     scalar = isinstance(js, (int, np.integer))

@@ -90,7 +90,6 @@ def optimal_expand(st: InfiniteMPS, H, trunc=("truncdim", 1), envs=None, log=Non
 
 def rand_expand(st: InfiniteMPS, trunc=("truncdim", 1), rng=None, log=None):
     """changebonds(psi::InfiniteMPS, alg::RandExpand) (randexpand.jl:15-35): the same with a random two-site tensor"""
-    from .blocks import mask3
     rng = rng or np.random.default_rng(0)
     N, d, pq = st.N, len(st.pq), st.pq
     ALp, ARp, newV = [None] * N, [None] * N, [None] * N
