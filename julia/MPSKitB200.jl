@@ -367,6 +367,67 @@ function TensorKit.leftnull(A::MPSTensor{<:GradedSpace{U1Irrep}})
     return download!(N, h)
 end
 
+# VectorInterface on handles (KrylovKit vectors that stay on the device between calls): inner, norm, add!!, scale!!
+function device_dot(a::Handle, b::Handle)
+    re = Ref(0.0); im_ = Ref(0.0)
+    check(ccall((:mpsk_dot, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{Float64}, Ref{Float64}), CTX[], a.p, b.p, re, im_))
+    return complex(re[], im_[])
+end
+function device_norm(a::Handle)
+    out = Ref(0.0)
+    check(ccall((:mpsk_norm, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{Float64}), CTX[], a.p, out))
+    return out[]
+end
+function device_axpy!(y::Handle, α::Number, x::Handle)                       # y += α x
+    check(ccall((:mpsk_axpy, LIB), Int32, (Ptr{Cvoid}, Float64, Float64, Ptr{Cvoid}, Ptr{Cvoid}), CTX[], real(α), imag(α), x.p, y.p))
+    return y
+end
+
+# leftorth!(A; alg = QRpos()) / rightorth!(A; alg = LQpos()) -- orthoview.jl:49-60, ortho.jl:127-138, finitemps.jl:150
+function device_qrpos(a::Handle)
+    q = Ref{Ptr{Cvoid}}(); r = Ref{Ptr{Cvoid}}()
+    check(ccall((:mpsk_qrpos, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}, Ref{Ptr{Cvoid}}), CTX[], a.p, q, r))
+    return Handle(q[]), Handle(r[])
+end
+function device_lqpos(a::Handle)
+    l = Ref{Ptr{Cvoid}}(); q = Ref{Ptr{Cvoid}}()
+    check(ccall((:mpsk_lqpos, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}, Ref{Ptr{Cvoid}}), CTX[], a.p, l, q))
+    return Handle(l[]), Handle(q[])
+end
+device_mul_right(a::Handle, c::Handle) = binary(:mpsk_mul_bond_right, a, c)   # AC = AL * C   (orthoview.jl:95-106)
+device_mul_left(c::Handle, a::Handle) = binary(:mpsk_mul_bond_left, c, a)     # AC = C * AR
+device_ac2(a1::Handle, a2::Handle) = binary(:mpsk_contract_ac2, a1, a2)       # dmrg.jl:92,108
+function binary(sym::Symbol, a::Handle, b::Handle)
+    out = Ref{Ptr{Cvoid}}()
+    check(ccall((sym, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), CTX[], a.p, b.p, out))
+    return Handle(out[])
+end
+
+# linsolve(flip(tm), b, x0, GMRES, 1, -1) -- src/environments/mpohaminfenv.jl:95,113,146,164: the regularised MPO-free
+# transfer matrix of the identity levels as ONE device operator (regularize: transfermatrix.jl:68-76) and the library's GMRES.
+# `left` = true is flip(tm) (v -> v * tm).  The levels with an operator on the diagonal pass their 1 x 1 slices in `slices`.
+function device_transfer_linsolve(A::AbstractVector, Ab::AbstractVector, left::Bool, b::MPSBondTensor, x0::MPSBondTensor, alg,
+                                  a0::Number, a1::Number; lvec=nothing, rvec=nothing, slices=nothing)
+    n = length(A)
+    pa = [resident(A[i]).p for i in 1:n]; pb = [resident(Ab[i]).p for i in 1:n]
+    ps = slices === nothing ? C_NULL : [slice_handle(s) for s in slices]
+    hb = upload(b); hx = upload(x0)
+    # regularisation pair: lvec_adj = adjoint(lvec) in the vector space of b, rvec the subtracted direction
+    hl = lvec === nothing ? C_NULL : device_adjoint(upload(lvec)).p
+    hr = rvec === nothing ? C_NULL : upload(rvec).p
+    op = Ref{Ptr{Cvoid}}()
+    GC.@preserve pa pb ps check(ccall((:mpsk_tmop_create, LIB), Int32,
+                                      (Ptr{Cvoid}, Int32, Int32, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}),
+                                      CTX[], left ? 1 : 0, n, ps, pa, pb, hb.p, hl, hr, op))
+    x = zeros_like(hx); info = Ref(CInfo(0, 0, 0, 0.0))
+    check(ccall((:mpsk_linsolve, LIB), Int32,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Float64, Float64, Float64, Float64, Int32, Int32, Float64, Ptr{Cvoid}, Ref{CInfo}),
+                CTX[], op[], hb.p, hx.p, real(a0), imag(a0), real(a1), imag(a1), alg.krylovdim, alg.maxiter, alg.tol, x.p, info))
+    free_op(op[])
+    info[].converged == 0 && @warn "linsolve failed to converge: normres = $(info[].normres)"          # mpohaminfenv.jl:97-98
+    return download!(similar(x0), x), info[]
+end
+
 # transfer_spectrum(above; below, tol, num_vals, sector) -- src/algorithms/toolbox.jl:42-58: the reference calls
 # eigsolve(flip(TransferMatrix(above.AL, below.AL)), init, num_vals, :LM; tol); here the unit-cell transfer operator is one
 # device operator and the Krylov-Schur solve for all `num_vals` values runs inside the library.
