@@ -1269,3 +1269,24 @@ def test_haldane_gap_device(ctx):
     print("Haldane gap on the device", en[0], d48["gap"], log[-1]["energy"], d48["energy_per_site"], eps)
     assert abs(log[-1]["energy"] - d48["energy_per_site"]) <= 1e-9
     assert abs(en[0] - 0.41047925) <= 1e-4 and abs(en[0] - d48["gap"]) <= 1e-6
+
+
+@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: never run on a GPU; XPASS = verified")
+def test_time_mpo_wii_approximate_vs_tdvp(ctx):
+    """test/algorithms.jl:447-466 with the reference's own time-evolution MPO: W = make_time_mpo(H, dt, WII())
+    (timeevmpo.jl:149-207; host-side construction, validated against exp(-i dt H) in tests/test_abi_cpu.py) applied to a U(1)
+    two-site InfiniteMPS and approximated with VOMPS and IDMRG2 on the device, against a device TDVP step (the reference asserts
+    |dot| = 1 within dt; here 1e-9, the oracle gives 3e-14).  The device algorithms are verified with a W^I MPO by the tests
+    above; this charged four-level W^II MPO has not been executed on a GPU, hence the non-strict xfail marker."""
+    from mpskit_b200.operators import make_time_mpo
+    dt = 1e-3
+    Hd = m.heisenberg_u1(2)
+    W = make_time_mpo(Hd, dt)
+    Vs = [m.Space((-2, 0, 2), (2, 3, 2)), m.Space((-1, 1), (3, 3))]
+    st = m.InfiniteMPS.random(np.random.default_rng(5), m.Space((-1, 1), (1, 1)), Vs, ctx)
+    a, _, eps = m.approximate(st, (W, st), m.VOMPS(tol=1e-12, maxiter=100))
+    b, _, eps2 = m.approximate(st, (W, st), m.IDMRG2(tol=1e-12, maxiter=200, trscheme=m.truncdim(7)))
+    t, _ = m.timestep_infinite(st, Hd, 0.0, dt)
+    ov_a, ov_b, ov_0 = abs(m.dot_infinite(a, t)), abs(m.dot_infinite(b, t)), abs(m.dot_infinite(st, t))
+    print("W^II approximate vs TDVP", eps, eps2, ov_a, ov_b, ov_0)
+    assert eps <= 1e-11 and abs(ov_a - 1.0) <= 1e-9 and abs(ov_b - 1.0) <= 1e-9 and abs(ov_0 - 1.0) > 1e-8
