@@ -49,3 +49,4 @@ from .statmech import approximate_idmrg1, approximate_idmrg2  # noqa: F401
 from .quasiparticle import QuasiparticleAnsatz, FiniteQP, excitations_qp  # noqa: F401
 from .quasiparticle import InfiniteQP, excitations_qp_infinite  # noqa: F401
 from .operators import make_time_mpo  # noqa: F401
+from .quasiparticle import fidelity_susceptibility  # noqa: F401

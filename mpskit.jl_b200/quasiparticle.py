@@ -387,3 +387,47 @@ def excitations_qp_infinite(H, alg: QuasiparticleAnsatz, momentum, gs, envs=None
         energies.append(float(np.real(val))); found.append(vec)
     heff.free()
     return energies, found, qp
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+def fidelity_susceptibility(gs, H0, Vs, henvs=None, tol=1e-12, maxiter=100):
+    """fidelity_susceptibility(state, H0, Vs, henvs; maxiter, tol) (src/algorithms/fidelity_susceptibility.jl:4-29) for a
+    FiniteMPS or an InfiniteMPS: for every perturbation V the tangent vector with B_i = dAC_V(i) * AC_i (projected on the left
+    null spaces, LeftGaugedQP) is the right-hand side of  H_eff x = Tos  with the effective excitation Hamiltonian of H0 at zero
+    momentum, solved by GMRES over the tuple of X tensors (x0 = Tos, as there); the result is the matrix dot(x_a, x_b)."""
+    from .krylov import linsolve_gmres
+    from . import infinite as di
+    infinite = hasattr(gs, "N") and not hasattr(gs, "L")
+    ctx = gs.ctx
+    if infinite:
+        henvs = henvs if henvs is not None else di.environments(gs, H0)
+        qp = InfiniteQP(gs, 0.0)
+        E = []
+        for loc in range(gs.N):
+            ac = gs.AC[loc]
+            h = MPO_ddAC(ctx, H0[loc], henvs.leftenv(loc, gs), henvs.rightenv(loc, gs), ac)
+            y = h(ac); h.free()
+            E.append(complex(ac.dot(y))); y.free()
+        heff = _InfHEff(H0, qp, henvs, E, solver_tol=min(tol, 1e-12))
+    else:
+        henvs = henvs if henvs is not None else environments(gs, H0)
+        qp = FiniteQP(gs)
+        heff = _HEff(H0, qp, henvs, renormalization_energy(H0, gs, henvs))
+    vecs = []
+    for V in Vs:
+        venvs = di.environments(gs, V) if infinite else environments(gs, V)
+        Xs = []
+        for i in qp.active:
+            ac = gs.AC[i]
+            h = MPO_ddAC(ctx, V[i], venvs.leftenv(i, gs), venvs.rightenv(i, gs), ac)
+            temp = h(ac); h.free()
+            Xs.append(_overlap(gs, temp, qp.VLs[i]))               # Tos[i] = temp (x) utility leg -> X_i = VL_i' * temp
+            temp.free()
+        b = RecursiveVec(Xs)
+        x, info = linsolve_gmres(heff, b, b, 0.0, 1.0, tol, 30, maxiter)
+        if info["converged"] == 0:
+            import warnings
+            warnings.warn(f"failed to converge: normres = {info['normres']}")      # fidelity_susceptibility.jl:21
+        vecs.append(x)
+    heff.free()
+    return np.array([[complex(a.dot(b)) for b in vecs] for a in vecs])

@@ -267,3 +267,39 @@ def excitations_infinite(H, momentum, gs, envs, num=1, tol=1e-10, krylovdim=30, 
         val, vec, info = eigsolve_lanczos(f, x0, "SR", tol, krylovdim, maxiter)
         energies.append(float(np.real(val))); found.append(vec)
     return energies, [qp.unpack(v) for v in found], qp
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+def fidelity_susceptibility(gs, H0, Vs, henvs=None, tol=1e-12, maxiter=100):
+    """fidelity_susceptibility(state, H0, Vs, henvs; maxiter, tol) (src/algorithms/fidelity_susceptibility.jl:4-29) for a
+    FiniteMPS or InfiniteMPS: for every perturbation V the tangent vector Tos with B_i = dAC_V(i) * AC_i (projected on the
+    left null spaces) is fed to the linear system  H_eff x = Tos  (GMRES, x0 = Tos) with the effective excitation Hamiltonian
+    of H0 at zero momentum; the susceptibility matrix is dot(x_a, x_b)."""
+    from .krylov import linsolve_gmres
+    from .infinite import MPOHamInfEnv
+    infinite = hasattr(gs, "N")
+    if infinite:
+        henvs = henvs or MPOHamInfEnv(gs, H0)
+        qp = InfiniteQP(gs, 0.0)
+        L = gs.N
+        AC = lambda i: gs.AC[i]
+        E = [np.vdot(AC(i), dAC_sparse(AC(i), H0[i], henvs.leftenv(i, gs), henvs.rightenv(i, gs))) for i in range(L)]
+        heff = lambda v: qp.pack(effective_excitation_hamiltonian_infinite(H0, qp, qp.unpack(v), henvs, E, 1e-13))
+    else:
+        henvs = henvs or FinEnv(gs, H0)
+        qp = FiniteQP(gs)
+        L = gs.L
+        AC = lambda i: gs.get_AC(i)
+        E = renormalization_energy(H0, gs, henvs)
+        heff = lambda v: qp.pack(effective_excitation_hamiltonian(H0, qp, qp.unpack(v), henvs, E))
+    vecs = []
+    for V in Vs:
+        venvs = MPOHamInfEnv(gs, V) if infinite else FinEnv(gs, V)
+        Xs = []
+        for i in range(L):
+            temp = dAC_sparse(AC(i), V[i], venvs.leftenv(i, gs), venvs.rightenv(i, gs))
+            Xs.append(np.einsum('apk,apr->kr', np.conj(qp.VLs[i]), temp))
+        b = qp.pack(Xs)
+        x, info = linsolve_gmres(heff, b, b, 0.0, 1.0, tol, 30, maxiter)
+        vecs.append(x)
+    return np.array([[np.vdot(a, b) for b in vecs] for a in vecs])

@@ -1290,3 +1290,34 @@ def test_time_mpo_wii_approximate_vs_tdvp(ctx):
     ov_a, ov_b, ov_0 = abs(m.dot_infinite(a, t)), abs(m.dot_infinite(b, t)), abs(m.dot_infinite(st, t))
     print("W^II approximate vs TDVP", eps, eps2, ov_a, ov_b, ov_0)
     assert eps <= 1e-11 and abs(ov_a - 1.0) <= 1e-9 and abs(ov_b - 1.0) <= 1e-9 and abs(ov_0 - 1.0) > 1e-8
+
+
+@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: never run on a GPU; XPASS = verified")
+def test_fidelity_susceptibility_device(ctx):
+    """fidelity_susceptibility(psi, H, [H_X], envs) (fidelity_susceptibility.jl:4-29; test/algorithms.jl:368-396 asserts the
+    analytic value |1 / (16 l^2 (l^2 - 1))| of the transverse-field Ising chain within 1e-2): infinite D = 16 states at l = 2 and
+    l = 4 against the analytic value (1e-8; the oracle gives 3e-13 / 2e-17) and a finite chain against the oracle (1e-8).  Built
+    from the quasiparticle effective Hamiltonian verified above plus the host-driven GMRES; this combination has not been
+    executed on a GPU, hence the non-strict xfail marker."""
+    from oracle import quasiparticle as oq
+    X = np.array([[0, 1], [1, 0]], dtype=complex)
+    for lam in (2.0, 4.0):
+        Hd = dev_hamiltonian(ompo.transverse_field_ising(1, lam))
+        Vd = dev_hamiltonian(ompo.fsm_hamiltonian(1, 2, {(0, 0): 1.0, (1, 1): 1.0, (0, 1): X}, (0, 0), (0, 0)))
+        st = m.InfiniteMPS.random(np.random.default_rng(3), m.Space((0,), (2,)), [m.Space((0,), (16,))], ctx)
+        st, envs, _ = m.find_groundstate_vumps(st, Hd, m.VUMPS(tol=1e-11, maxiter=300))
+        chi = m.fidelity_susceptibility(st, Hd, [Vd], envs)
+        exact = abs(1 / (16 * lam ** 2 * (lam ** 2 - 1)))
+        print("fidelity susceptibility", lam, chi[0, 0], exact)
+        assert abs(chi[0, 0] - exact) <= 1e-8
+    L, lam = 8, 2.0
+    Ho = ompo.transverse_field_ising(L, lam)
+    Vo = ompo.fsm_hamiltonian(L, 2, {(0, 0): 1.0, (1, 1): 1.0, (0, 1): X}, (0, 0), (0, 0))
+    psi_o = of.FiniteMPS.random(np.random.default_rng(1), OSpace((0,), (2,)), L, OSpace((0,), (16,)))
+    psi_o, envs_o, _ = of.dmrg2_sweeps(psi_o, Ho, nsweeps=8, trunc=("truncdim", 16), tol=1e-13)
+    chi_o = oq.fidelity_susceptibility(psi_o, Ho, [Vo], envs_o)
+    psi_d = m.FiniteMPS.random(np.random.default_rng(1), m.Space((0,), (2,)), L, m.Space((0,), (16,)), ctx)
+    psi_d, envs_d, _ = m.find_groundstate(psi_d, dev_hamiltonian(Ho), m.DMRG2(tol=1e-13, maxiter=8, eigalg=m.Lanczos(tol=1e-13), trscheme=m.truncdim(16)))
+    chi_d = m.fidelity_susceptibility(psi_d, dev_hamiltonian(Ho), [dev_hamiltonian(Vo)], envs_d)
+    print("finite fidelity susceptibility", chi_d[0, 0], chi_o[0, 0])
+    assert abs(chi_d[0, 0] - chi_o[0, 0]) <= 1e-8

@@ -670,3 +670,28 @@ def test_haldane_gap_pin_of_the_reference_test_suite():
         d28 = [r for r in rec["runs"] if r["D"] == 28][0]
         new = mod.run({int(k): v for k, v in d28["bond_space"].items()})
         assert abs(new["gap"] - d28["gap"]) < 1e-7 and abs(new["energy_per_site"] - d28["energy_per_site"]) < 1e-9
+
+
+def test_fidelity_susceptibility_oracle_equals_analytic_value():
+    """oracle fidelity_susceptibility (fidelity_susceptibility.jl:4-29) on VUMPS ground states of the TFI chain against the
+    analytic value |1 / (16 l^2 (l^2 - 1))| that test/algorithms.jl:368-396 asserts within 1e-2 (here 1e-10), and the finite
+    chain against exact perturbation theory (sum over exact eigenstates)."""
+    from oracle import infinite as oi, quasiparticle as oq
+    X = np.array([[0, 1], [1, 0]], dtype=complex)
+    for lam in (2.0, 4.0):
+        H = ompo.transverse_field_ising(1, lam)
+        V = ompo.fsm_hamiltonian(1, 2, {(0, 0): 1.0, (1, 1): 1.0, (0, 1): X}, (0, 0), (0, 0))
+        st = oi.InfiniteMPS.random(np.random.default_rng(3), Space((0,), (2,)), [Space((0,), (16,))])
+        st, envs, _ = oi.vumps(st, H, tol=1e-11, maxiter=300)
+        chi = oq.fidelity_susceptibility(st, H, [V], envs)
+        assert abs(chi[0, 0] - abs(1 / (16 * lam ** 2 * (lam ** 2 - 1)))) < 1e-10
+    L, lam = 8, 2.0
+    H = ompo.transverse_field_ising(L, lam)
+    V = ompo.fsm_hamiltonian(L, 2, {(0, 0): 1.0, (1, 1): 1.0, (0, 1): X}, (0, 0), (0, 0))
+    psi = of.FiniteMPS.random(np.random.default_rng(1), Space((0,), (2,)), L, Space((0,), (16,)))
+    psi, envs, _ = of.dmrg2_sweeps(psi, H, nsweeps=8, trunc=("truncdim", 16), tol=1e-13)
+    chi = oq.fidelity_susceptibility(psi, H, [V], envs)
+    ev, U = np.linalg.eigh(ompo.dense_hamiltonian(H))
+    Vm = ompo.dense_hamiltonian(V)
+    exact = sum(abs(U[:, n].conj() @ Vm @ U[:, 0]) ** 2 / (ev[n] - ev[0]) ** 2 for n in range(1, len(ev)))
+    assert abs(chi[0, 0] - exact) < 1e-9
