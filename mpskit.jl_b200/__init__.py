@@ -50,3 +50,4 @@ from .quasiparticle import QuasiparticleAnsatz, FiniteQP, excitations_qp  # noqa
 from .quasiparticle import InfiniteQP, excitations_qp_infinite  # noqa: F401
 from .operators import make_time_mpo  # noqa: F401
 from .quasiparticle import fidelity_susceptibility  # noqa: F401
+from .algorithms import UnionAlg, default_groundstate_algorithm  # noqa: F401

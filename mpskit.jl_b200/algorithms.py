@@ -103,13 +103,58 @@ def find_groundstate_dmrg_inplace(psi, H, alg: DMRG, envs=None, log=None):
     return psi, envs, eps
 
 
-def find_groundstate(psi, H, alg, envs=None, log=None):
-    """find_groundstate(psi, H, alg) = find_groundstate!(copy(psi), H, alg, envs) (dmrg.jl:139-141)"""
+@dataclass
+class UnionAlg:
+    """unionalg.jl:4-9: alg1 & alg2 -- run alg1, then alg2 from its result"""
+    alg1: object
+    alg2: object
+
+    def __and__(self, other):
+        return UnionAlg(self, other)
+
+
+def _is_infinite(psi):
+    return hasattr(psi, "N") and not hasattr(psi, "L")
+
+
+def default_groundstate_algorithm(psi, tol=1e-12, maxiter=100, verbosity=0, trscheme=None):
+    """the algorithm find_groundstate(psi, H; tol, maxiter, verbosity, trscheme) picks (find_groundstate.jl:19-41).  The
+    reference finishes InfiniteMPS runs below 1e-4 with GradientGrassmann, which is not built here: VUMPS runs to `tol`."""
+    from .infinite import VUMPS, IDMRG2
+    if _is_infinite(psi):
+        alg = VUMPS(tol=tol, maxiter=maxiter, verbosity=verbosity)
+        if trscheme is not None:
+            alg = UnionAlg(IDMRG2(tol=min(1e-2, 100 * tol), verbosity=verbosity, trscheme=trscheme), alg)
+        return alg
+    alg = DMRG(tol=tol, maxiter=maxiter, verbosity=verbosity)
+    if trscheme is not None:
+        alg = UnionAlg(DMRG2(tol=min(1e-2, 100 * tol), verbosity=verbosity, trscheme=trscheme), alg)
+    return alg
+
+
+def find_groundstate(psi, H, alg=None, envs=None, log=None, *, tol=1e-12, maxiter=100, verbosity=0, trscheme=None):
+    """find_groundstate(psi, H, alg, envs) for FiniteMPS (DMRG, DMRG2: find_groundstate!(copy(psi), ...), dmrg.jl:139-141) and
+    InfiniteMPS (VUMPS vumps.jl:29-92, IDMRG1 / IDMRG2 idmrg.jl:21-204), alg1 & alg2 (unionalg.jl:22-25), and the keyword form
+    find_groundstate(psi, H; tol, maxiter, verbosity, trscheme) of find_groundstate.jl:19-41 (alg = None)."""
+    if alg is None:
+        alg = default_groundstate_algorithm(psi, tol, maxiter, verbosity, trscheme)
+    if isinstance(alg, UnionAlg):
+        psi, envs, _ = find_groundstate(psi, H, alg.alg1, envs, log)
+        return find_groundstate(psi, H, alg.alg2, envs, log)
+    if _is_infinite(psi):
+        from . import infinite as di
+        if isinstance(alg, di.VUMPS):
+            return di.find_groundstate_vumps(psi, H, alg, envs, log)
+        if isinstance(alg, di.IDMRG1):
+            return di.find_groundstate_idmrg1(psi, H, alg, envs, log)
+        if isinstance(alg, di.IDMRG2):
+            return di.find_groundstate_idmrg2(psi, H, alg, envs, log)
+        raise TypeError("find_groundstate on InfiniteMPS: alg must be VUMPS, IDMRG1, IDMRG2 or a union of them")
     if isinstance(alg, DMRG2):
         return _dmrg2_inplace(psi.copy(), H, alg, envs, log)
     if isinstance(alg, DMRG):
         return find_groundstate_dmrg_inplace(psi.copy(), H, alg, envs, log)
-    raise TypeError("find_groundstate: only DMRG and DMRG2 are implemented on the device path")
+    raise TypeError("find_groundstate on FiniteMPS: alg must be DMRG, DMRG2 or a union of them")
 
 
 def timestep_inplace(psi, H, t, dt, alg, envs=None):
@@ -180,3 +225,13 @@ def time_evolve(psi, H, t_span, alg=None, envs=None):
             if alg.finalize is not None:
                 psi, envs = alg.finalize(t, psi, H, envs)
     return psi, envs
+
+
+def _enable_union_operator():
+    """Base.:&(alg1::Algorithm, alg2::Algorithm) = UnionAlg(alg1, alg2) (unionalg.jl:11) for the algorithm dataclasses"""
+    from .infinite import VUMPS, IDMRG1, IDMRG2
+    for cls in (DMRG, DMRG2, TDVP, TDVP2, VUMPS, IDMRG1, IDMRG2):
+        cls.__and__ = lambda a, b: UnionAlg(a, b)
+
+
+_enable_union_operator()

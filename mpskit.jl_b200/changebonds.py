@@ -126,6 +126,12 @@ def changebonds(psi, H=None, alg=None, envs=None, log=None):
     changebonds(psi, alg::SvdCut) = changebonds!(copy(psi), alg) (svdcut.jl:13)"""
     if alg is None:                                   # changebonds(psi, alg)
         H, alg = None, H
+    from .algorithms import UnionAlg
+    if isinstance(alg, UnionAlg):                     # unionalg.jl:13-23
+        if H is None:
+            return changebonds(changebonds(psi, alg.alg1, log=log), alg.alg2, log=log)
+        psi, envs = changebonds(psi, H, alg.alg1, envs, log)
+        return changebonds(psi, H, alg.alg2, envs, log)
     if hasattr(psi, "N") and not hasattr(psi, "L"):   # InfiniteMPS
         return changebonds_infinite(psi, H, alg, envs, log)
     if isinstance(alg, SvdCut):
@@ -409,3 +415,12 @@ def dot_infinite(a, b, krylovdim=30, tol=1e-12):
     device Arnoldi on the unit-cell transfer operator"""
     from .toolbox import transfer_spectrum
     return transfer_spectrum(b, below=a, num_vals=1, tol=tol, krylovdim=krylovdim)[0]
+
+
+def _union(a, b):
+    from .algorithms import UnionAlg
+    return UnionAlg(a, b)
+
+
+for _cls in (SvdCut, OptimalExpand, RandExpand, VUMPSSvdCut):          # alg1 & alg2 (unionalg.jl:11)
+    _cls.__and__ = _union

@@ -293,3 +293,41 @@ def test_make_time_mpo_wii_host_logic_without_gpu():
     a, _, eps = osm.vomps(st, sl, st, tol=1e-12, maxiter=100)
     t, _ = oi.tdvp_step(st, ompo.heisenberg_u1(2), dt)
     assert eps < 1e-11 and abs(abs(ocb.dot(a, t)) - 1) < 1e-10 and abs(abs(ocb.dot(st, t)) - 1) > 1e-8
+
+
+def test_find_groundstate_dispatch_and_union_algorithms_without_gpu(monkeypatch):
+    """host-side dispatch of find_groundstate (find_groundstate.jl:19-41, unionalg.jl:4-25): the keyword form picks DMRG
+    (FiniteMPS), DMRG2 & DMRG with a truncation scheme, VUMPS / IDMRG2 & VUMPS (InfiniteMPS); alg1 & alg2 runs both in order and
+    hands state and environments on.  The solvers are replaced by recorders: no device call."""
+    import mpskit_b200 as m
+    from mpskit_b200 import algorithms as alg_mod, infinite as di
+    calls = []
+
+    class Fin:
+        L = 4
+
+        def copy(self):
+            return self
+
+    class Inf:
+        N = 2
+    monkeypatch.setattr(alg_mod, "_dmrg2_inplace", lambda psi, H, a, envs, log: (calls.append(("DMRG2", a, envs)) or (psi, "envs-after-dmrg2", 0.0)))
+    monkeypatch.setattr(alg_mod, "find_groundstate_dmrg_inplace", lambda psi, H, a, envs, log: (calls.append(("DMRG", a, envs)) or (psi, "envs-after-dmrg", 0.0)))
+    monkeypatch.setattr(di, "find_groundstate_vumps", lambda psi, H, a, envs, log: (calls.append(("VUMPS", a, envs)) or (psi, "envs-after-vumps", 0.0)))
+    monkeypatch.setattr(di, "find_groundstate_idmrg2", lambda psi, H, a, envs, log: (calls.append(("IDMRG2", a, envs)) or (psi, "envs-after-idmrg2", 0.0)))
+    m.find_groundstate(Fin(), "H", tol=1e-9, maxiter=7)
+    assert [c[0] for c in calls] == ["DMRG"] and calls[0][1].tol == 1e-9 and calls[0][1].maxiter == 7
+    calls.clear()
+    m.find_groundstate(Fin(), "H", tol=1e-9, trscheme=m.truncdim(8))
+    assert [c[0] for c in calls] == ["DMRG2", "DMRG"] and abs(calls[0][1].tol - 1e-7) < 1e-20 and calls[1][2] == "envs-after-dmrg2"
+    calls.clear()
+    m.find_groundstate(Inf(), "H", tol=1e-10, trscheme=m.truncdim(8))
+    assert [c[0] for c in calls] == ["IDMRG2", "VUMPS"] and calls[1][1].tol == 1e-10 and calls[1][2] == "envs-after-idmrg2"
+    calls.clear()
+    u = m.DMRG2(trscheme=m.truncdim(4)) & m.DMRG(tol=1e-6) & m.DMRG(tol=1e-12)
+    assert isinstance(u, m.UnionAlg) and isinstance(u.alg1, m.UnionAlg)
+    m.find_groundstate(Fin(), "H", u)
+    assert [c[0] for c in calls] == ["DMRG2", "DMRG", "DMRG"] and calls[2][1].tol == 1e-12
+    assert isinstance(m.SvdCut() & m.OptimalExpand(), m.UnionAlg)
+    with pytest.raises(TypeError):
+        m.find_groundstate(Inf(), "H", m.DMRG())
