@@ -1321,3 +1321,27 @@ def test_fidelity_susceptibility_device(ctx):
     chi_d = m.fidelity_susceptibility(psi_d, dev_hamiltonian(Ho), [dev_hamiltonian(Vo)], envs_d)
     print("finite fidelity susceptibility", chi_d[0, 0], chi_o[0, 0])
     assert abs(chi_d[0, 0] - chi_o[0, 0]) <= 1e-8
+
+
+@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: never run on a GPU; XPASS = verified")
+def test_find_groundstate_keyword_form_and_union(ctx):
+    """find_groundstate(psi, H; tol, trscheme) (find_groundstate.jl:19-41) and alg1 & alg2 (unionalg.jl): the README quickstart
+    form on a finite chain (DMRG2 & DMRG) against exact diagonalisation, and on an InfiniteMPS (IDMRG2 & VUMPS) against the exact
+    TFI energy density.  Pure dispatch over the solvers verified above (the dispatch itself is tested on the CPU)."""
+    import scipy.integrate as si
+    L = 8
+    Ho = ompo.transverse_field_ising(L, 1.5)
+    psi = m.FiniteMPS.random(np.random.default_rng(1), m.Space((0,), (2,)), L, m.Space((0,), (4,)), ctx)
+    Hd = dev_hamiltonian(Ho)
+    psi, envs, eps = m.find_groundstate(psi, Hd, tol=1e-10, trscheme=m.truncdim(16))
+    E = float(np.sum(m.expectation_value(psi, Hd, envs)).real)
+    assert abs(E - np.linalg.eigvalsh(ompo.dense_hamiltonian(Ho))[0]) <= 1e-9
+    g = 0.5
+    H2 = dev_hamiltonian(ompo.transverse_field_ising(2, g))
+    st = m.InfiniteMPS.random(np.random.default_rng(3), m.Space((0,), (2,)), [m.Space((0,), (4,))] * 2, ctx)
+    st, ienvs, eps = m.find_groundstate(st, H2, m.IDMRG2(tol=1e-4, maxiter=50, trscheme=m.truncdim(12)) & m.VUMPS(tol=1e-11, maxiter=100))
+    from mpskit_b200 import infinite as di
+    e = float(np.mean(di.expectation_value(st, H2, ienvs)).real)
+    exact = -si.quad(lambda k: np.sqrt(1 + g * g + 2 * g * np.cos(k)), 0, np.pi)[0] / np.pi
+    print("keyword form / union", E, e, exact, st.V[0].dim)
+    assert st.V[0].dim == 12 and abs(e - exact) <= 1e-9
