@@ -51,3 +51,4 @@ from .quasiparticle import InfiniteQP, excitations_qp_infinite  # noqa: F401
 from .operators import make_time_mpo  # noqa: F401
 from .quasiparticle import fidelity_susceptibility  # noqa: F401
 from .algorithms import UnionAlg, default_groundstate_algorithm  # noqa: F401
+from .iterlog import IterLog, VERBOSE_NONE, VERBOSE_WARN, VERBOSE_CONV, VERBOSE_ITER, VERBOSE_ALL  # noqa: F401

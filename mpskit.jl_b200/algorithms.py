@@ -85,6 +85,11 @@ def find_groundstate_dmrg_inplace(psi, H, alg: DMRG, envs=None, log=None):
     envs = envs if envs is not None else environments(psi, H)
     L = len(psi)
     eps = max(calc_galerkin(psi, pos, envs) for pos in range(L))
+    from .iterlog import IterLog
+    from .excitations import expectation_value as _total_energy
+    ilog = IterLog("DMRG", alg.verbosity)                        # dmrg.jl:25-28
+    obj = lambda: np.sum(_total_energy(psi, H, envs))
+    ilog.init(eps, obj)
     for it in range(alg.maxiter):
         eps_s = np.zeros(L)
         for pos in list(range(0, L - 1)) + list(range(L - 1, 0, -1)):
@@ -99,7 +104,12 @@ def find_groundstate_dmrg_inplace(psi, H, alg: DMRG, envs=None, log=None):
         if alg.finalize is not None:
             psi, envs = alg.finalize(it, psi, H, envs)
         if eps <= alg.tol:
+            ilog.finish(it + 1, eps, obj)                        # dmrg.jl:42-49
             break
+        if it + 1 == alg.maxiter:
+            ilog.cancel(it + 1, eps, obj)
+        else:
+            ilog.iteration(it + 1, eps, obj)
     return psi, envs, eps
 
 

@@ -86,6 +86,10 @@ def find_groundstate_inplace(psi, H, alg: DMRG2, envs=None, log=None):
     envs = envs if envs is not None else environments(psi, H)
     L = len(psi)
     eps = 0.0
+    from .iterlog import IterLog
+    ilog = IterLog("DMRG2", alg.verbosity)                       # dmrg.jl:84-87
+    obj = lambda: np.sum(expectation_value(psi, H, envs)) if not hasattr(H, "_environments") else None
+    ilog.init(2 * alg.tol, obj)
     for it in range(alg.maxiter):
         eps_s = np.zeros(L)
         for direction, rng_ in (("lr", range(0, L - 1)), ("rl", range(L - 3, -1, -1))):
@@ -121,7 +125,12 @@ def find_groundstate_inplace(psi, H, alg: DMRG2, envs=None, log=None):
         if alg.finalize is not None:
             psi, envs = alg.finalize(it, psi, H, envs)
         if eps <= alg.tol:
+            ilog.finish(it + 1, eps, obj)                        # dmrg.jl:124-132
             break
+        if it + 1 == alg.maxiter:
+            ilog.cancel(it + 1, eps, obj)
+        else:
+            ilog.iteration(it + 1, eps, obj)
     return psi, envs, eps
 
 

@@ -478,6 +478,10 @@ def find_groundstate_vumps(st: InfiniteMPS, H, alg: VUMPS = None, envs=None, log
         envs = _lazy_environments(st, H)                             # MPOHamInfEnv, or MultipleEnvironments for a LazySum
     N = st.N
     eps = max(calc_galerkin(st, i, envs) for i in range(N))
+    from .iterlog import IterLog
+    ilog = IterLog("VUMPS", alg.verbosity)                       # vumps.jl:33-35
+    obj = lambda: np.sum(expectation_value_lazy(st, H, envs))
+    ilog.init(eps, obj)
     for it in range(1, alg.maxiter + 1):
         etol = dyn_tol(eps, it, 1e-12, 1e-5, 1e-5)
         eig = Lanczos(tol=etol, krylovdim=30, maxiter=100)
@@ -497,7 +501,12 @@ def find_groundstate_vumps(st: InfiniteMPS, H, alg: VUMPS = None, envs=None, log
         if log is not None:
             log.append(dict(iter=it, eps=eps, energy=float(np.sum(expectation_value(st, H, envs)).real)))
         if eps <= alg.tol:
+            ilog.finish(it, eps, obj)                            # vumps.jl:63-66
             break
+        if it == alg.maxiter:
+            ilog.cancel(it, eps, obj)
+        else:
+            ilog.iteration(it, eps, obj)
     return st, envs, eps
 
 

@@ -331,3 +331,30 @@ def test_find_groundstate_dispatch_and_union_algorithms_without_gpu(monkeypatch)
     assert isinstance(m.SvdCut() & m.OptimalExpand(), m.UnionAlg)
     with pytest.raises(TypeError):
         m.find_groundstate(Inf(), "H", m.DMRG())
+
+
+def test_iterlog_reproduces_the_reference_log_lines():
+    """mpskit_b200/iterlog.py (src/utility/logging.jl:12-142): the exact line formats the reference prints, checked against lines
+    of its own documentation (docs/src/examples/quantum1d/4.xxz-heisenberg/index.md:42-43,142; 3.ising-dqpt/index.md), the
+    verbosity levels of defaults.jl:12-16, and laziness of the objective (never evaluated when its level is off)."""
+    import io
+    from mpskit_b200.iterlog import IterLog, format_time
+    buf = io.StringIO()
+    lg = IterLog("VUMPS", 3, buf)
+    lg.init(7.9836e-03, lambda: 2.499921743436e-01)
+    lg.iteration(1, 3.7172694563e-01, lambda: -1.716410056492e-01)
+    lg.cancel(100, 2.3131204986e-01, lambda: -4.061058847078e-01)
+    lines = buf.getvalue().splitlines()
+    assert lines[0] == "[ Info: VUMPS init:\tobj = +2.499921743436e-01\terr = 7.9836e-03"
+    assert lines[1].startswith("[ Info: VUMPS   1:\tobj = -1.716410056492e-01\terr = 3.7172694563e-01\ttime = ") and lines[1].endswith(" sec")
+    assert lines[2].startswith("┌ Warning: VUMPS cancel 100:\tobj = -4.061058847078e-01\terr = 2.3131204986e-01\ttime = ")
+    assert format_time(4.5) == "4.50 sec" and format_time(120.0) == "2.00 min" and format_time(7200.0) == "2.00 hr"
+    called = []
+    quiet = IterLog("DMRG", 0, buf)
+    quiet.init(1.0, lambda: called.append(1)); quiet.iteration(1, 0.5, lambda: called.append(1))
+    quiet.finish(2, 0.1, lambda: called.append(1)); quiet.cancel(3, 0.1, lambda: called.append(1))
+    assert not called and len(buf.getvalue().splitlines()) == 3
+    conv = IterLog("DMRG", 2, buf)
+    conv.iteration(1, 0.5, lambda: called.append(1))            # level 3 line: silent at verbosity 2
+    conv.finish(2, 1e-13, lambda: -20.40021786703)
+    assert not called and buf.getvalue().splitlines()[-1].startswith("[ Info: DMRG conv 2:\tobj = -2.040021786703e+01\terr = 1.0000000000e-13\ttime = ")
