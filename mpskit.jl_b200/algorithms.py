@@ -245,3 +245,50 @@ def _enable_union_operator():
 
 
 _enable_union_operator()
+
+
+def exact_diagonalization(H, pspace, L=None, sector=0, num=1, which="SR", alg=None, ctx=None, seed=0, weight=1000.0):
+    """exact_diagonalization(opp::MPOHamiltonian; sector, len, num, which, alg) (src/algorithms/ED.jl:4-53): the largest possible
+    FiniteMPS of that length -- bond spaces limited only by the Hilbert spaces to their left and right, total charge `sector`
+    on the right edge -- whose middle site then parametrises the whole (symmetry sector of the) Hilbert space, so that the
+    single-site effective Hamiltonian IS the Hamiltonian; its lowest `num` eigenpairs come from the device Lanczos (further
+    ones by shifting the converged ones up by `weight`, host-driven over the device VectorInterface).
+    Returns (values, states, infos)."""
+    from .finitemps import FiniteMPS
+    from .spaces import Space, fuse, infimum, dual
+    from .krylov import eigsolve_lanczos
+    L = len(H) if L is None else int(L)
+    alg = alg or Lanczos(tol=1e-12, krylovdim=30, maxiter=100)
+    mod = pspace.modulus
+    Vl = [Space((0,), (1,), mod)]
+    for _ in range(L):
+        Vl.append(fuse(Vl[-1], pspace))
+    Vr = [Space((int(sector),), (1,), mod)]
+    for _ in range(L):
+        Vr.append(fuse(Vr[-1], dual(pspace)))
+    Vr = Vr[::-1]
+    V = [infimum(Vl[k], Vr[k]) for k in range(L + 1)]
+    if any(v.dim == 0 for v in V):
+        raise ValueError("invalid sector")                                    # ED.jl:36
+    psi = FiniteMPS.random(np.random.default_rng(seed), pspace, L, V[1:L], ctx, left=V[0], right=V[L])
+    mid = max(int(round(L / 2)) - 1, 0)                                       # ED.jl:11 (1-based there)
+    envs = environments(psi, H)
+    h = ddAC(mid, psi, H, envs)
+    vals, states, infos, found = [], [], [], []
+    for n in range(num):
+        if n == 0:
+            val, vec, info = fixedpoint(h, psi.AC[mid], which, alg, return_info=True)
+        else:
+            def f(v):
+                y = h(v)
+                for u in found:
+                    y.axpy(weight * complex(u.dot(v)), u)
+                return y
+            x0 = DeviceTensor.random(psi.ctx, psi.AC[mid].Vl, psi.AC[mid].mch, psi.AC[mid].Vr, seed + 7 * n, psi.dtype)
+            val, vec, info = eigsolve_lanczos(f, x0, which, alg.tol, alg.krylovdim, alg.maxiter)
+        found.append(vec)
+        st = psi.copy()
+        st.AC[mid] = vec
+        vals.append(complex(val)); states.append(st); infos.append(info)
+    h.free()
+    return vals, states, infos

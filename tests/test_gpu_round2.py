@@ -1345,3 +1345,24 @@ def test_find_groundstate_keyword_form_and_union(ctx):
     exact = -si.quad(lambda k: np.sqrt(1 + g * g + 2 * g * np.cos(k)), 0, np.pi)[0] / np.pi
     print("keyword form / union", E, e, exact, st.V[0].dim)
     assert st.V[0].dim == 12 and abs(e - exact) <= 1e-9
+
+
+@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: never run on a GPU; XPASS = verified")
+def test_exact_diagonalization_device(ctx):
+    """exact_diagonalization(H; sector, num) (ED.jl:4-53): a full-bond-dimension FiniteMPS whose middle site spans the symmetry
+    sector; the two lowest eigenvalues of the single-site effective Hamiltonian against dense diagonalisation (TFI chain, and
+    the S_z = 0 and S_z = 1 sectors of the U(1) Heisenberg chain)."""
+    L = 8
+    Ho = ompo.transverse_field_ising(L, 1.5)
+    vals, states, infos = m.exact_diagonalization(dev_hamiltonian(Ho), m.Space((0,), (2,)), num=2, ctx=ctx)
+    ev = np.linalg.eigvalsh(ompo.dense_hamiltonian(Ho))
+    assert abs(vals[0].real - ev[0]) <= 1e-10 and abs(vals[1].real - ev[1]) <= 1e-9
+    Hh = ompo.heisenberg_u1(L)
+    Hm = ompo.dense_hamiltonian(Hh)
+    for sector, nup in ((0, L // 2), (2, L // 2 + 1)):
+        keep = [k for k in range(2 ** L) if bin(k).count("1") == nup]
+        evs = np.linalg.eigvalsh(Hm[np.ix_(keep, keep)])
+        vals, states, infos = m.exact_diagonalization(dev_hamiltonian(Hh), m.Space((-1, 1), (1, 1)), sector=sector, num=1, ctx=ctx)
+        print("ED sector", sector, vals[0], evs[0])
+        # the sign convention of the sector label (S_z = +1 or -1) does not matter for the Heisenberg chain
+        assert abs(vals[0].real - evs[0]) <= 1e-10
