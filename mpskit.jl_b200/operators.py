@@ -360,8 +360,12 @@ def make_time_mpo(H: MPOHamiltonian, dt, alg="WII"):
     first block column of exp(F) gives W_D, W_C[k], W_B[j], W_A[j, k].  The result has odim - 1 levels -- the first and last
     level of H merge into level 0 -- and is used as a (periodic) list of slices, e.g. by approximate(psi, (W, psi), VOMPS()).
     Host-side model building on d x d numbers per entry; nothing here touches the device."""
+    if alg == "WI":
+        alg = ("TaylorCluster", 1)                                     # const WI = TaylorCluster{1} (timeevmpo.jl:10)
+    if isinstance(alg, tuple) and alg[0] == "TaylorCluster":
+        return _taylor_cluster(H, dt, int(alg[1]))
     if alg != "WII":
-        raise ValueError("make_time_mpo: only the W^II construction is built (TaylorCluster is not)")
+        raise ValueError("make_time_mpo: alg must be 'WII', 'WI' or ('TaylorCluster', N)")
     from scipy.linalg import expm
     delta = -1j * dt
     sq = np.sqrt(delta + 0j)
@@ -412,4 +416,164 @@ def make_time_mpo(H: MPOHamiltonian, dt, alg="WII"):
                 if np.abs(W[j][k]).max() == 0.0:
                     W[j][k] = 0
         out.append(SparseMPOSlice(W, cl, cr, sl.pcharges, sl.modulus))
+    return MPOHamiltonian(out)
+
+
+def _taylor_cluster(H: MPOHamiltonian, dt, N):
+    """make_time_mpo(H, dt, TaylorCluster{N}()) (src/algorithms/timestep/timeevmpo.jl:12-108; Van Damme et al.,
+    arXiv:2302.14181): the N-fold operator product MPO H * ... * H (levels = N-tuples of levels of H, first index fastest) with
+    (i) the next order embedded into the entries that continue, (ii) the tuples that have finished (only first / last levels)
+    looped back to level 1 with the Taylor weights tau^order (N - order)! / N!, (iii) permutation-equivalent rows / columns
+    merged, (iv) the approximate compression of the partially finished tuples, (v) orphan levels removed.  exp(-i dt H) is
+    reproduced to O(dt^(N+1)) per site.  Host-side model building on d x d matrices."""
+    import itertools
+    from math import factorial
+    tau = -1j * dt
+    out_slices = []
+    for sl in H.slices:
+        od, d = sl.odim, sl.d
+        eye = np.eye(d, dtype=np.complex128)
+
+        def hop(i, j):
+            e = sl.Os[i][j]
+            if np.isscalar(e):
+                return None if e == 0 else complex(e) * eye
+            return np.asarray(e, dtype=np.complex128)
+        base = [[hop(i, j) for j in range(od)] for i in range(od)]
+
+        def prod_elem(ta, tb):
+            """calc_prod_elem: H[a_n, b_n] ... H[a_2, b_2] H[a_1, b_1] (the first tuple entry acts first); None if absent"""
+            o = None
+            for a, b in zip(ta, tb):
+                e = base[a][b]
+                if e is None:
+                    return None
+                o = e if o is None else e @ o
+            return o
+        tuples = list(itertools.product(range(od), repeat=N))
+        tuples.sort(key=lambda t: sum(x * od ** k for k, x in enumerate(t)))      # LinearIndices: first index fastest
+        index = {t: k for k, t in enumerate(tuples)}
+        n = len(tuples)
+        W = [[None] * n for _ in range(n)]
+        for a in tuples:
+            for b in tuples:
+                e = prod_elem(a, b)
+                if e is not None:
+                    W[index[a]][index[b]] = e
+        first, last = 0, od - 1
+
+        def add(i, j, e):
+            W[i][j] = e if W[i][j] is None else W[i][j] + e
+
+        def interweave(x, t):
+            """all tuples obtained by inserting the single element x somewhere into t (timeevmpo.jl:123-147 for length(a) == 1)"""
+            return [t[:k] + (x,) + t[k:] for k in range(len(t) + 1)]
+        # (i) embed the next order (timeevmpo.jl:26-45)
+        for a in tuples:
+            for b in tuples:
+                if not all(x > first for x in b):
+                    continue
+                if all(x in (first, last) for x in a) and any(x == last for x in a):
+                    continue
+                n3 = sum(x == last for x in b) + 1
+                n1 = sum(x == first for x in a) + 1
+                for eb in interweave(last, b):
+                    for ea in interweave(first, a):
+                        e = prod_elem(ea, eb)
+                        if e is not None:
+                            add(index[a], index[b], e * tau * factorial(N) / (factorial(N + 1) * n1 * n3))
+
+        def zero_rowcol(c):
+            for k in range(n):
+                W[c][k] = None
+                W[k][c] = None
+        # (ii) loop back the finished tuples (timeevmpo.jl:48-57)
+        for a in itertools.product((first, last), repeat=N):
+            a = a[::-1]                                                 # Iterators.product: first index fastest
+            if all(x == first for x in a):
+                continue
+            order = sum(x == last for x in a)
+            c = index[a]
+            for r in range(c):
+                if W[r][c] is not None:
+                    add(r, 0, W[r][c] * tau ** order * factorial(N - order) / factorial(N))
+            zero_rowcol(c)
+        # (iii) merge permutation-equivalent columns / rows (timeevmpo.jl:60-91)
+        for c in tuples:
+            s_tc = tuple(sorted(c, key=lambda x: 2 if x == first else 1))
+            n1 = sum(x == first for x in c); n3 = sum(x == last for x in c)
+            if n1 >= n3 and c != s_tc:
+                for k in range(n):
+                    if W[index[c]][k] is not None:
+                        add(index[s_tc], k, W[index[c]][k])
+                zero_rowcol(index[c])
+        for c in tuples:
+            s_tc = tuple(sorted(c, key=lambda x: 2 if x == last else 1))
+            n1 = sum(x == first for x in c); n3 = sum(x == last for x in c)
+            if n3 > n1 and c != s_tc:
+                for k in range(n):
+                    if W[k][index[c]] is not None:
+                        add(k, index[s_tc], W[k][index[c]])
+                zero_rowcol(index[c])
+        # (iv) approximate compression (timeevmpo.jl:93-105)
+        for c in tuples:
+            nl = sum(x == last for x in c)
+            if not (all(x > first for x in c) and nl > 0):
+                continue
+            tr = tuple(first if x == last else x for x in c)
+            for k in range(n):
+                if W[k][index[c]] is not None:
+                    add(k, index[tr], W[k][index[c]] * tau ** nl * factorial(N - nl) / factorial(N))
+            zero_rowcol(index[c])
+        cl = [sum(sl.domcharges[x] for x in t) for t in tuples]
+        cr = [sum(sl.imcharges[x] for x in t) for t in tuples]
+        out_slices.append((W, cl, cr, sl))
+    # (v) remove_orphans (sparsempo.jl:310-350): levels that nothing enters or nothing leaves, repeated until stable
+    n = len(out_slices[0][0])
+    keep = list(range(n))
+    L = len(out_slices)
+    changed = True
+    while changed:
+        changed = False
+        for loc in range(L):
+            W = out_slices[loc][0]
+            Wp = out_slices[(loc - 1) % L][0]
+            Wn = out_slices[(loc + 1) % L][0]
+            for i in list(keep):
+                dead_start = all(W[i][k] is None for k in keep)         # nothing leaves level i at this site
+                dead_end = all(W[k][i] is None for k in keep)           # nothing enters level i at this site
+                if dead_start and any(Wp[k][i] is not None for k in keep):
+                    for k in keep:
+                        Wp[k][i] = None
+                    changed = True
+                if dead_end and any(Wn[i][k] is not None for k in keep):
+                    for k in keep:
+                        Wn[i][k] = None
+                    changed = True
+        alive = [i for i in keep if not all(all(out_slices[loc][0][i][k] is None for k in keep) for loc in range(L))
+                 and not all(all(out_slices[loc][0][k][i] is None for k in keep) for loc in range(L))]
+        if len(alive) != len(keep):
+            keep = alive
+            changed = True
+    out = []
+    for W, cl, cr, sl in out_slices:
+        d = sl.d
+        ent = [[0 for _ in keep] for _ in keep]
+        ncl = [cl[i] for i in keep]; ncr = [cr[i] for i in keep]
+        for a, i in enumerate(keep):
+            for b, j in enumerate(keep):
+                e = W[i][j]
+                if e is None:
+                    continue
+                e = np.array(e)
+                for p in range(d):
+                    for q in range(d):
+                        viol = ncr[b] - ncl[a] - sl.pcharges[p] + sl.pcharges[q]
+                        if (viol % sl.modulus if sl.modulus else viol) != 0:
+                            if abs(e[p, q]) > 1e-12:
+                                raise _lib.SpaceMismatch(_lib.ESPACE, f"time MPO entry ({a},{b}) violates charge conservation")
+                            e[p, q] = 0.0
+                if np.abs(e).max() > 0:
+                    ent[a][b] = e
+        out.append(SparseMPOSlice(ent, ncl, ncr, sl.pcharges, sl.modulus))
     return MPOHamiltonian(out)

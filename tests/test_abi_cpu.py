@@ -358,3 +358,50 @@ def test_iterlog_reproduces_the_reference_log_lines():
     conv.iteration(1, 0.5, lambda: called.append(1))            # level 3 line: silent at verbosity 2
     conv.finish(2, 1e-13, lambda: -20.40021786703)
     assert not called and buf.getvalue().splitlines()[-1].startswith("[ Info: DMRG conv 2:\tobj = -2.040021786703e+01\terr = 1.0000000000e-13\ttime = ")
+
+
+def test_make_time_mpo_taylor_cluster_orders_without_gpu():
+    """make_time_mpo(H, dt, TaylorCluster{N}()) (timeevmpo.jl:12-108) is host-side model building: the MPO reproduces
+    exp(-i dt H) on an L = 6 U(1) Heisenberg chain with an error that falls by 2^(N+1) when dt halves (N = 1, 2, 3: measured
+    3.99, 7.98, 15.98) -- a wrong weight anywhere in the embedding / loop-back / merging / compression steps breaks the order --
+    and every entry conserves charge (WI = TaylorCluster{1})."""
+    import numpy as np
+    import scipy.linalg as sla
+    import mpskit_b200 as m
+    from mpskit_b200.operators import make_time_mpo
+    from oracle import mpo as ompo
+
+    def dense_mpo(W, L):
+        cur = None
+        for i in range(L):
+            sl = W[i]; od, d = sl.odim, sl.d
+            T = np.zeros((od, d, d, od), dtype=complex)
+            for a in range(od):
+                for b in range(od):
+                    e = sl.Os[a][b]
+                    if not np.isscalar(e):
+                        T[a, :, :, b] = np.asarray(e)
+                    elif e != 0:
+                        T[a, :, :, b] = e * np.eye(d)
+            if cur is None:
+                cur = T[0]
+            else:
+                cur = np.einsum('abw,wcdv->acbdv', cur, T)
+                s = cur.shape
+                cur = cur.reshape(s[0] * s[1], s[2] * s[3], s[4])
+        return cur[:, :, 0]
+    L = 6
+    Hd, Hm = m.heisenberg_u1(L), ompo.dense_hamiltonian(ompo.heisenberg_u1(L))
+    for N in (1, 2, 3):
+        errs = []
+        for dt in (0.1, 0.05, 0.025):
+            W = make_time_mpo(Hd, dt, ("TaylorCluster", N))
+            for sl in W.slices:
+                ompo.SparseMPOSlice(sl.Os, sl.domcharges, sl.imcharges, sl.pcharges)      # asserts charge conservation
+            errs.append(np.abs(dense_mpo(W, L) - sla.expm(-1j * dt * Hm)).max())
+        for r in (errs[0] / errs[1], errs[1] / errs[2]):
+            assert 0.95 * 2 ** (N + 1) < r < 1.05 * 2 ** (N + 1)
+    W1 = make_time_mpo(m.transverse_field_ising(L, 1.3), 0.05, "WI")
+    assert W1[0].odim == 2
+    Ht = ompo.dense_hamiltonian(ompo.transverse_field_ising(L, 1.3))
+    assert np.abs(dense_mpo(make_time_mpo(m.transverse_field_ising(L, 1.3), 0.025, ("TaylorCluster", 3)), L) - sla.expm(-0.025j * Ht)).max() < 2e-7
