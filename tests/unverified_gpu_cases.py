@@ -1,0 +1,129 @@
+"""GPU cases written after the round's GPU budget was spent: device compositions of verified primitives that have never been
+executed on a GPU.  This file is NOT collected by default (its name does not match test_*.py); tests/test_gpu_round2.py runs every
+case in its own subprocess with a timeout (test_unverified_device_compositions), so that neither a failure nor a crash or a hang
+of an unexecuted composition can take the verified suite down with it.  Run directly:
+    python -m pytest tests/unverified_gpu_cases.py -m gpu -q"""
+import numpy as np
+import pytest
+import mpskit_b200 as m
+from oracle.spaces import Space as OSpace
+from oracle import mpo as ompo, finite as of
+from helpers import *
+
+pytestmark = pytest.mark.gpu
+
+
+def test_haldane_gap_device(ctx):
+    """The reference's own quasiparticle assertion on the device (test/algorithms.jl:204-211: energies[1] ~ 0.41047925,
+    atol 1e-4, D = 48): spin-1 Heisenberg chain with U(1) blocks, device VUMPS + device infinite quasiparticle ansatz at
+    momentum pi, against the reference constant (1e-4) and the oracle's recorded run in the same bond space
+    (tests/golden/haldane_gap_oracle.json, 1e-6).  Every primitive on this path is verified by the tests above (U(1) VUMPS,
+    U(1) finite quasiparticles, the infinite ansatz on the TFI chain); this combination itself has not been executed on a GPU,
+    hence the non-strict xfail marker."""
+    import json
+    import os
+    rec = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "haldane_gap_oracle.json")))
+    d48 = [r for r in rec["runs"] if r["D"] == 48][0]
+    Ho = ompo.heisenberg_u1(1, d=3)
+    Hd = dev_hamiltonian(Ho)
+    V = m.Space.from_dict({int(k): v for k, v in d48["bond_space"].items()})
+    st = m.InfiniteMPS.random(np.random.default_rng(3), m.Space((-2, 0, 2), (1, 1, 1)), [V], ctx)
+    log = []
+    st, envs, eps = m.find_groundstate_vumps(st, Hd, m.VUMPS(tol=1e-10, maxiter=400), log=log)
+    en, _, _ = m.excitations_qp_infinite(Hd, m.QuasiparticleAnsatz(tol=1e-8, maxiter=20), np.pi, st, envs)     # <= 600 applications
+    print("Haldane gap on the device", en[0], d48["gap"], log[-1]["energy"], d48["energy_per_site"], eps)
+    assert abs(log[-1]["energy"] - d48["energy_per_site"]) <= 1e-9
+    assert abs(en[0] - 0.41047925) <= 1e-4 and abs(en[0] - d48["gap"]) <= 1e-6
+
+
+def test_time_mpo_wii_approximate_vs_tdvp(ctx):
+    """test/algorithms.jl:447-466 with the reference's own time-evolution MPO: W = make_time_mpo(H, dt, WII())
+    (timeevmpo.jl:149-207; host-side construction, validated against exp(-i dt H) in tests/test_abi_cpu.py) applied to a U(1)
+    two-site InfiniteMPS and approximated with VOMPS and IDMRG2 on the device, against a device TDVP step (the reference asserts
+    |dot| = 1 within dt; here 1e-9, the oracle gives 3e-14).  The device algorithms are verified with a W^I MPO by the tests
+    above; this charged four-level W^II MPO has not been executed on a GPU, hence the non-strict xfail marker."""
+    from mpskit_b200.operators import make_time_mpo
+    dt = 1e-3
+    Hd = m.heisenberg_u1(2)
+    W = make_time_mpo(Hd, dt)
+    Vs = [m.Space((-2, 0, 2), (2, 3, 2)), m.Space((-1, 1), (3, 3))]
+    st = m.InfiniteMPS.random(np.random.default_rng(5), m.Space((-1, 1), (1, 1)), Vs, ctx)
+    a, _, eps = m.approximate(st, (W, st), m.VOMPS(tol=1e-12, maxiter=100))
+    b, _, eps2 = m.approximate(st, (W, st), m.IDMRG2(tol=1e-12, maxiter=200, trscheme=m.truncdim(7)))
+    t, _ = m.timestep_infinite(st, Hd, 0.0, dt)
+    ov_a, ov_b, ov_0 = abs(m.dot_infinite(a, t)), abs(m.dot_infinite(b, t)), abs(m.dot_infinite(st, t))
+    print("W^II approximate vs TDVP", eps, eps2, ov_a, ov_b, ov_0)
+    assert eps <= 1e-11 and abs(ov_a - 1.0) <= 1e-9 and abs(ov_b - 1.0) <= 1e-9 and abs(ov_0 - 1.0) > 1e-8
+
+
+def test_fidelity_susceptibility_device(ctx):
+    """fidelity_susceptibility(psi, H, [H_X], envs) (fidelity_susceptibility.jl:4-29; test/algorithms.jl:368-396 asserts the
+    analytic value |1 / (16 l^2 (l^2 - 1))| of the transverse-field Ising chain within 1e-2): infinite D = 16 states at l = 2 and
+    l = 4 against the analytic value (1e-8; the oracle gives 3e-13 / 2e-17) and a finite chain against the oracle (1e-8).  Built
+    from the quasiparticle effective Hamiltonian verified above plus the host-driven GMRES; this combination has not been
+    executed on a GPU, hence the non-strict xfail marker."""
+    from oracle import quasiparticle as oq
+    X = np.array([[0, 1], [1, 0]], dtype=complex)
+    for lam in (2.0, 4.0):
+        Hd = dev_hamiltonian(ompo.transverse_field_ising(1, lam))
+        Vd = dev_hamiltonian(ompo.fsm_hamiltonian(1, 2, {(0, 0): 1.0, (1, 1): 1.0, (0, 1): X}, (0, 0), (0, 0)))
+        st = m.InfiniteMPS.random(np.random.default_rng(3), m.Space((0,), (2,)), [m.Space((0,), (16,))], ctx)
+        st, envs, _ = m.find_groundstate_vumps(st, Hd, m.VUMPS(tol=1e-11, maxiter=300))
+        chi = m.fidelity_susceptibility(st, Hd, [Vd], envs)
+        exact = abs(1 / (16 * lam ** 2 * (lam ** 2 - 1)))
+        print("fidelity susceptibility", lam, chi[0, 0], exact)
+        assert abs(chi[0, 0] - exact) <= 1e-8
+    L, lam = 8, 2.0
+    Ho = ompo.transverse_field_ising(L, lam)
+    Vo = ompo.fsm_hamiltonian(L, 2, {(0, 0): 1.0, (1, 1): 1.0, (0, 1): X}, (0, 0), (0, 0))
+    psi_o = of.FiniteMPS.random(np.random.default_rng(1), OSpace((0,), (2,)), L, OSpace((0,), (16,)))
+    psi_o, envs_o, _ = of.dmrg2_sweeps(psi_o, Ho, nsweeps=8, trunc=("truncdim", 16), tol=1e-13)
+    chi_o = oq.fidelity_susceptibility(psi_o, Ho, [Vo], envs_o)
+    psi_d = m.FiniteMPS.random(np.random.default_rng(1), m.Space((0,), (2,)), L, m.Space((0,), (16,)), ctx)
+    psi_d, envs_d, _ = m.find_groundstate(psi_d, dev_hamiltonian(Ho), m.DMRG2(tol=1e-13, maxiter=8, eigalg=m.Lanczos(tol=1e-13), trscheme=m.truncdim(16)))
+    chi_d = m.fidelity_susceptibility(psi_d, dev_hamiltonian(Ho), [dev_hamiltonian(Vo)], envs_d)
+    print("finite fidelity susceptibility", chi_d[0, 0], chi_o[0, 0])
+    assert abs(chi_d[0, 0] - chi_o[0, 0]) <= 1e-8
+
+
+def test_find_groundstate_keyword_form_and_union(ctx):
+    """find_groundstate(psi, H; tol, trscheme) (find_groundstate.jl:19-41) and alg1 & alg2 (unionalg.jl): the README quickstart
+    form on a finite chain (DMRG2 & DMRG) against exact diagonalisation, and on an InfiniteMPS (IDMRG2 & VUMPS) against the exact
+    TFI energy density.  Pure dispatch over the solvers verified above (the dispatch itself is tested on the CPU)."""
+    import scipy.integrate as si
+    L = 8
+    Ho = ompo.transverse_field_ising(L, 1.5)
+    psi = m.FiniteMPS.random(np.random.default_rng(1), m.Space((0,), (2,)), L, m.Space((0,), (4,)), ctx)
+    Hd = dev_hamiltonian(Ho)
+    psi, envs, eps = m.find_groundstate(psi, Hd, tol=1e-10, trscheme=m.truncdim(16))
+    E = float(np.sum(m.expectation_value(psi, Hd, envs)).real)
+    assert abs(E - np.linalg.eigvalsh(ompo.dense_hamiltonian(Ho))[0]) <= 1e-9
+    g = 0.5
+    H2 = dev_hamiltonian(ompo.transverse_field_ising(2, g))
+    st = m.InfiniteMPS.random(np.random.default_rng(3), m.Space((0,), (2,)), [m.Space((0,), (4,))] * 2, ctx)
+    st, ienvs, eps = m.find_groundstate(st, H2, m.IDMRG2(tol=1e-4, maxiter=50, trscheme=m.truncdim(12)) & m.VUMPS(tol=1e-11, maxiter=100))
+    from mpskit_b200 import infinite as di
+    e = float(np.mean(di.expectation_value(st, H2, ienvs)).real)
+    exact = -si.quad(lambda k: np.sqrt(1 + g * g + 2 * g * np.cos(k)), 0, np.pi)[0] / np.pi
+    print("keyword form / union", E, e, exact, st.V[0].dim)
+    assert st.V[0].dim == 12 and abs(e - exact) <= 1e-9
+
+
+def test_exact_diagonalization_device(ctx):
+    """exact_diagonalization(H; sector, num) (ED.jl:4-53): a full-bond-dimension FiniteMPS whose middle site spans the symmetry
+    sector; the two lowest eigenvalues of the single-site effective Hamiltonian against dense diagonalisation (TFI chain, and
+    the S_z = 0 and S_z = 1 sectors of the U(1) Heisenberg chain)."""
+    L = 8
+    Ho = ompo.transverse_field_ising(L, 1.5)
+    vals, states, infos = m.exact_diagonalization(dev_hamiltonian(Ho), m.Space((0,), (2,)), num=2, ctx=ctx)
+    ev = np.linalg.eigvalsh(ompo.dense_hamiltonian(Ho))
+    assert abs(vals[0].real - ev[0]) <= 1e-10 and abs(vals[1].real - ev[1]) <= 1e-9
+    Hh = ompo.heisenberg_u1(L)
+    Hm = ompo.dense_hamiltonian(Hh)
+    for sector, nup in ((0, L // 2), (2, L // 2 + 1)):
+        keep = [k for k in range(2 ** L) if bin(k).count("1") == nup]
+        evs = np.linalg.eigvalsh(Hm[np.ix_(keep, keep)])
+        vals, states, infos = m.exact_diagonalization(dev_hamiltonian(Hh), m.Space((-1, 1), (1, 1)), sector=sector, num=1, ctx=ctx)
+        print("ED sector", sector, vals[0], evs[0])
+        # the sign convention of the sector label (S_z = +1 or -1) does not matter for the Heisenberg chain
+        assert abs(vals[0].real - evs[0]) <= 1e-10
