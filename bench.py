@@ -24,7 +24,7 @@ import sys
 import tempfile
 import time
 
-if "--impl" in sys.argv and "reference" in sys.argv:
+if "--impl=reference" in sys.argv or ("--impl" in sys.argv and "reference" in sys.argv):
     # torchrun exports OMP_NUM_THREADS=1; the CPU arm must use every host core (OpenBLAS reads these at import time)
     for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
         os.environ[_k] = str(os.cpu_count() or 1)

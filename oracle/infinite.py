@@ -312,19 +312,24 @@ def regauge(AC, C, Vl, Vr, pq, mod=0):
     return np.einsum('apb,cb->apc', Qac, np.conj(Qc))
 
 
-def vumps(st: InfiniteMPS, H, tol=1e-12, maxiter=100, envs=None, log=None):
-    """find_groundstate(psi::InfiniteMPS, H, VUMPS()) (vumps.jl:29-92) with the default dynamic tolerances"""
+def vumps(st: InfiniteMPS, H, tol=1e-12, maxiter=100, envs=None, log=None, project=None):
+    """find_groundstate(psi::InfiniteMPS, H, VUMPS()) (vumps.jl:29-92) with the default dynamic tolerances.
+    project = (pac, pc): optional projectors pac(loc, x), pc(loc, x) onto a symmetric subspace that the effective Hamiltonians
+    leave invariant; applied after every application, i.e. the eigenproblems are solved inside that subspace -- what the
+    reference does when its tensors carry a larger (non-abelian) symmetry than the U(1) blocks of this restatement
+    (tests/golden/make_su2_pins.py)."""
     envs = envs or MPOHamInfEnv(st, H)
     N = st.N
     eps = max(calc_galerkin(st, i, envs) for i in range(N))
+    pac, pc = project if project is not None else ((lambda loc, x: x), (lambda loc, x: x))
     for it in range(1, maxiter + 1):
         etol = dyn_tol(eps, it, 1e-12, 1e-5, 1e-5)
         newAL = []
         for loc in range(N):
             GL, GR = envs.leftenv(loc, st), envs.rightenv(loc, st)
-            _, ac, _ = eigsolve_lanczos(lambda x: dAC_sparse(x, H[loc], GL, GR), st.AC[loc], "SR", etol, 30, 100)
+            _, ac, _ = eigsolve_lanczos(lambda x: pac(loc, dAC_sparse(x, H[loc], GL, GR)), pac(loc, st.AC[loc]), "SR", etol, 30, 100)
             GLc, GRc = envs.leftenv(loc + 1, st), envs.rightenv(loc, st)
-            _, c, _ = eigsolve_lanczos(lambda x: dC_dense(x, GLc, GRc), st.CR[loc], "SR", etol, 30, 100)
+            _, c, _ = eigsolve_lanczos(lambda x: pc(loc, dC_dense(x, GLc, GRc)), pc(loc, st.CR[loc]), "SR", etol, 30, 100)
             newAL.append(regauge(ac, c, st.V[loc], st.V[(loc + 1) % N], st.pq, st.modulus))
         gtol = dyn_tol(eps, it, TOLGAUGE, 1e-5, 1e-8)
         st = InfiniteMPS.from_AL(newAL, st.CR[N - 1], st.V, st.pq, gtol, 100, st.modulus)

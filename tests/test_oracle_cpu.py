@@ -695,3 +695,102 @@ def test_fidelity_susceptibility_oracle_equals_analytic_value():
     Vm = ompo.dense_hamiltonian(V)
     exact = sum(abs(U[:, n].conj() @ Vm @ U[:, 0]) ** 2 / (ev[n] - ev[0]) ** 2 for n in range(1, len(ev)))
     assert abs(chi[0, 0] - exact) < 1e-9
+
+
+def _su2_pins_module():
+    import importlib.util
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_su2_pins.py")
+    spec = importlib.util.spec_from_file_location("make_su2_pins", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_su2_invariant_tensors_and_projectors():
+    """The machinery behind the SU(2) pins (tests/golden/make_su2_pins.py): Clebsch-Gordan coefficients are orthonormal, the
+    constructed tensors are invariant (the projector leaves them unchanged, kills a generic U(1) tensor's non-invariant part and is
+    idempotent), and their uniform gauge shows complete multiplets: the Schmidt values of charge 2m = those of all j >= |m|."""
+    from fractions import Fraction as F
+    from oracle import infinite as oi
+    mod = _su2_pins_module()
+    for j1, j2 in ((F(1, 2), 1), (1, 1), (F(3, 2), F(1, 2)), (2, 1)):
+        for j in (abs(F(j1) - F(j2)) + k for k in range(int(2 * min(F(j1), F(j2))) + 1)):
+            for m in (-j + k for k in range(int(2 * j) + 1)):
+                nrm = sum(mod.clebsch_gordan(j1, -F(j1) + k1, j2, m + F(j1) - k1, j, m) ** 2 for k1 in range(int(2 * F(j1)) + 1))
+                assert abs(nrm - 1.0) < 1e-13
+    h = F(1, 2)
+    cell = {h: 3, 3 * h: 2, 5 * h: 1}
+    rng = np.random.default_rng(0)
+    A, Vl, Vr = mod.symmetric_tensor(rng, cell, 1, cell)
+    P, Pc = mod.tensor_projector(cell, 1, cell), mod.matrix_projector(cell)
+    assert np.linalg.norm(P(A) - A) < 1e-13 * np.linalg.norm(A)
+    from oracle.blocks import mask3
+    pq = Space((-2, 0, 2), (1, 1, 1)).index_charges()
+    G = (rng.standard_normal(A.shape) + 1j * rng.standard_normal(A.shape)) * mask3(Vl, pq, Vr)
+    assert np.linalg.norm(P(P(G)) - P(G)) < 1e-13 * np.linalg.norm(G) and np.linalg.norm(P(G)) < 0.9 * np.linalg.norm(G)
+    assert abs(np.vdot(P(G), G - P(G))) < 1e-12 * np.linalg.norm(G) ** 2          # orthogonal projector
+    st = oi.InfiniteMPS.from_tensors([A], [Vl], pq, mod=0)
+    assert np.linalg.norm(Pc(st.CR[0]) - st.CR[0]) < 1e-9
+    from oracle import toolbox as ot
+    spec = {q: np.sort(v)[::-1] for q, v in ot.entanglement_spectrum(st, 0).items()}
+    assert len(spec[5]) == 1 and len(spec[3]) == 3 and len(spec[1]) == 6
+    for hi, lo in ((5, 3), (3, 1)):
+        assert max(np.min(np.abs(spec[lo] - x)) for x in spec[hi]) < 1e-10
+    for q in (1, 3, 5):
+        assert np.max(np.abs(spec[q] - spec[-q])) < 1e-10
+
+
+def test_reference_printed_su2_numbers_are_reproduced():
+    """Sixth to tenth reference-held pins, to the digits the reference printed for SU(2)-symmetric VUMPS states:
+      docs/src/examples/quantum1d/5.haldane-spt/index.md:385-404,1011-1019 (spin-1 Heisenberg chain)
+        V_plus  = SU2Space(0 => 10, 1 => 5, 2 => 3):       E_plus  = -1.401419331339301,  S_plus = 1.5450323530414438
+        V_minus = SU2Space(1/2 => 10, 3/2 => 5, 5/2 => 3): E_minus = -1.4014839739630869, S_minus + log(2) = 1.5486227235451633
+      docs/src/examples/quantum1d/4.xxz-heisenberg/index.md:579-671 (spin-1/2 chain, two-site cell, Rep[SU2](1/2 => 10, 3/2 => 5,
+        5/2 => 2) / Rep[SU2](0 => 15, 1 => 10, 2 => 5)):  "VUMPS conv 73: obj = -8.862878980874e-01".
+    The oracle's VUMPS restricted to the SU(2)-invariant tensors of the same multiplet spaces, written in U(1) blocks after the
+    reference's makefullrank! reduction (tests/golden/make_su2_pins.py), is RECOMPUTED here for V_plus (a non-injective state,
+    D = 35, 20 s) and V_minus (D = 58, 30 s at tol 1e-8): energies to 1e-12, entropies -- the Schmidt spectra of the gauge / SVD
+    path -- to 1e-9 / 1e-8.  The recorded tol-1e-10 / 1e-12 runs (tests/golden/su2_pins_oracle.json) agree with the printed numbers
+    to 7e-15 (E_plus), 2e-11 (S_plus), 4e-16 (E_minus), 2e-12 (S_minus) and in all 13 printed digits (xxz, 3 min, recorded only).
+    The generic U(1) run in the V_minus sectors leaves the SU(2) manifold and must lie between the symmetric optimum and the exact
+    ground-state energy density -1.401484038971."""
+    import json
+    mod = _su2_pins_module()
+    rec = json.load(open(os.path.join(GOLD, "su2_pins_oracle.json")))
+    ref = mod.REFERENCE
+    for k, etol, stol in (("minus", 2e-15, 1e-11), ("plus", 2e-14, 1e-10)):
+        r = rec["runs"][k]
+        assert abs(r["energy_unit_cell"] - ref[k]["energy"]) < etol and abs(r["entropy"][0] - ref[k]["entropy"]) < stol
+        assert r["multiplet_defect"] < 1e-12 and r["galerkin"] <= 1e-10
+    x = rec["runs"]["xxz"]
+    assert abs(x["energy_unit_cell"] - ref["xxz"]["energy"]) < 5e-14 and x["galerkin"] <= 1e-12
+    assert x["irreps"][0] == {"0": 10, "1": 10, "2": 5}               # makefullrank!: 10 of the 15 requested singlets survive
+    g = rec["runs"]["minus_generic_u1"]
+    assert -1.401484038971 - 1e-11 < g["energy_unit_cell"] < rec["runs"]["minus"]["energy_unit_cell"] - 1e-8
+    h = mod.Fraction(1, 2)
+    assert mod.fullrank_cells([{0: 10, 1: 5, 2: 3}], 1) == [{0: 5, 1: 5, 2: 3}]
+    new = mod.run("haldane-spt V_plus", 1, [{0: 10, 1: 5, 2: 3}], 1e-10, 100)
+    assert new["galerkin"] <= 1e-10 and new["multiplet_defect"] < 1e-11
+    assert abs(new["energy_unit_cell"] - (-1.401419331339301)) < 1e-12
+    assert abs(new["entropy"][0] - 1.5450323530414438) < 1e-9
+    new = mod.run("haldane-spt V_minus", 1, [{h: 10, 3 * h: 5, 5 * h: 3}], 1e-8, 100)
+    assert new["galerkin"] <= 1e-8 and new["multiplet_defect"] < 1e-11
+    assert abs(new["energy_unit_cell"] - (-1.4014839739630869)) < 1e-12
+    assert abs(new["entropy"][0] + np.log(2.0) - 1.5486227235451633) < 1e-8
+
+
+def test_recorded_su2_state_gives_the_reference_printed_readouts():
+    """tests/golden/su2_haldane_spt_minus_state.npz (the converged V_minus state the device read-out case uploads,
+    tests/unverified_gpu_cases.py) through the oracle's gauge, environments, expectation_value and entropy: the numbers the reference
+    printed (5.haldane-spt/index.md:397-404,1018) to 1e-12 / 1e-10, Galerkin error <= 1e-9."""
+    from oracle import infinite as oi, toolbox as ot
+    rec = np.load(os.path.join(GOLD, "su2_haldane_spt_minus_state.npz"))
+    V = Space(tuple(int(c) for c in rec["charges"]), tuple(int(d) for d in rec["dims"]))
+    pq = Space((-2, 0, 2), (1, 1, 1)).index_charges()
+    st = oi.InfiniteMPS.from_tensors([rec["AL0"]], [V], pq, mod=0)
+    H = ompo.heisenberg_u1(1, d=3)
+    envs = oi.MPOHamInfEnv(st, H)
+    e = float(oi.expectation_value(st, H, envs)[0].real)
+    assert abs(e - (-1.4014839739630869)) < 1e-12
+    assert abs(ot.entropy(st, 0) + np.log(2.0) - 1.5486227235451633) < 1e-10
+    assert oi.calc_galerkin(st, 0, envs) <= 1e-9

@@ -127,3 +127,29 @@ def test_exact_diagonalization_device(ctx):
         print("ED sector", sector, vals[0], evs[0])
         # the sign convention of the sector label (S_z = +1 or -1) does not matter for the Heisenberg chain
         assert abs(vals[0].real - evs[0]) <= 1e-10
+
+
+def test_reference_printed_su2_state_readouts_device(ctx):
+    """docs/src/examples/quantum1d/5.haldane-spt/index.md:397-404,1018 prints E_minus = -1.4014839739630869 and
+    S_minus + log(2) = 1.5486227235451633 for the SU(2)-symmetric VUMPS state in V_minus = SU2Space(1/2 => 10, 3/2 => 5, 5/2 => 3).
+    The oracle reproduces both (tests/golden/make_su2_pins.py; 4e-16 / 2e-12) and recorded the converged left-gauged tensor in U(1)
+    blocks (D = 58).  Here that tensor goes through the device's own path: upload, uniform gauge (device QR / Arnoldi), the
+    MPOHamInfEnv GMRES solves, expectation_value, entropy, calc_galerkin -- against the numbers the reference printed.  (A device
+    VUMPS iteration from this state would leave the SU(2) manifold, as the unprojected oracle does, hence read-outs only.)"""
+    import os
+    from mpskit_b200 import infinite as di
+    from mpskit_b200.tensor import DeviceTensor
+    rec = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "su2_haldane_spt_minus_state.npz"))
+    V = m.Space(tuple(int(c) for c in rec["charges"]), tuple(int(d) for d in rec["dims"]))
+    p = m.Space((-2, 0, 2), (1, 1, 1))
+    A = DeviceTensor.from_dense(ctx, rec["AL0"], V, [-2, 0, 2], V, np.complex128)
+    st = m.InfiniteMPS.from_tensors([A], [V], p, ctx)
+    Hd = dev_hamiltonian(ompo.heisenberg_u1(1, d=3))
+    envs = di.MPOHamInfEnv(st, Hd)
+    e = float(di.expectation_value(st, Hd, envs)[0].real)
+    S = m.entropy(st, 0)
+    gal = di.calc_galerkin(st, 0, envs)
+    print("device read-outs of the recorded SU(2) state", repr(e), repr(S + np.log(2.0)), gal)
+    assert abs(e - (-1.4014839739630869)) <= 1e-11
+    assert abs(S + np.log(2.0) - 1.5486227235451633) <= 1e-8
+    assert gal <= 1e-8
