@@ -153,3 +153,68 @@ def test_reference_printed_su2_state_readouts_device(ctx):
     assert abs(e - (-1.4014839739630869)) <= 1e-11
     assert abs(S + np.log(2.0) - 1.5486227235451633) <= 1e-8
     assert gal <= 1e-8
+
+
+def test_reference_printed_su2_numbers_device_vumps(ctx):
+    """The device VUMPS against a number the REFERENCE printed: docs/src/examples/quantum1d/5.haldane-spt/index.md:397-404,1018,
+    E_minus = -1.4014839739630869 and S_minus + log(2) = 1.5486227235451633 for V_minus = SU2Space(1/2 => 10, 3/2 => 5, 5/2 => 3).
+    As in tests/golden/make_su2_pins.py (where the oracle reproduces both to 4e-16 / 2e-12): the SU(2)-invariant start tensor in
+    U(1) blocks, and VUMPS restricted to the invariant subspace -- the loop of mpskit_b200.infinite.find_groundstate_vumps
+    (vumps.jl:29-92) with every application of the device ddAC / ddC operators followed by the orthogonal projector (download,
+    numpy projector, upload), so that the eigensolver is the host-driven Lanczos over device vectors that the lazy-sum tests verify.
+    Gauge fixing (device QR / Arnoldi), the MPOHamInfEnv GMRES solves, regauge, expectation_value and entropy are the product
+    path unchanged.  Energy 1e-11, entropy 1e-8."""
+    import importlib.util
+    import os
+    from fractions import Fraction
+    from mpskit_b200 import infinite as di
+    from mpskit_b200.tensor import DeviceTensor
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_su2_pins", os.path.join(here, "golden", "make_su2_pins.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    h = Fraction(1, 2)
+    cell = {h: 10, 3 * h: 5, 5 * h: 3}
+    A0, Vo, _ = mod.symmetric_tensor(np.random.default_rng(7), cell, 1, cell)
+    pa, pc = mod.tensor_projector(cell, 1, cell), mod.matrix_projector(cell)
+    V = m.Space(tuple(Vo.charges), tuple(Vo.dims))
+    p = m.Space((-2, 0, 2), (1, 1, 1))
+
+    def project(x):
+        dense = x.to_dense()
+        dense = pa(dense) if len(x.mch) == 3 else pc(dense[:, 0, :])[:, None, :]
+        return DeviceTensor.from_dense(ctx, dense, x.Vl, list(x.mch), x.Vr, x.dtype)
+
+    class Projected:
+        def __init__(self, op):
+            self.op = op
+
+        def __call__(self, x):
+            y = self.op(x)
+            z = project(y)
+            y.free()
+            return z
+
+    st = m.InfiniteMPS.from_tensors([DeviceTensor.from_dense(ctx, A0, V, [-2, 0, 2], V, np.complex128)], [V], p, ctx)
+    Hd = dev_hamiltonian(ompo.heisenberg_u1(1, d=3))
+    envs = di.MPOHamInfEnv(st, Hd)
+    eps = di.calc_galerkin(st, 0, envs)
+    for it in range(1, 101):
+        etol = di.dyn_tol(eps, it, 1e-12, 1e-5, 1e-5)
+        eig = m.Lanczos(tol=etol, krylovdim=30, maxiter=100)
+        hac = di._inf_ddAC(0, st, Hd, envs)
+        _, ac = di.fixedpoint(Projected(hac), project(st.AC[0]), "SR", eig); hac.free()
+        hc = di._inf_ddC(0, st, Hd, envs)
+        _, c = di.fixedpoint(Projected(hc), project(st.CR[0]), "SR", eig); hc.free()
+        newAL = [di.regauge(ac, c)]
+        st = m.InfiniteMPS.from_AL(newAL, st.CR[0], st.V, st.pspace, st.ctx, di.dyn_tol(eps, it, di.TOLGAUGE, 1e-5, 1e-8), 100)
+        envs.recalculate(st, di.dyn_tol(eps, it, 1e-12, 1e-5, 1e-5))
+        eps = di.calc_galerkin(st, 0, envs)
+        if eps <= 1e-9:
+            break
+    e = float(di.expectation_value(st, Hd, envs)[0].real)
+    S = m.entropy(st, 0)
+    print("device SU(2)-restricted VUMPS", it, eps, repr(e), repr(S + np.log(2.0)))
+    assert eps <= 1e-9
+    assert abs(e - (-1.4014839739630869)) <= 1e-11
+    assert abs(S + np.log(2.0) - 1.5486227235451633) <= 1e-8
