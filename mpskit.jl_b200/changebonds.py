@@ -275,6 +275,13 @@ def changebonds_infinite(st, H=None, alg=None, envs=None, log=None):
     if alg is None:
         H, alg = None, H
     N = st.N
+    from .operators import DenseMPO
+    if isinstance(alg, OptimalExpand) and isinstance(H, DenseMPO):
+        # changebonds(psi::InfiniteMPS, H::DenseMPO, alg::OptimalExpand, envs) (optimalexpand.jl:40-44): a one-row multiline
+        from .statmech import environments as _statmech_environments
+        envs = envs if envs is not None else _statmech_environments(st, H)
+        rows, envs = changebonds_multiline([st], [[H[c] for c in range(N)]], alg, envs, log)
+        return rows[0], envs
     if isinstance(alg, (OptimalExpand, RandExpand)):
         if isinstance(alg, OptimalExpand):
             envs = envs if envs is not None else di.environments(st, H)
@@ -310,6 +317,47 @@ def changebonds_infinite(st, H=None, alg=None, envs=None, log=None):
     if isinstance(alg, VUMPSSvdCut):
         return _vumps_svdcut(st, H, alg, envs, log)
     raise TypeError(f"changebonds: unsupported algorithm {alg!r}")
+
+
+def changebonds_multiline(rows, H=None, alg=None, envs=None, log=None):
+    """changebonds(psi::MPSMultiline, [H::MPOMultiline,] alg[, envs]).  rows: list of InfiniteMPS (one per row, equal bond
+    spaces); H[r][c]: MPO slices of row r, column c; envs: statmech.MultilineEnv (or PerMPOInfEnv for a single row).
+    OptimalExpand (optimalexpand.jl:46-66): the two-site tensor of row i - 1 through ddAC2(i - 1, j) lives in the bond spaces
+    of row i, whose null spaces (leftnull(AL[i, j]), rightnull(AR[i, j + 1])) select the expansion of row i; RandExpand
+    (randexpand.jl:36-38) and SvdCut (svdcut.jl:32-34) are row-wise maps.  The rows keep equal bond spaces when the truncation
+    scheme keeps the same sector dimensions in every row (truncdim on a trivial symmetry always does).
+    Returns (rows, envs) when an operator is given, else the rows."""
+    if alg is None:
+        H, alg = None, H
+    R, N = len(rows), rows[0].N
+    if isinstance(alg, OptimalExpand):
+        from .derivatives import MPO_ddAC2
+        from .statmech import MultilineEnv, PerMPOInfEnv
+        envs = envs if envs is not None else MultilineEnv(rows, H)
+        if isinstance(envs, PerMPOInfEnv):                                  # one row: lw[c] / rw[c]
+            envs.leftenv(0, rows[0])                                        # recalculates when the state changed
+            lw, rw = [envs.lw], [envs.rw]
+        else:
+            if envs.dependency is not rows:
+                envs.recalculate(rows)
+            lw, rw = envs.lw, envs.rw
+        out = []
+        for i in range(R):
+            r = (i - 1) % R
+            top = rows[r]
+            ALp, ARp = [None] * N, [None] * N
+            for j in range(N):
+                ac2 = contract_ac2(top, top.AC[j], top.AR[(j + 1) % N])
+                h = MPO_ddAC2(top.ctx, H[r][j], H[r][(j + 1) % N], lw[r][j], rw[r][(j + 1) % N], ac2)
+                AC2 = h(ac2); h.free(); ac2.free()
+                ALp[j], ARp[(j + 1) % N] = _expansion_vectors(rows[i], j, AC2, alg.trscheme, log)
+                AC2.free()
+            out.append(_expand(rows[i], ALp, ARp))
+        return out, envs
+    if isinstance(alg, (RandExpand, SvdCut)):
+        out = [changebonds_infinite(st, alg, log=log) for st in rows]
+        return (out, envs) if H is not None else out
+    raise TypeError(f"changebonds on MPSMultiline: unsupported algorithm {alg!r}")
 
 
 def _isometry(ctx, Vrow, Vcol, dtype):

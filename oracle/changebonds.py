@@ -182,3 +182,37 @@ def vumps_svdcut(st: InfiniteMPS, H, trunc=("notrunc",), tol_gauge=TOLGAUGE, tol
         V[(loc + 1) % N] = newV
         st = InfiniteMPS.from_tensors(copied, V, pq, tol=tol_gauge, mod=mod)
     return st, MPOHamInfEnv(st, H)
+
+
+# ------------------------------------------------------------------------------------------ MPSMultiline
+def optimal_expand_multiline(rows, slices, trunc=("truncdim", 1), envs=None, log=None):
+    """changebonds(psi::MPSMultiline, H::MPOMultiline, alg::OptimalExpand, envs) (optimalexpand.jl:46-66): the two-site tensor of
+    row i - 1, pushed through ddAC2(i - 1, j), lives in the bond spaces of row i; the null spaces of AL[i, j] and AR[i, j + 1]
+    pick the expansion of row i.  rows: list of InfiniteMPS, slices[r][c]: MPO tensors, envs: statmech.MultilineEnv.  The
+    single-row case is changebonds(psi::InfiniteMPS, H::DenseMPO, alg::OptimalExpand) (optimalexpand.jl:40-44)."""
+    from .statmech import MultilineEnv
+    envs = envs or MultilineEnv(rows, slices)
+    R, N = len(rows), rows[0].N
+    d = len(rows[0].pq)
+    out = []
+    for i in range(R):
+        top, r = rows[(i - 1) % R], (i - 1) % R
+        ALp, ARp, newV = [None] * N, [None] * N, [None] * N
+        for j in range(N):
+            ac2 = np.einsum('apk,kqr->aprq', top.AC[j], top.AR[(j + 1) % N])
+            AC2 = dAC2_sparse(ac2, slices[r][j], slices[r][(j + 1) % N], envs.lw[r][j], envs.rw[r][(j + 1) % N])
+            Mat = AC2.transpose(0, 1, 3, 2).reshape(ac2.shape[0] * d, d * ac2.shape[2])
+            ALp[j], ARp[(j + 1) % N], newV[j] = _expansion_vectors(rows[i], j, Mat, trunc, log)
+        out.append(expand(rows[i], ALp, ARp, newV))
+    return out, envs
+
+
+def rand_expand_multiline(rows, trunc=("truncdim", 1), rng=None, log=None):
+    """changebonds(psi::MPSMultiline, alg::RandExpand) (randexpand.jl:36-38): row-wise"""
+    rng = rng or np.random.default_rng(0)
+    return [rand_expand(st, trunc, rng, log) for st in rows]
+
+
+def svdcut_multiline(rows, trunc=("notrunc",), log=None):
+    """changebonds(psi::MPSMultiline, alg::SvdCut) (svdcut.jl:32-34): row-wise"""
+    return [svdcut(st, trunc, log) for st in rows]

@@ -7,8 +7,9 @@ numbers the REFERENCE ITSELF printed in its documentation for SU(2)-symmetric st
 * docs/src/examples/quantum1d/4.xxz-heisenberg/index.md:579-671 -- spin-1/2 Heisenberg chain, two-site unit cell,
   V1 = Rep[SU2](1/2 => 10, 3/2 => 5, 5/2 => 2), V2 = Rep[SU2](0 => 15, 1 => 10, 2 => 5):
   "VUMPS conv 73: obj = -8.862878980874e-01" (sum over the unit cell).
-* docs/src/examples/quantum1d/2.haldane/index.md:209-225 -- spin-1 chain, Rep[SU2](1/2 => 16, 3/2 => 16, 5/2 => 8, 7/2 => 4):
-  the conjugate-gradient refinement converges to f = -1.401484038967.
+(Not used: 2.haldane/index.md:209-300, Rep[SU2](1/2 => 16, 3/2 => 16, 5/2 => 8, 7/2 => 4) -- there VUMPS stops at err 1e-5 and a
+conjugate-gradient refinement, which the oracle does not restate, reaches f = -1.401484038967; the projected oracle VUMPS from a
+random symmetric start settles, after 22 iterations / 25 min at D = 176, near a different stationary point, -1.4014840254.)
 
 The oracle has U(1) blocks only.  An SU(2)-symmetric MPS in the U(1) basis: every multiplet (j, alpha) contributes its 2j+1 members
 m = -j..j to the U(1) sectors of charge 2m, and the tensor is  A[(j1 m1 a), ms, (j2 m2 b)] = R_{j1 j2}[a, b] <j1 m1; s ms | j2 m2>
@@ -21,7 +22,7 @@ manifold within five iterations: it converges to a LOWER, symmetry-broken energy
 minus_generic_u1), as it may by the variational principle -- the U(1) manifold of the same sectors is larger.
 The requested multiplet spaces first go through the reference's makefullrank! (fullrank_cells below): V_plus keeps 5 of its 10
 singlets, the xxz cell 10 of 15.  V_plus is a non-injective state (the "wrong" SPT phase); the projected iteration handles it too.
-    python tests/golden/make_su2_pins.py [minus plus xxz minus_generic_u1 haldane176]     (45 s, 20 s, 3 min, 1 min, ~40 min on 8 cores)"""
+    python tests/golden/make_su2_pins.py [minus plus xxz minus_generic_u1]     (45 s, 20 s, 3 min, 1 min on 8 cores)"""
 import json
 import os
 import sys
@@ -252,7 +253,6 @@ CASES = {
                                     seed=3, symmetric=False),
     "plus": lambda: run("haldane-spt V_plus", 1, [{0: 10, 1: 5, 2: 3}], 1e-10, 100),
     "xxz": lambda: run("xxz-heisenberg SU(2) two-site cell", H, [{0: 15, 1: 10, 2: 5}, {H: 10, 3 * H: 5, 5 * H: 2}], 1e-12, 400),
-    "haldane176": lambda: run("haldane D=176", 1, [{H: 16, 3 * H: 16, 5 * H: 8, 7 * H: 4}], 1e-10, 200),
 }
 REFERENCE = {
     "minus": dict(source="docs/src/examples/quantum1d/5.haldane-spt/index.md:397-404,1018", energy=-1.4014839739630869,
@@ -260,7 +260,6 @@ REFERENCE = {
     "plus": dict(source="docs/src/examples/quantum1d/5.haldane-spt/index.md:385-393,1019", energy=-1.401419331339301,
                  entropy=1.5450323530414438),
     "xxz": dict(source="docs/src/examples/quantum1d/4.xxz-heisenberg/index.md:671", energy=-8.862878980874e-01),
-    "haldane176": dict(source="docs/src/examples/quantum1d/2.haldane/index.md:225-300", energy=-1.401484038967),
 }
 
 if __name__ == "__main__":

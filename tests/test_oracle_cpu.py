@@ -794,3 +794,41 @@ def test_recorded_su2_state_gives_the_reference_printed_readouts():
     assert abs(e - (-1.4014839739630869)) < 1e-12
     assert abs(ot.entropy(st, 0) + np.log(2.0) - 1.5486227235451633) < 1e-10
     assert oi.calc_galerkin(st, 0, envs) <= 1e-9
+
+
+def test_multiline_changebonds_oracle():
+    """changebonds on MPSMultiline (test/algorithms.jl:318-338: a random dense MPO on a 1 x 1 multiline; `dot(state, state') ~ 1
+    atol 1e-8` after RandExpand and OptimalExpand, the bond shrinks after SvdCut) and on two classical-Ising rows
+    (optimalexpand.jl:46-66: row i is expanded with the two-site tensor of row i - 1): the expanded rows carry the old state
+    (|dot| = 1 to 1e-10), stay in the uniform gauge (AL isometric, AL CR = AC), gain the requested dimension, the expansion
+    vectors are orthogonal to the old AL / AR, and SvdCut returns to the old dimension; one boundary iteration after the
+    expansion does not lose the converged value."""
+    from oracle import infinite as oi, statmech as osm, changebonds as ocb
+    rng = np.random.default_rng(11)
+    p, D = Space((0,), (2,)), Space((0,), (3,))
+    o = rng.standard_normal((2, 2, 2, 2)) + 1j * rng.standard_normal((2, 2, 2, 2))          # [w, p_out, p_in, w]
+    sl = [[ompo.dense_mpo_slice(o)]]
+    rows = [oi.InfiniteMPS.random(rng, p, [D])]
+    for new in (ocb.rand_expand_multiline(rows, ("truncdim", 9), rng), ocb.optimal_expand_multiline(rows, sl, ("truncdim", 9))[0]):
+        assert new[0].V[0].dim == 6                                        # 3 old + 3 = d D - D null vectors
+        assert abs(abs(ocb.dot(rows[0], new[0])) - 1.0) < 1e-8             # the reference's assertion
+        cut = ocb.svdcut_multiline(new, ("truncdim", 3))
+        assert cut[0].V[0].dim == 3 < new[0].V[0].dim and abs(abs(ocb.dot(rows[0], cut[0])) - 1.0) < 1e-8
+    b1, b2 = 0.35, 0.30
+    so = [[ompo.dense_mpo_slice(ompo.classical_ising(b1))], [ompo.dense_mpo_slice(ompo.classical_ising(b2))]]
+    rows = [oi.InfiniteMPS.random(np.random.default_rng(3 + r), p, [Space((0,), (4,))]) for r in range(2)]
+    log = []
+    rows, envs, _ = osm.leading_boundary_multiline(rows, so, tol=1e-11, maxiter=80, log=log)
+    v0 = np.prod(log[-1]["value"])
+    new, _ = ocb.optimal_expand_multiline(rows, so, ("truncdim", 2), envs)
+    for r in range(2):
+        st, old = new[r], rows[r]
+        assert st.V[0].dim == 6 and abs(abs(ocb.dot(old, st)) - 1.0) < 1e-10
+        al = st.AL[0].reshape(-1, st.AL[0].shape[2])
+        assert np.linalg.norm(al.conj().T @ al - np.eye(al.shape[1])) < 1e-12
+        assert np.linalg.norm(np.einsum('apb,bc->apc', st.AL[0], st.CR[0]) - st.AC[0] * np.linalg.norm(np.einsum('apb,bc->apc', st.AL[0], st.CR[0]))) < 1e-12
+        assert np.linalg.norm(np.einsum('apb,apc->bc', old.AL[0].conj(), st.AL[0][:4, :, 4:])) < 1e-12     # AL' orthogonal to AL
+    log2 = []
+    osm.leading_boundary_multiline(new, so, tol=1e-11, maxiter=60, log=log2)
+    assert abs(np.prod(log2[0]["value"]) - v0) < 1e-6 * abs(v0)            # the expanded state is (nearly) the old fixed point
+    assert abs(np.prod(log2[-1]["value"]) - v0) < 1e-4 * abs(v0)           # and the larger manifold converges next to it

@@ -218,3 +218,48 @@ def test_reference_printed_su2_numbers_device_vumps(ctx):
     assert eps <= 1e-9
     assert abs(e - (-1.4014839739630869)) <= 1e-11
     assert abs(S + np.log(2.0) - 1.5486227235451633) <= 1e-8
+
+
+def test_changebonds_multiline_device(ctx):
+    """changebonds on MPSMultiline on the device (test/algorithms.jl:318-338; optimalexpand.jl:40-66, randexpand.jl:36-38,
+    svdcut.jl:32-34) against the oracle restatement (oracle/changebonds.py *_multiline): a random dense MPO on a one-row multiline
+    through the InfiniteMPS / DenseMPO form, and two classical-Ising rows where row i is expanded with the two-site tensor of row
+    i - 1: added dimensions bit-exact, singular values of the projected two-site tensors 1e-9, overlaps with the old rows 1 (the
+    reference asserts 1e-8; here 1e-10), SvdCut back to the old dimension.  Composition of verified device primitives
+    (MultilineEnv, MPO_ddAC2 on dense slices, the expansion step of the single-row changebonds test)."""
+    import importlib
+    from oracle import infinite as oi, statmech as osm, changebonds as ocb
+    dcb = importlib.import_module(m.__name__ + ".changebonds")
+    rng = np.random.default_rng(11)
+    o = rng.standard_normal((2, 2, 2, 2)) + 1j * rng.standard_normal((2, 2, 2, 2))
+    p_o, D_o = OSpace((0,), (2,)), OSpace((0,), (3,))
+    st_o = oi.InfiniteMPS.random(np.random.default_rng(2), p_o, [D_o])
+    st_d = m.InfiniteMPS.random(np.random.default_rng(2), m.Space((0,), (2,)), [m.Space((0,), (3,))], ctx)
+    log_o, log_d = [], []
+    oe_o, _ = ocb.optimal_expand_multiline([st_o], [[ompo.dense_mpo_slice(o)]], ("truncdim", 9), None, log_o)
+    oe_d, _ = m.changebonds(st_d, m.DenseMPO([o]), m.OptimalExpand(trscheme=m.truncdim(9)), log=log_d)
+    assert oe_d.V[0].as_dict() == oe_o[0].V[0].as_dict() == {0: 6}
+    for q, s in log_o[0]["spectrum"].items():
+        assert np.abs(np.asarray(log_d[0]["spectrum"][q]) - s).max() <= 1e-9 * max(1.0, np.abs(s).max())
+    assert abs(abs(dcb.dot_infinite(st_d, oe_d)) - 1.0) <= 1e-8                 # test/algorithms.jl:333
+    cut = m.changebonds(oe_d, m.SvdCut(trscheme=m.truncdim(3)))
+    assert cut.V[0].dim == 3 < oe_d.V[0].dim                                     # test/algorithms.jl:337-338
+    # two rows
+    b1, b2 = 0.35, 0.30
+    so = [[ompo.dense_mpo_slice(ompo.classical_ising(b1))], [ompo.dense_mpo_slice(ompo.classical_ising(b2))]]
+    sd = [[m.dense_mpo_slice(m.classical_ising(b1))], [m.dense_mpo_slice(m.classical_ising(b2))]]
+    rows_o = [oi.InfiniteMPS.random(np.random.default_rng(3 + r), p_o, [OSpace((0,), (4,))]) for r in range(2)]
+    rows_d = [m.InfiniteMPS.random(np.random.default_rng(3 + r), m.Space((0,), (2,)), [m.Space((0,), (4,))], ctx) for r in range(2)]
+    rows_o, envs_o, _ = osm.leading_boundary_multiline(rows_o, so, tol=1e-11, maxiter=80)
+    rows_d, envs_d, _ = m.leading_boundary_multiline(rows_d, sd, m.VUMPS(tol=1e-11, maxiter=80))
+    log_o, log_d = [], []
+    new_o, _ = ocb.optimal_expand_multiline(rows_o, so, ("truncdim", 2), envs_o, log_o)
+    new_d, _ = m.changebonds_multiline(rows_d, sd, m.OptimalExpand(trscheme=m.truncdim(2)), envs_d, log=log_d)
+    for r in range(2):
+        assert new_d[r].V[0].as_dict() == new_o[r].V[0].as_dict() == {0: 6}
+        for q, s in log_o[r]["spectrum"].items():
+            assert np.abs(np.asarray(log_d[r]["spectrum"][q]) - s).max() <= 1e-8 * np.abs(s).max()
+        assert abs(abs(dcb.dot_infinite(rows_d[r], new_d[r])) - 1.0) <= 1e-10
+    back = m.changebonds_multiline(new_d, m.SvdCut(trscheme=m.truncdim(4)))
+    assert all(b.V[0].dim == 4 for b in back)
+    assert all(abs(abs(dcb.dot_infinite(rows_d[r], back[r])) - 1.0) <= 1e-10 for r in range(2))
