@@ -35,7 +35,7 @@ from .approximate import approximate, approximate_inplace, ac_proj, ac2_proj  # 
 from .streaming import MatvecStream  # noqa: F401
 from .serialize import save_mps, load_mps, pack_tensor, unpack_tensor  # noqa: F401
 from .changebonds import (SvdCut, svdcut_inplace, OptimalExpand, RandExpand, VUMPSSvdCut, changebonds, changebonds_inplace,  # noqa: F401
-                          changebonds_infinite, changebonds_multiline, dot_infinite, leftnull, rightnull, contract_adjoint_left, cat)
+                          changebonds_infinite, changebonds_multiline, mpo_times_infinite, densempo_as_state, svdcut_densempo, dot_infinite, leftnull, rightnull, contract_adjoint_left, cat)
 from .excitations import (ProjectionOperator, AC_EffProj, AC2_EffProj, LinearCombination, LazyLincoCache, FiniteExcited,  # noqa: F401
                           excitations, unit_mpo)
 from .excitations import expectation_value  # noqa: F401,F811  (general form: MPOHamiltonian / LinearCombination / ProjectionOperator)

@@ -126,6 +126,9 @@ def changebonds(psi, H=None, alg=None, envs=None, log=None):
     changebonds(psi, alg::SvdCut) = changebonds!(copy(psi), alg) (svdcut.jl:13)"""
     if alg is None:                                   # changebonds(psi, alg)
         H, alg = None, H
+    from .operators import DenseMPO
+    if isinstance(psi, DenseMPO) and isinstance(alg, SvdCut):      # svdcut.jl:26-28
+        return svdcut_densempo(psi, alg, log=log)
     from .algorithms import UnionAlg
     if isinstance(alg, UnionAlg):                     # unionalg.jl:13-23
         if H is None:
@@ -472,3 +475,99 @@ def _union(a, b):
 
 for _cls in (SvdCut, OptimalExpand, RandExpand, VUMPSSvdCut):          # alg1 & alg2 (unionalg.jl:11)
     _cls.__and__ = _union
+
+
+# ------------------------------------------------------------------------------------------ DenseMPO products (state construction)
+def _slice_dense(sl):
+    """O[w, p_out, p_in, v] of a SparseMPOSlice (scalar entries are multiples of the identity, sparseslice.jl:40-55)"""
+    out = np.zeros((sl.odim, sl.d, sl.d, sl.odim), dtype=np.complex128)
+    for (i, j) in sl.keys():
+        e = sl.Os[i][j]
+        out[i, :, :, j] = e * np.eye(sl.d) if np.isscalar(e) else np.asarray(e)
+    return out
+
+
+def _fused(qa, qw, modulus):
+    from .spaces import Space
+    q = (np.asarray(qa)[:, None] + np.asarray(qw)[None, :]).reshape(-1)
+    if modulus:
+        q = q % modulus
+    perm = np.argsort(q, kind="stable")
+    cs, ns = np.unique(q, return_counts=True)
+    return Space([int(c) for c in cs], [int(n) for n in ns], modulus), perm
+
+
+def mpo_times_infinite(W, st):
+    """Base.:*(mpo::DenseMPO, st::InfiniteMPS) (src/operators/densempo.jl:31-45): A'[(a w), p, (b v)] = sum_q AL[a, q, b]
+    O[w, p, q, v], the fusers sorting the pair index into the sectors of charge q_a + c_w, then the InfiniteMPS constructor (device
+    uniform gauge).  State construction, not the hot path: the product tensors (chi^2 D^2 d numbers) are formed once on the host
+    from the downloaded AL and uploaded; the constructor's makefullrank! (abstractmps.jl:94-108) is not mirrored -- the fused bond
+    sectors must be fillable by the neighbouring tensors (always the case without charges)."""
+    from .infinite import InfiniteMPS
+    N = st.N
+    if len(W) % N and N % len(W):
+        raise ValueError("dimension mismatch")                      # densempo.jl:32
+    tensors, Vf = _product_tensors(W, [a.to_dense() for a in st.AL], st.V, st.pspace.modulus)
+    A = [DeviceTensor.from_dense(st.ctx, tensors[i], Vf[i], list(st.pq), Vf[(i + 1) % N], st.dtype) for i in range(N)]
+    return InfiniteMPS.from_tensors(A, Vf, st.pspace, st.ctx)
+
+
+def _product_tensors(W, AL, V, modulus=0):
+    """host part of mpo_times_infinite: dense (D chi, d, D chi) product tensors in the sector order of the fused bond spaces"""
+    N = len(AL)
+    fus = [_fused(V[i].index_charges(), W[i].domcharges, modulus) for i in range(N)]
+    out = []
+    for i in range(N):
+        t = np.einsum('aqb,wpqv->awpbv', AL[i], _slice_dense(W[i]))
+        Dl, chi, d, Dr, chir = t.shape
+        t = t.reshape(Dl * chi, d, Dr * chir)[fus[i][1]][:, :, fus[(i + 1) % N][1]]
+        out.append(np.ascontiguousarray(t))
+    return out, [f[0] for f in fus]
+
+
+def densempo_as_state(W, ctx=None):
+    """convert(InfiniteMPS, mpo::DenseMPO) (densempo.jl:18-22): the two physical legs fused into one of charge p_out - p_in;
+    returns the state and the permutation that sorted the fused physical index"""
+    from .infinite import InfiniteMPS
+    from .spaces import Space
+    from ._lib import default_context
+    ctx = ctx or default_context()
+    N = len(W)
+    pch = np.asarray(W[0].pcharges)
+    d, mod = len(pch), W[0].modulus
+    pq = (pch[:, None] - pch[None, :]).reshape(-1)
+    if mod:
+        pq = pq % mod
+    order = np.argsort(pq, kind="stable")
+    cs, ns = np.unique(pq, return_counts=True)
+    pspace = Space([int(c) for c in cs], [int(n) for n in ns], mod)
+    A, V = [], []
+    for i in range(N):
+        cl, cr = np.asarray(W[i].domcharges), np.asarray(W[i].imcharges)
+        pl, pr = np.argsort(cl, kind="stable"), np.argsort(cr, kind="stable")
+        t = _slice_dense(W[i]).reshape(len(cl), d * d, len(cr))[:, order, :][pl][:, :, pr]
+        ul, nl = np.unique(cl, return_counts=True)
+        ur, nr = np.unique(cr, return_counts=True)
+        Vl, Vr = Space([int(c) for c in ul], [int(n) for n in nl], mod), Space([int(c) for c in ur], [int(n) for n in nr], mod)
+        A.append(DeviceTensor.from_dense(ctx, np.ascontiguousarray(t), Vl, [int(c) for c in pq[order]], Vr, np.complex128))
+        V.append(Vl)
+    return InfiniteMPS.from_tensors(A, V, pspace, ctx), order
+
+
+def svdcut_densempo(W, alg: SvdCut, ctx=None, log=None):
+    """changebonds(mpo::DenseMPO, alg::SvdCut) (svdcut.jl:26-28): through the InfiniteMPS form, the device SvdCut, and back
+    (densempo.jl:24-28: the AL tensors with the physical leg split again; every bond index becomes a level of width 1)."""
+    from .operators import DenseMPO, SparseMPOSlice as _Slice
+    st, order = densempo_as_state(W, ctx)
+    cut = changebonds_infinite(st, alg, log=log)
+    d = W[0].d
+    inv = np.argsort(order)
+    slices = []
+    for i in range(cut.N):
+        a = cut.AL[i].to_dense()[:, inv, :]
+        O = a.reshape(a.shape[0], d, d, a.shape[2])
+        Os = [[(O[w, :, :, v] if np.abs(O[w, :, :, v]).max() > 0 else 0) for v in range(O.shape[3])] for w in range(O.shape[0])]
+        if O.shape[0] != O.shape[3]:
+            raise ValueError("SvdCut of a DenseMPO left different bond dimensions in the unit cell: not a square slice")
+        slices.append(_Slice(Os, tuple(cut.V[i].index_charges()), tuple(cut.V[(i + 1) % cut.N].index_charges()), W[0].pcharges, W[0].modulus))
+    return DenseMPO(slices)

@@ -291,6 +291,11 @@ class DenseMPO:
     def __getitem__(self, i):
         return self.slices[i % len(self.slices)]
 
+    def __mul__(self, st):
+        """mpo * st::InfiniteMPS (densempo.jl:31-45)"""
+        from .changebonds import mpo_times_infinite
+        return mpo_times_infinite(self, st)
+
 
 def periodic_boundary_conditions(H: MPOHamiltonian, L=None):
     """periodic_boundary_conditions(H, L) (src/algorithms/toolbox.jl:186-306) for width-1 levels: relabelled FSM over

@@ -216,3 +216,59 @@ def rand_expand_multiline(rows, trunc=("truncdim", 1), rng=None, log=None):
 def svdcut_multiline(rows, trunc=("notrunc",), log=None):
     """changebonds(psi::MPSMultiline, alg::SvdCut) (svdcut.jl:32-34): row-wise"""
     return [svdcut(st, trunc, log) for st in rows]
+
+
+# ------------------------------------------------------------------------------------------ DenseMPO products
+def _fused(qa, qw, mod):
+    """fuser of a bond index a (charges qa) with an MPO level w (charges qw): the pair index (a, w) sorted into the sectors of
+    the fused space (charge qa + qw); returns (Space, permutation of the a-major pair index)"""
+    q = (np.asarray(qa)[:, None] + np.asarray(qw)[None, :]).reshape(-1)
+    if mod:
+        q = q % mod
+    perm = np.argsort(q, kind="stable")
+    cs, ns = np.unique(q, return_counts=True)
+    return Space(tuple(int(c) for c in cs), tuple(int(n) for n in ns), mod), perm
+
+
+def mpo_times_state(slices, st: InfiniteMPS, tol=TOLGAUGE):
+    """Base.:*(mpo::DenseMPO, st::InfiniteMPS) (src/operators/densempo.jl:31-45): A'[(a w), p, (b v)] = sum_q AL[a, q, b]
+    O[w, p, q, v] with the fusers sorting (a, w) into the sectors of charge q_a + c_w, then the InfiniteMPS constructor"""
+    N, mod = st.N, st.modulus
+    fus = [_fused(st.V[i].index_charges(), slices[i].cl, mod) for i in range(N)]
+    A = []
+    for i in range(N):
+        t = np.einsum('aqb,wpqv->awpbv', st.AL[i], slices[i].dense())
+        Dl, chi, d, Dr, chir = t.shape
+        t = t.reshape(Dl * chi, d, Dr * chir)
+        A.append(t[fus[i][1]][:, :, fus[(i + 1) % N][1]])
+    return InfiniteMPS.from_tensors(A, [f[0] for f in fus], st.pq, tol=tol, mod=mod)
+
+
+def densempo_as_state(slices):
+    """convert(InfiniteMPS, mpo::DenseMPO) (densempo.jl:19-25): the two physical legs fused into one of charge p_out - p_in"""
+    N = len(slices)
+    pch = np.asarray(slices[0].pch)
+    d = len(pch)
+    pq = (pch[:, None] - pch[None, :]).reshape(-1)
+    order = np.argsort(pq, kind="stable")
+    A, V = [], []
+    for i in range(N):
+        cl, cr = np.asarray(slices[i].cl), np.asarray(slices[i].cr)
+        pl, pr = np.argsort(cl, kind="stable"), np.argsort(cr, kind="stable")
+        t = slices[i].dense().reshape(len(cl), d * d, len(cr))[:, order, :]
+        A.append(t[pl][:, :, pr])
+        cs, ns = np.unique(cl, return_counts=True)
+        V.append(Space(tuple(int(c) for c in cs), tuple(int(n) for n in ns)))
+    return InfiniteMPS.from_tensors(A, V, pq[order], mod=0), order
+
+
+def svdcut_densempo(slices, trunc=("notrunc",)):
+    """changebonds(mpo::DenseMPO, alg::SvdCut) (svdcut.jl:26-28): through the InfiniteMPS form (densempo.jl:18-22), SvdCut, and
+    back (densempo.jl:24-28: the AL tensors with the physical leg split again).  Returns the dense tensors O'[w, p_out, p_in, v]
+    per site and the bond spaces (level charges) of the cut state."""
+    st, order = densempo_as_state(slices)
+    cut = svdcut(st, trunc)
+    d = len(slices[0].pch)
+    inv = np.argsort(order)
+    tensors = [cut.AL[i][:, inv, :].reshape(cut.AL[i].shape[0], d, d, cut.AL[i].shape[2]) for i in range(cut.N)]
+    return tensors, list(cut.V)

