@@ -291,10 +291,14 @@ class DenseMPO:
     def __getitem__(self, i):
         return self.slices[i % len(self.slices)]
 
-    def __mul__(self, st):
-        """mpo * st::InfiniteMPS (densempo.jl:31-45)"""
+    def __mul__(self, other):
+        """mpo * st::InfiniteMPS (densempo.jl:31-45); mpo1 * mpo2 (densempo.jl:73-87: mpo2 acts first)"""
+        if isinstance(other, DenseMPO):
+            if len(self) != len(other):
+                raise ValueError("dimension mismatch")
+            return DenseMPO(mpo_product(self, other).slices)
         from .changebonds import mpo_times_infinite
-        return mpo_times_infinite(self, st)
+        return mpo_times_infinite(self, other)
 
 
 def periodic_boundary_conditions(H: MPOHamiltonian, L=None):

@@ -129,6 +129,18 @@ def dot(a: InfiniteMPS, b: InfiniteMPS):
     """dot(psi1, psi2) for InfiniteMPS: dominant eigenvalue of the mixed transfer matrix of the AL tensors (dense)"""
     Da, Db = a.AL[0].shape[0], b.AL[0].shape[0]
     n = Da * Db
+    if n > 600:                                    # large mixed transfer matrices: implicitly restarted Arnoldi instead of dense
+        import scipy.sparse.linalg as spl
+
+        def mv(x):
+            v = x.reshape(Da, Db)
+            for s_ in range(a.N):
+                v = transfer_left_bond(v, b.AL[s_], a.AL[s_])
+            return v.reshape(-1)
+        rng = np.random.default_rng(0)
+        ev = spl.eigs(spl.LinearOperator((n, n), matvec=mv, dtype=np.complex128), k=1, which="LM",
+                      v0=rng.standard_normal(n) + 1j * rng.standard_normal(n), tol=1e-13)[0]
+        return ev[0]
     T = np.zeros((n, n), dtype=np.complex128)
     for k in range(n):
         v = np.zeros(n, dtype=np.complex128); v[k] = 1

@@ -906,3 +906,28 @@ def test_makefullrank_in_the_infinite_mps_constructor():
     assert np.linalg.norm(al.conj().T @ al - np.eye(al.shape[1])) < 1e-12
     C, Vc = oi.makefullrank(B, W, p.index_charges())
     assert C is B and Vc is W                                             # full rank: untouched
+
+
+def test_densempo_products_reference_test_set():
+    """test/operators.jl:159-171 ("DenseMPO"): W = convert(DenseMPO, make_time_mpo(ham, 1im * 0.5, WII())) for the TFI and the
+    spin-1 Heisenberg chain, psi = InfiniteMPS([P], [oneunit (+) P]):  abs(dot(W * (W * psi), (W * W) * psi)) ~ 1 atol 1e-10.
+    W * W is the package's host-side operator product (DenseMPO.__mul__, densempo.jl:73-87), W * psi the oracle restatement of
+    densempo.jl:31-45; here also with U(1) charges on the Heisenberg chain."""
+    import mpskit_b200 as m
+    from mpskit_b200.operators import make_time_mpo
+    from oracle import infinite as oi, changebonds as ocb
+
+    def oslices(W):
+        return [ompo.SparseMPOSlice(s.Os, s.domcharges, s.imcharges, s.pcharges) for s in W.slices]
+    cases = [(m.transverse_field_ising(1, 1.0), Space((0,), (2,)), Space((0,), (3,))),
+             (m.drop_symmetry(m.heisenberg_u1(1, d=3)), Space((0,), (3,)), Space((0,), (4,))),
+             (m.heisenberg_u1(1, d=3), Space((-2, 0, 2), (1, 1, 1)), Space((-2, 0, 2), (1, 2, 1)))]
+    for Hd, p, V in cases:
+        W = m.DenseMPO(make_time_mpo(Hd, 0.5j).slices)
+        WW = W * W
+        assert WW[0].odim == W[0].odim ** 2
+        psi = oi.InfiniteMPS.random(np.random.default_rng(2), p, [V])
+        a = ocb.mpo_times_state(oslices(W), ocb.mpo_times_state(oslices(W), psi))
+        b = ocb.mpo_times_state(oslices(WW), psi)
+        assert abs(abs(ocb.dot(a, b)) - 1.0) < 1e-10
+        assert abs(abs(ocb.dot(a, psi)) - 1.0) > 1e-3              # and the operator did something

@@ -297,3 +297,23 @@ def test_densempo_times_state_and_svdcut_device(ctx):
     du = abs(abs(dcb.dot_infinite(cut, tu)) - 1.0)
     print("U(1) W^II * st, SvdCut vs TDVP", du, [v.as_dict() for v in cut.V])
     assert [v.as_dict() for v in cut.V] == [v.as_dict() for v in Vs] and du <= 1e-7
+
+
+def test_densempo_products_device(ctx):
+    """test/operators.jl:159-171 ("DenseMPO") on the device: W = convert(DenseMPO, make_time_mpo(ham, 1im * 0.5, WII())) for the
+    TFI and the spin-1 Heisenberg chain (trivial and U(1)), psi = InfiniteMPS([P], [oneunit (+) P]):
+    abs(dot(W * (W * psi), (W * W) * psi)) ~ 1 atol 1e-10 with the device constructor (uniform gauge) and the device dot."""
+    import importlib
+    from mpskit_b200.operators import make_time_mpo
+    dcb = importlib.import_module(m.__name__ + ".changebonds")
+    cases = [(m.transverse_field_ising(1, 1.0), m.Space((0,), (2,)), m.Space((0,), (3,))),
+             (m.drop_symmetry(m.heisenberg_u1(1, d=3)), m.Space((0,), (3,)), m.Space((0,), (4,))),
+             (m.heisenberg_u1(1, d=3), m.Space((-2, 0, 2), (1, 1, 1)), m.Space((-2, 0, 2), (1, 2, 1)))]
+    for Hd, p, V in cases:
+        W = m.DenseMPO(make_time_mpo(Hd, 0.5j).slices)
+        psi = m.InfiniteMPS.random(np.random.default_rng(2), p, [V], ctx)
+        a = W * (W * psi)
+        b = (W * W) * psi
+        ov = abs(dcb.dot_infinite(a, b))
+        print("DenseMPO products", a.V[0].as_dict(), b.V[0].as_dict(), ov)
+        assert abs(ov - 1.0) <= 1e-10 and abs(abs(dcb.dot_infinite(a, psi)) - 1.0) > 1e-3
