@@ -93,6 +93,124 @@ class MPOHamiltonian:
     def __getitem__(self, i):
         return self.slices[i % len(self.slices)]
 
+    # ---- arithmetic (src/operators/mpohamiltonian.jl:76-157); host-side operator construction -------------------------
+    def _map_slices(self, f):
+        return MPOHamiltonian([f(c, sl) for c, sl in enumerate(self.slices)])
+
+    def __neg__(self):                                      # mpohamiltonian.jl:77
+        return self * (-1.0)
+
+    def __mul__(self, b):
+        """a * b::Number scales the entries that end in the last level (mpohamiltonian.jl:147-154); b * a::MPOHamiltonian is
+        the operator product (mpohamiltonian.jl:156, sparsempo.jl:232-264)"""
+        if isinstance(b, MPOHamiltonian):
+            return mpo_product(self, b)
+        if hasattr(b, "AL"):                                # H * mps::InfiniteMPS = convert(DenseMPO, H) * mps (:164)
+            return DenseMPO(self.slices) * b
+
+        def scaled(c, sl):
+            Os = [row[:] for row in sl.Os]
+            for j in range(sl.odim - 1):
+                if sl.contains(j, sl.odim - 1):
+                    Os[j][sl.odim - 1] = Os[j][sl.odim - 1] * b
+            return SparseMPOSlice(Os, sl.domcharges, sl.imcharges, sl.pcharges, sl.modulus)
+        return self._map_slices(scaled)
+
+    def __rmul__(self, b):                                  # mpohamiltonian.jl:146
+        return self * b
+
+    def __add__(self, other):
+        """a + e::Vector adds e[c] * 1 per site to the entry (first, last) (mpohamiltonian.jl:78-90); a + b merges the two
+        automata: shared first and last level, b's inner levels appended after a's (mpohamiltonian.jl:97-142)"""
+        if not isinstance(other, MPOHamiltonian):
+            e = [complex(x) for x in np.atleast_1d(other)]
+            if len(e) != len(self):
+                raise ValueError(f"periodicity should match {len(self)} != {len(e)}")
+
+            def shifted(c, sl):
+                Os = [row[:] for row in sl.Os]
+                Os[0][sl.odim - 1] = _entry_add(Os[0][sl.odim - 1], e[c], sl.d)
+                return SparseMPOSlice(Os, sl.domcharges, sl.imcharges, sl.pcharges, sl.modulus)
+            return self._map_slices(shifted)
+        if len(self) != len(other):
+            raise ValueError(f"periodicity should match {len(self)} != {len(other)}")
+        out = []
+        for sa, sb in zip(self.slices, other.slices):
+            oa, ob = sa.odim, sb.odim
+            n = oa + ob - 2
+            Os = [[0 for _ in range(n)] for _ in range(n)]
+            for (i, j) in sa.keys():
+                if i < oa - 1 and j < oa - 1:
+                    Os[i][j] = sa.Os[i][j]
+                elif i < oa - 1 and j == oa - 1:
+                    Os[i][n - 1] = sa.Os[i][j]
+            for (i, j) in sb.keys():
+                if i == 0 and j > 0:
+                    Os[0][oa + j - 2] = _entry_add(Os[0][oa + j - 2], sb.Os[i][j], sb.d)
+                elif i > 0 and j > 0:
+                    Os[oa + i - 2][oa + j - 2] = sb.Os[i][j]
+            cl = list(sa.domcharges[:oa - 1]) + list(sb.domcharges[1:])
+            cr = list(sa.imcharges[:oa - 1]) + list(sb.imcharges[1:])
+            out.append(SparseMPOSlice(Os, cl, cr, sa.pcharges, sa.modulus))
+        return MPOHamiltonian(out)
+
+    def __radd__(self, e):                                  # mpohamiltonian.jl:93
+        return self + e
+
+    def __sub__(self, other):                               # mpohamiltonian.jl:94,143
+        return self + (-other if isinstance(other, MPOHamiltonian) else [-complex(x) for x in np.atleast_1d(other)])
+
+    def __rsub__(self, e):                                  # mpohamiltonian.jl:92
+        return self * (-1.0) + e
+
+    def repeat(self, n):                                    # mpohamiltonian.jl:157
+        return MPOHamiltonian(self.slices * int(n))
+
+    @staticmethod
+    def from_local(O, phys_charges=None, tol=1e-14):
+        """MPOHamiltonian(t::TensorMap) = MPOHamiltonian(decompose_localmpo(add_util_leg(t))) (mpohamiltonian.jl:16,19-31): the
+        n-site interaction O[p1_out .. pn_out, p1_in .. pn_in] on every n consecutive sites of a one-site unit cell; every index
+        of the k-th virtual bond of the decomposition becomes one level (width 1, with its charge) of the automaton."""
+        from .toolbox import decompose_localmpo
+        O = np.asarray(O, dtype=np.complex128)
+        d = O.shape[0]
+        pq = [0] * d if phys_charges is None else [int(c) for c in phys_charges]
+        Ts, charges = decompose_localmpo(O, pq, tol, return_charges=True)
+        scale = np.abs(O).max() or 1.0
+        widths = [T.shape[3] for T in Ts[:-1]]
+        offs = [1 + int(sum(widths[:k])) for k in range(len(widths) + 1)]          # first level of bond k (bond 0: level 0)
+        od = 2 + int(sum(widths))
+        lc = [0] * od
+        for k, w in enumerate(widths):
+            for a in range(w):
+                lc[offs[k] + a] = int(charges[k + 1][a])
+        Os = [[0 for _ in range(od)] for _ in range(od)]
+        Os[0][0] = 1.0
+        Os[od - 1][od - 1] = 1.0
+        for k, T in enumerate(Ts):
+            for a in range(T.shape[0]):
+                for b in range(T.shape[3]):
+                    row = 0 if k == 0 else offs[k - 1] + a
+                    col = od - 1 if k == len(Ts) - 1 else offs[k] + b
+                    allowed = np.array([[lc[col] == lc[row] + pq[x] - pq[y] for y in range(d)] for x in range(d)])
+                    blk = T[a, :, :, b]
+                    if np.abs(blk * ~allowed).max() > 1e-10 * scale:
+                        raise ValueError("from_local: the operator does not conserve the physical charges")
+                    blk = blk * allowed                         # rounding noise of the SVDs outside the allowed elements
+                    if np.abs(blk).max() == 0:
+                        continue
+                    Os[row][col] = _entry_add(Os[row][col], blk, d)
+        return MPOHamiltonian([SparseMPOSlice(Os, lc, lc, pq)])
+
+
+def _entry_add(a, b, d):
+    """sum of two slice entries; scalars stand for multiples of the identity (sparseslice.jl:40-55)"""
+    if np.isscalar(a) and np.isscalar(b):
+        return a + b
+    ea = a * np.eye(d) if np.isscalar(a) else np.asarray(a, dtype=np.complex128)
+    eb = b * np.eye(d) if np.isscalar(b) else np.asarray(b, dtype=np.complex128)
+    return ea + eb
+
 
 # --------------------------------------------------------------------------------------- models
 def spin_ops(d=2):

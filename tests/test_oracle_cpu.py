@@ -931,3 +931,63 @@ def test_densempo_products_reference_test_set():
         b = ocb.mpo_times_state(oslices(WW), psi)
         assert abs(abs(ocb.dot(a, b)) - 1.0) < 1e-10
         assert abs(abs(ocb.dot(a, psi)) - 1.0) > 1e-3              # and the operator did something
+
+
+def test_mpohamiltonian_arithmetic_reference_test_set():
+    """test/operators.jl:19-80 ("MPOHamiltonian"): random 1-, 2- and 3-body interactions (trivial and U(1) physical space);
+    h1 from the decomposed three-site operator, h2 = MPOHamiltonian(nn), h3 an on-site two-site-cell Hamiltonian written as an
+    automaton; expectation values on random InfiniteMPS through the oracle:
+      2 e1 - 1 = <2 h1 - [1]>,  2 e1 + e2 - 1 = <(2 h1 - [1]) + h2>,  e1' + e3 = <repeat(h, 2) + h3>  (all atol 1e-10),
+      real(sum <h4 h4>) >= 0.
+    The arithmetic (mpohamiltonian.jl:76-157) and the local-operator constructor (mpohamiltonian.jl:16) are the package's host-side
+    operator construction; also checked against the dense lattice sum on a finite chain."""
+    import mpskit_b200 as m
+    from oracle import infinite as oi
+
+    def osl(H):
+        return ompo.MPOHamiltonian([ompo.SparseMPOSlice(s.Os, s.domcharges, s.imcharges, s.pcharges) for s in H.slices])
+
+    def herm(rng, pq, n):
+        d = len(pq)
+        X = rng.standard_normal((d,) * (2 * n)) + 1j * rng.standard_normal((d,) * (2 * n))
+        q = np.asarray(pq)
+        tot = sum(q[idx] for idx in np.ix_(*([np.arange(d)] * n)))                 # charge of an n-site basis state
+        X = X * (tot.reshape(tot.shape + (1,) * n) == tot.reshape((1,) * n + tot.shape))
+        M = X.reshape(d ** n, d ** n)
+        return (M + M.conj().T).reshape((d,) * (2 * n))
+
+    def E(st, H):
+        return oi.expectation_value(st, osl(H), oi.MPOHamInfEnv(st, osl(H)))
+    for pq, p, V in (((0, 0), Space((0,), (2,)), Space((0,), (6,))), ((-1, 1), Space((-1, 1), (1, 1)), Space((-1, 0, 1), (2, 3, 2)))):
+        rng = np.random.default_rng(8)
+        n1, n2, n3 = herm(rng, pq, 1), herm(rng, pq, 2), herm(rng, pq, 3)
+        h1 = m.MPOHamiltonian.from_local(n3, pq)
+        h2 = m.MPOHamiltonian.from_local(n2, pq)
+        one = m.MPOHamiltonian.from_local(n1, pq)
+        h3 = (one + one).repeat(2)                                                  # d1 of the reference: n twice per site
+        # the constructors against the dense lattice sum on an open chain of 5 sites
+        L, d = 5, len(pq)
+        Hm = np.zeros((d ** L, d ** L), dtype=complex)
+        for i in range(L - 2):
+            Hm += np.kron(np.kron(np.eye(d ** i), n3.reshape(d ** 3, d ** 3)), np.eye(d ** (L - 3 - i)))
+        assert np.abs(ompo.dense_hamiltonian(ompo.MPOHamiltonian(osl(h1).slices * L)) - Hm).max() < 1e-12
+        # one-site unit cell: trivial symmetry only (with charges +-1 on the physical leg the bond parity alternates)
+        st1 = oi.InfiniteMPS.random(np.random.default_rng(1), p, [V]) if pq == (0, 0) else None
+        if st1 is not None:
+            e1, e2 = E(st1, h1), E(st1, h2)
+            g = 2 * h1 - [1]
+            assert abs(e1[0] * 2 - 1 - E(st1, g)[0]) < 1e-10
+            g = g + h2
+            assert abs(e1[0] * 2 + e2[0] - 1 - E(st1, g)[0]) < 1e-10
+        else:
+            g = (2 * h1 - [1]) + h2
+        Vs = [V, V] if pq == (0, 0) else [Space((-1, 1), (3, 3)), Space((-2, 0, 2), (2, 3, 2))]
+        st2 = oi.InfiniteMPS.random(np.random.default_rng(2), p, Vs)
+        g2 = g.repeat(2)
+        ea, e3 = E(st2, g2), E(st2, h3)
+        assert np.abs(ea + e3 - E(st2, g2 + h3)).max() < 1e-10
+        assert np.abs(e3 - 2 * E(st2, one.repeat(2))).max() < 1e-10
+        assert np.abs(E(st2, -g2) + ea).max() < 1e-10 and np.abs(E(st2, [0.5, 0.25] - g2) + ea - [0.5, 0.25]).max() < 1e-10
+        h4 = g2 + h3
+        h4 = h4 * h4
+        assert float(np.sum(E(st2, h4)).real) >= 0
