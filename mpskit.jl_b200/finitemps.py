@@ -131,6 +131,80 @@ class FiniteMPS:
     def __len__(self):
         return self.L
 
+    # ---- the state as a vector (finitemps.jl:372-469) -----------------------------------------------------------------
+    def _site_tensors(self):
+        """(AC[0], AR[1], ..., AR[L-1]): site tensors whose product is the state including its norm"""
+        return [self.AC[0]] + [self.AR[i] for i in range(1, self.L)]
+
+    def norm(self):
+        """norm(psi) = norm(psi.AC[1]) (finitemps.jl:467)"""
+        return float(self.AC[0].norm())
+
+    def dot(self, other):
+        """dot(self, other) = <self|other> (finitemps.jl:459-464), through the rectangular overlap environments of
+        `approximate` (FinEnv with a unit operator and `other` above) and the projection ac_proj (derivatives.jl:216-221)"""
+        from .environments import environments
+        from .approximate import ac_proj
+        from .operators import MPOHamiltonian, SparseMPOSlice
+        if len(self) != len(other):
+            raise ValueError("MPS with different length")
+        unit = MPOHamiltonian([SparseMPOSlice([[1.0]], (0,), (0,), self.pq, self.pspace.modulus)])
+        envs = environments(self, unit, other)
+        y = ac_proj(0, self, envs)
+        val = complex(self.AC[0].dot(y))
+        y.free()
+        return val
+
+    def __mul__(self, a):
+        """psi * a (finitemps.jl:372-373,445-455): the factor sits on the centre tensors"""
+        T = [t.copy() for t in self._site_tensors()]
+        T[0].scale(a)
+        return FiniteMPS(T, list(self.V), self.pspace, self.ctx, normalize=False, dtype=self.dtype)
+
+    __rmul__ = __mul__
+
+    def normalize(self):
+        """normalize(psi) (finitemps.jl:468-469)"""
+        return self * (1.0 / self.norm())
+
+    def __add__(self, other):
+        """psi1 + psi2 (finitemps.jl:375-441): direct sum of the bond spaces on the device (mpsk_tensor_cat) -- first tensor
+        [A1 A2], inner tensors block diagonal, last tensor [A1; A2] -- a right-to-left LQ sweep that cuts the summed bonds of
+        the right half and the constructor's QR chain for the left half (the leftorth! / rightorth! steps of the reference)."""
+        from .changebonds import cat
+        if len(self) != len(other):
+            raise ValueError(f"Cannot add states of length {len(self)} and {len(other)}")
+        L, ctx, mod = self.L, self.ctx, self.pspace.modulus
+        assert L > 1, "not implemented for length < 2"
+        Ta, Tb = self._site_tensors(), other._site_tensors()
+        out = []
+        for i in range(L):
+            if i == 0:
+                out.append(cat(Ta[i], Tb[i], 1))
+            elif i == L - 1:
+                out.append(cat(Ta[i], Tb[i], 0))
+            else:
+                za = DeviceTensor.zeros(ctx, Ta[i].Vl, Ta[i].mch, Tb[i].Vr, self.dtype)
+                zb = DeviceTensor.zeros(ctx, Tb[i].Vl, Tb[i].mch, Ta[i].Vr, self.dtype)
+                top, bot = cat(Ta[i], za, 1), cat(zb, Tb[i], 1)
+                out.append(cat(top, bot, 0))
+                for t in (za, zb, top, bot):
+                    t.free()
+        for i in range(L - 1, 0, -1):
+            Lm, Q = lqpos(ctx, out[i], mod)
+            out[i] = Q
+            h = C.c_void_p()
+            ctx.check(ctx.lib.mpsk_mul_bond_right(ctx.h, out[i - 1].h, Lm.h, C.byref(h)))
+            out[i - 1] = DeviceTensor.wrap(ctx, h, mod)
+        V = [out[0].Vl] + [t.Vr for t in out]
+        return FiniteMPS(out, V, self.pspace, ctx, normalize=False, dtype=self.dtype)
+
+    def __neg__(self):
+        return self * (-1.0)
+
+    def __sub__(self, other):                      # finitemps.jl:443
+        return self + (other * (-1.0))
+
     # ---- orthoview.jl getters ------------------------------------------------------------------
     def _get_CL(self, i):
         """CR[i-1] (orthoview.jl:49-60): LQpos of AC[i] when the left neighbour is left-canonical, else QRpos of AC[i-1]."""

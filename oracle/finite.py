@@ -589,3 +589,58 @@ def finite_excited(H, states, init: FiniteMPS, weight=10.0, nsweeps=1, tol=1e-12
         if eps <= tol:
             break
     return float(np.real(sum(expectation_value(psi, H, FinEnv(psi, H))))), psi
+
+
+# ------------------------------------------------------------------------------------------ FiniteMPS as a vector
+def _site_tensors(psi: FiniteMPS):
+    """(AC[0], AR[1], ..., AR[L-1]): site tensors whose product is the state including its norm"""
+    return [psi.get_AC(0)] + [psi.get_AR(i) for i in range(1, psi.L)]
+
+
+def mps_dot(a: FiniteMPS, b: FiniteMPS):
+    """dot(psi1, psi2) (src/states/finitemps.jl:459-464), antilinear in the first argument"""
+    assert a.L == b.L, "MPS with different length"
+    v = np.ones((1, 1), dtype=np.complex128)
+    for x, y in zip(_site_tensors(a), _site_tensors(b)):
+        v = np.einsum('ab,apc,bpd->cd', v, x.conj(), y)
+    return complex(np.trace(v))
+
+
+def mps_norm(psi: FiniteMPS):
+    """norm(psi) = norm(psi.AC[1]) (finitemps.jl:467)"""
+    return float(np.linalg.norm(psi.get_AC(0)))
+
+
+def mps_scale(psi: FiniteMPS, c):
+    """psi * a / a * psi (finitemps.jl:372-373, 445-455): every AC and C of the state carries the factor"""
+    T = _site_tensors(psi)
+    T[0] = T[0] * c
+    return FiniteMPS(T, list(psi.V), psi.p, normalize=False)
+
+
+def mps_add(a: FiniteMPS, b: FiniteMPS):
+    """psi1 + psi2 (finitemps.jl:375-441): direct sum of the bond spaces -- first tensor [A1 A2], inner tensors block
+    diagonal, last tensor [A1; A2] -- then the canonical form (whose QR chain also cuts the summed bond spaces back to full rank,
+    as the leftorth! / rightorth! steps of the reference do)."""
+    from .changebonds import _sum_space
+    assert a.L == b.L and a.L > 1
+    mod = a.p.modulus
+    Ta, Tb = _site_tensors(a), _site_tensors(b)
+    d = len(a.pq)
+    sums = [None] + [_sum_space(a.V[i], b.V[i], mod) for i in range(1, a.L)] + [None]
+    out, V = [], [a.V[0]]
+    for i in range(a.L):
+        lo = (np.arange(a.V[i].dim), np.arange(b.V[i].dim)) if sums[i] is None else sums[i][1:]
+        ro = (np.arange(a.V[i + 1].dim), np.arange(b.V[i + 1].dim)) if sums[i + 1] is None else sums[i + 1][1:]
+        Dl = a.V[i].dim if sums[i] is None else sums[i][0].dim
+        Dr = a.V[i + 1].dim if sums[i + 1] is None else sums[i + 1][0].dim
+        t = np.zeros((Dl, d, Dr), dtype=np.complex128)
+        t[np.ix_(lo[0], range(d), ro[0])] += Ta[i]
+        t[np.ix_(lo[1], range(d), ro[1])] += Tb[i]
+        out.append(t)
+        V.append(a.V[i + 1] if sums[i + 1] is None else sums[i + 1][0])
+    for i in range(a.L - 1, 0, -1):               # right-to-left LQ sweep: cuts the summed bonds on the right half
+        Lm, Q, newV = a._rightorth(out[i], V[i], V[i + 1])
+        out[i], V[i] = Q, newV
+        out[i - 1] = np.einsum('apb,bc->apc', out[i - 1], Lm)
+    return FiniteMPS(out, V, a.p, normalize=False)

@@ -991,3 +991,35 @@ def test_mpohamiltonian_arithmetic_reference_test_set():
         h4 = g2 + h3
         h4 = h4 * h4
         assert float(np.sum(E(st2, h4)).real) >= 0
+
+
+def test_finite_mps_vector_operations_reference_test_set():
+    """test/states.jl:15-38 ("FiniteMPS"): dot(psi, psi) = norm(psi.AC[1])^2, the gauge relations AC = AL CR = CR[i-1] AR on every
+    site, norm(3 psi)^2 = 9 norm(psi)^2, norm(2 psi + psi - 3 psi) ~ 0 (sqrt(eps)); plus dot / + against dense state vectors.
+    Trivial and U(1) bond spaces (the reference uses a trivial and an SU(2) space)."""
+    from oracle import finite as of_
+
+    def dense(psi):
+        v = np.ones((1, 1), dtype=complex)
+        for t in of_._site_tensors(psi):
+            v = np.einsum('xa,apb->xpb', v, t).reshape(-1, t.shape[2])
+        return v.reshape(-1)
+    for p, maxV, L in ((Space((0,), (2,)), Space((0,), (10,)), 7), (Space((-1, 1), (1, 1)), Space((-2, -1, 0, 1, 2), (2, 3, 4, 3, 2)), 6)):
+        rng = np.random.default_rng(12)
+        psi = of_.FiniteMPS.random(rng, p, L, maxV)
+        psi = of_.mps_scale(psi, 1.7)
+        ovl = of_.mps_dot(psi, psi)
+        assert abs(ovl - of_.mps_norm(psi) ** 2) < 1e-12 and abs(ovl - 1.7 ** 2) < 1e-12
+        for i in range(L):
+            ac = psi.get_AC(i)
+            assert np.linalg.norm(ac - np.einsum('apb,bc->apc', psi.get_AL(i), psi.get_CR(i))) < 1e-12
+            assert np.linalg.norm(ac - np.einsum('ab,bpc->apc', psi.get_CR(i - 1), psi.get_AR(i))) < 1e-12
+        p3 = of_.mps_scale(psi, 3)
+        assert abs(of_.mps_norm(p3) ** 2 - 9 * ovl.real) < 1e-11
+        zero = of_.mps_add(of_.mps_add(of_.mps_scale(psi, 2), psi), of_.mps_scale(psi, -3))
+        assert of_.mps_norm(zero) < 1e-7                                           # sqrt(eps), as in the reference
+        phi = of_.FiniteMPS.random(rng, p, L, maxV)
+        s = of_.mps_add(psi, of_.mps_scale(phi, 0.5 - 0.25j))
+        assert np.linalg.norm(dense(s) - dense(psi) - (0.5 - 0.25j) * dense(phi)) < 1e-12
+        assert abs(of_.mps_dot(psi, phi) - np.vdot(dense(psi), dense(phi))) < 1e-12
+        assert all(s.V[i].dim <= min(2 ** i, 2 ** (L - i)) for i in range(L + 1))  # the sum is cut back to full rank

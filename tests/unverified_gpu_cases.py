@@ -317,3 +317,31 @@ def test_densempo_products_device(ctx):
         ov = abs(dcb.dot_infinite(a, b))
         print("DenseMPO products", a.V[0].as_dict(), b.V[0].as_dict(), ov)
         assert abs(ov - 1.0) <= 1e-10 and abs(abs(dcb.dot_infinite(a, psi)) - 1.0) > 1e-3
+
+
+def test_finite_mps_vector_operations_device(ctx):
+    """test/states.jl:15-38 ("FiniteMPS") on the device: dot(psi, psi) = norm(psi.AC[1])^2, norm(3 psi)^2 = 9 norm(psi)^2,
+    norm(2 psi + psi - 3 psi) ~ 0 (sqrt(eps)), and dot / + / scalar * against the oracle's dense state vectors (1e-12); trivial
+    and U(1) bond spaces.  dot runs through the rectangular overlap environments of `approximate`, + through mpsk_tensor_cat and
+    the device QR / LQ (verified primitives; this composition has not been executed on a GPU)."""
+    from oracle import finite as of_
+    for p_o, maxV_o, L in ((OSpace((0,), (2,)), OSpace((0,), (10,)), 7),
+                           (OSpace((-1, 1), (1, 1)), OSpace((-2, -1, 0, 1, 2), (2, 3, 4, 3, 2)), 6)):
+        p_d, maxV_d = to_dev_space(p_o), to_dev_space(maxV_o)
+        psi_o = of_.FiniteMPS.random(np.random.default_rng(12), p_o, L, maxV_o)
+        phi_o = of_.FiniteMPS.random(np.random.default_rng(13), p_o, L, maxV_o)
+        psi = m.FiniteMPS.random(np.random.default_rng(12), p_d, L, maxV_d, ctx)
+        phi = m.FiniteMPS.random(np.random.default_rng(13), p_d, L, maxV_d, ctx)
+        ovl = psi.dot(psi)
+        assert abs(ovl - psi.norm() ** 2) <= 1e-12 and abs(ovl - 1.0) <= 1e-12
+        assert abs(psi.dot(phi) - of_.mps_dot(psi_o, phi_o)) <= 1e-12
+        p3 = 3 * (psi * 3)
+        assert abs(p3.norm() ** 2 - 81 * ovl.real) <= 1e-10
+        zero = 2 * psi + psi - 3 * psi
+        assert zero.norm() <= 1e-7
+        c = 0.5 - 0.25j
+        s_d, s_o = psi + c * phi, of_.mps_add(psi_o, of_.mps_scale(phi_o, c))
+        assert abs(s_d.norm() - of_.mps_norm(s_o)) <= 1e-12
+        assert abs(s_d.dot(psi) - of_.mps_dot(s_o, psi_o)) <= 1e-12 and abs(s_d.dot(phi) - of_.mps_dot(s_o, phi_o)) <= 1e-12
+        assert [v.dim for v in s_d.V] == [v.dim for v in s_o.V]
+        assert abs(s_d.normalize().norm() - 1.0) <= 1e-13
