@@ -1023,3 +1023,35 @@ def test_finite_mps_vector_operations_reference_test_set():
         assert np.linalg.norm(dense(s) - dense(psi) - (0.5 - 0.25j) * dense(phi)) < 1e-12
         assert abs(of_.mps_dot(psi, phi) - np.vdot(dense(psi), dense(phi))) < 1e-12
         assert all(s.V[i].dim <= min(2 ** i, 2 ** (L - i)) for i in range(L + 1))  # the sum is cut back to full rank
+
+
+def test_old_bugs_reference_test_set():
+    """test/other.jl:21-52 ("Old bugs") on the oracle: (i) IDMRG2 on a six-site unit cell of a spin-1 chain whose bond spaces
+    grow during the run (there: SU(2) bilinear-biquadratic, "used to error"; here the U(1) Heisenberg point of the same family,
+    half-integer bonds {+-1: 2, +-3: 1}, truncdim(16)) returns a state with consistent spaces; (ii) no NaN in the entanglement
+    entropy after RandExpand (exact zeros in the Schmidt spectrum); (iii) changebonds with a three-site unit cell of unequal bond
+    dimensions (2, 3, 4): OptimalExpand and RandExpand return normalised states."""
+    from oracle import infinite as oi, changebonds as ocb, toolbox as ot
+    H = ompo.heisenberg_u1(6, d=3)
+    p = Space((-2, 0, 2), (1, 1, 1))
+    V = Space((-3, -1, 1, 3), (1, 2, 2, 1))
+    st = oi.InfiniteMPS.random(np.random.default_rng(1), p, [V] * 6)
+    out, envs, eps = oi.idmrg2(st, H, trunc=("truncdim", 16), tol=1e-4, maxiter=12)
+    assert out.N == 6 and all(out.V[i].dim <= 16 for i in range(6)) and max(v.dim for v in out.V) > V.dim
+    for i in range(6):
+        assert out.AL[i].shape == (out.V[i].dim, 3, out.V[(i + 1) % 6].dim)
+    e = float(np.mean(oi.expectation_value(out, H, oi.MPOHamInfEnv(out, H))).real)
+    assert abs(e - (-1.401484)) < 5e-3                                   # the Haldane chain energy density at D = 16
+    st = oi.InfiniteMPS.random(np.random.default_rng(2), Space((0,), (2,)), [Space((0,), (5,))])
+    ex = ocb.rand_expand(st, ("truncdim", 2), np.random.default_rng(3))
+    S = ot.entropy(ex)
+    assert ex.V[0].dim == 7 and not np.isnan(np.sum(S)) and abs(S[0] - ot.entropy(st)[0]) < 1e-10
+    Vs = [Space((0,), (2,)), Space((0,), (3,)), Space((0,), (4,))]
+    st = oi.InfiniteMPS.random(np.random.default_rng(4), Space((0,), (2,)), Vs)
+    H3 = ompo.transverse_field_ising(3, 1.0)
+    s1, _ = ocb.optimal_expand(st, H3, ("truncdim", 2))
+    s2 = ocb.rand_expand(st, ("truncdim", 2), np.random.default_rng(5))
+    for s_ in (s1, s2):
+        assert [v.dim for v in s_.V] == [4, 4, 4]                        # limited by the null spaces: +2, +1, +0
+        assert abs(abs(ocb.dot(s_, s_)) - 1.0) < 1e-10 and abs(abs(ocb.dot(s_, st)) - 1.0) < 1e-10
+        assert all(abs(np.linalg.norm(c) - 1.0) < 1e-12 for c in s_.CR)
