@@ -61,6 +61,52 @@ def lqpos(ctx, A, modulus=0):
     return Lm, Q
 
 
+def decompose_localmps(T, pspace: Space, left=None, right=None, tol=1e-12):
+    """decompose_localmps (src/utility/utility.jl:57-68) for abelian charges: T[left, p_1 .. p_L, right] -> site arrays
+    A_k[l, p, r] and their bond spaces; one SVD per charge of the cut bond (the rows (l, p) are grouped by q_l + s_p), the
+    singular values stay on the left factor (A = U S, B = V) as in the reference."""
+    T = np.asarray(T)
+    L = T.ndim - 2
+    pq = np.asarray(pspace.index_charges())
+    d, mod = len(pq), pspace.modulus
+    Vl = left if left is not None else Space((0,), (T.shape[0],), mod)
+    As, Vs = [], [Vl]
+    cur, curV = T, Vl
+    scale = np.abs(T).max() or 1.0
+    for _ in range(L - 1):
+        Dl = cur.shape[0]
+        M = cur.reshape(Dl * d, -1)
+        rowq = (curV.index_charges()[:, None] + pq[None, :]).reshape(-1)
+        if mod:
+            rowq = rowq % mod
+        cols, rows_out, charges, dims = [], [], [], []
+        for q in sorted(set(int(x) for x in rowq)):
+            rows = np.nonzero(rowq == q)[0]
+            U, sv, Vh = np.linalg.svd(M[rows], full_matrices=False)
+            keep = int(np.sum(sv > tol * scale))
+            if keep == 0:
+                continue
+            blk = np.zeros((M.shape[0], keep), dtype=M.dtype)
+            blk[rows] = U[:, :keep] * sv[None, :keep]
+            cols.append(blk); rows_out.append(Vh[:keep])
+            charges.append(q); dims.append(keep)
+        newV = Space(charges, dims, mod)
+        As.append(np.concatenate(cols, axis=1).reshape(Dl, d, newV.dim))
+        cur = np.concatenate(rows_out, axis=0).reshape((newV.dim,) + cur.shape[2:])
+        curV = newV
+        Vs.append(newV)
+    if right is None:
+        rowq = (curV.index_charges()[:, None] + pq[None, :]).reshape(-1)
+        nz = np.abs(cur.reshape(len(rowq), -1)).max(axis=1) > tol * scale
+        tot = sorted(set(int(x) % mod if mod else int(x) for x in rowq[nz])) or [0]
+        if len(tot) != 1 or cur.shape[-1] != 1:
+            raise ValueError("decompose_localmps: pass the right edge space of a state without a definite total charge")
+        right = Space((tot[0],), (1,), mod)
+    As.append(cur.reshape(cur.shape[0], d, cur.shape[-1]))
+    Vs.append(right)
+    return As, Vs
+
+
 class FiniteMPS:
     def __init__(self, As, Vs, pspace: Space, ctx=None, normalize=True, dtype=np.complex128):
         """As: site tensors A[l,p,r] -- host arrays (dense charged) or DeviceTensors.  Like finitemps.jl:143-170 the
@@ -198,6 +244,24 @@ class FiniteMPS:
             out[i - 1] = DeviceTensor.wrap(ctx, h, mod)
         V = [out[0].Vl] + [t.Vr for t in out]
         return FiniteMPS(out, V, self.pspace, ctx, normalize=False, dtype=self.dtype)
+
+    def to_dense(self):
+        """convert(TensorMap, psi) (finitemps.jl:351-362): the state as one dense tensor [left, p_1 .. p_L, right] on the host
+        (exponential in L: small chains, tests, exact diagonalisation cross-checks)"""
+        T = None
+        for t in self._site_tensors():
+            a = t.to_dense()
+            T = a if T is None else np.tensordot(T, a, axes=([T.ndim - 1], [0]))
+        return T
+
+    @staticmethod
+    def from_dense(T, pspace, ctx=None, left=None, right=None, tol=1e-12, dtype=np.complex128):
+        """FiniteMPS(decompose_localmps(T)) (utility.jl:57-68, finitemps.jl:143-170): successive charged SVDs of the dense
+        tensor T[left, p_1 .. p_L, right] on the host (state construction), singular values below tol * s_max dropped, then the
+        device constructor.  left / right: the edge bond spaces (default: one-dimensional, charge 0 on the left and the total
+        charge found in T on the right)."""
+        As, Vs = decompose_localmps(T, pspace, left, right, tol)
+        return FiniteMPS(As, Vs, pspace, ctx, normalize=False, dtype=dtype)
 
     def __neg__(self):
         return self * (-1.0)

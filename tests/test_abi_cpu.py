@@ -442,3 +442,27 @@ def test_densempo_times_state_host_part_without_gpu():
         return lam
     # W^II is unitary up to O(dt^2): the product of a normalised state stays normalised to that order
     assert abs(leading(tensors) - 1.0) < 1e-5
+
+
+def test_decompose_localmps_host_part_without_gpu():
+    """test/states.jl:40-47: psi2 = FiniteMPS(decompose_localmps(convert(TensorMap, psi))) has dot(psi, psi2) = dot(psi, psi), for a
+    trivial and a U(1) (spin-1) bond space.  The charged SVD chain is the package's host-side state construction
+    (mpskit_b200.finitemps.decompose_localmps); the states themselves are evaluated through the oracle."""
+    import numpy as np
+    import mpskit_b200 as m
+    from mpskit_b200.finitemps import decompose_localmps
+    from oracle import finite as of_
+    from oracle.spaces import Space
+    for p, maxV in ((Space((0,), (2,)), Space((0,), (10,))), (Space((-1, 0, 1), (1, 1, 1)), Space((-1, 0, 1), (3, 3, 3)))):
+        psi = of_.FiniteMPS.random(np.random.default_rng(3), p, 4, maxV)
+        T = None
+        for t in of_._site_tensors(psi):
+            T = t if T is None else np.tensordot(T, t, axes=([T.ndim - 1], [0]))
+        As, Vs = decompose_localmps(T, m.Space(p.charges, p.dims))
+        assert [v.as_dict() for v in Vs] == [v.as_dict() for v in psi.V]          # full-rank state: the same bond spaces
+        psi2 = of_.FiniteMPS(As, [Space(v.charges, v.dims) for v in Vs], p, normalize=False)
+        assert abs(of_.mps_dot(psi, psi2) - of_.mps_dot(psi, psi)) < 1e-12
+        T2 = None
+        for t in As:
+            T2 = t if T2 is None else np.tensordot(T2, t, axes=([T2.ndim - 1], [0]))
+        assert np.abs(T2 - T).max() < 1e-13

@@ -345,3 +345,7 @@ def test_finite_mps_vector_operations_device(ctx):
         assert abs(s_d.dot(psi) - of_.mps_dot(s_o, psi_o)) <= 1e-12 and abs(s_d.dot(phi) - of_.mps_dot(s_o, phi_o)) <= 1e-12
         assert [v.dim for v in s_d.V] == [v.dim for v in s_o.V]
         assert abs(s_d.normalize().norm() - 1.0) <= 1e-13
+        # test/states.jl:40-47: psi2 = FiniteMPS(decompose_localmps(convert(TensorMap, psi))) -> dot(psi, psi2) = dot(psi, psi)
+        small = m.FiniteMPS.random(np.random.default_rng(3), p_d, 4, maxV_d, ctx)
+        again = m.FiniteMPS.from_dense(small.to_dense(), p_d, ctx)
+        assert abs(small.dot(again) - small.dot(small)) <= 1e-12
