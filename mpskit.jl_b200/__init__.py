@@ -44,7 +44,7 @@ from . import toolbox  # noqa: F401
 from .toolbox import (transfer_spectrum, marek_gap, correlation_length, entropy, entanglement_spectrum,  # noqa: F401
                       expectation_value_local, correlator, decompose_localmpo)
 from .propagator import DynamicalDMRG, propagator  # noqa: F401
-from .statmech import VOMPS, MixedPerMPOInfEnv, approximate_vomps  # noqa: F401
+from .statmech import VOMPS, MixedPerMPOInfEnv, approximate_vomps, approximate_vomps_multiline  # noqa: F401
 from .statmech import approximate_idmrg1, approximate_idmrg2  # noqa: F401
 from .quasiparticle import QuasiparticleAnsatz, FiniteQP, excitations_qp  # noqa: F401
 from .quasiparticle import InfiniteQP, excitations_qp_infinite  # noqa: F401

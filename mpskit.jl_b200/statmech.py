@@ -420,6 +420,22 @@ def approximate_vomps(psi: InfiniteMPS, toapprox, alg: VOMPS = None, envs=None, 
     return psi, envs, eps
 
 
+def approximate_vomps_multiline(rows, toapprox, alg: VOMPS = None, envs=None, log=None):
+    """approximate(psi::MPSMultiline, (O::MPOMultiline, psi0::MPSMultiline), alg::VOMPS) (src/algorithms/approximate/vomps.jl:
+    19-80): ac_proj / c_proj of row r (ket psi0[r], operator O[r], bra psi[r + 1]; derivatives.jl:204-219) are circshifted by
+    one row -- row r + 1 of psi approximates O[r] psi0[r].  The mixed environments of different rows do not couple, so this is
+    the row-wise map of approximate_vomps; returns (rows, environments per operator row, max Galerkin error).
+    rows / psi0: lists of InfiniteMPS, O[r][c]: MPO slices."""
+    opp, above = toapprox
+    R = len(rows)
+    out, menvs, eps = [None] * R, [None] * R, 0.0
+    for r in range(R):
+        out[(r + 1) % R], menvs[r], e = approximate_vomps(rows[(r + 1) % R], (opp[r], above[r]), alg,
+                                                          None if envs is None else envs[r], log)
+        eps = max(eps, e)
+    return out, menvs, eps
+
+
 # ------------------------------------------------------------------------------------------ approximate with IDMRG1 / IDMRG2
 def _normalized(t):
     t.scale(1.0 / t.norm())

@@ -383,3 +383,16 @@ def approximate_idmrg2(ost: InfiniteMPS, slices, above: InfiniteMPS, trunc=("tru
             break
     nst = InfiniteMPS.from_tensors(AR, V, pq, tol=tol_gauge, mod=mod)
     return nst, MixedPerMPOInfEnv(nst, slices, above), eps
+
+
+def vomps_multiline(rows, slices, above_rows, tol=1e-12, maxiter=100, log=None):
+    """approximate(psi::MPSMultiline, (O::MPOMultiline, psi0::MPSMultiline), VOMPS()) (src/algorithms/approximate/vomps.jl:19-80):
+    ac_proj / c_proj of row r (ket psi0[r], operator O[r], bra psi[r + 1]; derivatives.jl:204-219) are circshifted by one row,
+    i.e. row r + 1 of psi approximates O[r] psi0[r]; the mixed environments of different rows do not couple, so the update is
+    the row-wise map of the single-row one (the reference stops on the maximum of the Galerkin errors; so does this)."""
+    R = len(rows)
+    out, envs, eps = [None] * R, [None] * R, 0.0
+    for r in range(R):
+        out[(r + 1) % R], envs[r], e = vomps(rows[(r + 1) % R], slices[r], above_rows[r], tol, maxiter, log)
+        eps = max(eps, e)
+    return out, envs, eps

@@ -1055,3 +1055,28 @@ def test_old_bugs_reference_test_set():
         assert [v.dim for v in s_.V] == [4, 4, 4]                        # limited by the null spaces: +2, +1, +0
         assert abs(abs(ocb.dot(s_, s_)) - 1.0) < 1e-10 and abs(abs(ocb.dot(s_, st)) - 1.0) < 1e-10
         assert all(abs(np.linalg.norm(c) - 1.0) < 1e-12 for c in s_.CR)
+
+
+def test_multiline_approximate_oracle():
+    """approximate(psi::MPSMultiline, (O::MPOMultiline, psi0::MPSMultiline), VOMPS()) (approximate/vomps.jl:19-80): two rows with
+    different W^I time-evolution MPOs (dt and 2 dt) applied to two different states; row r + 1 of the result equals a TDVP step of
+    psi0[r] with the matching time step (overlap 1 to 1e-8; the reference's test asserts dt for the one-row case) and not the
+    other row's."""
+    import mpskit_b200 as m
+    from mpskit_b200.operators import make_time_mpo
+    from oracle import infinite as oi, statmech as osm, changebonds as ocb
+    dt = 1e-3
+    Ho = ompo.transverse_field_ising(1, 2.0)
+    p, V = Space((0,), (2,)), Space((0,), (6,))
+    psi0 = [oi.InfiniteMPS.random(np.random.default_rng(20 + r), p, [V]) for r in range(2)]
+    start = [oi.InfiniteMPS.random(np.random.default_rng(30 + r), p, [V]) for r in range(2)]
+    sl = []
+    for r in range(2):
+        W = make_time_mpo(m.transverse_field_ising(1, 2.0), dt * (r + 1), "WI")
+        sl.append([ompo.SparseMPOSlice(s.Os, s.domcharges, s.imcharges, s.pcharges) for s in W.slices])
+    out, _, eps = osm.vomps_multiline(start, sl, psi0, tol=1e-12, maxiter=200)
+    assert eps < 1e-11
+    for r in range(2):
+        ref, _ = oi.tdvp_step(psi0[r], Ho, dt * (r + 1))
+        assert abs(abs(ocb.dot(out[(r + 1) % 2], ref)) - 1.0) < 1e-8
+        assert abs(abs(ocb.dot(out[r], ref)) - 1.0) > 1e-3

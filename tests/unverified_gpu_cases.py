@@ -349,3 +349,27 @@ def test_finite_mps_vector_operations_device(ctx):
         small = m.FiniteMPS.random(np.random.default_rng(3), p_d, 4, maxV_d, ctx)
         again = m.FiniteMPS.from_dense(small.to_dense(), p_d, ctx)
         assert abs(small.dot(again) - small.dot(small)) <= 1e-12
+
+
+def test_multiline_approximate_device(ctx):
+    """approximate(psi::MPSMultiline, (O::MPOMultiline, psi0::MPSMultiline), VOMPS()) (approximate/vomps.jl:19-80) on the device:
+    two rows with W^I MPOs of dt and 2 dt on two different states; row r + 1 of the result equals a device TDVP step of psi0[r]
+    with the matching time step (overlap 1 to 1e-8) and the oracle's multi-row result (1e-8).  Row-wise map of the verified
+    single-row approximate_vomps."""
+    import importlib
+    from mpskit_b200.operators import make_time_mpo
+    from oracle import infinite as oi, statmech as osm
+    dcb = importlib.import_module(m.__name__ + ".changebonds")
+    dt = 1e-3
+    Hd = m.transverse_field_ising(1, 2.0)
+    p, V = m.Space((0,), (2,)), m.Space((0,), (6,))
+    psi0 = [m.InfiniteMPS.random(np.random.default_rng(20 + r), p, [V], ctx) for r in range(2)]
+    start = [m.InfiniteMPS.random(np.random.default_rng(30 + r), p, [V], ctx) for r in range(2)]
+    Ws = [m.DenseMPO(make_time_mpo(Hd, dt * (r + 1), "WI").slices) for r in range(2)]
+    out, _, eps = m.approximate_vomps_multiline(start, ([[W[0]] for W in Ws], psi0), m.VOMPS(tol=1e-12, maxiter=200))
+    assert eps <= 1e-11
+    for r in range(2):
+        ref, _ = m.timestep_infinite(psi0[r], Hd, 0.0, dt * (r + 1))
+        ov = abs(dcb.dot_infinite(out[(r + 1) % 2], ref))
+        print("multiline approximate", r, ov, eps)
+        assert abs(ov - 1.0) <= 1e-8 and abs(abs(dcb.dot_infinite(out[r], ref)) - 1.0) > 1e-3
