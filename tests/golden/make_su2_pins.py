@@ -235,7 +235,9 @@ def run(name, spin, cells, tol, maxiter, seed=7, symmetric=True, save_state=None
     S = ot.entropy(st)
     if save_state:       # the converged left-gauged tensors, for the device read-out test (tests/unverified_gpu_cases.py)
         np.savez_compressed(save_state, **{f"AL{i}": st.AL[i] for i in range(N)}, **{f"C{i}": st.CR[i] for i in range(N)},
-                            charges=np.array(Vs[0].charges), dims=np.array(Vs[0].dims))
+                            charges=np.array(Vs[0].charges), dims=np.array(Vs[0].dims),
+                            **{f"charges{i}": np.array(Vs[i].charges) for i in range(N)},
+                            **{f"dims{i}": np.array(Vs[i].dims) for i in range(N)})
     rec = dict(name=name, symmetric_start=symmetric, spin=float(spin), requested_irreps=requested,
                irreps=[{str(Fraction(k)): v for k, v in c.items()} for c in cells],
                bond_spaces=[{str(k): v for k, v in V.as_dict().items()} for V in Vs], D=[V.dim for V in Vs],
@@ -252,7 +254,8 @@ CASES = {
     "minus_generic_u1": lambda: run("haldane-spt V_minus sectors, generic U(1) start", 1, [{H: 10, 3 * H: 5, 5 * H: 3}], 1e-10, 100,
                                     seed=3, symmetric=False),
     "plus": lambda: run("haldane-spt V_plus", 1, [{0: 10, 1: 5, 2: 3}], 1e-10, 100),
-    "xxz": lambda: run("xxz-heisenberg SU(2) two-site cell", H, [{0: 15, 1: 10, 2: 5}, {H: 10, 3 * H: 5, 5 * H: 2}], 1e-12, 400),
+    "xxz": lambda: run("xxz-heisenberg SU(2) two-site cell", H, [{0: 15, 1: 10, 2: 5}, {H: 10, 3 * H: 5, 5 * H: 2}], 1e-12, 400,
+                       save_state=os.path.join(os.path.dirname(OUT), "su2_xxz_state.npz")),
 }
 REFERENCE = {
     "minus": dict(source="docs/src/examples/quantum1d/5.haldane-spt/index.md:397-404,1018", energy=-1.4014839739630869,

@@ -794,6 +794,14 @@ def test_recorded_su2_state_gives_the_reference_printed_readouts():
     assert abs(e - (-1.4014839739630869)) < 1e-12
     assert abs(ot.entropy(st, 0) + np.log(2.0) - 1.5486227235451633) < 1e-10
     assert oi.calc_galerkin(st, 0, envs) <= 1e-9
+    # the two-site SU(2) cell of 4.xxz-heisenberg/index.md:671 ("VUMPS conv 73: obj = -8.862878980874e-01", sum over the cell)
+    rec = np.load(os.path.join(GOLD, "su2_xxz_state.npz"))
+    Vs = [Space(tuple(int(c) for c in rec[f"charges{i}"]), tuple(int(d) for d in rec[f"dims{i}"])) for i in range(2)]
+    st = oi.InfiniteMPS.from_tensors([rec["AL0"], rec["AL1"]], Vs, Space((-1, 1), (1, 1)).index_charges(), mod=0)
+    H = ompo.heisenberg_u1(2)
+    envs = oi.MPOHamInfEnv(st, H)
+    assert abs(float(np.sum(oi.expectation_value(st, H, envs)).real) - (-8.862878980874e-01)) < 1e-12
+    assert max(oi.calc_galerkin(st, i, envs) for i in range(2)) <= 1e-10
 
 
 def test_multiline_changebonds_oracle():

@@ -135,7 +135,8 @@ def test_reference_printed_su2_state_readouts_device(ctx):
     The oracle reproduces both (tests/golden/make_su2_pins.py; 4e-16 / 2e-12) and recorded the converged left-gauged tensor in U(1)
     blocks (D = 58).  Here that tensor goes through the device's own path: upload, uniform gauge (device QR / Arnoldi), the
     MPOHamInfEnv GMRES solves, expectation_value, entropy, calc_galerkin -- against the numbers the reference printed.  (A device
-    VUMPS iteration from this state would leave the SU(2) manifold, as the unprojected oracle does, hence read-outs only.)"""
+    VUMPS iteration from this state would leave the SU(2) manifold, as the unprojected oracle does, hence read-outs only.)  The same
+    for the two-site SU(2) cell of 4.xxz-heisenberg/index.md:579-671 (D = 65 / 52): "VUMPS conv 73: obj = -8.862878980874e-01"."""
     import os
     from mpskit_b200 import infinite as di
     from mpskit_b200.tensor import DeviceTensor
@@ -153,6 +154,17 @@ def test_reference_printed_su2_state_readouts_device(ctx):
     assert abs(e - (-1.4014839739630869)) <= 1e-11
     assert abs(S + np.log(2.0) - 1.5486227235451633) <= 1e-8
     assert gal <= 1e-8
+    # 4.xxz-heisenberg/index.md:671: "VUMPS conv 73: obj = -8.862878980874e-01" (two-site SU(2) cell, sum over the cell)
+    rec = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "su2_xxz_state.npz"))
+    Vs = [m.Space(tuple(int(c) for c in rec[f"charges{i}"]), tuple(int(d) for d in rec[f"dims{i}"])) for i in range(2)]
+    A = [DeviceTensor.from_dense(ctx, rec[f"AL{i}"], Vs[i], [-1, 1], Vs[(i + 1) % 2], np.complex128) for i in range(2)]
+    st = m.InfiniteMPS.from_tensors(A, Vs, m.Space((-1, 1), (1, 1)), ctx)
+    Hx = dev_hamiltonian(ompo.heisenberg_u1(2))
+    envs = di.MPOHamInfEnv(st, Hx)
+    ex = float(np.sum(di.expectation_value(st, Hx, envs)).real)
+    gx = max(di.calc_galerkin(st, i, envs) for i in range(2))
+    print("device read-outs of the recorded xxz SU(2) state", repr(ex), gx)
+    assert abs(ex - (-8.862878980874e-01)) <= 1e-11 and gx <= 1e-8
 
 
 def test_reference_printed_su2_numbers_device_vumps(ctx):
