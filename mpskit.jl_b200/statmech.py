@@ -262,22 +262,28 @@ def calc_galerkin_multiline(rows, envs):
 
 
 def leading_boundary_multiline(rows, opp, alg: VUMPS = None, envs=None, log=None):
-    """leading_boundary(psi::MPSMultiline, H::MPOMultiline, alg::VUMPS, envs) (statmech/vumps.jl:20-84).  rows: list of
+    """leading_boundary(psi::MPSMultiline, H::MPOMultiline, alg::VUMPS, envs) (statmech/vumps.jl:20-84); with alg::VOMPS the
+    power method of statmech/vomps.jl:27-87 (one application of the multi-row derivatives per column).  rows: list of
     InfiniteMPS (one per row, same bond spaces); opp[r][c]: MPO slices.  Every column update is ONE Arnoldi eigensolve on
     the RecursiveVec of all rows inside the library."""
     alg = alg or VUMPS(tol=1e-10)
     envs = envs or MultilineEnv(rows, opp)
     R, N, ctx = len(rows), rows[0].N, rows[0].ctx
     eps = calc_galerkin_multiline(rows, envs)
+    power = type(alg).__name__ == "VOMPS"       # statmech/vomps.jl:27-87: one application instead of the eigensolve
     for it in range(1, alg.maxiter + 1):
         etol = dyn_tol(eps, it, 1e-12, 1e-5, 1e-5)
         eig = Arnoldi(tol=etol, krylovdim=30, maxiter=100, hermitian=False)
         newAL = [[None] * N for _ in range(R)]
         for col in range(N):
             hac = MultilineOp([MPO_ddAC(ctx, opp[r][col], envs.lw[r][col], envs.rw[r][col], rows[r].AC[col]) for r in range(R)])
-            _, ac = fixedpoint_multiline(hac, RecursiveVec([rows[r].AC[col] for r in range(R)]), "LM", eig); hac.free()
+            xac = RecursiveVec([rows[r].AC[col] for r in range(R)])
+            ac = hac(xac) if power else fixedpoint_multiline(hac, xac, "LM", eig)[1]
+            hac.free()
             hc = MultilineOp([MPO_ddC(ctx, envs.lw[r][(col + 1) % N], envs.rw[r][col], rows[r].CR[col]) for r in range(R)])
-            _, c = fixedpoint_multiline(hc, RecursiveVec([rows[r].CR[col] for r in range(R)]), "LM", eig); hc.free()
+            xc = RecursiveVec([rows[r].CR[col] for r in range(R)])
+            c = hc(xc) if power else fixedpoint_multiline(hc, xc, "LM", eig)[1]
+            hc.free()
             for r in range(R):
                 newAL[r][col] = regauge(ac.vecs[r], c.vecs[r])
         gtol = dyn_tol(eps, it, TOLGAUGE, 1e-5, 1e-8)

@@ -207,6 +207,31 @@ def leading_boundary_multiline(rows, slices, tol=1e-10, maxiter=100, log=None):
     return rows, envs, eps
 
 
+def leading_boundary_multiline_vomps(rows, slices, tol=1e-10, maxiter=100, log=None):
+    """leading_boundary(psi::MPSMultiline, O::MPOMultiline, VOMPS()) (statmech/vomps.jl:27-87): the power method -- one
+    application of the multi-row ddAC / ddC (row r feeds row r + 1, derivatives.jl:107-110) instead of the eigensolve of VUMPS."""
+    envs = MultilineEnv(rows, slices)
+    R, N = len(rows), rows[0].N
+    eps = calc_galerkin_multiline(rows, envs)
+    for it in range(1, maxiter + 1):
+        newAL = [[None] * N for _ in range(R)]
+        for col in range(N):
+            for r in range(R):
+                t = (r - 1) % R
+                ac = dAC_sparse(rows[t].AC[col], slices[t][col], envs.lw[t][col], envs.rw[t][col])
+                c = dC_dense(rows[t].CR[col], envs.lw[t][(col + 1) % N], envs.rw[t][col])
+                newAL[r][col] = regauge(ac, c, rows[r].V[col], rows[r].V[(col + 1) % N], rows[r].pq, rows[r].modulus)
+        gtol = dyn_tol(eps, it, TOLGAUGE, 1e-5, 1e-8)
+        rows = [InfiniteMPS.from_AL(newAL[r], rows[r].CR[N - 1], rows[r].V, rows[r].pq, gtol, 100, rows[r].modulus) for r in range(R)]
+        envs.recalculate(rows, dyn_tol(eps, it, 1e-12, 1e-5, 1e-5))
+        eps = calc_galerkin_multiline(rows, envs)
+        if log is not None:
+            log.append(dict(iter=it, eps=eps, value=expectation_value_multiline(rows, envs)))
+        if eps <= tol:
+            break
+    return rows, envs, eps
+
+
 # ------------------------------------------------------------------------------------------ VOMPS (approximate / power method)
 class MixedPerMPOInfEnv:
     """environments(below, (opp, above)) for one row (permpoinfenv.jl:29-63, mixed_fixpoints 138-189): fixed points of

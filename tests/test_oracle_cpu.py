@@ -1088,3 +1088,19 @@ def test_multiline_approximate_oracle():
         ref, _ = oi.tdvp_step(psi0[r], Ho, dt * (r + 1))
         assert abs(abs(ocb.dot(out[(r + 1) % 2], ref)) - 1.0) < 1e-8
         assert abs(abs(ocb.dot(out[r], ref)) - 1.0) > 1e-3
+
+
+def test_multiline_power_method_oracle():
+    """leading_boundary(psi::MPSMultiline, O::MPOMultiline, VOMPS()) (statmech/vomps.jl:27-87): the power method on two
+    classical-Ising rows reaches the fixed point of the multi-row VUMPS (product of the row values to 1e-9)."""
+    from oracle import infinite as oi, statmech as osm
+    b1, b2 = 0.35, 0.30
+    so = [[ompo.dense_mpo_slice(ompo.classical_ising(b1))], [ompo.dense_mpo_slice(ompo.classical_ising(b2))]]
+    p, V = Space((0,), (2,)), Space((0,), (4,))
+    mk = lambda: [oi.InfiniteMPS.random(np.random.default_rng(3 + r), p, [V]) for r in range(2)]
+    la, lb = [], []
+    osm.leading_boundary_multiline(mk(), so, tol=1e-11, maxiter=80, log=la)
+    _, _, eps = osm.leading_boundary_multiline_vomps(mk(), so, tol=1e-10, maxiter=400, log=lb)
+    assert eps <= 1e-10 and len(lb) > len(la)
+    va, vb = np.prod(la[-1]["value"]), np.prod(lb[-1]["value"])
+    assert abs(va - vb) < 1e-9 * abs(va)

@@ -363,6 +363,25 @@ def test_finite_mps_vector_operations_device(ctx):
         assert abs(small.dot(again) - small.dot(small)) <= 1e-12
 
 
+def test_multiline_power_method_device(ctx):
+    """leading_boundary(psi::MPSMultiline, O::MPOMultiline, VOMPS()) (statmech/vomps.jl:27-87) on the device: the power method
+    on two classical-Ising rows (one application of the verified multi-row operator per column instead of its eigensolve)
+    reaches the value of the device multi-row VUMPS and of the oracle's power method (product of the row values, 1e-9)."""
+    from oracle import infinite as oi, statmech as osm
+    b1, b2 = 0.35, 0.30
+    so = [[ompo.dense_mpo_slice(ompo.classical_ising(b1))], [ompo.dense_mpo_slice(ompo.classical_ising(b2))]]
+    sd = [[m.dense_mpo_slice(m.classical_ising(b1))], [m.dense_mpo_slice(m.classical_ising(b2))]]
+    rows_o = [oi.InfiniteMPS.random(np.random.default_rng(3 + r), OSpace((0,), (2,)), [OSpace((0,), (4,))]) for r in range(2)]
+    mk = lambda: [m.InfiniteMPS.random(np.random.default_rng(3 + r), m.Space((0,), (2,)), [m.Space((0,), (4,))], ctx) for r in range(2)]
+    lo, la, lb = [], [], []
+    osm.leading_boundary_multiline_vomps(rows_o, so, tol=1e-10, maxiter=400, log=lo)
+    m.leading_boundary_multiline(mk(), sd, m.VUMPS(tol=1e-11, maxiter=80), log=la)
+    _, _, eps = m.leading_boundary_multiline(mk(), sd, m.VOMPS(tol=1e-10, maxiter=400), log=lb)
+    va, vb, vo = np.prod(la[-1]["value"]), np.prod(lb[-1]["value"]), np.prod(lo[-1]["value"])
+    print("multi-row power method", va, vb, vo, eps, len(la), len(lb), len(lo))
+    assert eps <= 1e-10 and abs(va - vb) <= 1e-9 * abs(va) and abs(vo - vb) <= 1e-9 * abs(vo)
+
+
 def test_multiline_approximate_device(ctx):
     """approximate(psi::MPSMultiline, (O::MPOMultiline, psi0::MPSMultiline), VOMPS()) (approximate/vomps.jl:19-80) on the device:
     two rows with W^I MPOs of dt and 2 dt on two different states; row r + 1 of the result equals a device TDVP step of psi0[r]
