@@ -153,9 +153,18 @@ def expectation_value(psi, H, envs):
 
 
 def variance(psi, H, envs=None):
-    """variance(state::FiniteMPS, H, envs) (src/algorithms/toolbox.jl:141-145): Re(<H * H> - <H>^2) with H * H the product MPO
+    """variance(state::FiniteMPS, H, envs) (src/algorithms/toolbox.jl:141-145; InfiniteMPS: 136-139): Re(<H * H> - <H>^2) with H * H the product MPO
     (sparsempo.jl:232-264) and its own finite environments; everything but the host-side operator product runs on the device."""
     from .operators import mpo_product
+    if hasattr(psi, "N") and not hasattr(psi, "L"):
+        # variance(state::InfiniteMPS, H, envs) (toolbox.jl:136-139): rescaled_H = H - <H> per site,
+        # Re(sum(<rescaled_H * rescaled_H>)) -- the extensive parts cancel, the variance density remains
+        from . import infinite as di
+        envs = envs if envs is not None else di.environments(psi, H)
+        e = di.expectation_value(psi, H, envs)
+        Hr = H - [complex(x) for x in e]
+        H2 = Hr * Hr
+        return float(np.sum(di.expectation_value(psi, H2, di.environments(psi, H2))).real)
     envs = envs if envs is not None else environments(psi, H)
     H2 = mpo_product(H, H)
     e2 = expectation_value(psi, H2, environments(psi, H2))

@@ -1253,7 +1253,7 @@ UNVERIFIED_CASES = [("test_haldane_gap_device", 300), ("test_time_mpo_wii_approx
                     ("test_reference_printed_su2_numbers_device_vumps", 300), ("test_changebonds_multiline_device", 150),
                     ("test_densempo_times_state_and_svdcut_device", 150), ("test_densempo_products_device", 150),
                     ("test_finite_mps_vector_operations_device", 120), ("test_multiline_approximate_device", 120),
-                    ("test_multiline_power_method_device", 150)]
+                    ("test_multiline_power_method_device", 150), ("test_infinite_variance_device", 150)]
 
 
 @pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: never run on a GPU; XPASS = verified")

@@ -1104,3 +1104,34 @@ def test_multiline_power_method_oracle():
     assert eps <= 1e-10 and len(lb) > len(la)
     va, vb = np.prod(la[-1]["value"]), np.prod(lb[-1]["value"])
     assert abs(va - vb) < 1e-9 * abs(va)
+
+
+def test_infinite_variance_through_operator_arithmetic():
+    """variance(state::InfiniteMPS, H) (toolbox.jl:136-139): rescaled_H = H - <H>, Re(sum(<rescaled_H * rescaled_H>)), built with the
+    package's host-side MPOHamiltonian arithmetic and evaluated by the oracle's MPOHamInfEnv (identity levels in the middle of
+    the product automaton): a sigma_z product state of H = -sum ZZ - g sum X is an eigenstate of the ZZ part, so its variance
+    density is exactly g^2 (one (g X)^2 per site); a VUMPS ground state has a small non-negative one that shrinks with the bond
+    dimension."""
+    import mpskit_b200 as m
+    from oracle import infinite as oi
+
+    def osl(H):
+        return ompo.MPOHamiltonian([ompo.SparseMPOSlice(s.Os, s.domcharges, s.imcharges, s.pcharges) for s in H.slices])
+
+    def variance(st, Hd):
+        Ho = osl(Hd)
+        e = oi.expectation_value(st, Ho, oi.MPOHamInfEnv(st, Ho))
+        Hr = Hd - [complex(x) for x in e]
+        H2 = osl(Hr * Hr)
+        return float(np.sum(oi.expectation_value(st, H2, oi.MPOHamInfEnv(st, H2))).real)
+    Hd = m.transverse_field_ising(1, 0.7)
+    A = np.zeros((1, 2, 1), dtype=complex)
+    A[0, 1, 0] = 1.0                                              # a sigma_z eigenstate
+    up = oi.InfiniteMPS.from_tensors([A], [Space((0,), (1,))], Space((0,), (2,)).index_charges())
+    assert abs(variance(up, Hd) - 0.7 ** 2) < 1e-10
+    vs = []
+    for D in (4, 12):
+        st = oi.InfiniteMPS.random(np.random.default_rng(3), Space((0,), (2,)), [Space((0,), (D,))])
+        st, _, _ = oi.vumps(st, osl(Hd), tol=1e-11, maxiter=200)
+        vs.append(variance(st, Hd))
+    assert -1e-10 < vs[1] < vs[0] < 1e-3

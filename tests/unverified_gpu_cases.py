@@ -404,3 +404,27 @@ def test_multiline_approximate_device(ctx):
         ov = abs(dcb.dot_infinite(out[(r + 1) % 2], ref))
         print("multiline approximate", r, ov, eps)
         assert abs(ov - 1.0) <= 1e-8 and abs(abs(dcb.dot_infinite(out[r], ref)) - 1.0) > 1e-3
+
+
+def test_infinite_variance_device(ctx):
+    """variance(state::InfiniteMPS, H, envs) (toolbox.jl:136-139) on the device: rescaled_H = H - <H> (host-side operator
+    arithmetic), the product automaton rescaled_H * rescaled_H with identity levels in its middle through the device MPOHamInfEnv
+    (GMRES with the regularised transfer operators).  A sigma_z product state of H = -sum ZZ - g sum X has variance density g^2
+    exactly; VUMPS ground states have a small non-negative one that shrinks with the bond dimension; both against the oracle."""
+    from oracle import infinite as oi
+    g = 0.7
+    Hd, Ho = m.transverse_field_ising(1, g), ompo.transverse_field_ising(1, g)
+    from mpskit_b200.tensor import DeviceTensor
+    A = np.zeros((1, 2, 1), dtype=complex)
+    A[0, 1, 0] = 1.0
+    V1, p = m.Space((0,), (1,)), m.Space((0,), (2,))
+    up = m.InfiniteMPS.from_tensors([DeviceTensor.from_dense(ctx, A, V1, [0, 0], V1, np.complex128)], [V1], p, ctx)
+    v_up = m.variance(up, Hd)
+    assert abs(v_up - g ** 2) <= 1e-10
+    vs = []
+    for D in (4, 12):
+        st = m.InfiniteMPS.random(np.random.default_rng(3), p, [m.Space((0,), (D,))], ctx)
+        st, envs, _ = m.find_groundstate_vumps(st, Hd, m.VUMPS(tol=1e-11, maxiter=200))
+        vs.append(m.variance(st, Hd, envs))
+    print("infinite variance", v_up, vs)
+    assert -1e-10 < vs[1] < vs[0] < 1e-3
