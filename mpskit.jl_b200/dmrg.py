@@ -156,6 +156,11 @@ def variance(psi, H, envs=None):
     """variance(state::FiniteMPS, H, envs) (src/algorithms/toolbox.jl:141-145; InfiniteMPS: 136-139): Re(<H * H> - <H>^2) with H * H the product MPO
     (sparsempo.jl:232-264) and its own finite environments; everything but the host-side operator product runs on the device."""
     from .operators import mpo_product
+    if hasattr(H, "ops") and hasattr(H, "sum"):
+        # variance(psi, H::LazySum, envs = environments(psi, sum(H))) (toolbox.jl:176-181)
+        if envs is not None and hasattr(envs, "envs"):
+            raise ValueError("The environment cannot be Lazy i.e. use environments of sum(H)")
+        H = H.sum()
     if hasattr(psi, "N") and not hasattr(psi, "L"):
         # variance(state::InfiniteMPS, H, envs) (toolbox.jl:136-139): rescaled_H = H - <H> per site,
         # Re(sum(<rescaled_H * rescaled_H>)) -- the extensive parts cancel, the variance density remains

@@ -105,6 +105,18 @@ class LazySum:
             raise ValueError("attempting to evaluate time-independent LazySum at time")
         return LazySum([o(t) if isinstance(o, MultipliedOperator) else o for o in self.ops])
 
+    def sum(self):
+        """Base.sum(x::LazySum) = safe_eval(x) (lazysum.jl:48): the sum carried out with the operators' own arithmetic
+        (MPOHamiltonian: mpohamiltonian.jl:97-154); time-dependent terms must be evaluated first, H(t).sum()"""
+        tot = None
+        for o in self.ops:
+            if isinstance(o, MultipliedOperator):
+                if o.istimed:
+                    raise ValueError("attempting to evaluate a time-dependent LazySum without specifying a time")
+                o = o.f * o.op
+            tot = o if tot is None else tot + o
+        return tot
+
     def __add__(self, other):                       # lazysum.jl:50-56
         more = other.ops if isinstance(other, LazySum) else [other]
         return LazySum(self.ops + list(more))

@@ -107,6 +107,8 @@ class MPOHamiltonian:
             return mpo_product(self, b)
         if hasattr(b, "AL"):                                # H * mps::InfiniteMPS = convert(DenseMPO, H) * mps (:164)
             return DenseMPO(self.slices) * b
+        if not isinstance(b, (int, float, complex, np.number)):
+            return NotImplemented                           # e.g. f(t) * H -> MultipliedOperator (lazyops.py)
 
         def scaled(c, sl):
             Os = [row[:] for row in sl.Os]
@@ -123,6 +125,8 @@ class MPOHamiltonian:
         """a + e::Vector adds e[c] * 1 per site to the entry (first, last) (mpohamiltonian.jl:78-90); a + b merges the two
         automata: shared first and last level, b's inner levels appended after a's (mpohamiltonian.jl:97-142)"""
         if not isinstance(other, MPOHamiltonian):
+            if not isinstance(other, (list, tuple, np.ndarray, int, float, complex, np.number)):
+                return NotImplemented                       # H + LazySum / MultipliedOperator: the lazy algebra (lazyops.py)
             e = [complex(x) for x in np.atleast_1d(other)]
             if len(e) != len(self):
                 raise ValueError(f"periodicity should match {len(self)} != {len(e)}")
@@ -158,7 +162,11 @@ class MPOHamiltonian:
         return self + e
 
     def __sub__(self, other):                               # mpohamiltonian.jl:94,143
-        return self + (-other if isinstance(other, MPOHamiltonian) else [-complex(x) for x in np.atleast_1d(other)])
+        if isinstance(other, MPOHamiltonian):
+            return self + (-other)
+        if not isinstance(other, (list, tuple, np.ndarray, int, float, complex, np.number)):
+            return NotImplemented
+        return self + [-complex(x) for x in np.atleast_1d(other)]
 
     def __rsub__(self, e):                                  # mpohamiltonian.jl:92
         return self * (-1.0) + e

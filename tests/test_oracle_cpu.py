@@ -1135,3 +1135,24 @@ def test_infinite_variance_through_operator_arithmetic():
         st, _, _ = oi.vumps(st, osl(Hd), tol=1e-11, maxiter=200)
         vs.append(variance(st, Hd))
     assert -1e-10 < vs[1] < vs[0] < 1e-3
+
+
+def test_lazysum_sum_and_variance_dispatch():
+    """Base.sum(::LazySum) (lazysum.jl:48) with the MPOHamiltonian arithmetic: <sum(LazySum([H1, 2.5 H2]))> = <H1> + 2.5 <H2> on a
+    random InfiniteMPS (oracle expectation values, 1e-10) -- the operator variance(psi, H::LazySum) evaluates (toolbox.jl:176-181);
+    time-dependent sums must be evaluated at a time first."""
+    import pytest
+    import mpskit_b200 as m
+    from oracle import infinite as oi
+
+    def E(st, Hd):
+        Ho = ompo.MPOHamiltonian([ompo.SparseMPOSlice(s.Os, s.domcharges, s.imcharges, s.pcharges) for s in Hd.slices])
+        return oi.expectation_value(st, Ho, oi.MPOHamInfEnv(st, Ho))
+    H1, H2 = m.transverse_field_ising(2, 0.6), m.drop_symmetry(m.heisenberg_u1(2))
+    st = oi.InfiniteMPS.random(np.random.default_rng(6), Space((0,), (2,)), [Space((0,), (5,))] * 2)
+    Hs = m.LazySum([H1, m.UntimedOperator(H2, 2.5)]).sum()
+    assert np.abs(E(st, Hs) - E(st, H1) - 2.5 * E(st, H2)).max() < 1e-10
+    timed = m.LazySum([H1, m.TimedOperator(H2, lambda t: 2.5 * t)])
+    with pytest.raises(ValueError):
+        timed.sum()
+    assert np.abs(E(st, timed(1.0).sum()) - E(st, Hs)).max() < 1e-10
