@@ -106,6 +106,9 @@ class MPOHamiltonian:
         if isinstance(b, MPOHamiltonian):
             return mpo_product(self, b)
         if hasattr(b, "AL"):                                # H * mps::InfiniteMPS = convert(DenseMPO, H) * mps (:164)
+            if hasattr(b, "L"):
+                raise NotImplementedError("mpo * FiniteMPS (densempo.jl:46-71) is not built: "
+                                          "approximate(psi, (H, above), alg) applies an operator to a FiniteMPS")
             return DenseMPO(self.slices) * b
         if not isinstance(b, (int, float, complex, np.number)):
             return NotImplemented                           # e.g. f(t) * H -> MultipliedOperator (lazyops.py)
@@ -423,6 +426,9 @@ class DenseMPO:
             if len(self) != len(other):
                 raise ValueError("dimension mismatch")
             return DenseMPO(mpo_product(self, other).slices)
+        if hasattr(other, "L"):
+            raise NotImplementedError("mpo * FiniteMPS (densempo.jl:46-71) is not built: "
+                                      "approximate(psi, (O, above), alg) applies an operator to a FiniteMPS")
         from .changebonds import mpo_times_infinite
         return mpo_times_infinite(self, other)
 
