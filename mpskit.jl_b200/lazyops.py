@@ -117,6 +117,10 @@ class LazySum:
             tot = o if tot is None else tot + o
         return tot
 
+    def repeat(self, n):
+        """Base.repeat(x::LazySum, n) = LazySum(repeat.(x, n)) (lazysum.jl:59)"""
+        return LazySum([MultipliedOperator(o.op.repeat(n), o.f) if isinstance(o, MultipliedOperator) else o.repeat(n) for o in self.ops])
+
     def __add__(self, other):                       # lazysum.jl:50-56
         more = other.ops if isinstance(other, LazySum) else [other]
         return LazySum(self.ops + list(more))

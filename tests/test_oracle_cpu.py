@@ -1156,3 +1156,5 @@ def test_lazysum_sum_and_variance_dispatch():
     with pytest.raises(ValueError):
         timed.sum()
     assert np.abs(E(st, timed(1.0).sum()) - E(st, Hs)).max() < 1e-10
+    one = m.LazySum([m.transverse_field_ising(1, 0.6), m.UntimedOperator(m.drop_symmetry(m.heisenberg_u1(1)), 2.5)]).repeat(2)
+    assert len(one[0]) == 2 and len(one[1].op) == 2 and np.abs(E(st, one.sum()) - E(st, Hs)).max() < 1e-10     # lazysum.jl:59
