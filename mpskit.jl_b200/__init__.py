@@ -53,3 +53,4 @@ from .quasiparticle import fidelity_susceptibility  # noqa: F401
 from .algorithms import UnionAlg, default_groundstate_algorithm  # noqa: F401
 from .iterlog import IterLog, VERBOSE_NONE, VERBOSE_WARN, VERBOSE_CONV, VERBOSE_ITER, VERBOSE_ALL  # noqa: F401
 from .algorithms import exact_diagonalization  # noqa: F401
+from .finitemps import left_virtualspace, right_virtualspace, physicalspace, max_Ds  # noqa: F401,E402

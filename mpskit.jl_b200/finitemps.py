@@ -375,3 +375,27 @@ class FiniteMPS:
             ctx.lib.mpsk_tensor_free(ctx.h, h)
         from .dmrg import tsvd_spectrum
         return {q: vals for q, (vals, kept) in tsvd_spectrum(ctx).items()}
+
+
+# ---- space accessors (src/states/abstractmps.jl:141-161; 0-based sites) ---------------------------------------------------
+def left_virtualspace(psi, i):
+    """left_virtualspace(psi, i): the bond space to the left of site i (periodic for an InfiniteMPS)"""
+    return psi.V[i % psi.N] if hasattr(psi, "N") and not hasattr(psi, "L") else psi.V[i]
+
+
+def right_virtualspace(psi, i):
+    """right_virtualspace(psi, i): the bond space to the right of site i"""
+    return psi.V[(i + 1) % psi.N] if hasattr(psi, "N") and not hasattr(psi, "L") else psi.V[i + 1]
+
+
+def physicalspace(psi, i=0):
+    """physicalspace(psi, i): one physical space for all sites in this package"""
+    return psi.pspace
+
+
+def max_Ds(psi):
+    """max_Ds(psi::FiniteMPS) (finitemps.jl:297-303): min of the cumulative products of the physical dimensions from the two
+    edge spaces -- the largest dimension each of the L + 1 bonds could carry"""
+    L, d = len(psi), psi.pspace.dim
+    dl, dr = psi.V[0].dim, psi.V[L].dim
+    return [min(dl * d ** k, dr * d ** (L - k)) for k in range(L + 1)]

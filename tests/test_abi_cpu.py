@@ -466,3 +466,23 @@ def test_decompose_localmps_host_part_without_gpu():
         for t in As:
             T2 = t if T2 is None else np.tensordot(T2, t, axes=([T2.ndim - 1], [0]))
         assert np.abs(T2 - T).max() < 1e-13
+
+
+def test_space_accessors_without_gpu():
+    """left_virtualspace / right_virtualspace / physicalspace / max_Ds (abstractmps.jl:141-161, finitemps.jl:297-303; 0-based
+    sites) on stand-ins that carry only the bookkeeping of a FiniteMPS / InfiniteMPS."""
+    import types
+    import mpskit_b200 as m
+    p = m.Space((-1, 1), (1, 1))
+    Vs = m.finitemps.virtual_spaces(p, 6, m.Space((-2, -1, 0, 1, 2), (1, 2, 3, 2, 1)))
+
+    class Fin:
+        V, pspace, L = Vs, p, 6
+
+        def __len__(self):
+            return 6
+    fin = Fin()
+    assert m.left_virtualspace(fin, 2) == Vs[2] and m.right_virtualspace(fin, 2) == Vs[3] and m.physicalspace(fin, 2) is p
+    assert m.max_Ds(fin) == [1, 2, 4, 8, 4, 2, 1] and all(v.dim <= D for v, D in zip(Vs, m.max_Ds(fin)))
+    inf = types.SimpleNamespace(V=[m.Space((0,), (3,)), m.Space((0,), (5,))], N=2, pspace=p)
+    assert m.left_virtualspace(inf, 2).dim == 3 and m.right_virtualspace(inf, 1).dim == 3 and m.right_virtualspace(inf, 0).dim == 5
